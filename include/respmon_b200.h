@@ -1,0 +1,179 @@
+/*
+ * respmon_b200 -- C ABI of the B200-native hot path of kevroy314/respmon.
+ *
+ * The reference has no FFI: its boundary is the Python call graph of base.py / transforms.py / pyramid.py
+ * (SURVEY.md section 8b).  Each entry point below replaces the arithmetic behind one of those calls; the Python
+ * drop-in (respmon_b200/monitor.py, respmon_b200/pyramid.py, respmon_b200/transforms.py) binds them with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns int32: RM_OK (0) or a negative rm_status; rm_last_error(h) has the text.
+ *     Nothing throws, nothing calls exit().
+ *   - data pointers are CALLER-OWNED DEVICE pointers unless a parameter is named host_*.
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ *   - a handle is bound to one device and is not thread-safe; distinct handles are independent.
+ *   - per-clip failures are data, not errors: see rm_clip_status.
+ *   - images are row-major, clips are (T, H, W), batches are (n_clips, T, H, W), all contiguous.
+ */
+#ifndef RESPMON_B200_H
+#define RESPMON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RM_VERSION 100
+
+typedef enum rm_status {
+  RM_OK = 0,
+  RM_ERR_INVALID = -1,     /* bad argument */
+  RM_ERR_CUDA = -2,        /* CUDA runtime error (text in rm_last_error) */
+  RM_ERR_UNSUPPORTED = -3, /* shape / parameter outside what the kernels implement */
+  RM_ERR_WORKSPACE = -4    /* workspace too small */
+} rm_status;
+
+typedef enum rm_dtype { RM_U8 = 0, RM_F32 = 1, RM_F64 = 2 } rm_dtype;
+
+/* per-clip outcome of the batch path; replaces the reference's state flips (base.py:249-253, 451-454, 543-545) */
+typedef enum rm_clip_status {
+  RM_CLIP_OK = 0,
+  RM_CLIP_NO_ROI = 1,      /* locate() returned None (base.py:569-570) */
+  RM_CLIP_NO_CORNERS = 2,  /* goodFeaturesToTrack found nothing (base.py:367-368) */
+  RM_CLIP_TRACK_LOST = 3,  /* extract_motion returned nan (base.py:373-374, 385-386) */
+  RM_CLIP_NO_PEAKS = 4     /* fewer than two accepted peaks: no BPM (base.py:349) */
+} rm_clip_status;
+
+/* Hyper-parameters the reference hard-codes (base.py:80-106; locate defaults base.py:548-552). */
+typedef struct rm_params {
+  int32_t pyramid_levels;      /* 9    base.py:550 */
+  int32_t skip_levels_at_top;  /* 4    base.py:550 */
+  double freq_min;             /* 0.1  base.py:82 */
+  double freq_max;             /* 1.0  base.py:83 */
+  double amplification;        /* 500  base.py:549 */
+  double temporal_threshold;   /* 0.7  base.py:84 */
+  int32_t threshold;           /* 20 = int(round(0.08*255))  base.py:85, 448 */
+  int32_t max_corners;         /* 100  base.py:91 */
+  double quality_level;        /* 0.3  base.py:92 */
+  int32_t min_distance;        /* 7    base.py:93 */
+  int32_t block_size;          /* 7    base.py:94 */
+  int32_t lk_win;              /* 15   base.py:96 */
+  int32_t lk_max_level;        /* 2    base.py:97 */
+  int32_t lk_max_iter;         /* 10   base.py:98 */
+  double lk_eps;               /* 0.03 base.py:98 */
+  double lk_min_eig;           /* 1e-4 (OpenCV default minEigThreshold) */
+  double gaussian_cutoff;      /* 10.0 base.py:100 */
+  int32_t filter_order;        /* 3    base.py:101 */
+  int32_t measure_buffer_len;  /* 128  base.py:88 */
+  int32_t measure_init_len;    /* 12   base.py:106 */
+  double peak_threshold;       /* 0.3  peakutils.indexes default `thres` (base.py:314) */
+} rm_params;
+
+/* 32-byte per-clip result record, the unit of the final all-gather. */
+typedef struct rm_result {
+  double bpm;        /* freq[-1] (base.py:352) or NaN */
+  int32_t x, y, w, h;/* ROI (base.py:456) */
+  int32_t status;    /* rm_clip_status */
+  int32_t n_peaks;   /* len(peak_indices) of the last window (base.py:345) */
+} rm_result;
+
+typedef struct rm_handle rm_handle;
+
+/* ------------------------------------------------------------------ lifetime / host-side helpers (no GPU work) */
+int32_t rm_version(void);
+int32_t rm_default_params(rm_params* out);
+int32_t rm_create(const rm_params* params, int32_t device, rm_handle** out);
+int32_t rm_destroy(rm_handle* h);
+const char* rm_last_error(rm_handle* h);
+/* sizes (w,h) of `n_levels` pyramid levels: the ((n+1)//2) chain of cv2.pyrDown (pyramid.py:13-15). wh_out[2*n_levels]. */
+int32_t rm_level_sizes(int32_t W, int32_t H, int32_t n_levels, int32_t* wh_out);
+/* bound_low / bound_high of transforms.py:88-90 (argmin over scipy.fftpack.fftfreq). */
+int32_t rm_temporal_bounds(int32_t T, double fps, double freq_min, double freq_max, int32_t* lo, int32_t* hi);
+/* scipy.signal.butter(order, wn, 'low') coefficients (transforms.py:58-63); b[order+1], a[order+1]. */
+int32_t rm_butter_lowpass(int32_t order, double wn, double* host_b, double* host_a);
+/* the 256-entry LUT of uint8 -> float -> uint8 (transforms.py:20-29 round trip). */
+int32_t rm_lossy_u8_lut(uint8_t* host_lut256);
+
+/* ------------------------------------------------------------------ test data */
+typedef struct rm_clip_spec {
+  int32_t width, height, n_frames, seed;
+  int32_t x0, y0, w0, h0; /* moving patch rectangle */
+} rm_clip_spec;
+/* Generate n clips on the device; dq8 is (n, T) int32 displacement tables (host-computed, device-resident);
+ * specs is a device array; out is (n, T, H, W) uint8.  All clips share W,H,T.  Bit-identical to respmon_b200/synth.py. */
+int32_t rm_synth_clips(rm_handle* h, const rm_clip_spec* specs, const int32_t* dq8, int32_t n_clips, uint8_t* out,
+                       void* stream);
+
+/* ------------------------------------------------------------------ single-level ops (API parity: pyramid.py) */
+/* uint8_to_float (transforms.py:20-23): u8 -> f64 * (1/255); f32 -> f64 widening. */
+int32_t rm_to_f64(rm_handle* h, const void* src, int32_t dtype, double* dst, int64_t n, void* stream);
+/* cv2.pyrDown on float64 images (pyramid.py:14): (n_img, sh, sw) -> (n_img, (sh+1)/2, (sw+1)/2). */
+int32_t rm_pyr_down_f64(rm_handle* h, const double* src, double* dst, int64_t n_img, int32_t sw, int32_t sh, void* stream);
+/* cv2.pyrUp(src, dstsize=(dw,dh)) on float64 (pyramid.py:25, pyramid.py:55), fused with the caller's add/sub:
+ * mode 0: dst = up(src); mode 1: dst = other - up(src) (Laplacian level); mode 2: dst = up(src) + other (collapse). */
+int32_t rm_pyr_up_f64(rm_handle* h, const double* src, double* dst, const double* other, int32_t mode, int64_t n_img,
+                      int32_t sw, int32_t sh, int32_t dw, int32_t dh, void* stream);
+
+/* ------------------------------------------------------------------ calibrate: fused hot path */
+/* Number of doubles per frame in the packed Laplacian record: sum over levels skip..levels-2 of w_l*h_l
+ * (1600 at 640x480 with levels=9, skip=4), level `skip` first. */
+int32_t rm_lap_record_len(rm_handle* h, int32_t W, int32_t H, int64_t* out);
+/* Workspace (bytes) rm_pyramid_build / rm_heatmap need for a batch of n_frames / (n_clips, T). */
+int32_t rm_pyramid_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int64_t n_frames, size_t* out);
+int32_t rm_heatmap_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n_clips, int32_t T, size_t* out);
+
+/* create_laplacian_video_pyramid restricted to the levels that are ever read (pyramid.py:31-48 via
+ * transforms.py:148,156-170): frames (n_frames,H,W) of dtype -> lap (n_frames, record_len) float64.
+ * u8 frames mean gray/255 (transforms.py:20-23). */
+int32_t rm_pyramid_build(rm_handle* h, const void* frames, int32_t dtype, int64_t n_frames, int32_t W, int32_t H,
+                         double* lap_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* temporal_bandpass_filter_fft (transforms.py:82-102) on every column of (n_clips, T, record_len), in place allowed. */
+int32_t rm_temporal_bandpass(rm_handle* h, const double* lap, double* bp_out, int32_t n_clips, int32_t T,
+                             int64_t record_len, double fps, void* stream);
+
+/* collapse (pyramid.py:51-69) + global min/max clip (transforms.py:184-192) + time average, normalise, truncate
+ * (base.py:562-564): bp (n_clips,T,record_len) -> heat (n_clips,H,W) uint8.
+ * minmax_out (n_clips,4) = raw min, raw max, avg min, avg max (nullable). */
+int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, int32_t T, int32_t W, int32_t H, uint8_t* heat_out,
+                   double* minmax_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* threshold + external contours + largest contourArea + boundingRect (base.py:566-575): heat (n_clips,H,W) ->
+ * roi_out (n_clips,4) int32 x,y,w,h and status_out (n_clips) (RM_CLIP_OK / RM_CLIP_NO_ROI). */
+int32_t rm_roi_select(rm_handle* h, const uint8_t* heat, int32_t n_clips, int32_t W, int32_t H, int32_t* roi_out,
+                      int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
+int32_t rm_roi_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n_clips, size_t* out);
+
+/* ------------------------------------------------------------------ measure */
+int32_t rm_measure_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n_clips, int32_t n_frames, size_t* out);
+/* extract_motion 'flow' over a whole clip (base.py:360-407): for each clip, frames [first_frame, first_frame+n_frames)
+ * of (n_clips,T,H,W) uint8 cropped to roi (n_clips,4): LUT crop (transforms.py:26-29), Shi-Tomasi corners on the first
+ * frame, pyramidal LK frame to frame with lost points dropped, mean displacement, rolling 2-D PCA.
+ * Outputs: data_out (n_clips,n_frames) f64 (the `data` deque, base.py:478), motion_out (n_clips,n_frames,2) f32
+ * (row 0 unused; `motion_data`, base.py:389), npts_out (n_clips) corners found, status_io (n_clips). */
+int32_t rm_measure_flow(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
+                        const int32_t* roi, int32_t first_frame, int32_t n_frames, double* data_out, float* motion_out,
+                        int32_t* npts_out, int32_t* status_io, void* workspace, size_t workspace_bytes, void* stream);
+/* extract_motion 'average' (base.py:355-358): mean of the float crop. */
+int32_t rm_measure_average(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
+                           const int32_t* roi, int32_t first_frame, int32_t n_frames, double* data_out, void* stream);
+/* measure() for every frame of every clip (base.py:340-352, 312-338): rolling window of the last measure_buffer_len
+ * samples of data (n_clips,n_frames): Butterworth filtfilt, peak picking, Gaussian-fit gate, BPM.
+ * bpm_out (n_clips,n_frames) f64 (NaN where the reference appends nothing), filtered_out (n_clips, measure_buffer_len)
+ * and peaks_out (n_clips, measure_buffer_len) int32 (-1 terminated) for the LAST frame's window, npeaks_out (n_clips). */
+int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps, double* bpm_out,
+                      double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, const int32_t* status, void* stream);
+/* assemble the 32-byte records: last finite BPM per clip, ROI, status, n_peaks. */
+int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, const int32_t* status, const int32_t* npeaks,
+                        int32_t n_clips, int32_t n_frames, rm_result* out, void* stream);
+
+/* ------------------------------------------------------------------ bookkeeping */
+/* Number of kernel launches this handle has issued since creation (bench.py reports it as gpu_launches). */
+int64_t rm_launch_count(rm_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESPMON_B200_H */

@@ -1,0 +1,229 @@
+// Temporal band-pass of every pyramid column (transforms.py:82-102).
+//
+// The reference does  p = fftpack.rfft(x)  (packed real layout), zeroes p[hi:T-hi] and -- if lo != 0 -- p[:lo] and
+// p[T-lo:], then takes  real(fftpack.ifft(p))  of that *real packed array* and multiplies by the amplification,
+// i.e.  r[t] = amp/T * sum_j p[j] cos(2 pi j t / T)  (SURVEY.md App. A.4).  Both transforms are computed here as a
+// length-T complex FFT with zero imaginary input: one warp per column, radix-2 decimation-in-time in shared memory
+// for power-of-two T, and an O(T*K) direct evaluation of the kept bins for any other T.
+// Layout: (n_clips, T, P) float64, P = packed record length; 8 adjacent columns per block so that every global
+// access touches whole 32-byte sectors.
+#include "common.cuh"
+
+#define TB_WARPS 8
+
+struct TemporalParams {
+  const double* in;
+  double* out;
+  long long n_clips;
+  long long P;     // columns per clip
+  int T;
+  int logT;        // log2(T) or -1
+  int lo, hi;      // bound_low / bound_high (transforms.py:89-90)
+  double inv_T;    // 1/T
+  double amp;
+};
+
+__device__ __forceinline__ bool bin_kept(int j, int T, int lo, int hi) {
+  // numpy slice semantics of transforms.py:91-94: p[hi:-hi] (empty when hi == 0), p[:lo], p[-lo:]
+  if (hi > 0 && j >= hi && j < T - hi) return false;
+  if (lo != 0 && (j < lo || j >= T - lo)) return false;
+  return true;
+}
+
+__device__ __forceinline__ void warp_fft_pow2(double2* buf, const double2* tw, int T, int logT, int lane) {
+  // in-place radix-2 DIT on bit-reversed input; tw[k] = exp(-2 pi i k / T), k < T/2
+  for (int s = 1; s <= logT; ++s) {
+    const int half = 1 << (s - 1);
+    const int tstep = T >> s;
+    for (int b = lane; b < (T >> 1); b += 32) {
+      int grp = b >> (s - 1), k = b & (half - 1);
+      int i0 = (grp << s) + k, i1 = i0 + half;
+      double2 w = tw[k * tstep];
+      double2 u = buf[i0], v = buf[i1];
+      double2 t = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+      buf[i0] = make_double2(u.x + t.x, u.y + t.y);
+      buf[i1] = make_double2(u.x - t.x, u.y - t.y);
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(TB_WARPS * 32) temporal_pow2_kernel(const TemporalParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = p.T;
+  double2* tw = reinterpret_cast<double2*>(smem_raw);                       // T/2
+  double2* bufs = tw + (T >> 1);                                            // TB_WARPS * T
+  double* qs = reinterpret_cast<double*>(bufs + (size_t)TB_WARPS * T);      // TB_WARPS * T
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < (T >> 1); k += blockDim.x) {
+    double s, c;
+    sincospi(2.0 * (double)k / (double)T, &s, &c);
+    tw[k] = make_double2(c, -s);
+  }
+  const long long groups_per_clip = (p.P + TB_WARPS - 1) / TB_WARPS;
+  const long long n_groups = p.n_clips * groups_per_clip;
+  const int rev_shift = 32 - p.logT;
+  double2* buf = bufs + (size_t)warp * T;
+  double* q = qs + (size_t)warp * T;
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const long long clip = grp / groups_per_clip;
+    const long long c0 = (grp % groups_per_clip) * TB_WARPS;
+    const double* src = p.in + clip * T * p.P;
+    double* dst = p.out + clip * T * p.P;
+    __syncthreads();   // previous group's buffers are free, twiddles are written
+    // stage 8 columns x T samples, bit-reversed along T:   thread -> (t = i / 8, col = i % 8)
+    for (int i = threadIdx.x; i < T * TB_WARPS; i += blockDim.x) {
+      int t = i / TB_WARPS, c = i % TB_WARPS;
+      double v = (c0 + c < p.P) ? src[(long long)t * p.P + c0 + c] : 0.0;
+      int tr = (p.logT == 0) ? 0 : (int)(__brev((unsigned)t) >> rev_shift);
+      bufs[(size_t)c * T + tr] = make_double2(v, 0.0);
+    }
+    __syncthreads();
+    if (c0 + warp < p.P) {
+      warp_fft_pow2(buf, tw, T, p.logT, lane);
+      // packed real spectrum (scipy.fftpack.rfft layout), masked
+      for (int j = lane; j < T; j += 32) {
+        double v;
+        if (j == 0) v = buf[0].x;
+        else if (j == T - 1 && !(T & 1)) v = buf[T >> 1].x;
+        else v = (j & 1) ? buf[(j + 1) >> 1].x : buf[j >> 1].y;
+        q[j] = bin_kept(j, T, p.lo, p.hi) ? v : 0.0;
+      }
+      __syncwarp();
+      for (int j = lane; j < T; j += 32) {
+        int jr = (p.logT == 0) ? 0 : (int)(__brev((unsigned)j) >> rev_shift);
+        buf[jr] = make_double2(q[j], 0.0);
+      }
+      __syncwarp();
+      warp_fft_pow2(buf, tw, T, p.logT, lane);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * TB_WARPS; i += blockDim.x) {
+      int t = i / TB_WARPS, c = i % TB_WARPS;
+      if (c0 + c < p.P) dst[(long long)t * p.P + c0 + c] = bufs[(size_t)c * T + t].x * p.inv_T * p.amp;
+    }
+  }
+}
+
+// Any T: direct evaluation.  p[j] only for kept j, then r[t] = amp/T * sum_j p[j] cos(2 pi j t / T).
+__global__ void __launch_bounds__(TB_WARPS * 32) temporal_direct_kernel(const TemporalParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = p.T;
+  double* ct = reinterpret_cast<double*>(smem_raw);   // cos(2 pi m / T)
+  double* st = ct + T;                                 // sin(2 pi m / T)
+  double* xs = st + T;                                 // TB_WARPS * T
+  double* qs = xs + (size_t)TB_WARPS * T;              // TB_WARPS * T
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int m = threadIdx.x; m < T; m += blockDim.x) sincospi(2.0 * (double)m / (double)T, &st[m], &ct[m]);
+  const long long groups_per_clip = (p.P + TB_WARPS - 1) / TB_WARPS;
+  const long long n_groups = p.n_clips * groups_per_clip;
+  double* x = xs + (size_t)warp * T;
+  double* q = qs + (size_t)warp * T;
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const long long clip = grp / groups_per_clip;
+    const long long c0 = (grp % groups_per_clip) * TB_WARPS;
+    const double* src = p.in + clip * T * p.P;
+    double* dst = p.out + clip * T * p.P;
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * TB_WARPS; i += blockDim.x) {
+      int t = i / TB_WARPS, c = i % TB_WARPS;
+      xs[(size_t)c * T + t] = (c0 + c < p.P) ? src[(long long)t * p.P + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    if (c0 + warp < p.P) {
+      for (int j = lane; j < T; j += 32) {
+        double acc = 0.0;
+        if (bin_kept(j, T, p.lo, p.hi)) {
+          // packed index j -> harmonic k and real/imag part
+          int k = (j + 1) >> 1;
+          bool imag = (j != 0) && !(j & 1);   // even j > 0 holds Im X_k; for even T, j = T-1 is odd -> Re X_{T/2}
+          int m = 0;
+          for (int t = 0; t < T; ++t) {
+            acc += imag ? -x[t] * st[m] : x[t] * ct[m];
+            m += k;
+            if (m >= T) m -= T;
+          }
+        }
+        q[j] = acc;
+      }
+      __syncwarp();
+      for (int t = lane; t < T; t += 32) {
+        double acc = 0.0;
+        int m = 0;
+        for (int j = 0; j < T; ++j) {
+          acc += q[j] * ct[m];
+          m += t;
+          if (m >= T) m -= T;
+        }
+        x[t] = acc * p.inv_T * p.amp;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * TB_WARPS; i += blockDim.x) {
+      int t = i / TB_WARPS, c = i % TB_WARPS;
+      if (c0 + c < p.P) dst[(long long)t * p.P + c0 + c] = xs[(size_t)c * T + t];
+    }
+  }
+}
+
+// fftfreq-based bounds, restating transforms.py:88-90 / scipy.fftpack.fftfreq: f[j] = k_j * (1 / (T * d)), d = 1/fps.
+extern "C" int32_t rm_temporal_bounds(int32_t T, double fps, double freq_min, double freq_max, int32_t* lo, int32_t* hi) {
+  if (T < 1 || !(fps > 0) || !lo || !hi) return RM_ERR_INVALID;
+  const double d = 1.0 / fps;
+  const double val = 1.0 / ((double)T * d);
+  const int npos = (T - 1) / 2 + 1;
+  int best_lo = 0, best_hi = 0;
+  double dlo = 0, dhi = 0;
+  for (int j = 0; j < T; ++j) {
+    int k = (j < npos) ? j : j - T;
+    double f = (double)k * val;
+    double a = fabs(f - freq_min), b = fabs(f - freq_max);
+    if (j == 0 || a < dlo) { dlo = a; best_lo = j; }
+    if (j == 0 || b < dhi) { dhi = b; best_hi = j; }
+  }
+  *lo = best_lo;
+  *hi = best_hi;
+  return RM_OK;
+}
+
+extern "C" int32_t rm_temporal_bandpass(rm_handle* h, const double* lap, double* bp_out, int32_t n_clips, int32_t T,
+                                        int64_t record_len, double fps, void* stream) {
+  RM_CHECK_ARG(h, h && lap && bp_out && n_clips >= 0 && T >= 1 && record_len >= 1 && fps > 0, "null pointer or bad size");
+  if (n_clips == 0) return RM_OK;
+  DeviceGuard dg(h->device);
+  TemporalParams p;
+  p.in = lap;
+  p.out = bp_out;
+  p.n_clips = n_clips;
+  p.P = record_len;
+  p.T = T;
+  p.logT = -1;
+  for (int b = 0; b < 31; ++b)
+    if ((1 << b) == T) p.logT = b;
+  rm_temporal_bounds(T, fps, h->p.freq_min, h->p.freq_max, &p.lo, &p.hi);
+  p.inv_T = 1.0 / (double)T;
+  p.amp = h->p.amplification;
+  const long long n_groups = (long long)n_clips * ((record_len + TB_WARPS - 1) / TB_WARPS);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.logT >= 0 && T <= 2048) {
+    size_t smem = (size_t)(T >> 1) * 16 + (size_t)TB_WARPS * T * 16 + (size_t)TB_WARPS * T * 8;
+    if ((int)smem > h->smem_optin) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: T too large for shared memory", __func__);
+    RM_CUDA(h, cudaFuncSetAttribute(temporal_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, temporal_pow2_kernel, TB_WARPS * 32, smem));
+    long long grid = (long long)h->sm_count * (occ < 1 ? 1 : occ);
+    if (grid > n_groups) grid = n_groups;
+    temporal_pow2_kernel<<<(unsigned)grid, TB_WARPS * 32, smem, st>>>(p);
+  } else {
+    size_t smem = (size_t)2 * T * 8 + (size_t)2 * TB_WARPS * T * 8;
+    if ((int)smem > h->smem_optin) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: T too large for shared memory", __func__);
+    RM_CUDA(h, cudaFuncSetAttribute(temporal_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, temporal_direct_kernel, TB_WARPS * 32, smem));
+    long long grid = (long long)h->sm_count * (occ < 1 ? 1 : occ);
+    if (grid > n_groups) grid = n_groups;
+    temporal_direct_kernel<<<(unsigned)grid, TB_WARPS * 32, smem, st>>>(p);
+  }
+  RM_LAUNCH_CHECK(h);
+  return RM_OK;
+}

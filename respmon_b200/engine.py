@@ -1,0 +1,187 @@
+"""Host-side driver of the CUDA hot path: owns an rm_handle, allocates device buffers as torch tensors
+(torch is used ONLY as the device-memory / stream container) and calls the C ABI with raw pointers.
+
+Stage map (reference -> C ABI):
+  pyramid.py:31-48 + transforms.py:148            -> rm_pyramid_build      (levels skip..levels-2 only)
+  transforms.py:82-102 (per level, 156-170)      -> rm_temporal_bandpass
+  pyramid.py:51-69 + transforms.py:184-192 + base.py:562-564 -> rm_heatmap
+  base.py:566-575                                -> rm_roi_select
+  base.py:354-407                                -> rm_measure_flow / rm_measure_average
+  base.py:340-352, 312-338                       -> rm_signal_bpm
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import RM_F32, RM_F64, RM_U8, RmParams, check
+
+_DTYPES = {torch.uint8: RM_U8, torch.float32: RM_F32, torch.float64: RM_F64}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    """One handle = one GPU.  Not thread-safe (same contract as the C ABI)."""
+
+    def __init__(self, device: int | None = None, **overrides):
+        if not torch.cuda.is_available():
+            raise RuntimeError("respmon_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _cabi.lib()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.params = RmParams()
+        self.lib.rm_default_params(C.byref(self.params))
+        for k, v in overrides.items():
+            if not hasattr(self.params, k):
+                raise TypeError("unknown hyper-parameter %r" % k)
+            setattr(self.params, k, v)
+        self._h = C.c_void_p()
+        rc = self.lib.rm_create(C.byref(self.params), self.device_index, C.byref(self._h))
+        if rc != 0:
+            raise _cabi.RmError("rm_create failed (rc=%d): needs an sm_100 device" % rc)
+        self._ws = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.rm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, key, nbytes):
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def _call(self, name, *args):
+        check(self._h, getattr(self.lib, name)(self._h, *args), name)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rm_launch_count(self._h))
+
+    def level_sizes(self, W, H, n_levels=None):
+        n = n_levels or self.params.pyramid_levels
+        buf = (C.c_int32 * (2 * n))()
+        rc = self.lib.rm_level_sizes(W, H, n, buf)
+        if rc != 0:
+            raise _cabi.RmError("rm_level_sizes failed")
+        return [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
+
+    def record_len(self, W, H) -> int:
+        out = C.c_int64()
+        self._call("rm_lap_record_len", W, H, C.byref(out))
+        return out.value
+
+    def record_levels(self, W, H):
+        """[(level, w, h, offset)] of the packed Laplacian record."""
+        sizes = self.level_sizes(W, H)
+        out, off = [], 0
+        for l in range(self.params.skip_levels_at_top, self.params.pyramid_levels - 1):
+            w, h = sizes[l]
+            out.append((l, w, h, off))
+            off += w * h
+        return out
+
+    # ------------------------------------------------------------------ single-level ops
+    def to_f64(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.contiguous()
+        out = torch.empty(x.shape, dtype=torch.float64, device=self.device)
+        self._call("rm_to_f64", _ptr(x), _DTYPES[x.dtype], _ptr(out), x.numel(), self._stream())
+        return out
+
+    def pyr_down(self, x: torch.Tensor) -> torch.Tensor:
+        """(..., h, w) float64 -> (..., (h+1)//2, (w+1)//2)   [cv2.pyrDown, pyramid.py:14]"""
+        x = x.contiguous()
+        h, w = x.shape[-2:]
+        n = x.numel() // (h * w)
+        out = torch.empty(x.shape[:-2] + ((h + 1) // 2, (w + 1) // 2), dtype=torch.float64, device=self.device)
+        self._call("rm_pyr_down_f64", _ptr(x), _ptr(out), n, w, h, self._stream())
+        return out
+
+    def pyr_up(self, x: torch.Tensor, dst_w: int, dst_h: int, other: torch.Tensor | None = None, mode: int = 0):
+        """cv2.pyrUp(x, dstsize=(dst_w, dst_h)); mode 1: other - up, mode 2: up + other   [pyramid.py:25, 55]"""
+        x = x.contiguous()
+        h, w = x.shape[-2:]
+        n = x.numel() // (h * w)
+        out = torch.empty(x.shape[:-2] + (dst_h, dst_w), dtype=torch.float64, device=self.device)
+        if other is not None:
+            other = other.contiguous()
+            assert other.shape == out.shape
+        self._call("rm_pyr_up_f64", _ptr(x), _ptr(out), _ptr(other), mode, n, w, h, dst_w, dst_h, self._stream())
+        return out
+
+    # ------------------------------------------------------------------ calibrate
+    def pyramid_build(self, frames: torch.Tensor) -> torch.Tensor:
+        """frames (..., H, W) u8/f32/f64 on the device -> packed Laplacian records (..., record_len) float64."""
+        assert frames.is_cuda and frames.is_contiguous() and frames.dtype in _DTYPES
+        H, W = frames.shape[-2:]
+        n = frames.numel() // (H * W)
+        rec = self.record_len(W, H)
+        out = torch.empty(frames.shape[:-2] + (rec,), dtype=torch.float64, device=self.device)
+        need = C.c_size_t()
+        self._call("rm_pyramid_workspace_bytes", W, H, n, C.byref(need))
+        ws = self._workspace("pyr", need.value)
+        self._call("rm_pyramid_build", _ptr(frames), _DTYPES[frames.dtype], n, W, H, _ptr(out), _ptr(ws), ws.numel(),
+                   self._stream())
+        return out
+
+    def temporal_bandpass(self, lap: torch.Tensor, fps: float, out: torch.Tensor | None = None) -> torch.Tensor:
+        """lap (n_clips, T, P) float64 -> band-passed, amplified (in place if out is lap)."""
+        assert lap.is_cuda and lap.is_contiguous() and lap.dtype == torch.float64 and lap.dim() == 3
+        n, T, P = lap.shape
+        if out is None:
+            out = torch.empty_like(lap)
+        self._call("rm_temporal_bandpass", _ptr(lap), _ptr(out), n, T, P, float(fps), self._stream())
+        return out
+
+    def heatmap(self, bp: torch.Tensor, W: int, H: int):
+        """bp (n_clips, T, P) -> (heat (n_clips,H,W) uint8, minmax (n_clips,4) f64: raw min/max, avg min/max)."""
+        assert bp.is_cuda and bp.is_contiguous() and bp.dtype == torch.float64 and bp.dim() == 3
+        n, T, P = bp.shape
+        assert P == self.record_len(W, H)
+        heat = torch.empty((n, H, W), dtype=torch.uint8, device=self.device)
+        minmax = torch.empty((n, 4), dtype=torch.float64, device=self.device)
+        need = C.c_size_t()
+        self._call("rm_heatmap_workspace_bytes", W, H, n, T, C.byref(need))
+        ws = self._workspace("heat", need.value)
+        self._call("rm_heatmap", _ptr(bp), n, T, W, H, _ptr(heat), _ptr(minmax), _ptr(ws), ws.numel(), self._stream())
+        return heat, minmax
+
+    def calibrate_heatmaps(self, clips: torch.Tensor, fps: float):
+        """clips (n_clips, T, H, W) -> heat maps; the three calibration kernels back to back."""
+        n, T, H, W = clips.shape
+        lap = self.pyramid_build(clips)
+        self.temporal_bandpass(lap, fps, out=lap)
+        return self.heatmap(lap, W, H)
+
+    # ------------------------------------------------------------------ synthetic data
+    def synth_clips(self, specs, dq8: np.ndarray) -> torch.Tensor:
+        """Generate clips on the device (bit-identical to synth.make_clip).  specs: list of synth.ClipSpec."""
+        n = len(specs)
+        W, H, T = specs[0].width, specs[0].height, specs[0].n_frames
+        arr = (_cabi.RmClipSpec * n)()
+        for i, s in enumerate(specs):
+            assert (s.width, s.height, s.n_frames) == (W, H, T)
+            arr[i] = _cabi.RmClipSpec(s.width, s.height, s.n_frames, s.seed, s.x0, s.y0, s.w0, s.h0)
+        d_specs = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+        d_dq8 = torch.from_numpy(np.ascontiguousarray(dq8, dtype=np.int32)).to(self.device)
+        out = torch.empty((n, T, H, W), dtype=torch.uint8, device=self.device)
+        self._call("rm_synth_clips", _ptr(d_specs), _ptr(d_dq8), n, _ptr(out), self._stream())
+        return out

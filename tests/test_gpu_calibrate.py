@@ -1,0 +1,143 @@
+"""GPU parity: calibration kernels through the C ABI against the oracle (oracle/cpu_path.py, oracle/np_kernels.py)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import clip_from_fixture  # noqa: E402
+from oracle import cpu_path as P  # noqa: E402
+from oracle import np_kernels as K  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from respmon_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+SIZES = [(64, 48), (37, 23), (15, 8), (9, 5), (5, 4), (3, 2), (2, 1), (1, 1), (640, 480), (45, 23)]
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+def test_pyr_down_up_single_level(eng, w, h):
+    rng = np.random.default_rng(w * 131 + h)
+    src = rng.random((3, h, w))
+    out = eng.pyr_down(dev(src)).cpu().numpy()
+    for i in range(3):
+        assert np.abs(out[i] - K.pyr_down(src[i])).max() <= 1e-15
+    for dw, dh in {(2 * w, 2 * h), (2 * w - (w > 1), 2 * h - (h > 1))}:
+        other = rng.random((3, dh, dw))
+        for mode in (0, 1, 2):
+            got = eng.pyr_up(dev(src), dw, dh, dev(other) if mode else None, mode).cpu().numpy()
+            for i in range(3):
+                up = K.pyr_up(src[i], dw, dh)
+                want = up if mode == 0 else (other[i] - up if mode == 1 else up + other[i])
+                assert np.abs(got[i] - want).max() <= 1e-15
+
+
+@pytest.mark.parametrize("w,h,dtype", [(640, 480, "u8"), (640, 480, "f32"), (320, 240, "u8"), (250, 187, "u8"),
+                                       (250, 187, "f64"), (1280, 720, "u8"), (1920, 1080, "u8"), (97, 33, "f32"),
+                                       (33, 97, "u8"), (640, 480, "f64")])
+def test_pyramid_build_matches_oracle(eng, w, h, dtype):
+    rng = np.random.default_rng(w + h)
+    n = 5 if w * h < 700000 else 3
+    u8 = rng.integers(0, 256, (n, h, w)).astype(np.uint8)
+    if dtype == "u8":
+        frames, ref_in = u8, P.u8_to_unit(u8)
+    elif dtype == "f32":
+        frames = (u8 * (1.0 / 255)).astype(np.float32) + rng.random((n, h, w)).astype(np.float32) * np.float32(1e-3)
+        ref_in = frames.astype(np.float64)
+    else:
+        frames = rng.random((n, h, w))
+        ref_in = frames
+    rec = eng.pyramid_build(dev(frames)).cpu().numpy()
+    levels = eng.record_levels(w, h)
+    assert rec.shape == (n, levels[-1][3] + levels[-1][1] * levels[-1][2])
+    for i in range(n):
+        lap = P.laplacian_levels(ref_in[i], 9)
+        for (l, lw, lh, off) in levels:
+            got = rec[i, off:off + lw * lh].reshape(lh, lw)
+            assert got.shape == lap[l].shape
+            assert np.abs(got - lap[l]).max() <= 2e-14, (l, np.abs(got - lap[l]).max())
+
+
+def test_pyramid_build_golden_taps(eng, golden):
+    for name in ("vga_s0", "odd_s3"):
+        fix = golden(name)
+        spec, clip = clip_from_fixture(fix)
+        rec = eng.pyramid_build(dev(clip[1:129])).cpu().numpy()
+        for (l, lw, lh, off) in eng.record_levels(spec.width, spec.height):
+            got = rec[fix["tap_frames"], off:off + lw * lh].reshape(-1, lh, lw)
+            assert np.abs(got - fix["lap_%d" % l]).max() <= 2e-14
+
+
+@pytest.mark.parametrize("T,fps", [(128, 10.0), (256, 10.0), (128, 30.0), (64, 10.0), (100, 10.0), (77, 7.68), (16, 10.0)])
+def test_temporal_bandpass_matches_oracle(eng, T, fps):
+    rng = np.random.default_rng(T)
+    P_cols = 123
+    x = rng.standard_normal((3, T, P_cols))
+    x[0, :, 5] = 0.25            # a static column must come out as exact zeros when the DC bin is dropped
+    got = eng.temporal_bandpass(dev(x), fps).cpu().numpy()
+    for i in range(3):
+        want = P.temporal_filter(x[i], fps, 0.1, 1.0, 500)
+        assert np.abs(got[i] - want).max() <= 1e-9 * max(1.0, np.abs(want).max())
+    lo, _ = P.temporal_bounds(T, fps, 0.1, 1.0)
+    if lo != 0 and (T & (T - 1)) == 0:
+        assert np.all(got[0, :, 5] == 0.0)
+    # in place
+    xd = dev(x)
+    eng.temporal_bandpass(xd, fps, out=xd)
+    assert np.array_equal(xd.cpu().numpy(), got)
+
+
+@pytest.mark.parametrize("name", ["vga_s0", "vga_s2", "qvga_s1", "odd_s3"])
+def test_calibration_heatmap_and_roi_match_golden(eng, golden, name):
+    fix = golden(name)
+    spec, clip = clip_from_fixture(fix)
+    clips = dev(clip[None, 1:129])
+    lap = eng.pyramid_build(clips)
+    bp = eng.temporal_bandpass(lap, spec.fps)
+    tf = fix["tap_frames"]
+    for (l, lw, lh, off) in eng.record_levels(spec.width, spec.height):
+        got = bp[0, :, off:off + lw * lh].cpu().numpy()[tf].reshape(-1, lh, lw)
+        assert np.abs(got - fix["bp_%d" % l]).max() <= 1e-9
+    heat, minmax = eng.heatmap(bp, spec.width, spec.height)
+    heat = heat.cpu().numpy()[0]
+    minmax = minmax.cpu().numpy()[0]
+    assert abs(minmax[0] - fix["raw_min"]) <= 1e-9 and abs(minmax[1] - fix["raw_max"]) <= 1e-9
+    assert abs(minmax[2] - fix["avg_min"]) <= 1e-9 and abs(minmax[3] - fix["avg_max"]) <= 1e-9
+    diff = heat.astype(int) - fix["heat_u8"].astype(int)
+    assert np.abs(diff).max() <= 1 and np.count_nonzero(diff) <= 8, (np.abs(diff).max(), np.count_nonzero(diff))
+    assert np.array_equal(heat > P.THRESHOLD, fix["heat_u8"] > P.THRESHOLD)
+    assert P.select_roi(heat) == tuple(int(v) for v in fix["roi"])
+
+
+def test_calibration_batch_of_clips_matches_oracle(eng):
+    """Several clips at once (T=256, locate() on the whole clip as in BASELINE config 2) against the CPU oracle."""
+    from respmon_b200 import synth
+    specs = [synth.clip_spec(s, 320, 240, 256) for s in (11, 12, 13)]
+    clips = np.stack([synth.make_clip(s) for s in specs])
+    heat, _ = eng.calibrate_heatmaps(dev(clips), 10.0)
+    heat = heat.cpu().numpy()
+    for i in range(len(specs)):
+        taps = {}
+        roi = P.locate(P.u8_to_unit(clips[i]), 10.0, taps=taps)
+        diff = heat[i].astype(int) - taps["heat_u8"].astype(int)
+        assert np.abs(diff).max() <= 1 and np.count_nonzero(diff) <= 8
+        assert P.select_roi(heat[i]) == roi
+
+
+def test_device_synth_is_bit_identical(eng):
+    from respmon_b200 import synth
+    specs = [synth.clip_spec(s, 160, 120, 40) for s in (0, 5, 9)]
+    dq8 = np.stack([synth.displacement_q8(s) for s in specs])
+    got = eng.synth_clips(specs, dq8).cpu().numpy()
+    for i, s in enumerate(specs):
+        assert np.array_equal(got[i], synth.make_clip(s))
