@@ -140,22 +140,32 @@ int32_t rm_temporal_bandpass(rm_handle* h, const double* lap, double* bp_out, in
 int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, int32_t T, int32_t W, int32_t H, uint8_t* heat_out,
                    double* minmax_out, void* workspace, size_t workspace_bytes, void* stream);
 
-/* threshold + external contours + largest contourArea + boundingRect (base.py:566-575): heat (n_clips,H,W) ->
- * roi_out (n_clips,4) int32 x,y,w,h and status_out (n_clips) (RM_CLIP_OK / RM_CLIP_NO_ROI). */
-int32_t rm_roi_select(rm_handle* h, const uint8_t* heat, int32_t n_clips, int32_t W, int32_t H, int32_t* roi_out,
-                      int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
-int32_t rm_roi_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n_clips, size_t* out);
+/* Stand-alone tail of eulerian_magnification_bandpass on a materialised volume (transforms.py:184-192) plus the time
+ * average of base.py:562: raw (T,hw) -> clipped_out (T,hw; nullable), avg_out (hw; nullable; mean of the clipped volume,
+ * or of raw when clipped_out is null), minmax_out (2; nullable).  workspace: 64 bytes. */
+int32_t rm_volume_clip_mean(rm_handle* h, const double* raw, double* clipped_out, double* avg_out, double* minmax_out,
+                            int32_t T, int64_t hw, double threshold, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------ measure */
-int32_t rm_measure_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n_clips, int32_t n_frames, size_t* out);
+/* Workspace for rm_measure_flow when every ROI is at most max_roi_w x max_roi_h. */
+int32_t rm_measure_workspace_bytes(rm_handle* h, int32_t max_roi_w, int32_t max_roi_h, int32_t n_clips, int32_t n_frames,
+                                   size_t* out);
 /* extract_motion 'flow' over a whole clip (base.py:360-407): for each clip, frames [first_frame, first_frame+n_frames)
  * of (n_clips,T,H,W) uint8 cropped to roi (n_clips,4): LUT crop (transforms.py:26-29), Shi-Tomasi corners on the first
  * frame, pyramidal LK frame to frame with lost points dropped, mean displacement, rolling 2-D PCA.
  * Outputs: data_out (n_clips,n_frames) f64 (the `data` deque, base.py:478), motion_out (n_clips,n_frames,2) f32
- * (row 0 unused; `motion_data`, base.py:389), npts_out (n_clips) corners found, status_io (n_clips). */
+ * (row 0 unused; `motion_data`, base.py:389), npts_out (n_clips) corners found, status_io (n_clips; in: RM_CLIP_OK for
+ * clips to process, anything else skips the clip; out: NO_CORNERS / TRACK_LOST where they happen). */
 int32_t rm_measure_flow(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
-                        const int32_t* roi, int32_t first_frame, int32_t n_frames, double* data_out, float* motion_out,
-                        int32_t* npts_out, int32_t* status_io, void* workspace, size_t workspace_bytes, void* stream);
+                        const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t first_frame, int32_t n_frames,
+                        double* data_out, float* motion_out, int32_t* npts_out, int32_t* status_io, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* Diagnostic variant: additionally writes the tracked points after every frame, pts_out (n_clips,n_frames,128,2) f32,
+ * NaN padded (the reference's `motion_key_points`, base.py:382). */
+int32_t rm_measure_flow_debug(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
+                              const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t first_frame,
+                              int32_t n_frames, double* data_out, float* motion_out, int32_t* npts_out,
+                              int32_t* status_io, float* pts_out, void* workspace, size_t workspace_bytes, void* stream);
 /* extract_motion 'average' (base.py:355-358): mean of the float crop. */
 int32_t rm_measure_average(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
                            const int32_t* roi, int32_t first_frame, int32_t n_frames, double* data_out, void* stream);

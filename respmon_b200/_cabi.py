@@ -68,13 +68,13 @@ SIGNATURES = {
     "rm_temporal_bandpass": (_i32, [_H, _P, _P, _i32, _i32, _i64, _f64, _S]),
     "rm_heatmap": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _P, _P, _sz, _S]),
     "rm_volume_clip_mean": (_i32, [_H, _P, _P, _P, _P, _i32, _i64, _f64, _P, _S]),
-    # PENDING "rm_roi_workspace_bytes": (_i32, [_H, _i32, _i32, _i32, C.POINTER(_sz)]),
-    # PENDING "rm_roi_select": (_i32, [_H, _P, _i32, _i32, _i32, _P, _P, _P, _sz, _S]),
-    # PENDING "rm_measure_workspace_bytes": (_i32, [_H, _i32, _i32, _i32, _i32, C.POINTER(_sz)]),
-    # PENDING "rm_measure_flow": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _P, _P, _P, _P, _P, _sz, _S]),
-    # PENDING "rm_measure_average": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _P, _S]),
-    # PENDING "rm_signal_bpm": (_i32, [_H, _P, _i32, _i32, _f64, _P, _P, _P, _P, _P, _S]),
-    # PENDING "rm_pack_results": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _P, _S]),
+    "rm_measure_workspace_bytes": (_i32, [_H, _i32, _i32, _i32, _i32, C.POINTER(_sz)]),
+    "rm_measure_flow": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _i32, _i32, _P, _P, _P, _P, _P, _sz, _S]),
+    "rm_measure_flow_debug": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _i32, _i32, _P, _P, _P, _P, _P, _P, _sz,
+                                     _S]),
+    "rm_measure_average": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _P, _S]),
+    "rm_signal_bpm": (_i32, [_H, _P, _i32, _i32, _f64, _P, _P, _P, _P, _P, _S]),
+    "rm_pack_results": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _P, _S]),
     "rm_launch_count": (_i64, [_H]),
 }
 

@@ -14,7 +14,7 @@ OBJ_DIR = os.path.join(PKG, "csrc", "_obj")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
 # files whose double-precision scalar code mirrors SciPy/MINPACK operation by operation: no FMA contraction
-NO_FMAD = {"signal.cu"}
+NO_FMAD = {"signal.cu", "measure.cu"}
 
 
 def _nvcc():

@@ -117,9 +117,6 @@ extern "C" int32_t rm_create(const rm_params* params, int32_t device, rm_handle*
     free(h);
     return RM_ERR_CUDA;
   }
-  if (h->p.filter_order >= 1 && h->p.filter_order <= 7) {
-    // the cutoff depends on fps; coefficients are (re)computed per call in rm_signal_bpm
-  }
   h->err[0] = 0;
   *out = h;
   return RM_OK;
@@ -130,6 +127,7 @@ extern "C" int32_t rm_destroy(rm_handle* h) {
   {
     DeviceGuard dg(h->device);
     if (h->d_lut) cudaFree(h->d_lut);
+    if (h->d_tvals) cudaFree(h->d_tvals);
   }
   free(h);
   return RM_OK;

@@ -18,7 +18,8 @@ struct rm_handle {
   char err[512];
   uint8_t lut[256];     // lossy u8 round trip (transforms.py:20-29)
   uint8_t* d_lut;       // device copy
-  double butter_b[8], butter_a[8];
+  double* d_tvals;      // running time axis of the measure buffers (base.py:481-484), grown on demand
+  int tvals_cap;
 };
 
 // ---- error plumbing --------------------------------------------------------------------------------------------

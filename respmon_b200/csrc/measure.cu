@@ -1,0 +1,667 @@
+// Motion measurement over a whole clip: extract_motion(), 'flow' and 'average' branches (base.py:354-407).
+//
+//   float_to_uint8(crop)              transforms.py:26-29 after uint8_to_float -> a 256-entry LUT on the uint8 frame
+//   cv2.goodFeaturesToTrack           base.py:365-366  -> gftt_cov / gftt_eig / gftt_select kernels
+//   cv2.calcOpticalFlowPyrLK          base.py:371-372  -> lk_pyr_kernel (uint8 pyramids of every measure frame, in
+//                                                         parallel) + lk_track_kernel (one block per clip walks the
+//                                                         frames in order, one warp per corner)
+//   mean(old - new), PCA projection   base.py:388-405  -> lk_track_kernel epilogue + motion_pca_kernel
+//
+// Third-party semantics follow SURVEY.md App. A.5 / A.6 and oracle/np_kernels.py (validated against cv2 there).
+// The per-frame working set is a few KB per clip: these kernels are latency bound; throughput comes from the batch.
+// Compile with -fmad=false: float expressions mirror OpenCV's non-fused arithmetic.
+#include "common.cuh"
+#include "signal_core.h"
+
+#define LK_MAX_PTS 128
+#define LK_WARPS 8
+#define LK_MAX_LEVELS 4
+
+__device__ __forceinline__ int reflect101_multi(int p, int n) {   // cv::borderInterpolate(BORDER_REFLECT_101)
+  if (n == 1) return 0;
+  while ((unsigned)p >= (unsigned)n) p = (p < 0) ? -p : 2 * n - 2 - p;
+  return p;
+}
+__device__ __forceinline__ unsigned f32_key(float v) {
+  unsigned b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct MeasureParams {
+  const uint8_t* frames;   // (n_clips, T, H, W)
+  const int32_t* roi;      // (n_clips, 4) x,y,w,h
+  const uint8_t* lut;
+  int n_clips, T, W, H, first_frame, n_frames;
+  int maxw, maxh;          // workspace was sized for ROIs up to maxw x maxh
+  // hyper-parameters
+  int max_corners, min_distance, block_size;
+  float quality;
+  int win, max_level, max_iter;
+  double eps2;             // lk_eps^2 (double, as cv::TermCriteria keeps it)
+  float min_eig;
+  int buf_len;             // measure_buffer_len
+  // workspace
+  float* cov;              // (n_clips, 3, maxw*maxh)
+  float* eig;              // (n_clips, maxw*maxh)
+  unsigned* eigmax;        // (n_clips) key of the maximum
+  unsigned long long* cand;// (n_clips, maxw*maxh)
+  uint8_t* pyr[LK_MAX_LEVELS];      // levels 1..: (n_clips, n_frames, lvl_elems[l])
+  long long lvl_elems[LK_MAX_LEVELS];
+  // outputs
+  float* motion;           // (n_clips, n_frames, 2)
+  double* data;            // (n_clips, n_frames)
+  int32_t* npts;           // (n_clips)
+  int32_t* status;         // (n_clips)
+  float* pts_dbg;          // (n_clips, n_frames, LK_MAX_PTS, 2) or null: per-frame tracked points (tests)
+};
+
+__device__ __forceinline__ bool roi_ok(const MeasureParams& p, int clip, int& x, int& y, int& w, int& h) {
+  x = p.roi[clip * 4 + 0]; y = p.roi[clip * 4 + 1]; w = p.roi[clip * 4 + 2]; h = p.roi[clip * 4 + 3];
+  return p.status[clip] == RM_CLIP_OK && w >= 1 && h >= 1 && x >= 0 && y >= 0 && x + w <= p.W && y + h <= p.H &&
+         w <= p.maxw && h <= p.maxh;
+}
+
+// ------------------------------------------------------------------------------------------------ Shi-Tomasi
+// Sobel-3 derivatives scaled by 1/(4*block*255), products (cornerEigenValsVecs).  One thread per ROI pixel.
+__global__ void gftt_cov_kernel(const MeasureParams p) {
+  const int clip = blockIdx.y;
+  int rx, ry, rw, rh;
+  if (!roi_ok(p, clip, rx, ry, rw, rh)) return;
+  const uint8_t* img = p.frames + ((long long)clip * p.T + p.first_frame) * p.W * p.H + (long long)ry * p.W + rx;
+  const float k1 = (float)(1.0 / (4.0 * p.block_size * 255.0));
+  const float k0 = 2.0f * k1;
+  const long long plane = (long long)p.maxw * p.maxh;
+  float* cov = p.cov + (long long)clip * 3 * plane;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rw * rh; i += gridDim.x * blockDim.x) {
+    const int x = i % rw, y = i / rw;
+    const int xm = reflect101_multi(x - 1, rw), xp = reflect101_multi(x + 1, rw);
+    const int ym = reflect101_multi(y - 1, rh), yp = reflect101_multi(y + 1, rh);
+    float s[3][3];
+    const int ys[3] = {ym, y, yp}, xs[3] = {xm, x, xp};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) s[a][b] = (float)p.lut[img[(long long)ys[a] * p.W + xs[b]]];
+    // Dx: row pass [-1 0 1] (exact), column pass [1 2 1]*scale = fma(up+down, k1, mid*k0)
+    const float r0 = s[0][2] - s[0][0], r1 = s[1][2] - s[1][0], r2 = s[2][2] - s[2][0];
+    const float dx = fmaf(r0 + r2, k1, r1 * k0);
+    // Dy: row pass [1 2 1]*scale = fma(k1, right, fma(k0, mid, k1*left)), column pass [-1 0 1]
+    const float t0 = fmaf(k1, s[0][2], fmaf(k0, s[0][1], k1 * s[0][0]));
+    const float t2 = fmaf(k1, s[2][2], fmaf(k0, s[2][1], k1 * s[2][0]));
+    const float dy = t2 - t0;
+    cov[i] = dx * dx;
+    cov[plane + i] = dx * dy;
+    cov[2 * plane + i] = dy * dy;
+  }
+}
+
+// Un-normalised block x block box sums (float64 accumulation like cv::boxFilter), min eigenvalue, running maximum.
+__global__ void gftt_eig_kernel(const MeasureParams p) {
+  const int clip = blockIdx.y;
+  int rx, ry, rw, rh;
+  if (!roi_ok(p, clip, rx, ry, rw, rh)) return;
+  const long long plane = (long long)p.maxw * p.maxh;
+  const float* cov = p.cov + (long long)clip * 3 * plane;
+  float* eig = p.eig + (long long)clip * plane;
+  const int r = p.block_size / 2;
+  unsigned best = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rw * rh; i += gridDim.x * blockDim.x) {
+    const int x = i % rw, y = i / rw;
+    double sxx = 0.0, sxy = 0.0, syy = 0.0;
+    for (int dy = -r; dy < p.block_size - r; ++dy) {
+      const int yy = reflect101_multi(y + dy, rh);
+      double rxx = 0.0, rxy = 0.0, ryy = 0.0;
+      for (int dx = -r; dx < p.block_size - r; ++dx) {
+        const int j = yy * rw + reflect101_multi(x + dx, rw);
+        rxx += (double)cov[j];
+        rxy += (double)cov[plane + j];
+        ryy += (double)cov[2 * plane + j];
+      }
+      sxx += rxx; sxy += rxy; syy += ryy;
+    }
+    const float a = (float)sxx * 0.5f, b = (float)sxy, c = (float)syy * 0.5f;
+    const float d = a - c;
+    const float v = (a + c) - sqrtf(d * d + b * b);
+    eig[i] = v;
+    const unsigned k = f32_key(v);
+    best = k > best ? k : best;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(&p.eigmax[clip], best);
+}
+
+// threshold at quality*max, 3x3 local maxima on interior pixels, then greedy selection in descending order of
+// (value, address) with the minimum-distance rule.  One block per clip.
+__global__ void __launch_bounds__(256) gftt_select_kernel(const MeasureParams p, float* pts_out) {
+  const int clip = blockIdx.x;
+  int rx, ry, rw, rh;
+  __shared__ int s_ncand, s_naccept;
+  __shared__ unsigned long long s_red[8];
+  __shared__ unsigned long long s_best;
+  if (threadIdx.x == 0) { s_ncand = 0; s_naccept = 0; }
+  __syncthreads();
+  if (!roi_ok(p, clip, rx, ry, rw, rh)) {
+    if (threadIdx.x == 0) p.npts[clip] = 0;
+    return;
+  }
+  const long long plane = (long long)p.maxw * p.maxh;
+  const float* eig = p.eig + (long long)clip * plane;
+  unsigned long long* cand = p.cand + (long long)clip * plane;
+  const float maxv = key_f32(p.eigmax[clip]);
+  const float thr = (float)((double)maxv * (double)p.quality);   // cv::threshold receives a double, compares floats
+  for (int i = threadIdx.x; i < rw * rh; i += blockDim.x) {
+    const int x = i % rw, y = i / rw;
+    if (x < 1 || y < 1 || x >= rw - 1 || y >= rh - 1) continue;
+    const float v = eig[i];
+    if (!(v > thr) || v == 0.0f) continue;
+    bool is_max = true;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) is_max &= (v >= eig[(y + dy) * rw + x + dx]);
+    if (is_max) {
+      const int slot = atomicAdd(&s_ncand, 1);
+      cand[slot] = ((unsigned long long)f32_key(v) << 32) | (unsigned)i;
+    }
+  }
+  __syncthreads();
+  const int ncand = s_ncand;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int md2 = p.min_distance * p.min_distance;
+  float* out = pts_out + (long long)clip * LK_MAX_PTS * 2;
+  const int limit = p.max_corners < LK_MAX_PTS ? p.max_corners : LK_MAX_PTS;
+  for (;;) {
+    unsigned long long best = 0ull;
+    for (int i = threadIdx.x; i < ncand; i += blockDim.x) best = cand[i] > best ? cand[i] : best;
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) s_red[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) best = s_red[w] > best ? s_red[w] : best;
+      s_best = best;
+      if (best) {
+        const int addr = (int)(best & 0xffffffffu);
+        out[2 * s_naccept] = (float)(addr % rw);
+        out[2 * s_naccept + 1] = (float)(addr / rw);
+        s_naccept++;
+      }
+    }
+    __syncthreads();
+    const unsigned long long b = s_best;
+    if (!b || s_naccept >= limit) break;
+    const int addr = (int)(b & 0xffffffffu);
+    const int bx = addr % rw, by = addr / rw;
+    for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
+      const unsigned long long c = cand[i];
+      if (!c) continue;
+      const int a2 = (int)(c & 0xffffffffu);
+      const int dx = a2 % rw - bx, dy = a2 / rw - by;
+      if (c == b || (p.min_distance >= 1 && dx * dx + dy * dy < md2)) cand[i] = 0ull;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    p.npts[clip] = s_naccept;
+    if (s_naccept == 0) p.status[clip] = RM_CLIP_NO_CORNERS;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LK pyramids
+__device__ __forceinline__ int lk_num_levels(int w, int h, int win, int max_level, int* lw, int* lh) {
+  int n = 1;
+  lw[0] = w; lh[0] = h;
+  while (n <= max_level && n < LK_MAX_LEVELS) {
+    const int nw = (lw[n - 1] + 1) / 2, nh = (lh[n - 1] + 1) / 2;
+    if (nw <= win || nh <= win) break;
+    lw[n] = nw; lh[n] = nh;
+    ++n;
+  }
+  return n;
+}
+
+// cv2.pyrDown on uint8 (exact integers, (sum + 128) >> 8, REFLECT_101): level `lvl` of every measure frame.
+__global__ void lk_pyr_kernel(const MeasureParams p, int lvl) {
+  const int clip = blockIdx.z, f = blockIdx.y;
+  int rx, ry, rw, rh;
+  if (!roi_ok(p, clip, rx, ry, rw, rh)) return;
+  int lw[LK_MAX_LEVELS], lh[LK_MAX_LEVELS];
+  const int nlev = lk_num_levels(rw, rh, p.win, p.max_level, lw, lh);
+  if (lvl >= nlev) return;
+  const int sw = lw[lvl - 1], sh = lh[lvl - 1], dw = lw[lvl], dh = lh[lvl];
+  const uint8_t* src;
+  int spitch;
+  const bool use_lut = (lvl == 1);
+  if (lvl == 1) {
+    src = p.frames + ((long long)clip * p.T + p.first_frame + f) * p.W * p.H + (long long)ry * p.W + rx;
+    spitch = p.W;
+  } else {
+    src = p.pyr[lvl - 1] + ((long long)clip * p.n_frames + f) * p.lvl_elems[lvl - 1];
+    spitch = sw;
+  }
+  uint8_t* dst = p.pyr[lvl] + ((long long)clip * p.n_frames + f) * p.lvl_elems[lvl];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dw * dh; i += gridDim.x * blockDim.x) {
+    const int x = i % dw, y = i / dw;
+    int xs[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) xs[k] = reflect101_multi(2 * x + k - 2, sw);
+    int r[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const uint8_t* row = src + (long long)reflect101_multi(2 * y + k - 2, sh) * spitch;
+      int v[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) v[q] = use_lut ? p.lut[row[xs[q]]] : row[xs[q]];
+      r[k] = v[0] + v[4] + 4 * (v[1] + v[3]) + 6 * v[2];
+    }
+    dst[i] = (uint8_t)((r[0] + r[4] + 4 * (r[1] + r[3]) + 6 * r[2] + 128) >> 8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LK tracking
+struct LkImg {
+  const uint8_t* p;
+  int w, h, pitch;
+  bool lut;
+};
+__device__ __forceinline__ int lk_px(const LkImg& im, const uint8_t* lut, int y, int x) {
+  const uint8_t v = im.p[(long long)reflect101_multi(y, im.h) * im.pitch + reflect101_multi(x, im.w)];
+  return im.lut ? lut[v] : v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
+
+// One warp tracks one point through all pyramid levels (cv::LKTrackerInvoker).  patch / deriv are per-warp shared
+// scratch: (win+3)^2 ints and (win+1)^2 short2.  Returns status (1 = tracked).
+__device__ int lk_track_point(const MeasureParams& p, const LkImg* prev, const LkImg* next, int nlev,
+                              const uint8_t* lut, float px, float py, float* out_x, float* out_y, short* patch,
+                              short2* deriv, int lane) {
+  const int win = p.win;
+  const int pw = win + 3, dwid = win + 1;
+  const int npx = win * win;
+  const float half = (float)(win - 1) * 0.5f;
+  const float FLT_SCALE = 1.0f / (float)(1 << 20);
+  float nx = 0.f, ny = 0.f;
+  int status = 1;
+  for (int level = nlev - 1; level >= 0; --level) {
+    const float inv = (float)(1.0 / (double)(1 << level));
+    float ppx = px * inv, ppy = py * inv;
+    if (level == nlev - 1) { nx = ppx; ny = ppy; }
+    else { nx = nx * 2.f; ny = ny * 2.f; }
+    const LkImg& I = prev[level];
+    const LkImg& J = next[level];
+    ppx -= half; ppy -= half;
+    const int ix = (int)floorf(ppx), iy = (int)floorf(ppy);
+    if (ix < -win || ix >= I.w || iy < -win || iy >= I.h) {
+      if (level == 0) status = 0;
+      continue;
+    }
+    float a = ppx - (float)ix, b = ppy - (float)iy;
+    int iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+    int iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+    int iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+    int iw11 = 16384 - iw00 - iw01 - iw10;
+    // stage the (win+3)^2 neighbourhood of the previous image (reflect-101 padding like cv::copyMakeBorder)
+    __syncwarp();
+    for (int i = lane; i < pw * pw; i += 32) {
+      const int r = i / pw, c = i - r * pw;
+      patch[i] = (short)lk_px(I, lut, iy - 1 + r, ix - 1 + c);
+    }
+    __syncwarp();
+    // Scharr derivatives (calcScharrDeriv) on the (win+1)^2 positions the window touches; zero outside the image
+    for (int i = lane; i < dwid * dwid; i += 32) {
+      const int y = i / dwid, x = i - y * dwid;
+      short2 d = make_short2(0, 0);
+      if (iy + y >= 0 && iy + y < I.h && ix + x >= 0 && ix + x < I.w) {
+        const short* r0 = patch + y * pw + x;          // rows y-1, y, y+1 of the window position -> patch rows y..y+2
+        const short* r1 = r0 + pw;
+        const short* r2 = r1 + pw;
+        const int t0l = (r0[0] + r2[0]) * 3 + r1[0] * 10, t0r = (r0[2] + r2[2]) * 3 + r1[2] * 10;
+        const int t1l = r2[0] - r0[0], t1c = r2[1] - r0[1], t1r = r2[2] - r0[2];
+        d.x = (short)(t0r - t0l);
+        d.y = (short)((t1r + t1l) * 3 + t1c * 10);
+      }
+      deriv[i] = d;
+    }
+    __syncwarp();
+    int Iw[8], Ixv[8], Iyv[8];
+    long long sA11 = 0, sA12 = 0, sA22 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int q = lane + 32 * k;
+      Iw[k] = 0; Ixv[k] = 0; Iyv[k] = 0;
+      if (q < npx) {
+        const int wy = q / win, wx = q - wy * win;
+        const short* pr = patch + (wy + 1) * pw + wx + 1;
+        Iw[k] = descale(pr[0] * iw00 + pr[1] * iw01 + pr[pw] * iw10 + pr[pw + 1] * iw11, 9);
+        const short2 d00 = deriv[wy * dwid + wx], d01 = deriv[wy * dwid + wx + 1];
+        const short2 d10 = deriv[(wy + 1) * dwid + wx], d11 = deriv[(wy + 1) * dwid + wx + 1];
+        Ixv[k] = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, 14);
+        Iyv[k] = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, 14);
+        sA11 += (long long)Ixv[k] * Ixv[k];
+        sA12 += (long long)Ixv[k] * Iyv[k];
+        sA22 += (long long)Iyv[k] * Iyv[k];
+      }
+    }
+    sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
+    const float A11 = (float)sA11 * FLT_SCALE, A12 = (float)sA12 * FLT_SCALE, A22 = (float)sA22 * FLT_SCALE;
+    float D = A11 * A22 - A12 * A12;
+    const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+    if (minEig < p.min_eig || D < 1.1920929e-07f) {
+      if (level == 0) status = 0;
+      continue;
+    }
+    D = 1.f / D;
+    float qx = nx - half, qy = ny - half;
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < p.max_iter; ++j) {
+      const int jx = (int)floorf(qx), jy = (int)floorf(qy);
+      if (jx < -win || jx >= J.w || jy < -win || jy >= J.h) {
+        if (level == 0) status = 0;
+        break;
+      }
+      a = qx - (float)jx; b = qy - (float)jy;
+      iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+      iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+      iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+      iw11 = 16384 - iw00 - iw01 - iw10;
+      long long sb1 = 0, sb2 = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int q = lane + 32 * k;
+        if (q < npx) {
+          const int wy = q / win, wx = q - wy * win;
+          const int j00 = lk_px(J, lut, jy + wy, jx + wx), j01 = lk_px(J, lut, jy + wy, jx + wx + 1);
+          const int j10 = lk_px(J, lut, jy + wy + 1, jx + wx), j11 = lk_px(J, lut, jy + wy + 1, jx + wx + 1);
+          const int diff = descale(j00 * iw00 + j01 * iw01 + j10 * iw10 + j11 * iw11, 9) - Iw[k];
+          sb1 += (long long)diff * Ixv[k];
+          sb2 += (long long)diff * Iyv[k];
+        }
+      }
+      sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
+      const float b1 = (float)sb1 * FLT_SCALE, b2 = (float)sb2 * FLT_SCALE;
+      const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+      qx += dx; qy += dy;
+      nx = qx + half; ny = qy + half;
+      if ((double)dx * (double)dx + (double)dy * (double)dy <= p.eps2) break;
+      if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+        nx -= dx * 0.5f; ny -= dy * 0.5f;
+        break;
+      }
+      pdx = dx; pdy = dy;
+    }
+  }
+  *out_x = nx; *out_y = ny;
+  return status;
+}
+
+__global__ void __launch_bounds__(LK_WARPS * 32) lk_track_kernel(const MeasureParams p, const float* pts0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int clip = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float s_pts[LK_MAX_PTS][2], s_new[LK_MAX_PTS][2];
+  __shared__ int s_st[LK_MAX_PTS];
+  __shared__ int s_n, s_lost;
+  __shared__ uint8_t s_lut[256];
+  const int pw = p.win + 3, dwid = p.win + 1;
+  short* patch = reinterpret_cast<short*>(smem_raw) + (size_t)warp * (((pw * pw + 1) & ~1) + 2 * dwid * dwid);
+  short2* deriv = reinterpret_cast<short2*>(patch + ((pw * pw + 1) & ~1));
+  int rx, ry, rw, rh;
+  const bool ok = roi_ok(p, clip, rx, ry, rw, rh);
+  float* motion = p.motion + (long long)clip * p.n_frames * 2;
+  if (!ok || p.npts[clip] <= 0) {
+    for (int f = threadIdx.x; f < p.n_frames; f += blockDim.x) { motion[2 * f] = NAN; motion[2 * f + 1] = NAN; }
+    return;
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
+  if (threadIdx.x == 0) { s_n = p.npts[clip]; s_lost = 0; }
+  for (int i = threadIdx.x; i < p.npts[clip]; i += blockDim.x) {
+    s_pts[i][0] = pts0[((long long)clip * LK_MAX_PTS + i) * 2];
+    s_pts[i][1] = pts0[((long long)clip * LK_MAX_PTS + i) * 2 + 1];
+  }
+  if (threadIdx.x == 0) { motion[0] = 0.f; motion[1] = 0.f; }
+  __syncthreads();
+  int lw[LK_MAX_LEVELS], lh[LK_MAX_LEVELS];
+  const int nlev = lk_num_levels(rw, rh, p.win, p.max_level, lw, lh);
+  for (int f = 1; f < p.n_frames; ++f) {
+    LkImg prev[LK_MAX_LEVELS], next[LK_MAX_LEVELS];
+    for (int l = 0; l < nlev; ++l) {
+      if (l == 0) {
+        const uint8_t* base = p.frames + ((long long)clip * p.T + p.first_frame) * p.W * p.H + (long long)ry * p.W + rx;
+        prev[0] = {base + (long long)(f - 1) * p.W * p.H, rw, rh, p.W, true};
+        next[0] = {base + (long long)f * p.W * p.H, rw, rh, p.W, true};
+      } else {
+        const uint8_t* base = p.pyr[l] + (long long)clip * p.n_frames * p.lvl_elems[l];
+        prev[l] = {base + (long long)(f - 1) * p.lvl_elems[l], lw[l], lh[l], lw[l], false};
+        next[l] = {base + (long long)f * p.lvl_elems[l], lw[l], lh[l], lw[l], false};
+      }
+    }
+    const int n = s_n;
+    for (int i = warp; i < n; i += LK_WARPS) {
+      float ox, oy;
+      const int st = lk_track_point(p, prev, next, nlev, s_lut, s_pts[i][0], s_pts[i][1], &ox, &oy, patch, deriv, lane);
+      if (lane == 0) { s_new[i][0] = ox; s_new[i][1] = oy; s_st[i] = st; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // good_new = p1[st == 1], good_old = pts[st == 1]; mean(good_old - good_new, axis=0) in float32 (base.py:377-389)
+      int m = 0;
+      float sx = 0.f, sy = 0.f;
+      for (int i = 0; i < n; ++i) {
+        if (s_st[i]) {
+          sx += s_pts[i][0] - s_new[i][0];
+          sy += s_pts[i][1] - s_new[i][1];
+          s_pts[m][0] = s_new[i][0];
+          s_pts[m][1] = s_new[i][1];
+          ++m;
+        }
+      }
+      s_n = m;
+      if (m == 0) {
+        s_lost = 1;
+      } else {
+        motion[2 * f] = sx / (float)m;
+        motion[2 * f + 1] = sy / (float)m;
+      }
+    }
+    __syncthreads();
+    if (p.pts_dbg) {
+      float* dbg = p.pts_dbg + ((long long)clip * p.n_frames + f) * LK_MAX_PTS * 2;
+      for (int i = threadIdx.x; i < LK_MAX_PTS; i += blockDim.x) {
+        dbg[2 * i] = i < s_n ? s_pts[i][0] : NAN;
+        dbg[2 * i + 1] = i < s_n ? s_pts[i][1] : NAN;
+      }
+    }
+    if (s_lost) {   // tracking lost: extract_motion returns nan from here on (base.py:385-386)
+      for (int g = f + threadIdx.x; g < p.n_frames; g += blockDim.x) { motion[2 * g] = NAN; motion[2 * g + 1] = NAN; }
+      if (threadIdx.x == 0) p.status[clip] = RM_CLIP_TRACK_LOST;
+      return;
+    }
+  }
+}
+
+// data[f] (base.py:396-407): 0.0 for the first two frames, then the PCA projection of the rolling motion history.
+__global__ void motion_pca_kernel(const MeasureParams p) {
+  const int clip = blockIdx.y;
+  const float* motion = p.motion + (long long)clip * p.n_frames * 2;
+  double* data = p.data + (long long)clip * p.n_frames;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < p.n_frames; f += gridDim.x * blockDim.x) {
+    double v;
+    if (p.status[clip] == RM_CLIP_NO_ROI || p.status[clip] == RM_CLIP_NO_CORNERS) v = NAN;
+    else if (f < 2) v = 0.0;
+    else if (isnan(motion[2 * f])) v = NAN;
+    else {
+      // motion_data holds m_1..m_f, rolled to the last buf_len entries (base.py:473-475)
+      const int n = f < p.buf_len ? f : p.buf_len;
+      v = sc_pca_project_last(motion + 2 * (f - n + 1), n);
+    }
+    data[f] = v;
+  }
+}
+
+// extract_motion 'average' (base.py:355-358): np.average of the float64 crop = pairwise sum of gray*(1/255) / count.
+__global__ void measure_average_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ roi, int T, int W,
+                                       int H, int first_frame, int n_frames, double* __restrict__ data) {
+  const int clip = blockIdx.y, f = blockIdx.x;
+  const int rx = roi[clip * 4], ry = roi[clip * 4 + 1], rw = roi[clip * 4 + 2], rh = roi[clip * 4 + 3];
+  __shared__ double red[8];
+  const uint8_t* img = frames + ((long long)clip * T + first_frame + f) * W * H + (long long)ry * W + rx;
+  double acc = 0.0;
+  const double inv = 1.0 / 255;
+  for (int i = threadIdx.x; i < rw * rh; i += blockDim.x) acc += (double)img[(long long)(i / rw) * W + (i % rw)] * inv;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) acc += red[w];
+    data[(long long)clip * n_frames + f] = acc / (double)(rw * rh);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct MeasureLayout {
+  size_t cov, eig, eigmax, cand, pts0, pyr[LK_MAX_LEVELS], total;
+  long long lvl_elems[LK_MAX_LEVELS];
+};
+static MeasureLayout measure_layout(const rm_handle* h, int maxw, int maxh, int n_clips, int n_frames) {
+  MeasureLayout L;
+  memset(&L, 0, sizeof(L));
+  size_t off = 256;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t plane = (size_t)maxw * maxh;
+  L.cov = take((size_t)n_clips * 3 * plane * 4);
+  L.eig = take((size_t)n_clips * plane * 4);
+  L.eigmax = take((size_t)n_clips * 4);
+  L.cand = take((size_t)n_clips * plane * 8);
+  L.pts0 = take((size_t)n_clips * LK_MAX_PTS * 2 * 4);
+  int w = maxw, hh = maxh;
+  for (int l = 1; l < LK_MAX_LEVELS && l <= h->p.lk_max_level; ++l) {
+    w = (w + 1) / 2; hh = (hh + 1) / 2;
+    L.lvl_elems[l] = (long long)w * hh;
+    L.pyr[l] = take((size_t)n_clips * n_frames * w * hh);
+  }
+  L.total = off;
+  return L;
+}
+
+extern "C" int32_t rm_measure_workspace_bytes(rm_handle* h, int32_t max_roi_w, int32_t max_roi_h, int32_t n_clips,
+                                              int32_t n_frames, size_t* out) {
+  RM_CHECK_ARG(h, h && out && max_roi_w >= 1 && max_roi_h >= 1 && n_clips >= 0 && n_frames >= 0, "bad size");
+  *out = measure_layout(h, max_roi_w, max_roi_h, n_clips, n_frames).total;
+  return RM_OK;
+}
+
+static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
+                                 const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t first_frame,
+                                 int32_t n_frames, double* data_out, float* motion_out, int32_t* npts_out,
+                                 int32_t* status_io, float* pts_dbg, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  RM_CHECK_ARG(h, h && frames && roi && data_out && motion_out && npts_out && status_io, "null pointer");
+  RM_CHECK_ARG(h, n_clips >= 0 && T >= 1 && W >= 1 && H >= 1 && first_frame >= 0 && n_frames >= 1 &&
+                      first_frame + n_frames <= T, "frame range outside the clip");
+  RM_CHECK_ARG(h, max_roi_w >= 1 && max_roi_h >= 1 && max_roi_w <= W && max_roi_h <= H, "bad max ROI size");
+  if (h->p.max_corners > LK_MAX_PTS || h->p.max_corners < 1 || h->p.lk_win < 3 || h->p.lk_win > 31 ||
+      h->p.lk_win * h->p.lk_win > 256 || h->p.lk_max_level < 0 || h->p.lk_max_level >= LK_MAX_LEVELS)
+    return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: needs max_corners <= 128, 3 <= lk_win <= 16, lk_max_level <= 3", __func__);
+  if (n_clips == 0) return RM_OK;
+  MeasureLayout L = measure_layout(h, max_roi_w, max_roi_h, n_clips, n_frames);
+  if (!workspace || workspace_bytes < L.total)
+    return rm_fail(h, RM_ERR_WORKSPACE, "%s: workspace too small (%lld needed, %lld given)", __func__, (long long)L.total,
+                   (long long)workspace_bytes);
+  DeviceGuard dg(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  MeasureParams p;
+  memset(&p, 0, sizeof(p));
+  p.frames = frames; p.roi = roi; p.lut = h->d_lut;
+  p.n_clips = n_clips; p.T = T; p.W = W; p.H = H; p.first_frame = first_frame; p.n_frames = n_frames;
+  p.maxw = max_roi_w; p.maxh = max_roi_h;
+  p.max_corners = h->p.max_corners; p.min_distance = h->p.min_distance; p.block_size = h->p.block_size;
+  p.quality = (float)h->p.quality_level;
+  p.win = h->p.lk_win; p.max_level = h->p.lk_max_level;
+  p.max_iter = h->p.lk_max_iter < 0 ? 0 : (h->p.lk_max_iter > 100 ? 100 : h->p.lk_max_iter);
+  double eps = h->p.lk_eps < 0 ? 0 : (h->p.lk_eps > 10 ? 10 : h->p.lk_eps);
+  p.eps2 = eps * eps;
+  p.min_eig = (float)h->p.lk_min_eig;
+  p.buf_len = h->p.measure_buffer_len;
+  p.cov = reinterpret_cast<float*>(ws + L.cov);
+  p.eig = reinterpret_cast<float*>(ws + L.eig);
+  p.eigmax = reinterpret_cast<unsigned*>(ws + L.eigmax);
+  p.cand = reinterpret_cast<unsigned long long*>(ws + L.cand);
+  float* pts0 = reinterpret_cast<float*>(ws + L.pts0);
+  for (int l = 1; l < LK_MAX_LEVELS; ++l) {
+    p.pyr[l] = L.lvl_elems[l] ? ws + L.pyr[l] : nullptr;
+    p.lvl_elems[l] = L.lvl_elems[l];
+  }
+  p.motion = motion_out; p.data = data_out; p.npts = npts_out; p.status = status_io; p.pts_dbg = pts_dbg;
+
+  RM_CUDA(h, cudaMemsetAsync(p.eigmax, 0, (size_t)n_clips * 4, st));
+  const int roi_px = max_roi_w * max_roi_h;
+  dim3 g1(div_up(roi_px, 256) < 64 ? div_up(roi_px, 256) : 64, n_clips);
+  gftt_cov_kernel<<<g1, 256, 0, st>>>(p);
+  RM_LAUNCH_CHECK(h);
+  gftt_eig_kernel<<<g1, 256, 0, st>>>(p);
+  RM_LAUNCH_CHECK(h);
+  gftt_select_kernel<<<n_clips, 256, 0, st>>>(p, pts0);
+  RM_LAUNCH_CHECK(h);
+  for (int l = 1; l < LK_MAX_LEVELS && l <= h->p.lk_max_level; ++l) {
+    dim3 g2(div_up(L.lvl_elems[l], 256) < 32 ? div_up(L.lvl_elems[l], 256) : 32, n_frames, n_clips);
+    lk_pyr_kernel<<<g2, 256, 0, st>>>(p, l);
+    RM_LAUNCH_CHECK(h);
+  }
+  const int pw = p.win + 3, dwid = p.win + 1;
+  const size_t per_warp = (size_t)(((pw * pw + 1) & ~1) + 2 * dwid * dwid) * sizeof(short);
+  lk_track_kernel<<<n_clips, LK_WARPS * 32, per_warp * LK_WARPS, st>>>(p, pts0);
+  RM_LAUNCH_CHECK(h);
+  dim3 g3(div_up(n_frames, 128), n_clips);
+  motion_pca_kernel<<<g3, 128, 0, st>>>(p);
+  RM_LAUNCH_CHECK(h);
+  return RM_OK;
+}
+
+extern "C" int32_t rm_measure_flow(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
+                                   const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t first_frame,
+                                   int32_t n_frames, double* data_out, float* motion_out, int32_t* npts_out,
+                                   int32_t* status_io, void* workspace, size_t workspace_bytes, void* stream) {
+  return measure_flow_impl(h, frames, n_clips, T, W, H, roi, max_roi_w, max_roi_h, first_frame, n_frames, data_out,
+                           motion_out, npts_out, status_io, nullptr, workspace, workspace_bytes, stream);
+}
+
+// Same, additionally dumping the tracked points after every frame: pts_out (n_clips, n_frames, 128, 2) float32, NaN padded.
+extern "C" int32_t rm_measure_flow_debug(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W,
+                                         int32_t H, const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h,
+                                         int32_t first_frame, int32_t n_frames, double* data_out, float* motion_out,
+                                         int32_t* npts_out, int32_t* status_io, float* pts_out, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  RM_CHECK_ARG(h, pts_out != nullptr, "null pts_out");
+  return measure_flow_impl(h, frames, n_clips, T, W, H, roi, max_roi_w, max_roi_h, first_frame, n_frames, data_out,
+                           motion_out, npts_out, status_io, pts_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int32_t rm_measure_average(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W,
+                                      int32_t H, const int32_t* roi, int32_t first_frame, int32_t n_frames,
+                                      double* data_out, void* stream) {
+  RM_CHECK_ARG(h, h && frames && roi && data_out, "null pointer");
+  RM_CHECK_ARG(h, n_clips >= 0 && first_frame >= 0 && n_frames >= 1 && first_frame + n_frames <= T, "frame range");
+  if (n_clips == 0) return RM_OK;
+  DeviceGuard dg(h->device);
+  dim3 grid(n_frames, n_clips);
+  measure_average_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, roi, T, W, H, first_frame, n_frames, data_out);
+  RM_LAUNCH_CHECK(h);
+  return RM_OK;
+}

@@ -185,3 +185,77 @@ class Engine:
         out = torch.empty((n, T, H, W), dtype=torch.uint8, device=self.device)
         self._call("rm_synth_clips", _ptr(d_specs), _ptr(d_dq8), n, _ptr(out), self._stream())
         return out
+
+    # ------------------------------------------------------------------ measure
+    def measure_flow(self, clips: torch.Tensor, roi: torch.Tensor, first_frame: int, n_frames: int,
+                     status: torch.Tensor | None = None, max_roi: tuple[int, int] | None = None, debug_points=False):
+        """extract_motion 'flow' for every clip (base.py:360-407).
+
+        clips (n,T,H,W) uint8, roi (n,4) int32 x,y,w,h (device).  Returns dict(data (n,n_frames) f64, motion
+        (n,n_frames,2) f32, npts (n,), status (n,), [points (n,n_frames,128,2)])."""
+        assert clips.is_cuda and clips.dtype == torch.uint8 and clips.is_contiguous() and clips.dim() == 4
+        n, T, H, W = clips.shape
+        roi = roi.to(self.device, torch.int32).contiguous()
+        if status is None:
+            status = torch.zeros(n, dtype=torch.int32, device=self.device)
+        if max_roi is None:
+            r = roi.cpu()
+            max_roi = (max(1, int(r[:, 2].max())), max(1, int(r[:, 3].max()))) if n else (1, 1)
+        mw, mh = min(W, max_roi[0]), min(H, max_roi[1])
+        data = torch.empty((n, n_frames), dtype=torch.float64, device=self.device)
+        motion = torch.empty((n, n_frames, 2), dtype=torch.float32, device=self.device)
+        npts = torch.zeros(n, dtype=torch.int32, device=self.device)
+        need = C.c_size_t()
+        self._call("rm_measure_workspace_bytes", mw, mh, n, n_frames, C.byref(need))
+        ws = self._workspace("measure", need.value)
+        out = dict(data=data, motion=motion, npts=npts, status=status)
+        if debug_points:
+            pts = torch.empty((n, n_frames, 128, 2), dtype=torch.float32, device=self.device)
+            self._call("rm_measure_flow_debug", _ptr(clips), n, T, W, H, _ptr(roi), mw, mh, first_frame, n_frames,
+                       _ptr(data), _ptr(motion), _ptr(npts), _ptr(status), _ptr(pts), _ptr(ws), ws.numel(),
+                       self._stream())
+            out["points"] = pts
+        else:
+            self._call("rm_measure_flow", _ptr(clips), n, T, W, H, _ptr(roi), mw, mh, first_frame, n_frames,
+                       _ptr(data), _ptr(motion), _ptr(npts), _ptr(status), _ptr(ws), ws.numel(), self._stream())
+        return out
+
+    def measure_average(self, clips: torch.Tensor, roi: torch.Tensor, first_frame: int, n_frames: int) -> torch.Tensor:
+        """extract_motion 'average' (base.py:355-358)."""
+        n, T, H, W = clips.shape
+        roi = roi.to(self.device, torch.int32).contiguous()
+        data = torch.empty((n, n_frames), dtype=torch.float64, device=self.device)
+        self._call("rm_measure_average", _ptr(clips), n, T, W, H, _ptr(roi), first_frame, n_frames, _ptr(data),
+                   self._stream())
+        return data
+
+    def signal_bpm(self, data: torch.Tensor, fps: float, status: torch.Tensor | None = None):
+        """measure() at every frame (base.py:340-352): data (n,n_frames) f64 -> dict(bpm (n,n_frames), filtered
+        (n,buf_len), peaks (n,buf_len) (-1 padded), npeaks (n,))."""
+        assert data.is_cuda and data.dtype == torch.float64 and data.is_contiguous() and data.dim() == 2
+        n, nf = data.shape
+        L = self.params.measure_buffer_len
+        bpm = torch.empty((n, nf), dtype=torch.float64, device=self.device)
+        filt = torch.empty((n, L), dtype=torch.float64, device=self.device)
+        peaks = torch.empty((n, L), dtype=torch.int32, device=self.device)
+        npk = torch.zeros(n, dtype=torch.int32, device=self.device)
+        self._call("rm_signal_bpm", _ptr(data), n, nf, float(fps), _ptr(bpm), _ptr(filt), _ptr(peaks), _ptr(npk),
+                   _ptr(status), self._stream())
+        return dict(bpm=bpm, filtered=filt, peaks=peaks, npeaks=npk)
+
+    def pack_results(self, bpm, roi, status, npeaks) -> torch.Tensor:
+        """(n,32) uint8 view of rm_result records."""
+        n, nf = bpm.shape
+        out = torch.empty((n, 32), dtype=torch.uint8, device=self.device)
+        self._call("rm_pack_results", _ptr(bpm), _ptr(roi.to(self.device, torch.int32).contiguous()), _ptr(status),
+                   _ptr(npeaks), n, nf, _ptr(out), self._stream())
+        return out
+
+
+RESULT_DTYPE = np.dtype([("bpm", "<f8"), ("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("status", "<i4"),
+                         ("n_peaks", "<i4")])
+
+
+def results_to_numpy(records: torch.Tensor) -> np.ndarray:
+    """(n,32) uint8 tensor of rm_result -> structured numpy array."""
+    return records.cpu().numpy().view(RESULT_DTYPE).reshape(-1)

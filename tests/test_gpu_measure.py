@@ -1,0 +1,150 @@
+"""GPU parity: measure kernels through the C ABI against the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import clip_from_fixture  # noqa: E402
+from oracle import cpu_path as P  # noqa: E402
+from oracle import np_kernels as K  # noqa: E402
+
+CASES = ["vga_s0", "vga_s2", "qvga_s1", "odd_s3"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from respmon_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_flow_measure_matches_reference_golden(eng, golden, name):
+    fix = golden(name)
+    spec, clip = clip_from_fixture(fix)
+    roi = fix["roi"].astype(np.int32)[None]
+    nf = spec.n_frames - 130
+    out = eng.measure_flow(dev(clip[None]), dev(roi), 130, nf, debug_points=True)
+    assert int(out["status"][0]) == 0
+    # corners: identical to cv2.goodFeaturesToTrack inside the reference run
+    npts = int(out["npts"][0])
+    assert npts == len(fix["gftt_pts"])
+    pts = out["points"].cpu().numpy()[0]
+    # per-frame tracked points against the reference's calcOpticalFlowPyrLK outputs
+    off = 0
+    worst = 0.0
+    for i, n_i in enumerate(fix["lk_n"]):
+        st = fix["lk_status"][off:off + n_i].astype(bool)
+        want = fix["lk_next"][off:off + n_i][st]
+        got = pts[i + 1][:len(want)]
+        assert not np.isnan(got).any() and (len(want) == 128 or np.isnan(pts[i + 1][len(want)]).all())
+        worst = max(worst, np.abs(got - want).max())
+        off += n_i
+    assert worst < 2e-3, worst
+    data = out["data"].cpu().numpy()[0]
+    assert np.sqrt(np.mean((data - fix["data"]) ** 2)) <= 1e-4          # north-star gate: motion signal RMS
+    motion = out["motion"].cpu().numpy()[0][1:]
+    assert np.abs(motion - fix["motion"]).max() < 1e-3
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_gftt_matches_cv2_on_random_rois(eng, seed):
+    import cv2
+    rng = np.random.default_rng(seed)
+    H, W = 120, 160
+    img = cv2.GaussianBlur(rng.integers(0, 256, (H, W)).astype(np.uint8), (0, 0), 1.2)
+    clip = np.stack([img, img])[None]
+    rw, rh = int(rng.integers(20, 100)), int(rng.integers(20, 80))
+    rx, ry = int(rng.integers(0, W - rw)), int(rng.integers(0, H - rh))
+    out = eng.measure_flow(dev(clip), dev(np.array([[rx, ry, rw, rh]], dtype=np.int32)), 0, 2, debug_points=True)
+    lut = K.lossy_u8_lut()
+    want = cv2.goodFeaturesToTrack(lut[img[ry:ry + rh, rx:rx + rw]], mask=None, **P.FEATURE_PARAMS)
+    n = int(out["npts"][0])
+    if want is None:
+        assert n == 0 and int(out["status"][0]) == 2
+        return
+    assert n == len(want)
+    # identical frames: LK must leave every point where it is (to float rounding) and keep the order
+    got = out["points"].cpu().numpy()[0, 1, :n]
+    assert np.abs(got - want.reshape(-1, 2)).max() < 1e-3
+
+
+def test_lk_matches_cv2_on_shifted_texture(eng):
+    import cv2
+    rng = np.random.default_rng(7)
+    H, W = 200, 240
+    base = cv2.GaussianBlur(rng.integers(0, 256, (H + 8, W + 8)).astype(np.uint8), (0, 0), 2.0)
+    base = cv2.normalize(base, None, 0, 255, cv2.NORM_MINMAX)
+    frames = []
+    for k in range(6):
+        M = np.float32([[1, 0, 4 + 0.7 * k], [0, 1, 4 - 0.4 * k]])
+        frames.append(cv2.warpAffine(base, M, (W + 8, H + 8), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP)[:H, :W])
+    clip = np.stack(frames)[None].copy()
+    roi = np.array([[10, 20, 150, 140]], dtype=np.int32)      # big enough for three pyramid levels
+    out = eng.measure_flow(dev(clip), dev(roi), 0, 6, debug_points=True)
+    lut = K.lossy_u8_lut()
+    crop = lambda f: lut[clip[0, f, 20:160, 10:160]]
+    pts = cv2.goodFeaturesToTrack(crop(0), mask=None, **P.FEATURE_PARAMS)
+    got = out["points"].cpu().numpy()[0]
+    for f in range(1, 6):
+        p1, st, _ = cv2.calcOpticalFlowPyrLK(crop(f - 1), crop(f), pts, None, **P.LK_PARAMS)
+        pts = p1[st == 1].reshape(-1, 1, 2)
+        assert np.isnan(got[f][len(pts):]).all()
+        assert np.abs(got[f][:len(pts)] - pts.reshape(-1, 2)).max() < 2e-3
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_signal_bpm_matches_reference_golden(eng, golden, name):
+    fix = golden(name)
+    data = dev(fix["data"][None])
+    out = eng.signal_bpm(data, float(fix["fps"]))
+    bpm = out["bpm"].cpu().numpy()[0]
+    hist = bpm[~np.isnan(bpm)]
+    assert len(hist) == len(fix["freq"])
+    assert np.abs(hist - fix["freq"]).max() < 1e-6
+    n = len(fix["filtered"])
+    assert np.abs(out["filtered"].cpu().numpy()[0][:n] - fix["filtered"]).max() < 1e-12
+    k = int(out["npeaks"][0])
+    assert list(out["peaks"].cpu().numpy()[0][:k]) == [int(v) for v in fix["peaks"]]
+
+
+def test_signal_bpm_rolling_window_and_nan(eng):
+    """Longer than the 128-sample buffer (base.py:473-475) and a clip whose tracking was lost."""
+    rng = np.random.default_rng(3)
+    nf = 300
+    t = np.arange(nf) / 10.0
+    data = np.stack([0.1 * np.sin(2 * np.pi * 0.3 * t) + 0.01 * rng.standard_normal(nf),
+                     0.2 * np.sin(2 * np.pi * 0.21 * t + 1.0) + 0.02 * rng.standard_normal(nf)])
+    data[1, 200:] = np.nan
+    out = eng.signal_bpm(dev(data), 10.0)
+    bpm = out["bpm"].cpu().numpy()
+    tt = np.zeros(nf)
+    for i in range(1, nf):
+        tt[i] = tt[i - 1] + 1.0 / 10.0
+    for c in range(2):
+        for f in (12, 13, 50, 127, 128, 129, 199, 200, 250, 299):
+            lo = max(0, f + 1 - 128)
+            w = data[c, lo:f + 1]
+            if f < 13 - 1 or np.isnan(w).any():
+                assert np.isnan(bpm[c, f])
+                continue
+            _, _, want = P.measure_window(w, tt[lo:f + 1], 10.0)
+            if want is None:
+                assert np.isnan(bpm[c, f])
+            else:
+                assert abs(bpm[c, f] - want) < 1e-6
+
+
+def test_average_mode(eng, golden):
+    fix = golden("qvga_s1")
+    spec, clip = clip_from_fixture(fix)
+    x, y, w, h = (int(v) for v in fix["roi"])
+    got = eng.measure_average(dev(clip[None]), dev(fix["roi"].astype(np.int32)[None]), 130, 20).cpu().numpy()[0]
+    want = [np.average(P.u8_to_unit(clip[130 + f, y:y + h, x:x + w])) for f in range(20)]
+    assert np.abs(got - np.array(want)).max() < 1e-14
