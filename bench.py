@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for respmon_b200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): frames/sec (calibrate + measure) on 640x480 synthetic video.
+Workload at every N: each GPU holds a batch of 64 synthetic 640x480x256 uint8 clips (BASELINE config 2's batch) and
+runs the reference's whole per-clip path on it with the reference's frame routing (base.py:409-513): frames 1..128 ->
+locate() (pyramid + temporal band-pass + collapse + ROI), frames 130..255 -> extract_motion('flow') + measure().
+A step is one pass over the batch; frames counted = every input frame of every clip (n_clips * 256).
+
+  value     clips resident in HBM before the timed region; CUDA events on the launching stream, max over ranks.
+  e2e       the same through BatchMonitor.run() from pinned HOST memory: chunked H2D copies and the D2H read of the
+            result records are inside the timed region.
+  roofline  the HBM-bound streaming kernel of the path (pyramid front kernel), timed per launch by CUDA events that the
+            library records on its stream (rm_profile_*), against MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/cpu_path.py, cv2/scipy/numpy -- the
+            reference tree itself does not exist on the GPU box) on whole clips, one worker process per host core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H, T = 640, 480, 256
+FPS = 10.0
+METRIC = "frames/sec (calibrate+measure) on 640x480 synthetic video"
+UNIT = "frames/s"
+WORKLOAD = "64 clips/GPU x 640x480x256 u8 synthetic, full path (frames 1-128 calibrate -> ROI, frames 130-255 LK measure -> BPM)"
+
+
+# --------------------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    """One whole clip through the CPU oracle (TEST INFRASTRUCTURE used here only as the measured CPU baseline)."""
+    seed, = args
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import cpu_path as P
+    from respmon_b200 import synth
+    spec = synth.clip_spec(seed, W, H, T)
+    clip = synth.make_clip(spec)
+    t0 = time.perf_counter()
+    res = P.run_clip(clip, fps=FPS)
+    return time.perf_counter() - t0, res["bpm"], res["roi"], spec.truth_bpm
+
+
+def _cpu_workers():
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        import psutil
+        n = min(n, max(1, int(psutil.virtual_memory().available // (3 << 30))))   # ~2.5 GB of float64 volumes per clip
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
+def run_reference_arm(steps: int, warmup: int, n_gpus: int) -> dict:
+    """Each step: one clip per worker process, all host cores busy; value = frames of the sample / slowest worker."""
+    import multiprocessing as mp
+    workers = _cpu_workers()
+    ctx = mp.get_context("spawn")
+    times = []
+    bpm_err = []
+    with ctx.Pool(workers) as pool:
+        for it in range(warmup + steps):
+            seeds = [(1000 * it + i,) for i in range(workers)]
+            out = pool.map(_cpu_worker, seeds, chunksize=1)
+            dt = max(o[0] for o in out)          # workers run concurrently; clip synthesis is outside their timers
+            if it >= warmup:
+                times.append(dt)
+                bpm_err += [abs(o[1] - o[3]) for o in out if o[1] is not None]
+    ms = 1e3 * sum(times) / len(times)
+    value = workers * T / (ms / 1e3)
+    sample = "%d clips of 640x480x256 per step (one per worker process, cv2 threads = 1 each)" % workers
+    return {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample, "host_cores": os.cpu_count()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "median_abs_bpm_error_vs_truth": statistics.median(bpm_err) if bpm_err else None,
+    }
+
+
+# --------------------------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_gpu_arm(args) -> dict | None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE (%d) != --gpus (%d)" % (world, args.gpus))
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus %d needs torchrun (python -m torch.distributed.run --nproc-per-node %d bench.py ...)"
+                         % (args.gpus, args.gpus))
+
+    # CPU baseline first (rank 0, N=1 only), in its own interpreter, before this process touches CUDA
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                              "--warmup", "0"], capture_output=True, text=True, timeout=900)
+        for line in out.stdout.splitlines()[::-1]:
+            if line.startswith("{"):
+                cpu_baseline = json.loads(line)["cpu_baseline"]
+                break
+        if cpu_baseline is None:
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                            "sample": "failed: " + out.stderr[-300:]}
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from respmon_b200 import synth
+    from respmon_b200.batch import BatchMonitor
+    from respmon_b200.engine import RESULT_DTYPE
+
+    n_clips = args.clips
+    mon = BatchMonitor(local_rank, chunk_clips=args.chunk)
+    eng = mon.engine
+
+    # synthetic clips generated on the device (bit-identical to synth.make_clip); different seeds on every rank
+    specs = [synth.clip_spec(rank * n_clips + i, W, H, T, fps=FPS) for i in range(n_clips)]
+    dq8 = np.stack([synth.displacement_q8(s) for s in specs])
+    clips = eng.synth_clips(specs, dq8)
+    torch.cuda.synchronize()
+
+    gathered = torch.empty((world * n_clips, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=eng.device)
+
+    def step():
+        rec = eng.run_batch(clips, FPS)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, rec)        # the path's only collective: 32 B per clip
+            return gathered
+        return rec
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    eng.profile(True)
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        rec = step()
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    prof = eng.profile_report()
+    eng.profile(False)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    frames_per_step = world * n_clips * T
+    value = frames_per_step / (ms_per_step / 1e3)
+
+    # result sanity: BPM against the synthetic ground truth (parity with the CPU oracle is tests/ -m gpu)
+    recs = rec.cpu().numpy().view(RESULT_DTYPE).reshape(-1)[rank * n_clips:(rank + 1) * n_clips] if world > 1 \
+        else rec.cpu().numpy().view(RESULT_DTYPE).reshape(-1)
+    ok = recs["status"] == 0
+    truth = np.array([s.truth_bpm for s in specs])
+    bpm_err = np.abs(recs["bpm"][ok] - truth[ok])
+
+    # ---- end to end from host memory through the public batch API
+    host = torch.empty(clips.shape, dtype=torch.uint8).pin_memory()
+    host.copy_(clips)
+    torch.cuda.synchronize()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    mon.run(host, FPS)                                         # warm-up (allocations)
+    barrier()
+    mon.h2d_bytes = mon.d2h_bytes = 0
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = mon.run(host, FPS)
+        if world > 1:
+            from respmon_b200.batch import gather_records
+            out = gather_records(out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = frames_per_step * e2e_steps / e2e_s
+    same = bool(np.array_equal(out["bpm"][rank * n_clips:(rank + 1) * n_clips] if world > 1 else out["bpm"],
+                               recs["bpm"], equal_nan=True))
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+
+    # ---- roofline of the HBM-bound streaming kernel (pyramid front), per launch
+    peak, peak_src = measured_peaks()
+    total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
+    kernels = sorted(({"name": k, "ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+                       "share": v[0] / total_kernel_ms} for k, v in prof.items()), key=lambda d: -d["ms_per_step"])
+    lw, lh = eng.level_sizes(W, H)[eng.params.skip_levels_at_top]
+    front = prof.get("pyramid_front_kernel<u8>")
+    roofline = None
+    if front:
+        frames_per_launch = n_clips * 128                     # calibration frames of the batch, one launch per step
+        bytes_per_frame = W * H * 1 + lw * lh * 8             # frame read once (u8) + Gaussian level 4 written (f64)
+        dur_s = front[0] / front[1] / 1e3
+        achieved = frames_per_launch * bytes_per_frame / dur_s / 1e9
+        roofline = {"kernel": "pyramid_front_kernel<u8>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "bytes_per_launch": frames_per_launch * bytes_per_frame, "launch_ms": dur_s * 1e3,
+                    "share_of_step": front[0] / total_kernel_ms}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "clips_per_gpu": n_clips, "frames_per_step": frames_per_step,
+                   "input_dtype": "u8", "l2": "inputs %.1f GB per GPU per step > 126 MB L2 (no flush needed)"
+                                               % (clips.numel() / 1e9),
+                   "parallelism": "clips sharded over %d GPU(s), one all-gather of 32 B result records" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mon.h2d_bytes // e2e_steps,
+                "d2h_bytes_per_step": mon.d2h_bytes // e2e_steps, "steps": e2e_steps, "chunk_clips": args.chunk,
+                "same_results_as_resident_run": same},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "kernels": kernels,
+        "results": {"clips_ok": int(ok.sum()), "clips": int(n_clips),
+                    "median_abs_bpm_error_vs_truth": float(np.median(bpm_err)) if len(bpm_err) else None,
+                    "max_abs_bpm_error_vs_truth": float(bpm_err.max()) if len(bpm_err) else None},
+    }
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clips", type=int, default=64, help="clips per GPU")
+    ap.add_argument("--chunk", type=int, default=8, help="clips per H2D chunk of the end-to-end leg")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        print(json.dumps(run_reference_arm(max(1, args.steps), max(0, args.warmup), args.gpus)), flush=True)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    line = run_gpu_arm(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

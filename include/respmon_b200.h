@@ -130,6 +130,13 @@ int32_t rm_heatmap_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n
 int32_t rm_pyramid_build(rm_handle* h, const void* frames, int32_t dtype, int64_t n_frames, int32_t W, int32_t H,
                          double* lap_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same on a window of every clip of a batch, without copying it: frames (n_clips,T,H,W); clip c contributes frames
+ * [first_frame, first_frame+n_frames) (the calibration buffer of base.py:429-434) -> lap (n_clips, n_frames, record_len).
+ * Workspace as for n_clips*n_frames frames. */
+int32_t rm_pyramid_build_clips(rm_handle* h, const void* frames, int32_t dtype, int32_t n_clips, int32_t T,
+                               int32_t first_frame, int32_t n_frames, int32_t W, int32_t H, double* lap_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* temporal_bandpass_filter_fft (transforms.py:82-102) on every column of (n_clips, T, record_len), in place allowed. */
 int32_t rm_temporal_bandpass(rm_handle* h, const double* lap, double* bp_out, int32_t n_clips, int32_t T,
                              int64_t record_len, double fps, void* stream);
@@ -139,6 +146,14 @@ int32_t rm_temporal_bandpass(rm_handle* h, const double* lap, double* bp_out, in
  * minmax_out (n_clips,4) = raw min, raw max, avg min, avg max (nullable). */
 int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, int32_t T, int32_t W, int32_t H, uint8_t* heat_out,
                    double* minmax_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Tail of locate() (base.py:566-575): cv2.threshold(heat, threshold, 255, THRESH_BINARY), cv2.findContours(RETR_EXTERNAL),
+ * max by cv2.contourArea (ties: the contour cv2 lists first), cv2.boundingRect.  heat (n_clips,H,W) uint8 ->
+ * roi_out (n_clips,4) int32 x,y,w,h; status_out (n_clips; nullable) = RM_CLIP_OK or RM_CLIP_NO_ROI (locate() -> None,
+ * base.py:569-570; the box is then 0,0,0,0). */
+int32_t rm_roi_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n_clips, size_t* out);
+int32_t rm_roi_select(rm_handle* h, const uint8_t* heat, int32_t n_clips, int32_t W, int32_t H, int32_t threshold,
+                      int32_t* roi_out, int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stand-alone tail of eulerian_magnification_bandpass on a materialised volume (transforms.py:184-192) plus the time
  * average of base.py:562: raw (T,hw) -> clipped_out (T,hw; nullable), avg_out (hw; nullable; mean of the clipped volume,
@@ -182,6 +197,14 @@ int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, con
 /* ------------------------------------------------------------------ bookkeeping */
 /* Number of kernel launches this handle has issued since creation (bench.py reports it as gpu_launches). */
 int64_t rm_launch_count(rm_handle* h);
+
+/* Per-kernel device timing, the kernel-granular analogue of the reference's tools.Benchmarker (tools.py:60-82): while
+ * enabled every launch is bracketed by CUDA events on its own stream.  rm_profile_collect waits for them, folds them into
+ * a per-kernel table and returns its size; rm_profile_entry reads row i (name is a static string). */
+int32_t rm_profile_enable(rm_handle* h, int32_t on);
+int32_t rm_profile_reset(rm_handle* h);
+int32_t rm_profile_collect(rm_handle* h);
+int32_t rm_profile_entry(rm_handle* h, int32_t i, const char** host_name, double* host_total_ms, int64_t* host_launches);
 
 #ifdef __cplusplus
 }

@@ -65,8 +65,11 @@ SIGNATURES = {
     "rm_pyramid_workspace_bytes": (_i32, [_H, _i32, _i32, _i64, C.POINTER(_sz)]),
     "rm_heatmap_workspace_bytes": (_i32, [_H, _i32, _i32, _i32, _i32, C.POINTER(_sz)]),
     "rm_pyramid_build": (_i32, [_H, _P, _i32, _i64, _i32, _i32, _P, _P, _sz, _S]),
+    "rm_pyramid_build_clips": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _P, _P, _sz, _S]),
     "rm_temporal_bandpass": (_i32, [_H, _P, _P, _i32, _i32, _i64, _f64, _S]),
     "rm_heatmap": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _P, _P, _sz, _S]),
+    "rm_roi_workspace_bytes": (_i32, [_H, _i32, _i32, _i32, C.POINTER(_sz)]),
+    "rm_roi_select": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _P, _P, _sz, _S]),
     "rm_volume_clip_mean": (_i32, [_H, _P, _P, _P, _P, _i32, _i64, _f64, _P, _S]),
     "rm_measure_workspace_bytes": (_i32, [_H, _i32, _i32, _i32, _i32, C.POINTER(_sz)]),
     "rm_measure_flow": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _i32, _i32, _P, _P, _P, _P, _P, _sz, _S]),
@@ -76,6 +79,10 @@ SIGNATURES = {
     "rm_signal_bpm": (_i32, [_H, _P, _i32, _i32, _f64, _P, _P, _P, _P, _P, _S]),
     "rm_pack_results": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _P, _S]),
     "rm_launch_count": (_i64, [_H]),
+    "rm_profile_enable": (_i32, [_H, _i32]),
+    "rm_profile_reset": (_i32, [_H]),
+    "rm_profile_collect": (_i32, [_H]),
+    "rm_profile_entry": (_i32, [_H, _i32, C.POINTER(C.c_char_p), C.POINTER(_f64), C.POINTER(_i64)]),
 }
 
 _lib = None

@@ -128,8 +128,62 @@ extern "C" int32_t rm_destroy(rm_handle* h) {
     DeviceGuard dg(h->device);
     if (h->d_lut) cudaFree(h->d_lut);
     if (h->d_tvals) cudaFree(h->d_tvals);
+    for (int i = 0; i < h->prof_cap; ++i) {
+      cudaEventDestroy(h->prof_slots[i].a);
+      cudaEventDestroy(h->prof_slots[i].b);
+    }
   }
+  free(h->prof_slots);
+  free(h->prof_table);
   free(h);
+  return RM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- profiling
+extern "C" int32_t rm_profile_enable(rm_handle* h, int32_t on) {
+  if (!h) return RM_ERR_INVALID;
+  h->prof_on = on ? 1 : 0;
+  return RM_OK;
+}
+extern "C" int32_t rm_profile_reset(rm_handle* h) {
+  if (!h) return RM_ERR_INVALID;
+  h->prof_n = 0;
+  h->prof_open = 0;
+  h->prof_entries = 0;
+  return RM_OK;
+}
+// Waits for the recorded launches, folds their durations into the per-kernel table; returns the table size (or < 0).
+extern "C" int32_t rm_profile_collect(rm_handle* h) {
+  if (!h) return RM_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  if (!h->prof_table) h->prof_table = (rm_prof_entry*)calloc(RM_PROF_MAX_ENTRIES, sizeof(rm_prof_entry));
+  if (!h->prof_table) return RM_ERR_INVALID;
+  for (int i = 0; i < h->prof_n; ++i) {
+    rm_prof_slot* s = &h->prof_slots[i];
+    float ms = 0.f;
+    RM_CUDA(h, cudaEventSynchronize(s->b));
+    RM_CUDA(h, cudaEventElapsedTime(&ms, s->a, s->b));
+    int e = 0;
+    for (; e < h->prof_entries; ++e)
+      if (h->prof_table[e].name == s->name || strcmp(h->prof_table[e].name, s->name) == 0) break;
+    if (e == h->prof_entries) {
+      if (e >= RM_PROF_MAX_ENTRIES) continue;
+      h->prof_table[e].name = s->name;
+      h->prof_table[e].total_ms = 0.0;
+      h->prof_table[e].launches = 0;
+      h->prof_entries++;
+    }
+    h->prof_table[e].total_ms += ms;
+    h->prof_table[e].launches++;
+  }
+  h->prof_n = 0;
+  return h->prof_entries;
+}
+extern "C" int32_t rm_profile_entry(rm_handle* h, int32_t i, const char** name, double* total_ms, int64_t* launches) {
+  if (!h || i < 0 || i >= h->prof_entries || !name || !total_ms || !launches) return RM_ERR_INVALID;
+  *name = h->prof_table[i].name;
+  *total_ms = h->prof_table[i].total_ms;
+  *launches = h->prof_table[i].launches;
   return RM_OK;
 }
 
@@ -188,6 +242,7 @@ extern "C" int32_t rm_synth_clips(rm_handle* h, const rm_clip_spec* specs, const
   if (n_clips == 0) return RM_OK;
   DeviceGuard dg(h->device);
   dim3 grid(h->sm_count * 2 / (n_clips < 8 ? n_clips : 8) + 1, 1, n_clips);
+  RM_PROF(h, (cudaStream_t)stream, "synth_clips_kernel");
   synth_clips_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(specs, dq8, out);
   RM_LAUNCH_CHECK(h);
   return RM_OK;

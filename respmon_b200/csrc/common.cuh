@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/respmon_b200.h"
@@ -20,7 +21,48 @@ struct rm_handle {
   uint8_t* d_lut;       // device copy
   double* d_tvals;      // running time axis of the measure buffers (base.py:481-484), grown on demand
   int tvals_cap;
+  // per-kernel device timing (the reference's tools.Benchmarker tags, tools.py:60-82, at kernel granularity)
+  int prof_on;
+  int prof_n, prof_cap, prof_open;
+  struct rm_prof_slot* prof_slots;
+  int prof_entries;
+  struct rm_prof_entry* prof_table;
 };
+struct rm_prof_slot {
+  const char* name;
+  cudaEvent_t a, b;
+  cudaStream_t st;
+};
+struct rm_prof_entry {
+  const char* name;
+  double total_ms;
+  long long launches;
+};
+#define RM_PROF_MAX_SLOTS 16384
+#define RM_PROF_MAX_ENTRIES 64
+// open a timing slot on `st` for the launch that follows; RM_LAUNCH_CHECK closes it
+static inline void rm_prof_begin(rm_handle* h, cudaStream_t st, const char* name) {
+  if (!h->prof_on || h->prof_n >= RM_PROF_MAX_SLOTS) return;
+  if (!h->prof_slots) h->prof_slots = (rm_prof_slot*)calloc(RM_PROF_MAX_SLOTS, sizeof(rm_prof_slot));
+  if (!h->prof_slots) return;
+  rm_prof_slot* s = &h->prof_slots[h->prof_n];
+  if (h->prof_n >= h->prof_cap) {
+    if (cudaEventCreate(&s->a) != cudaSuccess || cudaEventCreate(&s->b) != cudaSuccess) return;
+    h->prof_cap = h->prof_n + 1;
+  }
+  s->name = name;
+  s->st = st;
+  cudaEventRecord(s->a, st);
+  h->prof_open = 1;
+}
+static inline void rm_prof_end(rm_handle* h) {
+  if (!h->prof_open) return;
+  rm_prof_slot* s = &h->prof_slots[h->prof_n];
+  cudaEventRecord(s->b, s->st);
+  h->prof_n++;
+  h->prof_open = 0;
+}
+#define RM_PROF(h, st, name) rm_prof_begin((h), (cudaStream_t)(st), (name))
 
 // ---- error plumbing --------------------------------------------------------------------------------------------
 static inline int32_t rm_fail(rm_handle* h, int32_t code, const char* fmt, const char* a = "", long long b = 0,
@@ -43,6 +85,7 @@ static inline int32_t rm_fail(rm_handle* h, int32_t code, const char* fmt, const
 #define RM_LAUNCH_CHECK(h)                                                                              \
   do {                                                                                                  \
     (h)->launches++;                                                                                    \
+    rm_prof_end(h);                                                                                     \
     cudaError_t e_ = cudaGetLastError();                                                                \
     if (e_ != cudaSuccess) {                                                                            \
       snprintf((h)->err, sizeof((h)->err), "%s: kernel launch failed: %s", __func__, cudaGetErrorString(e_)); \

@@ -408,24 +408,29 @@ extern "C" int32_t rm_volume_clip_mean(rm_handle* h, const double* raw, double* 
   DeviceGuard dg(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(workspace);   // 4 keys
+  RM_PROF(h, st, "minmax_init_kernel");
   minmax_init_kernel<<<1, 32, 0, st>>>(keys, 1);
   RM_LAUNCH_CHECK(h);
   long long n = (long long)T * hw;
   int grid = (int)((n + 255) / 256 < (long long)h->sm_count * 8 ? (n + 255) / 256 : (long long)h->sm_count * 8);
+  RM_PROF(h, st, "volume_minmax_kernel");
   volume_minmax_kernel<<<grid, 256, 0, st>>>(raw, n, keys);
   RM_LAUNCH_CHECK(h);
   const double* mean_src = raw;
   if (clipped_out) {
+    RM_PROF(h, st, "volume_clip_kernel");
     volume_clip_kernel<<<grid, 256, 0, st>>>(raw, clipped_out, n, keys, threshold);
     RM_LAUNCH_CHECK(h);
     mean_src = clipped_out;
   }
   if (avg_out) {
     int g2 = (int)((hw + 255) / 256);
+    RM_PROF(h, st, "volume_mean0_kernel");
     volume_mean0_kernel<<<g2, 256, 0, st>>>(mean_src, avg_out, T, hw);
     RM_LAUNCH_CHECK(h);
   }
   if (minmax_out) {
+    RM_PROF(h, st, "keys_to_f64_kernel");
     keys_to_f64_kernel<<<1, 32, 0, st>>>(keys, minmax_out, 2);
     RM_LAUNCH_CHECK(h);
   }
@@ -484,9 +489,11 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   if (head_smem > h->smem_optin) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: record too large for shared memory", __func__);
   RM_CUDA(h, cudaFuncSetAttribute(collapse_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head_smem));
   long long hgrid = hp.n_frames < (long long)h->sm_count * 8 ? hp.n_frames : (long long)h->sm_count * 8;
+  RM_PROF(h, st, "collapse_head_kernel");
   collapse_head_kernel<<<(unsigned)hgrid, 256, head_smem, st>>>(hp);
   RM_LAUNCH_CHECK(h);
 
+  RM_PROF(h, st, "minmax_init_kernel");
   minmax_init_kernel<<<div_up(n_clips * 4, 128), 128, 0, st>>>(keys, n_clips);
   RM_LAUNCH_CHECK(h);
 
@@ -518,12 +525,15 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   RM_CUDA(h, cudaFuncSetAttribute(upsample_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RM_CUDA(h, cudaFuncSetAttribute(upsample_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(tp.tiles_x * tp.tiles_y, n_clips);
+  RM_PROF(h, st, "upsample_pass_kernel<1>");
   upsample_pass_kernel<1><<<grid, 256, smem, st>>>(tp);
   RM_LAUNCH_CHECK(h);
+  RM_PROF(h, st, "upsample_pass_kernel<2>");
   upsample_pass_kernel<2><<<grid, 256, smem, st>>>(tp);
   RM_LAUNCH_CHECK(h);
   long long hw = (long long)W * H;
   dim3 ngrid((unsigned)((hw + 255) / 256 < 1024 ? (hw + 255) / 256 : 1024), n_clips);
+  RM_PROF(h, st, "heat_normalise_kernel");
   heat_normalise_kernel<<<ngrid, 256, 0, st>>>(avg, keys, heat_out, minmax_out, n_clips, hw);
   RM_LAUNCH_CHECK(h);
   return RM_OK;

@@ -613,22 +613,28 @@ static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_
   RM_CUDA(h, cudaMemsetAsync(p.eigmax, 0, (size_t)n_clips * 4, st));
   const int roi_px = max_roi_w * max_roi_h;
   dim3 g1(div_up(roi_px, 256) < 64 ? div_up(roi_px, 256) : 64, n_clips);
+  RM_PROF(h, st, "gftt_cov_kernel");
   gftt_cov_kernel<<<g1, 256, 0, st>>>(p);
   RM_LAUNCH_CHECK(h);
+  RM_PROF(h, st, "gftt_eig_kernel");
   gftt_eig_kernel<<<g1, 256, 0, st>>>(p);
   RM_LAUNCH_CHECK(h);
+  RM_PROF(h, st, "gftt_select_kernel");
   gftt_select_kernel<<<n_clips, 256, 0, st>>>(p, pts0);
   RM_LAUNCH_CHECK(h);
   for (int l = 1; l < LK_MAX_LEVELS && l <= h->p.lk_max_level; ++l) {
     dim3 g2(div_up(L.lvl_elems[l], 256) < 32 ? div_up(L.lvl_elems[l], 256) : 32, n_frames, n_clips);
+    RM_PROF(h, st, "lk_pyr_kernel");
     lk_pyr_kernel<<<g2, 256, 0, st>>>(p, l);
     RM_LAUNCH_CHECK(h);
   }
   const int pw = p.win + 3, dwid = p.win + 1;
   const size_t per_warp = (size_t)(((pw * pw + 1) & ~1) + 2 * dwid * dwid) * sizeof(short);
+  RM_PROF(h, st, "lk_track_kernel");
   lk_track_kernel<<<n_clips, LK_WARPS * 32, per_warp * LK_WARPS, st>>>(p, pts0);
   RM_LAUNCH_CHECK(h);
   dim3 g3(div_up(n_frames, 128), n_clips);
+  RM_PROF(h, st, "motion_pca_kernel");
   motion_pca_kernel<<<g3, 128, 0, st>>>(p);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
@@ -661,6 +667,7 @@ extern "C" int32_t rm_measure_average(rm_handle* h, const uint8_t* frames, int32
   if (n_clips == 0) return RM_OK;
   DeviceGuard dg(h->device);
   dim3 grid(n_frames, n_clips);
+  RM_PROF(h, (cudaStream_t)stream, "measure_average_kernel");
   measure_average_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, roi, T, W, H, first_frame, n_frames, data_out);
   RM_LAUNCH_CHECK(h);
   return RM_OK;

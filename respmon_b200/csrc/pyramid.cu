@@ -98,6 +98,8 @@ struct FrontParams {
   double* g_out;           // (n_frames, h[n_steps], w[n_steps]) float64
   long long n_frames;
   long long frame_elems;   // W*H
+  // frame f of the batch is source frame (f / seg_len) * seg_stride + seg_first + f % seg_len: a window of every clip
+  long long seg_len, seg_stride, seg_first;
   int n_steps;             // number of pyrDown steps (= skip_levels_at_top)
   int band_rows;           // level-0 rows per tick
   int n_bands;             // ceil(H / band_rows)
@@ -217,7 +219,8 @@ __global__ void __launch_bounds__(1024, 1) pyramid_front_kernel(const FrontParam
       long long fl = v / p.n_bands;
       int j = (int)(v % p.n_bands);
       long long frame = blockIdx.y + fl * gridDim.y;
-      const T* fsrc = reinterpret_cast<const T*>(p.frames) + frame * p.frame_elems;
+      const long long sframe = (frame / p.seg_len) * p.seg_stride + p.seg_first + frame % p.seg_len;
+      const T* fsrc = reinterpret_cast<const T*>(p.frames) + sframe * p.frame_elems;
       unsigned char* dst = smem + (size_t)(v % FRONT_STAGES) * sg.band_bytes;
       int r_begin = j * p.band_rows;
       int n_rows = min(p.band_rows, p.lh[0] - r_begin);
@@ -384,9 +387,9 @@ extern "C" int32_t rm_to_f64(rm_handle* h, const void* src, int32_t dtype, doubl
   DeviceGuard dg(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   int grid = grid_for(n, 256, h->sm_count);
-  if (dtype == RM_U8) to_f64_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)src, dst, n, 1.0 / 255);
-  else if (dtype == RM_F32) to_f64_kernel<float><<<grid, 256, 0, st>>>((const float*)src, dst, n, 1.0);
-  else if (dtype == RM_F64) to_f64_kernel<double><<<grid, 256, 0, st>>>((const double*)src, dst, n, 1.0);
+  if (dtype == RM_U8) { RM_PROF(h, st, "to_f64_kernel<uint8_t>"); to_f64_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)src, dst, n, 1.0 / 255); }
+  else if (dtype == RM_F32) { RM_PROF(h, st, "to_f64_kernel<float>"); to_f64_kernel<float><<<grid, 256, 0, st>>>((const float*)src, dst, n, 1.0); }
+  else if (dtype == RM_F64) { RM_PROF(h, st, "to_f64_kernel<double>"); to_f64_kernel<double><<<grid, 256, 0, st>>>((const double*)src, dst, n, 1.0); }
   else return rm_fail(h, RM_ERR_INVALID, "%s: unknown dtype", __func__);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
@@ -399,6 +402,7 @@ extern "C" int32_t rm_pyr_down_f64(rm_handle* h, const double* src, double* dst,
   DeviceGuard dg(h->device);
   int dw = (sw + 1) / 2, dh = (sh + 1) / 2;
   int grid = grid_for(n_img * dw * dh, 256, h->sm_count);
+  RM_PROF(h, (cudaStream_t)stream, "pyr_down_f64_kernel");
   pyr_down_f64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, n_img, sw, sh, dw, dh);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
@@ -414,6 +418,7 @@ extern "C" int32_t rm_pyr_up_f64(rm_handle* h, const double* src, double* dst, c
   if (n_img == 0) return RM_OK;
   DeviceGuard dg(h->device);
   int grid = grid_for(n_img * dw * dh, 256, h->sm_count);
+  RM_PROF(h, (cudaStream_t)stream, "pyr_up_f64_kernel");
   pyr_up_f64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, other, mode, n_img, sw, sh, dw, dh);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
@@ -462,13 +467,15 @@ static int32_t launch_front(rm_handle* h, FrontParams& p, int n_strips, cudaStre
   if (gy > p.n_frames) gy = p.n_frames;
   if (gy > 65535) gy = 65535;
   dim3 grid(n_strips, (unsigned)gy);
+  RM_PROF(h, st, sizeof(T) == 1 ? "pyramid_front_kernel<u8>" : (sizeof(T) == 4 ? "pyramid_front_kernel<f32>" : "pyramid_front_kernel<f64>"));
   pyramid_front_kernel<T><<<grid, max_threads, max_smem, st>>>(p);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
 }
 
-extern "C" int32_t rm_pyramid_build(rm_handle* h, const void* frames, int32_t dtype, int64_t n_frames, int32_t W,
-                                    int32_t H, double* lap_out, void* workspace, size_t workspace_bytes, void* stream) {
+static int32_t pyramid_build_impl(rm_handle* h, const void* frames, int32_t dtype, int64_t n_frames, int64_t seg_len,
+                                  int64_t seg_stride, int64_t seg_first, int32_t W, int32_t H, double* lap_out,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
   RM_CHECK_ARG(h, h && frames && lap_out && W >= 1 && H >= 1 && n_frames >= 0, "null pointer or bad size");
   RM_CHECK_ARG(h, dtype == RM_U8 || dtype == RM_F32 || dtype == RM_F64, "unknown dtype");
   const int L = h->p.pyramid_levels, s = h->p.skip_levels_at_top;
@@ -493,6 +500,9 @@ extern "C" int32_t rm_pyramid_build(rm_handle* h, const void* frames, int32_t dt
   fp.g_out = g_skip;
   fp.n_frames = n_frames;
   fp.frame_elems = (long long)W * H;
+  fp.seg_len = seg_len;
+  fp.seg_stride = seg_stride;
+  fp.seg_first = seg_first;
   fp.n_steps = s;
   fp.band_rows = pick_band_rows(W < 704 ? W : 704, elem);
   fp.n_bands = (H + fp.band_rows - 1) / fp.band_rows;
@@ -533,7 +543,23 @@ extern "C" int32_t rm_pyramid_build(rm_handle* h, const void* frames, int32_t dt
                    tail_smem);
   RM_CUDA(h, cudaFuncSetAttribute(pyramid_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem));
   long long tgrid = n_frames < (long long)h->sm_count * 8 ? n_frames : (long long)h->sm_count * 8;
+  RM_PROF(h, st, "pyramid_tail_kernel");
   pyramid_tail_kernel<<<(unsigned)tgrid, 256, tail_smem, st>>>(tp);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
+}
+
+extern "C" int32_t rm_pyramid_build(rm_handle* h, const void* frames, int32_t dtype, int64_t n_frames, int32_t W,
+                                    int32_t H, double* lap_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return pyramid_build_impl(h, frames, dtype, n_frames, n_frames > 0 ? n_frames : 1, 0, 0, W, H, lap_out, workspace,
+                            workspace_bytes, stream);
+}
+
+extern "C" int32_t rm_pyramid_build_clips(rm_handle* h, const void* frames, int32_t dtype, int32_t n_clips, int32_t T,
+                                          int32_t first_frame, int32_t n_frames, int32_t W, int32_t H, double* lap_out,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+  RM_CHECK_ARG(h, h && n_clips >= 0 && T >= 1 && first_frame >= 0 && n_frames >= 1 && first_frame + n_frames <= T,
+               "frame window outside the clip");
+  return pyramid_build_impl(h, frames, dtype, (int64_t)n_clips * n_frames, n_frames, T, first_frame, W, H, lap_out,
+                            workspace, workspace_bytes, stream);
 }

@@ -115,9 +115,11 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
     h->tvals_cap = n_frames;
   }
   p.tvals = h->d_tvals;
+  RM_PROF(h, st, "tvals_kernel");
   tvals_kernel<<<1, 32, 0, st>>>(p.tvals, n_frames, p.dt);
   RM_LAUNCH_CHECK(h);
   dim3 grid(div_up(n_frames, 64), n_clips);
+  RM_PROF(h, st, "signal_bpm_kernel");
   signal_bpm_kernel<<<grid, 64, 0, st>>>(p);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
@@ -128,6 +130,7 @@ extern "C" int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_
   RM_CHECK_ARG(h, h && bpm && roi && status && out && n_clips >= 0 && n_frames >= 1, "null pointer or bad size");
   if (n_clips == 0) return RM_OK;
   DeviceGuard dg(h->device);
+  RM_PROF(h, (cudaStream_t)stream, "pack_results_kernel");
   pack_results_kernel<<<div_up(n_clips, 128), 128, 0, (cudaStream_t)stream>>>(bpm, roi, status, npeaks, n_clips, n_frames, out);
   RM_LAUNCH_CHECK(h);
   return RM_OK;

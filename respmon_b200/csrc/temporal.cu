@@ -213,6 +213,7 @@ extern "C" int32_t rm_temporal_bandpass(rm_handle* h, const double* lap, double*
     RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, temporal_pow2_kernel, TB_WARPS * 32, smem));
     long long grid = (long long)h->sm_count * (occ < 1 ? 1 : occ);
     if (grid > n_groups) grid = n_groups;
+    RM_PROF(h, st, "temporal_pow2_kernel");
     temporal_pow2_kernel<<<(unsigned)grid, TB_WARPS * 32, smem, st>>>(p);
   } else {
     size_t smem = (size_t)2 * T * 8 + (size_t)2 * TB_WARPS * T * 8;
@@ -222,6 +223,7 @@ extern "C" int32_t rm_temporal_bandpass(rm_handle* h, const double* lap, double*
     RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, temporal_direct_kernel, TB_WARPS * 32, smem));
     long long grid = (long long)h->sm_count * (occ < 1 ? 1 : occ);
     if (grid > n_groups) grid = n_groups;
+    RM_PROF(h, st, "temporal_direct_kernel");
     temporal_direct_kernel<<<(unsigned)grid, TB_WARPS * 32, smem, st>>>(p);
   }
   RM_LAUNCH_CHECK(h);

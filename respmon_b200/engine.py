@@ -76,6 +76,24 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.rm_launch_count(self._h))
 
+    def profile(self, on: bool = True):
+        """Bracket every kernel launch with CUDA events on its stream (see rm_profile_enable)."""
+        self.lib.rm_profile_enable(self._h, 1 if on else 0)
+        if on:
+            self.lib.rm_profile_reset(self._h)
+
+    def profile_report(self) -> dict:
+        """{kernel name: (total ms, launches)} since profile(True)."""
+        n = self.lib.rm_profile_collect(self._h)
+        if n < 0:
+            raise _cabi.RmError("rm_profile_collect failed: %s" % self.lib.rm_last_error(self._h).decode())
+        out = {}
+        name, ms, cnt = C.c_char_p(), C.c_double(), C.c_int64()
+        for i in range(n):
+            self.lib.rm_profile_entry(self._h, i, C.byref(name), C.byref(ms), C.byref(cnt))
+            out[name.value.decode()] = (ms.value, cnt.value)
+        return out
+
     def level_sizes(self, W, H, n_levels=None):
         n = n_levels or self.params.pyramid_levels
         buf = (C.c_int32 * (2 * n))()
@@ -164,12 +182,76 @@ class Engine:
         self._call("rm_heatmap", _ptr(bp), n, T, W, H, _ptr(heat), _ptr(minmax), _ptr(ws), ws.numel(), self._stream())
         return heat, minmax
 
-    def calibrate_heatmaps(self, clips: torch.Tensor, fps: float):
-        """clips (n_clips, T, H, W) -> heat maps; the three calibration kernels back to back."""
+    def pyramid_build_clips(self, clips: torch.Tensor, first: int, length: int) -> torch.Tensor:
+        """Packed Laplacian records of frames [first, first+length) of every clip of (n,T,H,W), read in place."""
+        assert clips.is_cuda and clips.is_contiguous() and clips.dtype in _DTYPES and clips.dim() == 4
         n, T, H, W = clips.shape
-        lap = self.pyramid_build(clips)
+        rec = self.record_len(W, H)
+        out = torch.empty((n, length, rec), dtype=torch.float64, device=self.device)
+        need = C.c_size_t()
+        self._call("rm_pyramid_workspace_bytes", W, H, n * length, C.byref(need))
+        ws = self._workspace("pyr", need.value)
+        self._call("rm_pyramid_build_clips", _ptr(clips), _DTYPES[clips.dtype], n, T, first, length, W, H, _ptr(out),
+                   _ptr(ws), ws.numel(), self._stream())
+        return out
+
+    def calibrate_heatmaps(self, clips: torch.Tensor, fps: float, first: int = 0, length: int | None = None):
+        """clips (n_clips, T, H, W) -> heat maps of frames [first, first+length); the calibration kernels back to back."""
+        n, T, H, W = clips.shape
+        length = T - first if length is None else length
+        lap = self.pyramid_build_clips(clips, first, length)
         self.temporal_bandpass(lap, fps, out=lap)
         return self.heatmap(lap, W, H)
+
+    def roi_select(self, heat: torch.Tensor, threshold: int | None = None):
+        """Tail of locate() (base.py:566-575): heat (n,H,W) uint8 -> (roi (n,4) int32 x,y,w,h, status (n,) int32)."""
+        assert heat.is_cuda and heat.is_contiguous() and heat.dtype == torch.uint8 and heat.dim() == 3
+        n, H, W = heat.shape
+        roi = torch.empty((n, 4), dtype=torch.int32, device=self.device)
+        status = torch.empty(n, dtype=torch.int32, device=self.device)
+        need = C.c_size_t()
+        self._call("rm_roi_workspace_bytes", W, H, n, C.byref(need))
+        ws = self._workspace("roi", need.value)
+        thr = self.params.threshold if threshold is None else int(threshold)
+        self._call("rm_roi_select", _ptr(heat), n, W, H, thr, _ptr(roi), _ptr(status), _ptr(ws), ws.numel(),
+                   self._stream())
+        return roi, status
+
+    def locate(self, clips: torch.Tensor, fps: float, first: int = 0, length: int | None = None):
+        """locate() (base.py:547-575) on frames [first, first+length) of every clip of (n,T,H,W).
+        Returns (roi (n,4) int32, status (n,) int32, heat (n,H,W) uint8)."""
+        heat, _ = self.calibrate_heatmaps(clips, fps, first, length)
+        roi, status = self.roi_select(heat)
+        return roi, status, heat
+
+    # ------------------------------------------------------------------ whole clips
+    def run_batch(self, clips: torch.Tensor, fps: float, cal_first: int = 1, cal_len: int = 128,
+                  measure_first: int | None = None, method: str = "flow", keep: bool = False,
+                  out: torch.Tensor | None = None):
+        """The frame routing of run() (base.py:409-513) on a batch of whole clips resident in HBM.
+
+        clips (n,T,H,W) uint8.  Frame 0 is dropped by 'initialize' (base.py:423-425), frames cal_first ..
+        cal_first+cal_len-1 fill the calibration buffer (base.py:429-434), the next frame is consumed by the iteration
+        that runs locate() (base.py:439-448) and every later frame is measured (base.py:464-495).
+        Returns the (n,32) uint8 tensor of rm_result records (and the intermediate tensors when keep=True)."""
+        assert clips.is_cuda and clips.dtype == torch.uint8 and clips.is_contiguous() and clips.dim() == 4
+        n, T, H, W = clips.shape
+        if measure_first is None:
+            measure_first = cal_first + cal_len + 1
+        n_meas = T - measure_first
+        assert cal_first >= 0 and cal_first + cal_len <= T and n_meas >= 1
+        roi, status, heat = self.locate(clips, fps, cal_first, cal_len)
+        if method == "flow":
+            m = self.measure_flow(clips, roi, measure_first, n_meas, status=status)
+            data = m["data"]
+        else:
+            data = self.measure_average(clips, roi, measure_first, n_meas)
+            m = dict(data=data, status=status)
+        sig = self.signal_bpm(data, fps, status=status)
+        rec = self.pack_results(sig["bpm"], roi, status, sig["npeaks"], out=out)
+        if keep:
+            return rec, dict(roi=roi, status=status, heat=heat, **{k: v for k, v in m.items() if k != "status"}, **sig)
+        return rec
 
     # ------------------------------------------------------------------ synthetic data
     def synth_clips(self, specs, dq8: np.ndarray) -> torch.Tensor:
@@ -243,10 +325,12 @@ class Engine:
                    _ptr(status), self._stream())
         return dict(bpm=bpm, filtered=filt, peaks=peaks, npeaks=npk)
 
-    def pack_results(self, bpm, roi, status, npeaks) -> torch.Tensor:
+    def pack_results(self, bpm, roi, status, npeaks, out: torch.Tensor | None = None) -> torch.Tensor:
         """(n,32) uint8 view of rm_result records."""
         n, nf = bpm.shape
-        out = torch.empty((n, 32), dtype=torch.uint8, device=self.device)
+        if out is None:
+            out = torch.empty((n, 32), dtype=torch.uint8, device=self.device)
+        assert out.is_cuda and out.is_contiguous() and out.dtype == torch.uint8 and out.numel() == n * 32
         self._call("rm_pack_results", _ptr(bpm), _ptr(roi.to(self.device, torch.int32).contiguous()), _ptr(status),
                    _ptr(npeaks), n, nf, _ptr(out), self._stream())
         return out

@@ -6,12 +6,20 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def load():
-    so = os.path.join(_HERE, "_signal_host.so")
-    src = os.path.join(_HERE, "signal_host.cpp")
-    hdr = os.path.join(_HERE, "..", "..", "respmon_b200", "csrc", "signal_core.h")
+def _build(name, header):
+    so = os.path.join(_HERE, "_%s.so" % name)
+    src = os.path.join(_HERE, "%s.cpp" % name)
+    hdr = os.path.join(_HERE, "..", "..", "respmon_b200", "csrc", header)
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, src])
-    lib = C.CDLL(so)
+    return C.CDLL(so)
+
+
+def load():
+    lib = _build("signal_host", "signal_core.h")
     lib.host_pca_project_last.restype = C.c_double
     return lib
+
+
+def load_roi():
+    return _build("roi_host", "roi_core.h")

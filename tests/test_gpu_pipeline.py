@@ -1,0 +1,90 @@
+"""GPU parity: device ROI selection and the whole-clip batch path against cv2 / the reference golden vectors."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import clip_from_fixture  # noqa: E402
+from oracle import cpu_path as P  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from respmon_b200.engine import Engine, results_to_numpy  # noqa: F401
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (250, 187), (640, 480), (7, 5), (1, 1)])
+def test_roi_select_matches_cv2_on_random_heat_maps(eng, w, h):
+    import cv2
+    rng = np.random.default_rng(w * 7 + h)
+    n = 12
+    heats = np.zeros((n, h, w), np.uint8)
+    for i in range(n):
+        kind = i % 4
+        if kind == 0:
+            heats[i] = rng.integers(0, 256, (h, w))
+        elif kind == 1:
+            heats[i] = cv2.GaussianBlur(rng.integers(0, 256, (h, w)).astype(np.uint8), (0, 0), 2.0) // 5
+        elif kind == 2:
+            heats[i] = (rng.random((h, w)) < 0.03) * 255
+        # kind 3: all background -> no ROI
+    roi, status = eng.roi_select(dev(heats))
+    roi, status = roi.cpu().numpy(), status.cpu().numpy()
+    for i in range(n):
+        want = P.select_roi(heats[i])
+        if want is None:
+            assert status[i] == 1 and tuple(roi[i]) == (0, 0, 0, 0)
+        else:
+            assert status[i] == 0 and tuple(int(v) for v in roi[i]) == want, (i, roi[i], want)
+
+
+@pytest.mark.parametrize("name", ["vga_s0", "vga_s2", "qvga_s1", "odd_s3"])
+def test_run_batch_matches_reference_golden(eng, golden, name):
+    """One whole clip through calibrate + measure with the reference's frame routing (base.py:409-513)."""
+    from respmon_b200.engine import results_to_numpy
+    fix = golden(name)
+    spec, clip = clip_from_fixture(fix)
+    rec, taps = eng.run_batch(dev(clip[None]), spec.fps, keep=True)
+    r = results_to_numpy(rec)[0]
+    assert (r["x"], r["y"], r["w"], r["h"]) == tuple(int(v) for v in fix["roi"])          # ROI bit-exact
+    assert r["status"] == 0
+    assert abs(r["bpm"] - fix["freq"][-1]) <= 0.5                                          # north-star gate
+    data = taps["data"].cpu().numpy()[0]
+    assert np.sqrt(np.mean((data - fix["data"]) ** 2)) <= 1e-4                             # north-star gate
+    assert r["n_peaks"] == len(fix["peaks"])
+
+
+def test_run_batch_many_clips_match_oracle(eng):
+    """A batch of different clips (incl. device-generated input) against the CPU oracle clip by clip."""
+    from respmon_b200 import synth
+    from respmon_b200.engine import results_to_numpy
+    specs = [synth.clip_spec(s, 320, 240, 256) for s in range(20, 26)]
+    dq8 = np.stack([synth.displacement_q8(s) for s in specs])
+    clips = eng.synth_clips(specs, dq8)
+    rec, taps = eng.run_batch(clips, 10.0, keep=True)
+    recs = results_to_numpy(rec)
+    host = clips.cpu().numpy()
+    n_ok = 0
+    for i, s in enumerate(specs):
+        want = P.run_clip(host[i], fps=10.0)
+        got = recs[i]
+        if want["roi"] is None:
+            assert got["status"] == 1
+            continue
+        assert (got["x"], got["y"], got["w"], got["h"]) == tuple(want["roi"])
+        d = taps["data"].cpu().numpy()[i]
+        assert np.sqrt(np.nanmean((d - np.array(want["data"])) ** 2)) <= 1e-4
+        if want["bpm"] is None:
+            assert np.isnan(got["bpm"]) and got["status"] == 4
+        else:
+            assert abs(got["bpm"] - want["bpm"]) <= 0.5
+            n_ok += 1
+    assert n_ok >= 4
