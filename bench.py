@@ -280,15 +280,14 @@ def run_gpu_arm(args) -> dict | None:
     total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
     kernels = sorted(({"name": k, "ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
                        "share": v[0] / total_kernel_ms} for k, v in prof.items()), key=lambda d: -d["ms_per_step"])
-    lw, lh = eng.level_sizes(W, H)[eng.params.skip_levels_at_top]
-    front = prof.get("pyramid_front_kernel<u8>")
+    front = prof.get("pyramid_front_u8_kernel")
     roofline = None
     if front:
         frames_per_launch = n_clips * 128                     # calibration frames of the batch, one launch per step
-        bytes_per_frame = W * H * 1 + lw * lh * 8             # frame read once (u8) + Gaussian level 4 written (f64)
+        bytes_per_frame = W * H * 1 + (W // 8) * (H // 8) * 4  # frame read once (u8) + Gaussian level 3 written (u32)
         dur_s = front[0] / front[1] / 1e3
         achieved = frames_per_launch * bytes_per_frame / dur_s / 1e9
-        roofline = {"kernel": "pyramid_front_kernel<u8>", "bound": "hbm", "achieved": achieved, "peak": peak,
+        roofline = {"kernel": "pyramid_front_u8_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "bytes_per_launch": frames_per_launch * bytes_per_frame, "launch_ms": dur_s * 1e3,
                     "share_of_step": front[0] / total_kernel_ms}

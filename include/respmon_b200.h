@@ -198,6 +198,10 @@ int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, con
 /* Number of kernel launches this handle has issued since creation (bench.py reports it as gpu_launches). */
 int64_t rm_launch_count(rm_handle* h);
 
+/* Diagnostic switches.  "force_global_lk" (0/1): track from global memory even when the ROI fits shared memory (the
+ * fallback used for ROIs too large to stage; results are identical). */
+int32_t rm_set_option(rm_handle* h, const char* host_name, int64_t value);
+
 /* Per-kernel device timing, the kernel-granular analogue of the reference's tools.Benchmarker (tools.py:60-82): while
  * enabled every launch is bracketed by CUDA events on its own stream.  rm_profile_collect waits for them, folds them into
  * a per-kernel table and returns its size; rm_profile_entry reads row i (name is a static string). */

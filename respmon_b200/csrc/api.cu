@@ -128,6 +128,7 @@ extern "C" int32_t rm_destroy(rm_handle* h) {
     DeviceGuard dg(h->device);
     if (h->d_lut) cudaFree(h->d_lut);
     if (h->d_tvals) cudaFree(h->d_tvals);
+    if (h->d_sig_scratch) cudaFree(h->d_sig_scratch);
     for (int i = 0; i < h->prof_cap; ++i) {
       cudaEventDestroy(h->prof_slots[i].a);
       cudaEventDestroy(h->prof_slots[i].b);
@@ -137,6 +138,13 @@ extern "C" int32_t rm_destroy(rm_handle* h) {
   free(h->prof_table);
   free(h);
   return RM_OK;
+}
+
+extern "C" int32_t rm_set_option(rm_handle* h, const char* name, int64_t value) {
+  if (!h || !name) return RM_ERR_INVALID;
+  if (strcmp(name, "force_global_lk") == 0) { h->force_global_lk = value != 0; return RM_OK; }
+  if (strcmp(name, "force_generic_front") == 0) { h->force_generic_front = value != 0; return RM_OK; }
+  return rm_fail(h, RM_ERR_INVALID, "%s: unknown option", __func__);
 }
 
 // ---------------------------------------------------------------------------------------------------- profiling

@@ -22,6 +22,10 @@ struct rm_handle {
   double* d_tvals;      // running time axis of the measure buffers (base.py:481-484), grown on demand
   int tvals_cap;
   // per-kernel device timing (the reference's tools.Benchmarker tags, tools.py:60-82, at kernel granularity)
+  void* d_sig_scratch;  // measure() scratch (filtered windows, candidate peaks, fit queue), grown on demand
+  size_t sig_scratch_bytes;
+  int force_global_lk;
+  int force_generic_front;  // tests: float64 pyramid front even for uint8 frames the integer front supports  // tests: take the global-memory LK path even when the ROI fits shared memory
   int prof_on;
   int prof_n, prof_cap, prof_open;
   struct rm_prof_slot* prof_slots;

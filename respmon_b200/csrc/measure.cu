@@ -14,6 +14,11 @@
 #include "signal_core.h"
 
 #define LK_MAX_PTS 128
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 #define LK_WARPS 8
 #define LK_MAX_LEVELS 4
 
@@ -267,7 +272,7 @@ __global__ void lk_pyr_kernel(const MeasureParams p, int lvl) {
 }
 
 // ------------------------------------------------------------------------------------------------ LK tracking
-struct LkImg {
+struct LkImg {            // image in global memory, reflect-101 resolved per access (fallback path for huge ROIs)
   const uint8_t* p;
   int w, h, pitch;
   bool lut;
@@ -276,6 +281,12 @@ __device__ __forceinline__ int lk_px(const LkImg& im, const uint8_t* lut, int y,
   const uint8_t v = im.p[(long long)reflect101_multi(y, im.h) * im.pitch + reflect101_multi(x, im.w)];
   return im.lut ? lut[v] : v;
 }
+#define LK_PAD_EXTRA 1    // images staged in shared memory carry a reflect-101 border of win + LK_PAD_EXTRA pixels
+struct LkSImg {           // image in shared memory: LUT applied, border materialised, `p` points at pixel (0,0)
+  const uint8_t* p;
+  int w, h, pitch;
+};
+__device__ __forceinline__ int lk_px(const LkSImg& im, const uint8_t*, int y, int x) { return im.p[y * im.pitch + x]; }
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -284,7 +295,8 @@ __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1)
 
 // One warp tracks one point through all pyramid levels (cv::LKTrackerInvoker).  patch / deriv are per-warp shared
 // scratch: (win+3)^2 ints and (win+1)^2 short2.  Returns status (1 = tracked).
-__device__ int lk_track_point(const MeasureParams& p, const LkImg* prev, const LkImg* next, int nlev,
+template <typename Img>
+__device__ int lk_track_point(const MeasureParams& p, const Img* prev, const Img* next, int nlev,
                               const uint8_t* lut, float px, float py, float* out_x, float* out_y, short* patch,
                               short2* deriv, int lane) {
   const int win = p.win;
@@ -299,8 +311,8 @@ __device__ int lk_track_point(const MeasureParams& p, const LkImg* prev, const L
     float ppx = px * inv, ppy = py * inv;
     if (level == nlev - 1) { nx = ppx; ny = ppy; }
     else { nx = nx * 2.f; ny = ny * 2.f; }
-    const LkImg& I = prev[level];
-    const LkImg& J = next[level];
+    const Img& I = prev[level];
+    const Img& J = next[level];
     ppx -= half; ppy -= half;
     const int ix = (int)floorf(ppx), iy = (int)floorf(ppy);
     if (ix < -win || ix >= I.w || iy < -win || iy >= I.h) {
@@ -491,6 +503,211 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track_kernel(const MeasurePa
   }
 }
 
+// ------------------------------------------------------------------------------------------------ LK tracking, shared memory
+// The production path: the ROI crops of consecutive frames live in shared memory with the LUT applied and a
+// reflect-101 border of win+1 pixels materialised, so the iteration reads pixels without any border arithmetic and
+// never touches global memory.  The crop of frame f+1 is copied in with cp.async while frame f is being tracked; the
+// uint8 pyramid levels (cv2.buildOpticalFlowPyramid) are rebuilt in shared memory per frame.
+#define LKS_WARPS 16
+
+struct LkSmemLayout {
+  int nlev;
+  int lw[LK_MAX_LEVELS], lh[LK_MAX_LEVELS];
+  int pitch[LK_MAX_LEVELS], off[LK_MAX_LEVELS];   // padded pitch / byte offset of padded level l inside one pyramid
+  int pad;
+  int pyr_bytes;                                  // one padded pyramid
+  int raw_pitch, raw_bytes;                       // crop as copied from the frame (columns aligned down/up to 4)
+  int warp_scratch;                               // bytes of patch + derivative scratch per warp
+  int total;
+};
+__host__ __device__ inline LkSmemLayout lk_smem_layout(int rw, int rh, int win, int max_level, int warps) {
+  LkSmemLayout L;
+  L.pad = win + LK_PAD_EXTRA;
+  L.nlev = 1;
+  L.lw[0] = rw; L.lh[0] = rh;
+  while (L.nlev <= max_level && L.nlev < LK_MAX_LEVELS) {
+    const int nw = (L.lw[L.nlev - 1] + 1) / 2, nh = (L.lh[L.nlev - 1] + 1) / 2;
+    if (nw <= win || nh <= win) break;
+    L.lw[L.nlev] = nw; L.lh[L.nlev] = nh;
+    ++L.nlev;
+  }
+  int off = 0;
+  for (int l = 0; l < L.nlev; ++l) {
+    L.pitch[l] = L.lw[l] + 2 * L.pad;
+    L.off[l] = off;
+    off += (L.pitch[l] * (L.lh[l] + 2 * L.pad) + 15) & ~15;
+  }
+  L.pyr_bytes = off;
+  L.raw_pitch = (rw + 3 + 3) & ~3;
+  L.raw_bytes = (L.raw_pitch * rh + 15) & ~15;
+  const int pw = win + 3, dwid = win + 1;
+  L.warp_scratch = (2 * ((pw * pw + 1) & ~1) + 4 * dwid * dwid + 15) & ~15;
+  L.total = 2 * L.pyr_bytes + 2 * L.raw_bytes + warps * L.warp_scratch;
+  return L;
+}
+
+__device__ __forceinline__ void lk_cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const MeasureParams p, const float* pts0,
+                                                                       int max_total) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int clip = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float s_pts[LK_MAX_PTS][2], s_new[LK_MAX_PTS][2];
+  __shared__ int s_st[LK_MAX_PTS];
+  __shared__ int s_n, s_lost;
+  __shared__ uint8_t s_lut[256];
+  int rx, ry, rw, rh;
+  const bool ok = roi_ok(p, clip, rx, ry, rw, rh);
+  float* motion = p.motion + (long long)clip * p.n_frames * 2;
+  if (!ok || p.npts[clip] <= 0) {
+    for (int f = tid; f < p.n_frames; f += blockDim.x) { motion[2 * f] = NAN; motion[2 * f + 1] = NAN; }
+    return;
+  }
+  const LkSmemLayout L = lk_smem_layout(rw, rh, p.win, p.max_level, LKS_WARPS);
+  if (L.total > max_total) return;   // cannot happen: the host sized shared memory for the largest ROI
+  unsigned char* pyr[2] = {smem, smem + L.pyr_bytes};
+  unsigned char* raw[2] = {smem + 2 * L.pyr_bytes, smem + 2 * L.pyr_bytes + L.raw_bytes};
+  short* patch = reinterpret_cast<short*>(smem + 2 * L.pyr_bytes + 2 * L.raw_bytes + (size_t)warp * L.warp_scratch);
+  const int pw = p.win + 3;
+  short2* deriv = reinterpret_cast<short2*>(patch + ((pw * pw + 1) & ~1));
+
+  for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
+  if (tid == 0) { s_n = p.npts[clip]; s_lost = 0; motion[0] = 0.f; motion[1] = 0.f; }
+  for (int i = tid; i < p.npts[clip]; i += blockDim.x) {
+    s_pts[i][0] = pts0[((long long)clip * LK_MAX_PTS + i) * 2];
+    s_pts[i][1] = pts0[((long long)clip * LK_MAX_PTS + i) * 2 + 1];
+  }
+
+  const long long frame_elems = (long long)p.W * p.H;
+  const uint8_t* clip_base = p.frames + ((long long)clip * p.T + p.first_frame) * frame_elems;
+  const int x_al = rx & ~3;
+  const int raw_cols = ((rx + rw + 3) & ~3) - x_al;
+  const bool aligned = (((unsigned long long)p.frames & 3) == 0) && (p.W % 4 == 0) && (frame_elems % 4 == 0);
+  const int xoff = rx - x_al;
+
+  auto stage_raw = [&](int f, int slot) {
+    const uint8_t* src = clip_base + (long long)f * frame_elems + (long long)ry * p.W + x_al;
+    unsigned char* dst = raw[slot];
+    if (aligned) {
+      const int chunks = raw_cols >> 2;
+      for (int c = tid; c < rh * chunks; c += blockDim.x) {
+        const int r = c / chunks, cc = c - r * chunks;
+        lk_cp_async4(dst + r * L.raw_pitch + cc * 4, src + (long long)r * p.W + cc * 4);
+      }
+    } else {
+      for (int c = tid; c < rh * rw; c += blockDim.x) {
+        const int r = c / rw, cc = c - r * rw;
+        dst[r * L.raw_pitch + xoff + cc] = src[(long long)r * p.W + xoff + cc];
+      }
+    }
+    cp_async_commit();
+  };
+  // raw crop -> padded uint8 pyramid (LUT, reflect-101 border; pyrDown levels with their own borders)
+  auto build = [&](int raw_slot, int pyr_slot) {
+    const unsigned char* src = raw[raw_slot] + xoff;
+    unsigned char* base = pyr[pyr_slot];
+    {
+      const int pitch = L.pitch[0], ph = rh + 2 * L.pad, pwid = rw + 2 * L.pad;
+      for (int i = tid; i < ph * pwid; i += blockDim.x) {
+        const int py = i / pwid, px = i - py * pwid;
+        const int y = reflect101_multi(py - L.pad, rh), x = reflect101_multi(px - L.pad, rw);
+        base[L.off[0] + py * pitch + px] = s_lut[src[y * L.raw_pitch + x]];
+      }
+    }
+    __syncthreads();
+    for (int l = 1; l < L.nlev; ++l) {
+      const int spitch = L.pitch[l - 1], dpitch = L.pitch[l];
+      const unsigned char* s0 = base + L.off[l - 1] + L.pad * spitch + L.pad;
+      unsigned char* d0 = base + L.off[l] + L.pad * dpitch + L.pad;
+      const int dw = L.lw[l], dh = L.lh[l];
+      for (int i = tid; i < dw * dh; i += blockDim.x) {
+        const int y = i / dw, x = i - y * dw;
+        const unsigned char* c = s0 + (2 * y - 2) * spitch + 2 * x - 2;
+        int r[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const unsigned char* row = c + k * spitch;
+          r[k] = row[0] + row[4] + 4 * (row[1] + row[3]) + 6 * row[2];
+        }
+        d0[y * dpitch + x] = (unsigned char)((r[0] + r[4] + 4 * (r[1] + r[3]) + 6 * r[2] + 128) >> 8);
+      }
+      __syncthreads();
+      const int ph = dh + 2 * L.pad, pwid = dw + 2 * L.pad;
+      for (int i = tid; i < ph * pwid; i += blockDim.x) {
+        const int py = i / pwid - L.pad, px = i % pwid - L.pad;
+        if (py >= 0 && py < dh && px >= 0 && px < dw) continue;
+        d0[py * dpitch + px] = d0[reflect101_multi(py, dh) * dpitch + reflect101_multi(px, dw)];
+      }
+      __syncthreads();
+    }
+  };
+  auto images = [&](int pyr_slot, LkSImg* out) {
+    for (int l = 0; l < L.nlev; ++l)
+      out[l] = {pyr[pyr_slot] + L.off[l] + L.pad * L.pitch[l] + L.pad, L.lw[l], L.lh[l], L.pitch[l]};
+  };
+
+  stage_raw(0, 0);
+  cp_async_wait<0>();
+  __syncthreads();
+  build(0, 0);
+  if (p.n_frames > 1) stage_raw(1, 1);
+  for (int f = 1; f < p.n_frames; ++f) {
+    cp_async_wait<0>();
+    __syncthreads();
+    build(f & 1, f & 1);
+    if (f + 1 < p.n_frames) stage_raw(f + 1, (f + 1) & 1);   // lands while this frame is tracked
+    LkSImg prev[LK_MAX_LEVELS], next[LK_MAX_LEVELS];
+    images((f - 1) & 1, prev);
+    images(f & 1, next);
+    const int n = s_n;
+    for (int i = warp; i < n; i += LKS_WARPS) {
+      float ox, oy;
+      const int st = lk_track_point(p, prev, next, L.nlev, s_lut, s_pts[i][0], s_pts[i][1], &ox, &oy, patch, deriv, lane);
+      if (lane == 0) { s_new[i][0] = ox; s_new[i][1] = oy; s_st[i] = st; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // good_new = p1[st == 1], good_old = pts[st == 1]; mean(good_old - good_new, axis=0) in float32 (base.py:377-389)
+      int m = 0;
+      float sx = 0.f, sy = 0.f;
+      for (int i = 0; i < n; ++i) {
+        if (s_st[i]) {
+          sx += s_pts[i][0] - s_new[i][0];
+          sy += s_pts[i][1] - s_new[i][1];
+          s_pts[m][0] = s_new[i][0];
+          s_pts[m][1] = s_new[i][1];
+          ++m;
+        }
+      }
+      s_n = m;
+      if (m == 0) {
+        s_lost = 1;
+      } else {
+        motion[2 * f] = sx / (float)m;
+        motion[2 * f + 1] = sy / (float)m;
+      }
+    }
+    __syncthreads();
+    if (p.pts_dbg) {
+      float* dbg = p.pts_dbg + ((long long)clip * p.n_frames + f) * LK_MAX_PTS * 2;
+      for (int i = tid; i < LK_MAX_PTS; i += blockDim.x) {
+        dbg[2 * i] = i < s_n ? s_pts[i][0] : NAN;
+        dbg[2 * i + 1] = i < s_n ? s_pts[i][1] : NAN;
+      }
+    }
+    if (s_lost) {   // tracking lost: extract_motion returns nan from here on (base.py:385-386)
+      for (int g = f + tid; g < p.n_frames; g += blockDim.x) { motion[2 * g] = NAN; motion[2 * g + 1] = NAN; }
+      if (tid == 0) p.status[clip] = RM_CLIP_TRACK_LOST;
+      cp_async_wait<0>();
+      return;
+    }
+  }
+}
+
 // data[f] (base.py:396-407): 0.0 for the first two frames, then the PCA projection of the rolling motion history.
 __global__ void motion_pca_kernel(const MeasureParams p) {
   const int clip = blockIdx.y;
@@ -622,17 +839,27 @@ static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_
   RM_PROF(h, st, "gftt_select_kernel");
   gftt_select_kernel<<<n_clips, 256, 0, st>>>(p, pts0);
   RM_LAUNCH_CHECK(h);
-  for (int l = 1; l < LK_MAX_LEVELS && l <= h->p.lk_max_level; ++l) {
-    dim3 g2(div_up(L.lvl_elems[l], 256) < 32 ? div_up(L.lvl_elems[l], 256) : 32, n_frames, n_clips);
-    RM_PROF(h, st, "lk_pyr_kernel");
-    lk_pyr_kernel<<<g2, 256, 0, st>>>(p, l);
+  const LkSmemLayout SL = lk_smem_layout(max_roi_w, max_roi_h, p.win, p.max_level, LKS_WARPS);
+  if (SL.total + 4096 <= h->smem_optin && !h->force_global_lk) {
+    // production path: crops and their pyramids live in shared memory
+    RM_CUDA(h, cudaFuncSetAttribute(lk_track_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total));
+    RM_PROF(h, st, "lk_track_smem_kernel");
+    lk_track_smem_kernel<<<n_clips, LKS_WARPS * 32, SL.total, st>>>(p, pts0, SL.total);
+    RM_LAUNCH_CHECK(h);
+  } else {
+    // ROI too large for shared memory: pyramids of every frame in the workspace, pixels fetched from global memory
+    for (int l = 1; l < LK_MAX_LEVELS && l <= h->p.lk_max_level; ++l) {
+      dim3 g2(div_up(L.lvl_elems[l], 256) < 32 ? div_up(L.lvl_elems[l], 256) : 32, n_frames, n_clips);
+      RM_PROF(h, st, "lk_pyr_kernel");
+      lk_pyr_kernel<<<g2, 256, 0, st>>>(p, l);
+      RM_LAUNCH_CHECK(h);
+    }
+    const int pw = p.win + 3, dwid = p.win + 1;
+    const size_t per_warp = (size_t)(((pw * pw + 1) & ~1) + 2 * dwid * dwid) * sizeof(short);
+    RM_PROF(h, st, "lk_track_kernel");
+    lk_track_kernel<<<n_clips, LK_WARPS * 32, per_warp * LK_WARPS, st>>>(p, pts0);
     RM_LAUNCH_CHECK(h);
   }
-  const int pw = p.win + 3, dwid = p.win + 1;
-  const size_t per_warp = (size_t)(((pw * pw + 1) & ~1) + 2 * dwid * dwid) * sizeof(short);
-  RM_PROF(h, st, "lk_track_kernel");
-  lk_track_kernel<<<n_clips, LK_WARPS * 32, per_warp * LK_WARPS, st>>>(p, pts0);
-  RM_LAUNCH_CHECK(h);
   dim3 g3(div_up(n_frames, 128), n_clips);
   RM_PROF(h, st, "motion_pca_kernel");
   motion_pca_kernel<<<g3, 128, 0, st>>>(p);

@@ -12,6 +12,7 @@
 //  * pyramid_tail_kernel                      : per frame, G_skip -> G_skip+1..G_top and the Laplacian levels
 //    skip..top-1 that transforms.py:156-170 actually filters, packed into one record per frame.
 #include "common.cuh"
+#include "pyramid_u8.cuh"
 
 // ---------------------------------------------------------------------------------------------------- single level
 __global__ void pyr_down_f64_kernel(const double* __restrict__ src, double* __restrict__ dst, long long n_img, int sw,
@@ -314,7 +315,9 @@ __global__ void __launch_bounds__(1024, 1) pyramid_front_kernel(const FrontParam
 
 // ---------------------------------------------------------------------------------------------------- tail
 struct TailParams {
-  const double* g_in;     // (n_frames, h[first], w[first])
+  const double* g_in;     // (n_frames, h[first], w[first]), or null when the integer front ran:
+  const uint32_t* g3_in;  // (n_frames, h[first-1], w[first-1]) exact integers, level `first` = pyrDown * g_scale
+  double g_scale;
   double* lap_out;        // (n_frames, record_len)
   long long n_frames;
   int first, top;         // G levels first..top are built; Laplacian levels first..top-1 are written
@@ -333,8 +336,28 @@ __global__ void __launch_bounds__(256) pyramid_tail_kernel(const TailParams p) {
   }
   for (long long f = blockIdx.x; f < p.n_frames; f += gridDim.x) {
     const int n0 = p.w[p.first] * p.h[p.first];
-    const double* src = p.g_in + f * n0;
-    for (int i = threadIdx.x; i < n0; i += blockDim.x) g[i] = src[i];
+    if (p.g3_in) {
+      // integer level first-1 -> level first: the sums stay exact in float64 (< 2^53), one scale at the end
+      const int sw = p.w[p.first - 1], sh = p.h[p.first - 1], dw = p.w[p.first], dh = p.h[p.first];
+      uint32_t* s = reinterpret_cast<uint32_t*>(g + acc);     // staged as integers: half the shared memory of float64
+      const uint32_t* src = p.g3_in + f * (long long)(sw * sh);
+      for (int i = threadIdx.x; i < sw * sh; i += blockDim.x) s[i] = src[i];
+      __syncthreads();
+      for (int i = threadIdx.x; i < dw * dh; i += blockDim.x) {
+        int x = i % dw, y = i / dw;
+        double r[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const uint32_t* row = s + reflect101(2 * y + k - 2, sh) * sw;
+          r[k] = tap5((double)row[reflect101(2 * x - 2, sw)], (double)row[reflect101(2 * x - 1, sw)], (double)row[2 * x],
+                      (double)row[reflect101(2 * x + 1, sw)], (double)row[reflect101(2 * x + 2, sw)]);
+        }
+        g[i] = tap5(r[0], r[1], r[2], r[3], r[4]) * p.g_scale;
+      }
+    } else {
+      const double* src = p.g_in + f * n0;
+      for (int i = threadIdx.x; i < n0; i += blockDim.x) g[i] = src[i];
+    }
     __syncthreads();
     for (int l = p.first; l < p.top; ++l) {   // G_{l+1} = pyrDown(G_l)
       const double* s = g + goff[l];
@@ -435,7 +458,9 @@ extern "C" int32_t rm_pyramid_workspace_bytes(rm_handle* h, int32_t W, int32_t H
   RM_CHECK_ARG(h, h && out && W >= 1 && H >= 1 && n_frames >= 0, "null pointer or bad size");
   LevelGeom g = make_geom(W, H, h->p.pyramid_levels);
   int s = h->p.skip_levels_at_top;
-  *out = (size_t)n_frames * g.w[s] * g.h[s] * sizeof(double) + 256;
+  size_t a = (size_t)n_frames * g.w[s] * g.h[s] * sizeof(double);                    // level `skip`, float64
+  size_t b = s >= 1 ? (size_t)n_frames * g.w[s - 1] * g.h[s - 1] * sizeof(uint32_t) : 0;   // level skip-1, integers
+  *out = (a > b ? a : b) + 256;
   return RM_OK;
 }
 
@@ -493,38 +518,49 @@ static int32_t pyramid_build_impl(rm_handle* h, const void* frames, int32_t dtyp
   RecordGeom rec = make_record(g, s);
   double* g_skip = reinterpret_cast<double*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
 
-  const int elem = dtype == RM_U8 ? 1 : (dtype == RM_F32 ? 4 : 8);
-  FrontParams fp;
-  memset(&fp, 0, sizeof(fp));
-  fp.frames = frames;
-  fp.g_out = g_skip;
-  fp.n_frames = n_frames;
-  fp.frame_elems = (long long)W * H;
-  fp.seg_len = seg_len;
-  fp.seg_stride = seg_stride;
-  fp.seg_first = seg_first;
-  fp.n_steps = s;
-  fp.band_rows = pick_band_rows(W < 704 ? W : 704, elem);
-  fp.n_bands = (H + fp.band_rows - 1) / fp.band_rows;
-  for (int l = 0; l <= s; ++l) {
-    fp.lw[l] = g.w[l];
-    fp.lh[l] = g.h[l];
-  }
-  fp.max_final_cols = 40;
-  fp.vec_ok = (((uintptr_t)frames % 16) == 0 && ((long long)W * elem) % 16 == 0 && ((long long)W * H * elem) % 16 == 0);
-  fp.out_scale = 1.0;
-  for (int l = 0; l < s; ++l) fp.out_scale *= 1.0 / 256.0;
-  if (dtype == RM_U8) fp.out_scale *= 1.0 / 255;
-  int n_strips = (g.w[s] + fp.max_final_cols - 1) / fp.max_final_cols;
-  int32_t rc;
-  if (dtype == RM_U8) rc = launch_front<uint8_t>(h, fp, n_strips, st);
-  else if (dtype == RM_F32) rc = launch_front<float>(h, fp, n_strips, st);
-  else rc = launch_front<double>(h, fp, n_strips, st);
-  if (rc != RM_OK) return rc;
+  const bool integer_front = dtype == RM_U8 && !h->force_generic_front && pu_supported(frames, W, H, s);
+  if (integer_front) {
+    int32_t rc = pu_launch(h, (const uint8_t*)frames, reinterpret_cast<uint32_t*>(g_skip), n_frames, seg_len, seg_stride,
+                           seg_first, W, H, st);
+    if (rc != RM_OK) return rc;
+  } else {
+    const int elem = dtype == RM_U8 ? 1 : (dtype == RM_F32 ? 4 : 8);
+    FrontParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.frames = frames;
+    fp.g_out = g_skip;
+    fp.n_frames = n_frames;
+    fp.frame_elems = (long long)W * H;
+    fp.seg_len = seg_len;
+    fp.seg_stride = seg_stride;
+    fp.seg_first = seg_first;
+    fp.n_steps = s;
+    fp.band_rows = pick_band_rows(W < 704 ? W : 704, elem);
+    fp.n_bands = (H + fp.band_rows - 1) / fp.band_rows;
+    for (int l = 0; l <= s; ++l) {
+      fp.lw[l] = g.w[l];
+      fp.lh[l] = g.h[l];
+    }
+    fp.max_final_cols = 40;
+    fp.vec_ok = (((uintptr_t)frames % 16) == 0 && ((long long)W * elem) % 16 == 0 && ((long long)W * H * elem) % 16 == 0);
+    fp.out_scale = 1.0;
+    for (int l = 0; l < s; ++l) fp.out_scale *= 1.0 / 256.0;
+    if (dtype == RM_U8) fp.out_scale *= 1.0 / 255;
+    int n_strips = (g.w[s] + fp.max_final_cols - 1) / fp.max_final_cols;
+    int32_t rc;
+    if (dtype == RM_U8) rc = launch_front<uint8_t>(h, fp, n_strips, st);
+    else if (dtype == RM_F32) rc = launch_front<float>(h, fp, n_strips, st);
+    else rc = launch_front<double>(h, fp, n_strips, st);
+    if (rc != RM_OK) return rc;
 
+  }
   TailParams tp;
   memset(&tp, 0, sizeof(tp));
-  tp.g_in = g_skip;
+  tp.g_in = integer_front ? nullptr : g_skip;
+  tp.g3_in = integer_front ? reinterpret_cast<const uint32_t*>(g_skip) : nullptr;
+  tp.g_scale = 1.0;
+  for (int l = 0; l < s; ++l) tp.g_scale *= 1.0 / 256.0;
+  tp.g_scale *= 1.0 / 255;
   tp.lap_out = lap_out;
   tp.n_frames = n_frames;
   tp.first = s;
@@ -538,6 +574,7 @@ static int32_t pyramid_build_impl(rm_handle* h, const void* frames, int32_t dtyp
   }
   tp.record_len = rec.len;
   int tail_smem = tail_elems * (int)sizeof(double);
+  if (integer_front) tail_smem += g.w[s - 1] * g.h[s - 1] * (int)sizeof(uint32_t);
   if (tail_smem > h->smem_optin)
     return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: level %lld image too large for the tail kernel (%lld B)", __func__, s,
                    tail_smem);

@@ -5,6 +5,7 @@
 // Compiled with -fmad=false.
 #include "common.cuh"
 #include "signal_core.h"
+#include "lm_warp.cuh"
 
 struct SignalParams {
   const double* data;     // (n_clips, n_frames)
@@ -33,35 +34,120 @@ __global__ void tvals_kernel(double* tvals, int n, double dt) {
   }
 }
 
-__global__ void __launch_bounds__(64) signal_bpm_kernel(const SignalParams p) {
+// Stage A, one thread per (clip, frame) window: zero-phase Butterworth (filtfilt) and peakutils.indexes; every
+// candidate peak that find_peaks would hand to gaussian_fit (base.py:318-327) becomes one item of the fit queue.
+#define SIG_MAX_CAND 64   // peaks per window (min_dist >= 1 on <= 128 samples)
+
+struct SignalScratch {
+  double* filt;            // (n_windows, buf_len) filtered windows
+  unsigned char* cand;     // (n_windows, SIG_MAX_CAND) candidate indices
+  unsigned char* acc;      // (n_windows, SIG_MAX_CAND) 1 = accepted by the Gaussian gate
+  int* ncand;              // (n_windows) candidates, or -1 when measure() does not run / raises for this window
+  unsigned* queue;         // fit work items: window * SIG_MAX_CAND + k
+  unsigned* queue_n;
+};
+
+__global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalParams p, const SignalScratch s) {
   const int clip = blockIdx.y;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= p.n_frames) return;
-  double* bpm_out = p.bpm + (long long)clip * p.n_frames + f;
-  const bool last = (f == p.n_frames - 1);
+  const long long win = (long long)clip * p.n_frames + f;
   const bool clip_ok = !p.status || p.status[clip] == RM_CLIP_OK || p.status[clip] == RM_CLIP_TRACK_LOST;
-  int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
+  const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
   const double* data = p.data + (long long)clip * p.n_frames + (f + 1 - n);
-  const double* t = p.tvals + (f + 1 - n);
   bool run = clip_ok && (f + 1 > p.init_len);       // len(self.data) > measure_initialization_length (base.py:489)
   if (run)
     for (int i = 0; i < n; ++i) run &= (data[i] == data[i]);   // a NaN sample means tracking was lost
-  int nacc = 0;
-  double bpm = NAN;
-  double filtered[SC_MAX_WIN];
-  int peaks[SC_MAX_WIN];
+  int ncand = -1;
   if (run) {
-    ScScratch scratch;
-    nacc = sc_measure_window(data, t, n, p.b, p.a, p.nc, p.width, p.thres, p.cutoff, filtered, peaks, &bpm, &scratch);
-    if (nacc < 0) { nacc = 0; run = false; }
+    double filtered[SC_MAX_WIN];
+    double ext[SC_MAX_WIN + 6 * (SC_MAX_ORDER + 1)], dy[SC_MAX_WIN];
+    unsigned char mark[SC_MAX_WIN];
+    int cand[SC_MAX_WIN];
+    if (sc_filtfilt(p.b, p.a, p.nc, data, n, filtered, ext) == 0) {
+      double* fo = s.filt + win * p.buf_len;
+      for (int i = 0; i < n; ++i) fo[i] = filtered[i];
+      ncand = sc_peak_indexes(filtered, n, p.thres, p.width, cand, dy, ext, mark);
+      if (ncand > SIG_MAX_CAND) ncand = SIG_MAX_CAND;
+      for (int k = 0; k < ncand; ++k) {
+        const int idx = cand[k];
+        s.cand[win * SIG_MAX_CAND + k] = (unsigned char)idx;
+        s.acc[win * SIG_MAX_CAND + k] = 0;
+        int w = p.width;                             // base.py:319-323
+        if (idx - p.width < 0) w = idx;
+        if (idx + w > n) w = n - idx;
+        if (2 * w >= 3)                              // fewer points: gaussian_fit raises, the peak is dropped (base.py:336)
+          s.queue[atomicAdd(s.queue_n, 1u)] = (unsigned)(win * SIG_MAX_CAND + k);
+      }
+    }
   }
-  *bpm_out = bpm;
+  s.ncand[win] = ncand;
+}
+
+// Stage B, one warp per queued candidate: the Gaussian gate (lm_warp.cuh).
+__global__ void __launch_bounds__(256) signal_fit_kernel(const SignalParams p, const SignalScratch s) {
+  const int lane = threadIdx.x & 31;
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned total = *s.queue_n;
+  for (unsigned item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += warps) {
+    const unsigned q = s.queue[item];
+    const long long win = q / SIG_MAX_CAND;
+    const int k = q % SIG_MAX_CAND;
+    const int f = (int)(win % p.n_frames);
+    const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
+    const int idx = s.cand[win * SIG_MAX_CAND + k];
+    int w = p.width;
+    if (idx - p.width < 0) w = idx;
+    if (idx + w > n) w = n - idx;
+    int m = 2 * w;
+    if (m > SC_MAX_FIT) m = SC_MAX_FIT;
+    const double* t = p.tvals + (f + 1 - n) + (idx - w);
+    const double* y = s.filt + win * p.buf_len + (idx - w);
+    double xs[LMW_E], ys[LMW_E];
+    double mx = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < LMW_E; ++e) {
+      const int i = lane + 32 * e;
+      xs[e] = i < m ? t[i] : 0.0;
+      ys[e] = i < m ? y[i] : 0.0;
+      if (i < m) mx = fmax(mx, ys[e]);
+    }
+    mx = lmw_max(mx);
+    const double x0 = lmw_bcast(xs[0], 0), x1 = lmw_bcast(xs[0], 1);
+    double par[SC_NP] = {mx, x0, (x1 - x0) * 5.0};   // peakutils.gaussian_fit initial guess
+    const int info = lmw_lmdif_gauss(m, xs, ys, par, lane);
+    if (lane == 0) s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334
+  }
+}
+
+// Stage C, one thread per window: BPM = 60 / mean interval of the accepted peaks (base.py:347-352).
+__global__ void signal_bpm_kernel(const SignalParams p, const SignalScratch s) {
+  const int clip = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= p.n_frames) return;
+  const long long win = (long long)clip * p.n_frames + f;
+  const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
+  const double* t = p.tvals + (f + 1 - n);
+  const int ncand = s.ncand[win];
+  const bool last = (f == p.n_frames - 1);
+  int nacc = 0, prev = -1;
+  double sum = 0.0;
+  for (int k = 0; k < ncand; ++k) {
+    if (!s.acc[win * SIG_MAX_CAND + k]) continue;
+    const int idx = s.cand[win * SIG_MAX_CAND + k];
+    if (nacc > 0) sum += t[idx] - t[prev];
+    prev = idx;
+    if (last && p.peaks) p.peaks[(long long)clip * p.buf_len + nacc] = idx;
+    ++nacc;
+  }
+  p.bpm[win] = nacc >= 2 ? 60.0 / (sum / (double)(nacc - 1)) : NAN;
   if (last) {
     if (p.npeaks) p.npeaks[clip] = nacc;
     if (p.filtered)
-      for (int i = 0; i < p.buf_len; ++i) p.filtered[(long long)clip * p.buf_len + i] = (run && i < n) ? filtered[i] : NAN;
+      for (int i = 0; i < p.buf_len; ++i)
+        p.filtered[(long long)clip * p.buf_len + i] = (ncand >= 0 && i < n) ? s.filt[win * p.buf_len + i] : NAN;
     if (p.peaks)
-      for (int i = 0; i < p.buf_len; ++i) p.peaks[(long long)clip * p.buf_len + i] = (i < nacc) ? peaks[i] : -1;
+      for (int i = nacc; i < p.buf_len; ++i) p.peaks[(long long)clip * p.buf_len + i] = -1;
   }
 }
 
@@ -118,9 +204,34 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
   RM_PROF(h, st, "tvals_kernel");
   tvals_kernel<<<1, 32, 0, st>>>(p.tvals, n_frames, p.dt);
   RM_LAUNCH_CHECK(h);
+  // scratch owned by the handle, grown on demand
+  const size_t n_win = (size_t)n_clips * n_frames;
+  const size_t need = n_win * p.buf_len * 8 + n_win * SIG_MAX_CAND * 2 + n_win * 4 + n_win * SIG_MAX_CAND * 4 + 1024;
+  if (h->sig_scratch_bytes < need) {
+    if (h->d_sig_scratch) cudaFree(h->d_sig_scratch);
+    h->d_sig_scratch = nullptr;
+    h->sig_scratch_bytes = 0;
+    RM_CUDA(h, cudaMalloc(&h->d_sig_scratch, need));
+    h->sig_scratch_bytes = need;
+  }
+  SignalScratch sc;
+  unsigned char* base = reinterpret_cast<unsigned char*>(h->d_sig_scratch);
+  sc.filt = reinterpret_cast<double*>(base);                base += n_win * p.buf_len * 8;
+  sc.queue = reinterpret_cast<unsigned*>(base);             base += n_win * SIG_MAX_CAND * 4;
+  sc.ncand = reinterpret_cast<int*>(base);                  base += n_win * 4;
+  sc.queue_n = reinterpret_cast<unsigned*>(base);           base += 256;
+  sc.cand = base;                                           base += n_win * SIG_MAX_CAND;
+  sc.acc = base;
+  RM_CUDA(h, cudaMemsetAsync(sc.queue_n, 0, 4, st));
   dim3 grid(div_up(n_frames, 64), n_clips);
+  RM_PROF(h, st, "signal_filter_peaks_kernel");
+  signal_filter_peaks_kernel<<<grid, 64, 0, st>>>(p, sc);
+  RM_LAUNCH_CHECK(h);
+  RM_PROF(h, st, "signal_fit_kernel");
+  signal_fit_kernel<<<h->sm_count * 8, 256, 0, st>>>(p, sc);
+  RM_LAUNCH_CHECK(h);
   RM_PROF(h, st, "signal_bpm_kernel");
-  signal_bpm_kernel<<<grid, 64, 0, st>>>(p);
+  signal_bpm_kernel<<<grid, 64, 0, st>>>(p, sc);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
 }

@@ -76,6 +76,9 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.rm_launch_count(self._h))
 
+    def set_option(self, name: str, value: int):
+        self._call("rm_set_option", name.encode(), int(value))
+
     def profile(self, on: bool = True):
         """Bracket every kernel launch with CUDA events on its stream (see rm_profile_enable)."""
         self.lib.rm_profile_enable(self._h, 1 if on else 0)

@@ -68,6 +68,29 @@ def test_pyramid_build_matches_oracle(eng, w, h, dtype):
             assert np.abs(got - lap[l]).max() <= 2e-14, (l, np.abs(got - lap[l]).max())
 
 
+@pytest.mark.parametrize("w,h", [(640, 480), (64, 24), (328, 200), (16, 24), (1280, 720), (232, 136), (1920, 1080)])
+def test_integer_front_is_bit_identical_to_float64_front(eng, w, h):
+    """uint8 frames whose size allows it take the integer (dp4a) front kernel; every sum is exact in both paths, so the
+    packed Laplacian records must agree bit for bit -- including a window of every clip of a batch."""
+    rng = np.random.default_rng(w * 3 + h)
+    n_clips, T = 2, 5
+    clips = rng.integers(0, 256, (n_clips, T, h, w)).astype(np.uint8)
+    clips[0, 0] = 255
+    clips[0, 1] = 0
+    clips[1, 2, :, : w // 2] = 255
+    d = dev(clips)
+    fast = eng.pyramid_build_clips(d, 1, 3).cpu().numpy()
+    eng.set_option("force_generic_front", 1)
+    try:
+        slow = eng.pyramid_build_clips(d, 1, 3).cpu().numpy()
+    finally:
+        eng.set_option("force_generic_front", 0)
+    assert np.array_equal(fast, slow)
+    lap = P.laplacian_levels(P.u8_to_unit(clips[1, 2]), 9)
+    for (l, lw, lh, off) in eng.record_levels(w, h):
+        assert np.abs(fast[1, 1, off:off + lw * lh].reshape(lh, lw) - lap[l]).max() <= 2e-14
+
+
 def test_pyramid_build_golden_taps(eng, golden):
     for name in ("vga_s0", "odd_s3"):
         fix = golden(name)

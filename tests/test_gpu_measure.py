@@ -77,8 +77,10 @@ def test_gftt_matches_cv2_on_random_rois(eng, seed):
     assert np.abs(got - want.reshape(-1, 2)).max() < 1e-3
 
 
-def test_lk_matches_cv2_on_shifted_texture(eng):
+@pytest.mark.parametrize("force_global", [False, True])
+def test_lk_matches_cv2_on_shifted_texture(eng, force_global):
     import cv2
+    eng.set_option("force_global_lk", int(force_global))
     rng = np.random.default_rng(7)
     H, W = 200, 240
     base = cv2.GaussianBlur(rng.integers(0, 256, (H + 8, W + 8)).astype(np.uint8), (0, 0), 2.0)
@@ -98,6 +100,47 @@ def test_lk_matches_cv2_on_shifted_texture(eng):
         p1, st, _ = cv2.calcOpticalFlowPyrLK(crop(f - 1), crop(f), pts, None, **P.LK_PARAMS)
         pts = p1[st == 1].reshape(-1, 1, 2)
         assert np.isnan(got[f][len(pts):]).all()
+        assert np.abs(got[f][:len(pts)] - pts.reshape(-1, 2)).max() < 2e-3
+    eng.set_option("force_global_lk", 0)
+
+
+def test_lk_shared_and_global_paths_agree_bit_for_bit(eng, golden):
+    """The shared-memory tracker (production) and the global-memory fallback (huge ROIs) run the same arithmetic."""
+    fix = golden("vga_s2")
+    spec, clip = clip_from_fixture(fix)
+    roi = fix["roi"].astype(np.int32)[None]
+    nf = spec.n_frames - 130
+    outs = []
+    for force in (0, 1):
+        eng.set_option("force_global_lk", force)
+        o = eng.measure_flow(dev(clip[None]), dev(roi), 130, nf, debug_points=True)
+        outs.append((o["points"].cpu().numpy()[:, 1:], o["motion"].cpu().numpy(), o["data"].cpu().numpy()))
+    eng.set_option("force_global_lk", 0)
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_lk_large_roi_uses_global_path(eng):
+    """An ROI too large for shared memory (whole 640x480 frame) still tracks like cv2."""
+    import cv2
+    rng = np.random.default_rng(11)
+    H, W = 480, 640
+    base = cv2.GaussianBlur(rng.integers(0, 256, (H + 8, W + 8)).astype(np.uint8), (0, 0), 2.5)
+    base = cv2.normalize(base, None, 0, 255, cv2.NORM_MINMAX)
+    frames = []
+    for k in range(3):
+        M = np.float32([[1, 0, 4 + 0.6 * k], [0, 1, 4 + 0.3 * k]])
+        frames.append(cv2.warpAffine(base, M, (W + 8, H + 8), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP)[:H, :W])
+    clip = np.stack(frames)[None].copy()
+    roi = np.array([[0, 0, W, H]], dtype=np.int32)
+    out = eng.measure_flow(dev(clip), dev(roi), 0, 3, debug_points=True)
+    lut = K.lossy_u8_lut()
+    pts = cv2.goodFeaturesToTrack(lut[clip[0, 0]], mask=None, **P.FEATURE_PARAMS)
+    got = out["points"].cpu().numpy()[0]
+    assert int(out["npts"][0]) == len(pts)
+    for f in range(1, 3):
+        p1, st, _ = cv2.calcOpticalFlowPyrLK(lut[clip[0, f - 1]], lut[clip[0, f]], pts, None, **P.LK_PARAMS)
+        pts = p1[st == 1].reshape(-1, 1, 2)
         assert np.abs(got[f][:len(pts)] - pts.reshape(-1, 2)).max() < 2e-3
 
 
