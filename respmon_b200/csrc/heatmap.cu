@@ -32,6 +32,10 @@ __device__ __forceinline__ double up3(int odd, double a, double b, double c) {
 }
 
 // ---------------------------------------------------------------------------------------------------- collapse head
+// Per frame: collapse the band-passed levels last..first (img = pyrUp(img) + level, pyramid.py:53-55) into A_first.
+// The levels below `first` are all-zero in the band-passed pyramid, so the rest of the collapse is pure pyrUp:
+// up_level_kernel takes A_first down to A_2 (UNSCALED: x64 per step, the powers of two are folded into the final
+// scale), the image the two tile passes start from -- 160x120 at 640x480: 153 KB per frame, written once, read twice.
 struct HeadParams {
   const double* bp;     // (n_frames, record_len)
   double* a_out;        // (n_frames, h[first]*w[first])
@@ -41,6 +45,17 @@ struct HeadParams {
   int record_len;
 };
 
+__device__ __forceinline__ double up_at(const double* s, int sw, int sh, int x, int y) {
+  const Tap3 tx = tap3(x, sw), ty = tap3(y, sh);
+  const double* r0 = s + ty.i0 * sw;
+  const double* r1 = s + ty.i1 * sw;
+  const double* r2 = s + ty.i2 * sw;
+  const double h0 = up3(tx.odd, r0[tx.i0], r0[tx.i1], r0[tx.i2]);
+  const double h1 = up3(tx.odd, r1[tx.i0], r1[tx.i1], r1[tx.i2]);
+  const double h2 = up3(tx.odd, r2[tx.i0], r2[tx.i1], r2[tx.i2]);
+  return up3(ty.odd, h0, h1, h2);
+}
+
 __global__ void __launch_bounds__(256) collapse_head_kernel(const HeadParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* a = reinterpret_cast<double*>(smem_raw);
@@ -48,21 +63,13 @@ __global__ void __launch_bounds__(256) collapse_head_kernel(const HeadParams p) 
     const double* src = p.bp + f * p.record_len;
     for (int i = threadIdx.x; i < p.record_len; i += blockDim.x) a[i] = src[i];
     __syncthreads();
-    // img = pyrUp(img) + level, from the coarsest band-passed level down (pyramid.py:53-55); the top level is zeros
     for (int l = p.last - 1; l >= p.first; --l) {
       const double* s = a + p.off[l + 1];
       double* d = a + p.off[l];
       const int sw = p.w[l + 1], sh = p.h[l + 1], dw = p.w[l], dh = p.h[l];
       for (int i = threadIdx.x; i < dw * dh; i += blockDim.x) {
-        int x = i % dw, y = i / dw;
-        Tap3 tx = tap3(x, sw), ty = tap3(y, sh);
-        const double* r0 = s + ty.i0 * sw;
-        const double* r1 = s + ty.i1 * sw;
-        const double* r2 = s + ty.i2 * sw;
-        double h0 = up3(tx.odd, r0[tx.i0], r0[tx.i1], r0[tx.i2]);
-        double h1 = up3(tx.odd, r1[tx.i0], r1[tx.i1], r1[tx.i2]);
-        double h2 = up3(tx.odd, r2[tx.i0], r2[tx.i1], r2[tx.i2]);
-        d[i] = up3(ty.odd, h0, h1, h2) * (1.0 / 64.0) + d[i];
+        const int y = i / dw, x = i - y * dw;
+        d[i] = up_at(s, sw, sh, x, y) * (1.0 / 64.0) + d[i];
       }
       __syncthreads();
     }
@@ -73,19 +80,41 @@ __global__ void __launch_bounds__(256) collapse_head_kernel(const HeadParams p) 
   }
 }
 
+// One unscaled pyrUp step on a stack of images: (n_img, sh, sw) -> (n_img, dh, dw), 4 outputs (a 2x2 block) per thread.
+__global__ void __launch_bounds__(256) up_level_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                                       long long n_img, int sw, int sh, int dw, int dh) {
+  const long long per_img = (long long)sw * sh;        // one thread per source pixel -> outputs (2x, 2y) .. (2x+1, 2y+1)
+  const long long total = n_img * per_img;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long img = idx / per_img;
+    const int r = (int)(idx - img * per_img);
+    const int y = r / sw, x = r - y * sw;
+    const double* s = src + img * per_img;
+    double* d = dst + img * (long long)dw * dh;
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < 2; ++ox) {
+        const int X = 2 * x + ox, Y = 2 * y + oy;
+        if (X < dw && Y < dh) d[(long long)Y * dw + X] = up_at(s, sw, sh, X, Y);
+      }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------- tile passes
-#define HM_TILE 64          // output tile (level 0) is 64x64, 16x16 threads, 4x4 px per thread
-#define HM_MAX_STAGES 4     // shared-memory levels skip-1 .. 2
-#define HM_FR 2             // frames per staging round
+// Both passes evaluate every pixel of every frame from A_2: a thread owns a 4x4 block of level-0 pixels for all T
+// frames of its clip, loads the 4x4 level-2 values around it (L1/L2 hits: neighbouring threads share them) and runs
+// the last two pyrUp steps in registers.  No shared memory, no barriers.
+#define HM_TW 64            // output tile: 64 x 32 level-0 pixels, 16 x 8 threads
+#define HM_TH 32
 
 struct TileParams {
-  const double* a_in;      // (n_clips, T, h[s]*w[s])
+  const double* a2;        // (n_clips, T, h[2]*w[2]) level-2 images, unscaled by 64^(s-2)
   int n_clips, T;
-  int s;                   // number of pyrUp steps (= skip)
-  int w[RM_MAX_LEVELS], h[RM_MAX_LEVELS];
+  int w[3], h[3];          // sizes of levels 0, 1, 2
   int tiles_x, tiles_y;
   double scale;            // 2^(-6 s)
-  // pass 1 out / pass 2 in
   unsigned long long* minmax_keys;   // (n_clips, 4) order-preserving keys: raw min, raw max, avg min, avg max
   double threshold;        // temporal_threshold (pass 2)
   double* avg_out;         // (n_clips, H, W) pass 2
@@ -106,52 +135,13 @@ __host__ __device__ __forceinline__ double key_f64(unsigned long long k) {
 #endif
 }
 
-// ranges of source indices a destination range [o0,o1] (inclusive) touches along one axis of pyrUp
-__host__ __device__ __forceinline__ void src_range(int o0, int o1, int n, int* lo, int* hi) {
-  int a = (o0 >> 1) - 1;
-  if (a < 0) a = 0;
-  int b = (o1 >> 1) + 1;
-  if (b > n - 1) b = n - 1;
-  if (n > 1 && b < 1) b = 1;   // reflect-101 of index -1 is index 1
-  *lo = a;
-  *hi = b;
-}
-
-struct PatchGeom {   // per tile: inclusive index ranges at levels 2..s, patch pitches and shared-memory offsets
-  int x0[RM_MAX_LEVELS], x1[RM_MAX_LEVELS], y0[RM_MAX_LEVELS], y1[RM_MAX_LEVELS];
-  int off[RM_MAX_LEVELS];   // doubles, per frame slot
-  int per_frame;            // doubles per frame slot
-};
-__host__ __device__ inline PatchGeom make_patch(const TileParams& p, int tx, int ty) {
-  PatchGeom g;
-  // level-0 tile
-  int X0 = tx * HM_TILE, Y0 = ty * HM_TILE;
-  int X1 = min(p.w[0], X0 + HM_TILE) - 1, Y1 = min(p.h[0], Y0 + HM_TILE) - 1;
-  int lx0 = X0, lx1 = X1, ly0 = Y0, ly1 = Y1;
-  int acc = 0;
-  for (int l = 1; l <= p.s; ++l) {
-    int a, b, c, d;
-    src_range(lx0, lx1, p.w[l], &a, &b);
-    src_range(ly0, ly1, p.h[l], &c, &d);
-    g.x0[l] = a; g.x1[l] = b; g.y0[l] = c; g.y1[l] = d;
-    lx0 = a; lx1 = b; ly0 = c; ly1 = d;
-    g.off[l] = 0;
-    if (l >= 2 && l < p.s) {
-      g.off[l] = acc;
-      acc += (b - a + 1) * (d - c + 1);
-    }
-  }
-  g.per_frame = acc;
-  return g;
-}
-
 // One axis of the register stage.  A thread owns level-0 outputs 4i..4i+3; they read four level-1 "slots"
 //   m0 = L1[2i-1] (index -1 -> 1), m1 = L1[2i], m2 = L1[min(2i+1, n1-1)], m3 = L1[min(2i+2, n1-1)]
 // and the slots read four level-2 values v0..v3 at indices reflect101(i-1), i, min(i+1,n2-1), min(i+2,n2-1):
 //   m0 = 4(v0+v1)   m1 = v0+6v1+v2   m2 = 4(v1+v2)   m3 = v1+6v2+v3       (pyrUp even/odd taps, App. A.2)
 //   out0 = m0+6m1+m2   out1 = 4(m1+m2)   out2 = m1+6m2+m3   out3 = 4(m2+m3)
 // At the far border the clamped slot is a copy of its neighbour: c2 (m2 := m1), c3 (0: as computed, 1: m3 := m2,
-// 2: m3 := m1).  Everything is statically indexed, so it all lives in registers.
+// 2: m3 := m1); away from the right / bottom image border c2 = c3 = 0 and the selects disappear (EDGE = false).
 struct AxisGeom {
   int v[4];   // level-2 indices (absolute)
   int c2, c3;
@@ -166,13 +156,17 @@ __device__ __forceinline__ AxisGeom axis_geom(int i, int n1, int n2) {
   a.c3 = (2 * i + 2 <= n1 - 1) ? 0 : ((n1 - 1 == 2 * i + 1) ? 1 : 2);
   return a;
 }
+template <bool EDGE>
 __device__ __forceinline__ void slots4(double v0, double v1, double v2, double v3, int c2, int c3, double m[4]) {
   m[0] = 4.0 * (v0 + v1);
   m[1] = fma(6.0, v1, v0 + v2);
-  double m2 = 4.0 * (v1 + v2);
-  m[2] = c2 ? m[1] : m2;
-  double m3 = fma(6.0, v2, v1 + v3);
-  m[3] = (c3 == 0) ? m3 : (c3 == 1 ? m[2] : m[1]);
+  m[2] = 4.0 * (v1 + v2);
+  m[3] = fma(6.0, v2, v1 + v3);
+  if (EDGE) {
+    if (c2) m[2] = m[1];
+    if (c3 == 1) m[3] = m[2];
+    else if (c3 == 2) m[3] = m[1];
+  }
 }
 __device__ __forceinline__ void outs4(const double m[4], double o[4]) {
   o[0] = fma(6.0, m[1], m[0] + m[2]);
@@ -181,32 +175,54 @@ __device__ __forceinline__ void outs4(const double m[4], double o[4]) {
   o[3] = 4.0 * (m[2] + m[3]);
 }
 
-template <int PASS>
-__global__ void __launch_bounds__(256) upsample_pass_kernel(const TileParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sm = reinterpret_cast<double*>(smem_raw);
-  __shared__ double red_a[8], red_b[8];
+// the 4x4 level-0 block of one frame from its 4x4 level-2 neighbourhood
+template <bool EDGE>
+__device__ __forceinline__ void block4x4(const double v[4][4], const AxisGeom& gx, const AxisGeom& gy, double o[4][4]) {
+  double hx[4][4];   // [level-2 row][level-1 x slot]
+#pragma unroll
+  for (int r = 0; r < 4; ++r) slots4<EDGE>(v[r][0], v[r][1], v[r][2], v[r][3], gx.c2, gx.c3, hx[r]);
+  double ox[4][4];   // [level-1 y slot][level-0 x]
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    double m[4];
+    slots4<EDGE>(hx[0][c], hx[1][c], hx[2][c], hx[3][c], gy.c2, gy.c3, m);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) hx[r][c] = m[r];     // now [level-1 y slot][level-1 x slot]
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) outs4(hx[r], ox[r]);
+#pragma unroll
+  for (int kx = 0; kx < 4; ++kx) {
+    const double m[4] = {ox[0][kx], ox[1][kx], ox[2][kx], ox[3][kx]};
+    double col[4];
+    outs4(m, col);
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) o[ky][kx] = col[ky];
+  }
+}
+
+template <int PASS, bool EDGE>
+__device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* red_a, double* red_b) {
   const int tile = blockIdx.x;
   const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
   const int clip = blockIdx.y;
-  const PatchGeom pg = make_patch(p, tx, ty);
-  const int s = p.s;
   const int tid = threadIdx.x;
   const int bx = tid & 15, by = tid >> 4;
-  const int X0 = tx * HM_TILE + 4 * bx, Y0 = ty * HM_TILE + 4 * by;   // my 4x4 output block
+  const int X0 = tx * HM_TW + 4 * bx, Y0 = ty * HM_TH + 4 * by;   // my 4x4 output block
   const bool active = X0 < p.w[0] && Y0 < p.h[0];
-
-  // level-2 source of the register stage: the last shared patch (s > 2) or A_s in global memory (s == 2)
-  const int l2_pitch = (s > 2) ? (pg.x1[2] - pg.x0[2] + 1) : p.w[2];
-  const int l2_x0 = (s > 2) ? pg.x0[2] : 0, l2_y0 = (s > 2) ? pg.y0[2] : 0;
-  AxisGeom gx = axis_geom(active ? (X0 >> 2) : 0, p.w[1], p.w[2]);
-  AxisGeom gy = axis_geom(active ? (Y0 >> 2) : 0, p.h[1], p.h[2]);
+  const AxisGeom gx = axis_geom(active ? (X0 >> 2) : 0, p.w[1], p.w[2]);
+  const AxisGeom gy = axis_geom(active ? (Y0 >> 2) : 0, p.h[1], p.h[2]);
   int offs[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) offs[r][c] = (gy.v[r] - l2_y0) * l2_pitch + (gx.v[c] - l2_x0);
-
+    for (int c = 0; c < 4; ++c) offs[r][c] = gy.v[r] * p.w[2] + gx.v[c];
+  bool okx[4], oky[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    okx[k] = !EDGE || X0 + k < p.w[0];
+    oky[k] = !EDGE || Y0 + k < p.h[0];
+  }
   double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -215,87 +231,60 @@ __global__ void __launch_bounds__(256) upsample_pass_kernel(const TileParams p) 
   double vmin = INFINITY, vmax = -INFINITY;
   double top_s = 0.0, repl_s = 0.0;
   if (PASS == 2) {
-    double lo = key_f64(p.minmax_keys[clip * 4 + 0]), hi = key_f64(p.minmax_keys[clip * 4 + 1]);
+    const double lo = key_f64(p.minmax_keys[clip * 4 + 0]), hi = key_f64(p.minmax_keys[clip * 4 + 1]);
     // transforms.py:185-189 on the scaled values; the comparison runs in the unscaled domain (scale is 2^-k: exact)
-    double top = hi - (hi - lo) * p.threshold;
+    const double top = hi - (hi - lo) * p.threshold;
     top_s = top / p.scale;
     repl_s = lo / p.scale;
   }
-  bool okx[4], oky[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    okx[k] = X0 + k < p.w[0];
-    oky[k] = Y0 + k < p.h[0];
-  }
+  const long long n2 = (long long)p.w[2] * p.h[2];
+  const double* a_clip = p.a2 + (long long)clip * p.T * n2;
 
-  const int n_src = p.w[s] * p.h[s];
-  const double* a_clip = p.a_in + (long long)clip * p.T * n_src;
-
-  for (int t0 = 0; t0 < p.T; t0 += HM_FR) {
-    const int nf = min(HM_FR, p.T - t0);
-    // ---- shared-memory stages: level s (global) -> s-1 -> ... -> 2 (values unscaled: x64 per step) ------------------
-    for (int l = s - 1; l >= 2; --l) {
-      const int pw = pg.x1[l] - pg.x0[l] + 1, ph = pg.y1[l] - pg.y0[l] + 1;
-      const int sw = p.w[l + 1], sh = p.h[l + 1];
-      const bool from_global = (l + 1 == s);
-      const int spitch = from_global ? sw : (pg.x1[l + 1] - pg.x0[l + 1] + 1);
-      const int sx0 = from_global ? 0 : pg.x0[l + 1], sy0 = from_global ? 0 : pg.y0[l + 1];
-      for (int i = tid; i < nf * pw * ph; i += blockDim.x) {
-        int f = i / (pw * ph), r = i - f * pw * ph;
-        int y = r / pw, x = r - y * pw;
-        const double* src = from_global ? a_clip + (long long)(t0 + f) * n_src
-                                        : sm + (size_t)f * pg.per_frame + pg.off[l + 1];
-        Tap3 ax = tap3(pg.x0[l] + x, sw), ay = tap3(pg.y0[l] + y, sh);
-        const double* r0 = src + (ay.i0 - sy0) * spitch - sx0;
-        const double* r1 = src + (ay.i1 - sy0) * spitch - sx0;
-        const double* r2 = src + (ay.i2 - sy0) * spitch - sx0;
-        double h0 = up3(ax.odd, r0[ax.i0], r0[ax.i1], r0[ax.i2]);
-        double h1 = up3(ax.odd, r1[ax.i0], r1[ax.i1], r1[ax.i2]);
-        double h2 = up3(ax.odd, r2[ax.i0], r2[ax.i1], r2[ax.i2]);
-        sm[(size_t)f * pg.per_frame + pg.off[l] + r] = up3(ay.odd, h0, h1, h2);
-      }
-      __syncthreads();
-    }
-    // ---- register stage: level 2 -> 1 -> 0, 4x4 outputs per thread ---------------------------------------------------
-    if (active) {
-      for (int f = 0; f < nf; ++f) {
-        const double* l2 = (s > 2) ? sm + (size_t)f * pg.per_frame + pg.off[2] : a_clip + (long long)(t0 + f) * n_src;
-        double hx[4][4];   // [level-2 row][level-1 x slot]
+  if (active) {
+#pragma unroll 2
+    for (int t = 0; t < p.T; ++t) {
+      const double* l2 = a_clip + t * n2;
+      double v[4][4], o[4][4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-          slots4(l2[offs[r][0]], l2[offs[r][1]], l2[offs[r][2]], l2[offs[r][3]], gx.c2, gx.c3, hx[r]);
-        double l1[4][4];   // [level-1 y slot][level-1 x slot]
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          double m[4];
-          slots4(hx[0][c], hx[1][c], hx[2][c], hx[3][c], gy.c2, gy.c3, m);
+        for (int c = 0; c < 4; ++c) v[r][c] = __ldg(l2 + offs[r][c]);
+      block4x4<EDGE>(v, gx, gy, o);
+      if (PASS == 1) {
+        // Candidate filter on the high words: a new maximum above a positive running maximum is a positive double whose
+        // high word is >= the running one as a signed int; a new minimum below a negative running minimum is a negative
+        // double whose high word is >= the running one as an unsigned int.  The exact float64 update runs only then.
+        int mh = INT_MIN;
+        unsigned nh = 0u;
 #pragma unroll
-          for (int r = 0; r < 4; ++r) l1[r][c] = m[r];
-        }
-        double ox[4][4];   // [level-1 y slot][level-0 x]
+        for (int ky = 0; ky < 4; ++ky)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) outs4(l1[r], ox[r]);
-#pragma unroll
-        for (int kx = 0; kx < 4; ++kx) {
-          double m[4] = {ox[0][kx], ox[1][kx], ox[2][kx], ox[3][kx]};
-          double o[4];
-          outs4(m, o);
-#pragma unroll
-          for (int ky = 0; ky < 4; ++ky) {
-            const double v = o[ky];
-            if (PASS == 1) {
-              if (okx[kx] && oky[ky]) {
-                vmin = fmin(vmin, v);
-                vmax = fmax(vmax, v);
-              }
-            } else {
-              acc[ky][kx] += (v >= top_s) ? repl_s : v;
+          for (int kx = 0; kx < 4; ++kx) {
+            if (okx[kx] && oky[ky]) {
+              const int hw = __double2hiint(o[ky][kx]);
+              mh = max(mh, hw);
+              nh = max(nh, (unsigned)hw);
             }
           }
+        const int thr_max = vmax > 0.0 ? __double2hiint(vmax) : INT_MIN;
+        const unsigned thr_min = vmin < 0.0 ? (unsigned)__double2hiint(vmin) : 0u;
+        if (mh >= thr_max || nh >= thr_min) {
+#pragma unroll
+          for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx)
+              if (okx[kx] && oky[ky]) {
+                vmin = fmin(vmin, o[ky][kx]);
+                vmax = fmax(vmax, o[ky][kx]);
+              }
         }
+      } else {
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 4; ++kx) acc[ky][kx] += (o[ky][kx] >= top_s) ? repl_s : o[ky][kx];
       }
     }
-    __syncthreads();
   }
 
   // ---- epilogue ---------------------------------------------------------------------------------------------------------
@@ -305,16 +294,26 @@ __global__ void __launch_bounds__(256) upsample_pass_kernel(const TileParams p) 
     if (active) {
       double* dst = p.avg_out + (long long)clip * p.w[0] * p.h[0];
 #pragma unroll
-      for (int ky = 0; ky < 4; ++ky)
+      for (int ky = 0; ky < 4; ++ky) {
+        double row[4];
 #pragma unroll
         for (int kx = 0; kx < 4; ++kx) {
+          row[kx] = (acc[ky][kx] * p.scale) / (double)p.T;   // np.average over T (base.py:562)
           if (okx[kx] && oky[ky]) {
-            double avg = (acc[ky][kx] * p.scale) / (double)p.T;   // np.average over T (base.py:562)
-            dst[(long long)(Y0 + ky) * p.w[0] + X0 + kx] = avg;
-            vmin = fmin(vmin, avg);
-            vmax = fmax(vmax, avg);
+            vmin = fmin(vmin, row[kx]);
+            vmax = fmax(vmax, row[kx]);
           }
         }
+        if (!EDGE) {
+          double2* d2 = reinterpret_cast<double2*>(dst + (long long)(Y0 + ky) * p.w[0] + X0);
+          d2[0] = make_double2(row[0], row[1]);
+          d2[1] = make_double2(row[2], row[3]);
+        } else {
+#pragma unroll
+          for (int kx = 0; kx < 4; ++kx)
+            if (okx[kx] && oky[ky]) dst[(long long)(Y0 + ky) * p.w[0] + X0 + kx] = row[kx];
+        }
+      }
     }
   } else {
     vmin *= p.scale;   // exact: power of two
@@ -330,13 +329,23 @@ __global__ void __launch_bounds__(256) upsample_pass_kernel(const TileParams p) 
   if (lane == 0) { red_a[warp] = vmin; red_b[warp] = vmax; }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < 8; ++w) { vmin = fmin(vmin, red_a[w]); vmax = fmax(vmax, red_b[w]); }
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { vmin = fmin(vmin, red_a[w]); vmax = fmax(vmax, red_b[w]); }
     const int base = clip * 4 + (PASS == 1 ? 0 : 2);
     if (vmin <= vmax) {
       atomicMin(&p.minmax_keys[base + 0], f64_key(vmin));
       atomicMax(&p.minmax_keys[base + 1], f64_key(vmax));
     }
   }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(128) upsample_pass_kernel(const TileParams p) {
+  __shared__ double red_a[4], red_b[4];
+  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+  // tiles that touch the right / bottom image border (or an unaligned row) take the guarded variant
+  const bool edge = (tx + 1) * HM_TW >= p.w[0] || (ty + 1) * HM_TH >= p.h[0] || (p.w[0] & 1);
+  if (edge) upsample_pass_body<PASS, true>(p, red_a, red_b);
+  else upsample_pass_body<PASS, false>(p, red_a, red_b);
 }
 
 __global__ void minmax_init_kernel(unsigned long long* keys, int n_clips) {
@@ -441,11 +450,12 @@ extern "C" int32_t rm_volume_clip_mean(rm_handle* h, const double* raw, double* 
 extern "C" int32_t rm_heatmap_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n_clips, int32_t T, size_t* out) {
   RM_CHECK_ARG(h, h && out && W >= 1 && H >= 1 && n_clips >= 0 && T >= 1, "null pointer or bad size");
   LevelGeom g = make_geom(W, H, h->p.pyramid_levels);
-  int s = h->p.skip_levels_at_top;
-  size_t a = (size_t)n_clips * T * g.w[s] * g.h[s] * 8;       // A_skip
+  const int s = h->p.skip_levels_at_top;
+  size_t a = 0;                                                // A_s .. A_2
+  for (int l = 2; l <= s && l < g.n_levels; ++l) a += (((size_t)n_clips * T * g.w[l] * g.h[l] * 8) + 255) & ~(size_t)255;
   size_t avg = (size_t)n_clips * W * H * 8;                    // time average
   size_t keys = (size_t)n_clips * 4 * 8;
-  *out = a + avg + keys + 3 * 256;
+  *out = a + avg + keys + 4 * 256;
   return RM_OK;
 }
 
@@ -453,8 +463,8 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
                               uint8_t* heat_out, double* minmax_out, void* workspace, size_t workspace_bytes, void* stream) {
   RM_CHECK_ARG(h, h && bp && heat_out && n_clips >= 0 && T >= 1 && W >= 1 && H >= 1, "null pointer or bad size");
   const int L = h->p.pyramid_levels, s = h->p.skip_levels_at_top;
-  if (s < 2 || s - 2 > HM_MAX_STAGES || L - 1 <= s || L > RM_MAX_LEVELS)
-    return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: fused heat map needs 2 <= skip <= 6 and skip < levels-1", __func__);
+  if (s < 2 || L - 1 <= s || L > RM_MAX_LEVELS)
+    return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: fused heat map needs skip >= 2 and skip < levels-1", __func__);
   if (n_clips == 0) return RM_OK;
   size_t need = 0;
   rm_heatmap_workspace_bytes(h, W, H, n_clips, T, &need);
@@ -466,17 +476,21 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   LevelGeom g = make_geom(W, H, L);
   RecordGeom rec = make_record(g, s);
   uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
-  double* a_skip = reinterpret_cast<double*>(base);
-  base += ((size_t)n_clips * T * g.w[s] * g.h[s] * 8 + 255) & ~(size_t)255;
+  double* a_lvl[RM_MAX_LEVELS] = {nullptr};
+  for (int l = s; l >= 2; --l) {
+    a_lvl[l] = reinterpret_cast<double*>(base);
+    base += ((size_t)n_clips * T * g.w[l] * g.h[l] * 8 + 255) & ~(size_t)255;
+  }
   double* avg = reinterpret_cast<double*>(base);
   base += ((size_t)n_clips * W * H * 8 + 255) & ~(size_t)255;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
+  const long long n_frames = (long long)n_clips * T;
 
   HeadParams hp;
   memset(&hp, 0, sizeof(hp));
   hp.bp = bp;
-  hp.a_out = a_skip;
-  hp.n_frames = (long long)n_clips * T;
+  hp.a_out = a_lvl[s];
+  hp.n_frames = n_frames;
   hp.first = rec.first;
   hp.last = rec.last;
   for (int l = 0; l < L; ++l) {
@@ -488,10 +502,19 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   int head_smem = rec.len * 8;
   if (head_smem > h->smem_optin) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: record too large for shared memory", __func__);
   RM_CUDA(h, cudaFuncSetAttribute(collapse_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, head_smem));
-  long long hgrid = hp.n_frames < (long long)h->sm_count * 8 ? hp.n_frames : (long long)h->sm_count * 8;
+  long long hgrid = n_frames < (long long)h->sm_count * 8 ? n_frames : (long long)h->sm_count * 8;
   RM_PROF(h, st, "collapse_head_kernel");
   collapse_head_kernel<<<(unsigned)hgrid, 256, head_smem, st>>>(hp);
   RM_LAUNCH_CHECK(h);
+  for (int l = s - 1; l >= 2; --l) {   // A_{l+1} -> A_l, unscaled
+    const long long total = n_frames * g.w[l + 1] * g.h[l + 1];
+    const long long blocks = (total + 255) / 256;
+    const long long cap = (long long)h->sm_count * 32;
+    RM_PROF(h, st, "up_level_kernel");
+    up_level_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(a_lvl[l + 1], a_lvl[l], n_frames, g.w[l + 1],
+                                                                           g.h[l + 1], g.w[l], g.h[l]);
+    RM_LAUNCH_CHECK(h);
+  }
 
   RM_PROF(h, st, "minmax_init_kernel");
   minmax_init_kernel<<<div_up(n_clips * 4, 128), 128, 0, st>>>(keys, n_clips);
@@ -499,37 +522,26 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
 
   TileParams tp;
   memset(&tp, 0, sizeof(tp));
-  tp.a_in = a_skip;
+  tp.a2 = a_lvl[2];
   tp.n_clips = n_clips;
   tp.T = T;
-  tp.s = s;
-  for (int l = 0; l <= s; ++l) {
+  for (int l = 0; l <= 2; ++l) {
     tp.w[l] = g.w[l];
     tp.h[l] = g.h[l];
   }
-  tp.tiles_x = (W + HM_TILE - 1) / HM_TILE;
-  tp.tiles_y = (H + HM_TILE - 1) / HM_TILE;
+  tp.tiles_x = (W + HM_TW - 1) / HM_TW;
+  tp.tiles_y = (H + HM_TH - 1) / HM_TH;
   tp.scale = 1.0;
   for (int l = 0; l < s; ++l) tp.scale *= 1.0 / 64.0;
   tp.minmax_keys = keys;
   tp.threshold = h->p.temporal_threshold;
   tp.avg_out = avg;
-  int max_per_frame = 0;
-  for (int ty = 0; ty < tp.tiles_y; ++ty)
-    for (int tx = 0; tx < tp.tiles_x; ++tx) {
-      PatchGeom pg = make_patch(tp, tx, ty);
-      if (pg.per_frame > max_per_frame) max_per_frame = pg.per_frame;
-    }
-  size_t smem = (size_t)max_per_frame * HM_FR * 8 + 16;
-  if ((int)smem > h->smem_optin) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: patch too large for shared memory", __func__);
-  RM_CUDA(h, cudaFuncSetAttribute(upsample_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RM_CUDA(h, cudaFuncSetAttribute(upsample_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(tp.tiles_x * tp.tiles_y, n_clips);
   RM_PROF(h, st, "upsample_pass_kernel<1>");
-  upsample_pass_kernel<1><<<grid, 256, smem, st>>>(tp);
+  upsample_pass_kernel<1><<<grid, 128, 0, st>>>(tp);
   RM_LAUNCH_CHECK(h);
   RM_PROF(h, st, "upsample_pass_kernel<2>");
-  upsample_pass_kernel<2><<<grid, 256, smem, st>>>(tp);
+  upsample_pass_kernel<2><<<grid, 128, 0, st>>>(tp);
   RM_LAUNCH_CHECK(h);
   long long hw = (long long)W * H;
   dim3 ngrid((unsigned)((hw + 255) / 256 < 1024 ? (hw + 255) / 256 : 1024), n_clips);

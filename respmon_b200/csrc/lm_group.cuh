@@ -1,0 +1,237 @@
+// Group-cooperative Levenberg-Marquardt fit of peakutils' Gaussian model (base.py:327 -> peakutils.gaussian_fit ->
+// scipy.optimize.curve_fit -> MINPACK lmdif), device only.
+//
+// Same algorithm, constants and control flow as the scalar port in signal_core.h (sc_lmdif_gauss, which the host tests
+// pin against SciPy).  A group of LMG lanes works on one fit: the m residuals / Jacobian rows live in the group's slice
+// of shared memory, the O(m) loops (model evaluation, forward-difference Jacobian, Householder QR, Q^T f) are strided
+// over the lanes of the group and their sums are xor-butterfly reductions inside the group (every lane gets the same
+// bits, so the group's control flow stays uniform); the 3x3 trust-region algebra (lmpar, qrsolv) runs redundantly on
+// every lane through the scalar routines.  Several groups share a warp and diverge freely from each other: all
+// collectives carry the group's own lane mask.  Only the summation order differs from MINPACK; the accept / reject
+// decisions of find_peaks (base.py:334-337) are checked against the reference goldens and the oracle on the GPU.
+#pragma once
+#include "signal_core.h"
+
+#define LMG 8   // lanes per fit
+
+struct LmGroup {
+  unsigned mask;   // lanes of this group
+  int sub;         // 0..LMG-1
+};
+
+__device__ __forceinline__ double lmg_sum(const LmGroup& g, double v) {
+#pragma unroll
+  for (int o = LMG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
+  return v;
+}
+__device__ __forceinline__ double lmg_max(const LmGroup& g, double v) {
+#pragma unroll
+  for (int o = LMG / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(g.mask, v, o));
+  return v;
+}
+
+// Euclidean norm of rows from..m-1 of a shared vector (MINPACK enorm; rescaled only outside the safe range)
+__device__ __forceinline__ double lmg_enorm(const LmGroup& g, const double* v, int m, int from) {
+  double mx = 0.0, s = 0.0;
+  for (int i = from + g.sub; i < m; i += LMG) {
+    const double a = fabs(v[i]);
+    mx = fmax(mx, a);
+    s += a * a;
+  }
+  mx = lmg_max(g, mx);
+  if (mx == 0.0) return 0.0;
+  if (mx > 1e-140 && mx < 1e140) return sqrt(lmg_sum(g, s));
+  s = 0.0;
+  for (int i = from + g.sub; i < m; i += LMG) { const double d = fabs(v[i]) / mx; s += d * d; }
+  return mx * sqrt(lmg_sum(g, s));
+}
+
+__device__ __forceinline__ void lmg_resid(const LmGroup& g, int m, const double* xs, const double* ys, const double* p,
+                                          double* f) {
+  const double denom = 2.0 * (p[2] * p[2]) + SC_DBL_EPS;
+  for (int i = g.sub; i < m; i += LMG) {
+    const double d = xs[i] - p[1];
+    f[i] = p[0] * exp(-(d * d) / denom) - ys[i];
+  }
+}
+
+// xs, ys, fvec, wa4 (m each) and fjac (3m, column-major) are the group's shared-memory slices; xs/ys filled by the
+// caller (and visible: the caller syncs the group).  x[3] in/out (uniform over the group).  Returns MINPACK info.
+__device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double* xs, const double* ys, double* x,
+                                            double* fvec, double* wa4, double* fjac) {
+  const int n = SC_NP;
+  const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
+  const int maxfev = 200 * (n + 1);
+  const double epsmch = SC_DBL_EPS, epsfcn = SC_DBL_EPS;
+  const double p1 = 0.1, p5 = 0.5, p25 = 0.25, p75 = 0.75, p0001 = 1e-4;
+  double diag[SC_NP], qtf[SC_NP], wa1[SC_NP], wa2[SC_NP], wa3[SC_NP], sdiag[SC_NP];
+  double r[SC_NP * SC_NP];
+  int ipvt[SC_NP];
+  int info = 0, nfev = 0, iter = 1;
+  double par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0;
+  if (m < n) return 0;
+  lmg_resid(g, m, xs, ys, x, fvec);
+  nfev = 1;
+  double fnorm = lmg_enorm(g, fvec, m, 0);
+  for (;;) {
+    {   // fdjac2: forward differences (each lane differences the rows it evaluated)
+      const double eps = sqrt(epsfcn > epsmch ? epsfcn : epsmch);
+      for (int j = 0; j < n; ++j) {
+        const double temp = x[j];
+        double h = eps * fabs(temp);
+        if (h == 0.0) h = eps;
+        x[j] = temp + h;
+        lmg_resid(g, m, xs, ys, x, wa4);
+        x[j] = temp;
+        for (int i = g.sub; i < m; i += LMG) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
+      }
+      nfev += n;
+    }
+    __syncwarp(g.mask);
+    {   // qrfac with column pivoting; wa1 = rdiag, wa2 = acnorm, wa3 = work
+      for (int j = 0; j < n; ++j) {
+        wa2[j] = lmg_enorm(g, fjac + j * m, m, 0);
+        wa1[j] = wa2[j];
+        wa3[j] = wa1[j];
+        ipvt[j] = j;
+      }
+      for (int j = 0; j < n; ++j) {
+        int kmax = j;
+        for (int k = j; k < n; ++k)
+          if (wa1[k] > wa1[kmax]) kmax = k;
+        if (kmax != j) {
+          for (int i = g.sub; i < m; i += LMG) {
+            const double t = fjac[i + j * m];
+            fjac[i + j * m] = fjac[i + kmax * m];
+            fjac[i + kmax * m] = t;
+          }
+          wa1[kmax] = wa1[j];
+          wa3[kmax] = wa3[j];
+          const int t = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = t;
+          __syncwarp(g.mask);
+        }
+        double ajnorm = lmg_enorm(g, fjac + j * m, m, j);
+        if (ajnorm != 0.0) {
+          if (fjac[j + j * m] < 0.0) ajnorm = -ajnorm;
+          __syncwarp(g.mask);                                   // everyone has read the diagonal element
+          for (int i = j + g.sub; i < m; i += LMG) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
+          __syncwarp(g.mask);
+          const double ajj = fjac[j + j * m];
+          for (int k = j + 1; k < n; ++k) {
+            double part = 0.0;
+            for (int i = j + g.sub; i < m; i += LMG) part += fjac[i + j * m] * fjac[i + k * m];
+            const double temp = lmg_sum(g, part) / ajj;
+            for (int i = j + g.sub; i < m; i += LMG) fjac[i + k * m] -= temp * fjac[i + j * m];
+            __syncwarp(g.mask);
+            if (wa1[k] != 0.0) {
+              double t = fjac[j + k * m] / wa1[k];
+              const double d = 1.0 - t * t;
+              wa1[k] *= sqrt(d > 0.0 ? d : 0.0);
+              t = wa1[k] / wa3[k];
+              if (0.05 * (t * t) <= SC_DBL_EPS) {
+                wa1[k] = lmg_enorm(g, fjac + k * m, m, j + 1);
+                wa3[k] = wa1[k];
+              }
+            }
+          }
+        }
+        wa1[j] = -ajnorm;
+      }
+    }
+    if (iter == 1) {
+      for (int j = 0; j < n; ++j) { diag[j] = wa2[j]; if (wa2[j] == 0.0) diag[j] = 1.0; }
+      for (int j = 0; j < n; ++j) wa3[j] = diag[j] * x[j];
+      xnorm = sc_enorm(n, wa3);
+      delta = factor * xnorm;
+      if (delta == 0.0) delta = factor;
+    }
+    // qtf = first n components of Q^T fvec; R into a private 3x3 (column-major, ldr = 3)
+    for (int i = g.sub; i < m; i += LMG) wa4[i] = fvec[i];
+    __syncwarp(g.mask);
+    for (int j = 0; j < n; ++j) {
+      const double ajj = fjac[j + j * m];
+      if (ajj != 0.0) {
+        double part = 0.0;
+        for (int i = j + g.sub; i < m; i += LMG) part += fjac[i + j * m] * wa4[i];
+        const double temp = -lmg_sum(g, part) / ajj;
+        for (int i = j + g.sub; i < m; i += LMG) wa4[i] += fjac[i + j * m] * temp;
+        __syncwarp(g.mask);
+      }
+      qtf[j] = wa4[j];
+    }
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) r[i + j * SC_NP] = (i == j) ? wa1[j] : fjac[i + j * m];
+    __syncwarp(g.mask);                                          // R and qtf are read before fjac / wa4 change again
+    gnorm = 0.0;
+    if (fnorm != 0.0) {
+      for (int j = 0; j < n; ++j) {
+        const int l = ipvt[j];
+        if (wa2[l] != 0.0) {
+          double sum = 0.0;
+          for (int i = 0; i <= j; ++i) sum += r[i + j * SC_NP] * (qtf[i] / fnorm);
+          const double gg = fabs(sum / wa2[l]);
+          gnorm = gnorm > gg ? gnorm : gg;
+        }
+      }
+    }
+    if (gnorm <= gtol) { info = 4; break; }
+    for (int j = 0; j < n; ++j) diag[j] = diag[j] > wa2[j] ? diag[j] : wa2[j];
+    double ratio = 0.0;
+    do {
+      sc_lmpar(r, SC_NP, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
+      for (int j = 0; j < n; ++j) {
+        wa1[j] = -wa1[j];
+        wa2[j] = x[j] + wa1[j];
+        wa3[j] = diag[j] * wa1[j];
+      }
+      const double pnorm = sc_enorm(n, wa3);
+      if (iter == 1) delta = delta < pnorm ? delta : pnorm;
+      lmg_resid(g, m, xs, ys, wa2, wa4);
+      ++nfev;
+      const double fnorm1 = lmg_enorm(g, wa4, m, 0);
+      double actred = -1.0;
+      if (p1 * fnorm1 < fnorm) { const double d = fnorm1 / fnorm; actred = 1.0 - d * d; }
+      for (int j = 0; j < n; ++j) {
+        wa3[j] = 0.0;
+        const double temp = wa1[ipvt[j]];
+        for (int i = 0; i <= j; ++i) wa3[i] += r[i + j * SC_NP] * temp;
+      }
+      const double temp1 = sc_enorm(n, wa3) / fnorm;
+      const double temp2 = (sqrt(par) * pnorm) / fnorm;
+      const double prered = temp1 * temp1 + temp2 * temp2 / p5;
+      const double dirder = -(temp1 * temp1 + temp2 * temp2);
+      ratio = 0.0;
+      if (prered != 0.0) ratio = actred / prered;
+      if (ratio <= p25) {
+        double temp;
+        if (actred >= 0.0) temp = p5;
+        else temp = p5 * dirder / (dirder + p5 * actred);
+        if (p1 * fnorm1 >= fnorm || temp < p1) temp = p1;
+        const double q = pnorm / p1;
+        delta = temp * (delta < q ? delta : q);
+        par /= temp;
+      } else if (par == 0.0 || ratio >= p75) {
+        delta = pnorm / p5;
+        par = p5 * par;
+      }
+      if (ratio >= p0001) {
+        for (int j = 0; j < n; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
+        for (int i = g.sub; i < m; i += LMG) fvec[i] = wa4[i];   // own rows only: no sync needed
+        xnorm = sc_enorm(n, wa2);
+        fnorm = fnorm1;
+        ++iter;
+      }
+      if (fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0) info = 1;
+      if (delta <= xtol * xnorm) info = 2;
+      if (fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0 && info == 2) info = 3;
+      if (info != 0) break;
+      if (nfev >= maxfev) info = 5;
+      if (fabs(actred) <= epsmch && prered <= epsmch && p5 * ratio <= 1.0) info = 6;
+      if (delta <= epsmch * xnorm) info = 7;
+      if (gnorm <= epsmch) info = 8;
+      if (info != 0) break;
+    } while (ratio < p0001);
+    if (info != 0) break;
+  }
+  return info;
+}

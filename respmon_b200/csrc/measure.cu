@@ -282,11 +282,7 @@ __device__ __forceinline__ int lk_px(const LkImg& im, const uint8_t* lut, int y,
   return im.lut ? lut[v] : v;
 }
 #define LK_PAD_EXTRA 1    // images staged in shared memory carry a reflect-101 border of win + LK_PAD_EXTRA pixels
-struct LkSImg {           // image in shared memory: LUT applied, border materialised, `p` points at pixel (0,0)
-  const uint8_t* p;
-  int w, h, pitch;
-};
-__device__ __forceinline__ int lk_px(const LkSImg& im, const uint8_t*, int y, int x) { return im.p[y * im.pitch + x]; }
+
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -507,8 +503,11 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track_kernel(const MeasurePa
 // The production path: the ROI crops of consecutive frames live in shared memory with the LUT applied and a
 // reflect-101 border of win+1 pixels materialised, so the iteration reads pixels without any border arithmetic and
 // never touches global memory.  The crop of frame f+1 is copied in with cp.async while frame f is being tracked; the
-// uint8 pyramid levels (cv2.buildOpticalFlowPyramid) are rebuilt in shared memory per frame.
+// uint8 pyramid levels (cv2.buildOpticalFlowPyramid) are rebuilt in shared memory per frame.  Everything is addressed
+// by offsets into the one dynamic shared array (keeps the accesses LDS/STS), loops are division free, and the window
+// sums are reduced with REDUX (two 32-bit reductions per exact 64-bit sum).
 #define LKS_WARPS 16
+extern __shared__ __align__(16) unsigned char lks_smem[];
 
 struct LkSmemLayout {
   int nlev;
@@ -546,14 +545,156 @@ __host__ __device__ inline LkSmemLayout lk_smem_layout(int rw, int rh, int win, 
   return L;
 }
 
-__device__ __forceinline__ void lk_cp_async4(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+__device__ __forceinline__ void lk_cp_async4(unsigned smem_addr, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+// exact sum over the warp of per-lane partials |v| < 2^30: two 32-bit REDUX instead of five 64-bit shuffle steps
+__device__ __forceinline__ long long warp_sum_split(int v) {
+  const int lo = v & 0x3fff, hi = v >> 14;
+  return ((long long)__reduce_add_sync(0xffffffffu, hi) << 14) + (long long)__reduce_add_sync(0xffffffffu, lo);
+}
+
+struct LkSLevel {   // one padded level in shared memory: `org` is the offset of pixel (0,0)
+  int org, w, h, pitch;
+};
+
+// One warp tracks one point through the levels (cv::LKTrackerInvoker), images in shared memory.
+// wq[k] = offset (wy * pitch-independent pair) of the lane's k-th window pixel: wy = wq >> 8, wx = wq & 255.
+__device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, const LkSLevel* next, int nlev, float px,
+                               float py, float* out_x, float* out_y, int patch_off, int deriv_off, const int wq[8],
+                               int lane) {
+  const int win = p.win;
+  const int pw = win + 3, dwid = win + 1;
+  const float half = (float)(win - 1) * 0.5f;
+  const float FLT_SCALE = 1.0f / (float)(1 << 20);
+  short* patch = reinterpret_cast<short*>(lks_smem + patch_off);
+  short2* deriv = reinterpret_cast<short2*>(lks_smem + deriv_off);
+  float nx = 0.f, ny = 0.f;
+  int status = 1;
+  for (int level = nlev - 1; level >= 0; --level) {
+    const float inv = (float)(1.0 / (double)(1 << level));
+    float ppx = px * inv, ppy = py * inv;
+    if (level == nlev - 1) { nx = ppx; ny = ppy; }
+    else { nx = nx * 2.f; ny = ny * 2.f; }
+    const LkSLevel I = prev[level];
+    const LkSLevel J = next[level];
+    ppx -= half; ppy -= half;
+    const int ix = (int)floorf(ppx), iy = (int)floorf(ppy);
+    if (ix < -win || ix >= I.w || iy < -win || iy >= I.h) {
+      if (level == 0) status = 0;
+      continue;
+    }
+    float a = ppx - (float)ix, b = ppy - (float)iy;
+    int iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+    int iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+    int iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+    int iw11 = 16384 - iw00 - iw01 - iw10;
+    // stage the (win+3)^2 neighbourhood of the previous image (the border is already in the padded image)
+    __syncwarp();
+    {
+      const unsigned char* src = lks_smem + I.org + (iy - 1) * I.pitch + (ix - 1);
+      int r = 0, c = lane;
+      while (c >= pw) { c -= pw; ++r; }
+      for (int i = lane; i < pw * pw; i += 32) {
+        patch[i] = (short)src[r * I.pitch + c];
+        c += 32;
+        while (c >= pw) { c -= pw; ++r; }
+      }
+    }
+    __syncwarp();
+    // Scharr derivatives (calcScharrDeriv) on the (win+1)^2 positions the window touches; zero outside the image
+    {
+      int y = 0, x = lane;
+      while (x >= dwid) { x -= dwid; ++y; }
+      for (int i = lane; i < dwid * dwid; i += 32) {
+        short2 d = make_short2(0, 0);
+        if (iy + y >= 0 && iy + y < I.h && ix + x >= 0 && ix + x < I.w) {
+          const short* r0 = patch + y * pw + x;          // rows y-1, y, y+1 of the window position -> patch rows y..y+2
+          const short* r1 = r0 + pw;
+          const short* r2 = r1 + pw;
+          const int t0l = (r0[0] + r2[0]) * 3 + r1[0] * 10, t0r = (r0[2] + r2[2]) * 3 + r1[2] * 10;
+          const int t1l = r2[0] - r0[0], t1c = r2[1] - r0[1], t1r = r2[2] - r0[2];
+          d.x = (short)(t0r - t0l);
+          d.y = (short)((t1r + t1l) * 3 + t1c * 10);
+        }
+        deriv[i] = d;
+        x += 32;
+        while (x >= dwid) { x -= dwid; ++y; }
+      }
+    }
+    __syncwarp();
+    int Iw[8], Ixv[8], Iyv[8];
+    int sA11 = 0, sA12 = 0, sA22 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      Iw[k] = 0; Ixv[k] = 0; Iyv[k] = 0;
+      if (wq[k] >= 0) {
+        const int wy = wq[k] >> 8, wx = wq[k] & 255;
+        const short* pr = patch + (wy + 1) * pw + wx + 1;
+        Iw[k] = descale(pr[0] * iw00 + pr[1] * iw01 + pr[pw] * iw10 + pr[pw + 1] * iw11, 9);
+        const short2 d00 = deriv[wy * dwid + wx], d01 = deriv[wy * dwid + wx + 1];
+        const short2 d10 = deriv[(wy + 1) * dwid + wx], d11 = deriv[(wy + 1) * dwid + wx + 1];
+        Ixv[k] = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, 14);
+        Iyv[k] = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, 14);
+        sA11 += Ixv[k] * Ixv[k];      // |Ix| <= 4080: eight products stay far below 2^30
+        sA12 += Ixv[k] * Iyv[k];
+        sA22 += Iyv[k] * Iyv[k];
+      }
+    }
+    const float A11 = (float)warp_sum_split(sA11) * FLT_SCALE, A12 = (float)warp_sum_split(sA12) * FLT_SCALE,
+                A22 = (float)warp_sum_split(sA22) * FLT_SCALE;
+    float D = A11 * A22 - A12 * A12;
+    const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+    if (minEig < p.min_eig || D < 1.1920929e-07f) {
+      if (level == 0) status = 0;
+      continue;
+    }
+    D = 1.f / D;
+    float qx = nx - half, qy = ny - half;
+    float pdx = 0.f, pdy = 0.f;
+    int joff[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) joff[k] = wq[k] >= 0 ? (wq[k] >> 8) * J.pitch + (wq[k] & 255) : 0;
+    for (int j = 0; j < p.max_iter; ++j) {
+      const int jx = (int)floorf(qx), jy = (int)floorf(qy);
+      if (jx < -win || jx >= J.w || jy < -win || jy >= J.h) {
+        if (level == 0) status = 0;
+        break;
+      }
+      a = qx - (float)jx; b = qy - (float)jy;
+      iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+      iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+      iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+      iw11 = 16384 - iw00 - iw01 - iw10;
+      const unsigned char* jp = lks_smem + J.org + jy * J.pitch + jx;
+      int sb1 = 0, sb2 = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (wq[k] >= 0) {
+          const unsigned char* q = jp + joff[k];
+          const int diff = descale(q[0] * iw00 + q[1] * iw01 + q[J.pitch] * iw10 + q[J.pitch + 1] * iw11, 9) - Iw[k];
+          sb1 += diff * Ixv[k];       // |diff| <= 8160, |Ix| <= 4080: eight products stay below 2^30
+          sb2 += diff * Iyv[k];
+        }
+      }
+      const float b1 = (float)warp_sum_split(sb1) * FLT_SCALE, b2 = (float)warp_sum_split(sb2) * FLT_SCALE;
+      const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+      qx += dx; qy += dy;
+      nx = qx + half; ny = qy + half;
+      if ((double)dx * (double)dx + (double)dy * (double)dy <= p.eps2) break;
+      if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+        nx -= dx * 0.5f; ny -= dy * 0.5f;
+        break;
+      }
+      pdx = dx; pdy = dy;
+    }
+  }
+  *out_x = nx; *out_y = ny;
+  return status;
 }
 
 __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const MeasureParams p, const float* pts0,
                                                                        int max_total) {
-  extern __shared__ __align__(16) unsigned char smem[];
   const int clip = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ float s_pts[LK_MAX_PTS][2], s_new[LK_MAX_PTS][2];
@@ -569,17 +710,25 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
   }
   const LkSmemLayout L = lk_smem_layout(rw, rh, p.win, p.max_level, LKS_WARPS);
   if (L.total > max_total) return;   // cannot happen: the host sized shared memory for the largest ROI
-  unsigned char* pyr[2] = {smem, smem + L.pyr_bytes};
-  unsigned char* raw[2] = {smem + 2 * L.pyr_bytes, smem + 2 * L.pyr_bytes + L.raw_bytes};
-  short* patch = reinterpret_cast<short*>(smem + 2 * L.pyr_bytes + 2 * L.raw_bytes + (size_t)warp * L.warp_scratch);
+  const int raw_base = 2 * L.pyr_bytes;
+  const int patch_off = raw_base + 2 * L.raw_bytes + warp * L.warp_scratch;
   const int pw = p.win + 3;
-  short2* deriv = reinterpret_cast<short2*>(patch + ((pw * pw + 1) & ~1));
+  const int deriv_off = patch_off + 2 * ((pw * pw + 1) & ~1);
 
   for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
   if (tid == 0) { s_n = p.npts[clip]; s_lost = 0; motion[0] = 0.f; motion[1] = 0.f; }
   for (int i = tid; i < p.npts[clip]; i += blockDim.x) {
     s_pts[i][0] = pts0[((long long)clip * LK_MAX_PTS + i) * 2];
     s_pts[i][1] = pts0[((long long)clip * LK_MAX_PTS + i) * 2 + 1];
+  }
+  int wq[8];   // the lane's window pixels (wy << 8 | wx), -1 past the end of the window
+  {
+    const int npx = p.win * p.win;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int q = lane + 32 * k;
+      wq[k] = q < npx ? ((q / p.win) << 8) | (q % p.win) : -1;
+    }
   }
 
   const long long frame_elems = (long long)p.W * p.H;
@@ -588,66 +737,95 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
   const int raw_cols = ((rx + rw + 3) & ~3) - x_al;
   const bool aligned = (((unsigned long long)p.frames & 3) == 0) && (p.W % 4 == 0) && (frame_elems % 4 == 0);
   const int xoff = rx - x_al;
+  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(lks_smem);
+
+  // the thread's first element and per-step increments of a block-strided 2-D loop over `cols` columns
+  auto stride2d = [&](int cols, int& r0, int& c0, int& dr, int& dc) {
+    r0 = tid / cols; c0 = tid - r0 * cols;
+    dr = (int)blockDim.x / cols; dc = (int)blockDim.x - dr * cols;
+  };
 
   auto stage_raw = [&](int f, int slot) {
     const uint8_t* src = clip_base + (long long)f * frame_elems + (long long)ry * p.W + x_al;
-    unsigned char* dst = raw[slot];
+    const int dst = raw_base + slot * L.raw_bytes;
     if (aligned) {
       const int chunks = raw_cols >> 2;
-      for (int c = tid; c < rh * chunks; c += blockDim.x) {
-        const int r = c / chunks, cc = c - r * chunks;
-        lk_cp_async4(dst + r * L.raw_pitch + cc * 4, src + (long long)r * p.W + cc * 4);
+      int r, c, dr, dc;
+      stride2d(chunks, r, c, dr, dc);
+      for (; r < rh; r += dr) {
+        lk_cp_async4(smem_base + dst + r * L.raw_pitch + c * 4, src + (long long)r * p.W + c * 4);
+        c += dc;
+        if (c >= chunks) { c -= chunks; ++r; }
       }
     } else {
-      for (int c = tid; c < rh * rw; c += blockDim.x) {
-        const int r = c / rw, cc = c - r * rw;
-        dst[r * L.raw_pitch + xoff + cc] = src[(long long)r * p.W + xoff + cc];
+      int r, c, dr, dc;
+      stride2d(rw, r, c, dr, dc);
+      for (; r < rh; r += dr) {
+        lks_smem[dst + r * L.raw_pitch + xoff + c] = src[(long long)r * p.W + xoff + c];
+        c += dc;
+        if (c >= rw) { c -= rw; ++r; }
       }
     }
     cp_async_commit();
   };
   // raw crop -> padded uint8 pyramid (LUT, reflect-101 border; pyrDown levels with their own borders)
   auto build = [&](int raw_slot, int pyr_slot) {
-    const unsigned char* src = raw[raw_slot] + xoff;
-    unsigned char* base = pyr[pyr_slot];
+    const int src = raw_base + raw_slot * L.raw_bytes + xoff;
+    const int base = pyr_slot * L.pyr_bytes;
     {
       const int pitch = L.pitch[0], ph = rh + 2 * L.pad, pwid = rw + 2 * L.pad;
-      for (int i = tid; i < ph * pwid; i += blockDim.x) {
-        const int py = i / pwid, px = i - py * pwid;
-        const int y = reflect101_multi(py - L.pad, rh), x = reflect101_multi(px - L.pad, rw);
-        base[L.off[0] + py * pitch + px] = s_lut[src[y * L.raw_pitch + x]];
+      int py, pxx, dr, dc;
+      stride2d(pwid, py, pxx, dr, dc);
+      for (; py < ph; py += dr) {
+        const int y = reflect101_multi(py - L.pad, rh), x = reflect101_multi(pxx - L.pad, rw);
+        lks_smem[base + L.off[0] + py * pitch + pxx] = s_lut[lks_smem[src + y * L.raw_pitch + x]];
+        pxx += dc;
+        if (pxx >= pwid) { pxx -= pwid; ++py; }
       }
     }
     __syncthreads();
     for (int l = 1; l < L.nlev; ++l) {
       const int spitch = L.pitch[l - 1], dpitch = L.pitch[l];
-      const unsigned char* s0 = base + L.off[l - 1] + L.pad * spitch + L.pad;
-      unsigned char* d0 = base + L.off[l] + L.pad * dpitch + L.pad;
+      const int s0 = base + L.off[l - 1] + L.pad * spitch + L.pad;
+      const int d0 = base + L.off[l] + L.pad * dpitch + L.pad;
       const int dw = L.lw[l], dh = L.lh[l];
-      for (int i = tid; i < dw * dh; i += blockDim.x) {
-        const int y = i / dw, x = i - y * dw;
-        const unsigned char* c = s0 + (2 * y - 2) * spitch + 2 * x - 2;
-        int r[5];
+      {
+        int y, x, dr, dc;
+        stride2d(dw, y, x, dr, dc);
+        for (; y < dh; y += dr) {
+          const unsigned char* c = lks_smem + s0 + (2 * y - 2) * spitch + 2 * x - 2;
+          int r[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const unsigned char* row = c + k * spitch;
-          r[k] = row[0] + row[4] + 4 * (row[1] + row[3]) + 6 * row[2];
+          for (int k = 0; k < 5; ++k) {
+            const unsigned char* row = c + k * spitch;
+            r[k] = row[0] + row[4] + 4 * (row[1] + row[3]) + 6 * row[2];
+          }
+          lks_smem[d0 + y * dpitch + x] = (unsigned char)((r[0] + r[4] + 4 * (r[1] + r[3]) + 6 * r[2] + 128) >> 8);
+          x += dc;
+          if (x >= dw) { x -= dw; ++y; }
         }
-        d0[y * dpitch + x] = (unsigned char)((r[0] + r[4] + 4 * (r[1] + r[3]) + 6 * r[2] + 128) >> 8);
       }
       __syncthreads();
-      const int ph = dh + 2 * L.pad, pwid = dw + 2 * L.pad;
-      for (int i = tid; i < ph * pwid; i += blockDim.x) {
-        const int py = i / pwid - L.pad, px = i % pwid - L.pad;
-        if (py >= 0 && py < dh && px >= 0 && px < dw) continue;
-        d0[py * dpitch + px] = d0[reflect101_multi(py, dh) * dpitch + reflect101_multi(px, dw)];
+      {
+        const int ph = dh + 2 * L.pad, pwid = dw + 2 * L.pad;
+        int py, pxx, dr, dc;
+        stride2d(pwid, py, pxx, dr, dc);
+        for (; py < ph; py += dr) {
+          const int yy = py - L.pad, xx = pxx - L.pad;
+          if (!(yy >= 0 && yy < dh && xx >= 0 && xx < dw))
+            lks_smem[d0 + yy * dpitch + xx] = lks_smem[d0 + reflect101_multi(yy, dh) * dpitch + reflect101_multi(xx, dw)];
+          pxx += dc;
+          if (pxx >= pwid) { pxx -= pwid; ++py; }
+        }
       }
       __syncthreads();
     }
   };
-  auto images = [&](int pyr_slot, LkSImg* out) {
-    for (int l = 0; l < L.nlev; ++l)
-      out[l] = {pyr[pyr_slot] + L.off[l] + L.pad * L.pitch[l] + L.pad, L.lw[l], L.lh[l], L.pitch[l]};
+  auto levels = [&](int pyr_slot, LkSLevel* out) {
+#pragma unroll
+    for (int l = 0; l < LK_MAX_LEVELS; ++l)
+      if (l < L.nlev)
+        out[l] = {pyr_slot * L.pyr_bytes + L.off[l] + L.pad * L.pitch[l] + L.pad, L.lw[l], L.lh[l], L.pitch[l]};
   };
 
   stage_raw(0, 0);
@@ -660,13 +838,14 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
     __syncthreads();
     build(f & 1, f & 1);
     if (f + 1 < p.n_frames) stage_raw(f + 1, (f + 1) & 1);   // lands while this frame is tracked
-    LkSImg prev[LK_MAX_LEVELS], next[LK_MAX_LEVELS];
-    images((f - 1) & 1, prev);
-    images(f & 1, next);
+    LkSLevel prev[LK_MAX_LEVELS], next[LK_MAX_LEVELS];
+    levels((f - 1) & 1, prev);
+    levels(f & 1, next);
     const int n = s_n;
     for (int i = warp; i < n; i += LKS_WARPS) {
       float ox, oy;
-      const int st = lk_track_point(p, prev, next, L.nlev, s_lut, s_pts[i][0], s_pts[i][1], &ox, &oy, patch, deriv, lane);
+      const int st = lks_track_point(p, prev, next, L.nlev, s_pts[i][0], s_pts[i][1], &ox, &oy, patch_off, deriv_off, wq,
+                                     lane);
       if (lane == 0) { s_new[i][0] = ox; s_new[i][1] = oy; s_st[i] = st; }
     }
     __syncthreads();

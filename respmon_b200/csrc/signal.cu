@@ -5,7 +5,7 @@
 // Compiled with -fmad=false.
 #include "common.cuh"
 #include "signal_core.h"
-#include "lm_warp.cuh"
+#include "lm_group.cuh"
 
 struct SignalParams {
   const double* data;     // (n_clips, n_frames)
@@ -84,40 +84,50 @@ __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalPar
   s.ncand[win] = ncand;
 }
 
-// Stage B, one warp per queued candidate: the Gaussian gate (lm_warp.cuh).
-__global__ void __launch_bounds__(256) signal_fit_kernel(const SignalParams p, const SignalScratch s) {
+// Stage B, one group of LMG lanes per queued candidate: the Gaussian gate, peakutils.gaussian_fit = curve_fit =
+// MINPACK lmdif (lm_group.cuh).  The fit is a long dependent float64 chain, so the stage is latency bound: the lanes
+// of a group share the O(m) work and every fit of the batch is in flight at once.
+#define SIG_FIT_THREADS 128
+__global__ void __launch_bounds__(SIG_FIT_THREADS) signal_fit_kernel(const SignalParams p, const SignalScratch s,
+                                                                      int m_cap) {
+  extern __shared__ __align__(16) double fit_smem[];
   const int lane = threadIdx.x & 31;
-  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  LmGroup g;
+  g.sub = lane & (LMG - 1);
+  g.mask = ((1u << LMG) - 1u) << (lane & ~(LMG - 1));
+  const int group_in_block = threadIdx.x / LMG;
   const unsigned total = *s.queue_n;
-  for (unsigned item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < total; item += warps) {
-    const unsigned q = s.queue[item];
-    const long long win = q / SIG_MAX_CAND;
-    const int k = q % SIG_MAX_CAND;
-    const int f = (int)(win % p.n_frames);
-    const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
-    const int idx = s.cand[win * SIG_MAX_CAND + k];
-    int w = p.width;
-    if (idx - p.width < 0) w = idx;
-    if (idx + w > n) w = n - idx;
-    int m = 2 * w;
-    if (m > SC_MAX_FIT) m = SC_MAX_FIT;
-    const double* t = p.tvals + (f + 1 - n) + (idx - w);
-    const double* y = s.filt + win * p.buf_len + (idx - w);
-    double xs[LMW_E], ys[LMW_E];
-    double mx = -INFINITY;
-#pragma unroll
-    for (int e = 0; e < LMW_E; ++e) {
-      const int i = lane + 32 * e;
-      xs[e] = i < m ? t[i] : 0.0;
-      ys[e] = i < m ? y[i] : 0.0;
-      if (i < m) mx = fmax(mx, ys[e]);
-    }
-    mx = lmw_max(mx);
-    const double x0 = lmw_bcast(xs[0], 0), x1 = lmw_bcast(xs[0], 1);
-    double par[SC_NP] = {mx, x0, (x1 - x0) * 5.0};   // peakutils.gaussian_fit initial guess
-    const int info = lmw_lmdif_gauss(m, xs, ys, par, lane);
-    if (lane == 0) s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334
+  const unsigned item = blockIdx.x * (SIG_FIT_THREADS / LMG) + group_in_block;
+  if (item >= total) return;                          // whole groups leave together
+  double* xs = fit_smem + (size_t)group_in_block * 7 * m_cap;
+  double* ys = xs + m_cap;
+  double* fvec = ys + m_cap;
+  double* wa4 = fvec + m_cap;
+  double* fjac = wa4 + m_cap;
+  const unsigned q = s.queue[item];
+  const long long win = q / SIG_MAX_CAND;
+  const int k = q % SIG_MAX_CAND;
+  const int f = (int)(win % p.n_frames);
+  const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
+  const int idx = s.cand[win * SIG_MAX_CAND + k];
+  int w = p.width;                                   // base.py:319-323
+  if (idx - p.width < 0) w = idx;
+  if (idx + w > n) w = n - idx;
+  int m = 2 * w;
+  if (m > m_cap) m = m_cap;
+  const double* t = p.tvals + (f + 1 - n) + (idx - w);
+  const double* y = s.filt + win * p.buf_len + (idx - w);
+  double mx = -INFINITY;
+  for (int i = g.sub; i < m; i += LMG) {
+    xs[i] = t[i];
+    ys[i] = y[i];
+    mx = fmax(mx, y[i]);
   }
+  mx = lmg_max(g, mx);
+  __syncwarp(g.mask);
+  double par[SC_NP] = {mx, xs[0], (xs[1] - xs[0]) * 5.0};   // peakutils.gaussian_fit initial guess
+  const int info = lmg_lmdif_gauss(g, m, xs, ys, par, fvec, wa4, fjac);
+  if (g.sub == 0) s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334, 336
 }
 
 // Stage C, one thread per window: BPM = 60 / mean interval of the accepted peaks (base.py:347-352).
@@ -227,9 +237,19 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
   RM_PROF(h, st, "signal_filter_peaks_kernel");
   signal_filter_peaks_kernel<<<grid, 64, 0, st>>>(p, sc);
   RM_LAUNCH_CHECK(h);
-  RM_PROF(h, st, "signal_fit_kernel");
-  signal_fit_kernel<<<h->sm_count * 8, 256, 0, st>>>(p, sc);
-  RM_LAUNCH_CHECK(h);
+  {
+    // every window holds at most (buf_len / width + 1) candidates that survive min_dist = width
+    int m_cap = 2 * p.width < SC_MAX_FIT ? 2 * p.width : SC_MAX_FIT;
+    if (m_cap < 4) m_cap = 4;
+    const int groups = SIG_FIT_THREADS / LMG;
+    const size_t fit_smem = (size_t)groups * 7 * m_cap * sizeof(double);
+    const size_t per_win = (size_t)(p.buf_len / (p.width > 0 ? p.width : 1)) + 2;
+    size_t max_items = n_win * (per_win < SIG_MAX_CAND ? per_win : SIG_MAX_CAND);
+    RM_CUDA(h, cudaFuncSetAttribute(signal_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem));
+    RM_PROF(h, st, "signal_fit_kernel");
+    signal_fit_kernel<<<div_up((long long)max_items, groups), SIG_FIT_THREADS, fit_smem, st>>>(p, sc, m_cap);
+    RM_LAUNCH_CHECK(h);
+  }
   RM_PROF(h, st, "signal_bpm_kernel");
   signal_bpm_kernel<<<grid, 64, 0, st>>>(p, sc);
   RM_LAUNCH_CHECK(h);
