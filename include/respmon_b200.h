@@ -106,6 +106,10 @@ typedef struct rm_clip_spec {
 int32_t rm_synth_clips(rm_handle* h, const rm_clip_spec* specs, const int32_t* dq8, int32_t n_clips, uint8_t* out,
                        void* stream);
 
+/* ------------------------------------------------------------------ frame ingest */
+/* cv2.cvtColor(frame, COLOR_BGR2GRAY) of next_frame (base.py:230) on interleaved 8-bit BGR pixels. */
+int32_t rm_bgr_to_gray(rm_handle* h, const uint8_t* bgr, uint8_t* gray_out, int64_t n_pixels, void* stream);
+
 /* ------------------------------------------------------------------ single-level ops (API parity: pyramid.py) */
 /* uint8_to_float (transforms.py:20-23): u8 -> f64 * (1/255); f32 -> f64 widening. */
 int32_t rm_to_f64(rm_handle* h, const void* src, int32_t dtype, double* dst, int64_t n, void* stream);

@@ -298,6 +298,7 @@ def run_clip(frames_u8, fps=10.0, method="flow", fps_limit=10):
                     res["freq"].append(bpm)
     res["t"] = list(tt)
     res["window_data"] = list(data)
+    res["freq_window"] = list(freq)                                          # the `freq` deque as run() leaves it
     res["motion"] = np.array(tracker.motion)
     res["bpm"] = res["freq"][-1] if res["freq"] else None
     return res

@@ -58,6 +58,7 @@ SIGNATURES = {
     "rm_butter_lowpass": (_i32, [_i32, _f64, C.POINTER(_f64), C.POINTER(_f64)]),
     "rm_lossy_u8_lut": (_i32, [C.POINTER(C.c_uint8)]),
     "rm_synth_clips": (_i32, [_H, _P, _P, _i32, _P, _S]),
+    "rm_bgr_to_gray": (_i32, [_H, _P, _P, _i64, _S]),
     "rm_to_f64": (_i32, [_H, _P, _i32, _P, _i64, _S]),
     "rm_pyr_down_f64": (_i32, [_H, _P, _P, _i64, _i32, _i32, _S]),
     "rm_pyr_up_f64": (_i32, [_H, _P, _P, _P, _i32, _i64, _i32, _i32, _i32, _i32, _S]),

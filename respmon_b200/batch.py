@@ -20,6 +20,20 @@ def shard_range(n_clips: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def balance_clips(shapes, world: int) -> list[list[int]]:
+    """Mixed-resolution batches (BASELINE config 5): greedy longest-first assignment of clips to ranks by T*H*W so
+    every GPU streams about the same number of pixels.  shapes: [(T,H,W)] -> per-rank lists of clip indices (sorted)."""
+    cost = [int(t) * int(h) * int(w) for t, h, w in shapes]
+    order = sorted(range(len(shapes)), key=lambda i: (-cost[i], i))
+    load = [0] * world
+    owners = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        owners[r].append(i)
+        load[r] += cost[i]
+    return [sorted(o) for o in owners]
+
+
 def gather_records(local: np.ndarray, counts: list[int] | None = None) -> np.ndarray:
     """All-gather of per-clip result records over the default process group (no-op without one).
 
@@ -36,9 +50,9 @@ def gather_records(local: np.ndarray, counts: list[int] | None = None) -> np.nda
     buf = torch.zeros((cap, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     if len(local):
         buf[:len(local)] = torch.from_numpy(local.view(np.uint8).reshape(len(local), -1).copy()).to(dev)
-    out = torch.empty((world, cap, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    out = torch.empty((world * cap, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(out, buf)
-    out = out.cpu().numpy()
+    out = out.cpu().numpy().reshape(world, cap, RESULT_DTYPE.itemsize)
     return np.concatenate([out[r, :counts[r]].reshape(-1).view(RESULT_DTYPE) for r in range(world)])
 
 
@@ -95,4 +109,20 @@ class BatchMonitor:
             freed[i & 1].record(compute)
         out = records.cpu().numpy().view(RESULT_DTYPE).reshape(-1)   # the device->host read of the step's result
         self.d2h_bytes += records.numel()
+        return out
+
+    def run_mixed(self, clips: list, fps: float, cal_first: int = 1, cal_len: int = 128) -> np.ndarray:
+        """Ragged batch (BASELINE config 5): clips is a list of (T,H,W) uint8 arrays of different sizes.  Clips are
+        grouped into resolution classes (one kernel configuration and one set of level sizes per class) and every
+        class goes through `run`; records come back in the order the clips were given."""
+        classes = {}
+        for i, c in enumerate(clips):
+            classes.setdefault(tuple(c.shape), []).append(i)
+        out = np.zeros(len(clips), RESULT_DTYPE)
+        for shape, idx in sorted(classes.items()):
+            if isinstance(clips[idx[0]], np.ndarray):
+                stack = np.stack([clips[i] for i in idx])
+            else:
+                stack = torch.stack([clips[i] for i in idx])
+            out[idx] = self.run(stack, fps, cal_first=cal_first, cal_len=cal_len)
         return out

@@ -255,3 +255,25 @@ extern "C" int32_t rm_synth_clips(rm_handle* h, const rm_clip_spec* specs, const
   RM_LAUNCH_CHECK(h);
   return RM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- frame ingest
+// cv2.cvtColor(frame, COLOR_BGR2GRAY) on 8-bit frames (next_frame, base.py:230): OpenCV's 15-bit fixed point,
+// gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15 (exhaustively identical to cv2 over all 2^24 colours).
+__global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint8_t* px = bgr + 3 * i;
+    gray[i] = (uint8_t)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + (1u << 14)) >> 15);
+  }
+}
+
+extern "C" int32_t rm_bgr_to_gray(rm_handle* h, const uint8_t* bgr, uint8_t* gray_out, int64_t n_pixels, void* stream) {
+  RM_CHECK_ARG(h, h && bgr && gray_out && n_pixels >= 0, "null pointer or bad size");
+  if (n_pixels == 0) return RM_OK;
+  DeviceGuard dg(h->device);
+  const long long want = (n_pixels + 255) / 256;
+  const int blocks = (int)(want < (long long)h->sm_count * 8 ? want : (long long)h->sm_count * 8);
+  RM_PROF(h, (cudaStream_t)stream, "bgr_to_gray_kernel");
+  bgr_to_gray_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(bgr, gray_out, n_pixels);
+  RM_LAUNCH_CHECK(h);
+  return RM_OK;
+}

@@ -120,6 +120,15 @@ class Engine:
             off += w * h
         return out
 
+    # ------------------------------------------------------------------ frame ingest
+    def bgr_to_gray(self, bgr: torch.Tensor) -> torch.Tensor:
+        """(..., H, W, 3) uint8 BGR -> (..., H, W) uint8 gray   [cv2.cvtColor in next_frame, base.py:230]"""
+        assert bgr.is_cuda and bgr.dtype == torch.uint8 and bgr.shape[-1] == 3
+        bgr = bgr.contiguous()
+        out = torch.empty(bgr.shape[:-1], dtype=torch.uint8, device=self.device)
+        self._call("rm_bgr_to_gray", _ptr(bgr), _ptr(out), out.numel(), self._stream())
+        return out
+
     # ------------------------------------------------------------------ single-level ops
     def to_f64(self, x: torch.Tensor) -> torch.Tensor:
         x = x.contiguous()
@@ -205,6 +214,20 @@ class Engine:
         lap = self.pyramid_build_clips(clips, first, length)
         self.temporal_bandpass(lap, fps, out=lap)
         return self.heatmap(lap, W, H)
+
+    def volume_clip_mean(self, raw: torch.Tensor, threshold: float | None = None, want_clipped=True, want_avg=True):
+        """Tail of eulerian_magnification_bandpass on a materialised (T,H,W) float64 volume (transforms.py:184-192)
+        and the time average of base.py:562 -> (clipped or None, avg or None, (min, max) tensor)."""
+        assert raw.is_cuda and raw.is_contiguous() and raw.dtype == torch.float64 and raw.dim() == 3
+        T, H, W = raw.shape
+        thr = self.params.temporal_threshold if threshold is None else float(threshold)
+        clipped = torch.empty_like(raw) if want_clipped else None
+        avg = torch.empty((H, W), dtype=torch.float64, device=self.device) if want_avg else None
+        mm = torch.empty(2, dtype=torch.float64, device=self.device)
+        ws = self._workspace("vol", 256)
+        self._call("rm_volume_clip_mean", _ptr(raw), _ptr(clipped), _ptr(avg), _ptr(mm), T, H * W, thr, _ptr(ws),
+                   self._stream())
+        return clipped, avg, mm
 
     def roi_select(self, heat: torch.Tensor, threshold: int | None = None):
         """Tail of locate() (base.py:566-575): heat (n,H,W) uint8 -> (roi (n,4) int32 x,y,w,h, status (n,) int32)."""

@@ -1,0 +1,122 @@
+"""GPU parity: the RespiratoryMonitor drop-in (respmon_b200/monitor.py) against the attributes the UNMODIFIED reference
+left behind on the same clips (tests/golden/*.npz, made by tools/make_golden.py from base.RespiratoryMonitor)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import clip_from_fixture  # noqa: E402
+
+CASES = ["vga_s0", "vga_s2", "qvga_s1", "odd_s3", "qvga_long_s4"]
+
+
+def _check(rm, fix):
+    assert (rm.x, rm.y, rm.w, rm.h) == tuple(int(v) for v in fix["roi"])                  # ROI bit-exact
+    data = np.array(rm.data)
+    assert data.shape == fix["data"].shape
+    assert np.sqrt(np.mean((data - fix["data"]) ** 2)) <= 1e-4                             # north-star gate
+    np.testing.assert_allclose(np.array(rm.t), fix["t"], rtol=0, atol=1e-12)
+    assert len(rm.freq) == len(fix["freq"])
+    assert np.max(np.abs(np.array(rm.freq) - fix["freq"])) <= 0.5                          # north-star gate
+    assert [int(v) for v in rm.peak_indices] == [int(v) for v in fix["peaks"]]
+    np.testing.assert_allclose(np.asarray(rm.filtered_data), fix["filtered"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(np.asarray(rm.peak_times), np.take(fix["t"], fix["peaks"]), rtol=0, atol=1e-12)
+    motion = np.array(rm.motion_data, dtype=np.float32)
+    assert motion.shape == fix["motion"].shape
+    assert np.max(np.abs(motion - fix["motion"])) <= 1e-3
+    assert rm.state == "measure"
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_monitor_matches_reference_attributes(golden, name):
+    from respmon_b200.monitor import RespiratoryMonitor
+    fix = golden(name)
+    spec, clip = clip_from_fixture(fix)
+    rm = RespiratoryMonitor(clip, visualize=None, save_all_data=False, motion_extraction_method="flow", fps_limit=10)
+    _check(rm, fix)
+
+
+def test_monitor_accepts_a_capture_object_with_bgr_frames(golden):
+    """cv2.VideoCapture-like source returning BGR frames (base.py:227-231 converts with cv2.cvtColor)."""
+    from respmon_b200.monitor import RespiratoryMonitor
+    fix = golden("qvga_s1")
+    spec, clip = clip_from_fixture(fix)
+
+    class Cap:
+        def __init__(self):
+            self.i = 0
+
+        def get(self, prop):
+            return {5: 10, 3: spec.width, 4: spec.height}.get(prop, 0)
+
+        def isOpened(self):
+            return True
+
+        def read(self):
+            if self.i >= len(clip):
+                return False, None
+            self.i += 1
+            return True, np.repeat(clip[self.i - 1][:, :, None], 3, axis=2)
+
+        def release(self):
+            pass
+
+    rm = RespiratoryMonitor(Cap(), visualize=None, save_all_data=False, motion_extraction_method="flow")
+    _check(rm, fix)
+
+
+def test_bgr_to_gray_matches_cv2():
+    import cv2
+    from respmon_b200.engine import Engine
+    eng = Engine(0)
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    got = eng.bgr_to_gray(torch.from_numpy(img).cuda()).cpu().numpy()
+    assert np.array_equal(got, cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    eng.close()
+
+
+def test_locate_static_method_and_stepwise_api(golden):
+    """locate() on the reference's own float64 calibration buffer, then calibrate()/measure() called by hand."""
+    from respmon_b200.monitor import RespiratoryMonitor
+    fix = golden("qvga_s1")
+    spec, clip = clip_from_fixture(fix)
+    vid = clip[1:129] * (1.0 / 255)                                         # transforms.uint8_to_float
+    assert RespiratoryMonitor.locate(vid, 10, freq_min=0.1, freq_max=1.0, temporal_threshold=0.7,
+                                     threshold=20) == tuple(int(v) for v in fix["roi"])
+    rm = RespiratoryMonitor(clip, motion_extraction_method="flow", autorun=False)
+    assert rm.next_frame().shape == (spec.height, spec.width)              # 'initialize' drops frame 0
+    assert rm.calibrate() == tuple(int(v) for v in fix["roi"])
+    vals = rm.extract_motion()
+    assert np.sqrt(np.mean((np.array(vals) - fix["data"]) ** 2)) <= 1e-4
+    rm.data.extend(vals)
+    rm.t.extend(fix["t"].tolist())
+    rm.measure()
+    assert abs(rm.freq[-1] - fix["freq"][-1]) <= 0.5
+    assert [int(v) for v in rm.peak_indices] == [int(v) for v in fix["peaks"]]
+    idx, _ = rm.find_peaks()
+    assert idx == [int(v) for v in fix["peaks"]]
+
+
+def test_skip_calibration_and_average_mode(golden):
+    from respmon_b200.monitor import RespiratoryMonitor
+    fix = golden("qvga_s1")
+    spec, clip = clip_from_fixture(fix)
+    x, y, w, h = (int(v) for v in fix["roi"])
+    rm = RespiratoryMonitor(clip, motion_extraction_method="average", autorun=False)
+    rm.skip_calibration(x, y, w, h)                                         # base.py:166-172
+    rm.run()
+    want = np.array([np.average(clip[f, y:y + h, x:x + w] * (1.0 / 255)) for f in range(len(clip))])
+    got = np.array(rm.data)
+    assert len(got) == 128                                                  # rolled at measure_buffer_length
+    np.testing.assert_allclose(got, want[-128:], rtol=0, atol=1e-12)
+
+
+def test_no_roi_retries_and_stream_end():
+    """A static clip has no band-passed energy: locate() returns None and calibration restarts (base.py:451-454)."""
+    from respmon_b200.monitor import RespiratoryMonitor
+    clip = np.full((300, 48, 64), 90, np.uint8)
+    rm = RespiratoryMonitor(clip, motion_extraction_method="flow")
+    assert rm.state == "calibration" and rm.x is None and len(rm.data) == 0
+    assert rm.calibration_buffer_idx == 300 - 1 - 2 * 129                   # frames left in the third fill

@@ -1,0 +1,118 @@
+"""CPU-only tests of the host-side logic: constructor contract of the drop-in, clip sharding, and the N>1 result
+gather over a world_size-2 gloo group (the data path has no collective; this is the only one -- SURVEY.md 8e)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_constructor_asserts_like_the_reference():
+    """base.py:24-34: bad arguments raise AssertionError before anything else happens."""
+    from respmon_b200.monitor import RespiratoryMonitor
+    clip = np.zeros((4, 8, 8), np.uint8)
+    for kw in (dict(fps_limit=0), dict(fps_limit="10"), dict(save_calibration_image=1), dict(visualize="matplotlib"),
+               dict(fig_size=(1, 2, 3)), dict(error_reset_delay=-1), dict(save_all_data=None),
+               dict(motion_extraction_method="lk")):
+        with pytest.raises(AssertionError):
+            RespiratoryMonitor(clip, **kw)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_a_gpu():
+    from respmon_b200.engine import Engine
+    from respmon_b200.monitor import RespiratoryMonitor
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        RespiratoryMonitor(np.zeros((300, 48, 64), np.uint8), motion_extraction_method="flow")
+
+
+def test_product_package_never_imports_the_oracle():
+    import subprocess
+    code = ("import sys; import respmon_b200, respmon_b200.engine, respmon_b200.batch, respmon_b200.monitor, "
+            "respmon_b200.pyramid, respmon_b200.transforms; "
+            "bad=[m for m in sys.modules if m=='oracle' or m.startswith('oracle.') or m=='cv2' or m.startswith('scipy')];"
+            "print(bad); sys.exit(1 if bad else 0)")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_reduce_bounding_box_matches_reference_rule():
+    """tools.py:48-57."""
+    from respmon_b200.monitor import reduce_bounding_box
+    assert reduce_bounding_box(10, 20, 30, 40, np.inf) == (10, 20, 30, 40)
+    x, y, w, h = reduce_bounding_box(10, 20, 30, 40, 300)
+    assert w * h <= 300 and (w, h) == (15, 20) and (x, y) == (17, 30)
+
+
+@pytest.mark.parametrize("n,world", [(64, 8), (10, 4), (3, 8), (0, 2), (2048, 8)])
+def test_shard_range_partitions_every_clip_once(n, world):
+    from respmon_b200.batch import shard_range
+    spans = [shard_range(n, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    sizes = [hi - lo for lo, hi in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_balance_mixed_resolution_is_even_by_pixels():
+    from respmon_b200.batch import balance_clips
+    shapes = [(256, (240, 480, 1080)[i % 3], (320, 640, 1920)[i % 3]) for i in range(96)]
+    owners = balance_clips(shapes, 8)
+    assert sorted(i for o in owners for i in o) == list(range(96))
+    load = [sum(np.prod(shapes[i]) for i in o) for o in owners]
+    assert max(load) / min(load) < 1.05
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, counts, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from respmon_b200.batch import gather_records, shard_range
+    from respmon_b200.engine import RESULT_DTYPE
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    n = sum(counts)
+    lo, hi = shard_range(n, rank, world)
+    assert hi - lo == counts[rank]
+    local = np.zeros(hi - lo, RESULT_DTYPE)
+    local["bpm"] = np.arange(lo, hi) + 0.25
+    local["x"] = np.arange(lo, hi)
+    local["status"] = rank
+    out = gather_records(local, counts)
+    dist.destroy_process_group()
+    q.put((rank, out.tobytes()))
+
+
+@pytest.mark.parametrize("counts", [[3, 3], [4, 3]])
+def test_gather_records_world_size_2_gloo(counts):
+    import torch.multiprocessing as mp
+    from respmon_b200.engine import RESULT_DTYPE
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, counts, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = sum(counts)
+    a = np.frombuffer(got[0], RESULT_DTYPE)
+    b = np.frombuffer(got[1], RESULT_DTYPE)
+    assert np.array_equal(a, b) and len(a) == n                       # every rank holds every record, in clip order
+    assert np.array_equal(a["x"], np.arange(n)) and np.allclose(a["bpm"], np.arange(n) + 0.25)
+    assert list(a["status"]) == [0] * counts[0] + [1] * counts[1]

@@ -8,7 +8,7 @@ from conftest import clip_from_fixture
 from oracle import cpu_path as P
 from oracle import shim
 
-CASES = ["vga_s0", "vga_s2", "qvga_s1", "odd_s3"]
+CASES = ["vga_s0", "vga_s2", "qvga_s1", "odd_s3", "qvga_long_s4"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -22,7 +22,9 @@ def test_whole_clip_matches_reference_golden(golden, name):
     assert np.sqrt(np.mean((data - fix["data"]) ** 2)) <= 1e-6
     assert list(res["peaks"]) == [int(p) for p in fix["peaks"]]
     assert abs(res["bpm"] - fix["freq"][-1]) <= 1e-6
-    assert np.abs(np.array(res["freq"]) - fix["freq"]).max() <= 1e-6
+    assert np.abs(np.array(res["freq_window"]) - fix["freq"]).max() <= 1e-6
+    assert np.abs(np.array(res["t"]) - fix["t"]).max() <= 1e-12
+    assert np.abs(res["motion"] - fix["motion"]).max() <= 1e-6
     assert np.abs(res["filtered"] - fix["filtered"]).max() <= 1e-6
 
 
@@ -55,5 +57,5 @@ def test_oracle_equals_live_reference():
     res = P.run_clip(clip, fps=10)
     assert res["roi"] == (rm.x, rm.y, rm.w, rm.h)
     assert np.array_equal(np.array(res["window_data"]), np.array(rm.data))
-    assert np.array_equal(np.array(res["freq"]), np.array(rm.freq))
+    assert np.array_equal(np.array(res["freq_window"]), np.array(rm.freq))
     assert list(res["peaks"]) == [int(p) for p in rm.peak_indices]

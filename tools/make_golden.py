@@ -24,6 +24,7 @@ CASES = [  # (name, W, H, T, seed)
     ("vga_s2", 640, 480, 256, 2),
     ("qvga_s1", 320, 240, 256, 1),
     ("odd_s3", 250, 187, 256, 3),
+    ("qvga_long_s4", 320, 240, 420, 4),     # 290 measure frames: every 128-sample window rolls (base.py:473-475)
 ]
 TAP_FRAMES = [0, 1, 2, 63, 127]
 
@@ -34,7 +35,10 @@ def main():
     ref = shim.load_reference()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, W, H, T, seed in CASES:
+        if only and name not in only:
+            continue
         spec = synth.clip_spec(seed, W, H, T)
         clip = synth.make_clip(spec)
 
