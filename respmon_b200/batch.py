@@ -57,28 +57,153 @@ def gather_records(local: np.ndarray, counts: list[int] | None = None) -> np.nda
 
 
 class BatchMonitor:
-    """Calibrate + measure for a batch of whole clips held in host memory."""
+    """Calibrate + measure for a batch of whole clips held in host memory.
 
-    def __init__(self, device: int | None = None, chunk_clips: int = 8, method: str = "flow", **hyper):
+    Only the bytes the path reads cross PCIe: the calibration window of every clip (frames cal_first ..
+    cal_first+cal_len-1, base.py:429-434) goes up first; once locate() has produced the ROI, the measure frames go up
+    as ROI crops -- the reference itself only ever looks at `frame[y:y+h, x:x+w]` of those frames (base.py:471).
+    Uploads run on a copy stream and overlap the kernels of the previous chunk (two buffers of each kind)."""
+
+    def __init__(self, device: int | None = None, chunk_clips: int = 8, method: str = "flow", crop_upload: bool = True,
+                 measure_streams: int = 3, **hyper):
         self.engine = Engine(device, **hyper)
+        self._measure_engines = [Engine(self.engine.device_index, **hyper) for _ in range(max(1, measure_streams))]
+        self._measure_streams = [torch.cuda.Stream(self.engine.device) for _ in self._measure_engines]
+        self._crop_stream = torch.cuda.Stream(self.engine.device)
         self.chunk_clips = int(chunk_clips)
         self.method = method
-        self._bufs = [None, None]
+        self.crop_upload = bool(crop_upload)
+        self._bufs = {}
+        self._pinned = {}
         self._copy_stream = torch.cuda.Stream(self.engine.device)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def _buffer(self, slot, shape):
-        b = self._bufs[slot]
-        if b is None or b.shape[1:] != shape[1:] or b.shape[0] < shape[0]:
-            b = torch.empty(shape, dtype=torch.uint8, device=self.engine.device)
-            self._bufs[slot] = b
-        return b[:shape[0]]
+    def _buffer(self, key, shape):
+        """Device uint8 buffer of at least prod(shape) bytes, viewed as `shape`."""
+        n = int(np.prod(shape))
+        b = self._bufs.get(key)
+        if b is None or b.numel() < n:
+            b = torch.empty(max(n, 1), dtype=torch.uint8, device=self.engine.device)
+            self._bufs[key] = b
+        return b[:n].view(shape)
+
+    def _pinned_buffer(self, key, shape, dtype=torch.uint8):
+        n = int(np.prod(shape))
+        b = self._pinned.get(key)
+        if b is None or b.numel() < n or b.dtype != dtype:
+            b = torch.empty(max(n, 1), dtype=dtype).pin_memory()
+            self._pinned[key] = b
+        return b[:n].view(shape)
 
     def run(self, clips, fps: float, cal_first: int = 1, cal_len: int = 128) -> np.ndarray:
-        """clips: (n,T,H,W) uint8 numpy array or (preferably pinned) CPU tensor -> RESULT_DTYPE array of n records."""
+        """clips: (n,T,H,W) uint8 numpy array or (preferably pinned) CPU tensor -> RESULT_DTYPE array of n records.
+
+        Per chunk: calibration window H2D (copy stream) -> locate() (calibrate stream) -> ROI to the host -> ROI crops
+        of the measure frames H2D (second copy stream) -> LK measure + BPM on one of `measure_streams` streams.  The
+        measure kernels are latency bound (frames are sequential), so consecutive chunks run them
+        concurrently on different streams, each through its own rm_handle (handles own their scratch)."""
         host = torch.from_numpy(clips) if isinstance(clips, np.ndarray) else clips
-        assert host.dtype == torch.uint8 and host.dim() == 4 and not host.is_cuda
+        assert host.dtype == torch.uint8 and host.dim() == 4 and not host.is_cuda and host.is_contiguous()
+        n, T, H, W = host.shape
+        measure_first = cal_first + cal_len + 1
+        n_meas = T - measure_first
+        assert cal_first >= 0 and n_meas >= 1
+        if not self.crop_upload:
+            return self._run_full_frames(host, fps, cal_first, cal_len)
+        eng = self.engine
+        dev = eng.device
+        host_np = host.numpy()
+        main = torch.cuda.current_stream(dev)
+        copy, copy2 = self._copy_stream, self._crop_stream
+        n_ms = len(self._measure_streams)
+        chunks = [(lo, min(n, lo + self.chunk_clips)) for lo in range(0, n, self.chunk_clips)]
+        ev = lambda k: [torch.cuda.Event() for _ in range(k)]          # noqa: E731
+        cal_ready, cal_freed, roi_done = ev(2), ev(2), ev(2)
+        crop_ready, stage_freed, crop_dev_freed = ev(n_ms), ev(n_ms), ev(n_ms)
+        records = torch.empty((n, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        start = torch.cuda.Event()
+        start.record(main)
+        for s_ in [copy, copy2] + self._measure_streams:
+            s_.wait_event(start)                                       # everything queued before run() is done
+        keep = []                                                      # tensors shared across streams stay alive
+
+        def upload_cal(i):
+            lo, hi = chunks[i]
+            slot = i & 1
+            dst = self._buffer(("cal", slot), (hi - lo, cal_len, H, W))
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(cal_freed[slot])              # locate() of chunk i-2 has read this buffer
+                for c in range(lo, hi):                           # one contiguous block per clip
+                    dst[c - lo].copy_(host[c, cal_first:cal_first + cal_len], non_blocking=True)
+                cal_ready[slot].record(copy)
+            self.h2d_bytes += dst.numel()
+            return dst
+
+        pending = upload_cal(0) if chunks else None
+        for i, (lo, hi) in enumerate(chunks):
+            slot, ms = i & 1, i % n_ms
+            cal = pending
+            if i + 1 < len(chunks):
+                pending = upload_cal(i + 1)                       # overlaps everything below
+            m = hi - lo
+            main.wait_event(cal_ready[slot])
+            roi, status, _ = eng.locate(cal, fps, 0, cal_len)
+            cal_freed[slot].record(main)
+            roi_host = self._pinned_buffer(("roi", slot), (m, 4), torch.int32)
+            st_host = self._pinned_buffer(("st", slot), (m,), torch.int32)
+            roi_host.copy_(roi, non_blocking=True)
+            st_host.copy_(status, non_blocking=True)
+            roi_done[slot].record(main)
+            self.d2h_bytes += roi_host.numel() * 4 + st_host.numel() * 4
+            roi_done[slot].synchronize()                          # the ROI decides which bytes go up next
+            r = roi_host.numpy()
+            ok = st_host.numpy() == 0
+            mw = int(max(1, r[ok, 2].max())) if ok.any() else 1
+            mh = int(max(1, r[ok, 3].max())) if ok.any() else 1
+            stage = self._pinned_buffer(("crop", ms), (m, n_meas, mh, mw))
+            if i >= n_ms:
+                stage_freed[ms].synchronize()                     # the H2D of chunk i-n_ms has left this staging area
+            sv = stage.numpy()
+            for c in range(m):
+                if ok[c]:
+                    x, y, w, h = (int(v) for v in r[c])
+                    sv[c, :, :h, :w] = host_np[lo + c, measure_first:, y:y + h, x:x + w]   # base.py:471
+            crops = self._buffer(("cropdev", ms), (m, n_meas, mh, mw))
+            with torch.cuda.stream(copy2):
+                if i >= n_ms:
+                    copy2.wait_event(crop_dev_freed[ms])          # measure of chunk i-n_ms has read this device buffer
+                crops.copy_(stage, non_blocking=True)
+                crop_ready[ms].record(copy2)
+                stage_freed[ms].record(copy2)
+            self.h2d_bytes += crops.numel()
+            mstream, meng = self._measure_streams[ms], self._measure_engines[ms]
+            with torch.cuda.stream(mstream):
+                mstream.wait_event(roi_done[slot])
+                mstream.wait_event(crop_ready[ms])
+                roi0 = roi.clone()
+                roi0[:, :2] = 0                                   # the crop's own origin
+                st = status.clone()
+                if self.method == "flow":
+                    data = meng.measure_flow(crops, roi0, 0, n_meas, status=st, max_roi=(mw, mh))["data"]
+                else:
+                    data = meng.measure_average(crops, roi0, 0, n_meas)
+                sig = meng.signal_bpm(data, fps, status=st)
+                meng.pack_results(sig["bpm"], roi, st, sig["npeaks"], out=records[lo:hi])
+                crop_dev_freed[ms].record(mstream)
+            keep.append((roi, status, roi0, st, data, sig))
+        for k, mstream in enumerate(self._measure_streams):
+            e = torch.cuda.Event()
+            e.record(mstream)
+            main.wait_event(e)
+        out = records.cpu().numpy().view(RESULT_DTYPE).reshape(-1)   # the device->host read of the step's result
+        self.d2h_bytes += records.numel()
+        del keep
+        return out
+
+    def _run_full_frames(self, host, fps, cal_first, cal_len):
+        """Whole clips go up (2x the bytes of `run`); kept for comparison and for ROIs too large to be worth cropping."""
         n = host.shape[0]
         eng = self.engine
         compute = torch.cuda.current_stream(eng.device)
@@ -90,7 +215,7 @@ class BatchMonitor:
         def upload(i):
             lo, hi = chunks[i]
             slot = i & 1
-            dst = self._buffer(slot, (hi - lo,) + tuple(host.shape[1:]))
+            dst = self._buffer(("full", slot), (hi - lo,) + tuple(host.shape[1:]))
             with torch.cuda.stream(self._copy_stream):
                 if i >= 2:
                     self._copy_stream.wait_event(freed[slot])     # the chunk that used this buffer has been processed

@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "librespmon_b200.so")
 OBJ_DIR = os.path.join(PKG, "csrc", "_obj")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"] + os.environ.get("RM_NVCC_EXTRA", "").split()
 # files whose double-precision scalar code mirrors SciPy/MINPACK operation by operation: no FMA contraction
 NO_FMAD = {"signal.cu", "measure.cu"}
 

@@ -2,7 +2,7 @@
 // scipy.optimize.curve_fit -> MINPACK lmdif), device only.
 //
 // Same algorithm, constants and control flow as the scalar port in signal_core.h (sc_lmdif_gauss, which the host tests
-// pin against SciPy).  A group of LMG lanes works on one fit: the m residuals / Jacobian rows live in the group's slice
+// pin against SciPy).  A group of G lanes works on one fit: the m residuals / Jacobian rows live in the group's slice
 // of shared memory, the O(m) loops (model evaluation, forward-difference Jacobian, Householder QR, Q^T f) are strided
 // over the lanes of the group and their sums are xor-butterfly reductions inside the group (every lane gets the same
 // bits, so the group's control flow stays uniform); the 3x3 trust-region algebra (lmpar, qrsolv) runs redundantly on
@@ -12,44 +12,48 @@
 #pragma once
 #include "signal_core.h"
 
-#define LMG 8   // lanes per fit
+// G = lanes per fit (a power of two up to 32): a template parameter of every routine below.
 
 struct LmGroup {
   unsigned mask;   // lanes of this group
-  int sub;         // 0..LMG-1
+  int sub;         // 0..G-1
 };
 
+template <int G>
 __device__ __forceinline__ double lmg_sum(const LmGroup& g, double v) {
 #pragma unroll
-  for (int o = LMG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
   return v;
 }
+template <int G>
 __device__ __forceinline__ double lmg_max(const LmGroup& g, double v) {
 #pragma unroll
-  for (int o = LMG / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(g.mask, v, o));
+  for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(g.mask, v, o));
   return v;
 }
 
 // Euclidean norm of rows from..m-1 of a shared vector (MINPACK enorm; rescaled only outside the safe range)
+template <int G>
 __device__ __forceinline__ double lmg_enorm(const LmGroup& g, const double* v, int m, int from) {
   double mx = 0.0, s = 0.0;
-  for (int i = from + g.sub; i < m; i += LMG) {
+  for (int i = from + g.sub; i < m; i += G) {
     const double a = fabs(v[i]);
     mx = fmax(mx, a);
     s += a * a;
   }
-  mx = lmg_max(g, mx);
+  mx = lmg_max<G>(g, mx);
   if (mx == 0.0) return 0.0;
-  if (mx > 1e-140 && mx < 1e140) return sqrt(lmg_sum(g, s));
+  if (mx > 1e-140 && mx < 1e140) return sqrt(lmg_sum<G>(g, s));
   s = 0.0;
-  for (int i = from + g.sub; i < m; i += LMG) { const double d = fabs(v[i]) / mx; s += d * d; }
-  return mx * sqrt(lmg_sum(g, s));
+  for (int i = from + g.sub; i < m; i += G) { const double d = fabs(v[i]) / mx; s += d * d; }
+  return mx * sqrt(lmg_sum<G>(g, s));
 }
 
+template <int G>
 __device__ __forceinline__ void lmg_resid(const LmGroup& g, int m, const double* xs, const double* ys, const double* p,
                                           double* f) {
   const double denom = 2.0 * (p[2] * p[2]) + SC_DBL_EPS;
-  for (int i = g.sub; i < m; i += LMG) {
+  for (int i = g.sub; i < m; i += G) {
     const double d = xs[i] - p[1];
     f[i] = p[0] * exp(-(d * d) / denom) - ys[i];
   }
@@ -57,6 +61,7 @@ __device__ __forceinline__ void lmg_resid(const LmGroup& g, int m, const double*
 
 // xs, ys, fvec, wa4 (m each) and fjac (3m, column-major) are the group's shared-memory slices; xs/ys filled by the
 // caller (and visible: the caller syncs the group).  x[3] in/out (uniform over the group).  Returns MINPACK info.
+template <int G>
 __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double* xs, const double* ys, double* x,
                                             double* fvec, double* wa4, double* fjac) {
   const int n = SC_NP;
@@ -70,9 +75,9 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
   int info = 0, nfev = 0, iter = 1;
   double par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0;
   if (m < n) return 0;
-  lmg_resid(g, m, xs, ys, x, fvec);
+  lmg_resid<G>(g, m, xs, ys, x, fvec);
   nfev = 1;
-  double fnorm = lmg_enorm(g, fvec, m, 0);
+  double fnorm = lmg_enorm<G>(g, fvec, m, 0);
   for (;;) {
     {   // fdjac2: forward differences (each lane differences the rows it evaluated)
       const double eps = sqrt(epsfcn > epsmch ? epsfcn : epsmch);
@@ -81,16 +86,16 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
         double h = eps * fabs(temp);
         if (h == 0.0) h = eps;
         x[j] = temp + h;
-        lmg_resid(g, m, xs, ys, x, wa4);
+        lmg_resid<G>(g, m, xs, ys, x, wa4);
         x[j] = temp;
-        for (int i = g.sub; i < m; i += LMG) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
+        for (int i = g.sub; i < m; i += G) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
       }
       nfev += n;
     }
     __syncwarp(g.mask);
     {   // qrfac with column pivoting; wa1 = rdiag, wa2 = acnorm, wa3 = work
       for (int j = 0; j < n; ++j) {
-        wa2[j] = lmg_enorm(g, fjac + j * m, m, 0);
+        wa2[j] = lmg_enorm<G>(g, fjac + j * m, m, 0);
         wa1[j] = wa2[j];
         wa3[j] = wa1[j];
         ipvt[j] = j;
@@ -100,7 +105,7 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
         for (int k = j; k < n; ++k)
           if (wa1[k] > wa1[kmax]) kmax = k;
         if (kmax != j) {
-          for (int i = g.sub; i < m; i += LMG) {
+          for (int i = g.sub; i < m; i += G) {
             const double t = fjac[i + j * m];
             fjac[i + j * m] = fjac[i + kmax * m];
             fjac[i + kmax * m] = t;
@@ -110,18 +115,18 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
           const int t = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = t;
           __syncwarp(g.mask);
         }
-        double ajnorm = lmg_enorm(g, fjac + j * m, m, j);
+        double ajnorm = lmg_enorm<G>(g, fjac + j * m, m, j);
         if (ajnorm != 0.0) {
           if (fjac[j + j * m] < 0.0) ajnorm = -ajnorm;
           __syncwarp(g.mask);                                   // everyone has read the diagonal element
-          for (int i = j + g.sub; i < m; i += LMG) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
+          for (int i = j + g.sub; i < m; i += G) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
           __syncwarp(g.mask);
           const double ajj = fjac[j + j * m];
           for (int k = j + 1; k < n; ++k) {
             double part = 0.0;
-            for (int i = j + g.sub; i < m; i += LMG) part += fjac[i + j * m] * fjac[i + k * m];
-            const double temp = lmg_sum(g, part) / ajj;
-            for (int i = j + g.sub; i < m; i += LMG) fjac[i + k * m] -= temp * fjac[i + j * m];
+            for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * fjac[i + k * m];
+            const double temp = lmg_sum<G>(g, part) / ajj;
+            for (int i = j + g.sub; i < m; i += G) fjac[i + k * m] -= temp * fjac[i + j * m];
             __syncwarp(g.mask);
             if (wa1[k] != 0.0) {
               double t = fjac[j + k * m] / wa1[k];
@@ -129,7 +134,7 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
               wa1[k] *= sqrt(d > 0.0 ? d : 0.0);
               t = wa1[k] / wa3[k];
               if (0.05 * (t * t) <= SC_DBL_EPS) {
-                wa1[k] = lmg_enorm(g, fjac + k * m, m, j + 1);
+                wa1[k] = lmg_enorm<G>(g, fjac + k * m, m, j + 1);
                 wa3[k] = wa1[k];
               }
             }
@@ -146,15 +151,15 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
       if (delta == 0.0) delta = factor;
     }
     // qtf = first n components of Q^T fvec; R into a private 3x3 (column-major, ldr = 3)
-    for (int i = g.sub; i < m; i += LMG) wa4[i] = fvec[i];
+    for (int i = g.sub; i < m; i += G) wa4[i] = fvec[i];
     __syncwarp(g.mask);
     for (int j = 0; j < n; ++j) {
       const double ajj = fjac[j + j * m];
       if (ajj != 0.0) {
         double part = 0.0;
-        for (int i = j + g.sub; i < m; i += LMG) part += fjac[i + j * m] * wa4[i];
-        const double temp = -lmg_sum(g, part) / ajj;
-        for (int i = j + g.sub; i < m; i += LMG) wa4[i] += fjac[i + j * m] * temp;
+        for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * wa4[i];
+        const double temp = -lmg_sum<G>(g, part) / ajj;
+        for (int i = j + g.sub; i < m; i += G) wa4[i] += fjac[i + j * m] * temp;
         __syncwarp(g.mask);
       }
       qtf[j] = wa4[j];
@@ -186,9 +191,9 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
       }
       const double pnorm = sc_enorm(n, wa3);
       if (iter == 1) delta = delta < pnorm ? delta : pnorm;
-      lmg_resid(g, m, xs, ys, wa2, wa4);
+      lmg_resid<G>(g, m, xs, ys, wa2, wa4);
       ++nfev;
-      const double fnorm1 = lmg_enorm(g, wa4, m, 0);
+      const double fnorm1 = lmg_enorm<G>(g, wa4, m, 0);
       double actred = -1.0;
       if (p1 * fnorm1 < fnorm) { const double d = fnorm1 / fnorm; actred = 1.0 - d * d; }
       for (int j = 0; j < n; ++j) {
@@ -216,7 +221,7 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
       }
       if (ratio >= p0001) {
         for (int j = 0; j < n; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
-        for (int i = g.sub; i < m; i += LMG) fvec[i] = wa4[i];   // own rows only: no sync needed
+        for (int i = g.sub; i < m; i += G) fvec[i] = wa4[i];   // own rows only: no sync needed
         xnorm = sc_enorm(n, wa2);
         fnorm = fnorm1;
         ++iter;

@@ -45,6 +45,7 @@ struct SignalScratch {
   int* ncand;              // (n_windows) candidates, or -1 when measure() does not run / raises for this window
   unsigned* queue;         // fit work items: window * SIG_MAX_CAND + k
   unsigned* queue_n;
+  unsigned* cursor;        // next queue item to fit
 };
 
 __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalParams p, const SignalScratch s) {
@@ -84,50 +85,61 @@ __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalPar
   s.ncand[win] = ncand;
 }
 
-// Stage B, one group of LMG lanes per queued candidate: the Gaussian gate, peakutils.gaussian_fit = curve_fit =
-// MINPACK lmdif (lm_group.cuh).  The fit is a long dependent float64 chain, so the stage is latency bound: the lanes
-// of a group share the O(m) work and every fit of the batch is in flight at once.
+// Stage B, one group of G lanes per queued candidate: the Gaussian gate, peakutils.gaussian_fit = curve_fit =
+// MINPACK lmdif (lm_group.cuh).  The fit is a long dependent float64 chain, so the stage is latency bound.  G = 32:
+// a warp works on one fit, so its lanes never diverge (with several fits per warp every group's instruction stream
+// is issued separately and the warp runs the SUM of its groups' iterations).  The grid is persistent: warps pull
+// fits from the queue through an atomic cursor until it is empty, which balances the 10x spread in LM iterations.
 #define SIG_FIT_THREADS 128
+#ifndef SIG_FIT_G
+#define SIG_FIT_G 8
+#endif
+template <int G>
 __global__ void __launch_bounds__(SIG_FIT_THREADS) signal_fit_kernel(const SignalParams p, const SignalScratch s,
                                                                       int m_cap) {
   extern __shared__ __align__(16) double fit_smem[];
   const int lane = threadIdx.x & 31;
   LmGroup g;
-  g.sub = lane & (LMG - 1);
-  g.mask = ((1u << LMG) - 1u) << (lane & ~(LMG - 1));
-  const int group_in_block = threadIdx.x / LMG;
+  g.sub = lane & (G - 1);
+  g.mask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << (lane & ~(G - 1));
+  const int group_in_block = threadIdx.x / G;
   const unsigned total = *s.queue_n;
-  const unsigned item = blockIdx.x * (SIG_FIT_THREADS / LMG) + group_in_block;
-  if (item >= total) return;                          // whole groups leave together
   double* xs = fit_smem + (size_t)group_in_block * 7 * m_cap;
   double* ys = xs + m_cap;
   double* fvec = ys + m_cap;
   double* wa4 = fvec + m_cap;
   double* fjac = wa4 + m_cap;
-  const unsigned q = s.queue[item];
-  const long long win = q / SIG_MAX_CAND;
-  const int k = q % SIG_MAX_CAND;
-  const int f = (int)(win % p.n_frames);
-  const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
-  const int idx = s.cand[win * SIG_MAX_CAND + k];
-  int w = p.width;                                   // base.py:319-323
-  if (idx - p.width < 0) w = idx;
-  if (idx + w > n) w = n - idx;
-  int m = 2 * w;
-  if (m > m_cap) m = m_cap;
-  const double* t = p.tvals + (f + 1 - n) + (idx - w);
-  const double* y = s.filt + win * p.buf_len + (idx - w);
-  double mx = -INFINITY;
-  for (int i = g.sub; i < m; i += LMG) {
-    xs[i] = t[i];
-    ys[i] = y[i];
-    mx = fmax(mx, y[i]);
+  for (;;) {
+    unsigned item = 0;
+    if (g.sub == 0) item = atomicAdd(s.cursor, 1u);
+    item = __shfl_sync(g.mask, item, lane & ~(G - 1));
+    if (item >= total) return;                        // whole groups leave together
+    const unsigned q = s.queue[item];
+    const long long win = q / SIG_MAX_CAND;
+    const int k = q % SIG_MAX_CAND;
+    const int f = (int)(win % p.n_frames);
+    const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
+    const int idx = s.cand[win * SIG_MAX_CAND + k];
+    int w = p.width;                                   // base.py:319-323
+    if (idx - p.width < 0) w = idx;
+    if (idx + w > n) w = n - idx;
+    int m = 2 * w;
+    if (m > m_cap) m = m_cap;
+    const double* t = p.tvals + (f + 1 - n) + (idx - w);
+    const double* y = s.filt + win * p.buf_len + (idx - w);
+    double mx = -INFINITY;
+    __syncwarp(g.mask);                                // the previous fit's reads of xs/ys are done
+    for (int i = g.sub; i < m; i += G) {
+      xs[i] = t[i];
+      ys[i] = y[i];
+      mx = fmax(mx, y[i]);
+    }
+    mx = lmg_max<G>(g, mx);
+    __syncwarp(g.mask);
+    double par[SC_NP] = {mx, xs[0], (xs[1] - xs[0]) * 5.0};   // peakutils.gaussian_fit initial guess
+    const int info = lmg_lmdif_gauss<G>(g, m, xs, ys, par, fvec, wa4, fjac);
+    if (g.sub == 0) s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334, 336
   }
-  mx = lmg_max(g, mx);
-  __syncwarp(g.mask);
-  double par[SC_NP] = {mx, xs[0], (xs[1] - xs[0]) * 5.0};   // peakutils.gaussian_fit initial guess
-  const int info = lmg_lmdif_gauss(g, m, xs, ys, par, fvec, wa4, fjac);
-  if (g.sub == 0) s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334, 336
 }
 
 // Stage C, one thread per window: BPM = 60 / mean interval of the accepted peaks (base.py:347-352).
@@ -232,7 +244,8 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
   sc.queue_n = reinterpret_cast<unsigned*>(base);           base += 256;
   sc.cand = base;                                           base += n_win * SIG_MAX_CAND;
   sc.acc = base;
-  RM_CUDA(h, cudaMemsetAsync(sc.queue_n, 0, 4, st));
+  sc.cursor = sc.queue_n + 1;
+  RM_CUDA(h, cudaMemsetAsync(sc.queue_n, 0, 8, st));
   dim3 grid(div_up(n_frames, 64), n_clips);
   RM_PROF(h, st, "signal_filter_peaks_kernel");
   signal_filter_peaks_kernel<<<grid, 64, 0, st>>>(p, sc);
@@ -241,13 +254,20 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
     // every window holds at most (buf_len / width + 1) candidates that survive min_dist = width
     int m_cap = 2 * p.width < SC_MAX_FIT ? 2 * p.width : SC_MAX_FIT;
     if (m_cap < 4) m_cap = 4;
-    const int groups = SIG_FIT_THREADS / LMG;
+    const int groups = SIG_FIT_THREADS / SIG_FIT_G;
     const size_t fit_smem = (size_t)groups * 7 * m_cap * sizeof(double);
+    // persistent grid: as many blocks as can be resident (register limited), never more than there can be fits
     const size_t per_win = (size_t)(p.buf_len / (p.width > 0 ? p.width : 1)) + 2;
-    size_t max_items = n_win * (per_win < SIG_MAX_CAND ? per_win : SIG_MAX_CAND);
-    RM_CUDA(h, cudaFuncSetAttribute(signal_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem));
+    const size_t max_items = n_win * (per_win < SIG_MAX_CAND ? per_win : SIG_MAX_CAND);
+    int per_sm = 0;
+    RM_CUDA(h, cudaFuncSetAttribute(signal_fit_kernel<SIG_FIT_G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)fit_smem));
+    RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, signal_fit_kernel<SIG_FIT_G>, SIG_FIT_THREADS,
+                                                             fit_smem));
+    long long grid_fit = (long long)h->sm_count * (per_sm > 0 ? per_sm : 1);
+    if (grid_fit > div_up((long long)max_items, groups)) grid_fit = div_up((long long)max_items, groups);
     RM_PROF(h, st, "signal_fit_kernel");
-    signal_fit_kernel<<<div_up((long long)max_items, groups), SIG_FIT_THREADS, fit_smem, st>>>(p, sc, m_cap);
+    signal_fit_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, fit_smem, st>>>(p, sc, m_cap);
     RM_LAUNCH_CHECK(h);
   }
   RM_PROF(h, st, "signal_bpm_kernel");
