@@ -194,6 +194,15 @@ int32_t rm_measure_average(rm_handle* h, const uint8_t* frames, int32_t n_clips,
  * and peaks_out (n_clips, measure_buffer_len) int32 (-1 terminated) for the LAST frame's window, npeaks_out (n_clips). */
 int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps, double* bpm_out,
                       double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, const int32_t* status, void* stream);
+/* rm_measure_flow followed by rm_signal_bpm as one pipeline (the 'measure' branch of run(), base.py:464-495, over whole
+ * clips): identical results, but the tracker walks the frames in chunks (option "measure_chunks", default 8) on `stream`
+ * while the signal stage of the finished chunks runs underneath on a stream owned by the handle; `stream` is joined
+ * before the call returns control of it.  Arguments as in the two separate calls; workspace as rm_measure_flow. */
+int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
+                          const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t first_frame, int32_t n_frames,
+                          double fps, double* data_out, float* motion_out, int32_t* npts_out, int32_t* status_io,
+                          double* bpm_out, double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, void* workspace,
+                          size_t workspace_bytes, void* stream);
 /* assemble the 32-byte records: last finite BPM per clip, ROI, status, n_peaks. */
 int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, const int32_t* status, const int32_t* npeaks,
                         int32_t n_clips, int32_t n_frames, rm_result* out, void* stream);
@@ -202,7 +211,7 @@ int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, con
 /* Number of kernel launches this handle has issued since creation (bench.py reports it as gpu_launches). */
 int64_t rm_launch_count(rm_handle* h);
 
-/* Diagnostic switches.  "force_global_lk" (0/1): track from global memory even when the ROI fits shared memory (the
+/* Switches.  "measure_chunks" (1..16): frame chunks of rm_measure_signal.  "force_global_lk" (0/1): track from global memory even when the ROI fits shared memory (the
  * fallback used for ROIs too large to stage; results are identical). */
 int32_t rm_set_option(rm_handle* h, const char* host_name, int64_t value);
 

@@ -186,10 +186,11 @@ class BatchMonitor:
                 roi0[:, :2] = 0                                   # the crop's own origin
                 st = status.clone()
                 if self.method == "flow":
-                    data = meng.measure_flow(crops, roi0, 0, n_meas, status=st, max_roi=(mw, mh))["data"]
+                    sig = meng.measure_signal(crops, roi0, 0, n_meas, fps, status=st, max_roi=(mw, mh))
+                    data = sig["data"]
                 else:
                     data = meng.measure_average(crops, roi0, 0, n_meas)
-                sig = meng.signal_bpm(data, fps, status=st)
+                    sig = meng.signal_bpm(data, fps, status=st)
                 meng.pack_results(sig["bpm"], roi, st, sig["npeaks"], out=records[lo:hi])
                 crop_dev_freed[ms].record(mstream)
             keep.append((roi, status, roi0, st, data, sig))

@@ -117,6 +117,21 @@ extern "C" int32_t rm_create(const rm_params* params, int32_t device, rm_handle*
     free(h);
     return RM_ERR_CUDA;
   }
+  h->measure_chunks = 8;
+  bool ok = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < RM_MAX_CHUNKS; ++i) {
+    ok = cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_filt[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->fit_stream[i], cudaStreamNonBlocking) == cudaSuccess;
+  }
+  if (!ok) {
+    cudaFree(h->d_lut);
+    free(h);
+    return RM_ERR_CUDA;
+  }
   h->err[0] = 0;
   *out = h;
   return RM_OK;
@@ -129,6 +144,18 @@ extern "C" int32_t rm_destroy(rm_handle* h) {
     if (h->d_lut) cudaFree(h->d_lut);
     if (h->d_tvals) cudaFree(h->d_tvals);
     if (h->d_sig_scratch) cudaFree(h->d_sig_scratch);
+    free(h->sig_job);
+    if (h->d_lk_pts) cudaFree(h->d_lk_pts);
+    if (h->d_lk_n) cudaFree(h->d_lk_n);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (int i = 0; i < RM_MAX_CHUNKS; ++i) {
+      if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
+      if (h->ev_filt[i]) cudaEventDestroy(h->ev_filt[i]);
+      if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+      if (h->fit_stream[i]) cudaStreamDestroy(h->fit_stream[i]);
+    }
     for (int i = 0; i < h->prof_cap; ++i) {
       cudaEventDestroy(h->prof_slots[i].a);
       cudaEventDestroy(h->prof_slots[i].b);
@@ -144,6 +171,11 @@ extern "C" int32_t rm_set_option(rm_handle* h, const char* name, int64_t value) 
   if (!h || !name) return RM_ERR_INVALID;
   if (strcmp(name, "force_global_lk") == 0) { h->force_global_lk = value != 0; return RM_OK; }
   if (strcmp(name, "force_generic_front") == 0) { h->force_generic_front = value != 0; return RM_OK; }
+  if (strcmp(name, "measure_chunks") == 0) {
+    if (value < 1 || value > RM_MAX_CHUNKS) return rm_fail(h, RM_ERR_INVALID, "%s: measure_chunks must be 1..16", __func__);
+    h->measure_chunks = (int)value;
+    return RM_OK;
+  }
   return rm_fail(h, RM_ERR_INVALID, "%s: unknown option", __func__);
 }
 

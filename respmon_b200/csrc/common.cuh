@@ -9,6 +9,7 @@
 #include "../../include/respmon_b200.h"
 
 #define RM_MAX_LEVELS 16
+#define RM_MAX_CHUNKS 16   // frame chunks of the measure pipeline
 
 struct rm_handle {
   rm_params p;
@@ -24,6 +25,16 @@ struct rm_handle {
   // per-kernel device timing (the reference's tools.Benchmarker tags, tools.py:60-82, at kernel granularity)
   void* d_sig_scratch;  // measure() scratch (filtered windows, candidate peaks, fit queue), grown on demand
   size_t sig_scratch_bytes;
+  // measure pipeline (rm_measure_signal): LK walks the frames in chunks on the caller's stream while the signal
+  // stage of the finished chunks runs on aux_stream
+  cudaStream_t aux_stream;                   // PCA + filtfilt/peaks of the chunks, in frame order
+  cudaStream_t fit_stream[RM_MAX_CHUNKS];    // one per chunk: the Gaussian-fit gates of different chunks overlap
+  cudaEvent_t ev_fork, ev_join, ev_chunk[RM_MAX_CHUNKS], ev_filt[RM_MAX_CHUNKS], ev_done[RM_MAX_CHUNKS];
+  int measure_chunks;       // option "measure_chunks" (default 4)
+  float* d_lk_pts;          // (cap_clips, 128, 2) points carried from one LK chunk to the next
+  int* d_lk_n;              // (cap_clips)
+  int lk_state_cap;
+  void* sig_job;            // host-side SignalJob of the measure pipeline (signal.cu)
   int force_global_lk;
   int force_generic_front;  // tests: float64 pyramid front even for uint8 frames the integer front supports  // tests: take the global-memory LK path even when the ROI fits shared memory
   int prof_on;
@@ -164,3 +175,10 @@ __device__ __forceinline__ double tap5(double a, double b, double c, double d, d
 }
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- internal entry points shared between translation units (not part of the C ABI) ---------------------------------
+int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps, double* bpm_out,
+                         double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, const int32_t* status,
+                         int n_chunks, cudaStream_t st);
+int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t st, cudaStream_t st_fit,
+                         cudaEvent_t ev_filtered);

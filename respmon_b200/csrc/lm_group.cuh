@@ -34,8 +34,9 @@ __device__ __forceinline__ double lmg_max(const LmGroup& g, double v) {
 
 // Euclidean norm of rows from..m-1 of a shared vector (MINPACK enorm; rescaled only outside the safe range)
 template <int G>
-__device__ __forceinline__ double lmg_enorm(const LmGroup& g, const double* v, int m, int from) {
+__device__ __noinline__ double lmg_enorm(const LmGroup& g, const double* v, int m, int from) {
   double mx = 0.0, s = 0.0;
+#pragma unroll 1
   for (int i = from + g.sub; i < m; i += G) {
     const double a = fabs(v[i]);
     mx = fmax(mx, a);
@@ -45,14 +46,16 @@ __device__ __forceinline__ double lmg_enorm(const LmGroup& g, const double* v, i
   if (mx == 0.0) return 0.0;
   if (mx > 1e-140 && mx < 1e140) return sqrt(lmg_sum<G>(g, s));
   s = 0.0;
+#pragma unroll 1
   for (int i = from + g.sub; i < m; i += G) { const double d = fabs(v[i]) / mx; s += d * d; }
   return mx * sqrt(lmg_sum<G>(g, s));
 }
 
 template <int G>
-__device__ __forceinline__ void lmg_resid(const LmGroup& g, int m, const double* xs, const double* ys, const double* p,
+__device__ __noinline__ void lmg_resid(const LmGroup& g, int m, const double* xs, const double* ys, const double* p,
                                           double* f) {
   const double denom = 2.0 * (p[2] * p[2]) + SC_DBL_EPS;
+#pragma unroll 1
   for (int i = g.sub; i < m; i += G) {
     const double d = xs[i] - p[1];
     f[i] = p[0] * exp(-(d * d) / denom) - ys[i];
@@ -78,9 +81,11 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
   lmg_resid<G>(g, m, xs, ys, x, fvec);
   nfev = 1;
   double fnorm = lmg_enorm<G>(g, fvec, m, 0);
+#pragma unroll 1
   for (;;) {
     {   // fdjac2: forward differences (each lane differences the rows it evaluated)
       const double eps = sqrt(epsfcn > epsmch ? epsfcn : epsmch);
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         const double temp = x[j];
         double h = eps * fabs(temp);
@@ -88,23 +93,28 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
         x[j] = temp + h;
         lmg_resid<G>(g, m, xs, ys, x, wa4);
         x[j] = temp;
+#pragma unroll 1
         for (int i = g.sub; i < m; i += G) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
       }
       nfev += n;
     }
     __syncwarp(g.mask);
     {   // qrfac with column pivoting; wa1 = rdiag, wa2 = acnorm, wa3 = work
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         wa2[j] = lmg_enorm<G>(g, fjac + j * m, m, 0);
         wa1[j] = wa2[j];
         wa3[j] = wa1[j];
         ipvt[j] = j;
       }
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         int kmax = j;
+#pragma unroll 1
         for (int k = j; k < n; ++k)
           if (wa1[k] > wa1[kmax]) kmax = k;
         if (kmax != j) {
+#pragma unroll 1
           for (int i = g.sub; i < m; i += G) {
             const double t = fjac[i + j * m];
             fjac[i + j * m] = fjac[i + kmax * m];
@@ -119,13 +129,17 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
         if (ajnorm != 0.0) {
           if (fjac[j + j * m] < 0.0) ajnorm = -ajnorm;
           __syncwarp(g.mask);                                   // everyone has read the diagonal element
+#pragma unroll 1
           for (int i = j + g.sub; i < m; i += G) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
           __syncwarp(g.mask);
           const double ajj = fjac[j + j * m];
+#pragma unroll 1
           for (int k = j + 1; k < n; ++k) {
             double part = 0.0;
+#pragma unroll 1
             for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * fjac[i + k * m];
             const double temp = lmg_sum<G>(g, part) / ajj;
+#pragma unroll 1
             for (int i = j + g.sub; i < m; i += G) fjac[i + k * m] -= temp * fjac[i + j * m];
             __syncwarp(g.mask);
             if (wa1[k] != 0.0) {
@@ -144,35 +158,45 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
       }
     }
     if (iter == 1) {
+#pragma unroll 1
       for (int j = 0; j < n; ++j) { diag[j] = wa2[j]; if (wa2[j] == 0.0) diag[j] = 1.0; }
+#pragma unroll 1
       for (int j = 0; j < n; ++j) wa3[j] = diag[j] * x[j];
       xnorm = sc_enorm(n, wa3);
       delta = factor * xnorm;
       if (delta == 0.0) delta = factor;
     }
     // qtf = first n components of Q^T fvec; R into a private 3x3 (column-major, ldr = 3)
+#pragma unroll 1
     for (int i = g.sub; i < m; i += G) wa4[i] = fvec[i];
     __syncwarp(g.mask);
+#pragma unroll 1
     for (int j = 0; j < n; ++j) {
       const double ajj = fjac[j + j * m];
       if (ajj != 0.0) {
         double part = 0.0;
+#pragma unroll 1
         for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * wa4[i];
         const double temp = -lmg_sum<G>(g, part) / ajj;
+#pragma unroll 1
         for (int i = j + g.sub; i < m; i += G) wa4[i] += fjac[i + j * m] * temp;
         __syncwarp(g.mask);
       }
       qtf[j] = wa4[j];
     }
+#pragma unroll 1
     for (int j = 0; j < n; ++j)
+#pragma unroll 1
       for (int i = 0; i < n; ++i) r[i + j * SC_NP] = (i == j) ? wa1[j] : fjac[i + j * m];
     __syncwarp(g.mask);                                          // R and qtf are read before fjac / wa4 change again
     gnorm = 0.0;
     if (fnorm != 0.0) {
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         const int l = ipvt[j];
         if (wa2[l] != 0.0) {
           double sum = 0.0;
+#pragma unroll 1
           for (int i = 0; i <= j; ++i) sum += r[i + j * SC_NP] * (qtf[i] / fnorm);
           const double gg = fabs(sum / wa2[l]);
           gnorm = gnorm > gg ? gnorm : gg;
@@ -180,10 +204,12 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
       }
     }
     if (gnorm <= gtol) { info = 4; break; }
+#pragma unroll 1
     for (int j = 0; j < n; ++j) diag[j] = diag[j] > wa2[j] ? diag[j] : wa2[j];
     double ratio = 0.0;
     do {
       sc_lmpar(r, SC_NP, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         wa1[j] = -wa1[j];
         wa2[j] = x[j] + wa1[j];
@@ -196,9 +222,11 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
       const double fnorm1 = lmg_enorm<G>(g, wa4, m, 0);
       double actred = -1.0;
       if (p1 * fnorm1 < fnorm) { const double d = fnorm1 / fnorm; actred = 1.0 - d * d; }
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         wa3[j] = 0.0;
         const double temp = wa1[ipvt[j]];
+#pragma unroll 1
         for (int i = 0; i <= j; ++i) wa3[i] += r[i + j * SC_NP] * temp;
       }
       const double temp1 = sc_enorm(n, wa3) / fnorm;
@@ -220,7 +248,9 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
         par = p5 * par;
       }
       if (ratio >= p0001) {
+#pragma unroll 1
         for (int j = 0; j < n; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
+#pragma unroll 1
         for (int i = g.sub; i < m; i += G) fvec[i] = wa4[i];   // own rows only: no sync needed
         xnorm = sc_enorm(n, wa2);
         fnorm = fnorm1;

@@ -61,6 +61,10 @@ struct MeasureParams {
   int32_t* npts;           // (n_clips)
   int32_t* status;         // (n_clips)
   float* pts_dbg;          // (n_clips, n_frames, LK_MAX_PTS, 2) or null: per-frame tracked points (tests)
+  // frame chunk [f0, f1) of this launch and the tracker state carried between chunks (shared-memory tracker only)
+  int f0, f1;
+  float* st_pts;           // (n_clips, LK_MAX_PTS, 2)
+  int32_t* st_n;           // (n_clips)
 };
 
 __device__ __forceinline__ bool roi_ok(const MeasureParams& p, int clip, int& x, int& y, int& w, int& h) {
@@ -705,7 +709,8 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
   const bool ok = roi_ok(p, clip, rx, ry, rw, rh);
   float* motion = p.motion + (long long)clip * p.n_frames * 2;
   if (!ok || p.npts[clip] <= 0) {
-    for (int f = tid; f < p.n_frames; f += blockDim.x) { motion[2 * f] = NAN; motion[2 * f + 1] = NAN; }
+    if (p.f0 == 0)   // later chunks: the first one already did this (and a clip lost on the way keeps its history)
+      for (int f = tid; f < p.n_frames; f += blockDim.x) { motion[2 * f] = NAN; motion[2 * f + 1] = NAN; }
     return;
   }
   const LkSmemLayout L = lk_smem_layout(rw, rh, p.win, p.max_level, LKS_WARPS);
@@ -716,10 +721,16 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
   const int deriv_off = patch_off + 2 * ((pw * pw + 1) & ~1);
 
   for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
-  if (tid == 0) { s_n = p.npts[clip]; s_lost = 0; motion[0] = 0.f; motion[1] = 0.f; }
-  for (int i = tid; i < p.npts[clip]; i += blockDim.x) {
-    s_pts[i][0] = pts0[((long long)clip * LK_MAX_PTS + i) * 2];
-    s_pts[i][1] = pts0[((long long)clip * LK_MAX_PTS + i) * 2 + 1];
+  const bool resume = p.f0 > 0;               // a later chunk: points and count come from the previous launch
+  const int n_start = resume ? p.st_n[clip] : p.npts[clip];
+  if (resume && n_start <= 0) return;          // tracking was lost in an earlier chunk (its NaN fill is already done)
+  if (tid == 0) { s_n = n_start; s_lost = 0; if (!resume) { motion[0] = 0.f; motion[1] = 0.f; } }
+  {
+    const float* src = resume ? p.st_pts : pts0;
+    for (int i = tid; i < n_start; i += blockDim.x) {
+      s_pts[i][0] = src[((long long)clip * LK_MAX_PTS + i) * 2];
+      s_pts[i][1] = src[((long long)clip * LK_MAX_PTS + i) * 2 + 1];
+    }
   }
   int wq[8];   // the lane's window pixels (wy << 8 | wx), -1 past the end of the window
   {
@@ -828,16 +839,18 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
         out[l] = {pyr_slot * L.pyr_bytes + L.off[l] + L.pad * L.pitch[l] + L.pad, L.lw[l], L.lh[l], L.pitch[l]};
   };
 
-  stage_raw(0, 0);
+  // the frame before the chunk is the tracker's "previous image": frame 0 for the first chunk
+  const int f_first = resume ? p.f0 : 1;
+  stage_raw(f_first - 1, (f_first - 1) & 1);
   cp_async_wait<0>();
   __syncthreads();
-  build(0, 0);
-  if (p.n_frames > 1) stage_raw(1, 1);
-  for (int f = 1; f < p.n_frames; ++f) {
+  build((f_first - 1) & 1, (f_first - 1) & 1);
+  if (f_first < p.f1) stage_raw(f_first, f_first & 1);
+  for (int f = f_first; f < p.f1; ++f) {
     cp_async_wait<0>();
     __syncthreads();
     build(f & 1, f & 1);
-    if (f + 1 < p.n_frames) stage_raw(f + 1, (f + 1) & 1);   // lands while this frame is tracked
+    if (f + 1 < p.f1) stage_raw(f + 1, (f + 1) & 1);   // lands while this frame is tracked
     LkSLevel prev[LK_MAX_LEVELS], next[LK_MAX_LEVELS];
     levels((f - 1) & 1, prev);
     levels(f & 1, next);
@@ -880,10 +893,18 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
     }
     if (s_lost) {   // tracking lost: extract_motion returns nan from here on (base.py:385-386)
       for (int g = f + tid; g < p.n_frames; g += blockDim.x) { motion[2 * g] = NAN; motion[2 * g + 1] = NAN; }
-      if (tid == 0) p.status[clip] = RM_CLIP_TRACK_LOST;
+      if (tid == 0) { p.status[clip] = RM_CLIP_TRACK_LOST; if (p.st_n) p.st_n[clip] = 0; }
       cp_async_wait<0>();
       return;
     }
+  }
+  __syncthreads();
+  if (p.st_n) {   // hand the tracker state to the next chunk
+    for (int i = tid; i < s_n; i += blockDim.x) {
+      p.st_pts[((long long)clip * LK_MAX_PTS + i) * 2] = s_pts[i][0];
+      p.st_pts[((long long)clip * LK_MAX_PTS + i) * 2 + 1] = s_pts[i][1];
+    }
+    if (tid == 0) p.st_n[clip] = s_n;
   }
 }
 
@@ -892,7 +913,7 @@ __global__ void motion_pca_kernel(const MeasureParams p) {
   const int clip = blockIdx.y;
   const float* motion = p.motion + (long long)clip * p.n_frames * 2;
   double* data = p.data + (long long)clip * p.n_frames;
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < p.n_frames; f += gridDim.x * blockDim.x) {
+  for (int f = p.f0 + blockIdx.x * blockDim.x + threadIdx.x; f < p.f1; f += gridDim.x * blockDim.x) {
     double v;
     if (p.status[clip] == RM_CLIP_NO_ROI || p.status[clip] == RM_CLIP_NO_CORNERS) v = NAN;
     else if (f < 2) v = 0.0;
@@ -962,11 +983,19 @@ extern "C" int32_t rm_measure_workspace_bytes(rm_handle* h, int32_t max_roi_w, i
   return RM_OK;
 }
 
-static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
-                                 const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t first_frame,
-                                 int32_t n_frames, double* data_out, float* motion_out, int32_t* npts_out,
-                                 int32_t* status_io, float* pts_dbg, void* workspace, size_t workspace_bytes,
-                                 void* stream) {
+struct MeasureJob {
+  MeasureParams p;
+  MeasureLayout L;
+  LkSmemLayout SL;
+  float* pts0;
+  bool smem_path;
+};
+
+static int32_t measure_setup(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
+                             const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t first_frame,
+                             int32_t n_frames, double* data_out, float* motion_out, int32_t* npts_out,
+                             int32_t* status_io, float* pts_dbg, void* workspace, size_t workspace_bytes,
+                             MeasureJob* job) {
   RM_CHECK_ARG(h, h && frames && roi && data_out && motion_out && npts_out && status_io, "null pointer");
   RM_CHECK_ARG(h, n_clips >= 0 && T >= 1 && W >= 1 && H >= 1 && first_frame >= 0 && n_frames >= 1 &&
                       first_frame + n_frames <= T, "frame range outside the clip");
@@ -974,15 +1003,12 @@ static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_
   if (h->p.max_corners > LK_MAX_PTS || h->p.max_corners < 1 || h->p.lk_win < 3 || h->p.lk_win > 31 ||
       h->p.lk_win * h->p.lk_win > 256 || h->p.lk_max_level < 0 || h->p.lk_max_level >= LK_MAX_LEVELS)
     return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: needs max_corners <= 128, 3 <= lk_win <= 16, lk_max_level <= 3", __func__);
-  if (n_clips == 0) return RM_OK;
   MeasureLayout L = measure_layout(h, max_roi_w, max_roi_h, n_clips, n_frames);
-  if (!workspace || workspace_bytes < L.total)
+  if (n_clips > 0 && (!workspace || workspace_bytes < L.total))
     return rm_fail(h, RM_ERR_WORKSPACE, "%s: workspace too small (%lld needed, %lld given)", __func__, (long long)L.total,
                    (long long)workspace_bytes);
-  DeviceGuard dg(h->device);
-  cudaStream_t st = (cudaStream_t)stream;
   unsigned char* ws = reinterpret_cast<unsigned char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  MeasureParams p;
+  MeasureParams& p = job->p;
   memset(&p, 0, sizeof(p));
   p.frames = frames; p.roi = roi; p.lut = h->d_lut;
   p.n_clips = n_clips; p.T = T; p.W = W; p.H = H; p.first_frame = first_frame; p.n_frames = n_frames;
@@ -999,16 +1025,25 @@ static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_
   p.eig = reinterpret_cast<float*>(ws + L.eig);
   p.eigmax = reinterpret_cast<unsigned*>(ws + L.eigmax);
   p.cand = reinterpret_cast<unsigned long long*>(ws + L.cand);
-  float* pts0 = reinterpret_cast<float*>(ws + L.pts0);
+  job->pts0 = reinterpret_cast<float*>(ws + L.pts0);
   for (int l = 1; l < LK_MAX_LEVELS; ++l) {
     p.pyr[l] = L.lvl_elems[l] ? ws + L.pyr[l] : nullptr;
     p.lvl_elems[l] = L.lvl_elems[l];
   }
   p.motion = motion_out; p.data = data_out; p.npts = npts_out; p.status = status_io; p.pts_dbg = pts_dbg;
+  p.f0 = 0; p.f1 = n_frames;
+  job->L = L;
+  job->SL = lk_smem_layout(max_roi_w, max_roi_h, p.win, p.max_level, LKS_WARPS);
+  job->smem_path = job->SL.total + 4096 <= h->smem_optin && !h->force_global_lk;
+  return RM_OK;
+}
 
-  RM_CUDA(h, cudaMemsetAsync(p.eigmax, 0, (size_t)n_clips * 4, st));
-  const int roi_px = max_roi_w * max_roi_h;
-  dim3 g1(div_up(roi_px, 256) < 64 ? div_up(roi_px, 256) : 64, n_clips);
+// Shi-Tomasi corners of the first measure frame (base.py:365-366)
+static int32_t measure_gftt(rm_handle* h, MeasureJob* job, cudaStream_t st) {
+  const MeasureParams& p = job->p;
+  RM_CUDA(h, cudaMemsetAsync(p.eigmax, 0, (size_t)p.n_clips * 4, st));
+  const int roi_px = p.maxw * p.maxh;
+  dim3 g1(div_up(roi_px, 256) < 64 ? div_up(roi_px, 256) : 64, p.n_clips);
   RM_PROF(h, st, "gftt_cov_kernel");
   gftt_cov_kernel<<<g1, 256, 0, st>>>(p);
   RM_LAUNCH_CHECK(h);
@@ -1016,19 +1051,30 @@ static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_
   gftt_eig_kernel<<<g1, 256, 0, st>>>(p);
   RM_LAUNCH_CHECK(h);
   RM_PROF(h, st, "gftt_select_kernel");
-  gftt_select_kernel<<<n_clips, 256, 0, st>>>(p, pts0);
+  gftt_select_kernel<<<p.n_clips, 256, 0, st>>>(p, job->pts0);
   RM_LAUNCH_CHECK(h);
-  const LkSmemLayout SL = lk_smem_layout(max_roi_w, max_roi_h, p.win, p.max_level, LKS_WARPS);
-  if (SL.total + 4096 <= h->smem_optin && !h->force_global_lk) {
+  return RM_OK;
+}
+
+// LK over frames [f0, f1).  The shared-memory tracker can stop and resume at any frame (state in h->d_lk_*); the
+// global-memory fallback for very large ROIs runs the whole range at once (call it with f0 == 0 only).
+static int32_t measure_lk(rm_handle* h, MeasureJob* job, int f0, int f1, bool carry_state, cudaStream_t st) {
+  MeasureParams p = job->p;
+  p.f0 = f0; p.f1 = f1;
+  if (job->smem_path) {
+    p.st_pts = carry_state ? h->d_lk_pts : nullptr;
+    p.st_n = carry_state ? h->d_lk_n : nullptr;
     // production path: crops and their pyramids live in shared memory
-    RM_CUDA(h, cudaFuncSetAttribute(lk_track_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total));
+    RM_CUDA(h, cudaFuncSetAttribute(lk_track_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, job->SL.total));
     RM_PROF(h, st, "lk_track_smem_kernel");
-    lk_track_smem_kernel<<<n_clips, LKS_WARPS * 32, SL.total, st>>>(p, pts0, SL.total);
+    lk_track_smem_kernel<<<p.n_clips, LKS_WARPS * 32, job->SL.total, st>>>(p, job->pts0, job->SL.total);
     RM_LAUNCH_CHECK(h);
   } else {
+    if (f0 != 0) return RM_OK;          // done by the first call
+    p.f1 = p.n_frames;
     // ROI too large for shared memory: pyramids of every frame in the workspace, pixels fetched from global memory
     for (int l = 1; l < LK_MAX_LEVELS && l <= h->p.lk_max_level; ++l) {
-      dim3 g2(div_up(L.lvl_elems[l], 256) < 32 ? div_up(L.lvl_elems[l], 256) : 32, n_frames, n_clips);
+      dim3 g2(div_up(job->L.lvl_elems[l], 256) < 32 ? div_up(job->L.lvl_elems[l], 256) : 32, p.n_frames, p.n_clips);
       RM_PROF(h, st, "lk_pyr_kernel");
       lk_pyr_kernel<<<g2, 256, 0, st>>>(p, l);
       RM_LAUNCH_CHECK(h);
@@ -1036,13 +1082,85 @@ static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_
     const int pw = p.win + 3, dwid = p.win + 1;
     const size_t per_warp = (size_t)(((pw * pw + 1) & ~1) + 2 * dwid * dwid) * sizeof(short);
     RM_PROF(h, st, "lk_track_kernel");
-    lk_track_kernel<<<n_clips, LK_WARPS * 32, per_warp * LK_WARPS, st>>>(p, pts0);
+    lk_track_kernel<<<p.n_clips, LK_WARPS * 32, per_warp * LK_WARPS, st>>>(p, job->pts0);
     RM_LAUNCH_CHECK(h);
   }
-  dim3 g3(div_up(n_frames, 128), n_clips);
+  return RM_OK;
+}
+
+static int32_t measure_pca(rm_handle* h, MeasureJob* job, int f0, int f1, cudaStream_t st) {
+  MeasureParams p = job->p;
+  p.f0 = f0; p.f1 = f1;
+  dim3 g3(div_up(f1 - f0, 128), p.n_clips);
   RM_PROF(h, st, "motion_pca_kernel");
   motion_pca_kernel<<<g3, 128, 0, st>>>(p);
   RM_LAUNCH_CHECK(h);
+  return RM_OK;
+}
+
+static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
+                                 const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t first_frame,
+                                 int32_t n_frames, double* data_out, float* motion_out, int32_t* npts_out,
+                                 int32_t* status_io, float* pts_dbg, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  MeasureJob job;
+  int32_t rc = measure_setup(h, frames, n_clips, T, W, H, roi, max_roi_w, max_roi_h, first_frame, n_frames, data_out,
+                             motion_out, npts_out, status_io, pts_dbg, workspace, workspace_bytes, &job);
+  if (rc != RM_OK || n_clips == 0) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = measure_gftt(h, &job, st)) != RM_OK) return rc;
+  if ((rc = measure_lk(h, &job, 0, n_frames, false, st)) != RM_OK) return rc;
+  return measure_pca(h, &job, 0, n_frames, st);
+}
+
+// extract_motion + measure() for whole clips as one pipeline (base.py:464-495): rm_measure_flow followed by
+// rm_signal_bpm, except that the tracker walks the frames in `measure_chunks` chunks on the caller's stream and the
+// signal stage of every finished chunk runs on streams owned by the handle underneath the next chunk's tracking: PCA,
+// filtfilt and peak picking in frame order on one stream, the Gaussian-fit gate + BPM of each chunk on its own stream
+// (a handful of fits run ten times longer than the rest; their tails must not queue behind each other).  Both stages are latency bound (sequential frames; sequential LM
+// iterations), so overlapping them is what shortens the step.  Results are identical to the two separate calls.
+extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
+                                     const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t first_frame,
+                                     int32_t n_frames, double fps, double* data_out, float* motion_out,
+                                     int32_t* npts_out, int32_t* status_io, double* bpm_out, double* filtered_out,
+                                     int32_t* peaks_out, int32_t* npeaks_out, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  RM_CHECK_ARG(h, h && bpm_out && fps > 0, "null pointer or bad fps");
+  MeasureJob job;
+  int32_t rc = measure_setup(h, frames, n_clips, T, W, H, roi, max_roi_w, max_roi_h, first_frame, n_frames, data_out,
+                             motion_out, npts_out, status_io, nullptr, workspace, workspace_bytes, &job);
+  if (rc != RM_OK || n_clips == 0) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t sa = (cudaStream_t)stream, sb = h->aux_stream;
+  int n_chunks = job.smem_path ? h->measure_chunks : 1;
+  if (n_chunks > n_frames) n_chunks = n_frames;
+  if (n_chunks > RM_MAX_CHUNKS) n_chunks = RM_MAX_CHUNKS;
+  if (h->lk_state_cap < n_clips) {
+    if (h->d_lk_pts) cudaFree(h->d_lk_pts);
+    if (h->d_lk_n) cudaFree(h->d_lk_n);
+    h->d_lk_pts = nullptr; h->d_lk_n = nullptr; h->lk_state_cap = 0;
+    RM_CUDA(h, cudaMalloc((void**)&h->d_lk_pts, (size_t)n_clips * LK_MAX_PTS * 2 * sizeof(float)));
+    RM_CUDA(h, cudaMalloc((void**)&h->d_lk_n, (size_t)n_clips * sizeof(int)));
+    h->lk_state_cap = n_clips;
+  }
+  // everything that allocates happens before the first launch
+  if ((rc = rmi_signal_setup(h, data_out, n_clips, n_frames, fps, bpm_out, filtered_out, peaks_out, npeaks_out, status_io,
+                             n_chunks, sa)) != RM_OK)
+    return rc;
+  if ((rc = measure_gftt(h, &job, sa)) != RM_OK) return rc;
+  RM_CUDA(h, cudaEventRecord(h->ev_fork, sa));
+  RM_CUDA(h, cudaStreamWaitEvent(sb, h->ev_fork, 0));
+  for (int c = 0; c < n_chunks; ++c) {
+    const int f0 = (int)((long long)n_frames * c / n_chunks), f1 = (int)((long long)n_frames * (c + 1) / n_chunks);
+    if ((rc = measure_lk(h, &job, f0, f1, n_chunks > 1, sa)) != RM_OK) return rc;
+    RM_CUDA(h, cudaEventRecord(h->ev_chunk[c], sa));
+    RM_CUDA(h, cudaStreamWaitEvent(sb, h->ev_chunk[c], 0));
+    if ((rc = measure_pca(h, &job, f0, f1, sb)) != RM_OK) return rc;
+    if ((rc = rmi_signal_range(h, f0, f1, c, sb, h->fit_stream[c], h->ev_filt[c])) != RM_OK) return rc;
+    RM_CUDA(h, cudaEventRecord(h->ev_done[c], h->fit_stream[c]));
+  }
+  for (int c = 0; c < n_chunks; ++c) RM_CUDA(h, cudaStreamWaitEvent(sa, h->ev_done[c], 0));   // join
   return RM_OK;
 }
 

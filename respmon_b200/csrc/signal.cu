@@ -11,6 +11,7 @@ struct SignalParams {
   const double* data;     // (n_clips, n_frames)
   const int32_t* status;  // (n_clips) or null
   int n_clips, n_frames;
+  int f0, f1;             // windows (frames) handled by this launch
   double dt;              // 1 / fps
   double b[SC_MAX_ORDER + 1], a[SC_MAX_ORDER + 1];
   int nc;                 // filter_order + 1
@@ -50,8 +51,8 @@ struct SignalScratch {
 
 __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalParams p, const SignalScratch s) {
   const int clip = blockIdx.y;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= p.n_frames) return;
+  const int f = p.f0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= p.f1) return;
   const long long win = (long long)clip * p.n_frames + f;
   const bool clip_ok = !p.status || p.status[clip] == RM_CLIP_OK || p.status[clip] == RM_CLIP_TRACK_LOST;
   const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
@@ -95,7 +96,10 @@ __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalPar
 #define SIG_FIT_G 8
 #endif
 template <int G>
-__global__ void __launch_bounds__(SIG_FIT_THREADS) signal_fit_kernel(const SignalParams p, const SignalScratch s,
+#ifndef SIG_FIT_MINB
+#define SIG_FIT_MINB 1
+#endif
+__global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_kernel(const SignalParams p, const SignalScratch s,
                                                                       int m_cap) {
   extern __shared__ __align__(16) double fit_smem[];
   const int lane = threadIdx.x & 31;
@@ -145,8 +149,8 @@ __global__ void __launch_bounds__(SIG_FIT_THREADS) signal_fit_kernel(const Signa
 // Stage C, one thread per window: BPM = 60 / mean interval of the accepted peaks (base.py:347-352).
 __global__ void signal_bpm_kernel(const SignalParams p, const SignalScratch s) {
   const int clip = blockIdx.y;
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= p.n_frames) return;
+  const int f = p.f0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= p.f1) return;
   const long long win = (long long)clip * p.n_frames + f;
   const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
   const double* t = p.tvals + (f + 1 - n);
@@ -191,15 +195,27 @@ __global__ void pack_results_kernel(const double* __restrict__ bpm, const int32_
   out[clip] = r;
 }
 
-extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps,
-                                 double* bpm_out, double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out,
-                                 const int32_t* status, void* stream) {
+struct SignalJob {
+  SignalParams p;
+  SignalScratch sc;        // queue / queue_n / cursor are those of chunk 0; chunk c uses its own slice
+  int m_cap, n_chunks, grid_cap;
+  size_t fit_smem, max_items_per_frame;
+};
+
+// Validation, filter design, time axis and scratch for measure() over (n_clips, n_frames) windows that will be
+// processed in up to n_chunks frame ranges (possibly concurrently with the producer of `data`).  Allocates; launches
+// only tvals_kernel (on st).
+int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps, double* bpm_out,
+                         double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, const int32_t* status,
+                         int n_chunks, cudaStream_t st) {
   RM_CHECK_ARG(h, h && data && bpm_out && n_clips >= 0 && n_frames >= 1 && fps > 0, "null pointer or bad size");
   const int order = h->p.filter_order;
   if (order < 1 || order > SC_MAX_ORDER || h->p.measure_buffer_len > SC_MAX_WIN || h->p.measure_buffer_len < 2)
     return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: needs filter_order <= 7 and measure_buffer_len <= 128", __func__);
-  if (n_clips == 0) return RM_OK;
-  SignalParams p;
+  if (!h->sig_job) h->sig_job = calloc(1, sizeof(SignalJob));
+  if (!h->sig_job) return rm_fail(h, RM_ERR_INVALID, "%s: out of host memory", __func__);
+  SignalJob* job = reinterpret_cast<SignalJob*>(h->sig_job);
+  SignalParams& p = job->p;
   memset(&p, 0, sizeof(p));
   // butter_lowpass(cutoff = freq_max*0.5, fs = fps): normal_cutoff = cutoff / (0.5*fs)  (transforms.py:59-60, base.py:342)
   const double wn = (h->p.freq_max * 0.5) / (0.5 * fps);
@@ -209,12 +225,14 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
   p.width = (int)floor(fps / h->p.freq_max);       // base.py:441
   if (2 * p.width > SC_MAX_FIT) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: fps/freq_max > 32 not supported", __func__);
   p.data = data; p.status = status; p.n_clips = n_clips; p.n_frames = n_frames;
+  p.f0 = 0; p.f1 = n_frames;
   p.dt = 1.0 / fps;
   p.buf_len = h->p.measure_buffer_len; p.init_len = h->p.measure_init_len;
   p.thres = h->p.peak_threshold; p.cutoff = h->p.gaussian_cutoff;
   p.bpm = bpm_out; p.filtered = filtered_out; p.peaks = peaks_out; p.npeaks = npeaks_out;
+  job->n_chunks = n_chunks < 1 ? 1 : (n_chunks > RM_MAX_CHUNKS ? RM_MAX_CHUNKS : n_chunks);
+  if (n_clips == 0) return RM_OK;
   DeviceGuard dg(h->device);
-  cudaStream_t st = (cudaStream_t)stream;
   if (h->tvals_cap < n_frames) {
     if (h->d_tvals) cudaFree(h->d_tvals);
     h->d_tvals = nullptr;
@@ -223,9 +241,6 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
     h->tvals_cap = n_frames;
   }
   p.tvals = h->d_tvals;
-  RM_PROF(h, st, "tvals_kernel");
-  tvals_kernel<<<1, 32, 0, st>>>(p.tvals, n_frames, p.dt);
-  RM_LAUNCH_CHECK(h);
   // scratch owned by the handle, grown on demand
   const size_t n_win = (size_t)n_clips * n_frames;
   const size_t need = n_win * p.buf_len * 8 + n_win * SIG_MAX_CAND * 2 + n_win * 4 + n_win * SIG_MAX_CAND * 4 + 1024;
@@ -236,44 +251,75 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
     RM_CUDA(h, cudaMalloc(&h->d_sig_scratch, need));
     h->sig_scratch_bytes = need;
   }
-  SignalScratch sc;
+  SignalScratch& sc = job->sc;
   unsigned char* base = reinterpret_cast<unsigned char*>(h->d_sig_scratch);
   sc.filt = reinterpret_cast<double*>(base);                base += n_win * p.buf_len * 8;
   sc.queue = reinterpret_cast<unsigned*>(base);             base += n_win * SIG_MAX_CAND * 4;
   sc.ncand = reinterpret_cast<int*>(base);                  base += n_win * 4;
-  sc.queue_n = reinterpret_cast<unsigned*>(base);           base += 256;
+  sc.queue_n = reinterpret_cast<unsigned*>(base);           base += 256;   // 2 counters per chunk (RM_MAX_CHUNKS <= 32)
   sc.cand = base;                                           base += n_win * SIG_MAX_CAND;
   sc.acc = base;
   sc.cursor = sc.queue_n + 1;
-  RM_CUDA(h, cudaMemsetAsync(sc.queue_n, 0, 8, st));
-  dim3 grid(div_up(n_frames, 64), n_clips);
+  // every window holds at most (buf_len / width + 1) candidates that survive min_dist = width
+  job->m_cap = 2 * p.width < SC_MAX_FIT ? 2 * p.width : SC_MAX_FIT;
+  if (job->m_cap < 4) job->m_cap = 4;
+  const int groups = SIG_FIT_THREADS / SIG_FIT_G;
+  job->fit_smem = (size_t)groups * 7 * job->m_cap * sizeof(double);
+  const size_t per_win = (size_t)(p.buf_len / (p.width > 0 ? p.width : 1)) + 2;
+  job->max_items_per_frame = (size_t)n_clips * (per_win < SIG_MAX_CAND ? per_win : SIG_MAX_CAND);
+  int per_sm = 0;
+  RM_CUDA(h, cudaFuncSetAttribute(signal_fit_kernel<SIG_FIT_G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)job->fit_smem));
+  RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, signal_fit_kernel<SIG_FIT_G>, SIG_FIT_THREADS,
+                                                           job->fit_smem));
+  job->grid_cap = h->sm_count * (per_sm > 0 ? per_sm : 1);   // persistent grid: what can be resident
+  RM_CUDA(h, cudaMemsetAsync(sc.queue_n, 0, 256, st));
+  RM_PROF(h, st, "tvals_kernel");
+  tvals_kernel<<<1, 32, 0, st>>>(p.tvals, n_frames, p.dt);
+  RM_LAUNCH_CHECK(h);
+  return RM_OK;
+}
+
+// measure() for the windows ending at frames [f0, f1) (chunk index `chunk` selects the fit queue) on stream st.
+int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t st, cudaStream_t st_fit,
+                         cudaEvent_t ev_filtered) {
+  SignalJob* job = reinterpret_cast<SignalJob*>(h->sig_job);
+  if (!job || chunk < 0 || chunk >= RM_MAX_CHUNKS) return rm_fail(h, RM_ERR_INVALID, "%s: no signal job", __func__);
+  if (job->p.n_clips == 0 || f1 <= f0) return RM_OK;
+  SignalParams p = job->p;
+  SignalScratch sc = job->sc;
+  p.f0 = f0; p.f1 = f1;
+  sc.queue = job->sc.queue + (size_t)p.n_clips * f0 * SIG_MAX_CAND;   // a slice no other chunk's windows can reach
+  sc.queue_n = job->sc.queue_n + 2 * chunk;
+  sc.cursor = sc.queue_n + 1;
+  dim3 grid(div_up(f1 - f0, 64), p.n_clips);
   RM_PROF(h, st, "signal_filter_peaks_kernel");
   signal_filter_peaks_kernel<<<grid, 64, 0, st>>>(p, sc);
   RM_LAUNCH_CHECK(h);
-  {
-    // every window holds at most (buf_len / width + 1) candidates that survive min_dist = width
-    int m_cap = 2 * p.width < SC_MAX_FIT ? 2 * p.width : SC_MAX_FIT;
-    if (m_cap < 4) m_cap = 4;
-    const int groups = SIG_FIT_THREADS / SIG_FIT_G;
-    const size_t fit_smem = (size_t)groups * 7 * m_cap * sizeof(double);
-    // persistent grid: as many blocks as can be resident (register limited), never more than there can be fits
-    const size_t per_win = (size_t)(p.buf_len / (p.width > 0 ? p.width : 1)) + 2;
-    const size_t max_items = n_win * (per_win < SIG_MAX_CAND ? per_win : SIG_MAX_CAND);
-    int per_sm = 0;
-    RM_CUDA(h, cudaFuncSetAttribute(signal_fit_kernel<SIG_FIT_G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)fit_smem));
-    RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, signal_fit_kernel<SIG_FIT_G>, SIG_FIT_THREADS,
-                                                             fit_smem));
-    long long grid_fit = (long long)h->sm_count * (per_sm > 0 ? per_sm : 1);
-    if (grid_fit > div_up((long long)max_items, groups)) grid_fit = div_up((long long)max_items, groups);
-    RM_PROF(h, st, "signal_fit_kernel");
-    signal_fit_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, fit_smem, st>>>(p, sc, m_cap);
-    RM_LAUNCH_CHECK(h);
+  if (st_fit != st) {   // the fits (and the BPM that folds them) continue on their own stream
+    RM_CUDA(h, cudaEventRecord(ev_filtered, st));
+    RM_CUDA(h, cudaStreamWaitEvent(st_fit, ev_filtered, 0));
   }
-  RM_PROF(h, st, "signal_bpm_kernel");
-  signal_bpm_kernel<<<grid, 64, 0, st>>>(p, sc);
+  const int groups = SIG_FIT_THREADS / SIG_FIT_G;
+  long long grid_fit = div_up((long long)(job->max_items_per_frame * (size_t)(f1 - f0)), groups);
+  if (grid_fit > job->grid_cap) grid_fit = job->grid_cap;
+  RM_PROF(h, st_fit, "signal_fit_kernel");
+  signal_fit_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, job->fit_smem, st_fit>>>(p, sc, job->m_cap);
+  RM_LAUNCH_CHECK(h);
+  RM_PROF(h, st_fit, "signal_bpm_kernel");
+  signal_bpm_kernel<<<grid, 64, 0, st_fit>>>(p, sc);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
+}
+
+extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps,
+                                 double* bpm_out, double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out,
+                                 const int32_t* status, void* stream) {
+  int32_t rc = rmi_signal_setup(h, data, n_clips, n_frames, fps, bpm_out, filtered_out, peaks_out, npeaks_out, status, 1,
+                                (cudaStream_t)stream);
+  if (rc != RM_OK || n_clips == 0) return rc;
+  DeviceGuard dg(h->device);
+  return rmi_signal_range(h, 0, n_frames, 0, (cudaStream_t)stream, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, const int32_t* status,

@@ -122,10 +122,11 @@ RM_HD int sc_peak_indexes(const double* y, int n, double thres_frac, int min_dis
 }
 
 // ------------------------------------------------------------------------------------------------ MINPACK (lmdif)
-RM_HD double sc_enorm(int n, const double* x) {
+RM_HD_NOINLINE double sc_enorm(int n, const double* x) {
   const double rdwarf = 3.834e-20, rgiant = 1.304e19;
   double s1 = 0.0, s2 = 0.0, s3 = 0.0, x1max = 0.0, x3max = 0.0;
   const double agiant = rgiant / (double)n;
+#pragma unroll 1
   for (int i = 0; i < n; ++i) {
     const double xabs = fabs(x[i]);
     if (xabs > rdwarf && xabs < agiant) {
@@ -162,6 +163,7 @@ RM_HD double sc_enorm(int n, const double* x) {
 // peakutils.gaussian residuals: ampl * exp(-(x - center)^2 / (2 dev^2 + eps)) - y
 RM_HD void sc_gauss_resid(int m, const double* xs, const double* ys, const double* p, double* f) {
   const double denom = 2.0 * (p[2] * p[2]) + SC_DBL_EPS;
+#pragma unroll 1
   for (int i = 0; i < m; ++i) {
     const double d = xs[i] - p[1];
     f[i] = p[0] * exp(-(d * d) / denom) - ys[i];
@@ -171,6 +173,7 @@ RM_HD void sc_gauss_resid(int m, const double* xs, const double* ys, const doubl
 // QR with column pivoting, a is m x 3 column-major (lda = m)
 RM_HD void sc_qrfac(int m, double* a, int* ipvt, double* rdiag, double* acnorm, double* wa) {
   const int n = SC_NP;
+#pragma unroll 1
   for (int j = 0; j < n; ++j) {
     acnorm[j] = sc_enorm(m, a + j * m);
     rdiag[j] = acnorm[j];
@@ -178,11 +181,14 @@ RM_HD void sc_qrfac(int m, double* a, int* ipvt, double* rdiag, double* acnorm, 
     ipvt[j] = j;
   }
   const int minmn = m < n ? m : n;
+#pragma unroll 1
   for (int j = 0; j < minmn; ++j) {
     int kmax = j;
+#pragma unroll 1
     for (int k = j; k < n; ++k)
       if (rdiag[k] > rdiag[kmax]) kmax = k;
     if (kmax != j) {
+#pragma unroll 1
       for (int i = 0; i < m; ++i) { double t = a[i + j * m]; a[i + j * m] = a[i + kmax * m]; a[i + kmax * m] = t; }
       rdiag[kmax] = rdiag[j];
       wa[kmax] = wa[j];
@@ -191,12 +197,16 @@ RM_HD void sc_qrfac(int m, double* a, int* ipvt, double* rdiag, double* acnorm, 
     double ajnorm = sc_enorm(m - j, a + j + j * m);
     if (ajnorm != 0.0) {
       if (a[j + j * m] < 0.0) ajnorm = -ajnorm;
+#pragma unroll 1
       for (int i = j; i < m; ++i) a[i + j * m] /= ajnorm;
       a[j + j * m] += 1.0;
+#pragma unroll 1
       for (int k = j + 1; k < n; ++k) {
         double sum = 0.0;
+#pragma unroll 1
         for (int i = j; i < m; ++i) sum += a[i + j * m] * a[i + k * m];
         const double temp = sum / a[j + j * m];
+#pragma unroll 1
         for (int i = j; i < m; ++i) a[i + k * m] -= temp * a[i + j * m];
         if (rdiag[k] != 0.0) {
           double t = a[j + k * m] / rdiag[k];
@@ -214,20 +224,25 @@ RM_HD void sc_qrfac(int m, double* a, int* ipvt, double* rdiag, double* acnorm, 
   }
 }
 
-RM_HD void sc_qrsolv(double* r, int ldr, const int* ipvt, const double* diag, const double* qtb, double* x,
+RM_HD_NOINLINE void sc_qrsolv(double* r, int ldr, const int* ipvt, const double* diag, const double* qtb, double* x,
                      double* sdiag, double* wa) {
   const int n = SC_NP;
+#pragma unroll 1
   for (int j = 0; j < n; ++j) {
+#pragma unroll 1
     for (int i = j; i < n; ++i) r[i + j * ldr] = r[j + i * ldr];
     x[j] = r[j + j * ldr];
     wa[j] = qtb[j];
   }
+#pragma unroll 1
   for (int j = 0; j < n; ++j) {
     const int l = ipvt[j];
     if (diag[l] != 0.0) {
+#pragma unroll 1
       for (int k = j; k < n; ++k) sdiag[k] = 0.0;
       sdiag[j] = diag[l];
       double qtbpj = 0.0;
+#pragma unroll 1
       for (int k = j; k < n; ++k) {
         if (sdiag[k] != 0.0) {
           double cs, sn;
@@ -244,6 +259,7 @@ RM_HD void sc_qrsolv(double* r, int ldr, const int* ipvt, const double* diag, co
           double temp = cs * wa[k] + sn * qtbpj;
           qtbpj = -sn * wa[k] + cs * qtbpj;
           wa[k] = temp;
+#pragma unroll 1
           for (int i = k + 1; i < n; ++i) {
             temp = cs * r[i + k * ldr] + sn * sdiag[i];
             sdiag[i] = -sn * r[i + k * ldr] + cs * sdiag[i];
@@ -256,54 +272,68 @@ RM_HD void sc_qrsolv(double* r, int ldr, const int* ipvt, const double* diag, co
     r[j + j * ldr] = x[j];
   }
   int nsing = n;
+#pragma unroll 1
   for (int j = 0; j < n; ++j) {
     if (sdiag[j] == 0.0 && nsing == n) nsing = j;
     if (nsing < n) wa[j] = 0.0;
   }
+#pragma unroll 1
   for (int k = 1; k <= nsing; ++k) {
     const int j = nsing - k;
     double sum = 0.0;
+#pragma unroll 1
     for (int i = j + 1; i < nsing; ++i) sum += r[i + j * ldr] * wa[i];
     wa[j] = (wa[j] - sum) / sdiag[j];
   }
+#pragma unroll 1
   for (int j = 0; j < n; ++j) x[ipvt[j]] = wa[j];
 }
 
-RM_HD void sc_lmpar(double* r, int ldr, const int* ipvt, const double* diag, const double* qtb, double delta,
+RM_HD_NOINLINE void sc_lmpar(double* r, int ldr, const int* ipvt, const double* diag, const double* qtb, double delta,
                     double* par, double* x, double* sdiag, double* wa1, double* wa2) {
   const int n = SC_NP;
   const double p1 = 0.1, p001 = 0.001, dwarf = SC_DBL_MIN;
   int nsing = n;
+#pragma unroll 1
   for (int j = 0; j < n; ++j) {
     wa1[j] = qtb[j];
     if (r[j + j * ldr] == 0.0 && nsing == n) nsing = j;
     if (nsing < n) wa1[j] = 0.0;
   }
+#pragma unroll 1
   for (int k = 1; k <= nsing; ++k) {
     const int j = nsing - k;
     wa1[j] /= r[j + j * ldr];
     const double temp = wa1[j];
+#pragma unroll 1
     for (int i = 0; i < j; ++i) wa1[i] -= r[i + j * ldr] * temp;
   }
+#pragma unroll 1
   for (int j = 0; j < n; ++j) x[ipvt[j]] = wa1[j];
   int iter = 0;
+#pragma unroll 1
   for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
   double dxnorm = sc_enorm(n, wa2);
   double fp = dxnorm - delta;
   if (fp <= p1 * delta) { *par = 0.0; return; }
   double parl = 0.0;
   if (nsing >= n) {
+#pragma unroll 1
     for (int j = 0; j < n; ++j) { const int l = ipvt[j]; wa1[j] = diag[l] * (wa2[l] / dxnorm); }
+#pragma unroll 1
     for (int j = 0; j < n; ++j) {
       double sum = 0.0;
+#pragma unroll 1
       for (int i = 0; i < j; ++i) sum += r[i + j * ldr] * wa1[i];
       wa1[j] = (wa1[j] - sum) / r[j + j * ldr];
     }
     const double temp = sc_enorm(n, wa1);
     parl = fp / delta / temp / temp;
   }
+#pragma unroll 1
   for (int j = 0; j < n; ++j) {
     double sum = 0.0;
+#pragma unroll 1
     for (int i = 0; i <= j; ++i) sum += r[i + j * ldr] * qtb[i];
     wa1[j] = sum / diag[ipvt[j]];
   }
@@ -313,21 +343,27 @@ RM_HD void sc_lmpar(double* r, int ldr, const int* ipvt, const double* diag, con
   *par = *par > parl ? *par : parl;
   *par = *par < paru ? *par : paru;
   if (*par == 0.0) *par = gnorm / dxnorm;
+#pragma unroll 1
   for (;;) {
     ++iter;
     if (*par == 0.0) { const double t = p001 * paru; *par = dwarf > t ? dwarf : t; }
     double temp = sqrt(*par);
+#pragma unroll 1
     for (int j = 0; j < n; ++j) wa1[j] = temp * diag[j];
     sc_qrsolv(r, ldr, ipvt, wa1, qtb, x, sdiag, wa2);
+#pragma unroll 1
     for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
     dxnorm = sc_enorm(n, wa2);
     temp = fp;
     fp = dxnorm - delta;
     if (fabs(fp) <= p1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+#pragma unroll 1
     for (int j = 0; j < n; ++j) { const int l = ipvt[j]; wa1[j] = diag[l] * (wa2[l] / dxnorm); }
+#pragma unroll 1
     for (int j = 0; j < n; ++j) {
       wa1[j] /= sdiag[j];
       temp = wa1[j];
+#pragma unroll 1
       for (int i = j + 1; i < n; ++i) wa1[i] -= r[i + j * ldr] * temp;
     }
     temp = sc_enorm(n, wa1);
@@ -359,9 +395,11 @@ RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, dou
   sc_gauss_resid(m, xs, ys, x, fvec);
   nfev = 1;
   double fnorm = sc_enorm(m, fvec);
+#pragma unroll 1
   for (;;) {
     {   // fdjac2: forward differences
       const double eps = sqrt(epsfcn > epsmch ? epsfcn : epsmch);
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         const double temp = x[j];
         double h = eps * fabs(temp);
@@ -369,24 +407,31 @@ RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, dou
         x[j] = temp + h;
         sc_gauss_resid(m, xs, ys, x, wa4);
         x[j] = temp;
+#pragma unroll 1
         for (int i = 0; i < m; ++i) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
       }
       nfev += n;
     }
     sc_qrfac(m, fjac, ipvt, wa1, wa2, wa3);
     if (iter == 1) {
+#pragma unroll 1
       for (int j = 0; j < n; ++j) { diag[j] = wa2[j]; if (wa2[j] == 0.0) diag[j] = 1.0; }
+#pragma unroll 1
       for (int j = 0; j < n; ++j) wa3[j] = diag[j] * x[j];
       xnorm = sc_enorm(n, wa3);
       delta = factor * xnorm;
       if (delta == 0.0) delta = factor;
     }
+#pragma unroll 1
     for (int i = 0; i < m; ++i) wa4[i] = fvec[i];
+#pragma unroll 1
     for (int j = 0; j < n; ++j) {
       if (fjac[j + j * m] != 0.0) {
         double sum = 0.0;
+#pragma unroll 1
         for (int i = j; i < m; ++i) sum += fjac[i + j * m] * wa4[i];
         const double temp = -sum / fjac[j + j * m];
+#pragma unroll 1
         for (int i = j; i < m; ++i) wa4[i] += fjac[i + j * m] * temp;
       }
       fjac[j + j * m] = wa1[j];
@@ -394,10 +439,12 @@ RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, dou
     }
     gnorm = 0.0;
     if (fnorm != 0.0) {
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         const int l = ipvt[j];
         if (wa2[l] != 0.0) {
           double sum = 0.0;
+#pragma unroll 1
           for (int i = 0; i <= j; ++i) sum += fjac[i + j * m] * (qtf[i] / fnorm);
           const double g = fabs(sum / wa2[l]);
           gnorm = gnorm > g ? gnorm : g;
@@ -405,10 +452,12 @@ RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, dou
       }
     }
     if (gnorm <= gtol) { info = 4; break; }
+#pragma unroll 1
     for (int j = 0; j < n; ++j) diag[j] = diag[j] > wa2[j] ? diag[j] : wa2[j];
     double ratio = 0.0;
     do {
       sc_lmpar(fjac, m, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         wa1[j] = -wa1[j];
         wa2[j] = x[j] + wa1[j];
@@ -421,9 +470,11 @@ RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, dou
       const double fnorm1 = sc_enorm(m, wa4);
       double actred = -1.0;
       if (p1 * fnorm1 < fnorm) { const double d = fnorm1 / fnorm; actred = 1.0 - d * d; }
+#pragma unroll 1
       for (int j = 0; j < n; ++j) {
         wa3[j] = 0.0;
         const double temp = wa1[ipvt[j]];
+#pragma unroll 1
         for (int i = 0; i <= j; ++i) wa3[i] += fjac[i + j * m] * temp;
       }
       const double temp1 = sc_enorm(n, wa3) / fnorm;
@@ -445,7 +496,9 @@ RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, dou
         par = p5 * par;
       }
       if (ratio >= p0001) {
+#pragma unroll 1
         for (int j = 0; j < n; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
+#pragma unroll 1
         for (int i = 0; i < m; ++i) fvec[i] = wa4[i];
         xnorm = sc_enorm(n, wa2);
         fnorm = fnorm1;

@@ -253,7 +253,7 @@ class Engine:
     # ------------------------------------------------------------------ whole clips
     def run_batch(self, clips: torch.Tensor, fps: float, cal_first: int = 1, cal_len: int = 128,
                   measure_first: int | None = None, method: str = "flow", keep: bool = False,
-                  out: torch.Tensor | None = None):
+                  out: torch.Tensor | None = None, max_roi: tuple[int, int] | None = None):
         """The frame routing of run() (base.py:409-513) on a batch of whole clips resident in HBM.
 
         clips (n,T,H,W) uint8.  Frame 0 is dropped by 'initialize' (base.py:423-425), frames cal_first ..
@@ -268,15 +268,16 @@ class Engine:
         assert cal_first >= 0 and cal_first + cal_len <= T and n_meas >= 1
         roi, status, heat = self.locate(clips, fps, cal_first, cal_len)
         if method == "flow":
-            m = self.measure_flow(clips, roi, measure_first, n_meas, status=status)
-            data = m["data"]
+            m = self.measure_signal(clips, roi, measure_first, n_meas, fps, status=status, max_roi=max_roi)
+            sig = {k: m[k] for k in ("bpm", "filtered", "peaks", "npeaks")}
+            m = {k: m[k] for k in ("data", "motion", "npts")}
         else:
             data = self.measure_average(clips, roi, measure_first, n_meas)
-            m = dict(data=data, status=status)
-        sig = self.signal_bpm(data, fps, status=status)
+            m = dict(data=data)
+            sig = self.signal_bpm(data, fps, status=status)
         rec = self.pack_results(sig["bpm"], roi, status, sig["npeaks"], out=out)
         if keep:
-            return rec, dict(roi=roi, status=status, heat=heat, **{k: v for k, v in m.items() if k != "status"}, **sig)
+            return rec, dict(roi=roi, status=status, heat=heat, **m, **sig)
         return rec
 
     # ------------------------------------------------------------------ synthetic data
@@ -327,6 +328,34 @@ class Engine:
             self._call("rm_measure_flow", _ptr(clips), n, T, W, H, _ptr(roi), mw, mh, first_frame, n_frames,
                        _ptr(data), _ptr(motion), _ptr(npts), _ptr(status), _ptr(ws), ws.numel(), self._stream())
         return out
+
+    def measure_signal(self, clips: torch.Tensor, roi: torch.Tensor, first_frame: int, n_frames: int, fps: float,
+                       status: torch.Tensor | None = None, max_roi: tuple[int, int] | None = None):
+        """measure_flow + signal_bpm as one overlapped pipeline (rm_measure_signal); same outputs as the two calls."""
+        assert clips.is_cuda and clips.dtype == torch.uint8 and clips.is_contiguous() and clips.dim() == 4
+        n, T, H, W = clips.shape
+        roi = roi.to(self.device, torch.int32).contiguous()
+        if status is None:
+            status = torch.zeros(n, dtype=torch.int32, device=self.device)
+        if max_roi is None:
+            r = roi.cpu()
+            max_roi = (max(1, int(r[:, 2].max())), max(1, int(r[:, 3].max()))) if n else (1, 1)
+        mw, mh = min(W, max_roi[0]), min(H, max_roi[1])
+        L = self.params.measure_buffer_len
+        data = torch.empty((n, n_frames), dtype=torch.float64, device=self.device)
+        motion = torch.empty((n, n_frames, 2), dtype=torch.float32, device=self.device)
+        npts = torch.zeros(n, dtype=torch.int32, device=self.device)
+        bpm = torch.empty((n, n_frames), dtype=torch.float64, device=self.device)
+        filt = torch.empty((n, L), dtype=torch.float64, device=self.device)
+        peaks = torch.empty((n, L), dtype=torch.int32, device=self.device)
+        npk = torch.zeros(n, dtype=torch.int32, device=self.device)
+        need = C.c_size_t()
+        self._call("rm_measure_workspace_bytes", mw, mh, n, n_frames, C.byref(need))
+        ws = self._workspace("measure", need.value)
+        self._call("rm_measure_signal", _ptr(clips), n, T, W, H, _ptr(roi), mw, mh, first_frame, n_frames, float(fps),
+                   _ptr(data), _ptr(motion), _ptr(npts), _ptr(status), _ptr(bpm), _ptr(filt), _ptr(peaks), _ptr(npk),
+                   _ptr(ws), ws.numel(), self._stream())
+        return dict(data=data, motion=motion, npts=npts, status=status, bpm=bpm, filtered=filt, peaks=peaks, npeaks=npk)
 
     def measure_average(self, clips: torch.Tensor, roi: torch.Tensor, first_frame: int, n_frames: int) -> torch.Tensor:
         """extract_motion 'average' (base.py:355-358)."""

@@ -193,3 +193,45 @@ def test_average_mode(eng, golden):
     got = eng.measure_average(dev(clip[None]), dev(fix["roi"].astype(np.int32)[None]), 130, 20).cpu().numpy()[0]
     want = [np.average(P.u8_to_unit(clip[130 + f, y:y + h, x:x + w])) for f in range(20)]
     assert np.abs(got - np.array(want)).max() < 1e-14
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 4, 16])
+def test_measure_signal_pipeline_equals_separate_calls(eng, golden, chunks):
+    """rm_measure_signal (chunked tracker + overlapped signal stage) == rm_measure_flow + rm_signal_bpm, bit for bit."""
+    from conftest import clip_from_fixture
+    fixes = [golden(n) for n in ("vga_s0", "vga_s2")]
+    clips = np.stack([clip_from_fixture(f)[1] for f in fixes])
+    roi = torch.tensor(np.stack([f["roi"] for f in fixes]), dtype=torch.int32).cuda()
+    d = torch.from_numpy(clips).cuda()
+    a = eng.measure_flow(d, roi, 130, 126)
+    sa = eng.signal_bpm(a["data"], 10.0, status=a["status"])
+    eng.set_option("measure_chunks", chunks)
+    try:
+        b = eng.measure_signal(d, roi, 130, 126, 10.0)
+    finally:
+        eng.set_option("measure_chunks", 8)
+    for k in ("data", "motion", "npts", "status"):
+        assert torch.equal(a[k], b[k]) or np.array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), equal_nan=True), k
+    for k in ("bpm", "filtered", "peaks", "npeaks"):
+        assert np.array_equal(sa[k].cpu().numpy(), b[k].cpu().numpy(), equal_nan=True), k
+    assert abs(float(b["bpm"][0, -1]) - fixes[0]["freq"][-1]) <= 0.5
+
+
+def test_measure_signal_pipeline_track_lost_in_a_later_chunk(eng):
+    """Points that leave the image in chunk 2 of 4: NaN from there on, earlier samples and BPMs untouched."""
+    from respmon_b200 import synth
+    clip = synth.make_clip(synth.clip_spec(3, 320, 240, 256))
+    spec = synth.clip_spec(3, 320, 240, 256)
+    clip = clip.copy()
+    clip[200:] = 0                                   # the texture vanishes at measure frame 70: every corner is lost
+    d = torch.from_numpy(clip[None]).cuda()
+    roi = torch.tensor([[spec.x0 + 4, spec.y0 + 4, spec.w0 - 8, spec.h0 - 8]], dtype=torch.int32).cuda()
+    a = eng.measure_flow(d, roi, 130, 126)
+    sa = eng.signal_bpm(a["data"], 10.0, status=a["status"])
+    b = eng.measure_signal(d, roi, 130, 126, 10.0)
+    assert int(b["status"][0]) == int(a["status"][0])
+    for k in ("data", "motion"):
+        assert np.array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), equal_nan=True), k
+    assert np.array_equal(sa["bpm"].cpu().numpy(), b["bpm"].cpu().numpy(), equal_nan=True)
+    data = b["data"].cpu().numpy()[0]
+    assert np.isfinite(data[:60]).all()

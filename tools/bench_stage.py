@@ -9,6 +9,8 @@ from respmon_b200.engine import Engine, results_to_numpy
 n_clips = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 eng = Engine(0)
+if os.environ.get("RM_CHUNKS"):
+    eng.set_option("measure_chunks", int(os.environ["RM_CHUNKS"]))
 specs = [synth.clip_spec(i, 640, 480, 256) for i in range(n_clips)]
 dq8 = np.stack([synth.displacement_q8(s) for s in specs])
 clips = eng.synth_clips(specs, dq8)
