@@ -182,6 +182,10 @@ def run_gpu_arm(args) -> dict | None:
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                             "sample": "failed: " + out.stderr[-300:]}
 
+    # libraries (NCCL's version banner, for one) print to stdout: keep fd 1 for the single JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -272,6 +276,9 @@ def run_gpu_arm(args) -> dict | None:
 
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank != 0:
         return None
 
@@ -287,8 +294,17 @@ def run_gpu_arm(args) -> dict | None:
         bytes_per_frame = W * H * 1 + (W // 8) * (H // 8) * 4  # frame read once (u8) + Gaussian level 3 written (u32)
         dur_s = front[0] / front[1] / 1e3
         achieved = frames_per_launch * bytes_per_frame / dur_s / 1e9
+        traffic, traffic_src = None, None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                tj = json.load(f)["pyramid_front_u8_kernel"]
+            traffic = tj["dram_bytes_per_frame"] * frames_per_launch
+            traffic_src = tj["source"]
+        except Exception:
+            pass
         roofline = {"kernel": "pyramid_front_u8_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src,
                     "bytes_per_launch": frames_per_launch * bytes_per_frame, "launch_ms": dur_s * 1e3,
                     "share_of_step": front[0] / total_kernel_ms}
     line = {
@@ -321,7 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU")
-    ap.add_argument("--chunk", type=int, default=8, help="clips per H2D chunk of the end-to-end leg")
+    ap.add_argument("--chunk", type=int, default=16, help="clips per H2D chunk of the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -64,10 +64,12 @@ class BatchMonitor:
     as ROI crops -- the reference itself only ever looks at `frame[y:y+h, x:x+w]` of those frames (base.py:471).
     Uploads run on a copy stream and overlap the kernels of the previous chunk (two buffers of each kind)."""
 
-    def __init__(self, device: int | None = None, chunk_clips: int = 8, method: str = "flow", crop_upload: bool = True,
-                 measure_streams: int = 3, **hyper):
+    def __init__(self, device: int | None = None, chunk_clips: int = 16, method: str = "flow", crop_upload: bool = True,
+                 measure_streams: int = 2, measure_chunks: int = 4, **hyper):
         self.engine = Engine(device, **hyper)
         self._measure_engines = [Engine(self.engine.device_index, **hyper) for _ in range(max(1, measure_streams))]
+        for e in self._measure_engines:
+            e.set_option("measure_chunks", measure_chunks)
         self._measure_streams = [torch.cuda.Stream(self.engine.device) for _ in self._measure_engines]
         self._crop_stream = torch.cuda.Stream(self.engine.device)
         self.chunk_clips = int(chunk_clips)
