@@ -201,8 +201,12 @@ __device__ __forceinline__ void block4x4(const double v[4][4], const AxisGeom& g
   }
 }
 
+#define HM_STAGES 4
+#define HM_PW 20            // pitch (doubles) of a staged level-2 patch: 64/4 + 3 columns, padded
+#define HM_PH 11            // 32/4 + 3 rows
+#define HM_COPIES 2         // ceil(19 * 11 / 128) cp.async per thread per frame
 template <int PASS, bool EDGE>
-__device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* red_a, double* red_b) {
+__device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* red_a, double* red_b, double* stage) {
   const int tile = blockIdx.x;
   const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
   const int clip = blockIdx.y;
@@ -240,15 +244,52 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
   const long long n2 = (long long)p.w[2] * p.h[2];
   const double* a_clip = p.a2 + (long long)clip * p.T * n2;
 
-  if (active) {
-#pragma unroll 2
-    for (int t = 0; t < p.T; ++t) {
+  // The tile's level-2 neighbourhood (at most 19 x 11 values per frame) is staged in shared memory by cp.async, HM_STAGES
+  // frames deep, so the loads of the register stage are shared-memory hits and the global latency hides behind the
+  // float64 work of the frames in between.  One __syncthreads per frame.
+  const int xlo = max(0, tx * (HM_TW / 4) - 1), xhi = min(p.w[2] - 1, tx * (HM_TW / 4) + HM_TW / 4 + 1);
+  const int ylo = max(0, ty * (HM_TH / 4) - 1), yhi = min(p.h[2] - 1, ty * (HM_TH / 4) + HM_TH / 4 + 1);
+  const int pwid = xhi - xlo + 1, n_patch = pwid * (yhi - ylo + 1);
+  int src_off[HM_COPIES], dst_off[HM_COPIES];
+#pragma unroll
+  for (int k = 0; k < HM_COPIES; ++k) {
+    const int e = tid + k * 128;
+    const int r = e / pwid, c = e - r * pwid;
+    src_off[k] = e < n_patch ? (ylo + r) * p.w[2] + xlo + c : -1;
+    dst_off[k] = r * HM_PW + c;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) offs[r][c] = (gy.v[r] - ylo) * HM_PW + (gx.v[c] - xlo);
+  const unsigned stage_base = (unsigned)__cvta_generic_to_shared(stage);
+  auto issue = [&](int t) {
+    if (t < p.T) {
       const double* l2 = a_clip + t * n2;
+      const unsigned dst = stage_base + (unsigned)((t % HM_STAGES) * HM_PW * HM_PH * 8);
+#pragma unroll
+      for (int k = 0; k < HM_COPIES; ++k)
+        if (src_off[k] >= 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + dst_off[k] * 8), "l"(l2 + src_off[k])
+                       : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+#pragma unroll
+  for (int t = 0; t < HM_STAGES - 1; ++t) issue(t);
+
+  {
+    for (int t = 0; t < p.T; ++t) {
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(HM_STAGES - 2) : "memory");
+      __syncthreads();                 // frame t has landed for everyone; everyone is done with frame t-1's stage
+      issue(t + HM_STAGES - 1);        // refills the stage frame t-1 used
+      if (!active) continue;
+      const double* l2 = stage + (t % HM_STAGES) * HM_PW * HM_PH;
       double v[4][4], o[4][4];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[r][c] = __ldg(l2 + offs[r][c]);
+        for (int c = 0; c < 4; ++c) v[r][c] = l2[offs[r][c]];
       block4x4<EDGE>(v, gx, gy, o);
       if (PASS == 1) {
         // Candidate filter on the high words: a new maximum above a positive running maximum is a positive double whose
@@ -341,11 +382,12 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
 template <int PASS>
 __global__ void __launch_bounds__(128) upsample_pass_kernel(const TileParams p) {
   __shared__ double red_a[4], red_b[4];
+  __shared__ __align__(16) double stage[HM_STAGES * HM_PW * HM_PH];
   const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
   // tiles that touch the right / bottom image border (or an unaligned row) take the guarded variant
   const bool edge = (tx + 1) * HM_TW >= p.w[0] || (ty + 1) * HM_TH >= p.h[0] || (p.w[0] & 1);
-  if (edge) upsample_pass_body<PASS, true>(p, red_a, red_b);
-  else upsample_pass_body<PASS, false>(p, red_a, red_b);
+  if (edge) upsample_pass_body<PASS, true>(p, red_a, red_b, stage);
+  else upsample_pass_body<PASS, false>(p, red_a, red_b, stage);
 }
 
 __global__ void minmax_init_kernel(unsigned long long* keys, int n_clips) {
