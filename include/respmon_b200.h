@@ -195,7 +195,7 @@ int32_t rm_measure_average(rm_handle* h, const uint8_t* frames, int32_t n_clips,
 int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps, double* bpm_out,
                       double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, const int32_t* status, void* stream);
 /* rm_measure_flow followed by rm_signal_bpm as one pipeline (the 'measure' branch of run(), base.py:464-495, over whole
- * clips): identical results, but the tracker walks the frames in chunks (option "measure_chunks", default 8) on `stream`
+ * clips): identical results, but the tracker walks the frames in chunks (option "measure_chunks", default 4) on `stream`
  * while the signal stage of the finished chunks runs underneath on a stream owned by the handle; `stream` is joined
  * before the call returns control of it.  Arguments as in the two separate calls; workspace as rm_measure_flow. */
 int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t T, int32_t W, int32_t H,
@@ -211,7 +211,15 @@ int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, con
 /* Number of kernel launches this handle has issued since creation (bench.py reports it as gpu_launches). */
 int64_t rm_launch_count(rm_handle* h);
 
-/* Switches.  "measure_chunks" (1..16): frame chunks of rm_measure_signal.  "force_global_lk" (0/1): track from global memory even when the ROI fits shared memory (the
+/* Deferred join.  With option "defer_join" = 1, rm_measure_signal returns without making `stream` wait for its signal
+ * stage and the rm_pack_results that follows runs behind that stage on a stream owned by the handle, so work enqueued on
+ * `stream` afterwards (the next batch's calibration) overlaps the longest Gaussian fits of this batch.  The outputs of
+ * both calls are complete only after rm_join(h, stream) -- which makes `stream` wait for them -- or after the next
+ * rm_measure_signal / rm_measure_flow / rm_signal_bpm on the handle, which join first.  Keep the output buffers alive
+ * until then. */
+int32_t rm_join(rm_handle* h, void* stream);
+
+/* Switches.  "defer_join" (0/1, see rm_join).  "measure_chunks" (1..16): frame chunks of rm_measure_signal.  "force_global_lk" (0/1): track from global memory even when the ROI fits shared memory (the
  * fallback used for ROIs too large to stage; results are identical). */
 int32_t rm_set_option(rm_handle* h, const char* host_name, int64_t value);
 

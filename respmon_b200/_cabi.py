@@ -80,6 +80,7 @@ SIGNATURES = {
     "rm_signal_bpm": (_i32, [_H, _P, _i32, _i32, _f64, _P, _P, _P, _P, _P, _S]),
     "rm_measure_signal": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _i32, _i32, _f64, _P, _P, _P, _P, _P, _P,
                                  _P, _P, _P, _sz, _S]),
+    "rm_join": (_i32, [_H, _S]),
     "rm_pack_results": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _P, _S]),
     "rm_launch_count": (_i64, [_H]),
     "rm_set_option": (_i32, [_H, C.c_char_p, _i64]),

@@ -117,10 +117,13 @@ extern "C" int32_t rm_create(const rm_params* params, int32_t device, rm_handle*
     free(h);
     return RM_ERR_CUDA;
   }
-  h->measure_chunks = 8;
+  h->measure_chunks = 4;
   bool ok = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&h->tail_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_packed, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_tail_fork, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < RM_MAX_CHUNKS; ++i) {
     ok = cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_filt[i], cudaEventDisableTiming) == cudaSuccess;
@@ -146,10 +149,14 @@ extern "C" int32_t rm_destroy(rm_handle* h) {
     if (h->d_sig_scratch) cudaFree(h->d_sig_scratch);
     free(h->sig_job);
     if (h->d_lk_pts) cudaFree(h->d_lk_pts);
+    if (h->d_lk_idx) cudaFree(h->d_lk_idx);
     if (h->d_lk_n) cudaFree(h->d_lk_n);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->tail_stream) cudaStreamDestroy(h->tail_stream);
+    if (h->ev_packed) cudaEventDestroy(h->ev_packed);
+    if (h->ev_tail_fork) cudaEventDestroy(h->ev_tail_fork);
     for (int i = 0; i < RM_MAX_CHUNKS; ++i) {
       if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
       if (h->ev_filt[i]) cudaEventDestroy(h->ev_filt[i]);
@@ -171,12 +178,26 @@ extern "C" int32_t rm_set_option(rm_handle* h, const char* name, int64_t value) 
   if (!h || !name) return RM_ERR_INVALID;
   if (strcmp(name, "force_global_lk") == 0) { h->force_global_lk = value != 0; return RM_OK; }
   if (strcmp(name, "force_generic_front") == 0) { h->force_generic_front = value != 0; return RM_OK; }
+  if (strcmp(name, "defer_join") == 0) { h->defer_join = value != 0; return RM_OK; }
   if (strcmp(name, "measure_chunks") == 0) {
     if (value < 1 || value > RM_MAX_CHUNKS) return rm_fail(h, RM_ERR_INVALID, "%s: measure_chunks must be 1..16", __func__);
     h->measure_chunks = (int)value;
     return RM_OK;
   }
   return rm_fail(h, RM_ERR_INVALID, "%s: unknown option", __func__);
+}
+
+int32_t rmi_join(rm_handle* h, cudaStream_t st) {
+  if (h->pending_pack) RM_CUDA(h, cudaStreamWaitEvent(st, h->ev_packed, 0));
+  for (int c = 0; c < h->pending_chunks; ++c) RM_CUDA(h, cudaStreamWaitEvent(st, h->ev_done[c], 0));
+  h->pending_pack = 0;
+  h->pending_chunks = 0;
+  return RM_OK;
+}
+extern "C" int32_t rm_join(rm_handle* h, void* stream) {
+  if (!h) return RM_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  return rmi_join(h, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------- profiling

@@ -30,9 +30,19 @@ struct rm_handle {
   cudaStream_t aux_stream;                   // PCA + filtfilt/peaks of the chunks, in frame order
   cudaStream_t fit_stream[RM_MAX_CHUNKS];    // one per chunk: the Gaussian-fit gates of different chunks overlap
   cudaEvent_t ev_fork, ev_join, ev_chunk[RM_MAX_CHUNKS], ev_filt[RM_MAX_CHUNKS], ev_done[RM_MAX_CHUNKS];
-  int measure_chunks;       // option "measure_chunks" (default 4)
+  int measure_chunks;       // option "measure_chunks"
+  // Deferred join (option "defer_join"): rm_measure_signal returns without making the caller's stream wait for the
+  // signal stage; rm_pack_results then runs on tail_stream behind it, and the caller's stream catches up in rm_join or
+  // at the next call that reuses the handle's scratch.  Lets the next batch's calibration run under this batch's
+  // longest Gaussian fits.
+  int defer_join;
+  int pending_chunks;       // > 0: ev_done[0..pending_chunks) of the last rm_measure_signal have not been waited for
+  int pending_pack;         // 1: ev_packed (tail_stream) has not been waited for
+  cudaStream_t tail_stream;
+  cudaEvent_t ev_packed, ev_tail_fork;
   float* d_lk_pts;          // (cap_clips, 128, 2) points carried from one LK chunk to the next
-  int* d_lk_n;              // (cap_clips)
+  int* d_lk_idx;            // (cap_clips, 128) original corner index of every carried point
+  int* d_lk_n;              // (cap_clips, 16) points each block of a clip still tracks
   int lk_state_cap;
   void* sig_job;            // host-side SignalJob of the measure pipeline (signal.cu)
   int force_global_lk;
@@ -180,5 +190,6 @@ static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / 
 int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps, double* bpm_out,
                          double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, const int32_t* status,
                          int n_chunks, cudaStream_t st);
+int32_t rmi_join(rm_handle* h, cudaStream_t st);   // make st wait for whatever a deferred rm_measure_signal left running
 int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t st, cudaStream_t st_fit,
                          cudaEvent_t ev_filtered);

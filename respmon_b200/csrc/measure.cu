@@ -63,10 +63,24 @@ struct MeasureParams {
   float* pts_dbg;          // (n_clips, n_frames, LK_MAX_PTS, 2) or null: per-frame tracked points (tests)
   // frame chunk [f0, f1) of this launch and the tracker state carried between chunks (shared-memory tracker only)
   int f0, f1;
-  float* st_pts;           // (n_clips, LK_MAX_PTS, 2)
-  int32_t* st_n;           // (n_clips)
+  float* st_pts;           // (n_clips, LK_MAX_PTS, 2)   points of block b start at slot b * ppb
+  int32_t* st_idx;         // (n_clips, LK_MAX_PTS)      their indices in the first frame's corner list
+  int32_t* st_n;           // (n_clips, LK_MAX_BLOCKS)   points block b still tracks
+  // shared-memory tracker: the corners of a clip are split over `bpc` blocks of at most `ppb` points each (one warp per
+  // point, so a clip with many corners is not the batch's critical path); every block writes old-new of its surviving
+  // points per frame, indexed by the point's original index, and motion_reduce_kernel folds them in that order
+  int bpc, ppb;
+  float2* delta;           // (n_clips, n_frames, LK_MAX_PTS), NaN = the point is gone
 };
+#define LK_MAX_BLOCKS 16
+#ifndef LK_PPB
+#define LK_PPB 16
+#endif
 
+__device__ __forceinline__ bool roi_ok_geom(const MeasureParams& p, int clip, int& x, int& y, int& w, int& h) {
+  x = p.roi[clip * 4 + 0]; y = p.roi[clip * 4 + 1]; w = p.roi[clip * 4 + 2]; h = p.roi[clip * 4 + 3];
+  return w >= 1 && h >= 1 && x >= 0 && y >= 0 && x + w <= p.W && y + h <= p.H && w <= p.maxw && h <= p.maxh;
+}
 __device__ __forceinline__ bool roi_ok(const MeasureParams& p, int clip, int& x, int& y, int& w, int& h) {
   x = p.roi[clip * 4 + 0]; y = p.roi[clip * 4 + 1]; w = p.roi[clip * 4 + 2]; h = p.roi[clip * 4 + 3];
   return p.status[clip] == RM_CLIP_OK && w >= 1 && h >= 1 && x >= 0 && y >= 0 && x + w <= p.W && y + h <= p.H &&
@@ -593,56 +607,49 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
     int iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
     int iw10 = __float2int_rn((1.f - a) * b * 16384.f);
     int iw11 = 16384 - iw00 - iw01 - iw10;
-    // stage the (win+3)^2 neighbourhood of the previous image (the border is already in the padded image)
-    __syncwarp();
-    {
-      const unsigned char* src = lks_smem + I.org + (iy - 1) * I.pitch + (ix - 1);
-      int r = 0, c = lane;
-      while (c >= pw) { c -= pw; ++r; }
-      for (int i = lane; i < pw * pw; i += 32) {
-        patch[i] = (short)src[r * I.pitch + c];
-        c += 32;
-        while (c >= pw) { c -= pw; ++r; }
-      }
-    }
-    __syncwarp();
-    // Scharr derivatives (calcScharrDeriv) on the (win+1)^2 positions the window touches; zero outside the image
-    {
-      int y = 0, x = lane;
-      while (x >= dwid) { x -= dwid; ++y; }
-      for (int i = lane; i < dwid * dwid; i += 32) {
-        short2 d = make_short2(0, 0);
-        if (iy + y >= 0 && iy + y < I.h && ix + x >= 0 && ix + x < I.w) {
-          const short* r0 = patch + y * pw + x;          // rows y-1, y, y+1 of the window position -> patch rows y..y+2
-          const short* r1 = r0 + pw;
-          const short* r2 = r1 + pw;
-          const int t0l = (r0[0] + r2[0]) * 3 + r1[0] * 10, t0r = (r0[2] + r2[2]) * 3 + r1[2] * 10;
-          const int t1l = r2[0] - r0[0], t1c = r2[1] - r0[1], t1r = r2[2] - r0[2];
-          d.x = (short)(t0r - t0l);
-          d.y = (short)((t1r + t1l) * 3 + t1c * 10);
-        }
-        deriv[i] = d;
-        x += 32;
-        while (x >= dwid) { x -= dwid; ++y; }
-      }
-    }
-    __syncwarp();
+    // The lane's 8 window pixels sit side by side in window row wy: everything they need of the previous image -- the
+    // intensities for the bilinear sample and the 3x3 neighbourhoods of the Scharr derivatives (calcScharrDeriv) at
+    // rows wy, wy+1 and columns wx0..wx0+8 -- is a 4 x 11 byte block, walked column by column in registers.  The
+    // derivative image is zero outside the image (cv::copyMakeBorder CONSTANT), the intensity image is reflect-padded.
     int Iw[8], Ixv[8], Iyv[8];
     int sA11 = 0, sA12 = 0, sA22 = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      Iw[k] = 0; Ixv[k] = 0; Iyv[k] = 0;
-      if (wq[k] >= 0) {
-        const int wy = wq[k] >> 8, wx = wq[k] & 255;
-        const short* pr = patch + (wy + 1) * pw + wx + 1;
-        Iw[k] = descale(pr[0] * iw00 + pr[1] * iw01 + pr[pw] * iw10 + pr[pw + 1] * iw11, 9);
-        const short2 d00 = deriv[wy * dwid + wx], d01 = deriv[wy * dwid + wx + 1];
-        const short2 d10 = deriv[(wy + 1) * dwid + wx], d11 = deriv[(wy + 1) * dwid + wx + 1];
-        Ixv[k] = descale(d00.x * iw00 + d01.x * iw01 + d10.x * iw10 + d11.x * iw11, 14);
-        Iyv[k] = descale(d00.y * iw00 + d01.y * iw01 + d10.y * iw10 + d11.y * iw11, 14);
-        sA11 += Ixv[k] * Ixv[k];      // |Ix| <= 4080: eight products stay far below 2^30
-        sA12 += Ixv[k] * Iyv[k];
-        sA22 += Iyv[k] * Iyv[k];
+    for (int k = 0; k < 8; ++k) { Iw[k] = 0; Ixv[k] = 0; Iyv[k] = 0; }
+    if (wq[0] >= 0) {
+      const int wy = wq[0] >> 8, wx0 = wq[0] & 255;
+      const unsigned char* src = lks_smem + I.org + (iy + wy - 1) * I.pitch + (ix + wx0 - 1);
+      const bool row_ok0 = iy + wy >= 0 && iy + wy < I.h, row_ok1 = iy + wy + 1 >= 0 && iy + wy + 1 < I.h;
+      int c0[4], c1[4], c2[4];   // three neighbouring columns of the block, rows wy-1 .. wy+2
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { c0[r] = src[r * I.pitch]; c1[r] = src[r * I.pitch + 1]; }
+      int pdx0 = 0, pdy0 = 0, pdx1 = 0, pdy1 = 0;   // derivatives of the previous column at rows wy, wy+1
+#pragma unroll
+      for (int cc = 0; cc <= 8; ++cc) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) c2[r] = src[r * I.pitch + cc + 2];
+        const bool col_ok = ix + wx0 + cc >= 0 && ix + wx0 + cc < I.w;
+        // Scharr at (wy, wx0+cc) from rows 0..2 and at (wy+1, wx0+cc) from rows 1..3
+        int dx0 = (short)(((c2[0] + c2[2]) * 3 + c2[1] * 10) - ((c0[0] + c0[2]) * 3 + c0[1] * 10));
+        int dy0 = (short)(((c2[2] - c2[0]) + (c0[2] - c0[0])) * 3 + (c1[2] - c1[0]) * 10);
+        int dx1 = (short)(((c2[1] + c2[3]) * 3 + c2[2] * 10) - ((c0[1] + c0[3]) * 3 + c0[2] * 10));
+        int dy1 = (short)(((c2[3] - c2[1]) + (c0[3] - c0[1])) * 3 + (c1[3] - c1[1]) * 10);
+        if (!(col_ok && row_ok0)) { dx0 = 0; dy0 = 0; }
+        if (!(col_ok && row_ok1)) { dx1 = 0; dy1 = 0; }
+        if (cc >= 1) {
+          const int k = cc - 1;            // pixel k: columns k (previous) and k+1 (this one)
+          if (wx0 + k < win) {
+            // at this point c0 = column k, c1 = column k+1 of the intensities (block columns k+1, k+2 before the shift)
+            Iw[k] = descale(c0[1] * iw00 + c1[1] * iw01 + c0[2] * iw10 + c1[2] * iw11, 9);
+            Ixv[k] = descale(pdx0 * iw00 + dx0 * iw01 + pdx1 * iw10 + dx1 * iw11, 14);
+            Iyv[k] = descale(pdy0 * iw00 + dy0 * iw01 + pdy1 * iw10 + dy1 * iw11, 14);
+            sA11 += Ixv[k] * Ixv[k];      // |Ix| <= 4080: eight products stay far below 2^30
+            sA12 += Ixv[k] * Iyv[k];
+            sA22 += Iyv[k] * Iyv[k];
+          }
+        }
+        pdx0 = dx0; pdy0 = dy0; pdx1 = dx1; pdy1 = dy1;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
       }
     }
     const float A11 = (float)warp_sum_split(sA11) * FLT_SCALE, A12 = (float)warp_sum_split(sA12) * FLT_SCALE,
@@ -656,9 +663,8 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
     D = 1.f / D;
     float qx = nx - half, qy = ny - half;
     float pdx = 0.f, pdy = 0.f;
-    int joff[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) joff[k] = wq[k] >= 0 ? (wq[k] >> 8) * J.pitch + (wq[k] & 255) : 0;
+    // the lane's window pixels are 8 consecutive columns of one row (wq[0] is the first): 2 x 9 bytes of J per iteration
+    const int jrow = (wq[0] >= 0 ? (wq[0] >> 8) : 0) * J.pitch + (wq[0] >= 0 ? (wq[0] & 255) : 0);
     for (int j = 0; j < p.max_iter; ++j) {
       const int jx = (int)floorf(qx), jy = (int)floorf(qy);
       if (jx < -win || jx >= J.w || jy < -win || jy >= J.h) {
@@ -670,16 +676,18 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
       iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
       iw10 = __float2int_rn((1.f - a) * b * 16384.f);
       iw11 = 16384 - iw00 - iw01 - iw10;
-      const unsigned char* jp = lks_smem + J.org + jy * J.pitch + jx;
+      const unsigned char* r0 = lks_smem + J.org + jy * J.pitch + jx + jrow;
+      const unsigned char* r1 = r0 + J.pitch;
       int sb1 = 0, sb2 = 0;
+      int t0 = r0[0], t1 = r1[0];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if (wq[k] >= 0) {
-          const unsigned char* q = jp + joff[k];
-          const int diff = descale(q[0] * iw00 + q[1] * iw01 + q[J.pitch] * iw10 + q[J.pitch + 1] * iw11, 9) - Iw[k];
-          sb1 += diff * Ixv[k];       // |diff| <= 8160, |Ix| <= 4080: eight products stay below 2^30
-          sb2 += diff * Iyv[k];
-        }
+        const int u0 = r0[k + 1], u1 = r1[k + 1];
+        // pixels past the end of the window carry Ix = Iy = 0: whatever they read contributes nothing
+        const int diff = descale(t0 * iw00 + u0 * iw01 + t1 * iw10 + u1 * iw11, 9) - Iw[k];
+        sb1 += diff * Ixv[k];       // |diff| <= 8160, |Ix| <= 4080: eight products stay below 2^30
+        sb2 += diff * Iyv[k];
+        t0 = u0; t1 = u1;
       }
       const float b1 = (float)warp_sum_split(sb1) * FLT_SCALE, b2 = (float)warp_sum_split(sb2) * FLT_SCALE;
       const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
@@ -697,20 +705,32 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
   return status;
 }
 
+#ifdef LK_TIMING
+__device__ long long lk_timing[64 * 8 * 8];
+extern "C" int32_t rm_debug_lk_timing(long long* host_out, int32_t reset) {
+  if (host_out) cudaMemcpyFromSymbol(host_out, lk_timing, sizeof(long long) * 64 * 8 * 8);
+  if (reset) { static long long z[64 * 8 * 8]; cudaMemcpyToSymbol(lk_timing, z, sizeof(z)); }
+  return 0;
+}
+#endif
 __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const MeasureParams p, const float* pts0,
                                                                        int max_total) {
   const int clip = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int blk = blockIdx.y;                  // which slice of the clip's corners this block tracks
   __shared__ float s_pts[LK_MAX_PTS][2], s_new[LK_MAX_PTS][2];
-  __shared__ int s_st[LK_MAX_PTS];
-  __shared__ int s_n, s_lost;
+  __shared__ int s_st[LK_MAX_PTS], s_idx[LK_MAX_PTS];
+  __shared__ int s_n;
   __shared__ uint8_t s_lut[256];
   int rx, ry, rw, rh;
   const bool ok = roi_ok(p, clip, rx, ry, rw, rh);
-  float* motion = p.motion + (long long)clip * p.n_frames * 2;
-  if (!ok || p.npts[clip] <= 0) {
-    if (p.f0 == 0)   // later chunks: the first one already did this (and a clip lost on the way keeps its history)
-      for (int f = tid; f < p.n_frames; f += blockDim.x) { motion[2 * f] = NAN; motion[2 * f + 1] = NAN; }
+  const bool resume = p.f0 > 0;               // a later chunk: points and count come from the previous launch
+  int n_start = 0;
+  if (resume) n_start = p.st_n[clip * LK_MAX_BLOCKS + blk];
+  else if (ok && p.npts[clip] > 0) { n_start = p.npts[clip] - blk * p.ppb; if (n_start > p.ppb) n_start = p.ppb; }
+  if (n_start <= 0) {   // no corners in this slice, a clip without ROI / corners (motion_reduce_kernel writes its NaNs),
+                        // or every point of the slice lost in an earlier chunk
+    if (!resume && p.st_n && tid == 0) p.st_n[clip * LK_MAX_BLOCKS + blk] = 0;
     return;
   }
   const LkSmemLayout L = lk_smem_layout(rw, rh, p.win, p.max_level, LKS_WARPS);
@@ -721,25 +741,21 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
   const int deriv_off = patch_off + 2 * ((pw * pw + 1) & ~1);
 
   for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
-  const bool resume = p.f0 > 0;               // a later chunk: points and count come from the previous launch
-  const int n_start = resume ? p.st_n[clip] : p.npts[clip];
-  if (resume && n_start <= 0) return;          // tracking was lost in an earlier chunk (its NaN fill is already done)
-  if (tid == 0) { s_n = n_start; s_lost = 0; if (!resume) { motion[0] = 0.f; motion[1] = 0.f; } }
+  if (tid == 0) s_n = n_start;
   {
     const float* src = resume ? p.st_pts : pts0;
     for (int i = tid; i < n_start; i += blockDim.x) {
-      s_pts[i][0] = src[((long long)clip * LK_MAX_PTS + i) * 2];
-      s_pts[i][1] = src[((long long)clip * LK_MAX_PTS + i) * 2 + 1];
+      const long long slot = (long long)clip * LK_MAX_PTS + blk * p.ppb + i;
+      s_pts[i][0] = src[slot * 2];
+      s_pts[i][1] = src[slot * 2 + 1];
+      s_idx[i] = resume ? p.st_idx[slot] : blk * p.ppb + i;
     }
   }
-  int wq[8];   // the lane's window pixels (wy << 8 | wx), -1 past the end of the window
+  int wq[8];   // the lane's window pixels (wy << 8 | wx), -1 past the end of the window: row lane/2, columns 8*(lane&1)..+7
   {
-    const int npx = p.win * p.win;
+    const int wy = lane >> 1, wx0 = (lane & 1) * 8;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int q = lane + 32 * k;
-      wq[k] = q < npx ? ((q / p.win) << 8) | (q % p.win) : -1;
-    }
+    for (int k = 0; k < 8; ++k) wq[k] = (wy < p.win && wx0 + k < p.win) ? (wy << 8) | (wx0 + k) : -1;
   }
 
   const long long frame_elems = (long long)p.W * p.H;
@@ -780,18 +796,33 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
     cp_async_commit();
   };
   // raw crop -> padded uint8 pyramid (LUT, reflect-101 border; pyrDown levels with their own borders)
+  // Linear block-strided loops (index -> row/column by one multiply-high: exact for n * d < 2^32) that the compiler can
+  // unroll, so several independent load -> LUT -> store chains are in flight per thread; the stage is latency bound.
+  auto magic_of = [](int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1u) / (unsigned)d); };
+  auto refl1 = [](int v, int n) { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); };   // one reflection (n > |overhang|)
+  const int nthr = LKS_WARPS * 32;
   auto build = [&](int raw_slot, int pyr_slot) {
     const int src = raw_base + raw_slot * L.raw_bytes + xoff;
     const int base = pyr_slot * L.pyr_bytes;
     {
       const int pitch = L.pitch[0], ph = rh + 2 * L.pad, pwid = rw + 2 * L.pad;
-      int py, pxx, dr, dc;
-      stride2d(pwid, py, pxx, dr, dc);
-      for (; py < ph; py += dr) {
-        const int y = reflect101_multi(py - L.pad, rh), x = reflect101_multi(pxx - L.pad, rw);
-        lks_smem[base + L.off[0] + py * pitch + pxx] = s_lut[lks_smem[src + y * L.raw_pitch + x]];
-        pxx += dc;
-        if (pxx >= pwid) { pxx -= pwid; ++py; }
+      const unsigned mg = magic_of(pwid);
+      const int total = ph * pwid;
+      unsigned char* dst = lks_smem + base + L.off[0];
+      const unsigned char* raw = lks_smem + src;
+      if (rw > L.pad && rh > L.pad) {
+#pragma unroll 4
+        for (int i = tid; i < total; i += nthr) {
+          const int py = (int)__umulhi((unsigned)i, mg), pxx = i - py * pwid;
+          const int y = refl1(py - L.pad, rh), x = refl1(pxx - L.pad, rw);
+          dst[py * pitch + pxx] = s_lut[raw[y * L.raw_pitch + x]];
+        }
+      } else {
+        for (int i = tid; i < total; i += nthr) {
+          const int py = (int)__umulhi((unsigned)i, mg), pxx = i - py * pwid;
+          const int y = reflect101_multi(py - L.pad, rh), x = reflect101_multi(pxx - L.pad, rw);
+          dst[py * pitch + pxx] = s_lut[raw[y * L.raw_pitch + x]];
+        }
       }
     }
     __syncthreads();
@@ -801,9 +832,11 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
       const int d0 = base + L.off[l] + L.pad * dpitch + L.pad;
       const int dw = L.lw[l], dh = L.lh[l];
       {
-        int y, x, dr, dc;
-        stride2d(dw, y, x, dr, dc);
-        for (; y < dh; y += dr) {
+        const unsigned mg = magic_of(dw);
+        const int total = dw * dh;
+#pragma unroll 2
+        for (int i = tid; i < total; i += nthr) {
+          const int y = (int)__umulhi((unsigned)i, mg), x = i - y * dw;
           const unsigned char* c = lks_smem + s0 + (2 * y - 2) * spitch + 2 * x - 2;
           int r[5];
 #pragma unroll
@@ -812,21 +845,30 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
             r[k] = row[0] + row[4] + 4 * (row[1] + row[3]) + 6 * row[2];
           }
           lks_smem[d0 + y * dpitch + x] = (unsigned char)((r[0] + r[4] + 4 * (r[1] + r[3]) + 6 * r[2] + 128) >> 8);
-          x += dc;
-          if (x >= dw) { x -= dw; ++y; }
         }
       }
       __syncthreads();
       {
-        const int ph = dh + 2 * L.pad, pwid = dw + 2 * L.pad;
-        int py, pxx, dr, dc;
-        stride2d(pwid, py, pxx, dr, dc);
-        for (; py < ph; py += dr) {
-          const int yy = py - L.pad, xx = pxx - L.pad;
-          if (!(yy >= 0 && yy < dh && xx >= 0 && xx < dw))
-            lks_smem[d0 + yy * dpitch + xx] = lks_smem[d0 + reflect101_multi(yy, dh) * dpitch + reflect101_multi(xx, dw)];
-          pxx += dc;
-          if (pxx >= pwid) { pxx -= pwid; ++py; }
+        // border pixels only: `pad` full rows above and below, 2 * pad columns beside every image row
+        const int pad = L.pad, pwid = dw + 2 * pad;
+        const int n_tb = 2 * pad * pwid, total = n_tb + dh * 2 * pad;
+        const unsigned mg = magic_of(pwid), mg2 = magic_of(2 * pad);
+        const bool simple = dw > pad && dh > pad;
+#pragma unroll 2
+        for (int i = tid; i < total; i += nthr) {
+          int yy, xx;
+          if (i < n_tb) {
+            const int r = (int)__umulhi((unsigned)i, mg);
+            xx = i - r * pwid - pad;
+            yy = r < pad ? r - pad : dh + (r - pad);
+          } else {
+            const int j = i - n_tb, r = (int)__umulhi((unsigned)j, mg2), k = j - r * 2 * pad;
+            yy = r;
+            xx = k < pad ? k - pad : dw + (k - pad);
+          }
+          const int sy = simple ? refl1(yy, dh) : reflect101_multi(yy, dh);
+          const int sx = simple ? refl1(xx, dw) : reflect101_multi(xx, dw);
+          lks_smem[d0 + yy * dpitch + xx] = lks_smem[d0 + sy * dpitch + sx];
         }
       }
       __syncthreads();
@@ -841,16 +883,26 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
 
   // the frame before the chunk is the tracker's "previous image": frame 0 for the first chunk
   const int f_first = resume ? p.f0 : 1;
+#ifdef LK_TIMING
+  long long tk0 = 0, acc_wait = 0, acc_build = 0, acc_track = 0, acc_book = 0;
+#define LKT(acc) do { if (tid == 0) { long long n_ = clock64(); acc += n_ - tk0; tk0 = n_; } } while (0)
+  if (tid == 0) tk0 = clock64();
+#else
+#define LKT(acc) do { } while (0)
+#endif
   stage_raw(f_first - 1, (f_first - 1) & 1);
   cp_async_wait<0>();
   __syncthreads();
   build((f_first - 1) & 1, (f_first - 1) & 1);
   if (f_first < p.f1) stage_raw(f_first, f_first & 1);
+  LKT(acc_book);
   for (int f = f_first; f < p.f1; ++f) {
     cp_async_wait<0>();
     __syncthreads();
+    LKT(acc_wait);
     build(f & 1, f & 1);
     if (f + 1 < p.f1) stage_raw(f + 1, (f + 1) & 1);   // lands while this frame is tracked
+    LKT(acc_build);
     LkSLevel prev[LK_MAX_LEVELS], next[LK_MAX_LEVELS];
     levels((f - 1) & 1, prev);
     levels(f & 1, next);
@@ -862,49 +914,87 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
       if (lane == 0) { s_new[i][0] = ox; s_new[i][1] = oy; s_st[i] = st; }
     }
     __syncthreads();
+    LKT(acc_track);
     if (tid == 0) {
-      // good_new = p1[st == 1], good_old = pts[st == 1]; mean(good_old - good_new, axis=0) in float32 (base.py:377-389)
+      // good_new = p1[st == 1], good_old = pts[st == 1] (base.py:377-382): survivors keep their relative order; their
+      // old - new goes out under the point's original index for the ordered float32 mean (base.py:388)
+      float2* out = p.delta + ((long long)clip * p.n_frames + f) * LK_MAX_PTS;
       int m = 0;
-      float sx = 0.f, sy = 0.f;
       for (int i = 0; i < n; ++i) {
         if (s_st[i]) {
-          sx += s_pts[i][0] - s_new[i][0];
-          sy += s_pts[i][1] - s_new[i][1];
+          out[s_idx[i]] = make_float2(s_pts[i][0] - s_new[i][0], s_pts[i][1] - s_new[i][1]);
           s_pts[m][0] = s_new[i][0];
           s_pts[m][1] = s_new[i][1];
+          s_idx[m] = s_idx[i];
           ++m;
         }
       }
       s_n = m;
-      if (m == 0) {
-        s_lost = 1;
-      } else {
-        motion[2 * f] = sx / (float)m;
-        motion[2 * f + 1] = sy / (float)m;
-      }
     }
     __syncthreads();
-    if (p.pts_dbg) {
+    LKT(acc_book);
+    if (p.pts_dbg) {   // single-block mode only (bpc == 1): the compacted list is the reference's motion_key_points
       float* dbg = p.pts_dbg + ((long long)clip * p.n_frames + f) * LK_MAX_PTS * 2;
       for (int i = tid; i < LK_MAX_PTS; i += blockDim.x) {
         dbg[2 * i] = i < s_n ? s_pts[i][0] : NAN;
         dbg[2 * i + 1] = i < s_n ? s_pts[i][1] : NAN;
       }
     }
-    if (s_lost) {   // tracking lost: extract_motion returns nan from here on (base.py:385-386)
-      for (int g = f + tid; g < p.n_frames; g += blockDim.x) { motion[2 * g] = NAN; motion[2 * g + 1] = NAN; }
-      if (tid == 0) { p.status[clip] = RM_CLIP_TRACK_LOST; if (p.st_n) p.st_n[clip] = 0; }
+    if (s_n == 0) {    // every corner of this slice is gone; nothing left to track here
+      if (tid == 0 && p.st_n) p.st_n[clip * LK_MAX_BLOCKS + blk] = 0;
       cp_async_wait<0>();
       return;
     }
   }
   __syncthreads();
+#ifdef LK_TIMING
+  LKT(acc_book);
+  if (tid == 0) {
+    long long* row = lk_timing + (clip * 8 + (blk & 7)) * 8;
+    row[0] += acc_wait; row[1] += acc_build; row[2] += acc_track; row[3] += acc_book;
+    row[4] += p.f1 - f_first; row[5] = s_n; row[6] = rw; row[7] = rh;
+  }
+#endif
   if (p.st_n) {   // hand the tracker state to the next chunk
     for (int i = tid; i < s_n; i += blockDim.x) {
-      p.st_pts[((long long)clip * LK_MAX_PTS + i) * 2] = s_pts[i][0];
-      p.st_pts[((long long)clip * LK_MAX_PTS + i) * 2 + 1] = s_pts[i][1];
+      const long long slot = (long long)clip * LK_MAX_PTS + blk * p.ppb + i;
+      p.st_pts[slot * 2] = s_pts[i][0];
+      p.st_pts[slot * 2 + 1] = s_pts[i][1];
+      p.st_idx[slot] = s_idx[i];
     }
-    if (tid == 0) p.st_n[clip] = s_n;
+    if (tid == 0) p.st_n[clip * LK_MAX_BLOCKS + blk] = s_n;
+  }
+}
+
+// mean(good_old - good_new, axis=0) (base.py:388) for frames [f0, f1): float32, the surviving points in their original
+// order (numpy reduces axis 0 of an (N,2) array row by row).  A frame without survivors is where extract_motion starts
+// returning nan (base.py:385-386): the clip is marked TRACK_LOST; points never come back, so later frames are NaN too.
+__global__ void motion_reduce_kernel(const MeasureParams p) {
+  const int clip = blockIdx.y;
+  int rx, ry, rw, rh;
+  const int st = p.status[clip];
+  const bool bad = st == RM_CLIP_NO_ROI || st == RM_CLIP_NO_CORNERS || p.npts[clip] <= 0 ||
+                   !(roi_ok_geom(p, clip, rx, ry, rw, rh));
+  float* motion = p.motion + (long long)clip * p.n_frames * 2;
+  const int n0 = p.npts[clip];
+  for (int f = p.f0 + blockIdx.x * blockDim.x + threadIdx.x; f < p.f1; f += gridDim.x * blockDim.x) {
+    float mx = NAN, my = NAN;
+    if (!bad) {
+      if (f == 0) { mx = 0.f; my = 0.f; }
+      else {
+        const float2* d = p.delta + ((long long)clip * p.n_frames + f) * LK_MAX_PTS;
+        int m = 0;
+        float sx = 0.f, sy = 0.f;
+        for (int i = 0; i < n0; ++i) {
+          const float2 v = d[i];
+          if (v.x == v.x) { sx += v.x; sy += v.y; ++m; }
+        }
+        if (m > 0) { mx = sx / (float)m; my = sy / (float)m; }
+        else p.status[clip] = RM_CLIP_TRACK_LOST;
+      }
+    }
+    motion[2 * f] = mx;
+    motion[2 * f + 1] = my;
   }
 }
 
@@ -948,7 +1038,7 @@ __global__ void measure_average_kernel(const uint8_t* __restrict__ frames, const
 
 // ------------------------------------------------------------------------------------------------ host side
 struct MeasureLayout {
-  size_t cov, eig, eigmax, cand, pts0, pyr[LK_MAX_LEVELS], total;
+  size_t cov, eig, eigmax, cand, pts0, delta, pyr[LK_MAX_LEVELS], total;
   long long lvl_elems[LK_MAX_LEVELS];
 };
 static MeasureLayout measure_layout(const rm_handle* h, int maxw, int maxh, int n_clips, int n_frames) {
@@ -966,6 +1056,7 @@ static MeasureLayout measure_layout(const rm_handle* h, int maxw, int maxh, int 
   L.eigmax = take((size_t)n_clips * 4);
   L.cand = take((size_t)n_clips * plane * 8);
   L.pts0 = take((size_t)n_clips * LK_MAX_PTS * 2 * 4);
+  L.delta = take((size_t)n_clips * n_frames * LK_MAX_PTS * sizeof(float2));
   int w = maxw, hh = maxh;
   for (int l = 1; l < LK_MAX_LEVELS && l <= h->p.lk_max_level; ++l) {
     w = (w + 1) / 2; hh = (hh + 1) / 2;
@@ -1032,6 +1123,13 @@ static int32_t measure_setup(rm_handle* h, const uint8_t* frames, int32_t n_clip
   }
   p.motion = motion_out; p.data = data_out; p.npts = npts_out; p.status = status_io; p.pts_dbg = pts_dbg;
   p.f0 = 0; p.f1 = n_frames;
+  p.delta = reinterpret_cast<float2*>(ws + L.delta);
+  if (pts_dbg) { p.bpc = 1; p.ppb = LK_MAX_PTS; }          // the diagnostic dump wants one compacted list per clip
+  else {
+    p.ppb = LK_PPB;                                        // at most one corner per warp, half of the warps per block
+    p.bpc = (h->p.max_corners + p.ppb - 1) / p.ppb;
+    if (p.bpc > LK_MAX_BLOCKS) { p.bpc = LK_MAX_BLOCKS; p.ppb = (h->p.max_corners + p.bpc - 1) / p.bpc; }
+  }
   job->L = L;
   job->SL = lk_smem_layout(max_roi_w, max_roi_h, p.win, p.max_level, LKS_WARPS);
   job->smem_path = job->SL.total + 4096 <= h->smem_optin && !h->force_global_lk;
@@ -1063,11 +1161,13 @@ static int32_t measure_lk(rm_handle* h, MeasureJob* job, int f0, int f1, bool ca
   p.f0 = f0; p.f1 = f1;
   if (job->smem_path) {
     p.st_pts = carry_state ? h->d_lk_pts : nullptr;
+    p.st_idx = carry_state ? h->d_lk_idx : nullptr;
     p.st_n = carry_state ? h->d_lk_n : nullptr;
+    if (f0 == 0) RM_CUDA(h, cudaMemsetAsync(p.delta, 0xFF, (size_t)p.n_clips * p.n_frames * LK_MAX_PTS * sizeof(float2), st));
     // production path: crops and their pyramids live in shared memory
     RM_CUDA(h, cudaFuncSetAttribute(lk_track_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, job->SL.total));
     RM_PROF(h, st, "lk_track_smem_kernel");
-    lk_track_smem_kernel<<<p.n_clips, LKS_WARPS * 32, job->SL.total, st>>>(p, job->pts0, job->SL.total);
+    lk_track_smem_kernel<<<dim3(p.n_clips, p.bpc), LKS_WARPS * 32, job->SL.total, st>>>(p, job->pts0, job->SL.total);
     RM_LAUNCH_CHECK(h);
   } else {
     if (f0 != 0) return RM_OK;          // done by the first call
@@ -1091,6 +1191,12 @@ static int32_t measure_lk(rm_handle* h, MeasureJob* job, int f0, int f1, bool ca
 static int32_t measure_pca(rm_handle* h, MeasureJob* job, int f0, int f1, cudaStream_t st) {
   MeasureParams p = job->p;
   p.f0 = f0; p.f1 = f1;
+  if (job->smem_path) {   // the blocks of a clip left per-point displacements: fold them into motion[f0..f1)
+    dim3 g0(div_up(f1 - f0, 64), p.n_clips);
+    RM_PROF(h, st, "motion_reduce_kernel");
+    motion_reduce_kernel<<<g0, 64, 0, st>>>(p);
+    RM_LAUNCH_CHECK(h);
+  }
   dim3 g3(div_up(f1 - f0, 128), p.n_clips);
   RM_PROF(h, st, "motion_pca_kernel");
   motion_pca_kernel<<<g3, 128, 0, st>>>(p);
@@ -1109,6 +1215,7 @@ static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_
   if (rc != RM_OK || n_clips == 0) return rc;
   DeviceGuard dg(h->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = rmi_join(h, st)) != RM_OK) return rc;
   if ((rc = measure_gftt(h, &job, st)) != RM_OK) return rc;
   if ((rc = measure_lk(h, &job, 0, n_frames, false, st)) != RM_OK) return rc;
   return measure_pca(h, &job, 0, n_frames, st);
@@ -1133,15 +1240,18 @@ extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_
   if (rc != RM_OK || n_clips == 0) return rc;
   DeviceGuard dg(h->device);
   cudaStream_t sa = (cudaStream_t)stream, sb = h->aux_stream;
+  if ((rc = rmi_join(h, sa)) != RM_OK) return rc;   // a deferred predecessor still owns the scratch and the events
   int n_chunks = job.smem_path ? h->measure_chunks : 1;
   if (n_chunks > n_frames) n_chunks = n_frames;
   if (n_chunks > RM_MAX_CHUNKS) n_chunks = RM_MAX_CHUNKS;
   if (h->lk_state_cap < n_clips) {
     if (h->d_lk_pts) cudaFree(h->d_lk_pts);
+    if (h->d_lk_idx) cudaFree(h->d_lk_idx);
     if (h->d_lk_n) cudaFree(h->d_lk_n);
-    h->d_lk_pts = nullptr; h->d_lk_n = nullptr; h->lk_state_cap = 0;
+    h->d_lk_pts = nullptr; h->d_lk_idx = nullptr; h->d_lk_n = nullptr; h->lk_state_cap = 0;
     RM_CUDA(h, cudaMalloc((void**)&h->d_lk_pts, (size_t)n_clips * LK_MAX_PTS * 2 * sizeof(float)));
-    RM_CUDA(h, cudaMalloc((void**)&h->d_lk_n, (size_t)n_clips * sizeof(int)));
+    RM_CUDA(h, cudaMalloc((void**)&h->d_lk_idx, (size_t)n_clips * LK_MAX_PTS * sizeof(int)));
+    RM_CUDA(h, cudaMalloc((void**)&h->d_lk_n, (size_t)n_clips * LK_MAX_BLOCKS * sizeof(int)));
     h->lk_state_cap = n_clips;
   }
   // everything that allocates happens before the first launch
@@ -1160,7 +1270,8 @@ extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_
     if ((rc = rmi_signal_range(h, f0, f1, c, sb, h->fit_stream[c], h->ev_filt[c])) != RM_OK) return rc;
     RM_CUDA(h, cudaEventRecord(h->ev_done[c], h->fit_stream[c]));
   }
-  for (int c = 0; c < n_chunks; ++c) RM_CUDA(h, cudaStreamWaitEvent(sa, h->ev_done[c], 0));   // join
+  h->pending_chunks = n_chunks;
+  if (!h->defer_join) return rmi_join(h, sa);
   return RM_OK;
 }
 

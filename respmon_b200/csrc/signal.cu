@@ -315,8 +315,14 @@ int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t s
 extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps,
                                  double* bpm_out, double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out,
                                  const int32_t* status, void* stream) {
-  int32_t rc = rmi_signal_setup(h, data, n_clips, n_frames, fps, bpm_out, filtered_out, peaks_out, npeaks_out, status, 1,
-                                (cudaStream_t)stream);
+  if (!h) return RM_ERR_INVALID;
+  int32_t rc;
+  {
+    DeviceGuard dg0(h->device);
+    if ((rc = rmi_join(h, (cudaStream_t)stream)) != RM_OK) return rc;
+  }
+  rc = rmi_signal_setup(h, data, n_clips, n_frames, fps, bpm_out, filtered_out, peaks_out, npeaks_out, status, 1,
+                        (cudaStream_t)stream);
   if (rc != RM_OK || n_clips == 0) return rc;
   DeviceGuard dg(h->device);
   return rmi_signal_range(h, 0, n_frames, 0, (cudaStream_t)stream, (cudaStream_t)stream, nullptr);
@@ -327,8 +333,22 @@ extern "C" int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_
   RM_CHECK_ARG(h, h && bpm && roi && status && out && n_clips >= 0 && n_frames >= 1, "null pointer or bad size");
   if (n_clips == 0) return RM_OK;
   DeviceGuard dg(h->device);
-  RM_PROF(h, (cudaStream_t)stream, "pack_results_kernel");
-  pack_results_kernel<<<div_up(n_clips, 128), 128, 0, (cudaStream_t)stream>>>(bpm, roi, status, npeaks, n_clips, n_frames, out);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->defer_join && h->pending_chunks > 0) {
+    // the signal stage of a deferred rm_measure_signal is still running: pack behind it on the tail stream and let the
+    // caller's stream go on; `out` is complete once rm_join (or the next call that joins) has been waited for
+    RM_CUDA(h, cudaEventRecord(h->ev_tail_fork, st));
+    RM_CUDA(h, cudaStreamWaitEvent(h->tail_stream, h->ev_tail_fork, 0));
+    for (int c = 0; c < h->pending_chunks; ++c) RM_CUDA(h, cudaStreamWaitEvent(h->tail_stream, h->ev_done[c], 0));
+    st = h->tail_stream;
+  }
+  RM_PROF(h, st, "pack_results_kernel");
+  pack_results_kernel<<<div_up(n_clips, 128), 128, 0, st>>>(bpm, roi, status, npeaks, n_clips, n_frames, out);
   RM_LAUNCH_CHECK(h);
+  if (st == h->tail_stream) {
+    RM_CUDA(h, cudaEventRecord(h->ev_packed, st));
+    h->pending_pack = 1;
+    h->pending_chunks = 0;     // ev_packed is behind every ev_done
+  }
   return RM_OK;
 }

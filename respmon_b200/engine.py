@@ -46,6 +46,21 @@ class Engine:
         if rc != 0:
             raise _cabi.RmError("rm_create failed (rc=%d): needs an sm_100 device" % rc)
         self._ws = {}
+        self._held = None       # tensors a deferred step may still be writing (see defer_join)
+
+    def defer_join(self, on: bool = True):
+        """Let run_batch return while the signal stage of the batch is still running on the handle's own streams
+        (rm_join in include/respmon_b200.h): the records are complete after join().  The engine keeps the step's
+        tensors alive until then."""
+        self.set_option("defer_join", 1 if on else 0)
+        self._defer = bool(on)
+        if not on:
+            self.join()
+
+    def join(self):
+        """Make the current stream wait for everything a deferred run_batch left running."""
+        self._call("rm_join", self._stream())
+        self._held = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -276,6 +291,9 @@ class Engine:
             m = dict(data=data)
             sig = self.signal_bpm(data, fps, status=status)
         rec = self.pack_results(sig["bpm"], roi, status, sig["npeaks"], out=out)
+        if getattr(self, "_defer", False):
+            # the previous step's tensors are safe to release now: this step's rm_measure_signal joined them on the stream
+            self._held = (roi, status, heat, m, sig, rec)
         if keep:
             return rec, dict(roi=roi, status=status, heat=heat, **m, **sig)
         return rec

@@ -209,7 +209,7 @@ def test_measure_signal_pipeline_equals_separate_calls(eng, golden, chunks):
     try:
         b = eng.measure_signal(d, roi, 130, 126, 10.0)
     finally:
-        eng.set_option("measure_chunks", 8)
+        eng.set_option("measure_chunks", 4)
     for k in ("data", "motion", "npts", "status"):
         assert torch.equal(a[k], b[k]) or np.array_equal(a[k].cpu().numpy(), b[k].cpu().numpy(), equal_nan=True), k
     for k in ("bpm", "filtered", "peaks", "npeaks"):

@@ -88,3 +88,45 @@ def test_run_batch_many_clips_match_oracle(eng):
             assert abs(got["bpm"] - want["bpm"]) <= 0.5
             n_ok += 1
     assert n_ok >= 4
+
+
+def test_deferred_join_gives_the_same_records(eng):
+    """Option defer_join: run_batch returns while the signal stage still runs; after join() nothing differs."""
+    from respmon_b200 import synth
+    from respmon_b200.engine import Engine, results_to_numpy
+    specs = [synth.clip_spec(s, 320, 240, 256) for s in range(60, 66)]
+    dq8 = np.stack([synth.displacement_q8(s) for s in specs])
+    clips = eng.synth_clips(specs, dq8)
+    want = results_to_numpy(eng.run_batch(clips, 10.0))
+    e2 = Engine(0)
+    e2.defer_join(True)
+    outs = [torch.empty((len(specs), 32), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    for k in range(4):                                   # back to back: every step's start joins the one before
+        e2.run_batch(clips, 10.0, out=outs[k & 1])
+    e2.join()
+    torch.cuda.synchronize()
+    for o in outs:
+        got = results_to_numpy(o)
+        for f in want.dtype.names:
+            assert np.array_equal(got[f], want[f], equal_nan=True), f
+    e2.defer_join(False)
+    e2.close()
+
+
+def test_measure_state_does_not_leak_between_batches(eng):
+    """A batch with many corners per clip, then one with few, through the same handle (chunk state is per call)."""
+    from respmon_b200 import synth
+    from respmon_b200.engine import Engine, results_to_numpy
+    rng = np.random.default_rng(7)
+    busy = rng.integers(0, 256, (2, 256, 96, 128), dtype=np.uint8)        # white noise: 100 corners per clip
+    roi_busy = torch.tensor([[8, 8, 112, 80]] * 2, dtype=torch.int32).cuda()
+    eng.measure_signal(torch.from_numpy(busy).cuda(), roi_busy, 130, 126, 10.0)
+    specs = [synth.clip_spec(s, 320, 240, 256) for s in range(70, 73)]
+    dq8 = np.stack([synth.displacement_q8(s) for s in specs])
+    clips = eng.synth_clips(specs, dq8)
+    got = results_to_numpy(eng.run_batch(clips, 10.0))
+    fresh = Engine(0)
+    want = results_to_numpy(fresh.run_batch(clips, 10.0))
+    fresh.close()
+    for f in want.dtype.names:
+        assert np.array_equal(got[f], want[f], equal_nan=True), f
