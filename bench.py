@@ -365,7 +365,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU")
-    ap.add_argument("--chunk", type=int, default=16, help="clips per H2D chunk of the end-to-end leg")
+    ap.add_argument("--chunk", type=int, default=32, help="clips per H2D chunk of the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--defer-join", action="store_true", help="overlap consecutive steps (see run_gpu_arm)")

@@ -15,7 +15,7 @@ host = torch.empty(clips.shape, dtype=torch.uint8).pin_memory()
 host.copy_(clips); torch.cuda.synchronize()
 del clips
 ref = None
-for chunk, streams, mch in [(8, 3, 8), (8, 3, 1), (8, 3, 2), (16, 3, 2), (8, 4, 1), (4, 4, 1), (16, 2, 4), (8, 2, 1)]:
+for chunk, streams, mch in [(32, 2, 4), (32, 2, 1), (32, 3, 2), (16, 2, 4), (64, 2, 4)]:
     mon = BatchMonitor(0, chunk_clips=chunk, measure_streams=streams)
     for e in mon._measure_engines:
         e.set_option("measure_chunks", mch)
