@@ -25,10 +25,10 @@ except Exception as e: print("bench parse failed", e)
 PY
 # launch list (cold-cache, serialised: shares only), 16 clips x 2 steps, skip nothing
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/launches.csv \
-    python tools/prof_step.py 16 2 > $OUT/launches.log 2>&1
+    python tools/prof_step.py 64 2 > $OUT/launches.log 2>&1
 # full captures of the dominant kernels (second step = warm)
-for K in pyramid_front_u8_kernel upsample_pass_kernel lk_track_smem_kernel; do
+for K in pyramid_front_u8_kernel upsample_pass_kernel lk_track_smem_kernel signal_fit_kernel; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 2 -f -o $OUT/$K \
-      python tools/prof_step.py 16 2 > $OUT/ncu_$K.log 2>&1
+      python tools/prof_step.py 64 2 > $OUT/ncu_$K.log 2>&1
 done
 ls -la $OUT
