@@ -197,6 +197,10 @@ __global__ void __launch_bounds__(512, 1) pyramid_front_u8_kernel(const PuParams
     const long long sframe = (frame / p.seg_len) * p.seg_stride + p.seg_first + frame % p.seg_len;
     const uint8_t* fsrc = p.frames + sframe * p.frame_elems;
     uint32_t* g3 = p.g3 + frame * g3_elems;
+    // The strips of a frame share their halo columns.  Left alone, the warps of a slot drift apart over the frames (edge
+    // strips are cheaper) until a halo sector read by one warp has left L2 before its neighbour asks for it -- 23 % extra
+    // DRAM reads at 8192 frames per launch (ncu, profiles/r01g).  A named barrier per slot re-aligns them every frame.
+    if (p.n_strips > 1) asm volatile("bar.sync %0, %1;\n" ::"r"(slot + 1), "r"(p.n_strips * 32) : "memory");
     if (left && right) pu_run_frame<WT, true, true>(p, fsrc, g3, ring, lane, col, store_lo, store_hi, store_hi);
     else if (left) pu_run_frame<WT, true, false>(p, fsrc, g3, ring, lane, col, store_lo, store_hi, store_hi);
     else if (right) pu_run_frame<WT, false, true>(p, fsrc, g3, ring, lane, col, store_lo, store_hi, store_hi);
