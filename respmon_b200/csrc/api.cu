@@ -128,6 +128,7 @@ extern "C" int32_t rm_create(const rm_params* params, int32_t device, rm_handle*
     ok = cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_filt[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_bulk[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->fit_stream[i], cudaStreamNonBlocking) == cudaSuccess;
   }
   if (!ok) {
@@ -161,6 +162,7 @@ extern "C" int32_t rm_destroy(rm_handle* h) {
       if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
       if (h->ev_filt[i]) cudaEventDestroy(h->ev_filt[i]);
       if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+      if (h->ev_bulk[i]) cudaEventDestroy(h->ev_bulk[i]);
       if (h->fit_stream[i]) cudaStreamDestroy(h->fit_stream[i]);
     }
     for (int i = 0; i < h->prof_cap; ++i) {

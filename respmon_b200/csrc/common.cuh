@@ -30,6 +30,7 @@ struct rm_handle {
   cudaStream_t aux_stream;                   // PCA + filtfilt/peaks of the chunks, in frame order
   cudaStream_t fit_stream[RM_MAX_CHUNKS];    // one per chunk: the Gaussian-fit gates of different chunks overlap
   cudaEvent_t ev_fork, ev_join, ev_chunk[RM_MAX_CHUNKS], ev_filt[RM_MAX_CHUNKS], ev_done[RM_MAX_CHUNKS];
+  cudaEvent_t ev_bulk[RM_MAX_CHUNKS];        // first fit pass of the chunk finished (deferred pipeline)
   int measure_chunks;       // option "measure_chunks"
   // Deferred join (option "defer_join"): rm_measure_signal returns without making the caller's stream wait for the
   // signal stage; rm_pack_results then runs on tail_stream behind it, and the caller's stream catches up in rm_join or
@@ -192,4 +193,4 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
                          int n_chunks, cudaStream_t st);
 int32_t rmi_join(rm_handle* h, cudaStream_t st);   // make st wait for whatever a deferred rm_measure_signal left running
 int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t st, cudaStream_t st_fit,
-                         cudaEvent_t ev_filtered);
+                         cudaEvent_t ev_filtered, cudaEvent_t ev_bulk);

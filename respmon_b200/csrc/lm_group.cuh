@@ -42,9 +42,15 @@ __device__ __noinline__ double lmg_enorm(const LmGroup& g, const double* v, int 
     mx = fmax(mx, a);
     s += a * a;
   }
-  mx = lmg_max<G>(g, mx);
+  // both butterflies in one pass: the two shuffle chains are independent, so their latencies overlap
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const double om = __shfl_xor_sync(g.mask, mx, o), os = __shfl_xor_sync(g.mask, s, o);
+    mx = fmax(mx, om);
+    s += os;
+  }
   if (mx == 0.0) return 0.0;
-  if (mx > 1e-140 && mx < 1e140) return sqrt(lmg_sum<G>(g, s));
+  if (mx > 1e-140 && mx < 1e140) return sqrt(s);
   s = 0.0;
 #pragma unroll 1
   for (int i = from + g.sub; i < m; i += G) { const double d = fabs(v[i]) / mx; s += d * d; }
@@ -64,29 +70,54 @@ __device__ __noinline__ void lmg_resid(const LmGroup& g, int m, const double* xs
 
 // xs, ys, fvec, wa4 (m each) and fjac (3m, column-major) are the group's shared-memory slices; xs/ys filled by the
 // caller (and visible: the caller syncs the group).  x[3] in/out (uniform over the group).  Returns MINPACK info.
+#ifdef LM_TIMING
+__device__ unsigned long long lm_timing[8];
+#define LMT(k) do { if (g.sub == 0) { long long n_ = clock64(); atomicAdd(&lm_timing[k], (unsigned long long)(n_ - tk_)); tk_ = n_; } } while (0)
+#define LMC(k) do { if (g.sub == 0) atomicAdd(&lm_timing[k], 1ull); } while (0)
+#else
+#define LMT(k) do { } while (0)
+#define LMC(k) do { } while (0)
+#endif
+__device__ __forceinline__ int i3_get(const int v[3], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }
+__device__ __forceinline__ void i3_put(int v[3], int i, int x) {
+  if (i == 0) v[0] = x;
+  else if (i == 1) v[1] = x;
+  else v[2] = x;
+}
+
+// The 3-parameter state (x, diag, qtf, R, the work vectors, the permutation) is indexed by compile-time constants only
+// -- loops over the parameters are unrolled, run-time indices go through selects (l3_get / l3_put, signal_core.h) -- so
+// it stays in registers; the routine is inlined into the kernel for the same reason.  The O(m) loops are not unrolled.
+// bail_nfev > 0: give up (return -1) once that many function evaluations have been spent at the top of an outer
+// iteration -- the caller re-queues the fit for the long-fit pass, which runs it again from the start without a limit.
 template <int G>
-__device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double* xs, const double* ys, double* x,
-                                            double* fvec, double* wa4, double* fjac) {
-  const int n = SC_NP;
+__device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double* xs, const double* ys, double x[3],
+                                               double* fvec, double* wa4, double* fjac, int bail_nfev) {
   const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
-  const int maxfev = 200 * (n + 1);
+  const int maxfev = 200 * (3 + 1);
   const double epsmch = SC_DBL_EPS, epsfcn = SC_DBL_EPS;
   const double p1 = 0.1, p5 = 0.5, p25 = 0.25, p75 = 0.75, p0001 = 1e-4;
-  double diag[SC_NP], qtf[SC_NP], wa1[SC_NP], wa2[SC_NP], wa3[SC_NP], sdiag[SC_NP];
-  double r[SC_NP * SC_NP];
-  int ipvt[SC_NP];
+  double diag[3], qtf[3], wa1[3], wa2[3], wa3[3], sdiag[3];
+  double r[9];
+  int ipvt[3];
   int info = 0, nfev = 0, iter = 1;
   double par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0;
-  if (m < n) return 0;
+  if (m < 3) return 0;
   lmg_resid<G>(g, m, xs, ys, x, fvec);
   nfev = 1;
   double fnorm = lmg_enorm<G>(g, fvec, m, 0);
+#ifdef LM_TIMING
+  long long tk_ = clock64();
+#endif
 #pragma unroll 1
   for (;;) {
+    if (bail_nfev > 0 && nfev >= bail_nfev) return -1;
+    LMT(5);
+    LMC(7);
     {   // fdjac2: forward differences (each lane differences the rows it evaluated)
       const double eps = sqrt(epsfcn > epsmch ? epsfcn : epsmch);
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
         const double temp = x[j];
         double h = eps * fabs(temp);
         if (h == 0.0) h = eps;
@@ -96,23 +127,24 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
 #pragma unroll 1
         for (int i = g.sub; i < m; i += G) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
       }
-      nfev += n;
+      nfev += 3;
     }
     __syncwarp(g.mask);
+    LMT(0);
     {   // qrfac with column pivoting; wa1 = rdiag, wa2 = acnorm, wa3 = work
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
         wa2[j] = lmg_enorm<G>(g, fjac + j * m, m, 0);
         wa1[j] = wa2[j];
         wa3[j] = wa1[j];
         ipvt[j] = j;
       }
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
         int kmax = j;
-#pragma unroll 1
-        for (int k = j; k < n; ++k)
-          if (wa1[k] > wa1[kmax]) kmax = k;
+#pragma unroll
+        for (int k = j; k < 3; ++k)
+          if (wa1[k] > l3_get(wa1, kmax)) kmax = k;
         if (kmax != j) {
 #pragma unroll 1
           for (int i = g.sub; i < m; i += G) {
@@ -120,9 +152,11 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
             fjac[i + j * m] = fjac[i + kmax * m];
             fjac[i + kmax * m] = t;
           }
-          wa1[kmax] = wa1[j];
-          wa3[kmax] = wa3[j];
-          const int t = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = t;
+          l3_put(wa1, kmax, wa1[j]);
+          l3_put(wa3, kmax, wa3[j]);
+          const int t = ipvt[j];
+          ipvt[j] = i3_get(ipvt, kmax);
+          i3_put(ipvt, kmax, t);
           __syncwarp(g.mask);
         }
         double ajnorm = lmg_enorm<G>(g, fjac + j * m, m, j);
@@ -133,8 +167,8 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
           for (int i = j + g.sub; i < m; i += G) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
           __syncwarp(g.mask);
           const double ajj = fjac[j + j * m];
-#pragma unroll 1
-          for (int k = j + 1; k < n; ++k) {
+#pragma unroll
+          for (int k = j + 1; k < 3; ++k) {
             double part = 0.0;
 #pragma unroll 1
             for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * fjac[i + k * m];
@@ -157,12 +191,13 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
         wa1[j] = -ajnorm;
       }
     }
+    LMT(1);
     if (iter == 1) {
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) { diag[j] = wa2[j]; if (wa2[j] == 0.0) diag[j] = 1.0; }
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) wa3[j] = diag[j] * x[j];
-      xnorm = sc_enorm(n, wa3);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { diag[j] = wa2[j]; if (wa2[j] == 0.0) diag[j] = 1.0; }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) wa3[j] = diag[j] * x[j];
+      xnorm = l3_enorm3(wa3[0], wa3[1], wa3[2]);
       delta = factor * xnorm;
       if (delta == 0.0) delta = factor;
     }
@@ -170,8 +205,8 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
 #pragma unroll 1
     for (int i = g.sub; i < m; i += G) wa4[i] = fvec[i];
     __syncwarp(g.mask);
-#pragma unroll 1
-    for (int j = 0; j < n; ++j) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
       const double ajj = fjac[j + j * m];
       if (ajj != 0.0) {
         double part = 0.0;
@@ -184,52 +219,56 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
       }
       qtf[j] = wa4[j];
     }
-#pragma unroll 1
-    for (int j = 0; j < n; ++j)
-#pragma unroll 1
-      for (int i = 0; i < n; ++i) r[i + j * SC_NP] = (i == j) ? wa1[j] : fjac[i + j * m];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) r[i + j * 3] = (i == j) ? wa1[j] : fjac[i + j * m];
     __syncwarp(g.mask);                                          // R and qtf are read before fjac / wa4 change again
     gnorm = 0.0;
     if (fnorm != 0.0) {
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) {
-        const int l = ipvt[j];
-        if (wa2[l] != 0.0) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double w2l = l3_get(wa2, ipvt[j]);
+        if (w2l != 0.0) {
           double sum = 0.0;
-#pragma unroll 1
-          for (int i = 0; i <= j; ++i) sum += r[i + j * SC_NP] * (qtf[i] / fnorm);
-          const double gg = fabs(sum / wa2[l]);
+#pragma unroll
+          for (int i = 0; i <= j; ++i) sum += r[i + j * 3] * (qtf[i] / fnorm);
+          const double gg = fabs(sum / w2l);
           gnorm = gnorm > gg ? gnorm : gg;
         }
       }
     }
     if (gnorm <= gtol) { info = 4; break; }
-#pragma unroll 1
-    for (int j = 0; j < n; ++j) diag[j] = diag[j] > wa2[j] ? diag[j] : wa2[j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) diag[j] = diag[j] > wa2[j] ? diag[j] : wa2[j];
     double ratio = 0.0;
-    do {
-      sc_lmpar(r, SC_NP, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
+    LMT(2);
 #pragma unroll 1
-      for (int j = 0; j < n; ++j) {
+    do {
+      l3_lmpar(r, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
+      LMT(3);
+      LMC(6);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
         wa1[j] = -wa1[j];
         wa2[j] = x[j] + wa1[j];
         wa3[j] = diag[j] * wa1[j];
       }
-      const double pnorm = sc_enorm(n, wa3);
+      const double pnorm = l3_enorm3(wa3[0], wa3[1], wa3[2]);
       if (iter == 1) delta = delta < pnorm ? delta : pnorm;
       lmg_resid<G>(g, m, xs, ys, wa2, wa4);
       ++nfev;
       const double fnorm1 = lmg_enorm<G>(g, wa4, m, 0);
       double actred = -1.0;
       if (p1 * fnorm1 < fnorm) { const double d = fnorm1 / fnorm; actred = 1.0 - d * d; }
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
         wa3[j] = 0.0;
-        const double temp = wa1[ipvt[j]];
-#pragma unroll 1
-        for (int i = 0; i <= j; ++i) wa3[i] += r[i + j * SC_NP] * temp;
+        const double temp = l3_get(wa1, ipvt[j]);
+#pragma unroll
+        for (int i = 0; i <= j; ++i) wa3[i] += r[i + j * 3] * temp;
       }
-      const double temp1 = sc_enorm(n, wa3) / fnorm;
+      const double temp1 = l3_enorm3(wa3[0], wa3[1], wa3[2]) / fnorm;
       const double temp2 = (sqrt(par) * pnorm) / fnorm;
       const double prered = temp1 * temp1 + temp2 * temp2 / p5;
       const double dirder = -(temp1 * temp1 + temp2 * temp2);
@@ -248,11 +287,11 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
         par = p5 * par;
       }
       if (ratio >= p0001) {
-#pragma unroll 1
-        for (int j = 0; j < n; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
 #pragma unroll 1
         for (int i = g.sub; i < m; i += G) fvec[i] = wa4[i];   // own rows only: no sync needed
-        xnorm = sc_enorm(n, wa2);
+        xnorm = l3_enorm3(wa2[0], wa2[1], wa2[2]);
         fnorm = fnorm1;
         ++iter;
       }
@@ -264,6 +303,7 @@ __device__ __noinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double
       if (fabs(actred) <= epsmch && prered <= epsmch && p5 * ratio <= 1.0) info = 6;
       if (delta <= epsmch * xnorm) info = 7;
       if (gnorm <= epsmch) info = 8;
+      LMT(4);
       if (info != 0) break;
     } while (ratio < p0001);
     if (info != 0) break;

@@ -1267,11 +1267,14 @@ extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_
     RM_CUDA(h, cudaEventRecord(h->ev_chunk[c], sa));
     RM_CUDA(h, cudaStreamWaitEvent(sb, h->ev_chunk[c], 0));
     if ((rc = measure_pca(h, &job, f0, f1, sb)) != RM_OK) return rc;
-    if ((rc = rmi_signal_range(h, f0, f1, c, sb, h->fit_stream[c], h->ev_filt[c])) != RM_OK) return rc;
+    if ((rc = rmi_signal_range(h, f0, f1, c, sb, h->fit_stream[c], h->ev_filt[c], h->ev_bulk[c])) != RM_OK) return rc;
     RM_CUDA(h, cudaEventRecord(h->ev_done[c], h->fit_stream[c]));
   }
   h->pending_chunks = n_chunks;
   if (!h->defer_join) return rmi_join(h, sa);
+  // deferred: the caller's stream waits for the first fit pass only; the long fits, the BPM fold and rm_pack_results
+  // finish behind it (rm_join)
+  for (int c = 0; c < n_chunks; ++c) RM_CUDA(h, cudaStreamWaitEvent(sa, h->ev_bulk[c], 0));
   return RM_OK;
 }
 

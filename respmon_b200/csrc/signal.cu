@@ -47,6 +47,9 @@ struct SignalScratch {
   unsigned* queue;         // fit work items: window * SIG_MAX_CAND + k
   unsigned* queue_n;
   unsigned* cursor;        // next queue item to fit
+  unsigned* long_queue;    // fits that exceeded the evaluation budget of the first pass (same item encoding)
+  unsigned* long_n;
+  unsigned* long_cursor;
 };
 
 __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalParams p, const SignalScratch s) {
@@ -99,15 +102,21 @@ template <int G>
 #ifndef SIG_FIT_MINB
 #define SIG_FIT_MINB 1
 #endif
+// bail_nfev > 0 (first pass of the deferred pipeline): a fit that has not converged after that many evaluations is
+// pushed to the long queue instead of being finished; long_pass = 1 drains that queue without a limit.  A handful of
+// fits per batch run ten times longer than the rest (MINPACK gives up on them after 800 evaluations): taking them out
+// of the first pass bounds the latency of everything that waits for the bulk.
 __global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_kernel(const SignalParams p, const SignalScratch s,
-                                                                      int m_cap) {
+                                                                      int m_cap, int bail_nfev, int long_pass) {
   extern __shared__ __align__(16) double fit_smem[];
   const int lane = threadIdx.x & 31;
   LmGroup g;
   g.sub = lane & (G - 1);
   g.mask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << (lane & ~(G - 1));
   const int group_in_block = threadIdx.x / G;
-  const unsigned total = *s.queue_n;
+  const unsigned total = long_pass ? *s.long_n : *s.queue_n;
+  const unsigned* queue = long_pass ? s.long_queue : s.queue;
+  unsigned* cursor = long_pass ? s.long_cursor : s.cursor;
   double* xs = fit_smem + (size_t)group_in_block * 7 * m_cap;
   double* ys = xs + m_cap;
   double* fvec = ys + m_cap;
@@ -115,10 +124,10 @@ __global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_kern
   double* fjac = wa4 + m_cap;
   for (;;) {
     unsigned item = 0;
-    if (g.sub == 0) item = atomicAdd(s.cursor, 1u);
+    if (g.sub == 0) item = atomicAdd(cursor, 1u);
     item = __shfl_sync(g.mask, item, lane & ~(G - 1));
     if (item >= total) return;                        // whole groups leave together
-    const unsigned q = s.queue[item];
+    const unsigned q = queue[item];
     const long long win = q / SIG_MAX_CAND;
     const int k = q % SIG_MAX_CAND;
     const int f = (int)(win % p.n_frames);
@@ -141,8 +150,11 @@ __global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_kern
     mx = lmg_max<G>(g, mx);
     __syncwarp(g.mask);
     double par[SC_NP] = {mx, xs[0], (xs[1] - xs[0]) * 5.0};   // peakutils.gaussian_fit initial guess
-    const int info = lmg_lmdif_gauss<G>(g, m, xs, ys, par, fvec, wa4, fjac);
-    if (g.sub == 0) s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334, 336
+    const int info = lmg_lmdif_gauss<G>(g, m, xs, ys, par, fvec, wa4, fjac, long_pass ? 0 : bail_nfev);
+    if (g.sub == 0) {
+      if (info == -1) s.long_queue[atomicAdd(s.long_n, 1u)] = q;
+      else s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334, 336
+    }
   }
 }
 
@@ -243,7 +255,7 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
   p.tvals = h->d_tvals;
   // scratch owned by the handle, grown on demand
   const size_t n_win = (size_t)n_clips * n_frames;
-  const size_t need = n_win * p.buf_len * 8 + n_win * SIG_MAX_CAND * 2 + n_win * 4 + n_win * SIG_MAX_CAND * 4 + 1024;
+  const size_t need = n_win * p.buf_len * 8 + n_win * SIG_MAX_CAND * 2 + n_win * 4 + 2 * n_win * SIG_MAX_CAND * 4 + 1024;
   if (h->sig_scratch_bytes < need) {
     if (h->d_sig_scratch) cudaFree(h->d_sig_scratch);
     h->d_sig_scratch = nullptr;
@@ -255,11 +267,14 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
   unsigned char* base = reinterpret_cast<unsigned char*>(h->d_sig_scratch);
   sc.filt = reinterpret_cast<double*>(base);                base += n_win * p.buf_len * 8;
   sc.queue = reinterpret_cast<unsigned*>(base);             base += n_win * SIG_MAX_CAND * 4;
+  sc.long_queue = reinterpret_cast<unsigned*>(base);        base += n_win * SIG_MAX_CAND * 4;
   sc.ncand = reinterpret_cast<int*>(base);                  base += n_win * 4;
-  sc.queue_n = reinterpret_cast<unsigned*>(base);           base += 256;   // 2 counters per chunk (RM_MAX_CHUNKS <= 32)
+  sc.queue_n = reinterpret_cast<unsigned*>(base);           base += 256;   // 4 counters per chunk (RM_MAX_CHUNKS <= 16)
   sc.cand = base;                                           base += n_win * SIG_MAX_CAND;
   sc.acc = base;
   sc.cursor = sc.queue_n + 1;
+  sc.long_n = sc.queue_n + 2;
+  sc.long_cursor = sc.queue_n + 3;
   // every window holds at most (buf_len / width + 1) candidates that survive min_dist = width
   job->m_cap = 2 * p.width < SC_MAX_FIT ? 2 * p.width : SC_MAX_FIT;
   if (job->m_cap < 4) job->m_cap = 4;
@@ -281,8 +296,17 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
 }
 
 // measure() for the windows ending at frames [f0, f1) (chunk index `chunk` selects the fit queue) on stream st.
+#ifdef LM_TIMING
+extern "C" int32_t rm_debug_lm_timing(unsigned long long* host_out8, int32_t reset) {
+  if (host_out8) cudaMemcpyFromSymbol(host_out8, lm_timing, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(lm_timing, z, sizeof(z)); }
+  return 0;
+}
+#endif
+#define SIG_BAIL_NFEV 200     // evaluations a fit may spend in the first pass (99.97 % of fits need fewer)
+#define SIG_LONG_BLOCKS 16
 int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t st, cudaStream_t st_fit,
-                         cudaEvent_t ev_filtered) {
+                         cudaEvent_t ev_filtered, cudaEvent_t ev_bulk) {
   SignalJob* job = reinterpret_cast<SignalJob*>(h->sig_job);
   if (!job || chunk < 0 || chunk >= RM_MAX_CHUNKS) return rm_fail(h, RM_ERR_INVALID, "%s: no signal job", __func__);
   if (job->p.n_clips == 0 || f1 <= f0) return RM_OK;
@@ -290,8 +314,11 @@ int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t s
   SignalScratch sc = job->sc;
   p.f0 = f0; p.f1 = f1;
   sc.queue = job->sc.queue + (size_t)p.n_clips * f0 * SIG_MAX_CAND;   // a slice no other chunk's windows can reach
-  sc.queue_n = job->sc.queue_n + 2 * chunk;
+  sc.long_queue = job->sc.long_queue + (size_t)p.n_clips * f0 * SIG_MAX_CAND;
+  sc.queue_n = job->sc.queue_n + 4 * chunk;
   sc.cursor = sc.queue_n + 1;
+  sc.long_n = sc.queue_n + 2;
+  sc.long_cursor = sc.queue_n + 3;
   dim3 grid(div_up(f1 - f0, 64), p.n_clips);
   RM_PROF(h, st, "signal_filter_peaks_kernel");
   signal_filter_peaks_kernel<<<grid, 64, 0, st>>>(p, sc);
@@ -303,9 +330,21 @@ int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t s
   const int groups = SIG_FIT_THREADS / SIG_FIT_G;
   long long grid_fit = div_up((long long)(job->max_items_per_frame * (size_t)(f1 - f0)), groups);
   if (grid_fit > job->grid_cap) grid_fit = job->grid_cap;
+  // deferred pipeline: the first pass hands fits that are still running after SIG_BAIL_NFEV evaluations to a second,
+  // narrow pass (64-thread blocks: they fit beside the next batch's calibration kernels on an SM); ev_bulk marks the
+  // end of the first pass, which is all the caller's stream has to wait for
+  const int bail = (ev_bulk && h->defer_join) ? SIG_BAIL_NFEV : 0;
   RM_PROF(h, st_fit, "signal_fit_kernel");
-  signal_fit_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, job->fit_smem, st_fit>>>(p, sc, job->m_cap);
+  signal_fit_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, job->fit_smem, st_fit>>>(p, sc, job->m_cap, bail, 0);
   RM_LAUNCH_CHECK(h);
+  if (ev_bulk) RM_CUDA(h, cudaEventRecord(ev_bulk, st_fit));
+  if (bail) {
+    const int long_threads = 64, long_groups = long_threads / SIG_FIT_G;
+    RM_PROF(h, st_fit, "signal_fit_long_kernel");
+    signal_fit_kernel<SIG_FIT_G><<<SIG_LONG_BLOCKS, long_threads, (size_t)long_groups * 7 * job->m_cap * sizeof(double),
+                                   st_fit>>>(p, sc, job->m_cap, 0, 1);
+    RM_LAUNCH_CHECK(h);
+  }
   RM_PROF(h, st_fit, "signal_bpm_kernel");
   signal_bpm_kernel<<<grid, 64, 0, st_fit>>>(p, sc);
   RM_LAUNCH_CHECK(h);
@@ -325,7 +364,7 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
                         (cudaStream_t)stream);
   if (rc != RM_OK || n_clips == 0) return rc;
   DeviceGuard dg(h->device);
-  return rmi_signal_range(h, 0, n_frames, 0, (cudaStream_t)stream, (cudaStream_t)stream, nullptr);
+  return rmi_signal_range(h, 0, n_frames, 0, (cudaStream_t)stream, (cudaStream_t)stream, nullptr, nullptr);
 }
 
 extern "C" int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, const int32_t* status,

@@ -376,12 +376,241 @@ RM_HD_NOINLINE void sc_lmpar(double* r, int ldr, const int* ipvt, const double* 
   if (iter == 0) *par = 0.0;
 }
 
+// ------------------------------------------------------------------------------------------------ register-resident 3x3
+// MINPACK's 3-parameter trust-region algebra (enorm, qrsolv, lmpar) once more, with every array index a compile-time
+// constant: same operations in the same order as sc_enorm / sc_qrsolv / sc_lmpar above (the scalar port the host tests
+// pin against SciPy's curve_fit); what changes is only how the code is laid out for the GPU: the loops over the three
+// parameters are fully unrolled, the permutation vector is read through selects, and nothing takes the address of a local
+// array across a call -- so the 3x3 state lives in registers instead of local memory.  The Gaussian-fit gate is a long
+// dependent float64 chain (MINPACK spends up to 200 outer iterations on a handful of fits per batch), and that chain was
+// spending most of its time on local-memory round trips and instruction fetch.  sc_lmdif_gauss(..., use_l3 = 1) runs the
+// scalar fit through these routines; tests/test_signal_core_host.py checks it against use_l3 = 0 bit for bit.
+#ifdef __CUDACC__
+#define L3_INL __host__ __device__ __forceinline__
+#define L3_NOINL static __host__ __device__ __noinline__
+#else
+#define L3_INL inline
+#define L3_NOINL static inline
+#endif
+
+// v[i] for a run-time i in 0..2 without indexing memory
+L3_INL double l3_get(const double v[3], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }
+L3_INL void l3_put(double v[3], int i, double x) {
+  if (i == 0) v[0] = x;
+  else if (i == 1) v[1] = x;
+  else v[2] = x;
+}
+
+// one term of MINPACK enorm's three-range accumulation
+L3_INL void l3_enorm_acc(double xabs, double agiant, double& s1, double& s2, double& s3, double& x1max, double& x3max) {
+  const double rdwarf = 3.834e-20;
+  if (xabs > rdwarf && xabs < agiant) {
+    s2 += xabs * xabs;
+  } else if (xabs <= rdwarf) {
+    if (xabs <= x3max) {
+      if (xabs != 0.0) { const double d = xabs / x3max; s3 += d * d; }
+    } else {
+      const double d = x3max / xabs;
+      s3 = 1.0 + s3 * (d * d);
+      x3max = xabs;
+    }
+  } else {
+    if (xabs <= x1max) {
+      const double d = xabs / x1max;
+      s1 += d * d;
+    } else {
+      const double d = x1max / xabs;
+      s1 = 1.0 + s1 * (d * d);
+      x1max = xabs;
+    }
+  }
+}
+// sc_enorm(3, {a, b, c}).  The common case (all three in the unscaled range) is sqrt(a^2 + b^2 + c^2) summed in order,
+// which is what the general routine computes for it; everything else takes the general path.
+L3_NOINL double l3_enorm3(double a, double b, double c) {
+  const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+  const double agiant = rgiant / 3.0;
+  const double xa = fabs(a), xb = fabs(b), xc = fabs(c);
+  if (xa > rdwarf && xa < agiant && xb > rdwarf && xb < agiant && xc > rdwarf && xc < agiant) {
+    double s2 = 0.0;
+    s2 += xa * xa;
+    s2 += xb * xb;
+    s2 += xc * xc;
+    return sqrt(s2);                 // s1 == 0, s2 != 0, x3max == 0 <= s2:  sqrt(s2 * (1 + (0 / s2) * (0 * s3))) == sqrt(s2)
+  }
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0, x1max = 0.0, x3max = 0.0;
+  l3_enorm_acc(xa, agiant, s1, s2, s3, x1max, x3max);
+  l3_enorm_acc(xb, agiant, s1, s2, s3, x1max, x3max);
+  l3_enorm_acc(xc, agiant, s1, s2, s3, x1max, x3max);
+  if (s1 != 0.0) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+  if (s2 != 0.0) {
+    if (s2 >= x3max) return sqrt(s2 * (1.0 + (x3max / s2) * (x3max * s3)));
+    return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
+  }
+  return x3max * sqrt(s3);
+}
+
+// sc_qrsolv with ldr = 3: r is the full 3x3 (column-major) work matrix, as in MINPACK.
+L3_INL void l3_qrsolv(double r[9], const int ipvt[3], const double diag[3], const double qtb[3], double x[3],
+                      double sdiag[3], double wa[3]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+#pragma unroll
+    for (int i = j; i < 3; ++i) r[i + j * 3] = r[j + i * 3];
+    x[j] = r[j + j * 3];
+    wa[j] = qtb[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double dl = l3_get(diag, ipvt[j]);
+    if (dl != 0.0) {
+#pragma unroll
+      for (int k = j; k < 3; ++k) sdiag[k] = 0.0;
+      sdiag[j] = dl;
+      double qtbpj = 0.0;
+#pragma unroll
+      for (int k = j; k < 3; ++k) {
+        if (sdiag[k] != 0.0) {
+          double cs, sn;
+          if (fabs(r[k + k * 3]) < fabs(sdiag[k])) {
+            const double cotan = r[k + k * 3] / sdiag[k];
+            sn = 0.5 / sqrt(0.25 + 0.25 * (cotan * cotan));
+            cs = sn * cotan;
+          } else {
+            const double tn = sdiag[k] / r[k + k * 3];
+            cs = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
+            sn = cs * tn;
+          }
+          r[k + k * 3] = cs * r[k + k * 3] + sn * sdiag[k];
+          double temp = cs * wa[k] + sn * qtbpj;
+          qtbpj = -sn * wa[k] + cs * qtbpj;
+          wa[k] = temp;
+#pragma unroll
+          for (int i = k + 1; i < 3; ++i) {
+            temp = cs * r[i + k * 3] + sn * sdiag[i];
+            sdiag[i] = -sn * r[i + k * 3] + cs * sdiag[i];
+            r[i + k * 3] = temp;
+          }
+        }
+      }
+    }
+    sdiag[j] = r[j + j * 3];
+    r[j + j * 3] = x[j];
+  }
+  int nsing = 3;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (sdiag[j] == 0.0 && nsing == 3) nsing = j;
+    if (nsing < 3) wa[j] = 0.0;
+  }
+#pragma unroll
+  for (int j = 2; j >= 0; --j) {             // for k = 1..nsing: j = nsing - k
+    if (j < nsing) {
+      double sum = 0.0;
+#pragma unroll
+      for (int i = j + 1; i < 3; ++i)
+        if (i < nsing) sum += r[i + j * 3] * wa[i];
+      wa[j] = (wa[j] - sum) / sdiag[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) l3_put(x, ipvt[j], wa[j]);
+}
+
+// sc_lmpar with ldr = 3.
+L3_INL void l3_lmpar(double r[9], const int ipvt[3], const double diag[3], const double qtb[3], double delta, double* par,
+                     double x[3], double sdiag[3], double wa1[3], double wa2[3]) {
+  const double p1 = 0.1, p001 = 0.001, dwarf = SC_DBL_MIN;
+  int nsing = 3;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    wa1[j] = qtb[j];
+    if (r[j + j * 3] == 0.0 && nsing == 3) nsing = j;
+    if (nsing < 3) wa1[j] = 0.0;
+  }
+#pragma unroll
+  for (int j = 2; j >= 0; --j) {             // for k = 1..nsing: j = nsing - k
+    if (j < nsing) {
+      wa1[j] /= r[j + j * 3];
+      const double temp = wa1[j];
+#pragma unroll
+      for (int i = 0; i < j; ++i) wa1[i] -= r[i + j * 3] * temp;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) l3_put(x, ipvt[j], wa1[j]);
+  int iter = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) wa2[j] = diag[j] * x[j];
+  double dxnorm = l3_enorm3(wa2[0], wa2[1], wa2[2]);
+  double fp = dxnorm - delta;
+  if (fp <= p1 * delta) { *par = 0.0; return; }
+  double parl = 0.0;
+  if (nsing >= 3) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const int l = ipvt[j]; wa1[j] = l3_get(diag, l) * (l3_get(wa2, l) / dxnorm); }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double sum = 0.0;
+#pragma unroll
+      for (int i = 0; i < j; ++i) sum += r[i + j * 3] * wa1[i];
+      wa1[j] = (wa1[j] - sum) / r[j + j * 3];
+    }
+    const double temp = l3_enorm3(wa1[0], wa1[1], wa1[2]);
+    parl = fp / delta / temp / temp;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i <= j; ++i) sum += r[i + j * 3] * qtb[i];
+    wa1[j] = sum / l3_get(diag, ipvt[j]);
+  }
+  const double gnorm = l3_enorm3(wa1[0], wa1[1], wa1[2]);
+  double paru = gnorm / delta;
+  if (paru == 0.0) paru = dwarf / (delta < p1 ? delta : p1);
+  *par = *par > parl ? *par : parl;
+  *par = *par < paru ? *par : paru;
+  if (*par == 0.0) *par = gnorm / dxnorm;
+#pragma unroll 1
+  for (;;) {
+    ++iter;
+    if (*par == 0.0) { const double t = p001 * paru; *par = dwarf > t ? dwarf : t; }
+    double temp = sqrt(*par);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) wa1[j] = temp * diag[j];
+    l3_qrsolv(r, ipvt, wa1, qtb, x, sdiag, wa2);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) wa2[j] = diag[j] * x[j];
+    dxnorm = l3_enorm3(wa2[0], wa2[1], wa2[2]);
+    temp = fp;
+    fp = dxnorm - delta;
+    if (fabs(fp) <= p1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const int l = ipvt[j]; wa1[j] = l3_get(diag, l) * (l3_get(wa2, l) / dxnorm); }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      wa1[j] /= sdiag[j];
+      temp = wa1[j];
+#pragma unroll
+      for (int i = j + 1; i < 3; ++i) wa1[i] -= r[i + j * 3] * temp;
+    }
+    temp = l3_enorm3(wa1[0], wa1[1], wa1[2]);
+    const double parc = fp / delta / temp / temp;
+    if (fp > 0.0) parl = parl > *par ? parl : *par;
+    if (fp < 0.0) paru = paru < *par ? paru : *par;
+    const double cand = *par + parc;
+    *par = parl > cand ? parl : cand;
+  }
+  if (iter == 0) *par = 0.0;
+}
+
 // scipy.optimize.curve_fit(gaussian, xs, ys, p0) -> leastsq -> MINPACK lmdif with SciPy's defaults
 // (ftol = xtol = 1.49012e-8, gtol = 0, maxfev = 200*(n+1), epsfcn = eps, factor = 100, mode 1).
 // x[3] in/out.  Returns MINPACK `info` (1..4 = converged; anything else makes curve_fit raise RuntimeError).
 // fjac: scratch m*3, fvec/wa4: scratch m each.
 RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, double* x, double* fvec, double* fjac,
-                                  double* wa4, int* nfev_out) {
+                                  double* wa4, int* nfev_out, int use_l3 = 0) {
   const int n = SC_NP;
   const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
   const int maxfev = 200 * (n + 1);
@@ -418,7 +647,7 @@ RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, dou
       for (int j = 0; j < n; ++j) { diag[j] = wa2[j]; if (wa2[j] == 0.0) diag[j] = 1.0; }
 #pragma unroll 1
       for (int j = 0; j < n; ++j) wa3[j] = diag[j] * x[j];
-      xnorm = sc_enorm(n, wa3);
+      xnorm = (use_l3 ? l3_enorm3(wa3[0], wa3[1], wa3[2]) : sc_enorm(n, wa3));
       delta = factor * xnorm;
       if (delta == 0.0) delta = factor;
     }
@@ -456,14 +685,23 @@ RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, dou
     for (int j = 0; j < n; ++j) diag[j] = diag[j] > wa2[j] ? diag[j] : wa2[j];
     double ratio = 0.0;
     do {
-      sc_lmpar(fjac, m, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
+      if (use_l3) {
+        double r3[9];
+        for (int j = 0; j < 3; ++j)
+          for (int i = 0; i < 3; ++i) r3[i + j * 3] = fjac[i + j * m];
+        l3_lmpar(r3, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
+        for (int j = 0; j < 3; ++j)
+          for (int i = 0; i < 3; ++i) fjac[i + j * m] = r3[i + j * 3];
+      } else {
+        sc_lmpar(fjac, m, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
+      }
 #pragma unroll 1
       for (int j = 0; j < n; ++j) {
         wa1[j] = -wa1[j];
         wa2[j] = x[j] + wa1[j];
         wa3[j] = diag[j] * wa1[j];
       }
-      const double pnorm = sc_enorm(n, wa3);
+      const double pnorm = (use_l3 ? l3_enorm3(wa3[0], wa3[1], wa3[2]) : sc_enorm(n, wa3));
       if (iter == 1) delta = delta < pnorm ? delta : pnorm;
       sc_gauss_resid(m, xs, ys, wa2, wa4);
       ++nfev;
@@ -477,7 +715,7 @@ RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, dou
 #pragma unroll 1
         for (int i = 0; i <= j; ++i) wa3[i] += fjac[i + j * m] * temp;
       }
-      const double temp1 = sc_enorm(n, wa3) / fnorm;
+      const double temp1 = (use_l3 ? l3_enorm3(wa3[0], wa3[1], wa3[2]) : sc_enorm(n, wa3)) / fnorm;
       const double temp2 = (sqrt(par) * pnorm) / fnorm;
       const double prered = temp1 * temp1 + temp2 * temp2 / p5;
       const double dirder = -(temp1 * temp1 + temp2 * temp2);
@@ -500,7 +738,7 @@ RM_HD_NOINLINE int sc_lmdif_gauss(int m, const double* xs, const double* ys, dou
         for (int j = 0; j < n; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
 #pragma unroll 1
         for (int i = 0; i < m; ++i) fvec[i] = wa4[i];
-        xnorm = sc_enorm(n, wa2);
+        xnorm = (use_l3 ? l3_enorm3(wa2[0], wa2[1], wa2[2]) : sc_enorm(n, wa2));
         fnorm = fnorm1;
         ++iter;
       }

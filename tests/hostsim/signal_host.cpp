@@ -15,6 +15,10 @@ int host_gauss_fit(int m, const double* xs, const double* ys, double* p, int* nf
   ScScratch s;
   return sc_lmdif_gauss(m, xs, ys, p, s.fvec, s.fjac, s.wa4, nfev);
 }
+int host_gauss_fit_l3(int m, const double* xs, const double* ys, double* p, int* nfev) {
+  ScScratch s;   // the same fit through the register-layout 3x3 routines (l3_*) the CUDA kernel uses
+  return sc_lmdif_gauss(m, xs, ys, p, s.fvec, s.fjac, s.wa4, nfev, 1);
+}
 int host_measure_window(const double* data, const double* t, int n, const double* b, const double* a, int nc, int width,
                         double thres, double cutoff, double* filtered, int* peaks, double* bpm) {
   ScScratch s;

@@ -122,3 +122,52 @@ def test_pca_projection(lib):
         want = P.pca_project_last(m)
         got = lib.host_pca_project_last(m.ctypes.data_as(C.POINTER(C.c_float)), len(m))
         assert abs(got - want) <= 1e-13 * max(1.0, abs(want))
+
+
+def _golden_fit_windows(golden):
+    """Every (xs, ys) the reference's find_peaks hands to gaussian_fit on the golden clips (base.py:318-327)."""
+    b, a = scipy.signal.butter(3, 0.1)
+    for name in ("vga_s0", "vga_s2", "qvga_s1", "odd_s3", "qvga_long_s4"):
+        fix = golden(name)
+        data = fix["data"]
+        t_all = np.concatenate([[0.0], np.cumsum(np.full(len(data) - 1, 0.1))])
+        for f in range(12, len(data)):
+            n = f + 1
+            y = scipy.signal.filtfilt(b, a, data[:n])
+            for idx in pk.indexes(y, min_dist=10):
+                w = 10
+                if idx - 10 < 0:
+                    w = idx
+                if idx + w > n:
+                    w = n - idx
+                if 2 * w >= 3:
+                    yield np.ascontiguousarray(t_all[idx - w:idx + w]), np.ascontiguousarray(y[idx - w:idx + w])
+
+
+def test_register_layout_lm_is_bit_identical_to_the_scalar_port(lib, golden):
+    """l3_enorm3 / l3_qrsolv / l3_lmpar (the unrolled, select-indexed 3x3 routines the CUDA kernel runs) against
+    sc_enorm / sc_qrsolv / sc_lmpar on whole fits: same info, same nfev, same parameter bits -- on synthetic windows,
+    on windows scaled into enorm's rescaling ranges, and on every fit of the golden clips (incl. the ones MINPACK gives
+    up on after 800 evaluations)."""
+    cases = list(_fit_cases())
+    rng = np.random.default_rng(3)
+    for xs, ys in list(cases[:40]):
+        cases.append((xs, ys * 1e-25))                  # residuals below enorm's rdwarf
+        cases.append((xs * 1e3, ys * 1e21))             # above rgiant / n
+        cases.append((xs, np.zeros_like(ys)))           # exact zeros
+    for m in (3, 4, 5, 6):
+        for _ in range(40):
+            xs = 1.6 + 0.1 * np.arange(m)
+            cases.append((xs, rng.uniform(-0.2, 0.2, m)))   # tiny windows: the degenerate fits of the first frames
+    cases += list(_golden_fit_windows(golden))
+    n_long = 0
+    for xs, ys in cases:
+        out = []
+        for fn in (lib.host_gauss_fit, lib.host_gauss_fit_l3):
+            p = np.array([ys.max(), xs[0], (xs[1] - xs[0]) * 5])
+            nfev = C.c_int()
+            info = fn(len(xs), dptr(xs), dptr(ys), dptr(p), C.byref(nfev))
+            out.append((info, nfev.value, p.tobytes()))
+        assert out[0] == out[1], (xs, ys, out[0][:2], out[1][:2])
+        n_long += out[0][1] >= 400
+    assert len(cases) > 1500 and n_long >= 1
