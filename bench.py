@@ -278,6 +278,32 @@ def run_gpu_arm(args) -> dict | None:
     truth = np.array([s.truth_bpm for s in specs])
     bpm_err = np.abs(recs["bpm"][ok] - truth[ok])
 
+    # ---- per-stage figures for BASELINE configs 2 and 3 (N = 1 only; not part of the timed region above)
+    extras = None
+    if world == 1:
+        def timed(fn, iters=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters
+        roi_dev, st_dev, _ = eng.locate(clips, FPS, 1, 128)
+        t128 = timed(lambda: eng.locate(clips, FPS, 1, 128))
+        t256 = timed(lambda: eng.locate(clips, FPS, 0, 256))
+        tm = timed(lambda: eng.measure_signal(clips, roi_dev, 130, T - 130, FPS, status=st_dev.clone()))
+        extras = {
+            "calibrate_only_frames_per_s": {"T_cal_128 (reference routing)": n_clips * 128 / t128 * 1e3,
+                                            "T_cal_256 (locate on the whole clip)": n_clips * 256 / t256 * 1e3,
+                                            "ms": [t128, t256], "config": "BASELINE config 2: 64 clips, calibration only"},
+            "measure_only_frame_steps_per_s": {"value": n_clips * (T - 130) / tm * 1e3, "ms": tm,
+                                               "config": "BASELINE config 3's loop at 64 clips: LK + PCA + filtfilt + "
+                                                         "peaks + LM gate + BPM over 126 frames per clip, ROIs given"},
+        }
+
     # ---- end to end from host memory through the public batch API
     host = torch.empty(clips.shape, dtype=torch.uint8).pin_memory()
     host.copy_(clips)
@@ -350,6 +376,7 @@ def run_gpu_arm(args) -> dict | None:
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "extras": extras,
         "kernels": kernels,
         "results": {"clips_ok": int(ok.sum()), "clips": int(n_clips),
                     "median_abs_bpm_error_vs_truth": float(np.median(bpm_err)) if len(bpm_err) else None,
