@@ -46,6 +46,7 @@ struct rm_handle {
   int* d_lk_n;              // (cap_clips, 16) points each block of a clip still tracks
   int lk_state_cap;
   void* sig_job;            // host-side SignalJob of the measure pipeline (signal.cu)
+  int no_minmax_seed;       // tests: pass 1 of the heat map without the seed kernel (no pruning at the start)
   int force_global_lk;
   int force_generic_front;  // tests: float64 pyramid front even for uint8 frames the integer front supports  // tests: take the global-memory LK path even when the ROI fits shared memory
   int prof_on;

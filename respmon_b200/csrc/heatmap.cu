@@ -118,6 +118,9 @@ struct TileParams {
   unsigned long long* minmax_keys;   // (n_clips, 4) order-preserving keys: raw min, raw max, avg min, avg max
   double threshold;        // temporal_threshold (pass 2)
   double* avg_out;         // (n_clips, H, W) pass 2
+  const double2* bounds;   // (n_clips, tiles, T) smallest / largest level-`skip` value each tile-frame depends on, or null
+  const double* a_top;     // (n_clips, T, h_top * w_top) level `skip` images (tile_bounds_kernel)
+  int top_w, top_h, n_up;  // their size; number of pyrUp steps from there to level 0
 };
 
 __device__ __forceinline__ unsigned long long f64_key(double v) {   // monotone map double -> uint64
@@ -206,7 +209,8 @@ __device__ __forceinline__ void block4x4(const double v[4][4], const AxisGeom& g
 #define HM_PH 11            // 32/4 + 3 rows
 #define HM_COPIES 2         // ceil(19 * 11 / 128) cp.async per thread per frame
 template <int PASS, bool EDGE>
-__device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* red_a, double* red_b, double* stage) {
+__device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* red_a, double* red_b, double* stage,
+                                                   int* frame_list) {
   const int tile = blockIdx.x;
   const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
   const int clip = blockIdx.y;
@@ -234,6 +238,29 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
   double vmin = INFINITY, vmax = -INFINITY;
   double top_s = 0.0, repl_s = 0.0;
+  // Pass 1 looks only at the frames that can still change the clip's min / max.  pyrUp is a convex combination, so every
+  // level-0 value of this tile in frame t lies between the smallest and the largest level-`skip` value of the tile's
+  // neighbourhood (tile_bounds_kernel); if that interval -- widened by 1e-12 relative, far above the few ulps the
+  // evaluation can add -- is inside the extremes already known when the block starts (the seed kernel's and earlier
+  // blocks'), the frame is skipped: nothing is staged or evaluated for it.  The result is bit-identical.
+  int n_list = p.T;
+  if (PASS == 1 && p.bounds) {
+    __shared__ int s_count;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    const unsigned long long kmin = p.minmax_keys[clip * 4 + 0], kmax = p.minmax_keys[clip * 4 + 1];
+    const bool known = kmin <= kmax;   // the keys are at their initial values otherwise (min key > max key)
+    const double gmin = known ? key_f64(kmin) : 0.0, gmax = known ? key_f64(kmax) : 0.0;
+    const double2* b = p.bounds + ((long long)clip * gridDim.x + tile) * p.T;
+    for (int t = tid; t < p.T; t += blockDim.x) {
+      const double2 lh = b[t];
+      const double mrg = 1e-12 * fmax(fabs(lh.x), fabs(lh.y));
+      const bool skip = known && lh.y + mrg <= gmax && lh.x - mrg >= gmin;
+      if (!skip) frame_list[atomicAdd(&s_count, 1)] = t;
+    }
+    __syncthreads();
+    n_list = s_count;
+  }
   if (PASS == 2) {
     const double lo = key_f64(p.minmax_keys[clip * 4 + 0]), hi = key_f64(p.minmax_keys[clip * 4 + 1]);
     // transforms.py:185-189 on the scaled values; the comparison runs in the unscaled domain (scale is 2^-k: exact)
@@ -263,10 +290,11 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
 #pragma unroll
     for (int c = 0; c < 4; ++c) offs[r][c] = (gy.v[r] - ylo) * HM_PW + (gx.v[c] - xlo);
   const unsigned stage_base = (unsigned)__cvta_generic_to_shared(stage);
-  auto issue = [&](int t) {
-    if (t < p.T) {
+  auto issue = [&](int k) {
+    if (k < n_list) {
+      const int t = (PASS == 1 && p.bounds) ? frame_list[k] : k;
       const double* l2 = a_clip + t * n2;
-      const unsigned dst = stage_base + (unsigned)((t % HM_STAGES) * HM_PW * HM_PH * 8);
+      const unsigned dst = stage_base + (unsigned)((k % HM_STAGES) * HM_PW * HM_PH * 8);
 #pragma unroll
       for (int k = 0; k < HM_COPIES; ++k)
         if (src_off[k] >= 0)
@@ -279,7 +307,7 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
   for (int t = 0; t < HM_STAGES - 1; ++t) issue(t);
 
   {
-    for (int t = 0; t < p.T; ++t) {
+    for (int t = 0; t < n_list; ++t) {   // t = position in the frame list (pass 2: the frame itself)
       asm volatile("cp.async.wait_group %0;\n" ::"n"(HM_STAGES - 2) : "memory");
       __syncthreads();                 // frame t has landed for everyone; everyone is done with frame t-1's stage
       issue(t + HM_STAGES - 1);        // refills the stage frame t-1 used
@@ -379,6 +407,90 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
   }
 }
 
+// (lo, hi) of the level-`skip` values that the level-0 pixels of tile `tile` depend on in frame t.  The footprint is the
+// tile's pixel range pushed up one level at a time: x at level l needs floor(x/2) - 1 .. floor(x/2) + 1 at level l+1 (the
+// border rules -- reflect-101 below, clamp above -- only ever pick indices inside that range once it is clamped to the
+// image).  One thread per (frame, tile, clip).
+__global__ void tile_bounds_kernel(const TileParams p, double2* __restrict__ out) {
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int clip = blockIdx.y;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)tiles * p.T;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tile = (int)(i / p.T), t = (int)(i - (long long)tile * p.T);
+    const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
+    int x0 = tx * HM_TW, x1 = min(p.w[0], x0 + HM_TW) - 1, y0 = ty * HM_TH, y1 = min(p.h[0], y0 + HM_TH) - 1;
+    for (int l = 0; l < p.n_up; ++l) {
+      x0 = (x0 >> 1) - 1; x1 = (x1 >> 1) + 1;
+      y0 = (y0 >> 1) - 1; y1 = (y1 >> 1) + 1;
+    }
+    x0 = max(x0, 0); y0 = max(y0, 0);
+    x1 = min(x1, p.top_w - 1); y1 = min(y1, p.top_h - 1);
+    const double* a = p.a_top + ((long long)clip * p.T + t) * p.top_w * p.top_h;
+    double lo = INFINITY, hi = -INFINITY;
+    for (int y = y0; y <= y1; ++y)
+      for (int x = x0; x <= x1; ++x) {
+        const double v = a[y * p.top_w + x];
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+      }
+    out[((long long)clip * tiles + tile) * p.T + t] = make_double2(lo, hi);
+  }
+}
+
+// Seeds the clip's min/max keys before pass 1: per (clip, sampled frame) the positions of the level-2 maximum and minimum
+// are located and the 4x4 level-0 blocks above them are evaluated exactly as pass 1 would.  Any value so obtained is a
+// value pass 1 would also have produced, so the keys are valid lower bounds of the extremes; pass 1 then skips every
+// (tile, frame) that cannot beat them.  One block per (sampled frame, clip).
+__global__ void __launch_bounds__(256) minmax_seed_kernel(const TileParams p, int frame_stride) {
+  const int clip = blockIdx.y, t = blockIdx.x * frame_stride, tid = threadIdx.x;
+  if (t >= p.T) return;
+  const int n2 = p.w[2] * p.h[2];
+  const double* l2 = p.a2 + ((long long)clip * p.T + t) * n2;
+  double vmx = -INFINITY, vmn = INFINITY;
+  int imx = 0, imn = 0;
+  for (int i = tid; i < n2; i += 256) {
+    const double v = l2[i];
+    if (v > vmx) { vmx = v; imx = i; }
+    if (v < vmn) { vmn = v; imn = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, vmx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, imx, o);
+    if (ov > vmx) { vmx = ov; imx = oi; }
+    const double uv = __shfl_xor_sync(0xffffffffu, vmn, o);
+    const int ui = __shfl_xor_sync(0xffffffffu, imn, o);
+    if (uv < vmn) { vmn = uv; imn = ui; }
+  }
+  __shared__ double s_mx[8], s_mn[8];
+  __shared__ int s_imx[8], s_imn[8];
+  if ((tid & 31) == 0) { s_mx[tid >> 5] = vmx; s_imx[tid >> 5] = imx; s_mn[tid >> 5] = vmn; s_imn[tid >> 5] = imn; }
+  __syncthreads();
+  if (tid < 2) {   // thread 0: the block above the maximum, thread 1: above the minimum
+    double best = tid == 0 ? -INFINITY : INFINITY;
+    int idx = 0;
+    for (int w = 0; w < 8; ++w) {
+      const double v = tid == 0 ? s_mx[w] : s_mn[w];
+      if (tid == 0 ? v > best : v < best) { best = v; idx = tid == 0 ? s_imx[w] : s_imn[w]; }
+    }
+    const int i2x = idx % p.w[2], i2y = idx / p.w[2];
+    const int X0 = 4 * i2x, Y0 = 4 * i2y;
+    const AxisGeom gx = axis_geom(i2x, p.w[1], p.w[2]), gy = axis_geom(i2y, p.h[1], p.h[2]);
+    double v[4][4], o[4][4];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) v[r][c] = l2[gy.v[r] * p.w[2] + gx.v[c]];
+    block4x4<true>(v, gx, gy, o);
+    double vmin = INFINITY, vmax = -INFINITY;
+    for (int ky = 0; ky < 4; ++ky)
+      for (int kx = 0; kx < 4; ++kx)
+        if (X0 + kx < p.w[0] && Y0 + ky < p.h[0]) { vmin = fmin(vmin, o[ky][kx]); vmax = fmax(vmax, o[ky][kx]); }
+    if (vmin <= vmax) {
+      atomicMin(&p.minmax_keys[clip * 4 + 0], f64_key(vmin * p.scale));
+      atomicMax(&p.minmax_keys[clip * 4 + 1], f64_key(vmax * p.scale));
+    }
+  }
+}
+
 template <int PASS>
 __global__ void __launch_bounds__(128) upsample_pass_kernel(const TileParams p) {
   __shared__ double red_a[4], red_b[4];
@@ -386,8 +498,9 @@ __global__ void __launch_bounds__(128) upsample_pass_kernel(const TileParams p) 
   const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
   // tiles that touch the right / bottom image border (or an unaligned row) take the guarded variant
   const bool edge = (tx + 1) * HM_TW >= p.w[0] || (ty + 1) * HM_TH >= p.h[0] || (p.w[0] & 1);
-  if (edge) upsample_pass_body<PASS, true>(p, red_a, red_b, stage);
-  else upsample_pass_body<PASS, false>(p, red_a, red_b, stage);
+  extern __shared__ int frame_list_smem[];   // pass 1: T ints
+  if (edge) upsample_pass_body<PASS, true>(p, red_a, red_b, stage, frame_list_smem);
+  else upsample_pass_body<PASS, false>(p, red_a, red_b, stage, frame_list_smem);
 }
 
 __global__ void minmax_init_kernel(unsigned long long* keys, int n_clips) {
@@ -496,8 +609,10 @@ extern "C" int32_t rm_heatmap_workspace_bytes(rm_handle* h, int32_t W, int32_t H
   size_t a = 0;                                                // A_s .. A_2
   for (int l = 2; l <= s && l < g.n_levels; ++l) a += (((size_t)n_clips * T * g.w[l] * g.h[l] * 8) + 255) & ~(size_t)255;
   size_t avg = (size_t)n_clips * W * H * 8;                    // time average
-  size_t keys = (size_t)n_clips * 4 * 8;
-  *out = a + avg + keys + 4 * 256;
+  size_t keys = ((size_t)n_clips * 4 * 8 + 255) & ~(size_t)255;
+  const size_t tiles = (size_t)((W + HM_TW - 1) / HM_TW) * ((H + HM_TH - 1) / HM_TH);
+  size_t bounds = (size_t)n_clips * tiles * T * sizeof(double2);      // pass-1 pruning bounds
+  *out = a + avg + keys + bounds + 5 * 256;
   return RM_OK;
 }
 
@@ -526,6 +641,8 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   double* avg = reinterpret_cast<double*>(base);
   base += ((size_t)n_clips * W * H * 8 + 255) & ~(size_t)255;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
+  base += ((size_t)n_clips * 4 * 8 + 255) & ~(size_t)255;
+  double2* bounds = reinterpret_cast<double2*>(base);
   const long long n_frames = (long long)n_clips * T;
 
   HeadParams hp;
@@ -579,9 +696,25 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   tp.threshold = h->p.temporal_threshold;
   tp.avg_out = avg;
   dim3 grid(tp.tiles_x * tp.tiles_y, n_clips);
+  tp.a_top = a_lvl[s];
+  tp.top_w = g.w[s];
+  tp.top_h = g.h[s];
+  tp.n_up = s;
+  if (!h->no_minmax_seed && (size_t)T * 4 <= 32768) {
+    const long long items = (long long)grid.x * T;
+    RM_PROF(h, st, "tile_bounds_kernel");
+    tile_bounds_kernel<<<dim3((unsigned)((items + 255) / 256), n_clips), 256, 0, st>>>(tp, bounds);
+    RM_LAUNCH_CHECK(h);
+    tp.bounds = bounds;
+    const int stride = T >= 8 ? 2 : 1;
+    RM_PROF(h, st, "minmax_seed_kernel");
+    minmax_seed_kernel<<<dim3((T + stride - 1) / stride, n_clips), 256, 0, st>>>(tp, stride);
+    RM_LAUNCH_CHECK(h);
+  }
   RM_PROF(h, st, "upsample_pass_kernel<1>");
-  upsample_pass_kernel<1><<<grid, 128, 0, st>>>(tp);
+  upsample_pass_kernel<1><<<grid, 128, tp.bounds ? (size_t)T * 4 : 0, st>>>(tp);
   RM_LAUNCH_CHECK(h);
+  tp.bounds = nullptr;
   RM_PROF(h, st, "upsample_pass_kernel<2>");
   upsample_pass_kernel<2><<<grid, 128, 0, st>>>(tp);
   RM_LAUNCH_CHECK(h);

@@ -164,3 +164,24 @@ def test_device_synth_is_bit_identical(eng):
     got = eng.synth_clips(specs, dq8).cpu().numpy()
     for i, s in enumerate(specs):
         assert np.array_equal(got[i], synth.make_clip(s))
+
+
+def test_heatmap_minmax_pruning_is_exact(eng):
+    """Pass 1 of the heat map skips (tile, frame) pairs whose level-2 patch cannot beat the extremes the seed kernel found:
+    min/max keys, heat map and ROI are bit-identical to the unpruned evaluation (option no_minmax_seed)."""
+    from respmon_b200 import synth
+    specs = [synth.clip_spec(s, 320, 240, 160) for s in (90, 91, 92)]
+    dq8 = np.stack([synth.displacement_q8(s) for s in specs])
+    clips = eng.synth_clips(specs, dq8)
+    noisy = clips.clone()
+    noise = torch.randint(0, 6, noisy.shape, dtype=torch.uint8, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    noisy = (noisy.to(torch.int16) + noise.to(torch.int16)).clamp(0, 255).to(torch.uint8)   # sensor noise: no exact zeros
+    for c in (clips, noisy):
+        heat_a, mm_a = eng.calibrate_heatmaps(c, 10.0, 1, 128)
+        eng.set_option("no_minmax_seed", 1)
+        try:
+            heat_b, mm_b = eng.calibrate_heatmaps(c, 10.0, 1, 128)
+        finally:
+            eng.set_option("no_minmax_seed", 0)
+        assert torch.equal(mm_a, mm_b)
+        assert torch.equal(heat_a, heat_b)
