@@ -229,6 +229,9 @@ int32_t rm_set_option(rm_handle* h, const char* host_name, int64_t value);
 int32_t rm_profile_enable(rm_handle* h, int32_t on);
 int32_t rm_profile_reset(rm_handle* h);
 int32_t rm_profile_collect(rm_handle* h);
+/* timeline form, valid before rm_profile_collect: i < 0 returns the number of recorded launches; otherwise start / end of
+ * launch i in ms relative to the start of launch 0. */
+int32_t rm_profile_slot(rm_handle* h, int32_t i, const char** host_name, double* host_start_ms, double* host_end_ms);
 int32_t rm_profile_entry(rm_handle* h, int32_t i, const char** host_name, double* host_total_ms, int64_t* host_launches);
 
 #ifdef __cplusplus

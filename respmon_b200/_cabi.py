@@ -87,6 +87,7 @@ SIGNATURES = {
     "rm_profile_enable": (_i32, [_H, _i32]),
     "rm_profile_reset": (_i32, [_H]),
     "rm_profile_collect": (_i32, [_H]),
+    "rm_profile_slot": (_i32, [_H, _i32, C.POINTER(C.c_char_p), C.POINTER(_f64), C.POINTER(_f64)]),
     "rm_profile_entry": (_i32, [_H, _i32, C.POINTER(C.c_char_p), C.POINTER(_f64), C.POINTER(_i64)]),
 }
 

@@ -217,6 +217,25 @@ extern "C" int32_t rm_profile_reset(rm_handle* h) {
   return RM_OK;
 }
 // Waits for the recorded launches, folds their durations into the per-kernel table; returns the table size (or < 0).
+// Timeline view of the recorded launches (before rm_profile_collect folds them): start / end of launch i in ms relative
+// to the start of launch 0.  Returns the number of recorded launches when i < 0.
+extern "C" int32_t rm_profile_slot(rm_handle* h, int32_t i, const char** name, double* start_ms, double* end_ms) {
+  if (!h) return RM_ERR_INVALID;
+  if (i < 0) return h->prof_n;
+  if (i >= h->prof_n || !name || !start_ms || !end_ms) return RM_ERR_INVALID;
+  DeviceGuard dg(h->device);
+  rm_prof_slot* s0 = &h->prof_slots[0];
+  rm_prof_slot* s = &h->prof_slots[i];
+  float a = 0.f, b = 0.f;
+  RM_CUDA(h, cudaEventSynchronize(s->b));
+  RM_CUDA(h, cudaEventElapsedTime(&a, s0->a, s->a));
+  RM_CUDA(h, cudaEventElapsedTime(&b, s0->a, s->b));
+  *name = s->name;
+  *start_ms = a;
+  *end_ms = b;
+  return RM_OK;
+}
+
 extern "C" int32_t rm_profile_collect(rm_handle* h) {
   if (!h) return RM_ERR_INVALID;
   DeviceGuard dg(h->device);

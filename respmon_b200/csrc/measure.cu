@@ -1261,8 +1261,21 @@ extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_
   if ((rc = measure_gftt(h, &job, sa)) != RM_OK) return rc;
   RM_CUDA(h, cudaEventRecord(h->ev_fork, sa));
   RM_CUDA(h, cudaStreamWaitEvent(sb, h->ev_fork, 0));
+  // Chunk boundaries: a short first chunk (the first measure() windows -- the shortest data, the most degenerate and
+  // therefore longest Gaussian fits -- start as early as possible), the rest split evenly.
+  int bounds[RM_MAX_CHUNKS + 1];
+  bounds[0] = 0;
+  if (n_chunks == 1) bounds[1] = n_frames;
+  else {
+    int first = h->p.measure_init_len + 8;
+    if (first > n_frames / n_chunks) first = n_frames / n_chunks;
+    if (first < 1) first = 1;
+    bounds[1] = first;
+    for (int c = 2; c <= n_chunks; ++c)
+      bounds[c] = first + (int)((long long)(n_frames - first) * (c - 1) / (n_chunks - 1));
+  }
   for (int c = 0; c < n_chunks; ++c) {
-    const int f0 = (int)((long long)n_frames * c / n_chunks), f1 = (int)((long long)n_frames * (c + 1) / n_chunks);
+    const int f0 = bounds[c], f1 = bounds[c + 1];
     if ((rc = measure_lk(h, &job, f0, f1, n_chunks > 1, sa)) != RM_OK) return rc;
     RM_CUDA(h, cudaEventRecord(h->ev_chunk[c], sa));
     RM_CUDA(h, cudaStreamWaitEvent(sb, h->ev_chunk[c], 0));

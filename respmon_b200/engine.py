@@ -100,6 +100,17 @@ class Engine:
         if on:
             self.lib.rm_profile_reset(self._h)
 
+    def profile_timeline(self) -> list:
+        """[(kernel, start ms, end ms)] of every launch since profile(True), relative to the first one; call it
+        before profile_report() (which folds the launches into totals)."""
+        n = self.lib.rm_profile_slot(self._h, -1, None, None, None)
+        out = []
+        name, a, b = C.c_char_p(), C.c_double(), C.c_double()
+        for i in range(max(n, 0)):
+            if self.lib.rm_profile_slot(self._h, i, C.byref(name), C.byref(a), C.byref(b)) == 0:
+                out.append((name.value.decode(), a.value, b.value))
+        return out
+
     def profile_report(self) -> dict:
         """{kernel name: (total ms, launches)} since profile(True)."""
         n = self.lib.rm_profile_collect(self._h)
