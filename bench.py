@@ -313,11 +313,19 @@ def run_gpu_arm(args) -> dict | None:
     barrier()
     mon.h2d_bytes = mon.d2h_bytes = 0
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        out = mon.run(host, FPS)
-        if world > 1:
-            from respmon_b200.batch import gather_records
-            out = gather_records(out)
+    prev = None
+    for _ in range(e2e_steps):           # submit / collect: the upload of step k+1 overlaps the measure tail of step k;
+        ticket = mon.submit(host, FPS)   # every step's records are read back to the host inside the timed region
+        if prev is not None:
+            out = mon.collect(prev)
+            if world > 1:
+                from respmon_b200.batch import gather_records
+                out = gather_records(out)
+        prev = ticket
+    out = mon.collect(prev)
+    if world > 1:
+        from respmon_b200.batch import gather_records
+        out = gather_records(out)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -393,7 +401,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU")
     ap.add_argument("--chunk", type=int, default=32, help="clips per H2D chunk of the end-to-end leg")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--defer-join", action="store_true", help="overlap consecutive steps (see run_gpu_arm)")
     args = ap.parse_args()

@@ -77,6 +77,7 @@ class BatchMonitor:
         self.crop_upload = bool(crop_upload)
         self._bufs = {}
         self._pinned = {}
+        self._ev = None
         self._copy_stream = torch.cuda.Stream(self.engine.device)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -86,6 +87,8 @@ class BatchMonitor:
         n = int(np.prod(shape))
         b = self._bufs.get(key)
         if b is None or b.numel() < n:
+            if b is not None:
+                torch.cuda.synchronize(self.engine.device)   # an earlier batch may still be using the buffer being replaced
             b = torch.empty(max(n, 1), dtype=torch.uint8, device=self.engine.device)
             self._bufs[key] = b
         return b[:n].view(shape)
@@ -94,12 +97,31 @@ class BatchMonitor:
         n = int(np.prod(shape))
         b = self._pinned.get(key)
         if b is None or b.numel() < n or b.dtype != dtype:
+            if b is not None:
+                torch.cuda.synchronize(self.engine.device)   # a copy out of the buffer being replaced may be in flight
             b = torch.empty(max(n, 1), dtype=dtype).pin_memory()
             self._pinned[key] = b
         return b[:n].view(shape)
 
     def run(self, clips, fps: float, cal_first: int = 1, cal_len: int = 128) -> np.ndarray:
         """clips: (n,T,H,W) uint8 numpy array or (preferably pinned) CPU tensor -> RESULT_DTYPE array of n records.
+        submit() followed by collect(); use the two directly to overlap consecutive batches."""
+        return self.collect(self.submit(clips, fps, cal_first, cal_len))
+
+    def _slot_events(self):
+        if self._ev is None:
+            n_ms = len(self._measure_streams)
+            mk = lambda k: [torch.cuda.Event() for _ in range(k)]          # noqa: E731
+            self._ev = dict(cal_ready=mk(2), cal_freed=mk(2), roi_done=mk(2), crop_ready=mk(n_ms), stage_freed=mk(n_ms),
+                            crop_dev_freed=mk(n_ms))
+            self._used = dict(cal=[False, False], ms=[False] * n_ms)
+            self._seq = 0                                                  # chunks submitted so far (slot rotation)
+        return self._ev
+
+    def submit(self, clips, fps: float, cal_first: int = 1, cal_len: int = 128):
+        """Enqueue a batch and return a ticket for collect().  Returns as soon as the last chunk's measure stage has been
+        enqueued, so the upload of the next submit() overlaps the tail of this one (buffers and streams are handed from
+        batch to batch through events; the results of every batch are complete when its collect() returns).
 
         Per chunk: calibration window H2D (copy stream) -> locate() (calibrate stream) -> ROI to the host -> ROI crops
         of the measure frames H2D (second copy stream) -> LK measure + BPM on one of `measure_streams` streams.  The
@@ -112,7 +134,7 @@ class BatchMonitor:
         n_meas = T - measure_first
         assert cal_first >= 0 and n_meas >= 1
         if not self.crop_upload:
-            return self._run_full_frames(host, fps, cal_first, cal_len)
+            return dict(done=self._run_full_frames(host, fps, cal_first, cal_len))
         eng = self.engine
         dev = eng.device
         host_np = host.numpy()
@@ -120,53 +142,50 @@ class BatchMonitor:
         copy, copy2 = self._copy_stream, self._crop_stream
         n_ms = len(self._measure_streams)
         chunks = self._chunk_schedule(n)
-        ev = lambda k: [torch.cuda.Event() for _ in range(k)]          # noqa: E731
-        cal_ready, cal_freed, roi_done = ev(2), ev(2), ev(2)
-        crop_ready, stage_freed, crop_dev_freed = ev(n_ms), ev(n_ms), ev(n_ms)
+        E = self._slot_events()
+        used = self._used
         records = torch.empty((n, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-        start = torch.cuda.Event()
-        start.record(main)
-        for s_ in [copy, copy2] + self._measure_streams:
-            s_.wait_event(start)                                       # everything queued before run() is done
-        keep = []                                                      # tensors shared across streams stay alive
+        keep = [host]                                                  # tensors shared across streams stay alive
+        seq0 = self._seq
 
         def upload_cal(i):
             lo, hi = chunks[i]
-            slot = i & 1
+            slot = (seq0 + i) & 1
             dst = self._buffer(("cal", slot), (hi - lo, cal_len, H, W))
             with torch.cuda.stream(copy):
-                if i >= 2:
-                    copy.wait_event(cal_freed[slot])              # locate() of chunk i-2 has read this buffer
+                if used["cal"][slot]:
+                    copy.wait_event(E["cal_freed"][slot])         # locate() of the chunk that last used this buffer is done
                 for c in range(lo, hi):                           # one contiguous block per clip
                     dst[c - lo].copy_(host[c, cal_first:cal_first + cal_len], non_blocking=True)
-                cal_ready[slot].record(copy)
+                E["cal_ready"][slot].record(copy)
+            used["cal"][slot] = True
             self.h2d_bytes += dst.numel()
             return dst
 
         pending = upload_cal(0) if chunks else None
         for i, (lo, hi) in enumerate(chunks):
-            slot, ms = i & 1, i % n_ms
+            slot, ms = (seq0 + i) & 1, (seq0 + i) % n_ms
             cal = pending
             if i + 1 < len(chunks):
                 pending = upload_cal(i + 1)                       # overlaps everything below
             m = hi - lo
-            main.wait_event(cal_ready[slot])
+            main.wait_event(E["cal_ready"][slot])
             roi, status, _ = eng.locate(cal, fps, 0, cal_len)
-            cal_freed[slot].record(main)
+            E["cal_freed"][slot].record(main)
             roi_host = self._pinned_buffer(("roi", slot), (m, 4), torch.int32)
             st_host = self._pinned_buffer(("st", slot), (m,), torch.int32)
             roi_host.copy_(roi, non_blocking=True)
             st_host.copy_(status, non_blocking=True)
-            roi_done[slot].record(main)
+            E["roi_done"][slot].record(main)
             self.d2h_bytes += roi_host.numel() * 4 + st_host.numel() * 4
-            roi_done[slot].synchronize()                          # the ROI decides which bytes go up next
+            E["roi_done"][slot].synchronize()                     # the ROI decides which bytes go up next
             r = roi_host.numpy()
             ok = st_host.numpy() == 0
             mw = int(max(1, r[ok, 2].max())) if ok.any() else 1
             mh = int(max(1, r[ok, 3].max())) if ok.any() else 1
             stage = self._pinned_buffer(("crop", ms), (m, n_meas, mh, mw))
-            if i >= n_ms:
-                stage_freed[ms].synchronize()                     # the H2D of chunk i-n_ms has left this staging area
+            if used["ms"][ms]:
+                E["stage_freed"][ms].synchronize()                # the H2D that last used this staging area has left it
             sv = stage.numpy()
             for c in range(m):
                 if ok[c]:
@@ -174,16 +193,17 @@ class BatchMonitor:
                     sv[c, :, :h, :w] = host_np[lo + c, measure_first:, y:y + h, x:x + w]   # base.py:471
             crops = self._buffer(("cropdev", ms), (m, n_meas, mh, mw))
             with torch.cuda.stream(copy2):
-                if i >= n_ms:
-                    copy2.wait_event(crop_dev_freed[ms])          # measure of chunk i-n_ms has read this device buffer
+                if used["ms"][ms]:
+                    copy2.wait_event(E["crop_dev_freed"][ms])     # the measure stage that last read this buffer is done
                 crops.copy_(stage, non_blocking=True)
-                crop_ready[ms].record(copy2)
-                stage_freed[ms].record(copy2)
+                E["crop_ready"][ms].record(copy2)
+                E["stage_freed"][ms].record(copy2)
+            used["ms"][ms] = True
             self.h2d_bytes += crops.numel()
             mstream, meng = self._measure_streams[ms], self._measure_engines[ms]
             with torch.cuda.stream(mstream):
-                mstream.wait_event(roi_done[slot])
-                mstream.wait_event(crop_ready[ms])
+                mstream.wait_event(E["roi_done"][slot])
+                mstream.wait_event(E["crop_ready"][ms])
                 roi0 = roi.clone()
                 roi0[:, :2] = 0                                   # the crop's own origin
                 st = status.clone()
@@ -194,15 +214,26 @@ class BatchMonitor:
                     data = meng.measure_average(crops, roi0, 0, n_meas)
                     sig = meng.signal_bpm(data, fps, status=st)
                 meng.pack_results(sig["bpm"], roi, st, sig["npeaks"], out=records[lo:hi])
-                crop_dev_freed[ms].record(mstream)
+                E["crop_dev_freed"][ms].record(mstream)
             keep.append((roi, status, roi0, st, data, sig))
-        for k, mstream in enumerate(self._measure_streams):
+        self._seq = seq0 + len(chunks)
+        done = []
+        for mstream in self._measure_streams:
             e = torch.cuda.Event()
             e.record(mstream)
+            done.append(e)
+        return dict(records=records, done_events=done, keep=keep)
+
+    def collect(self, ticket) -> np.ndarray:
+        """Wait for a submitted batch and read its records back (the device->host read of the step's result)."""
+        if "done" in ticket:
+            return ticket["done"]
+        main = torch.cuda.current_stream(self.engine.device)
+        for e in ticket["done_events"]:
             main.wait_event(e)
-        out = records.cpu().numpy().view(RESULT_DTYPE).reshape(-1)   # the device->host read of the step's result
-        self.d2h_bytes += records.numel()
-        del keep
+        out = ticket["records"].cpu().numpy().view(RESULT_DTYPE).reshape(-1)
+        self.d2h_bytes += ticket["records"].numel()
+        ticket["keep"] = None
         return out
 
     def _chunk_schedule(self, n):

@@ -75,3 +75,24 @@ def test_mixed_resolution_batch():
     assert (got["x"][1], got["y"][1], got["w"][1], got["h"][1]) == tuple(want["roi"])
     if want["bpm"] is not None:
         assert abs(got["bpm"][1] - want["bpm"]) <= 0.5
+
+
+def test_submit_collect_overlapped_batches_equal_sequential_runs():
+    """Two batches in flight (the second one's upload overlaps the first one's measure tail), different sizes and
+    resolutions so every buffer is handed over or replaced: records equal those of plain run() calls."""
+    from respmon_b200.batch import BatchMonitor
+    a = _clips(range(50, 55), 320, 240)
+    b = _clips(range(55, 58), 320, 240)
+    c = _clips(range(58, 60), 250, 187)
+    ref = BatchMonitor(0, chunk_clips=2)
+    want = [ref.run(x, 10.0) for x in (a, b, c, a)]
+    mon = BatchMonitor(0, chunk_clips=2)
+    tickets = []
+    got = []
+    for x in (a, b, c, a):
+        tickets.append(mon.submit(torch.from_numpy(x).pin_memory(), 10.0))
+        if len(tickets) >= 2:
+            got.append(mon.collect(tickets[-2]))
+    got.append(mon.collect(tickets[-1]))
+    for g, w in zip(got, want):
+        _same(g, w)
