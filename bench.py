@@ -10,11 +10,15 @@ runs the reference's whole per-clip path on it with the reference's frame routin
 locate() (pyramid + temporal band-pass + collapse + ROI), frames 130..255 -> extract_motion('flow') + measure().
 A step is one pass over the batch; frames counted = every input frame of every clip (n_clips * 256).
 
-  value     clips resident in HBM before the timed region; CUDA events on the launching stream, max over ranks.
-  e2e       the same through BatchMonitor.run() from pinned HOST memory: chunked H2D copies and the D2H read of the
-            result records are inside the timed region.
+  value     clips resident in HBM before the timed region; CUDA events on the launching stream, max over ranks.  Every
+            step is joined before the next starts (each kernel runs alone; --defer-join overlaps consecutive steps).
+  e2e       the same through BatchMonitor.submit()/collect() from pinned HOST memory: the H2D copies (calibration window
+            + ROI crops of the measure frames), the ROI round trip and the D2H read of every step's result records are
+            inside the timed region; consecutive steps overlap (upload of step k+1 under the measure tail of step k).
   roofline  the HBM-bound streaming kernel of the path (pyramid front kernel), timed per launch by CUDA events that the
-            library records on its stream (rm_profile_*), against MEASURED_PEAKS.json.
+            library records on its stream (rm_profile_*), against MEASURED_PEAKS.json; traffic from the committed ncu
+            capture of the same launch shape (profiles/roofline_traffic.json).
+  extras    calibration-only (BASELINE config 2) and measure-only (config 3's loop) rates, outside the timed region.
   cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/cpu_path.py, cv2/scipy/numpy -- the
             reference tree itself does not exist on the GPU box) on whole clips, one worker process per host core.
 """

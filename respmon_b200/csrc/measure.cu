@@ -534,7 +534,6 @@ struct LkSmemLayout {
   int pad;
   int pyr_bytes;                                  // one padded pyramid
   int raw_pitch, raw_bytes;                       // crop as copied from the frame (columns aligned down/up to 4)
-  int warp_scratch;                               // bytes of patch + derivative scratch per warp
   int total;
 };
 __host__ __device__ inline LkSmemLayout lk_smem_layout(int rw, int rh, int win, int max_level, int warps) {
@@ -557,9 +556,8 @@ __host__ __device__ inline LkSmemLayout lk_smem_layout(int rw, int rh, int win, 
   L.pyr_bytes = off;
   L.raw_pitch = (rw + 3 + 3) & ~3;
   L.raw_bytes = (L.raw_pitch * rh + 15) & ~15;
-  const int pw = win + 3, dwid = win + 1;
-  L.warp_scratch = (2 * ((pw * pw + 1) & ~1) + 4 * dwid * dwid + 15) & ~15;
-  L.total = 2 * L.pyr_bytes + 2 * L.raw_bytes + warps * L.warp_scratch;
+  (void)warps;   // the window setup runs in registers: no per-warp scratch any more
+  L.total = 2 * L.pyr_bytes + 2 * L.raw_bytes;
   return L;
 }
 
@@ -579,14 +577,11 @@ struct LkSLevel {   // one padded level in shared memory: `org` is the offset of
 // One warp tracks one point through the levels (cv::LKTrackerInvoker), images in shared memory.
 // wq[k] = offset (wy * pitch-independent pair) of the lane's k-th window pixel: wy = wq >> 8, wx = wq & 255.
 __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, const LkSLevel* next, int nlev, float px,
-                               float py, float* out_x, float* out_y, int patch_off, int deriv_off, const int wq[8],
+                               float py, float* out_x, float* out_y, const int wq[8],
                                int lane) {
   const int win = p.win;
-  const int pw = win + 3, dwid = win + 1;
   const float half = (float)(win - 1) * 0.5f;
   const float FLT_SCALE = 1.0f / (float)(1 << 20);
-  short* patch = reinterpret_cast<short*>(lks_smem + patch_off);
-  short2* deriv = reinterpret_cast<short2*>(lks_smem + deriv_off);
   float nx = 0.f, ny = 0.f;
   int status = 1;
   for (int level = nlev - 1; level >= 0; --level) {
@@ -736,9 +731,6 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
   const LkSmemLayout L = lk_smem_layout(rw, rh, p.win, p.max_level, LKS_WARPS);
   if (L.total > max_total) return;   // cannot happen: the host sized shared memory for the largest ROI
   const int raw_base = 2 * L.pyr_bytes;
-  const int patch_off = raw_base + 2 * L.raw_bytes + warp * L.warp_scratch;
-  const int pw = p.win + 3;
-  const int deriv_off = patch_off + 2 * ((pw * pw + 1) & ~1);
 
   for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
   if (tid == 0) s_n = n_start;
@@ -909,7 +901,7 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
     const int n = s_n;
     for (int i = warp; i < n; i += LKS_WARPS) {
       float ox, oy;
-      const int st = lks_track_point(p, prev, next, L.nlev, s_pts[i][0], s_pts[i][1], &ox, &oy, patch_off, deriv_off, wq,
+      const int st = lks_track_point(p, prev, next, L.nlev, s_pts[i][0], s_pts[i][1], &ox, &oy, wq,
                                      lane);
       if (lane == 0) { s_new[i][0] = ox; s_new[i][1] = oy; s_st[i] = st; }
     }

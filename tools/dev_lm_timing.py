@@ -1,3 +1,4 @@
+"""Developer tool: per-section cycle counts of the LM fit (needs a build with RM_NVCC_EXTRA=-DLM_TIMING)."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
