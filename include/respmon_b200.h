@@ -203,6 +203,25 @@ int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_t n_clips, 
                           double fps, double* data_out, float* motion_out, int32_t* npts_out, int32_t* status_io,
                           double* bpm_out, double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, void* workspace,
                           size_t workspace_bytes, void* stream);
+/* Live streams (the reference's actual use, base.py:464-495 frame by frame): a cohort of n_clips cameras whose measure
+ * states started on the same frame, fed a few frames at a time.  `frames` is a ring of ring_len ROI crops per camera
+ * (n_clips, ring_len, H, W), the crop of absolute measure frame f in slot f % ring_len (rm_crop_to_ring); each call tracks
+ * the new frames [f_begin, f_end) from the tracker state the handle carries over from the previous call (f_begin = 0:
+ * corners are detected on frame 0), writes their motion / data / BPM at their absolute positions in the (n_clips, cap)
+ * arrays and leaves filtered / peaks / npeaks of the window ending at f_end - 1.  Identical to rm_measure_signal on the
+ * whole clip for any block sizes.  One handle per cohort; f_end - f_begin < ring_len; workspace as
+ * rm_measure_workspace_bytes(max_roi_w, max_roi_h, n_clips, ring_len). */
+int32_t rm_measure_signal_stream(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t ring_len, int32_t W,
+                                 int32_t H, const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t cap,
+                                 int32_t f_begin, int32_t f_end, double fps, double* data_out, float* motion_out,
+                                 int32_t* npts_out, int32_t* status_io, double* bpm_out, double* filtered_out,
+                                 int32_t* peaks_out, int32_t* npeaks_out, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+/* crop = frame[y:y+h, x:x+w] (base.py:471) of k new frames per camera into the crop ring: frames (n_clips, k, H, W), roi
+ * in frame coordinates, ring (n_clips, ring_len, ring_h, ring_w); block frame j goes to slot (f_first + j) % ring_len. */
+int32_t rm_crop_to_ring(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t k, int32_t W, int32_t H,
+                        const int32_t* roi, uint8_t* ring, int32_t ring_len, int32_t ring_w, int32_t ring_h,
+                        int32_t f_first, void* stream);
 /* assemble the 32-byte records: last finite BPM per clip, ROI, status, n_peaks. */
 int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, const int32_t* status, const int32_t* npeaks,
                         int32_t n_clips, int32_t n_frames, rm_result* out, void* stream);

@@ -191,7 +191,7 @@ static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / 
 // ---- internal entry points shared between translation units (not part of the C ABI) ---------------------------------
 int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps, double* bpm_out,
                          double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, const int32_t* status,
-                         int n_chunks, cudaStream_t st);
+                         int n_chunks, cudaStream_t st, int win_f0, int win_frames);
 int32_t rmi_join(rm_handle* h, cudaStream_t st);   // make st wait for whatever a deferred rm_measure_signal left running
 int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t st, cudaStream_t st_fit,
                          cudaEvent_t ev_filtered, cudaEvent_t ev_bulk);

@@ -70,7 +70,9 @@ struct MeasureParams {
   // point, so a clip with many corners is not the batch's critical path); every block writes old-new of its surviving
   // points per frame, indexed by the point's original index, and motion_reduce_kernel folds them in that order
   int bpc, ppb;
-  float2* delta;           // (n_clips, n_frames, LK_MAX_PTS), NaN = the point is gone
+  float2* delta;           // (n_clips, delta_frames, LK_MAX_PTS) for frames delta_f0 .., NaN = the point is gone
+  int delta_f0, delta_frames;
+  int ring;                // > 0: `frames` is a ring of that many frames per clip, frame f lives in slot f % ring
 };
 #define LK_MAX_BLOCKS 16
 #ifndef LK_PPB
@@ -765,7 +767,7 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
   };
 
   auto stage_raw = [&](int f, int slot) {
-    const uint8_t* src = clip_base + (long long)f * frame_elems + (long long)ry * p.W + x_al;
+    const uint8_t* src = clip_base + (long long)(p.ring > 0 ? f % p.ring : f) * frame_elems + (long long)ry * p.W + x_al;
     const int dst = raw_base + slot * L.raw_bytes;
     if (aligned) {
       const int chunks = raw_cols >> 2;
@@ -910,7 +912,7 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
     if (tid == 0) {
       // good_new = p1[st == 1], good_old = pts[st == 1] (base.py:377-382): survivors keep their relative order; their
       // old - new goes out under the point's original index for the ordered float32 mean (base.py:388)
-      float2* out = p.delta + ((long long)clip * p.n_frames + f) * LK_MAX_PTS;
+      float2* out = p.delta + ((long long)clip * p.delta_frames + (f - p.delta_f0)) * LK_MAX_PTS;
       int m = 0;
       for (int i = 0; i < n; ++i) {
         if (s_st[i]) {
@@ -974,7 +976,7 @@ __global__ void motion_reduce_kernel(const MeasureParams p) {
     if (!bad) {
       if (f == 0) { mx = 0.f; my = 0.f; }
       else {
-        const float2* d = p.delta + ((long long)clip * p.n_frames + f) * LK_MAX_PTS;
+        const float2* d = p.delta + ((long long)clip * p.delta_frames + (f - p.delta_f0)) * LK_MAX_PTS;
         int m = 0;
         float sx = 0.f, sy = 0.f;
         for (int i = 0; i < n0; ++i) {
@@ -1078,15 +1080,18 @@ static int32_t measure_setup(rm_handle* h, const uint8_t* frames, int32_t n_clip
                              const int32_t* roi, int32_t max_roi_w, int32_t max_roi_h, int32_t first_frame,
                              int32_t n_frames, double* data_out, float* motion_out, int32_t* npts_out,
                              int32_t* status_io, float* pts_dbg, void* workspace, size_t workspace_bytes,
-                             MeasureJob* job) {
+                             MeasureJob* job, int ring = 0, int layout_frames = -1) {
+  // ring > 0 (streaming): `frames` holds the last `ring` = T frames of every clip, n_frames is the capacity of the
+  // per-frame output arrays and layout_frames the number of frames one call processes (sizes the workspace)
+  if (layout_frames < 0) layout_frames = n_frames;
   RM_CHECK_ARG(h, h && frames && roi && data_out && motion_out && npts_out && status_io, "null pointer");
   RM_CHECK_ARG(h, n_clips >= 0 && T >= 1 && W >= 1 && H >= 1 && first_frame >= 0 && n_frames >= 1 &&
-                      first_frame + n_frames <= T, "frame range outside the clip");
+                      (ring > 0 || first_frame + n_frames <= T), "frame range outside the clip");
   RM_CHECK_ARG(h, max_roi_w >= 1 && max_roi_h >= 1 && max_roi_w <= W && max_roi_h <= H, "bad max ROI size");
   if (h->p.max_corners > LK_MAX_PTS || h->p.max_corners < 1 || h->p.lk_win < 3 || h->p.lk_win > 31 ||
       h->p.lk_win * h->p.lk_win > 256 || h->p.lk_max_level < 0 || h->p.lk_max_level >= LK_MAX_LEVELS)
     return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: needs max_corners <= 128, 3 <= lk_win <= 16, lk_max_level <= 3", __func__);
-  MeasureLayout L = measure_layout(h, max_roi_w, max_roi_h, n_clips, n_frames);
+  MeasureLayout L = measure_layout(h, max_roi_w, max_roi_h, n_clips, layout_frames);
   if (n_clips > 0 && (!workspace || workspace_bytes < L.total))
     return rm_fail(h, RM_ERR_WORKSPACE, "%s: workspace too small (%lld needed, %lld given)", __func__, (long long)L.total,
                    (long long)workspace_bytes);
@@ -1116,6 +1121,8 @@ static int32_t measure_setup(rm_handle* h, const uint8_t* frames, int32_t n_clip
   p.motion = motion_out; p.data = data_out; p.npts = npts_out; p.status = status_io; p.pts_dbg = pts_dbg;
   p.f0 = 0; p.f1 = n_frames;
   p.delta = reinterpret_cast<float2*>(ws + L.delta);
+  p.delta_f0 = 0; p.delta_frames = layout_frames;
+  p.ring = ring;
   if (pts_dbg) { p.bpc = 1; p.ppb = LK_MAX_PTS; }          // the diagnostic dump wants one compacted list per clip
   else {
     p.ppb = LK_PPB;                                        // at most one corner per warp, half of the warps per block
@@ -1155,7 +1162,8 @@ static int32_t measure_lk(rm_handle* h, MeasureJob* job, int f0, int f1, bool ca
     p.st_pts = carry_state ? h->d_lk_pts : nullptr;
     p.st_idx = carry_state ? h->d_lk_idx : nullptr;
     p.st_n = carry_state ? h->d_lk_n : nullptr;
-    if (f0 == 0) RM_CUDA(h, cudaMemsetAsync(p.delta, 0xFF, (size_t)p.n_clips * p.n_frames * LK_MAX_PTS * sizeof(float2), st));
+    if (f0 == p.delta_f0)
+      RM_CUDA(h, cudaMemsetAsync(p.delta, 0xFF, (size_t)p.n_clips * p.delta_frames * LK_MAX_PTS * sizeof(float2), st));
     // production path: crops and their pyramids live in shared memory
     RM_CUDA(h, cudaFuncSetAttribute(lk_track_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, job->SL.total));
     RM_PROF(h, st, "lk_track_smem_kernel");
@@ -1248,7 +1256,7 @@ extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_
   }
   // everything that allocates happens before the first launch
   if ((rc = rmi_signal_setup(h, data_out, n_clips, n_frames, fps, bpm_out, filtered_out, peaks_out, npeaks_out, status_io,
-                             n_chunks, sa)) != RM_OK)
+                             n_chunks, sa, 0, 0)) != RM_OK)
     return rc;
   if ((rc = measure_gftt(h, &job, sa)) != RM_OK) return rc;
   RM_CUDA(h, cudaEventRecord(h->ev_fork, sa));
@@ -1280,6 +1288,80 @@ extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_
   // deferred: the caller's stream waits for the first fit pass only; the long fits, the BPM fold and rm_pack_results
   // finish behind it (rm_join)
   for (int c = 0; c < n_chunks; ++c) RM_CUDA(h, cudaStreamWaitEvent(sa, h->ev_bulk[c], 0));
+  return RM_OK;
+}
+
+// The measure branch for LIVE streams (base.py:464-495 frame by frame): a cohort of n_clips cameras whose measure states
+// started on the same frame.  `frames` is a ring of ring_len ROI crops per camera (crop of absolute measure frame f in
+// slot f % ring_len, written by rm_crop_to_ring); every call tracks the new frames [f_begin, f_end) from the tracker
+// state the handle carries from the previous call (f_begin = 0: corners are detected on frame 0), appends their motion,
+// data and BPM at their absolute positions in the (n_clips, cap) arrays and leaves filtered / peaks of the window that
+// ends at f_end - 1.  Results equal those of rm_measure_signal on the whole clip, whatever the block sizes (tested).
+// One handle per cohort; ring_len > f_end - f_begin; the shared-memory tracker only (ROI up to about 100 x 100).
+extern "C" int32_t rm_measure_signal_stream(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t ring_len,
+                                            int32_t W, int32_t H, const int32_t* roi, int32_t max_roi_w,
+                                            int32_t max_roi_h, int32_t cap, int32_t f_begin, int32_t f_end, double fps,
+                                            double* data_out, float* motion_out, int32_t* npts_out, int32_t* status_io,
+                                            double* bpm_out, double* filtered_out, int32_t* peaks_out,
+                                            int32_t* npeaks_out, void* workspace, size_t workspace_bytes, void* stream) {
+  RM_CHECK_ARG(h, h && bpm_out && fps > 0, "null pointer or bad fps");
+  RM_CHECK_ARG(h, f_begin >= 0 && f_end > f_begin && f_end <= cap && f_end - f_begin < ring_len, "bad frame block");
+  MeasureJob job;
+  const int k = f_end - f_begin;
+  int32_t rc = measure_setup(h, frames, n_clips, ring_len, W, H, roi, max_roi_w, max_roi_h, 0, cap, data_out, motion_out,
+                             npts_out, status_io, nullptr, workspace, workspace_bytes, &job, ring_len, k);
+  if (rc != RM_OK || n_clips == 0) return rc;
+  if (!job.smem_path) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: ROI too large for the shared-memory tracker", __func__);
+  DeviceGuard dg(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = rmi_join(h, st)) != RM_OK) return rc;
+  if (h->lk_state_cap < n_clips) {
+    if (f_begin != 0) return rm_fail(h, RM_ERR_INVALID, "%s: no tracker state for this cohort (start with f_begin = 0)", __func__);
+    if (h->d_lk_pts) cudaFree(h->d_lk_pts);
+    if (h->d_lk_idx) cudaFree(h->d_lk_idx);
+    if (h->d_lk_n) cudaFree(h->d_lk_n);
+    h->d_lk_pts = nullptr; h->d_lk_idx = nullptr; h->d_lk_n = nullptr; h->lk_state_cap = 0;
+    RM_CUDA(h, cudaMalloc((void**)&h->d_lk_pts, (size_t)n_clips * LK_MAX_PTS * 2 * sizeof(float)));
+    RM_CUDA(h, cudaMalloc((void**)&h->d_lk_idx, (size_t)n_clips * LK_MAX_PTS * sizeof(int)));
+    RM_CUDA(h, cudaMalloc((void**)&h->d_lk_n, (size_t)n_clips * LK_MAX_BLOCKS * sizeof(int)));
+    h->lk_state_cap = n_clips;
+  }
+  if ((rc = rmi_signal_setup(h, data_out, n_clips, cap, fps, bpm_out, filtered_out, peaks_out, npeaks_out, status_io, 1, st,
+                             f_begin, k)) != RM_OK)
+    return rc;
+  job.p.delta_f0 = f_begin;
+  job.p.delta_frames = k;
+  if (f_begin == 0 && (rc = measure_gftt(h, &job, st)) != RM_OK) return rc;
+  if ((rc = measure_lk(h, &job, f_begin, f_end, true, st)) != RM_OK) return rc;
+  if ((rc = measure_pca(h, &job, f_begin, f_end, st)) != RM_OK) return rc;
+  return rmi_signal_range(h, f_begin, f_end, 0, st, st, nullptr, nullptr);
+}
+
+// Copies the ROI crop of k new frames of every camera into its crop ring: frames (n_clips, k, H, W), roi (n_clips, 4) in
+// frame coordinates, ring (n_clips, ring_len, ring_h, ring_w); frame j of the block goes to slot (f_first + j) % ring_len.
+__global__ void crop_to_ring_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ roi,
+                                    uint8_t* __restrict__ ring, int k, int W, int H, int ring_len, int ring_w, int ring_h,
+                                    int f_first) {
+  const int clip = blockIdx.y, j = blockIdx.x;
+  const int x = roi[clip * 4], y = roi[clip * 4 + 1], w = roi[clip * 4 + 2], hh = roi[clip * 4 + 3];
+  if (w < 1 || hh < 1 || x < 0 || y < 0 || x + w > W || y + hh > H || w > ring_w || hh > ring_h) return;
+  const uint8_t* src = frames + ((long long)clip * k + j) * W * H + (long long)y * W + x;
+  uint8_t* dst = ring + ((long long)clip * ring_len + (f_first + j) % ring_len) * ring_w * ring_h;
+  for (int i = threadIdx.x; i < w * hh; i += blockDim.x) {
+    const int r = i / w, c = i - r * w;
+    dst[r * ring_w + c] = src[(long long)r * W + c];
+  }
+}
+extern "C" int32_t rm_crop_to_ring(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t k, int32_t W, int32_t H,
+                                   const int32_t* roi, uint8_t* ring, int32_t ring_len, int32_t ring_w, int32_t ring_h,
+                                   int32_t f_first, void* stream) {
+  RM_CHECK_ARG(h, h && frames && roi && ring && n_clips >= 0 && k >= 1 && k <= ring_len && f_first >= 0, "bad argument");
+  if (n_clips == 0) return RM_OK;
+  DeviceGuard dg(h->device);
+  RM_PROF(h, (cudaStream_t)stream, "crop_to_ring_kernel");
+  crop_to_ring_kernel<<<dim3(k, n_clips), 256, 0, (cudaStream_t)stream>>>(frames, roi, ring, k, W, H, ring_len, ring_w,
+                                                                           ring_h, f_first);
+  RM_LAUNCH_CHECK(h);
   return RM_OK;
 }
 

@@ -12,6 +12,8 @@ struct SignalParams {
   const int32_t* status;  // (n_clips) or null
   int n_clips, n_frames;
   int f0, f1;             // windows (frames) handled by this launch
+  int win_f0, win_frames; // scratch rows are indexed by (clip, f - win_f0) with win_frames rows per clip
+  int last_f;             // the frame whose window is exported through filtered / peaks / npeaks
   double dt;              // 1 / fps
   double b[SC_MAX_ORDER + 1], a[SC_MAX_ORDER + 1];
   int nc;                 // filter_order + 1
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalPar
   const int clip = blockIdx.y;
   const int f = p.f0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= p.f1) return;
-  const long long win = (long long)clip * p.n_frames + f;
+  const long long win = (long long)clip * p.win_frames + (f - p.win_f0);
   const bool clip_ok = !p.status || p.status[clip] == RM_CLIP_OK || p.status[clip] == RM_CLIP_TRACK_LOST;
   const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
   const double* data = p.data + (long long)clip * p.n_frames + (f + 1 - n);
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_kern
     const unsigned q = queue[item];
     const long long win = q / SIG_MAX_CAND;
     const int k = q % SIG_MAX_CAND;
-    const int f = (int)(win % p.n_frames);
+    const int f = (int)(win % p.win_frames) + p.win_f0;
     const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
     const int idx = s.cand[win * SIG_MAX_CAND + k];
     int w = p.width;                                   // base.py:319-323
@@ -163,11 +165,11 @@ __global__ void signal_bpm_kernel(const SignalParams p, const SignalScratch s) {
   const int clip = blockIdx.y;
   const int f = p.f0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= p.f1) return;
-  const long long win = (long long)clip * p.n_frames + f;
+  const long long win = (long long)clip * p.win_frames + (f - p.win_f0);
   const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
   const double* t = p.tvals + (f + 1 - n);
   const int ncand = s.ncand[win];
-  const bool last = (f == p.n_frames - 1);
+  const bool last = (f == p.last_f);
   int nacc = 0, prev = -1;
   double sum = 0.0;
   for (int k = 0; k < ncand; ++k) {
@@ -178,7 +180,7 @@ __global__ void signal_bpm_kernel(const SignalParams p, const SignalScratch s) {
     if (last && p.peaks) p.peaks[(long long)clip * p.buf_len + nacc] = idx;
     ++nacc;
   }
-  p.bpm[win] = nacc >= 2 ? 60.0 / (sum / (double)(nacc - 1)) : NAN;
+  p.bpm[(long long)clip * p.n_frames + f] = nacc >= 2 ? 60.0 / (sum / (double)(nacc - 1)) : NAN;
   if (last) {
     if (p.npeaks) p.npeaks[clip] = nacc;
     if (p.filtered)
@@ -219,7 +221,8 @@ struct SignalJob {
 // only tvals_kernel (on st).
 int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps, double* bpm_out,
                          double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, const int32_t* status,
-                         int n_chunks, cudaStream_t st) {
+                         int n_chunks, cudaStream_t st, int win_f0, int win_frames) {
+  if (win_frames <= 0) { win_f0 = 0; win_frames = n_frames; }   // whole clips: one scratch row per frame
   RM_CHECK_ARG(h, h && data && bpm_out && n_clips >= 0 && n_frames >= 1 && fps > 0, "null pointer or bad size");
   const int order = h->p.filter_order;
   if (order < 1 || order > SC_MAX_ORDER || h->p.measure_buffer_len > SC_MAX_WIN || h->p.measure_buffer_len < 2)
@@ -238,6 +241,8 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
   if (2 * p.width > SC_MAX_FIT) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: fps/freq_max > 32 not supported", __func__);
   p.data = data; p.status = status; p.n_clips = n_clips; p.n_frames = n_frames;
   p.f0 = 0; p.f1 = n_frames;
+  p.win_f0 = win_f0; p.win_frames = win_frames;
+  p.last_f = win_f0 + win_frames - 1;
   p.dt = 1.0 / fps;
   p.buf_len = h->p.measure_buffer_len; p.init_len = h->p.measure_init_len;
   p.thres = h->p.peak_threshold; p.cutoff = h->p.gaussian_cutoff;
@@ -254,7 +259,7 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
   }
   p.tvals = h->d_tvals;
   // scratch owned by the handle, grown on demand
-  const size_t n_win = (size_t)n_clips * n_frames;
+  const size_t n_win = (size_t)n_clips * win_frames;
   const size_t need = n_win * p.buf_len * 8 + n_win * SIG_MAX_CAND * 2 + n_win * 4 + 2 * n_win * SIG_MAX_CAND * 4 + 1024;
   if (h->sig_scratch_bytes < need) {
     if (h->d_sig_scratch) cudaFree(h->d_sig_scratch);
@@ -313,8 +318,8 @@ int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t s
   SignalParams p = job->p;
   SignalScratch sc = job->sc;
   p.f0 = f0; p.f1 = f1;
-  sc.queue = job->sc.queue + (size_t)p.n_clips * f0 * SIG_MAX_CAND;   // a slice no other chunk's windows can reach
-  sc.long_queue = job->sc.long_queue + (size_t)p.n_clips * f0 * SIG_MAX_CAND;
+  sc.queue = job->sc.queue + (size_t)p.n_clips * (f0 - p.win_f0) * SIG_MAX_CAND;   // a slice no other chunk's windows reach
+  sc.long_queue = job->sc.long_queue + (size_t)p.n_clips * (f0 - p.win_f0) * SIG_MAX_CAND;
   sc.queue_n = job->sc.queue_n + 4 * chunk;
   sc.cursor = sc.queue_n + 1;
   sc.long_n = sc.queue_n + 2;
@@ -361,7 +366,7 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
     if ((rc = rmi_join(h, (cudaStream_t)stream)) != RM_OK) return rc;
   }
   rc = rmi_signal_setup(h, data, n_clips, n_frames, fps, bpm_out, filtered_out, peaks_out, npeaks_out, status, 1,
-                        (cudaStream_t)stream);
+                        (cudaStream_t)stream, 0, 0);
   if (rc != RM_OK || n_clips == 0) return rc;
   DeviceGuard dg(h->device);
   return rmi_signal_range(h, 0, n_frames, 0, (cudaStream_t)stream, (cudaStream_t)stream, nullptr, nullptr);
