@@ -230,6 +230,11 @@ int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, con
 /* Number of kernel launches this handle has issued since creation (bench.py reports it as gpu_launches). */
 int64_t rm_launch_count(rm_handle* h);
 
+/* the same from the (n_clips, cap) histories of a live cohort of which the first n_valid frames have been measured. */
+int32_t rm_pack_results_stream(rm_handle* h, const double* bpm, const int32_t* roi, const int32_t* status,
+                               const int32_t* npeaks, int32_t n_clips, int32_t cap, int32_t n_valid, rm_result* out,
+                               void* stream);
+
 /* Deferred join.  With option "defer_join" = 1, rm_measure_signal returns without making `stream` wait for its signal
  * stage and the rm_pack_results that follows runs behind that stage on a stream owned by the handle, so work enqueued on
  * `stream` afterwards (the next batch's calibration) overlaps the longest Gaussian fits of this batch.  The outputs of

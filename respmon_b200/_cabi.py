@@ -85,6 +85,7 @@ SIGNATURES = {
     "rm_crop_to_ring": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _P, _i32, _i32, _i32, _i32, _S]),
     "rm_join": (_i32, [_H, _S]),
     "rm_pack_results": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _P, _S]),
+    "rm_pack_results_stream": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _i32, _P, _S]),
     "rm_launch_count": (_i64, [_H]),
     "rm_set_option": (_i32, [_H, C.c_char_p, _i64]),
     "rm_profile_enable": (_i32, [_H, _i32]),

@@ -193,12 +193,12 @@ __global__ void signal_bpm_kernel(const SignalParams p, const SignalScratch s) {
 
 __global__ void pack_results_kernel(const double* __restrict__ bpm, const int32_t* __restrict__ roi,
                                     const int32_t* __restrict__ status, const int32_t* __restrict__ npeaks, int n_clips,
-                                    int n_frames, rm_result* __restrict__ out) {
+                                    int n_frames, int n_scan, rm_result* __restrict__ out) {
   const int clip = blockIdx.x * blockDim.x + threadIdx.x;
   if (clip >= n_clips) return;
   rm_result r;
   r.bpm = NAN;
-  for (int f = n_frames - 1; f >= 0; --f) {      // freq[-1]: the most recent frame that appended a BPM
+  for (int f = n_scan - 1; f >= 0; --f) {        // freq[-1]: the most recent frame that appended a BPM
     const double v = bpm[(long long)clip * n_frames + f];
     if (v == v) { r.bpm = v; break; }
   }
@@ -387,12 +387,27 @@ extern "C" int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_
     st = h->tail_stream;
   }
   RM_PROF(h, st, "pack_results_kernel");
-  pack_results_kernel<<<div_up(n_clips, 128), 128, 0, st>>>(bpm, roi, status, npeaks, n_clips, n_frames, out);
+  pack_results_kernel<<<div_up(n_clips, 128), 128, 0, st>>>(bpm, roi, status, npeaks, n_clips, n_frames, n_frames, out);
   RM_LAUNCH_CHECK(h);
   if (st == h->tail_stream) {
     RM_CUDA(h, cudaEventRecord(h->ev_packed, st));
     h->pending_pack = 1;
     h->pending_chunks = 0;     // ev_packed is behind every ev_done
   }
+  return RM_OK;
+}
+
+// Live streams: the same records from (n_clips, cap) histories of which the first n_valid frames have been measured.
+extern "C" int32_t rm_pack_results_stream(rm_handle* h, const double* bpm, const int32_t* roi, const int32_t* status,
+                                          const int32_t* npeaks, int32_t n_clips, int32_t cap, int32_t n_valid,
+                                          rm_result* out, void* stream) {
+  RM_CHECK_ARG(h, h && bpm && roi && status && out && n_clips >= 0 && cap >= 1 && n_valid >= 0 && n_valid <= cap,
+               "null pointer or bad size");
+  if (n_clips == 0) return RM_OK;
+  DeviceGuard dg(h->device);
+  RM_PROF(h, (cudaStream_t)stream, "pack_results_kernel");
+  pack_results_kernel<<<div_up(n_clips, 128), 128, 0, (cudaStream_t)stream>>>(bpm, roi, status, npeaks, n_clips, cap,
+                                                                              n_valid, out);
+  RM_LAUNCH_CHECK(h);
   return RM_OK;
 }

@@ -44,8 +44,19 @@ class LiveCohort:
         Returns dict(state, bpm (n,) latest estimate or NaN, status (n,), roi (n,4) or None)."""
         f = torch.from_numpy(frames) if isinstance(frames, np.ndarray) else frames
         assert f.dim() == 4 and f.shape[0] == self.n and tuple(f.shape[2:]) == (self.H, self.W) and f.dtype == torch.uint8
-        f = f.to(self.engine.device, non_blocking=True).contiguous()
         k, j = f.shape[1], 0
+        if not f.is_cuda and self.state == "measure":
+            # host frames in the measure state: only the ROI crops cross PCIe (the reference reads nothing else of these
+            # frames, base.py:471)
+            while j < k:
+                m = min(k - j, self.ring_len - 1, self.cap - self.n_measured)
+                if m <= 0:
+                    break
+                self._measure(self._host_crops(f[:, j:j + m]), cropped=True)
+                j += m
+            self.frames_seen += k
+            return self.latest()
+        f = f.to(self.engine.device, non_blocking=True).contiguous()
         while j < k:
             if self.state == "initialize":                         # base.py:423-425: this frame is dropped
                 self.state, j = "calibration", j + 1
@@ -77,6 +88,7 @@ class LiveCohort:
             self._cal_idx = 0
             return
         self.roi, self.status = roi, status
+        self._roi_host, self._ok_host, self._stage = [tuple(int(v) for v in row) for row in r], ok, None
         self._mw, self._mh = int(max(1, r[ok, 2].max())), int(max(1, r[ok, 3].max()))
         dev = eng.device
         self._ring = torch.zeros((self.n, self.ring_len, self._mh, self._mw), dtype=torch.uint8, device=dev)
@@ -96,13 +108,31 @@ class LiveCohort:
         self.n_measured = 0
         self.state = "measure"
 
-    def _measure(self, block):
+    def _host_crops(self, block):
+        """(n, k, H, W) host frames -> (n, k, mh, mw) device tensor of ROI crops (top-left aligned)."""
+        k = block.shape[1]
+        hb = block.numpy()
+        stage = torch.empty((self.n, k, self._mh, self._mw), dtype=torch.uint8).pin_memory() \
+            if getattr(self, "_stage", None) is None or self._stage.shape[1] < k else self._stage
+        self._stage = stage
+        sv = stage.numpy()
+        for c in range(self.n):
+            if self._ok_host[c]:
+                x, y, w, h = self._roi_host[c]
+                sv[c, :k, :h, :w] = hb[c, :, y:y + h, x:x + w]
+        return stage[:, :k].to(self.engine.device, non_blocking=True)
+
+    def _measure(self, block, cropped=False):
         eng = self.engine
         block = block.contiguous()
         k = block.shape[1]
         f0 = self.n_measured
-        eng._call("rm_crop_to_ring", _ptr(block), self.n, k, self.W, self.H, _ptr(self.roi), _ptr(self._ring), self.ring_len,
-                  self._mw, self._mh, f0, eng._stream())
+        if cropped:
+            eng._call("rm_crop_to_ring", _ptr(block), self.n, k, self._mw, self._mh, _ptr(self._roi0), _ptr(self._ring),
+                      self.ring_len, self._mw, self._mh, f0, eng._stream())
+        else:
+            eng._call("rm_crop_to_ring", _ptr(block), self.n, k, self.W, self.H, _ptr(self.roi), _ptr(self._ring),
+                      self.ring_len, self._mw, self._mh, f0, eng._stream())
         eng._call("rm_measure_signal_stream", _ptr(self._ring), self.n, self.ring_len, self._mw, self._mh, _ptr(self._roi0),
                   self._mw, self._mh, self.cap, f0, f0 + k, self.fps, _ptr(self.data), _ptr(self.motion), _ptr(self.npts),
                   _ptr(self.status), _ptr(self.bpm), _ptr(self.filtered), _ptr(self.peaks), _ptr(self.npeaks),
@@ -111,16 +141,20 @@ class LiveCohort:
 
     # ------------------------------------------------------------------ results
     def latest(self) -> dict:
+        """state, and per camera: the latest BPM (`freq[-1]`, base.py:352; NaN before the first one), ROI, rm_clip_status
+        (NO_PEAKS until a BPM exists), n_peaks of the current window -- one 32-byte record per camera read back."""
         out = dict(state=self.state, roi=None, status=None, bpm=np.full(self.n, np.nan), n_measured=self.n_measured)
         if self.state == "measure":
-            out["roi"] = self.roi.cpu().numpy()
-            out["status"] = self.status.cpu().numpy()
-            if self.n_measured > 0:
-                b = self.bpm[:, :self.n_measured].cpu().numpy()
-                for c in range(self.n):                             # freq[-1]: the latest frame that produced a BPM
-                    v = b[c][~np.isnan(b[c])]
-                    if len(v):
-                        out["bpm"][c] = v[-1]
+            from .engine import results_to_numpy
+            eng = self.engine
+            rec_dev = torch.empty((self.n, 32), dtype=torch.uint8, device=eng.device)
+            eng._call("rm_pack_results_stream", _ptr(self.bpm), _ptr(self.roi), _ptr(self.status), _ptr(self.npeaks), self.n,
+                      self.cap, self.n_measured, _ptr(rec_dev), eng._stream())
+            rec = results_to_numpy(rec_dev)
+            out["roi"] = np.stack([rec["x"], rec["y"], rec["w"], rec["h"]], axis=1)
+            out["status"] = rec["status"]
+            out["bpm"] = rec["bpm"]
+            out["n_peaks"] = rec["n_peaks"]
         return out
 
     def history(self) -> dict:
