@@ -309,6 +309,8 @@ def run_gpu_arm(args) -> dict | None:
         }
 
     # ---- end to end from host memory through the public batch API
+    from respmon_b200.hostmem import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else None     # pinned buffers on the GPU's own socket
     host = torch.empty(clips.shape, dtype=torch.uint8).pin_memory()
     host.copy_(clips)
     torch.cuda.synchronize()
@@ -383,7 +385,7 @@ def run_gpu_arm(args) -> dict | None:
                    "parallelism": "clips sharded over %d GPU(s), one all-gather of 32 B result records" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mon.h2d_bytes // e2e_steps,
                 "d2h_bytes_per_step": mon.d2h_bytes // e2e_steps, "steps": e2e_steps, "chunk_clips": args.chunk,
-                "same_results_as_resident_run": same},
+                "same_results_as_resident_run": same, "numa": numa},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
