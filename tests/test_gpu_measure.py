@@ -235,3 +235,32 @@ def test_measure_signal_pipeline_track_lost_in_a_later_chunk(eng):
     assert np.array_equal(sa["bpm"].cpu().numpy(), b["bpm"].cpu().numpy(), equal_nan=True)
     data = b["data"].cpu().numpy()[0]
     assert np.isfinite(data[:60]).all()
+
+
+@pytest.mark.parametrize("fps", [5.01, 7.68, 30.0])
+def test_signal_bpm_at_other_frame_rates(eng, fps):
+    """The author's recorded rates (prototypes/signal_measurement.py:103) and a 30 frames/s camera with fps_limit raised:
+    filter design, peak distance floor(fps / freq_max) and fit windows all follow fps (base.py:342, 441)."""
+    rng = np.random.default_rng(int(fps * 100))
+    nf = 200
+    tt = np.zeros(nf)
+    for i in range(1, nf):
+        tt[i] = tt[i - 1] + 1.0 / fps
+    data = 0.1 * np.sin(2 * np.pi * (0.027 * fps) * tt + 0.4) + 0.004 * rng.standard_normal(nf)   # ~3.5 periods per window
+    out = eng.signal_bpm(dev(data[None]), fps)
+    bpm = out["bpm"].cpu().numpy()[0]
+    checked = 0
+    for f in (13, 40, 127, 128, 150, 199):
+        lo = max(0, f + 1 - 128)
+        filt, peaks, want = P.measure_window(data[lo:f + 1], tt[lo:f + 1], fps)
+        if want is None:
+            assert np.isnan(bpm[f])
+        else:
+            assert abs(bpm[f] - want) < 1e-6
+            checked += 1
+    assert checked >= 3
+    lo = nf - 128
+    filt, peaks, _ = P.measure_window(data[lo:], tt[lo:], fps)
+    assert np.abs(out["filtered"].cpu().numpy()[0] - filt).max() < 1e-12
+    k = int(out["npeaks"][0])
+    assert list(out["peaks"].cpu().numpy()[0][:k]) == list(peaks)

@@ -130,3 +130,31 @@ def test_measure_state_does_not_leak_between_batches(eng):
     fresh.close()
     for f in want.dtype.names:
         assert np.array_equal(got[f], want[f], equal_nan=True), f
+
+
+def test_measure_pipeline_with_a_roi_too_large_for_shared_memory(eng):
+    """A 352 x 264 ROI (what skip_calibration() or a large moving region gives): more than the shared-memory tracker can
+    stage, so rm_measure_signal takes the global-memory tracker (one chunk).  Signal and BPM still match the CPU oracle."""
+    from respmon_b200 import synth
+    base = synth.clip_spec(5, 640, 480, 256)
+    spec = synth.ClipSpec(base.width, base.height, base.n_frames, base.seed, base.fps, base.freq_hz, 120, 90, 352, 264)
+    clip = synth.make_clip(spec)
+    x, y, w, h = 120, 90, 352, 264
+    n = 80
+    roi = torch.tensor([[x, y, w, h]], dtype=torch.int32).cuda()
+    out = eng.measure_signal(dev(clip[None]), roi, 130, n, 10.0)
+    assert int(out["status"][0]) == 0 and int(out["npts"][0]) > 16
+    tracker = P.FlowTracker()
+    want = [tracker.step(P.u8_to_unit(clip[130 + f, y:y + h, x:x + w])) for f in range(n)]
+    d = out["data"].cpu().numpy()[0]
+    assert np.sqrt(np.mean((d - np.array(want)) ** 2)) <= 1e-4
+    tt = np.zeros(n)
+    for i in range(1, n):
+        tt[i] = tt[i - 1] + 0.1
+    _, peaks, bpm = P.measure_window(np.array(want), tt, 10.0)
+    got = float(out["bpm"][0, -1])
+    if bpm is None:
+        assert np.isnan(got)
+    else:
+        assert abs(got - bpm) <= 0.5
+        assert int(out["npeaks"][0]) == len(peaks)

@@ -26,6 +26,9 @@ PY
 # launch list (cold-cache, serialised: shares only), 16 clips x 2 steps, skip nothing
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/launches.csv \
     python tools/prof_step.py 64 2 > $OUT/launches.log 2>&1
+# the launch list of the bench command itself (what the contract asks for)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/bench_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.json 2> $OUT/bench_under_ncu.err
 # full captures of the dominant kernels (second step = warm)
 for K in pyramid_front_u8_kernel upsample_pass_kernel lk_track_smem_kernel signal_fit_kernel; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 2 -f -o $OUT/$K \
