@@ -117,6 +117,28 @@ def main():
             lines.append("| %s | %d | %.1f | %.1f%% |" % (k, a[1], a[0], 100 * a[0] / tot))
         with open(os.path.join(dst, "%s_launches.csv" % tag), "w") as f:
             f.write(txt[start:] if start >= 0 else txt)
+    bl = os.path.join(src, "bench_launches.csv")
+    if os.path.exists(bl):   # the launch list of `python bench.py` itself
+        txt = open(bl).read()
+        start = txt.find('"ID"')
+        rows = list(csv.DictReader(io.StringIO(txt[start:]))) if start >= 0 else []
+        agg = OrderedDict()
+        for r in rows:
+            if r.get("Metric Name") != "gpu__time_duration.sum":
+                continue
+            v = float(r["Metric Value"].replace(",", ""))
+            v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r.get("Metric Unit", "ns"), 1e-3)
+            a = agg.setdefault(r["Kernel Name"].split("(")[0], [0.0, 0])
+            a[0] += v
+            a[1] += 1
+        tot = sum(a[0] for a in agg.values()) or 1.0
+        lines += ["", "## launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` under ncu "
+                  "(all legs: warm-up, timed steps, extras, end-to-end)", "", "| kernel | launches | total us | share |",
+                  "|---|---|---|---|"]
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            lines.append("| %s | %d | %.1f | %.1f%% |" % (k, a[1], a[0], 100 * a[0] / tot))
+        with open(os.path.join(dst, "%s_bench_launches.csv" % tag), "w") as f:
+            f.write(txt[start:] if start >= 0 else txt)
     bj = os.path.join(src, "bench.json")
     if os.path.exists(bj):
         try:
