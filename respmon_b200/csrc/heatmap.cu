@@ -267,6 +267,28 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
     const double top = hi - (hi - lo) * p.threshold;
     top_s = top / p.scale;
     repl_s = lo / p.scale;
+    if (p.bounds) {
+      // Pass 2 replaces every value >= top by the minimum (transforms.py:190-192).  Where the convexity bound says that
+      // ALL level-0 values of this tile in frame t are >= top (with the same rounding margin), the frame contributes the
+      // minimum to every pixel whatever the values are: it is neither staged nor evaluated, its additions still happen,
+      // in frame order.  That is the fate of everything that does not move: top sits 30 % above the most negative value.
+      const double2* b = p.bounds + ((long long)clip * gridDim.x + tile) * p.T;
+      unsigned char* flag = reinterpret_cast<unsigned char*>(frame_list + p.T);
+      for (int t = tid; t < p.T; t += blockDim.x) {
+        const double2 lh = b[t];
+        const double mrg = 1e-12 * fmax(fabs(lh.x), fabs(lh.y));
+        flag[t] = !(lh.x - mrg >= top);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int n = 0;
+        for (int t = 0; t < p.T; ++t)
+          if (flag[t]) frame_list[n++] = t;
+        frame_list[p.T + (p.T + 3) / 4] = n;   // past the flags
+      }
+      __syncthreads();
+      n_list = frame_list[p.T + (p.T + 3) / 4];
+    }
   }
   const long long n2 = (long long)p.w[2] * p.h[2];
   const double* a_clip = p.a2 + (long long)clip * p.T * n2;
@@ -292,13 +314,13 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
   const unsigned stage_base = (unsigned)__cvta_generic_to_shared(stage);
   auto issue = [&](int k) {
     if (k < n_list) {
-      const int t = (PASS == 1 && p.bounds) ? frame_list[k] : k;
+      const int t = p.bounds ? frame_list[k] : k;
       const double* l2 = a_clip + t * n2;
       const unsigned dst = stage_base + (unsigned)((k % HM_STAGES) * HM_PW * HM_PH * 8);
 #pragma unroll
-      for (int k = 0; k < HM_COPIES; ++k)
-        if (src_off[k] >= 0)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + dst_off[k] * 8), "l"(l2 + src_off[k])
+      for (int c = 0; c < HM_COPIES; ++c)
+        if (src_off[c] >= 0)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + dst_off[c] * 8), "l"(l2 + src_off[c])
                        : "memory");
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -307,7 +329,23 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
   for (int t = 0; t < HM_STAGES - 1; ++t) issue(t);
 
   {
-    for (int t = 0; t < n_list; ++t) {   // t = position in the frame list (pass 2: the frame itself)
+    // pass 1 walks the frame list; pass 2 walks every frame in order and consumes the list as it goes (k = position of
+    // the next staged frame): a frame that is not on the list only adds the replacement value
+    int k = 0;
+    const int n_iter = (PASS == 2 && p.bounds) ? p.T : n_list;
+    for (int it = 0; it < n_iter; ++it) {
+      if (PASS == 2 && p.bounds) {
+        if (k >= n_list || frame_list[k] != it) {          // block-uniform
+          if (active) {
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 4; ++kx) acc[ky][kx] += repl_s;
+          }
+          continue;
+        }
+      }
+      const int t = k++;               // position in the staging ring
       asm volatile("cp.async.wait_group %0;\n" ::"n"(HM_STAGES - 2) : "memory");
       __syncthreads();                 // frame t has landed for everyone; everyone is done with frame t-1's stage
       issue(t + HM_STAGES - 1);        // refills the stage frame t-1 used
@@ -700,7 +738,7 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   tp.top_w = g.w[s];
   tp.top_h = g.h[s];
   tp.n_up = s;
-  if (!h->no_minmax_seed && (size_t)T * 4 <= 32768) {
+  if (!h->no_minmax_seed && (size_t)T * 5 + 32 <= 32768) {
     const long long items = (long long)grid.x * T;
     RM_PROF(h, st, "tile_bounds_kernel");
     tile_bounds_kernel<<<dim3((unsigned)((items + 255) / 256), n_clips), 256, 0, st>>>(tp, bounds);
@@ -712,11 +750,11 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
     RM_LAUNCH_CHECK(h);
   }
   RM_PROF(h, st, "upsample_pass_kernel<1>");
-  upsample_pass_kernel<1><<<grid, 128, tp.bounds ? (size_t)T * 4 : 0, st>>>(tp);
+  const size_t list_smem = tp.bounds ? (size_t)T * 4 + (size_t)((T + 3) / 4) * 4 + 16 : 0;   // frame list, flags, count
+  upsample_pass_kernel<1><<<grid, 128, list_smem, st>>>(tp);
   RM_LAUNCH_CHECK(h);
-  tp.bounds = nullptr;
   RM_PROF(h, st, "upsample_pass_kernel<2>");
-  upsample_pass_kernel<2><<<grid, 128, 0, st>>>(tp);
+  upsample_pass_kernel<2><<<grid, 128, list_smem, st>>>(tp);
   RM_LAUNCH_CHECK(h);
   long long hw = (long long)W * H;
   dim3 ngrid((unsigned)((hw + 255) / 256 < 1024 ? (hw + 255) / 256 : 1024), n_clips);
