@@ -115,7 +115,7 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
     LMT(5);
     LMC(7);
     {   // fdjac2: forward differences (each lane differences the rows it evaluated)
-      const double eps = sqrt(epsfcn > epsmch ? epsfcn : epsmch);
+      const double eps = l3_sqrt(epsfcn > epsmch ? epsfcn : epsmch);
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const double temp = x[j];
@@ -172,15 +172,15 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
             double part = 0.0;
 #pragma unroll 1
             for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * fjac[i + k * m];
-            const double temp = lmg_sum<G>(g, part) / ajj;
+            const double temp = l3_div(lmg_sum<G>(g, part), ajj);
 #pragma unroll 1
             for (int i = j + g.sub; i < m; i += G) fjac[i + k * m] -= temp * fjac[i + j * m];
             __syncwarp(g.mask);
             if (wa1[k] != 0.0) {
-              double t = fjac[j + k * m] / wa1[k];
+              double t = l3_div(fjac[j + k * m], wa1[k]);
               const double d = 1.0 - t * t;
-              wa1[k] *= sqrt(d > 0.0 ? d : 0.0);
-              t = wa1[k] / wa3[k];
+              wa1[k] *= l3_sqrt(d > 0.0 ? d : 0.0);
+              t = l3_div(wa1[k], wa3[k]);
               if (0.05 * (t * t) <= SC_DBL_EPS) {
                 wa1[k] = lmg_enorm<G>(g, fjac + k * m, m, j + 1);
                 wa3[k] = wa1[k];
@@ -212,7 +212,7 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
         double part = 0.0;
 #pragma unroll 1
         for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * wa4[i];
-        const double temp = -lmg_sum<G>(g, part) / ajj;
+        const double temp = l3_div(-lmg_sum<G>(g, part), ajj);
 #pragma unroll 1
         for (int i = j + g.sub; i < m; i += G) wa4[i] += fjac[i + j * m] * temp;
         __syncwarp(g.mask);
@@ -232,8 +232,8 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
         if (w2l != 0.0) {
           double sum = 0.0;
 #pragma unroll
-          for (int i = 0; i <= j; ++i) sum += r[i + j * 3] * (qtf[i] / fnorm);
-          const double gg = fabs(sum / w2l);
+          for (int i = 0; i <= j; ++i) sum += r[i + j * 3] * l3_div(qtf[i], fnorm);
+          const double gg = fabs(l3_div(sum, w2l));
           gnorm = gnorm > gg ? gnorm : gg;
         }
       }
@@ -260,7 +260,7 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
       ++nfev;
       const double fnorm1 = lmg_enorm<G>(g, wa4, m, 0);
       double actred = -1.0;
-      if (p1 * fnorm1 < fnorm) { const double d = fnorm1 / fnorm; actred = 1.0 - d * d; }
+      if (p1 * fnorm1 < fnorm) { const double d = l3_div(fnorm1, fnorm); actred = 1.0 - d * d; }
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         wa3[j] = 0.0;
@@ -268,22 +268,22 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
 #pragma unroll
         for (int i = 0; i <= j; ++i) wa3[i] += r[i + j * 3] * temp;
       }
-      const double temp1 = l3_enorm3(wa3[0], wa3[1], wa3[2]) / fnorm;
-      const double temp2 = (sqrt(par) * pnorm) / fnorm;
-      const double prered = temp1 * temp1 + temp2 * temp2 / p5;
+      const double temp1 = l3_div(l3_enorm3(wa3[0], wa3[1], wa3[2]), fnorm);
+      const double temp2 = l3_div(l3_sqrt(par) * pnorm, fnorm);
+      const double prered = temp1 * temp1 + l3_div(temp2 * temp2, p5);
       const double dirder = -(temp1 * temp1 + temp2 * temp2);
       ratio = 0.0;
-      if (prered != 0.0) ratio = actred / prered;
+      if (prered != 0.0) ratio = l3_div(actred, prered);
       if (ratio <= p25) {
         double temp;
         if (actred >= 0.0) temp = p5;
-        else temp = p5 * dirder / (dirder + p5 * actred);
+        else temp = l3_div(p5 * dirder, dirder + p5 * actred);
         if (p1 * fnorm1 >= fnorm || temp < p1) temp = p1;
-        const double q = pnorm / p1;
+        const double q = l3_div(pnorm, p1);
         delta = temp * (delta < q ? delta : q);
-        par /= temp;
+        par = l3_div(par, temp);
       } else if (par == 0.0 || ratio >= p75) {
-        delta = pnorm / p5;
+        delta = l3_div(pnorm, p5);
         par = p5 * par;
       }
       if (ratio >= p0001) {

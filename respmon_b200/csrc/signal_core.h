@@ -401,6 +401,12 @@ L3_INL void l3_put(double v[3], int i, double x) {
   else v[2] = x;
 }
 
+// IEEE division and square root as calls: the inline expansions are 25-40 instructions each and the trust-region code
+// has about a hundred of them -- as calls the fit kernel is half the size (it is instruction-fetch bound otherwise) and the
+// results are the same bits.
+L3_NOINL double l3_div(double a, double b) { return a / b; }
+L3_NOINL double l3_sqrt(double a) { return sqrt(a); }
+
 // one term of MINPACK enorm's three-range accumulation
 L3_INL void l3_enorm_acc(double xabs, double agiant, double& s1, double& s2, double& s3, double& x1max, double& x3max) {
   const double rdwarf = 3.834e-20;
@@ -408,18 +414,18 @@ L3_INL void l3_enorm_acc(double xabs, double agiant, double& s1, double& s2, dou
     s2 += xabs * xabs;
   } else if (xabs <= rdwarf) {
     if (xabs <= x3max) {
-      if (xabs != 0.0) { const double d = xabs / x3max; s3 += d * d; }
+      if (xabs != 0.0) { const double d = l3_div(xabs, x3max); s3 += d * d; }
     } else {
-      const double d = x3max / xabs;
+      const double d = l3_div(x3max, xabs);
       s3 = 1.0 + s3 * (d * d);
       x3max = xabs;
     }
   } else {
     if (xabs <= x1max) {
-      const double d = xabs / x1max;
+      const double d = l3_div(xabs, x1max);
       s1 += d * d;
     } else {
-      const double d = x1max / xabs;
+      const double d = l3_div(x1max, xabs);
       s1 = 1.0 + s1 * (d * d);
       x1max = xabs;
     }
@@ -436,18 +442,18 @@ L3_NOINL double l3_enorm3(double a, double b, double c) {
     s2 += xa * xa;
     s2 += xb * xb;
     s2 += xc * xc;
-    return sqrt(s2);                 // s1 == 0, s2 != 0, x3max == 0 <= s2:  sqrt(s2 * (1 + (0 / s2) * (0 * s3))) == sqrt(s2)
+    return l3_sqrt(s2);              // s1 == 0, s2 != 0, x3max == 0 <= s2:  sqrt(s2 * (1 + (0 / s2) * (0 * s3))) == sqrt(s2)
   }
   double s1 = 0.0, s2 = 0.0, s3 = 0.0, x1max = 0.0, x3max = 0.0;
   l3_enorm_acc(xa, agiant, s1, s2, s3, x1max, x3max);
   l3_enorm_acc(xb, agiant, s1, s2, s3, x1max, x3max);
   l3_enorm_acc(xc, agiant, s1, s2, s3, x1max, x3max);
-  if (s1 != 0.0) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+  if (s1 != 0.0) return x1max * l3_sqrt(s1 + l3_div(l3_div(s2, x1max), x1max));
   if (s2 != 0.0) {
-    if (s2 >= x3max) return sqrt(s2 * (1.0 + (x3max / s2) * (x3max * s3)));
-    return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
+    if (s2 >= x3max) return l3_sqrt(s2 * (1.0 + l3_div(x3max, s2) * (x3max * s3)));
+    return l3_sqrt(x3max * (l3_div(s2, x3max) + (x3max * s3)));
   }
-  return x3max * sqrt(s3);
+  return x3max * l3_sqrt(s3);
 }
 
 // sc_qrsolv with ldr = 3: r is the full 3x3 (column-major) work matrix, as in MINPACK.
@@ -473,12 +479,12 @@ L3_INL void l3_qrsolv(double r[9], const int ipvt[3], const double diag[3], cons
         if (sdiag[k] != 0.0) {
           double cs, sn;
           if (fabs(r[k + k * 3]) < fabs(sdiag[k])) {
-            const double cotan = r[k + k * 3] / sdiag[k];
-            sn = 0.5 / sqrt(0.25 + 0.25 * (cotan * cotan));
+            const double cotan = l3_div(r[k + k * 3], sdiag[k]);
+            sn = l3_div(0.5, l3_sqrt(0.25 + 0.25 * (cotan * cotan)));
             cs = sn * cotan;
           } else {
-            const double tn = sdiag[k] / r[k + k * 3];
-            cs = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
+            const double tn = l3_div(sdiag[k], r[k + k * 3]);
+            cs = l3_div(0.5, l3_sqrt(0.25 + 0.25 * (tn * tn)));
             sn = cs * tn;
           }
           r[k + k * 3] = cs * r[k + k * 3] + sn * sdiag[k];
@@ -510,7 +516,7 @@ L3_INL void l3_qrsolv(double r[9], const int ipvt[3], const double diag[3], cons
 #pragma unroll
       for (int i = j + 1; i < 3; ++i)
         if (i < nsing) sum += r[i + j * 3] * wa[i];
-      wa[j] = (wa[j] - sum) / sdiag[j];
+      wa[j] = l3_div(wa[j] - sum, sdiag[j]);
     }
   }
 #pragma unroll
@@ -531,7 +537,7 @@ L3_INL void l3_lmpar(double r[9], const int ipvt[3], const double diag[3], const
 #pragma unroll
   for (int j = 2; j >= 0; --j) {             // for k = 1..nsing: j = nsing - k
     if (j < nsing) {
-      wa1[j] /= r[j + j * 3];
+      wa1[j] = l3_div(wa1[j], r[j + j * 3]);
       const double temp = wa1[j];
 #pragma unroll
       for (int i = 0; i < j; ++i) wa1[i] -= r[i + j * 3] * temp;
@@ -548,35 +554,35 @@ L3_INL void l3_lmpar(double r[9], const int ipvt[3], const double diag[3], const
   double parl = 0.0;
   if (nsing >= 3) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { const int l = ipvt[j]; wa1[j] = l3_get(diag, l) * (l3_get(wa2, l) / dxnorm); }
+    for (int j = 0; j < 3; ++j) { const int l = ipvt[j]; wa1[j] = l3_get(diag, l) * l3_div(l3_get(wa2, l), dxnorm); }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       double sum = 0.0;
 #pragma unroll
       for (int i = 0; i < j; ++i) sum += r[i + j * 3] * wa1[i];
-      wa1[j] = (wa1[j] - sum) / r[j + j * 3];
+      wa1[j] = l3_div(wa1[j] - sum, r[j + j * 3]);
     }
     const double temp = l3_enorm3(wa1[0], wa1[1], wa1[2]);
-    parl = fp / delta / temp / temp;
+    parl = l3_div(l3_div(l3_div(fp, delta), temp), temp);
   }
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     double sum = 0.0;
 #pragma unroll
     for (int i = 0; i <= j; ++i) sum += r[i + j * 3] * qtb[i];
-    wa1[j] = sum / l3_get(diag, ipvt[j]);
+    wa1[j] = l3_div(sum, l3_get(diag, ipvt[j]));
   }
   const double gnorm = l3_enorm3(wa1[0], wa1[1], wa1[2]);
-  double paru = gnorm / delta;
-  if (paru == 0.0) paru = dwarf / (delta < p1 ? delta : p1);
+  double paru = l3_div(gnorm, delta);
+  if (paru == 0.0) paru = l3_div(dwarf, delta < p1 ? delta : p1);
   *par = *par > parl ? *par : parl;
   *par = *par < paru ? *par : paru;
-  if (*par == 0.0) *par = gnorm / dxnorm;
+  if (*par == 0.0) *par = l3_div(gnorm, dxnorm);
 #pragma unroll 1
   for (;;) {
     ++iter;
     if (*par == 0.0) { const double t = p001 * paru; *par = dwarf > t ? dwarf : t; }
-    double temp = sqrt(*par);
+    double temp = l3_sqrt(*par);
 #pragma unroll
     for (int j = 0; j < 3; ++j) wa1[j] = temp * diag[j];
     l3_qrsolv(r, ipvt, wa1, qtb, x, sdiag, wa2);
@@ -587,16 +593,16 @@ L3_INL void l3_lmpar(double r[9], const int ipvt[3], const double diag[3], const
     fp = dxnorm - delta;
     if (fabs(fp) <= p1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { const int l = ipvt[j]; wa1[j] = l3_get(diag, l) * (l3_get(wa2, l) / dxnorm); }
+    for (int j = 0; j < 3; ++j) { const int l = ipvt[j]; wa1[j] = l3_get(diag, l) * l3_div(l3_get(wa2, l), dxnorm); }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      wa1[j] /= sdiag[j];
+      wa1[j] = l3_div(wa1[j], sdiag[j]);
       temp = wa1[j];
 #pragma unroll
       for (int i = j + 1; i < 3; ++i) wa1[i] -= r[i + j * 3] * temp;
     }
     temp = l3_enorm3(wa1[0], wa1[1], wa1[2]);
-    const double parc = fp / delta / temp / temp;
+    const double parc = l3_div(l3_div(l3_div(fp, delta), temp), temp);
     if (fp > 0.0) parl = parl > *par ? parl : *par;
     if (fp < 0.0) paru = paru < *par ? paru : *par;
     const double cand = *par + parc;
