@@ -22,7 +22,12 @@ struct RoiParams {
   int n_clips, W, H, threshold;
   int32_t* roi;             // (n_clips, 4)
   int32_t* status;          // (n_clips)
+  // every traced component leaves (key, packed bounding box) in its clip's list so that the winner's box is looked up
+  // instead of being traced a second time; a clip with more than ROI_LIST_CAP components falls back to the second trace
+  unsigned long long* list; // (n_clips, ROI_LIST_CAP, 2)
+  int* list_n;              // (n_clips)
 };
+#define ROI_LIST_CAP 2048
 
 __device__ __forceinline__ int uf_find(const int32_t* L, int i) {
   const volatile int32_t* V = L;   // parents only ever decrease; a stale read is still an ancestor
@@ -51,7 +56,7 @@ __global__ void roi_init_kernel(const RoiParams p) {
   int32_t* L = p.labels + blockIdx.y * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x)
     L[i] = heat[i] > p.threshold ? (int)i : -1;
-  if (blockIdx.x == 0 && threadIdx.x == 0) p.best[blockIdx.y] = 0ull;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { p.best[blockIdx.y] = 0ull; p.list_n[blockIdx.y] = 0; }
 }
 
 __global__ void roi_merge_kernel(const RoiParams p) {
@@ -86,7 +91,15 @@ __global__ void roi_trace_kernel(const RoiParams p) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
     if (L[i] != (int)i) continue;   // not the first pixel of a component
     const RoiTrace t = roi_trace_outer((int)(i % p.W), (int)(i / p.W), fg, max_steps);
-    atomicMax(&p.best[blockIdx.y], roi_key(t.area2, (int)i));
+    const unsigned long long key = roi_key(t.area2, (int)i);
+    atomicMax(&p.best[blockIdx.y], key);
+    const int slot = atomicAdd(&p.list_n[blockIdx.y], 1);
+    if (slot < ROI_LIST_CAP && p.W < 65536 && p.H < 65536) {
+      unsigned long long* e = p.list + ((long long)blockIdx.y * ROI_LIST_CAP + slot) * 2;
+      e[0] = key;
+      e[1] = (unsigned long long)t.x0 | ((unsigned long long)t.y0 << 16) | ((unsigned long long)t.x1 << 32) |
+             ((unsigned long long)t.y1 << 48);
+    }
   }
 }
 
@@ -101,6 +114,17 @@ __global__ void roi_finish_kernel(const RoiParams p) {
     if (p.status) p.status[clip] = RM_CLIP_NO_ROI;
     return;
   }
+  if (p.list_n[clip] <= ROI_LIST_CAP && p.W < 65536 && p.H < 65536) {   // the winner's box is in the list
+    const unsigned long long* e = p.list + (long long)clip * ROI_LIST_CAP * 2;
+    for (int i = 0; i < p.list_n[clip]; ++i)
+      if (e[2 * i] == k) {
+        const unsigned long long b = e[2 * i + 1];
+        const int x0 = (int)(b & 0xffff), y0 = (int)((b >> 16) & 0xffff), x1 = (int)((b >> 32) & 0xffff), y1 = (int)(b >> 48);
+        out[0] = x0; out[1] = y0; out[2] = x1 - x0 + 1; out[3] = y1 - y0 + 1;
+        if (p.status) p.status[clip] = RM_CLIP_OK;
+        return;
+      }
+  }
   const int start = (int)(k & 0xffffffffu) - 1;
   const HeatFg fg{p.heat + clip * hw, p.W, p.H, p.threshold};
   const int max_steps = (int)(4 * hw + 8 < 0x7fffffff ? 4 * hw + 8 : 0x7fffffff);
@@ -111,7 +135,8 @@ __global__ void roi_finish_kernel(const RoiParams p) {
 
 extern "C" int32_t rm_roi_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n_clips, size_t* out) {
   RM_CHECK_ARG(h, h && out && W >= 1 && H >= 1 && n_clips >= 0, "null pointer or bad size");
-  *out = (size_t)n_clips * W * H * 4 + (size_t)n_clips * 8 + 2 * 256;
+  *out = (size_t)n_clips * W * H * 4 + (size_t)n_clips * 8 + (size_t)n_clips * ROI_LIST_CAP * 16 + (size_t)n_clips * 4 +
+         4 * 256;
   return RM_OK;
 }
 
@@ -133,6 +158,10 @@ extern "C" int32_t rm_roi_select(rm_handle* h, const uint8_t* heat, int32_t n_cl
   p.labels = reinterpret_cast<int32_t*>(base);
   base += ((size_t)n_clips * W * H * 4 + 255) & ~(size_t)255;
   p.best = reinterpret_cast<unsigned long long*>(base);
+  base += ((size_t)n_clips * 8 + 255) & ~(size_t)255;
+  p.list = reinterpret_cast<unsigned long long*>(base);
+  base += ((size_t)n_clips * ROI_LIST_CAP * 16 + 255) & ~(size_t)255;
+  p.list_n = reinterpret_cast<int*>(base);
   p.heat = heat; p.n_clips = n_clips; p.W = W; p.H = H; p.threshold = threshold;
   p.roi = roi_out; p.status = status_out;
   const long long hw = (long long)W * H;
