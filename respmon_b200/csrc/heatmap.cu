@@ -80,10 +80,13 @@ __global__ void __launch_bounds__(256) collapse_head_kernel(const HeadParams p) 
   }
 }
 
-// One unscaled pyrUp step on a stack of images: (n_img, sh, sw) -> (n_img, dh, dw), 4 outputs (a 2x2 block) per thread.
+// One unscaled pyrUp step on a stack of images: (n_img, sh, sw) -> (n_img, dh, dw).  One thread per source pixel (x, y):
+// it loads the 3x3 source neighbourhood once and produces the 2x2 outputs (2x..2x+1, 2y..2y+1) -- the horizontal taps
+// of the three rows first, then the vertical ones, in the operation order of up_at (the kernel is a stream: 1 read,
+// 4 writes per thread).
 __global__ void __launch_bounds__(256) up_level_kernel(const double* __restrict__ src, double* __restrict__ dst,
                                                        long long n_img, int sw, int sh, int dw, int dh) {
-  const long long per_img = (long long)sw * sh;        // one thread per source pixel -> outputs (2x, 2y) .. (2x+1, 2y+1)
+  const long long per_img = (long long)sw * sh;
   const long long total = n_img * per_img;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -92,13 +95,27 @@ __global__ void __launch_bounds__(256) up_level_kernel(const double* __restrict_
     const int y = r / sw, x = r - y * sw;
     const double* s = src + img * per_img;
     double* d = dst + img * (long long)dw * dh;
-#pragma unroll
-    for (int oy = 0; oy < 2; ++oy)
-#pragma unroll
-      for (int ox = 0; ox < 2; ++ox) {
-        const int X = 2 * x + ox, Y = 2 * y + oy;
-        if (X < dw && Y < dh) d[(long long)Y * dw + X] = up_at(s, sw, sh, X, Y);
-      }
+    const int xm = reflect101(x - 1, sw), xp = x + 1 < sw ? x + 1 : sw - 1;
+    const int ym = reflect101(y - 1, sh), yp = y + 1 < sh ? y + 1 : sh - 1;
+    const double* r0 = s + (long long)ym * sw;
+    const double* r1 = s + (long long)y * sw;
+    const double* r2 = s + (long long)yp * sw;
+    const double a0 = r0[xm], a1 = r0[x], a2 = r0[xp];
+    const double b0 = r1[xm], b1 = r1[x], b2 = r1[xp];
+    const double c0 = r2[xm], c1 = r2[x], c2 = r2[xp];
+    // even output column 2x: s[x-1] + 6 s[x] + s[x+1]; odd column 2x+1: 4 (s[x] + s[x+1])      (up3)
+    const double ea = fma(6.0, a1, a0 + a2), eb = fma(6.0, b1, b0 + b2), ec = fma(6.0, c1, c0 + c2);
+    const double oa = 4.0 * (a1 + a2), ob = 4.0 * (b1 + b2), oc = 4.0 * (c1 + c2);
+    const int X = 2 * x, Y = 2 * y;
+    // even output row 2y: rows y-1, y, y+1; odd row 2y+1: rows y, y+1
+    if (Y < dh) {
+      if (X < dw) d[(long long)Y * dw + X] = fma(6.0, eb, ea + ec);
+      if (X + 1 < dw) d[(long long)Y * dw + X + 1] = fma(6.0, ob, oa + oc);
+    }
+    if (Y + 1 < dh) {
+      if (X < dw) d[(long long)(Y + 1) * dw + X] = 4.0 * (eb + ec);
+      if (X + 1 < dw) d[(long long)(Y + 1) * dw + X + 1] = 4.0 * (ob + oc);
+    }
   }
 }
 
@@ -449,12 +466,15 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
 // tile's pixel range pushed up one level at a time: x at level l needs floor(x/2) - 1 .. floor(x/2) + 1 at level l+1 (the
 // border rules -- reflect-101 below, clamp above -- only ever pick indices inside that range once it is clamped to the
 // image).  One thread per (frame, tile, clip).
-__global__ void tile_bounds_kernel(const TileParams p, double2* __restrict__ out) {
+__global__ void __launch_bounds__(256) tile_bounds_kernel(const TileParams p, double2* __restrict__ out) {
+  extern __shared__ double tb_img[];   // the level-`skip` image of this (frame, clip)
   const int tiles = p.tiles_x * p.tiles_y;
-  const int clip = blockIdx.y;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)tiles * p.T;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int tile = (int)(i / p.T), t = (int)(i - (long long)tile * p.T);
+  const int clip = blockIdx.y, t = blockIdx.x;
+  const int n_top = p.top_w * p.top_h;
+  const double* a = p.a_top + ((long long)clip * p.T + t) * n_top;
+  for (int i = threadIdx.x; i < n_top; i += blockDim.x) tb_img[i] = a[i];
+  __syncthreads();
+  for (int tile = threadIdx.x; tile < tiles; tile += blockDim.x) {
     const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
     int x0 = tx * HM_TW, x1 = min(p.w[0], x0 + HM_TW) - 1, y0 = ty * HM_TH, y1 = min(p.h[0], y0 + HM_TH) - 1;
     for (int l = 0; l < p.n_up; ++l) {
@@ -463,11 +483,10 @@ __global__ void tile_bounds_kernel(const TileParams p, double2* __restrict__ out
     }
     x0 = max(x0, 0); y0 = max(y0, 0);
     x1 = min(x1, p.top_w - 1); y1 = min(y1, p.top_h - 1);
-    const double* a = p.a_top + ((long long)clip * p.T + t) * p.top_w * p.top_h;
     double lo = INFINITY, hi = -INFINITY;
     for (int y = y0; y <= y1; ++y)
       for (int x = x0; x <= x1; ++x) {
-        const double v = a[y * p.top_w + x];
+        const double v = tb_img[y * p.top_w + x];
         lo = fmin(lo, v);
         hi = fmax(hi, v);
       }
@@ -738,10 +757,11 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   tp.top_w = g.w[s];
   tp.top_h = g.h[s];
   tp.n_up = s;
-  if (!h->no_minmax_seed && (size_t)T * 5 + 32 <= 32768) {
-    const long long items = (long long)grid.x * T;
+  if (!h->no_minmax_seed && (size_t)T * 5 + 32 <= 32768 && g.w[s] * g.h[s] * 8 <= h->smem_optin) {
+    const int tb_smem = g.w[s] * g.h[s] * 8;
+    RM_CUDA(h, cudaFuncSetAttribute(tile_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tb_smem));
     RM_PROF(h, st, "tile_bounds_kernel");
-    tile_bounds_kernel<<<dim3((unsigned)((items + 255) / 256), n_clips), 256, 0, st>>>(tp, bounds);
+    tile_bounds_kernel<<<dim3(T, n_clips), 256, tb_smem, st>>>(tp, bounds);
     RM_LAUNCH_CHECK(h);
     tp.bounds = bounds;
     const int stride = T >= 8 ? 2 : 1;
