@@ -551,7 +551,7 @@ __host__ __device__ inline LkSmemLayout lk_smem_layout(int rw, int rh, int win, 
   }
   int off = 0;
   for (int l = 0; l < L.nlev; ++l) {
-    L.pitch[l] = L.lw[l] + 2 * L.pad;
+    L.pitch[l] = (L.lw[l] + 2 * L.pad + 3) & ~3;   // word-aligned rows: the pyramid build moves 4 pixels at a time
     L.off[l] = off;
     off += (L.pitch[l] * (L.lh[l] + 2 * L.pad) + 15) & ~15;
   }
@@ -795,10 +795,52 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
   auto magic_of = [](int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1u) / (unsigned)d); };
   auto refl1 = [](int v, int n) { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); };   // one reflection (n > |overhang|)
   const int nthr = LKS_WARPS * 32;
+#ifdef LK_TIMING
+  long long tb_[6] = {0, 0, 0, 0, 0, 0}, tkb_ = 0;
+#define LKTB(k) do { if (tid == 0) { long long n_ = clock64(); tb_[k] += n_ - tkb_; tkb_ = n_; } } while (0)
+#else
+#define LKTB(k) do { } while (0)
+#endif
   auto build = [&](int raw_slot, int pyr_slot) {
+#ifdef LK_TIMING
+    if (tid == 0) tkb_ = clock64();
+#endif
     const int src = raw_base + raw_slot * L.raw_bytes + xoff;
     const int base = pyr_slot * L.pyr_bytes;
-    {
+    const bool words = (L.pad & 3) == 0;           // interior columns start on a word boundary
+    if (words && rw > L.pad + 4 && rh > L.pad) {
+      // level 0, border included, one 32-bit word (4 pixels) per step: interior words are two aligned loads of the raw
+      // crop funnel-shifted to its byte offset, four LUT look-ups and one store; words that touch the left / right border
+      // take their pixels one by one through the reflection
+      const int pitch = L.pitch[0], ph = rh + 2 * L.pad, nw = pitch >> 2;
+      const unsigned mg = magic_of(nw);
+      const int total = ph * nw;
+      unsigned* dst = reinterpret_cast<unsigned*>(lks_smem + base + L.off[0]);
+      const int raw0 = raw_base + raw_slot * L.raw_bytes;   // word-aligned start of the raw rows
+#pragma unroll 2
+      for (int i = tid; i < total; i += nthr) {
+        const int py = (int)__umulhi((unsigned)i, mg), j = i - py * nw;
+        const int y = refl1(py - L.pad, rh);
+        const int x0 = 4 * j - L.pad;
+        unsigned v;
+        if (x0 >= 0 && x0 + 3 < rw) {
+          const int o = y * L.raw_pitch + xoff + x0;
+          const unsigned* wp = reinterpret_cast<const unsigned*>(lks_smem + raw0 + (o & ~3));
+          v = __funnelshift_r(wp[0], wp[1], (o & 3) * 8);
+        } else {
+          const unsigned char* row = lks_smem + raw0 + y * L.raw_pitch + xoff;
+          v = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            int x = refl1(x0 + b, rw);
+            x = x < 0 ? 0 : (x >= rw ? rw - 1 : x);            // slack columns past the padded width
+            v |= (unsigned)row[x] << (8 * b);
+          }
+        }
+        dst[py * nw + j] = (unsigned)s_lut[v & 255] | ((unsigned)s_lut[(v >> 8) & 255] << 8) |
+                           ((unsigned)s_lut[(v >> 16) & 255] << 16) | ((unsigned)s_lut[v >> 24] << 24);
+      }
+    } else {
       const int pitch = L.pitch[0], ph = rh + 2 * L.pad, pwid = rw + 2 * L.pad;
       const unsigned mg = magic_of(pwid);
       const int total = ph * pwid;
@@ -820,12 +862,39 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
       }
     }
     __syncthreads();
+    LKTB(0);
     for (int l = 1; l < L.nlev; ++l) {
       const int spitch = L.pitch[l - 1], dpitch = L.pitch[l];
       const int s0 = base + L.off[l - 1] + L.pad * spitch + L.pad;
       const int d0 = base + L.off[l] + L.pad * dpitch + L.pad;
       const int dw = L.lw[l], dh = L.lh[l];
-      {
+      if (words) {
+        // cv::pyrDown (uint8), four outputs per step: per source row four aligned words hold the 11 bytes the four
+        // 5-tap windows span (they start two bytes into the first word); the taps 1 4 6 4 are one dp4a each
+        const int qw = (dw + 3) >> 2;
+        const unsigned mg = magic_of(qw);
+        const int total = qw * dh;
+#pragma unroll 1
+        for (int i = tid; i < total; i += nthr) {
+          const int y = (int)__umulhi((unsigned)i, mg), x = 4 * (i - y * qw);
+          const unsigned* c = reinterpret_cast<const unsigned*>(lks_smem + s0 + (2 * y - 2) * spitch + 2 * x - 4);
+          int r[4][5];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const unsigned* row = c + k * (spitch >> 2);
+            const unsigned w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
+            r[0][k] = (int)__dp4a(__funnelshift_r(w0, w1, 16), 0x04060401u, (w1 >> 16) & 255u);
+            r[1][k] = (int)__dp4a(w1, 0x04060401u, w2 & 255u);
+            r[2][k] = (int)__dp4a(__funnelshift_r(w1, w2, 16), 0x04060401u, (w2 >> 16) & 255u);
+            r[3][k] = (int)__dp4a(w2, 0x04060401u, w3 & 255u);
+          }
+          unsigned out = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            out |= (unsigned)((r[q][0] + r[q][4] + 4 * (r[q][1] + r[q][3]) + 6 * r[q][2] + 128) >> 8) << (8 * q);
+          *reinterpret_cast<unsigned*>(lks_smem + d0 + y * dpitch + x) = out;   // columns past dw land in the border,
+        }                                                                         // which the next pass overwrites
+      } else {
         const unsigned mg = magic_of(dw);
         const int total = dw * dh;
 #pragma unroll 2
@@ -842,6 +911,7 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
         }
       }
       __syncthreads();
+      LKTB(l == 1 ? 1 : 3);
       {
         // border pixels only: `pad` full rows above and below, 2 * pad columns beside every image row
         const int pad = L.pad, pwid = dw + 2 * pad;
@@ -866,6 +936,7 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
         }
       }
       __syncthreads();
+      LKTB(l == 1 ? 2 : 4);
     }
   };
   auto levels = [&](int pyr_slot, LkSLevel* out) {
@@ -947,6 +1018,10 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
     long long* row = lk_timing + (clip * 8 + (blk & 7)) * 8;
     row[0] += acc_wait; row[1] += acc_build; row[2] += acc_track; row[3] += acc_book;
     row[4] += p.f1 - f_first; row[5] = s_n; row[6] = rw; row[7] = rh;
+    if (clip == 22 && blk == 0) {
+      long long* r2 = lk_timing + (63 * 8 + 7) * 8;   // spare row: build sub-phases of one big block
+      for (int q = 0; q < 5; ++q) r2[q] += tb_[q];
+    }
   }
 #endif
   if (p.st_n) {   // hand the tracker state to the next chunk

@@ -26,3 +26,6 @@ for c, b in order:
     r = a[c, b]; nf = max(r[4], 1)
     print("%3d %2d  %3d  %3dx%-3d  %9d   %6d %6d %6d %6d" % (c, b, npts[c], r[6], r[7], tot[c, b], r[0] / nf, r[1] / nf, r[2] / nf, r[3] / nf))
 print("active blocks", int((tot > 0).sum()), "median total", np.median(tot[tot > 0]))
+
+sub = a[63, 7, :5].astype(float) / max(a[22, 0, 4], 1)
+print("build sub-phases of clip 22 blk 0 (cycles/frame): L0 fill %.0f, L1 down %.0f, L1 border %.0f, L2 down %.0f, L2 border %.0f" % tuple(sub))
