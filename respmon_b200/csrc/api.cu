@@ -182,6 +182,7 @@ extern "C" int32_t rm_set_option(rm_handle* h, const char* name, int64_t value) 
   if (strcmp(name, "force_generic_front") == 0) { h->force_generic_front = value != 0; return RM_OK; }
   if (strcmp(name, "no_minmax_seed") == 0) { h->no_minmax_seed = value != 0; return RM_OK; }
   if (strcmp(name, "defer_join") == 0) { h->defer_join = value != 0; return RM_OK; }
+  if (strcmp(name, "measure_tail_frames") == 0) { h->measure_tail_frames = value < 0 ? 0 : (int)value; return RM_OK; }
   if (strcmp(name, "measure_chunks") == 0) {
     if (value < 1 || value > RM_MAX_CHUNKS) return rm_fail(h, RM_ERR_INVALID, "%s: measure_chunks must be 1..16", __func__);
     h->measure_chunks = (int)value;

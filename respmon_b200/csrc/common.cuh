@@ -32,6 +32,7 @@ struct rm_handle {
   cudaEvent_t ev_fork, ev_join, ev_chunk[RM_MAX_CHUNKS], ev_filt[RM_MAX_CHUNKS], ev_done[RM_MAX_CHUNKS];
   cudaEvent_t ev_bulk[RM_MAX_CHUNKS];        // first fit pass of the chunk finished (deferred pipeline)
   int measure_chunks;       // option "measure_chunks"
+  int measure_tail_frames;  // option "measure_tail_frames": frames of the last chunk (0: like the others)
   // Deferred join (option "defer_join"): rm_measure_signal returns without making the caller's stream wait for the
   // signal stage; rm_pack_results then runs on tail_stream behind it, and the caller's stream catches up in rm_join or
   // at the next call that reuses the handle's scratch.  Lets the next batch's calibration run under this batch's

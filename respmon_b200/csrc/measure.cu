@@ -817,7 +817,7 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
       const int total = ph * nw;
       unsigned* dst = reinterpret_cast<unsigned*>(lks_smem + base + L.off[0]);
       const int raw0 = raw_base + raw_slot * L.raw_bytes;   // word-aligned start of the raw rows
-#pragma unroll 2
+#pragma unroll 4
       for (int i = tid; i < total; i += nthr) {
         const int py = (int)__umulhi((unsigned)i, mg), j = i - py * nw;
         const int y = refl1(py - L.pad, rh);
@@ -918,7 +918,7 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
         const int n_tb = 2 * pad * pwid, total = n_tb + dh * 2 * pad;
         const unsigned mg = magic_of(pwid), mg2 = magic_of(2 * pad);
         const bool simple = dw > pad && dh > pad;
-#pragma unroll 2
+#pragma unroll 4
         for (int i = tid; i < total; i += nthr) {
           int yy, xx;
           if (i < n_tb) {
@@ -1345,9 +1345,13 @@ extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_
     int first = h->p.measure_init_len + 8;
     if (first > n_frames / n_chunks) first = n_frames / n_chunks;
     if (first < 1) first = 1;
+    // a short LAST chunk too (option "measure_tail_frames"): its fits are all that is left when the tracker ends
+    int tail = h->measure_tail_frames;
+    if (n_chunks < 3 || tail < 1 || tail > (n_frames - first) / 2) tail = 0;
+    const int mid_chunks = n_chunks - 1 - (tail ? 1 : 0), mid_frames = n_frames - first - tail;
     bounds[1] = first;
-    for (int c = 2; c <= n_chunks; ++c)
-      bounds[c] = first + (int)((long long)(n_frames - first) * (c - 1) / (n_chunks - 1));
+    for (int c = 2; c <= 1 + mid_chunks; ++c) bounds[c] = first + (int)((long long)mid_frames * (c - 1) / mid_chunks);
+    if (tail) bounds[n_chunks] = n_frames;
   }
   for (int c = 0; c < n_chunks; ++c) {
     const int f0 = bounds[c], f1 = bounds[c + 1];

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalPar
 // fits from the queue through an atomic cursor until it is empty, which balances the 10x spread in LM iterations.
 #define SIG_FIT_THREADS 128
 #ifndef SIG_FIT_G
-#define SIG_FIT_G 8
+#define SIG_FIT_G 4
 #endif
 template <int G>
 #ifndef SIG_FIT_MINB

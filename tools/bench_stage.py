@@ -13,6 +13,8 @@ engs = [Engine(0), Engine(0)] if defer else [Engine(0)]
 for e in engs:
     if os.environ.get("RM_CHUNKS"):
         e.set_option("measure_chunks", int(os.environ["RM_CHUNKS"]))
+    if os.environ.get("RM_TAIL"):
+        e.set_option("measure_tail_frames", int(os.environ["RM_TAIL"]))
     if defer:
         e.defer_join(True)
 eng = engs[0]
