@@ -31,14 +31,15 @@ __device__ __forceinline__ bool bin_kept(int j, int T, int lo, int hi) {
 }
 
 __device__ __forceinline__ void warp_fft_pow2(double2* buf, const double2* tw, int T, int logT, int lane) {
-  // in-place radix-2 DIT on bit-reversed input; tw[k] = exp(-2 pi i k / T), k < T/2
+  // in-place radix-2 DIT on bit-reversed input.  tw holds the twiddles stage by stage, stage s (half = 2^(s-1)) at
+  // tw[half - 1 + k] = exp(-2 pi i k 2^(logT - s) / T), k < half: contiguous per stage, so a warp's reads do not pile up
+  // on one bank the way a single strided table does
   for (int s = 1; s <= logT; ++s) {
     const int half = 1 << (s - 1);
-    const int tstep = T >> s;
     for (int b = lane; b < (T >> 1); b += 32) {
       int grp = b >> (s - 1), k = b & (half - 1);
       int i0 = (grp << s) + k, i1 = i0 + half;
-      double2 w = tw[k * tstep];
+      double2 w = tw[half - 1 + k];
       double2 u = buf[i0], v = buf[i1];
       double2 t = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
       buf[i0] = make_double2(u.x + t.x, u.y + t.y);
@@ -51,19 +52,24 @@ __device__ __forceinline__ void warp_fft_pow2(double2* buf, const double2* tw, i
 __global__ void __launch_bounds__(TB_WARPS * 32) temporal_pow2_kernel(const TemporalParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = p.T;
-  double2* tw = reinterpret_cast<double2*>(smem_raw);                       // T/2
-  double2* bufs = tw + (T >> 1);                                            // TB_WARPS * T
-  double* qs = reinterpret_cast<double*>(bufs + (size_t)TB_WARPS * T);      // TB_WARPS * T
+  const int TS = T + 1;   // column stride (elements): neighbouring columns start 16 B apart -> different banks
+  double2* tw = reinterpret_cast<double2*>(smem_raw);                       // T (T - 1 used): twiddles per stage
+  double2* bufs = tw + T;                                                   // TB_WARPS * TS
+  double* qs = reinterpret_cast<double*>(bufs + (size_t)TB_WARPS * TS);     // TB_WARPS * T
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = threadIdx.x; k < (T >> 1); k += blockDim.x) {
-    double s, c;
-    sincospi(2.0 * (double)k / (double)T, &s, &c);
-    tw[k] = make_double2(c, -s);
+  for (int e = threadIdx.x; e < T - 1; e += blockDim.x) {
+    // entry e = half - 1 + k of stage s: the value exp(-2 pi i (k * T / 2^s) / T) of the single-table layout
+    const int s_ = 32 - __clz(e + 1);            // stage (1-based): half = 2^(s_-1) <= e + 1 < 2^s_
+    const int half = 1 << (s_ - 1), k = e + 1 - half;
+    const int kk = k * (T >> s_);
+    double sn, cs;
+    sincospi(2.0 * (double)kk / (double)T, &sn, &cs);
+    tw[e] = make_double2(cs, -sn);
   }
   const long long groups_per_clip = (p.P + TB_WARPS - 1) / TB_WARPS;
   const long long n_groups = p.n_clips * groups_per_clip;
   const int rev_shift = 32 - p.logT;
-  double2* buf = bufs + (size_t)warp * T;
+  double2* buf = bufs + (size_t)warp * TS;
   double* q = qs + (size_t)warp * T;
   for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
     const long long clip = grp / groups_per_clip;
@@ -76,7 +82,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32) temporal_pow2_kernel(const Temp
       int t = i / TB_WARPS, c = i % TB_WARPS;
       double v = (c0 + c < p.P) ? src[(long long)t * p.P + c0 + c] : 0.0;
       int tr = (p.logT == 0) ? 0 : (int)(__brev((unsigned)t) >> rev_shift);
-      bufs[(size_t)c * T + tr] = make_double2(v, 0.0);
+      bufs[(size_t)c * TS + tr] = make_double2(v, 0.0);
     }
     __syncthreads();
     if (c0 + warp < p.P) {
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(TB_WARPS * 32) temporal_pow2_kernel(const Temp
     __syncthreads();
     for (int i = threadIdx.x; i < T * TB_WARPS; i += blockDim.x) {
       int t = i / TB_WARPS, c = i % TB_WARPS;
-      if (c0 + c < p.P) dst[(long long)t * p.P + c0 + c] = bufs[(size_t)c * T + t].x * p.inv_T * p.amp;
+      if (c0 + c < p.P) dst[(long long)t * p.P + c0 + c] = bufs[(size_t)c * TS + t].x * p.inv_T * p.amp;
     }
   }
 }
@@ -206,7 +212,7 @@ extern "C" int32_t rm_temporal_bandpass(rm_handle* h, const double* lap, double*
   const long long n_groups = (long long)n_clips * ((record_len + TB_WARPS - 1) / TB_WARPS);
   cudaStream_t st = (cudaStream_t)stream;
   if (p.logT >= 0 && T <= 2048) {
-    size_t smem = (size_t)(T >> 1) * 16 + (size_t)TB_WARPS * T * 16 + (size_t)TB_WARPS * T * 8;
+    size_t smem = (size_t)T * 16 + (size_t)TB_WARPS * (T + 1) * 16 + (size_t)TB_WARPS * T * 8;
     if ((int)smem > h->smem_optin) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: T too large for shared memory", __func__);
     RM_CUDA(h, cudaFuncSetAttribute(temporal_pow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
