@@ -113,6 +113,8 @@ int32_t rm_bgr_to_gray(rm_handle* h, const uint8_t* bgr, uint8_t* gray_out, int6
 /* ------------------------------------------------------------------ single-level ops (API parity: pyramid.py) */
 /* uint8_to_float (transforms.py:20-23): u8 -> f64 * (1/255); f32 -> f64 widening. */
 int32_t rm_to_f64(rm_handle* h, const void* src, int32_t dtype, double* dst, int64_t n, void* stream);
+/* float_to_uint8 (transforms.py:26-29): img * 255 truncated into uint8 (values in [0,1]). */
+int32_t rm_f64_to_u8(rm_handle* h, const double* src, uint8_t* dst, int64_t n, void* stream);
 /* cv2.pyrDown on float64 images (pyramid.py:14): (n_img, sh, sw) -> (n_img, (sh+1)/2, (sw+1)/2). */
 int32_t rm_pyr_down_f64(rm_handle* h, const double* src, double* dst, int64_t n_img, int32_t sw, int32_t sh, void* stream);
 /* cv2.pyrUp(src, dstsize=(dw,dh)) on float64 (pyramid.py:25, pyramid.py:55), fused with the caller's add/sub:

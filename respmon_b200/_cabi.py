@@ -60,6 +60,7 @@ SIGNATURES = {
     "rm_synth_clips": (_i32, [_H, _P, _P, _i32, _P, _S]),
     "rm_bgr_to_gray": (_i32, [_H, _P, _P, _i64, _S]),
     "rm_to_f64": (_i32, [_H, _P, _i32, _P, _i64, _S]),
+    "rm_f64_to_u8": (_i32, [_H, _P, _P, _i64, _S]),
     "rm_pyr_down_f64": (_i32, [_H, _P, _P, _i64, _i32, _i32, _S]),
     "rm_pyr_up_f64": (_i32, [_H, _P, _P, _P, _i32, _i64, _i32, _i32, _i32, _i32, _S]),
     "rm_lap_record_len": (_i32, [_H, _i32, _i32, C.POINTER(_i64)]),

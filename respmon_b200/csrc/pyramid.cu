@@ -418,6 +418,21 @@ extern "C" int32_t rm_to_f64(rm_handle* h, const void* src, int32_t dtype, doubl
   return RM_OK;
 }
 
+// float_to_uint8 (transforms.py:26-29): img * 255 stored into a uint8 array, i.e. truncated toward zero.
+__global__ void f64_to_u8_kernel(const double* __restrict__ src, uint8_t* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = (uint8_t)(int)(src[i] * 255.0);
+}
+extern "C" int32_t rm_f64_to_u8(rm_handle* h, const double* src, uint8_t* dst, int64_t n, void* stream) {
+  RM_CHECK_ARG(h, h && src && dst && n >= 0, "null pointer or negative size");
+  if (n == 0) return RM_OK;
+  DeviceGuard dg(h->device);
+  RM_PROF(h, (cudaStream_t)stream, "f64_to_u8_kernel");
+  f64_to_u8_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+  RM_LAUNCH_CHECK(h);
+  return RM_OK;
+}
+
 extern "C" int32_t rm_pyr_down_f64(rm_handle* h, const double* src, double* dst, int64_t n_img, int32_t sw, int32_t sh,
                                    void* stream) {
   RM_CHECK_ARG(h, h && src && dst && n_img >= 0 && sw >= 1 && sh >= 1, "null pointer or bad size");

@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalPar
 // a warp works on one fit, so its lanes never diverge (with several fits per warp every group's instruction stream
 // is issued separately and the warp runs the SUM of its groups' iterations).  The grid is persistent: warps pull
 // fits from the queue through an atomic cursor until it is empty, which balances the 10x spread in LM iterations.
+#ifndef SIG_FIT_THREADS
 #define SIG_FIT_THREADS 128
+#endif
 #ifndef SIG_FIT_G
 #define SIG_FIT_G 4
 #endif

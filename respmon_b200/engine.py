@@ -162,6 +162,14 @@ class Engine:
         self._call("rm_to_f64", _ptr(x), _DTYPES[x.dtype], _ptr(out), x.numel(), self._stream())
         return out
 
+    def to_u8(self, x: torch.Tensor) -> torch.Tensor:
+        """float_to_uint8 (transforms.py:26-29): float64 in [0,1] -> x*255 truncated, on the device."""
+        assert x.is_cuda and x.dtype == torch.float64
+        x = x.contiguous()
+        out = torch.empty(x.shape, dtype=torch.uint8, device=self.device)
+        self._call("rm_f64_to_u8", _ptr(x), _ptr(out), x.numel(), self._stream())
+        return out
+
     def pyr_down(self, x: torch.Tensor) -> torch.Tensor:
         """(..., h, w) float64 -> (..., (h+1)//2, (w+1)//2)   [cv2.pyrDown, pyramid.py:14]"""
         x = x.contiguous()

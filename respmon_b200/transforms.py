@@ -16,18 +16,19 @@ from . import _cabi
 from .pyramid import _collapse, _dev, _laplacian_levels, default_engine
 
 
-def uint8_to_float(img):
-    """transforms.py:20-23: float64 copy scaled by 1/255 (a cast and one multiply: host numpy, as in the reference)."""
-    result = np.ndarray(shape=img.shape, dtype='float')
-    result[:] = img * (1. / 255)
-    return result
+def uint8_to_float(img, engine=None):
+    """transforms.py:20-23: float64 copy scaled by 1/255 (rm_to_f64)."""
+    eng = engine or default_engine()
+    a = np.ascontiguousarray(img)
+    if a.dtype != np.uint8:
+        raise TypeError("uint8_to_float expects a uint8 image (frames as cap.read() yields them, base.py:229-231)")
+    return eng.to_f64(torch.from_numpy(a).to(eng.device)).cpu().numpy()
 
 
-def float_to_uint8(img):
-    """transforms.py:26-29: img*255 stored into a uint8 array (truncation)."""
-    result = np.ndarray(shape=img.shape, dtype='uint8')
-    result[:] = img * 255
-    return result
+def float_to_uint8(img, engine=None):
+    """transforms.py:26-29: img*255 stored into a uint8 array (truncation; rm_f64_to_u8)."""
+    eng = engine or default_engine()
+    return eng.to_u8(_dev(img, eng)).cpu().numpy()
 
 
 def butter_lowpass(cutoff, fs, order=5):
