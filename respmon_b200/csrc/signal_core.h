@@ -48,6 +48,23 @@ RM_HD void sc_lfilter(const double* b, const double* a, int nc, double* x, int n
     x[i] = yi;
   }
 }
+// the same with the order known at compile time: the state lives in registers and the tap loop unrolls (same operations)
+template <int NC>
+RM_HD void sc_lfilter_n(const double* b, const double* a, double* x, int n, double* zin) {
+  double z[NC - 1], bb[NC], aa[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) { bb[k] = b[k]; aa[k] = a[k]; }
+#pragma unroll
+  for (int k = 0; k < NC - 1; ++k) z[k] = zin[k];
+  for (int i = 0; i < n; ++i) {
+    const double xi = x[i];
+    const double yi = z[0] + bb[0] * xi;
+#pragma unroll
+    for (int k = 0; k < NC - 2; ++k) z[k] = z[k + 1] + bb[k + 1] * xi - aa[k + 1] * yi;
+    z[NC - 2] = bb[NC - 1] * xi - aa[NC - 1] * yi;
+    x[i] = yi;
+  }
+}
 // filtfilt(b, a, x) with SciPy defaults: odd extension by padlen = 3*nc, zi * first sample, forward, reverse, forward.
 // `ext` is scratch of n + 2*padlen doubles; returns 0, or -1 when n <= padlen (SciPy raises ValueError).
 RM_HD int sc_filtfilt(const double* b, const double* a, int nc, const double* x, int n, double* y, double* ext) {
@@ -60,10 +77,12 @@ RM_HD int sc_filtfilt(const double* b, const double* a, int nc, const double* x,
   double zi[SC_MAX_ORDER + 1], z[SC_MAX_ORDER + 1];
   sc_lfilter_zi(b, a, nc, zi);
   for (int k = 0; k < nc - 1; ++k) z[k] = zi[k] * ext[0];
-  sc_lfilter(b, a, nc, ext, ne, z);
+  if (nc == 4) sc_lfilter_n<4>(b, a, ext, ne, z);          // the reference's filter_order = 3 (base.py:101)
+  else sc_lfilter(b, a, nc, ext, ne, z);
   for (int i = 0; i < ne / 2; ++i) { double t = ext[i]; ext[i] = ext[ne - 1 - i]; ext[ne - 1 - i] = t; }
   for (int k = 0; k < nc - 1; ++k) z[k] = zi[k] * ext[0];
-  sc_lfilter(b, a, nc, ext, ne, z);
+  if (nc == 4) sc_lfilter_n<4>(b, a, ext, ne, z);
+  else sc_lfilter(b, a, nc, ext, ne, z);
   for (int i = 0; i < n; ++i) y[i] = ext[ne - 1 - pad - i];
   return 0;
 }
