@@ -65,12 +65,17 @@ __global__ void roi_merge_kernel(const RoiParams p) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
     if (L[i] < 0) continue;
     const int x = (int)(i % p.W), y = (int)(i / p.W);
-    if (x > 0 && L[i - 1] >= 0) uf_union(L, (int)i, (int)i - 1);
-    if (y > 0) {
-      const long long up = i - p.W;
-      if (L[up] >= 0) uf_union(L, (int)i, (int)up);
-      if (x > 0 && L[up - 1] >= 0) uf_union(L, (int)i, (int)up - 1);
-      if (x + 1 < p.W && L[up + 1] >= 0) uf_union(L, (int)i, (int)up + 1);
+    // 8-connectivity with the redundant unions left out: a foreground pixel above is adjacent to the left, upper-left and
+    // upper-right neighbours, which join it through their own unions; likewise the left neighbour covers the upper-left
+    const long long up = i - p.W;
+    const bool f_left = x > 0 && L[i - 1] >= 0;
+    const bool f_up = y > 0 && L[up] >= 0;
+    if (f_up) {
+      uf_union(L, (int)i, (int)up);
+    } else {
+      if (f_left) uf_union(L, (int)i, (int)i - 1);
+      else if (y > 0 && x > 0 && L[up - 1] >= 0) uf_union(L, (int)i, (int)up - 1);
+      if (y > 0 && x + 1 < p.W && L[up + 1] >= 0) uf_union(L, (int)i, (int)up + 1);
     }
   }
 }
