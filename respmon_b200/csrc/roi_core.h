@@ -30,15 +30,24 @@ ROI_HD RoiTrace roi_trace_outer(int sx, int sy, Fg fg, int max_steps) {
   r.x0 = r.x1 = sx;
   r.y0 = r.y1 = sy;
   r.steps = 0;
+  // The 8 neighbours of the current pixel are probed together (independent loads, one round trip) into a bit mask, bit k
+  // = direction k; the direction searches below then run on the mask.
+  auto mask8 = [&](int x, int y) {
+    unsigned m = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < 8; ++k) m |= (fg(x + dx[k], y + dy[k]) ? 1u : 0u) << k;
+    return m;
+  };
   // first non-zero neighbour clockwise from W
   int s = 4;
   int x1 = sx, y1 = sy;
   bool found = false;
+  unsigned m = mask8(sx, sy);
   for (int k = 0; k < 7; ++k) {
     s = (s - 1) & 7;
-    x1 = sx + dx[s];
-    y1 = sy + dy[s];
-    if (fg(x1, y1)) { found = true; break; }
+    if ((m >> s) & 1u) { x1 = sx + dx[s]; y1 = sy + dy[s]; found = true; break; }
   }
   if (!found) return r;   // isolated pixel: area 0, bbox 1x1
   int x3 = sx, y3 = sy;
@@ -49,10 +58,10 @@ ROI_HD RoiTrace roi_trace_outer(int sx, int sy, Fg fg, int max_steps) {
     int x4, y4;
     for (;;) {   // next border pixel counter-clockwise
       s = (s + 1) & 7;
-      x4 = x3 + dx[s];
-      y4 = y3 + dy[s];
-      if (fg(x4, y4)) break;
+      if ((m >> s) & 1u) break;
     }
+    x4 = x3 + dx[s];
+    y4 = y3 + dy[s];
     if (have) acc += (long long)px * y3 - (long long)py * x3;
     else { fx = x3; fy = y3; have = true; }
     px = x3; py = y3;
@@ -62,6 +71,7 @@ ROI_HD RoiTrace roi_trace_outer(int sx, int sy, Fg fg, int max_steps) {
     if ((x4 == sx && y4 == sy && x3 == x1 && y3 == y1) || r.steps >= max_steps) break;
     x3 = x4; y3 = y4;
     s = (s + 4) & 7;
+    m = mask8(x3, y3);
   }
   acc += (long long)px * fy - (long long)py * fx;   // close the polygon
   r.area2 = acc < 0 ? -acc : acc;
