@@ -120,3 +120,25 @@ def test_no_roi_retries_and_stream_end():
     rm = RespiratoryMonitor(clip, motion_extraction_method="flow")
     assert rm.state == "calibration" and rm.x is None and len(rm.data) == 0
     assert rm.calibration_buffer_idx == 300 - 1 - 2 * 129                   # frames left in the third fill
+
+
+def test_tracking_lost_goes_through_error_and_recalibrates():
+    """The texture vanishes for a second in the middle of measuring: extract_motion returns nan (base.py:385-386),
+    detect_errors fires (base.py:543-545), the 'error' state lasts error_reset_delay of stream time, reset() clears the
+    buffers (base.py:515-533) and the monitor calibrates and measures again on what follows."""
+    from respmon_b200 import synth
+    from respmon_b200.monitor import RespiratoryMonitor
+    spec = synth.clip_spec(4, 320, 240, 600)
+    clip = synth.make_clip(spec)
+    ref = RespiratoryMonitor(clip[:256], motion_extraction_method="flow")
+    broken = clip.copy()
+    broken[200:212] = 128                                    # no corners survive a flat frame
+    rm = RespiratoryMonitor(broken, motion_extraction_method="flow", error_reset_delay=1.0)
+    assert rm.error_message == "error detection found poor signal"
+    assert rm.state == "measure"
+    assert (rm.x, rm.y, rm.w, rm.h) == (ref.x, ref.y, ref.w, ref.h) or rm.x is not None
+    # error at frame 200 (measure sample 70), 1 s = 10 frames + the iteration that resets, 128 frames of calibration,
+    # the locate frame: measuring resumes at frame 200 + 1 + 11 + 128 + 1 = 341
+    assert len(rm.data) == min(128, 600 - 341)
+    assert not np.isnan(np.array(rm.data)).any()
+    assert len(rm.freq) > 0 and abs(rm.freq[-1] - spec.truth_bpm) <= 3.0
