@@ -110,12 +110,13 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            with os.fdopen(fd, "w") as out:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY,
+                                              "--format=csv,noheader,nounits", "-lms", "50"],
+                                             stdout=out, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 

@@ -136,7 +136,7 @@ def test_tracking_lost_goes_through_error_and_recalibrates():
     rm = RespiratoryMonitor(broken, motion_extraction_method="flow", error_reset_delay=1.0)
     assert rm.error_message == "error detection found poor signal"
     assert rm.state == "measure"
-    assert (rm.x, rm.y, rm.w, rm.h) == (ref.x, ref.y, ref.w, ref.h) or rm.x is not None
+    assert rm.x is not None and ref.x is not None            # both runs found a ROI (not necessarily the same window)
     # error at frame 200 (measure sample 70), 1 s = 10 frames + the iteration that resets, 128 frames of calibration,
     # the locate frame: measuring resumes at frame 200 + 1 + 11 + 128 + 1 = 341
     assert len(rm.data) == min(128, 600 - 341)
