@@ -56,6 +56,25 @@ __device__ __forceinline__ double up_at(const double* s, int sw, int sh, int x, 
   return up3(ty.odd, h0, h1, h2);
 }
 
+// Level-2 value (X, Y) from a patch of the level-3 image, in the operation order of up_level_kernel (one unscaled pyrUp
+// step): `s3` holds the level-3 rows y3lo.. and columns x3lo.. with pitch pw3; w3 x h3 is the full level-3 size (the
+// border rules refer to it).  Bit-identical to the materialised level 2.
+__device__ __forceinline__ double a2_value(const double* s3, int pw3, int x3lo, int y3lo, int w3, int h3, int X, int Y) {
+  const int x = X >> 1, y = Y >> 1;
+  const int xm = reflect101(x - 1, w3) - x3lo, xp = (x + 1 < w3 ? x + 1 : w3 - 1) - x3lo, xc = x - x3lo;
+  const int ym = reflect101(y - 1, h3) - y3lo, yp = (y + 1 < h3 ? y + 1 : h3 - 1) - y3lo, yc = y - y3lo;
+  const double* r0 = s3 + ym * pw3;
+  const double* r1 = s3 + yc * pw3;
+  const double* r2 = s3 + yp * pw3;
+  double ha, hb, hc;
+  if (X & 1) {
+    ha = 4.0 * (r0[xc] + r0[xp]); hb = 4.0 * (r1[xc] + r1[xp]); hc = 4.0 * (r2[xc] + r2[xp]);
+  } else {
+    ha = fma(6.0, r0[xc], r0[xm] + r0[xp]); hb = fma(6.0, r1[xc], r1[xm] + r1[xp]); hc = fma(6.0, r2[xc], r2[xm] + r2[xp]);
+  }
+  return (Y & 1) ? 4.0 * (hb + hc) : fma(6.0, hb, ha + hc);
+}
+
 __global__ void __launch_bounds__(256) collapse_head_kernel(const HeadParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* a = reinterpret_cast<double*>(smem_raw);
@@ -136,6 +155,8 @@ struct TileParams {
   double threshold;        // temporal_threshold (pass 2)
   double* avg_out;         // (n_clips, H, W) pass 2
   const double2* bounds;   // (n_clips, tiles, T) smallest / largest level-`skip` value each tile-frame depends on, or null
+  const double* a3;        // lazy level 2: (n_clips, T, h3 * w3) level-3 images (unscaled), or null -> a2 is materialised
+  int w3, h3;
   const double* a_top;     // (n_clips, T, h_top * w_top) level `skip` images (tile_bounds_kernel)
   int top_w, top_h, n_up;  // their size; number of pyrUp steps from there to level 0
 };
@@ -226,8 +247,9 @@ __device__ __forceinline__ void block4x4(const double v[4][4], const AxisGeom& g
 #define HM_PH 11            // 32/4 + 3 rows
 #define HM_COPIES 2         // ceil(19 * 11 / 128) cp.async per thread per frame
 template <int PASS, bool EDGE>
+#define HM_P3 96            // level-3 patch of a tile: at most 12 x 8 values
 __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* red_a, double* red_b, double* stage,
-                                                   int* frame_list) {
+                                                   double* stage3, int* frame_list) {
   const int tile = blockIdx.x;
   const int tx = tile % p.tiles_x, ty = tile / p.tiles_x;
   const int clip = blockIdx.y;
@@ -329,16 +351,34 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
 #pragma unroll
     for (int c = 0; c < 4; ++c) offs[r][c] = (gy.v[r] - ylo) * HM_PW + (gx.v[c] - xlo);
   const unsigned stage_base = (unsigned)__cvta_generic_to_shared(stage);
+  // Lazy level 2 (p.a3 != null): only the tile-frames that are evaluated at all need their level-2 patch, so level 2 is
+  // not materialised; the ring stages the level-3 patch (at most 12 x 8 values) and the block expands it into the patch
+  // buffer with up_level_kernel's arithmetic -- one more barrier per evaluated frame, one 1.3 GB array less.
+  const bool lazy = p.a3 != nullptr;
+  const int x3lo = lazy ? max(0, (xlo >> 1) - 1) : 0, x3hi = lazy ? min(p.w3 - 1, (xhi >> 1) + 1) : 0;
+  const int y3lo = lazy ? max(0, (ylo >> 1) - 1) : 0, y3hi = lazy ? min(p.h3 - 1, (yhi >> 1) + 1) : 0;
+  const int pw3 = x3hi - x3lo + 1, n3 = pw3 * (y3hi - y3lo + 1);
+  const long long n3img = (long long)p.w3 * p.h3;
+  const int src3 = (lazy && tid < n3) ? (y3lo + tid / pw3) * p.w3 + x3lo + tid % pw3 : -1;
+  const unsigned stage3_base = (unsigned)__cvta_generic_to_shared(stage3);
   auto issue = [&](int k) {
     if (k < n_list) {
       const int t = p.bounds ? frame_list[k] : k;
-      const double* l2 = a_clip + t * n2;
-      const unsigned dst = stage_base + (unsigned)((k % HM_STAGES) * HM_PW * HM_PH * 8);
+      if (lazy) {
+        if (src3 >= 0) {
+          const double* l3 = p.a3 + ((long long)clip * p.T + t) * n3img;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(stage3_base + (unsigned)(((k % HM_STAGES) * HM_P3 + tid) * 8)),
+                       "l"(l3 + src3) : "memory");
+        }
+      } else {
+        const double* l2 = a_clip + t * n2;
+        const unsigned dst = stage_base + (unsigned)((k % HM_STAGES) * HM_PW * HM_PH * 8);
 #pragma unroll
-      for (int c = 0; c < HM_COPIES; ++c)
-        if (src_off[c] >= 0)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + dst_off[c] * 8), "l"(l2 + src_off[c])
-                       : "memory");
+        for (int c = 0; c < HM_COPIES; ++c)
+          if (src_off[c] >= 0)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst + dst_off[c] * 8), "l"(l2 + src_off[c])
+                         : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
@@ -366,8 +406,20 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
       asm volatile("cp.async.wait_group %0;\n" ::"n"(HM_STAGES - 2) : "memory");
       __syncthreads();                 // frame t has landed for everyone; everyone is done with frame t-1's stage
       issue(t + HM_STAGES - 1);        // refills the stage frame t-1 used
+      if (lazy) {                      // expand the level-3 patch of this frame into the level-2 patch buffer (slot 0)
+        const double* s3 = stage3 + (t % HM_STAGES) * HM_P3;
+#pragma unroll
+        for (int c = 0; c < HM_COPIES; ++c) {
+          const int e = tid + c * 128;
+          if (e < n_patch) {
+            const int r = e / pwid, cc = e - r * pwid;
+            stage[r * HM_PW + cc] = a2_value(s3, pw3, x3lo, y3lo, p.w3, p.h3, xlo + cc, ylo + r);
+          }
+        }
+        __syncthreads();               // the patch is complete (the barrier above keeps the previous frame's readers out)
+      }
       if (!active) continue;
-      const double* l2 = stage + (t % HM_STAGES) * HM_PW * HM_PH;
+      const double* l2 = lazy ? stage : stage + (t % HM_STAGES) * HM_PW * HM_PH;
       double v[4][4], o[4][4];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -501,12 +553,16 @@ __global__ void __launch_bounds__(256) tile_bounds_kernel(const TileParams p, do
 __global__ void __launch_bounds__(256) minmax_seed_kernel(const TileParams p, int frame_stride) {
   const int clip = blockIdx.y, t = blockIdx.x * frame_stride, tid = threadIdx.x;
   if (t >= p.T) return;
-  const int n2 = p.w[2] * p.h[2];
-  const double* l2 = p.a2 + ((long long)clip * p.T + t) * n2;
+  // the extremes are located on level 2 when it is materialised, else on level 3 (lazy level 2): any block evaluated
+  // exactly seeds valid bounds, the choice only affects how tight they are
+  const bool lazy = p.a3 != nullptr;
+  const int sw = lazy ? p.w3 : p.w[2], sh = lazy ? p.h3 : p.h[2];
+  const int n_src = sw * sh;
+  const double* src = (lazy ? p.a3 : p.a2) + ((long long)clip * p.T + t) * n_src;
   double vmx = -INFINITY, vmn = INFINITY;
   int imx = 0, imn = 0;
-  for (int i = tid; i < n2; i += 256) {
-    const double v = l2[i];
+  for (int i = tid; i < n_src; i += 256) {
+    const double v = src[i];
     if (v > vmx) { vmx = v; imx = i; }
     if (v < vmn) { vmn = v; imn = i; }
   }
@@ -530,12 +586,17 @@ __global__ void __launch_bounds__(256) minmax_seed_kernel(const TileParams p, in
       const double v = tid == 0 ? s_mx[w] : s_mn[w];
       if (tid == 0 ? v > best : v < best) { best = v; idx = tid == 0 ? s_imx[w] : s_imn[w]; }
     }
-    const int i2x = idx % p.w[2], i2y = idx / p.w[2];
+    int i2x = idx % sw, i2y = idx / sw;
+    if (lazy) {    // level-3 position -> the level-2 sample on top of it
+      i2x = min(2 * i2x, p.w[2] - 1);
+      i2y = min(2 * i2y, p.h[2] - 1);
+    }
     const int X0 = 4 * i2x, Y0 = 4 * i2y;
     const AxisGeom gx = axis_geom(i2x, p.w[1], p.w[2]), gy = axis_geom(i2y, p.h[1], p.h[2]);
     double v[4][4], o[4][4];
     for (int r = 0; r < 4; ++r)
-      for (int c = 0; c < 4; ++c) v[r][c] = l2[gy.v[r] * p.w[2] + gx.v[c]];
+      for (int c = 0; c < 4; ++c)
+        v[r][c] = lazy ? a2_value(src, p.w3, 0, 0, p.w3, p.h3, gx.v[c], gy.v[r]) : src[gy.v[r] * p.w[2] + gx.v[c]];
     block4x4<true>(v, gx, gy, o);
     double vmin = INFINITY, vmax = -INFINITY;
     for (int ky = 0; ky < 4; ++ky)
@@ -555,9 +616,10 @@ __global__ void __launch_bounds__(128) upsample_pass_kernel(const TileParams p) 
   const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
   // tiles that touch the right / bottom image border (or an unaligned row) take the guarded variant
   const bool edge = (tx + 1) * HM_TW >= p.w[0] || (ty + 1) * HM_TH >= p.h[0] || (p.w[0] & 1);
+  __shared__ __align__(16) double stage3[HM_STAGES * HM_P3];
   extern __shared__ int frame_list_smem[];   // pass 1: T ints
-  if (edge) upsample_pass_body<PASS, true>(p, red_a, red_b, stage, frame_list_smem);
-  else upsample_pass_body<PASS, false>(p, red_a, red_b, stage, frame_list_smem);
+  if (edge) upsample_pass_body<PASS, true>(p, red_a, red_b, stage, stage3, frame_list_smem);
+  else upsample_pass_body<PASS, false>(p, red_a, red_b, stage, stage3, frame_list_smem);
 }
 
 __global__ void minmax_init_kernel(unsigned long long* keys, int n_clips) {
@@ -722,7 +784,10 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   RM_PROF(h, st, "collapse_head_kernel");
   collapse_head_kernel<<<(unsigned)hgrid, 256, head_smem, st>>>(hp);
   RM_LAUNCH_CHECK(h);
-  for (int l = s - 1; l >= 2; --l) {   // A_{l+1} -> A_l, unscaled
+  // pruning (and with it the lazy level 2) needs the frame list to fit in shared memory and level 4 in one block
+  const bool prune = !h->no_minmax_seed && (size_t)T * 5 + 32 <= 32768 && g.w[s] * g.h[s] * 8 <= h->smem_optin;
+  const bool lazy_l2 = prune && s >= 3;   // level 2 is expanded per evaluated tile-frame from level 3
+  for (int l = s - 1; l >= (lazy_l2 ? 3 : 2); --l) {   // A_{l+1} -> A_l, unscaled
     const long long total = n_frames * g.w[l + 1] * g.h[l + 1];
     const long long blocks = (total + 255) / 256;
     const long long cap = (long long)h->sm_count * 32;
@@ -757,7 +822,12 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   tp.top_w = g.w[s];
   tp.top_h = g.h[s];
   tp.n_up = s;
-  if (!h->no_minmax_seed && (size_t)T * 5 + 32 <= 32768 && g.w[s] * g.h[s] * 8 <= h->smem_optin) {
+  if (lazy_l2) {
+    tp.a3 = a_lvl[3];
+    tp.w3 = g.w[3];
+    tp.h3 = g.h[3];
+  }
+  if (prune) {
     const int tb_smem = g.w[s] * g.h[s] * 8;
     RM_CUDA(h, cudaFuncSetAttribute(tile_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tb_smem));
     RM_PROF(h, st, "tile_bounds_kernel");
