@@ -721,12 +721,22 @@ extern "C" int32_t rm_volume_clip_mean(rm_handle* h, const double* raw, double* 
 }
 
 // ---------------------------------------------------------------------------------------------------- host side
+// Pruning (and with it the lazy level 2) needs the frame list to fit in shared memory and level `s` in one block.
+static bool heatmap_prunes(const rm_handle* h, const LevelGeom& g, int T, int s) {
+  return !h->no_minmax_seed && s < g.n_levels && (size_t)T * 5 + 32 <= 32768 && g.w[s] * g.h[s] * 8 <= h->smem_optin;
+}
+// Lowest level that is materialised: 3 when the passes expand level 2 themselves, else 2.
+static int heatmap_lowest_level(const rm_handle* h, const LevelGeom& g, int T, int s) {
+  return (heatmap_prunes(h, g, T, s) && s >= 3) ? 3 : 2;
+}
+
 extern "C" int32_t rm_heatmap_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n_clips, int32_t T, size_t* out) {
   RM_CHECK_ARG(h, h && out && W >= 1 && H >= 1 && n_clips >= 0 && T >= 1, "null pointer or bad size");
   LevelGeom g = make_geom(W, H, h->p.pyramid_levels);
   const int s = h->p.skip_levels_at_top;
-  size_t a = 0;                                                // A_s .. A_2
-  for (int l = 2; l <= s && l < g.n_levels; ++l) a += (((size_t)n_clips * T * g.w[l] * g.h[l] * 8) + 255) & ~(size_t)255;
+  size_t a = 0;                                                // A_s .. A_lowest (depends on the "no_minmax_seed" option)
+  for (int l = heatmap_lowest_level(h, g, T, s); l <= s && l < g.n_levels; ++l)
+    a += (((size_t)n_clips * T * g.w[l] * g.h[l] * 8) + 255) & ~(size_t)255;
   size_t avg = (size_t)n_clips * W * H * 8;                    // time average
   size_t keys = ((size_t)n_clips * 4 * 8 + 255) & ~(size_t)255;
   const size_t tiles = (size_t)((W + HM_TW - 1) / HM_TW) * ((H + HM_TH - 1) / HM_TH);
@@ -753,7 +763,10 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   RecordGeom rec = make_record(g, s);
   uintptr_t base = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
   double* a_lvl[RM_MAX_LEVELS] = {nullptr};
-  for (int l = s; l >= 2; --l) {
+  const bool prune = heatmap_prunes(h, g, T, s);
+  const int lowest = heatmap_lowest_level(h, g, T, s);
+  const bool lazy_l2 = lowest == 3;     // level 2 is expanded per evaluated tile-frame from level 3
+  for (int l = s; l >= lowest; --l) {
     a_lvl[l] = reinterpret_cast<double*>(base);
     base += ((size_t)n_clips * T * g.w[l] * g.h[l] * 8 + 255) & ~(size_t)255;
   }
@@ -784,10 +797,7 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   RM_PROF(h, st, "collapse_head_kernel");
   collapse_head_kernel<<<(unsigned)hgrid, 256, head_smem, st>>>(hp);
   RM_LAUNCH_CHECK(h);
-  // pruning (and with it the lazy level 2) needs the frame list to fit in shared memory and level 4 in one block
-  const bool prune = !h->no_minmax_seed && (size_t)T * 5 + 32 <= 32768 && g.w[s] * g.h[s] * 8 <= h->smem_optin;
-  const bool lazy_l2 = prune && s >= 3;   // level 2 is expanded per evaluated tile-frame from level 3
-  for (int l = s - 1; l >= (lazy_l2 ? 3 : 2); --l) {   // A_{l+1} -> A_l, unscaled
+  for (int l = s - 1; l >= lowest; --l) {   // A_{l+1} -> A_l, unscaled
     const long long total = n_frames * g.w[l + 1] * g.h[l + 1];
     const long long blocks = (total + 255) / 256;
     const long long cap = (long long)h->sm_count * 32;

@@ -17,6 +17,8 @@ What differs, deliberately:
     iteration that runs `locate`, every later frame measured, windows rolled at 128;
   * the UI (pyqtgraph), `time.sleep` pacing and the .avi writer are out of scope:
     `visualize` must be None, pacing is a no-op, `save_all_data` keeps `all_data` and writes the `.npy` only;
+    `save_calibration_image` writes the same calibrationN.png as base.py:577-596 (panels from the device, drawing and
+    file output through cv2, imported only then);
   * the error state (base.py:496-500) waits `error_reset_delay` seconds of *stream* time (delay * fps frames), then
     recalibrates; the reference's `reset()` dereferences `self.ui` and so crashes when `visualize=None` (App. B.8).
 """
@@ -24,6 +26,7 @@ from __future__ import annotations
 
 import logging
 import math
+import os
 import time
 from collections import deque
 
@@ -92,6 +95,43 @@ class _ArrayCapture:
 
     def release(self):
         pass
+
+
+def calibration_mosaic(eng, vid, fps, heat, box, threshold):
+    """The 2x3 diagnostic mosaic of locate(save_calibration_image=True) (base.py:577-592) as a (2H, 3W) uint8 array:
+    row 0 = mean calibration frame | normalised mean of the unclipped magnified video | heat map,
+    row 1 = thresholded heat map | mean frame with all contours drawn | mean frame + heat map with the ROI box.
+    vid (T,H,W) device tensor (uint8 or float in [0,1]); heat (H,W) uint8 device tensor from the same frames.
+    The three averaged panels come from the device (`rm_to_f64`, `rm_volume_clip_mean`, `rm_f64_to_u8`, and the
+    calibration kernels run once more with the temporal clipping switched off); drawing is cv2's, as in the reference."""
+    frames = vid if vid.dtype == torch.float64 else eng.to_f64(vid)       # uint8_to_float (transforms.py:20-23)
+    _, mean_frame, _ = eng.volume_clip_mean(frames.contiguous(), want_clipped=False)       # base.py:579, :588
+    total_avg = eng.to_u8(mean_frame).cpu().numpy()
+    # `raw` (transforms.py:182-183) is the magnified video before `>= top -> min`; with temporal_threshold = -1 the cut
+    # `top = max + (max - min)` lies above every value, so the same kernels produce its normalised time average
+    hyper = {name: getattr(eng.params, name) for name, _ in eng.params._fields_}
+    raw_eng = Engine(eng.device_index, **dict(hyper, temporal_threshold=-1.0))
+    try:
+        with torch.cuda.device(eng.device):
+            avg_raw = raw_eng.calibrate_heatmaps(vid[None].contiguous(), fps)[0][0].cpu().numpy()   # base.py:585-587
+    finally:
+        raw_eng.close()
+    return compose_mosaic(total_avg, avg_raw, heat.cpu().numpy(), box, threshold)
+
+
+def compose_mosaic(total_avg, avg_raw, avg, box, threshold):
+    """Host half of the mosaic (base.py:566-568, 580-592): threshold panel, contour and box drawing (cv2, as in the
+    reference) and the 2x3 layout, from the three (H,W) uint8 panels the device produced."""
+    import cv2
+    x, y, w, h = box
+    thresh = np.where(avg > threshold, 255, 0).astype(np.uint8)                            # base.py:566 (THRESH_BINARY)
+    contours = cv2.findContours(thresh.copy(), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)[-2]
+    contour_img = total_avg.copy()
+    cv2.drawContours(contour_img, contours, -1, (0, 255, 0), 3)                            # base.py:581
+    drawn = cv2.rectangle(total_avg + avg, (x, y), (x + w, y + h), 255, 2)                 # base.py:583 (uint8 wrap)
+    row0 = np.hstack((total_avg, avg_raw, avg))
+    row1 = np.hstack((thresh, contour_img, drawn))
+    return np.vstack((row0, row1))
 
 
 class RespiratoryMonitor:
@@ -289,22 +329,31 @@ class RespiratoryMonitor:
         uint8, or a device tensor of either.  Returns (x, y, w, h) or None."""
         if threshold_type != 0:
             raise NotImplementedError("only cv2.THRESH_BINARY (0) is implemented")
-        if save_calibration_image:
-            raise NotImplementedError("the calibration PNG mosaic (base.py:577-596) is diagnostic output, out of scope")
-        eng = engine or Engine(None, freq_min=freq_min, freq_max=freq_max, amplification=amplification,
-                               pyramid_levels=pyramid_levels, skip_levels_at_top=skip_levels_at_top,
-                               temporal_threshold=temporal_threshold, threshold=int(threshold))
+        hyper = dict(freq_min=freq_min, freq_max=freq_max, amplification=amplification, pyramid_levels=pyramid_levels,
+                     skip_levels_at_top=skip_levels_at_top, temporal_threshold=temporal_threshold,
+                     threshold=int(threshold))
+        eng = engine or Engine(None, **hyper)
         vid = calibration_video_data
         vid = torch.from_numpy(np.ascontiguousarray(vid)) if isinstance(vid, np.ndarray) else vid
         vid = vid.to(eng.device)
         if vid.dtype not in (torch.uint8, torch.float32, torch.float64):
             raise TypeError("calibration_video_data must be uint8 / float32 / float64")
-        roi, status, _ = eng.locate(vid[None].contiguous(), float(fps))
+        roi, status, heat = eng.locate(vid[None].contiguous(), float(fps))
         if verbose:
             print("roi", roi.cpu().numpy()[0], "status", int(status[0]))
         if int(status[0]) != 0:
             return None
-        return tuple(int(v) for v in roi[0].cpu())
+        box = tuple(int(v) for v in roi[0].cpu())
+        if save_calibration_image:
+            _log.info("Creating calibration image.")
+            mosaic = calibration_mosaic(eng, vid, float(fps), heat[0], box, int(eng.params.threshold))
+            import cv2   # file output and drawing only; the panels themselves are computed on the device
+            i = 0
+            while os.path.exists("calibration%s.png" % i):       # base.py:593-595
+                i += 1
+            cv2.imwrite("calibration%s.png" % i, mosaic)
+            _log.info("Calibration image saved.")
+        return box
 
     def calibrate(self, frames=None):
         """The calibration branch of run() (base.py:436-463) on a (128,H,W) window (default: the next 128 frames of
@@ -322,7 +371,8 @@ class RespiratoryMonitor:
         self.detect_fps()
         self.peak_minimum_sample_distance = int(np.floor(self.fps / self.freq_max))
         self.benchmarker.tick_start('Calibration Measurement')
-        location = self.locate(frames, self.fps, freq_min=self.freq_min, freq_max=self.freq_max,
+        location = self.locate(frames, self.fps, save_calibration_image=self.save_calibration_image,
+                               freq_min=self.freq_min, freq_max=self.freq_max,
                                temporal_threshold=self.temporal_threshold,
                                threshold=int(np.round(self.threshold * 255)), engine=self.engine)
         torch.cuda.synchronize(self.engine.device)

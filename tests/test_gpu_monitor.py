@@ -142,3 +142,23 @@ def test_tracking_lost_goes_through_error_and_recalibrates():
     assert len(rm.data) == min(128, 600 - 341)
     assert not np.isnan(np.array(rm.data)).any()
     assert len(rm.freq) > 0 and abs(rm.freq[-1] - spec.truth_bpm) <= 3.0
+
+
+@pytest.mark.parametrize("name", ["mosaic_qvga_s1", "mosaic_odd_s3"])
+def test_locate_writes_the_reference_calibration_png(golden, name, tmp_path, monkeypatch):
+    """locate(save_calibration_image=True) (base.py:577-596): the PNG equals, byte for byte, the one the unmodified
+    reference wrote for the same 128 frames (tools/make_golden_mosaic.py); a second call takes the next free name."""
+    cv2 = pytest.importorskip("cv2")
+    from respmon_b200.monitor import RespiratoryMonitor
+    fix = golden(name)
+    spec, clip = clip_from_fixture(fix)
+    monkeypatch.chdir(tmp_path)
+    for dtype in (np.uint8, np.float64):       # the reference passes its float64 calibration buffer
+        frames = clip[1:129] if dtype == np.uint8 else clip[1:129] * (1.0 / 255.0)
+        box = RespiratoryMonitor.locate(frames, 10, freq_min=0.1, freq_max=1.0, temporal_threshold=0.7, threshold=20,
+                                        save_calibration_image=True)
+        assert box == tuple(int(v) for v in fix["roi"])
+    for i in (0, 1):
+        png = cv2.imread(str(tmp_path / ("calibration%d.png" % i)), cv2.IMREAD_UNCHANGED)
+        assert png is not None and png.dtype == np.uint8 and png.shape == fix["mosaic"].shape
+        assert np.array_equal(png, fix["mosaic"])
