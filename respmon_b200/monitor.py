@@ -103,7 +103,9 @@ def calibration_mosaic(eng, vid, fps, heat, box, threshold):
     row 1 = thresholded heat map | mean frame with all contours drawn | mean frame + heat map with the ROI box.
     vid (T,H,W) device tensor (uint8 or float in [0,1]); heat (H,W) uint8 device tensor from the same frames.
     The three averaged panels come from the device (`rm_to_f64`, `rm_volume_clip_mean`, `rm_f64_to_u8`, and the
-    calibration kernels run once more with the temporal clipping switched off); drawing is cv2's, as in the reference."""
+    calibration kernels run once more with the temporal clipping switched off); drawing is cv2's, as in the reference.
+    The middle panel of row 0 is, in the reference too, the normalised rounding residue of a zero-mean signal (the
+    band-pass removes the DC bin): noise of order 1e-17 before normalisation, not comparable between FFT implementations."""
     frames = vid if vid.dtype == torch.float64 else eng.to_f64(vid)       # uint8_to_float (transforms.py:20-23)
     _, mean_frame, _ = eng.volume_clip_mean(frames.contiguous(), want_clipped=False)       # base.py:579, :588
     total_avg = eng.to_u8(mean_frame).cpu().numpy()
