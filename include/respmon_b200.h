@@ -126,7 +126,8 @@ int32_t rm_pyr_up_f64(rm_handle* h, const double* src, double* dst, const double
 /* Number of doubles per frame in the packed Laplacian record: sum over levels skip..levels-2 of w_l*h_l
  * (1600 at 640x480 with levels=9, skip=4), level `skip` first. */
 int32_t rm_lap_record_len(rm_handle* h, int32_t W, int32_t H, int64_t* out);
-/* Workspace (bytes) rm_pyramid_build / rm_heatmap need for a batch of n_frames / (n_clips, T). */
+/* Workspace (bytes) rm_pyramid_build / rm_heatmap need for a batch of n_frames / (n_clips, T).  The heat-map figure
+ * depends on the "no_minmax_seed" option (rm_set_option): query it after setting the option. */
 int32_t rm_pyramid_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int64_t n_frames, size_t* out);
 int32_t rm_heatmap_workspace_bytes(rm_handle* h, int32_t W, int32_t H, int32_t n_clips, int32_t T, size_t* out);
 
@@ -245,8 +246,15 @@ int32_t rm_pack_results_stream(rm_handle* h, const double* bpm, const int32_t* r
  * until then. */
 int32_t rm_join(rm_handle* h, void* stream);
 
-/* Switches.  "defer_join" (0/1, see rm_join).  "measure_chunks" (1..16): frame chunks of rm_measure_signal.  "force_global_lk" (0/1): track from global memory even when the ROI fits shared memory (the
- * fallback used for ROIs too large to stage; results are identical). */
+/* Switches (results never depend on them; they select between bit-identical code paths or schedules).
+ *   "defer_join" (0/1)           see rm_join.
+ *   "measure_chunks" (1..16)     frame chunks of rm_measure_signal (default 4).
+ *   "measure_tail_frames" (>=0)  rm_measure_signal: give the last n frames a chunk of their own (default 0 = off).
+ *   "force_global_lk" (0/1)      track from global memory even when the ROI fits shared memory (the path used for ROIs
+ *                                too large to stage).
+ *   "force_generic_front" (0/1)  uint8 frames take the float pyramid front kernel instead of the integer one.
+ *   "no_minmax_seed" (0/1)       rm_heatmap evaluates every tile-frame (no pruning) and materialises level 2; changes
+ *                                what rm_heatmap_workspace_bytes returns, so set it before sizing the workspace. */
 int32_t rm_set_option(rm_handle* h, const char* host_name, int64_t value);
 
 /* Per-kernel device timing, the kernel-granular analogue of the reference's tools.Benchmarker (tools.py:60-82): while
