@@ -390,7 +390,20 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
     // the next staged frame): a frame that is not on the list only adds the replacement value
     int k = 0;
     const int n_iter = (PASS == 2 && p.bounds) ? p.T : n_list;
-    for (int it = 0; it < n_iter; ++it) {
+    int it0 = 0;
+    if (PASS == 2 && p.bounds) {
+      // Until the first frame that is evaluated every accumulator of the tile receives the same additions
+      // (0 + repl + repl + ...): one chain instead of sixteen.  Most tiles evaluate no frame at all.
+      it0 = n_list > 0 ? frame_list[0] : p.T;                // block-uniform
+      double pre = 0.0;
+#pragma unroll 4
+      for (int it = 0; it < it0; ++it) pre += repl_s;
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) acc[ky][kx] = pre;
+    }
+    for (int it = it0; it < n_iter; ++it) {
       if (PASS == 2 && p.bounds) {
         if (k >= n_list || frame_list[k] != it) {          // block-uniform
           if (active) {
