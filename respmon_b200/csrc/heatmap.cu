@@ -641,17 +641,33 @@ __global__ void minmax_init_kernel(unsigned long long* keys, int n_clips) {
 }
 
 // base.py:563-564: (avg - min) / (max - min) * 255, truncated to uint8 (NaN from a flat map becomes 0)
-__global__ void heat_normalise_kernel(const double* __restrict__ avg, const unsigned long long* __restrict__ keys,
-                                      uint8_t* __restrict__ heat, double* __restrict__ minmax_out, int n_clips,
-                                      long long hw) {
+__device__ __forceinline__ uint8_t heat_u8(double a, double mn, double range) {
+  const double v = ((a - mn) / range) * 255.0;       // base.py:563-564: min-max normalise, *255, truncate
+  return (v == v) ? (uint8_t)(int)v : (uint8_t)0;
+}
+// VEC: hw is a multiple of 4, so every clip plane starts 32-byte aligned in `avg` and 4-byte aligned in `heat`: a thread
+// converts four pixels per iteration (two 16-byte loads in flight, one 4-byte store).
+template <bool VEC>
+__global__ void __launch_bounds__(256) heat_normalise_kernel(const double* __restrict__ avg,
+                                                             const unsigned long long* __restrict__ keys,
+                                                             uint8_t* __restrict__ heat, double* __restrict__ minmax_out,
+                                                             int n_clips, long long hw) {
   const int clip = blockIdx.y;
   const double mn = key_f64(keys[clip * 4 + 2]), mx = key_f64(keys[clip * 4 + 3]);
   const double range = mx - mn;
   const double* a = avg + clip * hw;
   uint8_t* o = heat + clip * hw;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
-    double v = ((a[i] - mn) / range) * 255.0;
-    o[i] = (v == v) ? (uint8_t)(int)v : (uint8_t)0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (VEC) {
+    const double2* a2 = reinterpret_cast<const double2*>(a);
+    uchar4* o4 = reinterpret_cast<uchar4*>(o);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < hw / 4; q += stride) {
+      const double2 lo = a2[2 * q], hi = a2[2 * q + 1];
+      o4[q] = make_uchar4(heat_u8(lo.x, mn, range), heat_u8(lo.y, mn, range), heat_u8(hi.x, mn, range),
+                          heat_u8(hi.y, mn, range));
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw; i += stride) o[i] = heat_u8(a[i], mn, range);
   }
   if (minmax_out && blockIdx.x == 0 && threadIdx.x < 4)
     minmax_out[clip * 4 + threadIdx.x] = key_f64(keys[clip * 4 + threadIdx.x]);
@@ -870,9 +886,14 @@ extern "C" int32_t rm_heatmap(rm_handle* h, const double* bp, int32_t n_clips, i
   upsample_pass_kernel<2><<<grid, 128, list_smem, st>>>(tp);
   RM_LAUNCH_CHECK(h);
   long long hw = (long long)W * H;
-  dim3 ngrid((unsigned)((hw + 255) / 256 < 1024 ? (hw + 255) / 256 : 1024), n_clips);
+  const bool vec = hw % 4 == 0 && ((uintptr_t)heat_out & 3) == 0;
+  const long long items = vec ? hw / 4 : hw;
+  dim3 ngrid((unsigned)((items + 255) / 256 < 1024 ? (items + 255) / 256 : 1024), n_clips);
   RM_PROF(h, st, "heat_normalise_kernel");
-  heat_normalise_kernel<<<ngrid, 256, 0, st>>>(avg, keys, heat_out, minmax_out, n_clips, hw);
+  if (vec)
+    heat_normalise_kernel<true><<<ngrid, 256, 0, st>>>(avg, keys, heat_out, minmax_out, n_clips, hw);
+  else
+    heat_normalise_kernel<false><<<ngrid, 256, 0, st>>>(avg, keys, heat_out, minmax_out, n_clips, hw);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
 }
