@@ -23,6 +23,15 @@
 
 #define PU_STAGES 4
 #define PU_ROWS 8
+// Developer switch (round-2 experiment, default off): the x1 taps of the 5-tap rows as a mask on the ALU pipe instead of a
+// dot product with the coefficient vector (…, 0, 1) on the multiplier pipe.  Bit 0: level-1 rows (dp2a), bit 1: level-0
+// rows (dp4a).  Integer arithmetic either way, identical results.
+#ifndef PU_ALU_TAPS
+#define PU_ALU_TAPS 0
+#endif
+#ifndef PU_MAX_WARPS
+#define PU_MAX_WARPS 16     // warps per CTA (one CTA per SM); each warp owns PU_STAGES * 2 KB of shared memory
+#endif
 #define PU_STAGE_BYTES (PU_ROWS * 256)
 
 __device__ __forceinline__ void pu_cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -53,8 +62,13 @@ __device__ __forceinline__ void pu_h1(unsigned P, unsigned Q, int lane, int last
   unsigned Pr = __shfl_down_sync(0xffffffffu, P, 1);
   if (LEFT && lane == 0) Ql = __byte_perm(P, Q, 0x3254);   // columns -2, -1 are columns 2, 1
   if (RIGHT && lane == last_lane) Pr = Q;                  // column W1 is column W1-2
+#if PU_ALU_TAPS & 1
+  g0 = __dp2a_lo(Ql, 0x0401u, __dp2a_lo(P, 0x0406u, Q & 0xffffu));
+  g1 = __dp2a_lo(P, 0x0401u, __dp2a_lo(Q, 0x0406u, Pr & 0xffffu));
+#else
   g0 = __dp2a_lo(Ql, 0x0401u, __dp2a_lo(P, 0x0406u, __dp2a_lo(Q, 0x0001u, 0u)));
   g1 = __dp2a_lo(P, 0x0401u, __dp2a_lo(Q, 0x0406u, __dp2a_lo(Pr, 0x0001u, 0u)));
+#endif
 }
 // horizontal 5-tap at level 2 -> the lane's level-3 column.  q0, q1 = level-2 columns (2L, 2L+1).
 template <bool LEFT, bool RIGHT>
@@ -78,9 +92,15 @@ __device__ __forceinline__ void pu_block(PuState& s, const uint2 w[PU_ROWS], int
     if (LEFT && lane == 0) wl = __byte_perm(w0, w1, 0x1234);          // pixels -2, -1 are pixels 2, 1
     if (RIGHT && lane == last_lane) wr = __byte_perm(w1, 0u, 0x0002); // pixel W is pixel W-2
     const unsigned k0 = __dp4a(wl, 0x04010000u, __dp4a(w0, 0x00010406u, 0u));
+#if PU_ALU_TAPS & 2
+    const unsigned k1 = __dp4a(w0, 0x04060401u, w1 & 0xffu);
+    const unsigned k2 = __dp4a(w0, 0x04010000u, __dp4a(w1, 0x00010406u, 0u));
+    const unsigned k3 = __dp4a(w1, 0x04060401u, wr & 0xffu);
+#else
     const unsigned k1 = __dp4a(w0, 0x04060401u, __dp4a(w1, 0x00000001u, 0u));
     const unsigned k2 = __dp4a(w0, 0x04010000u, __dp4a(w1, 0x00010406u, 0u));
     const unsigned k3 = __dp4a(w1, 0x04060401u, __dp4a(wr, 0x00000001u, 0u));
+#endif
     ha[i] = k0 + (k1 << 16);
     hb[i] = k2 + (k3 << 16);
   }
@@ -180,7 +200,7 @@ __device__ __forceinline__ void pu_run_frame(const PuParams& p, const uint8_t* _
 }
 
 template <int WT>
-__global__ void __launch_bounds__(512, 1) pyramid_front_u8_kernel(const PuParams p) {
+__global__ void __launch_bounds__(PU_MAX_WARPS * 32, 1) pyramid_front_u8_kernel(const PuParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / p.n_strips, strip = warp - slot * p.n_strips;
@@ -225,7 +245,7 @@ int32_t pu_launch(rm_handle* h, const uint8_t* frames, uint32_t* g3, long long n
   p.n_strips = (p.W3 + cap - 1) / cap;
   p.cols_per_strip = (p.W3 + p.n_strips - 1) / p.n_strips;
   if (p.n_strips > 16) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: frame wider than 3584 pixels", __func__);
-  p.frames_per_cta = 16 / p.n_strips;
+  p.frames_per_cta = PU_MAX_WARPS / p.n_strips;
   const int warps = p.frames_per_cta * p.n_strips;
   const int smem = warps * PU_STAGES * PU_STAGE_BYTES;
   void (*kern)(const PuParams) = W == 640 ? pyramid_front_u8_kernel<640>
