@@ -5,12 +5,16 @@
 // (max-min)*threshold, values >= top replaced by min) and base.py:562-564 (mean over T, min-max normalise, *255
 // truncated to uint8).
 //
-// Nothing of size (T,H,W) is ever stored: the collapsed full-resolution value of every pixel-frame is evaluated twice
-// (pass 1: min/max, pass 2: clipped mean).  Per frame the coarse part (levels top-1..skip, 1600 values at VGA) is
-// collapsed once by collapse_head_kernel into A_skip (40x30); the two passes then upsample A_skip by `skip` pyrUp
-// steps on the fly: levels skip-1..2 as small shared-memory patches per 64x64 output tile, the last two steps
-// (16x the pixels) entirely in registers, 4x4 outputs per thread.  All 1/64 factors are exact powers of two and are
-// folded into one final scale.  These passes are FP64-ALU bound (about 11 flop per pixel-frame), not HBM bound.
+// Nothing of size (T,H,W) is ever stored: the collapsed full-resolution value of a pixel-frame is evaluated on the fly,
+// up to twice (pass 1: min/max, pass 2: clipped mean).  Per frame the coarse part (levels top-1..skip, 1600 values at
+// VGA) is collapsed once by collapse_head_kernel into A_skip (40x30) and upsampled to level 3 (level 2 when pruning is
+// off) by up_level_kernel.  The two tile passes own 64x32 output tiles: per evaluated (tile, frame) the level-3 patch is
+// staged in shared memory by a cp.async ring, expanded to the tile's level-2 patch, and the last two pyrUp steps (16x
+// the pixels) run entirely in registers, 4x4 outputs per thread.  pyrUp is a convex combination, so the level-`skip`
+// values under a tile bound everything the tile can produce: tile-frames that cannot change the clip's min/max (pass 1)
+// or whose values are all clipped (pass 2) are not evaluated at all -- exactly, not approximately (tile_bounds_kernel,
+// minmax_seed_kernel).  All 1/64 factors are exact powers of two and are folded into one final scale.  Where evaluated
+// the passes are FP64-ALU bound (about 11 flop per pixel-frame), not HBM bound.
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------------- pyrUp taps
@@ -139,9 +143,8 @@ __global__ void __launch_bounds__(256) up_level_kernel(const double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------- tile passes
-// Both passes evaluate every pixel of every frame from A_2: a thread owns a 4x4 block of level-0 pixels for all T
-// frames of its clip, loads the 4x4 level-2 values around it (L1/L2 hits: neighbouring threads share them) and runs
-// the last two pyrUp steps in registers.  No shared memory, no barriers.
+// A thread owns a 4x4 block of level-0 pixels of its tile for all T frames of its clip: it reads the 4x4 level-2 values
+// around the block from the tile's staged patch and runs the last two pyrUp steps in registers.
 #define HM_TW 64            // output tile: 64 x 32 level-0 pixels, 16 x 8 threads
 #define HM_TH 32
 
