@@ -2,10 +2,17 @@
 //
 //   float_to_uint8(crop)              transforms.py:26-29 after uint8_to_float -> a 256-entry LUT on the uint8 frame
 //   cv2.goodFeaturesToTrack           base.py:365-366  -> gftt_cov / gftt_eig / gftt_select kernels
-//   cv2.calcOpticalFlowPyrLK          base.py:371-372  -> lk_pyr_kernel (uint8 pyramids of every measure frame, in
-//                                                         parallel) + lk_track_kernel (one block per clip walks the
-//                                                         frames in order, one warp per corner)
-//   mean(old - new), PCA projection   base.py:388-405  -> lk_track_kernel epilogue + motion_pca_kernel
+//   cv2.calcOpticalFlowPyrLK          base.py:371-372  -> lk_track_smem_kernel: the clip's LUT-mapped ROI crops and their
+//                                                         uint8 pyramids live in shared memory (prefetched a frame
+//                                                         ahead), one warp per corner, the corners of a clip split over
+//                                                         blocks of at most LK_PPB, frames walked in resumable chunks;
+//                                                         lk_pyr_kernel + lk_track_kernel (global-memory pyramids) for
+//                                                         ROIs too large to stage
+//   mean(old - new), PCA projection   base.py:388-405  -> motion_reduce_kernel (ordered float32 mean over the surviving
+//                                                         points) + motion_pca_kernel
+//   rm_measure_signal                                  -> the tracker chunks on the caller's stream, PCA / filtfilt /
+//                                                         peaks / LM gate / BPM of finished chunks on the handle's own
+//                                                         streams (signal.cu)
 //
 // Third-party semantics follow SURVEY.md App. A.5 / A.6 and oracle/np_kernels.py (validated against cv2 there).
 // The per-frame working set is a few KB per clip: these kernels are latency bound; throughput comes from the batch.

@@ -6,7 +6,8 @@
 //                                                             where Suzuki-Abe starts its outer border), then one
 //                                                             thread per root follows the outer border (roi_core.h)
 //   max(contours, key=cv2.contourArea)                     -> atomicMax of (2*area, start index) keys per clip
-//   cv2.boundingRect                                       -> the winner's border is followed once more for its box
+//   cv2.boundingRect                                       -> every traced border leaves its box in a per-clip list;
+//                                                             the winner's is looked up
 //
 // A component nested in a hole of another one is not an external contour, but its polygon lies strictly inside the
 // enclosing one, so it can never be the maximum: treating every component as a candidate gives the same answer.

@@ -1,8 +1,9 @@
 // measure() for every frame of every clip (base.py:340-352 with find_peaks base.py:312-338) and result packing.
-// One thread per (clip, frame): the 128-sample rolling window is filtered (Butterworth filtfilt), peaks are picked
-// (peakutils.indexes), each is gated by a Levenberg-Marquardt Gaussian fit (MINPACK lmdif as SciPy's curve_fit
-// runs it) and the BPM is 60 / mean peak interval.  The arithmetic is in signal_core.h (shared with the host tests).
-// Compiled with -fmad=false.
+// signal_filter_peaks_kernel: one thread per (clip, frame) filters the 128-sample rolling window (Butterworth filtfilt)
+// and picks the peaks (peakutils.indexes), queueing one Gaussian fit per peak.  signal_fit_kernel: a persistent grid
+// pulls fits from the queue through an atomic cursor; SIG_FIT_G lanes share one Levenberg-Marquardt fit (MINPACK lmdif
+// as SciPy's curve_fit runs it, lm_group.cuh).  signal_bpm_kernel: 60 / mean interval of the accepted peaks.
+// The arithmetic is in signal_core.h (shared with the host tests).  Compiled with -fmad=false.
 #include "common.cuh"
 #include "signal_core.h"
 #include "lm_group.cuh"
