@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "librespmon_b200.so")
+# RESPMON_B200_LIB selects another build of the same library (developer A/B timing, see build.build_variant)
+LIB_PATH = os.environ.get("RESPMON_B200_LIB") or os.path.join(_PKG, "librespmon_b200.so")
 
 RM_OK = 0
 RM_U8, RM_F32, RM_F64 = 0, 1, 2

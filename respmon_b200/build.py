@@ -32,6 +32,32 @@ def _digest(paths):
     return h.hexdigest()
 
 
+def build_variant(tag, extra_flags):
+    """Developer builds for A/B timing: the same sources with extra nvcc flags (e.g. "-DPU_MAX_WARPS=24") linked into
+    respmon_b200/_variants/librespmon_b200.<tag>.so.  Select one at run time with RESPMON_B200_LIB=<path> (_cabi.py);
+    the product library is not touched."""
+    nvcc = _nvcc()
+    vdir = os.path.join(PKG, "_variants")
+    odir = os.path.join(vdir, "_obj_" + tag)
+    os.makedirs(odir, exist_ok=True)
+    sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    procs, objs = [], []
+    for s in sources:
+        obj = os.path.join(odir, s[:-3] + ".o")
+        cmd = [nvcc, *ARCH, *COMMON, *extra_flags.split(), "-c", os.path.join(CSRC, s), "-o", obj]
+        if s in NO_FMAD:
+            cmd.insert(1, "-fmad=false")
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed on %s (%s):\n%s" % (s, tag, out))
+    out_path = os.path.join(vdir, "librespmon_b200.%s.so" % tag)
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", out_path, *objs, "-Xcompiler", "-fPIC"])
+    return out_path
+
+
 def build(force=False, verbose=False):
     sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
@@ -69,4 +95,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if len(sys.argv) >= 4 and sys.argv[1] == "--variant":      # python -m respmon_b200.build --variant w24 "-DPU_MAX_WARPS=24"
+        print(build_variant(sys.argv[2], " ".join(sys.argv[3:])))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
