@@ -109,13 +109,20 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
 #ifdef LM_TIMING
   long long tk_ = clock64();
 #endif
+#ifdef LM_DIV3
+  const double eps_fd = l3_sqrt(epsfcn > epsmch ? epsfcn : epsmch);   // loop invariant (MINPACK recomputes it per call)
+#endif
 #pragma unroll 1
   for (;;) {
     if (bail_nfev > 0 && nfev >= bail_nfev) return -1;
     LMT(5);
     LMC(7);
     {   // fdjac2: forward differences (each lane differences the rows it evaluated)
+#ifdef LM_DIV3
+      const double eps = eps_fd;
+#else
       const double eps = l3_sqrt(epsfcn > epsmch ? epsfcn : epsmch);
+#endif
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const double temp = x[j];
@@ -226,6 +233,28 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
     __syncwarp(g.mask);                                          // R and qtf are read before fjac / wa4 change again
     gnorm = 0.0;
     if (fnorm != 0.0) {
+#ifdef LM_DIV3
+      // the same quotients qtf[i] / fnorm and sum_j / wa2[l], three per call (a skipped column's quotient is not used)
+      const L3Triple qf = l3_div3(qtf[0], fnorm, qtf[1], fnorm, qtf[2], fnorm);
+      const double qn[3] = {qf.a, qf.b, qf.c};
+      double sum[3], w2[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        w2[j] = l3_get(wa2, ipvt[j]);
+        sum[j] = 0.0;
+#pragma unroll
+        for (int i = 0; i <= j; ++i) sum[j] += r[i + j * 3] * qn[i];
+      }
+      const L3Triple qg = l3_div3(sum[0], w2[0], sum[1], w2[1], sum[2], w2[2]);
+      const double gq[3] = {qg.a, qg.b, qg.c};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (w2[j] != 0.0) {
+          const double gg = fabs(gq[j]);
+          gnorm = gnorm > gg ? gnorm : gg;
+        }
+      }
+#else
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const double w2l = l3_get(wa2, ipvt[j]);
@@ -237,6 +266,7 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
           gnorm = gnorm > gg ? gnorm : gg;
         }
       }
+#endif
     }
     if (gnorm <= gtol) { info = 4; break; }
 #pragma unroll
@@ -260,7 +290,9 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
       ++nfev;
       const double fnorm1 = lmg_enorm<G>(g, wa4, m, 0);
       double actred = -1.0;
+#ifndef LM_DIV3
       if (p1 * fnorm1 < fnorm) { const double d = l3_div(fnorm1, fnorm); actred = 1.0 - d * d; }
+#endif
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         wa3[j] = 0.0;
@@ -268,8 +300,15 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
 #pragma unroll
         for (int i = 0; i <= j; ++i) wa3[i] += r[i + j * 3] * temp;
       }
+#ifdef LM_DIV3
+      const L3Triple qr = l3_div3(fnorm1, fnorm, l3_enorm3(wa3[0], wa3[1], wa3[2]), fnorm, l3_sqrt(par) * pnorm, fnorm);
+      if (p1 * fnorm1 < fnorm) actred = 1.0 - qr.a * qr.a;
+      const double temp1 = qr.b;
+      const double temp2 = qr.c;
+#else
       const double temp1 = l3_div(l3_enorm3(wa3[0], wa3[1], wa3[2]), fnorm);
       const double temp2 = l3_div(l3_sqrt(par) * pnorm, fnorm);
+#endif
       const double prered = temp1 * temp1 + l3_div(temp2 * temp2, p5);
       const double dirder = -(temp1 * temp1 + temp2 * temp2);
       ratio = 0.0;

@@ -1,6 +1,7 @@
 """The header-only scalar cores used by the CUDA signal kernel (respmon_b200/csrc/signal_core.h), compiled for the
 host, against SciPy / NumPy / the oracle.  No GPU needed."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -171,3 +172,28 @@ def test_register_layout_lm_is_bit_identical_to_the_scalar_port(lib, golden):
         assert out[0] == out[1], (xs, ys, out[0][:2], out[1][:2])
         n_long += out[0][1] >= 400
     assert len(cases) > 1500 and n_long >= 1
+
+
+def test_div3_build_switch_changes_no_bits(lib, golden, tmp_path):
+    """-DLM_DIV3 (developer switch: three independent divisions of the trust-region code per call) must be a pure
+    scheduling change: same info, nfev and parameter bits as the default build on every fit window."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path / "_signal_host_div3.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-DLM_DIV3", "-shared", "-fPIC", "-o", so,
+                           os.path.join(here, "hostsim", "signal_host.cpp")])
+    alt = C.CDLL(so)
+    cases = list(_fit_cases()) + list(_golden_fit_windows(golden))
+    rng = np.random.default_rng(5)
+    for m in (3, 4, 6):
+        for _ in range(40):
+            cases.append((1.6 + 0.1 * np.arange(m), rng.uniform(-0.2, 0.2, m)))
+    for xs, ys in cases:
+        out = []
+        for fn in (lib.host_gauss_fit_l3, alt.host_gauss_fit_l3):
+            p = np.array([ys.max(), xs[0], (xs[1] - xs[0]) * 5])
+            nfev = C.c_int()
+            info = fn(len(xs), dptr(xs), dptr(ys), dptr(p), C.byref(nfev))
+            out.append((info, nfev.value, p.tobytes()))
+        assert out[0] == out[1]
+    assert len(cases) > 500
