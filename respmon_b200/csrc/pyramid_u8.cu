@@ -30,8 +30,11 @@
 #define PU_ALU_TAPS 0
 #endif
 #ifndef PU_MAX_WARPS
-#define PU_MAX_WARPS 16     // warps per CTA (one CTA per SM); each warp owns PU_STAGES * 2 KB of shared memory
+#define PU_MAX_WARPS 16     // warps per CTA; each warp owns PU_STAGES * 2 KB of shared memory
 #endif
+#ifndef PU_CTAS_PER_SM
+#define PU_CTAS_PER_SM 1    // resident CTAs per SM the grid is sized for (smaller CTAs leave room for the measure stage of
+#endif                      // the previous batch when steps overlap: rm_join / "defer_join")
 #define PU_STAGE_BYTES (PU_ROWS * 256)
 
 __device__ __forceinline__ void pu_cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -200,7 +203,7 @@ __device__ __forceinline__ void pu_run_frame(const PuParams& p, const uint8_t* _
 }
 
 template <int WT>
-__global__ void __launch_bounds__(PU_MAX_WARPS * 32, 1) pyramid_front_u8_kernel(const PuParams p) {
+__global__ void __launch_bounds__(PU_MAX_WARPS * 32, PU_CTAS_PER_SM) pyramid_front_u8_kernel(const PuParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / p.n_strips, strip = warp - slot * p.n_strips;
@@ -254,7 +257,7 @@ int32_t pu_launch(rm_handle* h, const uint8_t* frames, uint32_t* g3, long long n
                                  : W == 320 ? pyramid_front_u8_kernel<320> : pyramid_front_u8_kernel<0>;
   RM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   long long ctas = (n_frames + p.frames_per_cta - 1) / p.frames_per_cta;
-  if (ctas > h->sm_count) ctas = h->sm_count;
+  if (ctas > (long long)h->sm_count * PU_CTAS_PER_SM) ctas = (long long)h->sm_count * PU_CTAS_PER_SM;
   RM_PROF(h, st, "pyramid_front_u8_kernel");
   kern<<<(unsigned)ctas, warps * 32, smem, st>>>(p);
   RM_LAUNCH_CHECK(h);
