@@ -23,3 +23,7 @@ def load():
 
 def load_roi():
     return _build("roi_host", "roi_core.h")
+
+
+def load_heat():
+    return _build("heat_host", "heat_core.h")
