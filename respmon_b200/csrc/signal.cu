@@ -103,22 +103,28 @@ __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalPar
 #ifndef SIG_FIT_G
 #define SIG_FIT_G 4
 #endif
-template <int G>
 #ifndef SIG_FIT_MINB
 #define SIG_FIT_MINB 1
+#endif
+#ifndef SIG_LONG_G
+#define SIG_LONG_G 8          // lanes per fit in the solo long pass (option "fit_bail_nfev")
 #endif
 // bail_nfev > 0 (first pass of the deferred pipeline): a fit that has not converged after that many evaluations is
 // pushed to the long queue instead of being finished; long_pass = 1 drains that queue without a limit.  A handful of
 // fits per batch run ten times longer than the rest (MINPACK gives up on them after 800 evaluations): taking them out
 // of the first pass bounds the latency of everything that waits for the bulk.
+// SOLO (long pass only, option "fit_bail_nfev"): one fit per warp.  Groups that share a warp diverge from each other, so a
+// warp's groups take turns; a fit that runs alone in its warp iterates at its own latency.
+template <int G, bool SOLO = false>
 __global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_kernel(const SignalParams p, const SignalScratch s,
                                                                       int m_cap, int bail_nfev, int long_pass) {
   extern __shared__ __align__(16) double fit_smem[];
   const int lane = threadIdx.x & 31;
+  if (SOLO && lane >= G) return;
   LmGroup g;
   g.sub = lane & (G - 1);
   g.mask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << (lane & ~(G - 1));
-  const int group_in_block = threadIdx.x / G;
+  const int group_in_block = SOLO ? (int)(threadIdx.x >> 5) : (int)(threadIdx.x / G);
   const unsigned total = long_pass ? *s.long_n : *s.queue_n;
   const unsigned* queue = long_pass ? s.long_queue : s.queue;
   unsigned* cursor = long_pass ? s.long_cursor : s.cursor;
@@ -341,12 +347,20 @@ int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t s
   // deferred pipeline: the first pass hands fits that are still running after SIG_BAIL_NFEV evaluations to a second,
   // narrow pass (64-thread blocks: they fit beside the next batch's calibration kernels on an SM); ev_bulk marks the
   // end of the first pass, which is all the caller's stream has to wait for
-  const int bail = (ev_bulk && h->defer_join) ? SIG_BAIL_NFEV : 0;
+  // option "fit_bail_nfev" = N > 0 (any mode): the first pass gives up on a fit after N evaluations and the second pass
+  // runs those fits again, one per warp (SOLO), so that the few 800-evaluation fits do not take turns with other groups
+  const int bail = h->fit_bail_nfev > 0 ? h->fit_bail_nfev : ((ev_bulk && h->defer_join) ? SIG_BAIL_NFEV : 0);
   RM_PROF(h, st_fit, "signal_fit_kernel");
   signal_fit_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, job->fit_smem, st_fit>>>(p, sc, job->m_cap, bail, 0);
   RM_LAUNCH_CHECK(h);
   if (ev_bulk) RM_CUDA(h, cudaEventRecord(ev_bulk, st_fit));
-  if (bail) {
+  if (h->fit_bail_nfev > 0) {
+    const int long_threads = 64, long_warps = long_threads / 32;
+    RM_PROF(h, st_fit, "signal_fit_solo_kernel");
+    signal_fit_kernel<SIG_LONG_G, true><<<SIG_LONG_BLOCKS, long_threads, (size_t)long_warps * 7 * job->m_cap * sizeof(double),
+                                          st_fit>>>(p, sc, job->m_cap, 0, 1);
+    RM_LAUNCH_CHECK(h);
+  } else if (bail) {
     const int long_threads = 64, long_groups = long_threads / SIG_FIT_G;
     RM_PROF(h, st_fit, "signal_fit_long_kernel");
     signal_fit_kernel<SIG_FIT_G><<<SIG_LONG_BLOCKS, long_threads, (size_t)long_groups * 7 * job->m_cap * sizeof(double),
