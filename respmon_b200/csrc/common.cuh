@@ -38,6 +38,7 @@ struct rm_handle {
   // at the next call that reuses the handle's scratch.  Lets the next batch's calibration run under this batch's
   // longest Gaussian fits.
   int defer_join;
+  int temporal_sparse;      // option "temporal_sparse": band-pass through the kept bins only (temporal.cu; experimental)
   int fit_bail_nfev;        // option "fit_bail_nfev": > 0 -> bail + solo long pass in every mode (signal.cu)
   int pending_chunks;       // > 0: ev_done[0..pending_chunks) of the last rm_measure_signal have not been waited for
   int pending_pack;         // 1: ev_packed (tail_stream) has not been waited for

@@ -172,6 +172,108 @@ __global__ void __launch_bounds__(TB_WARPS * 32) temporal_direct_kernel(const Te
   }
 }
 
+// Sparse form (option "temporal_sparse", experimental): the mask keeps K of the T packed bins (24 of 128 at 10 fps), so
+//   q[a] = sum_t F[a][t] x[t]        F[a][t] = cos or -sin of harmonic k(j_a) at t        (only the kept bins of the rfft)
+//   r[t] = amp/T sum_a G[a][t] q[a]  G[a][t] = cos(2 pi j_a t / T)                         (the real part of the ifft)
+// is 2 K T multiply-adds per column instead of two length-T FFTs, with no bit reversal and no per-stage barriers.  Same
+// sums in the same order as temporal_direct_kernel (bit-identical to it); the FFT kernel differs from both by rounding.
+// A block owns a tile of TS_COLS columns: the tile is staged in shared memory, a thread accumulates 2 bins x 4 columns in
+// stage 1 and 8 time samples x 4 columns in stage 2; the coefficient tables are built once per (persistent) block.
+#define TS_COLS 32
+#define TS_THREADS 128
+#define TS_MAXK 32
+struct SparseParams {
+  TemporalParams b;
+  int K;
+  int kept[TS_MAXK];   // kept packed indices, increasing
+};
+
+__global__ void __launch_bounds__(TS_THREADS) temporal_sparse_kernel(const SparseParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = p.b.T, K = p.K, Tp = T + 2;       // padded table rows: neighbouring bins start 4 banks apart
+  double* F = reinterpret_cast<double*>(smem_raw);   // K * Tp
+  double* G = F + (size_t)K * Tp;                    // K * Tp
+  double* X = G + (size_t)K * Tp;                    // T * TS_COLS
+  double* Q = X + (size_t)T * TS_COLS;               // TS_MAXK * TS_COLS
+  const int tid = threadIdx.x;
+  for (int e = tid; e < K * T; e += TS_THREADS) {
+    const int a = e / T, t = e - a * T;
+    const int j = p.kept[a];
+    const int k = (j + 1) >> 1;
+    const bool imag = (j != 0) && !(j & 1);
+    const int m1 = (int)(((long long)k * t) % T), m2 = (int)(((long long)j * t) % T);
+    double sn, cs, sn2, cs2;
+    sincospi(2.0 * (double)m1 / (double)T, &sn, &cs);
+    sincospi(2.0 * (double)m2 / (double)T, &sn2, &cs2);
+    F[a * Tp + t] = imag ? -sn : cs;
+    G[a * Tp + t] = cs2;
+  }
+  const long long tiles_per_clip = (p.b.P + TS_COLS - 1) / TS_COLS;
+  const long long n_tiles = p.b.n_clips * tiles_per_clip;
+  const int cg = tid & 7, rg = tid >> 3;          // 4 columns 4cg..4cg+3; bin / time-sample group 0..15
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long clip = tile / tiles_per_clip;
+    const long long c0 = (tile % tiles_per_clip) * TS_COLS;
+    const double* src = p.b.in + clip * T * p.b.P;
+    double* dst = p.b.out + clip * T * p.b.P;
+    __syncthreads();                               // tables written; the previous tile's X and Q are free
+    for (int i = tid; i < T * TS_COLS; i += TS_THREADS) {
+      const int t = i >> 5, c = i & 31;
+      X[i] = (c0 + c < p.b.P) ? src[(long long)t * p.b.P + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    {   // stage 1: bins rg and rg + 16
+      const bool v0 = rg < K, v1 = rg + 16 < K;
+      const double* f0 = F + (size_t)(v0 ? rg : 0) * Tp;
+      const double* f1 = F + (size_t)(v1 ? rg + 16 : 0) * Tp;
+      double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+      const double2* x2 = reinterpret_cast<const double2*>(X + 4 * cg);
+#pragma unroll 4
+      for (int t = 0; t < T; ++t) {
+        const double2 xa = x2[t * (TS_COLS / 2)], xb = x2[t * (TS_COLS / 2) + 1];
+        const double c0f = f0[t], c1f = f1[t];
+        a0[0] += c0f * xa.x; a0[1] += c0f * xa.y; a0[2] += c0f * xb.x; a0[3] += c0f * xb.y;
+        a1[0] += c1f * xa.x; a1[1] += c1f * xa.y; a1[2] += c1f * xb.x; a1[3] += c1f * xb.y;
+      }
+      if (v0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Q[rg * TS_COLS + 4 * cg + c] = a0[c];
+      }
+      if (v1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Q[(rg + 16) * TS_COLS + 4 * cg + c] = a1[c];
+      }
+    }
+    __syncthreads();
+    for (int tbase = 0; tbase < T; tbase += 128) {   // stage 2: time samples tbase + rg + 16 i
+      double acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = 0.0;
+      const double2* q2 = reinterpret_cast<const double2*>(Q + 4 * cg);
+      for (int a = 0; a < K; ++a) {
+        const double2 qa = q2[a * (TS_COLS / 2)], qb = q2[a * (TS_COLS / 2) + 1];
+        const double* g = G + (size_t)a * Tp + tbase + rg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const double gv = (tbase + rg + 16 * i < T) ? g[16 * i] : 0.0;
+          acc[i][0] += qa.x * gv; acc[i][1] += qa.y * gv; acc[i][2] += qb.x * gv; acc[i][3] += qb.y * gv;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int t = tbase + rg + 16 * i;
+        if (t < T) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c0 + 4 * cg + c < p.b.P) dst[(long long)t * p.b.P + c0 + 4 * cg + c] = acc[i][c] * p.b.inv_T * p.b.amp;
+        }
+      }
+    }
+  }
+}
+
 // fftfreq-based bounds, restating transforms.py:88-90 / scipy.fftpack.fftfreq: f[j] = k_j * (1 / (T * d)), d = 1/fps.
 extern "C" int32_t rm_temporal_bounds(int32_t T, double fps, double freq_min, double freq_max, int32_t* lo, int32_t* hi) {
   if (T < 1 || !(fps > 0) || !lo || !hi) return RM_ERR_INVALID;
@@ -211,6 +313,33 @@ extern "C" int32_t rm_temporal_bandpass(rm_handle* h, const double* lap, double*
   p.amp = h->p.amplification;
   const long long n_groups = (long long)n_clips * ((record_len + TB_WARPS - 1) / TB_WARPS);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->temporal_sparse && T <= 256) {
+    SparseParams sp;
+    sp.b = p;
+    sp.K = 0;
+    bool fits = true;
+    for (int j = 0; j < T; ++j) {
+      bool kept = true;     // bin_kept(), host side
+      if (p.hi > 0 && j >= p.hi && j < T - p.hi) kept = false;
+      if (p.lo != 0 && (j < p.lo || j >= T - p.lo)) kept = false;
+      if (!kept) continue;
+      if (sp.K == TS_MAXK) { fits = false; break; }
+      sp.kept[sp.K++] = j;
+    }
+    const size_t smem = ((size_t)2 * sp.K * (T + 2) + (size_t)T * TS_COLS + (size_t)TS_MAXK * TS_COLS) * sizeof(double);
+    if (fits && sp.K >= 1 && (int)smem <= h->smem_optin) {
+      RM_CUDA(h, cudaFuncSetAttribute(temporal_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 1;
+      RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, temporal_sparse_kernel, TS_THREADS, smem));
+      const long long n_tiles = (long long)n_clips * ((record_len + TS_COLS - 1) / TS_COLS);
+      long long grid = (long long)h->sm_count * (occ < 1 ? 1 : occ);
+      if (grid > n_tiles) grid = n_tiles;
+      RM_PROF(h, st, "temporal_sparse_kernel");
+      temporal_sparse_kernel<<<(unsigned)grid, TS_THREADS, smem, st>>>(sp);
+      RM_LAUNCH_CHECK(h);
+      return RM_OK;
+    }
+  }
   if (p.logT >= 0 && T <= 2048) {
     size_t smem = (size_t)T * 16 + (size_t)TB_WARPS * (T + 1) * 16 + (size_t)TB_WARPS * T * 8;
     if ((int)smem > h->smem_optin) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: T too large for shared memory", __func__);
