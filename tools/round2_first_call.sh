@@ -1,0 +1,15 @@
+#!/bin/bash
+# One gpurun call that times every experiment prepared at the end of round 1:
+#   here (CPU, before the call):
+#     python -m respmon_b200.build --variant w24  "-DPU_MAX_WARPS=24"
+#     python -m respmon_b200.build --variant alu1 "-DPU_ALU_TAPS=1"
+#     python -m respmon_b200.build --variant alu2 "-DPU_ALU_TAPS=2"
+#     python -m respmon_b200.build --variant div3 "-DLM_DIV3"
+#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh r02a w24 alu1 alu2 div3'
+TAG=${1:-r02a}; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+timeout 300 python -m pytest tests -m gpu -q -x > $OUT/gpu_tests.log 2>&1; tail -2 $OUT/gpu_tests.log
+timeout 200 python tools/dev_temporal_sparse.py > $OUT/temporal_sparse.log 2>&1; cat $OUT/temporal_sparse.log
+timeout 200 python tools/dev_fit_solo.py 64 10 > $OUT/fit_solo.log 2>&1; cat $OUT/fit_solo.log
+bash tools/variants.sh $TAG "$@"
