@@ -46,6 +46,8 @@ class Engine:
         if rc != 0:
             raise _cabi.RmError("rm_create failed (rc=%d): needs an sm_100 device" % rc)
         self._ws = {}
+        self._ws_tag = ""       # workspace namespace (locate(parts > 1) runs parts side by side, each with its own scratch)
+        self._side = []         # side streams of locate(parts > 1)
         self._held = None       # tensors a deferred step may still be writing (see defer_join)
 
     def defer_join(self, on: bool = True):
@@ -78,6 +80,7 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _workspace(self, key, nbytes):
+        key = key + self._ws_tag
         ws = self._ws.get(key)
         if ws is None or ws.numel() < nbytes:
             ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
@@ -277,17 +280,47 @@ class Engine:
                    self._stream())
         return roi, status
 
-    def locate(self, clips: torch.Tensor, fps: float, first: int = 0, length: int | None = None):
+    def locate(self, clips: torch.Tensor, fps: float, first: int = 0, length: int | None = None, parts: int = 1):
         """locate() (base.py:547-575) on frames [first, first+length) of every clip of (n,T,H,W).
-        Returns (roi (n,4) int32, status (n,) int32, heat (n,H,W) uint8)."""
-        heat, _ = self.calibrate_heatmaps(clips, fps, first, length)
-        roi, status = self.roi_select(heat)
-        return roi, status, heat
+        Returns (roi (n,4) int32, status (n,) int32, heat (n,H,W) uint8).
+
+        parts > 1 (experimental, not timed yet): the batch is cut into that many groups of clips whose calibration
+        kernels run on side streams next to each other, so that the latency-bound ones (pyramid tail, ROI tracing, the
+        small heat-map kernels) of one group fill the gaps of another.  Clips are independent: same results."""
+        n = clips.shape[0]
+        if parts <= 1 or n < 2 * parts:
+            heat, _ = self.calibrate_heatmaps(clips, fps, first, length)
+            roi, status = self.roi_select(heat)
+            return roi, status, heat
+        cur = torch.cuda.current_stream(self.device)
+        while len(self._side) < parts:
+            self._side.append(torch.cuda.Stream(device=self.device))
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        outs = []
+        try:
+            for i in range(parts):
+                b0, b1 = n * i // parts, n * (i + 1) // parts
+                st = self._side[i]
+                st.wait_event(fork)
+                self._ws_tag = "/part%d" % i
+                with torch.cuda.stream(st):
+                    heat, _ = self.calibrate_heatmaps(clips[b0:b1], fps, first, length)
+                    roi, status = self.roi_select(heat)
+                for t in (roi, status, heat):
+                    t.record_stream(cur)
+                outs.append((roi, status, heat))
+                done = torch.cuda.Event()
+                done.record(st)
+                cur.wait_event(done)
+        finally:
+            self._ws_tag = ""
+        return tuple(torch.cat([o[k] for o in outs]) for k in range(3))
 
     # ------------------------------------------------------------------ whole clips
     def run_batch(self, clips: torch.Tensor, fps: float, cal_first: int = 1, cal_len: int = 128,
                   measure_first: int | None = None, method: str = "flow", keep: bool = False,
-                  out: torch.Tensor | None = None, max_roi: tuple[int, int] | None = None):
+                  out: torch.Tensor | None = None, max_roi: tuple[int, int] | None = None, cal_parts: int = 1):
         """The frame routing of run() (base.py:409-513) on a batch of whole clips resident in HBM.
 
         clips (n,T,H,W) uint8.  Frame 0 is dropped by 'initialize' (base.py:423-425), frames cal_first ..
@@ -300,7 +333,7 @@ class Engine:
             measure_first = cal_first + cal_len + 1
         n_meas = T - measure_first
         assert cal_first >= 0 and cal_first + cal_len <= T and n_meas >= 1
-        roi, status, heat = self.locate(clips, fps, cal_first, cal_len)
+        roi, status, heat = self.locate(clips, fps, cal_first, cal_len, parts=cal_parts)
         if method == "flow":
             m = self.measure_signal(clips, roi, measure_first, n_meas, fps, status=status, max_roi=max_roi)
             sig = {k: m[k] for k in ("bpm", "filtered", "peaks", "npeaks")}

@@ -12,4 +12,5 @@ mkdir -p $OUT
 timeout 300 python -m pytest tests -m gpu -q -x > $OUT/gpu_tests.log 2>&1; tail -2 $OUT/gpu_tests.log
 timeout 200 python tools/dev_temporal_sparse.py > $OUT/temporal_sparse.log 2>&1; cat $OUT/temporal_sparse.log
 timeout 200 python tools/dev_fit_solo.py 64 10 > $OUT/fit_solo.log 2>&1; cat $OUT/fit_solo.log
+timeout 200 python tools/dev_cal_split.py 64 10 > $OUT/cal_split.log 2>&1; cat $OUT/cal_split.log
 bash tools/variants.sh $TAG "$@"
