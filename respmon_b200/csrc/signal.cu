@@ -357,7 +357,9 @@ int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t s
   if (h->fit_bail_nfev > 0) {
     const int long_threads = 64, long_warps = long_threads / 32;
     RM_PROF(h, st_fit, "signal_fit_solo_kernel");
-    signal_fit_kernel<SIG_LONG_G, true><<<SIG_LONG_BLOCKS, long_threads, (size_t)long_warps * 7 * job->m_cap * sizeof(double),
+    // one fit per warp: size the grid for many bailed fits (a small N sends a good part of the queue here); blocks
+    // that find the queue empty leave at once
+    signal_fit_kernel<SIG_LONG_G, true><<<h->sm_count * 4, long_threads, (size_t)long_warps * 7 * job->m_cap * sizeof(double),
                                           st_fit>>>(p, sc, job->m_cap, 0, 1);
     RM_LAUNCH_CHECK(h);
   } else if (bail) {
