@@ -302,6 +302,7 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
   RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, signal_fit_kernel<SIG_FIT_G>, SIG_FIT_THREADS,
                                                            job->fit_smem));
   job->grid_cap = h->sm_count * (per_sm > 0 ? per_sm : 1);   // persistent grid: what can be resident
+  if (h->fit_blocks_per_sm > 0 && h->fit_blocks_per_sm < per_sm) job->grid_cap = h->sm_count * h->fit_blocks_per_sm;
   RM_CUDA(h, cudaMemsetAsync(sc.queue_n, 0, 256, st));
   RM_PROF(h, st, "tvals_kernel");
   tvals_kernel<<<1, 32, 0, st>>>(p.tvals, n_frames, p.dt);

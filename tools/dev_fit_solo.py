@@ -15,8 +15,9 @@ specs = [synth.clip_spec(i, 640, 480, 256) for i in range(n_clips)]
 dq8 = np.stack([synth.displacement_q8(s) for s in specs])
 clips = eng.synth_clips(specs, dq8)
 base = None
-for bail in (0, 40, 60, 100, 200):
+for bail, per_sm in ((0, 0), (0, 1), (40, 0), (60, 0), (100, 0), (200, 0), (100, 1)):
     eng.set_option("fit_bail_nfev", bail)
+    eng.set_option("fit_blocks_per_sm", per_sm)
     rec, taps = eng.run_batch(clips, 10.0, keep=True)
     for _ in range(2):
         eng.run_batch(clips, 10.0)
@@ -35,5 +36,5 @@ for bail in (0, 40, 60, 100, 200):
         base = cur
     else:
         same = all(np.array_equal(a, b, equal_nan=True) for a, b in zip(base, cur))
-    print("fit_bail_nfev %3d: step %.3f ms   records and BPM history identical to default: %s" % (
-        bail, e0.elapsed_time(e1) / steps, same))
+    print("fit_bail_nfev %3d, fit_blocks_per_sm %d: step %.3f ms   records and BPM history identical to default: %s" % (
+        bail, per_sm, e0.elapsed_time(e1) / steps, same))
