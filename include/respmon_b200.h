@@ -252,6 +252,8 @@ int32_t rm_join(rm_handle* h, void* stream);
  *   "measure_tail_frames" (>=0)  rm_measure_signal: give the last n frames a chunk of their own (default 0 = off).
  *   "temporal_sparse" (0/1)      rm_temporal_bandpass evaluates only the bins the mask keeps (2 K T multiply-adds per column
  *                                instead of two FFTs; same sums as the any-T kernel; default 0 = off; experimental).
+ *   "fit_sync" (0/1)             the groups of a warp run their Gaussian fits in lockstep (warp-uniform LM loops) instead
+ *                                of free-running; same results (default 0 = off; experimental).
  *   "fit_blocks_per_sm" (>=0)    > 0: cap on the resident Gaussian-fit blocks per SM (default 0 = what fits; experimental).
  *   "fit_bail_nfev" (0..800)     > 0: the first Gaussian-fit pass gives up on a fit after that many evaluations and a
  *                                second pass runs those fits again, one per warp (default 0 = off; experimental).

@@ -184,6 +184,7 @@ extern "C" int32_t rm_set_option(rm_handle* h, const char* name, int64_t value) 
   if (strcmp(name, "defer_join") == 0) { h->defer_join = value != 0; return RM_OK; }
   if (strcmp(name, "measure_tail_frames") == 0) { h->measure_tail_frames = value < 0 ? 0 : (int)value; return RM_OK; }
   if (strcmp(name, "temporal_sparse") == 0) { h->temporal_sparse = value != 0; return RM_OK; }
+  if (strcmp(name, "fit_sync") == 0) { h->fit_sync = value != 0; return RM_OK; }
   if (strcmp(name, "fit_blocks_per_sm") == 0) { h->fit_blocks_per_sm = value < 0 ? 0 : (int)value; return RM_OK; }
   if (strcmp(name, "fit_bail_nfev") == 0) {
     if (value < 0 || value > 800) return rm_fail(h, RM_ERR_INVALID, "%s: fit_bail_nfev must be 0..800", __func__);

@@ -39,6 +39,7 @@ struct rm_handle {
   // longest Gaussian fits.
   int defer_join;
   int temporal_sparse;      // option "temporal_sparse": band-pass through the kept bins only (temporal.cu; experimental)
+  int fit_sync;             // option "fit_sync": warp-synchronous first fit pass (signal.cu; experimental)
   int fit_blocks_per_sm;    // option "fit_blocks_per_sm": > 0 caps the resident fit blocks per SM (fewer divergent streams per SMSP)
   int fit_bail_nfev;        // option "fit_bail_nfev": > 0 -> bail + solo long pass in every mode (signal.cu)
   int pending_chunks;       // > 0: ev_done[0..pending_chunks) of the last rm_measure_signal have not been waited for

@@ -12,6 +12,17 @@
 #pragma once
 #include "signal_core.h"
 
+#ifndef __CUDACC__
+// Host build (tests/hostsim/lm_group_host.cpp, G = 1): a group of one lane needs no collectives, which leaves exactly
+// the control flow and the arithmetic to compare with the scalar port.
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+static inline double __shfl_xor_sync(unsigned, double v, int) { return v; }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline int __any_sync(unsigned, int p) { return p; }
+#endif
+
 // G = lanes per fit (a power of two up to 32): a template parameter of every routine below.
 
 struct LmGroup {
@@ -348,4 +359,240 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
     if (info != 0) break;
   }
   return info;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-synchronous form (option "fit_sync", experimental).  lmg_lmdif_gauss lets the groups of a warp run free: each is at
+// its own point of MINPACK's control flow, the warp issues their instruction streams one after the other, and an SMSP
+// ends up interleaving a dozen 4-lane streams.  Here every lane of the warp calls the routine together (groups without
+// a fit pass m = 0) and the two data-dependent loops -- outer iterations, trust-region retries -- are warp-uniform:
+// a group that has left a loop idles until the last group of the warp leaves it, so the groups re-converge at the top of
+// every iteration and one instruction stream serves all of them.  Shorter data-dependent branches (pivot swaps, lmpar's
+// own iterations) re-converge at their ends as usual.  Same arithmetic, same order, same results as lmg_lmdif_gauss.
+template <int G>
+__device__ __forceinline__ int lmg_lmdif_gauss_sync(const LmGroup g, int m, const double* xs, const double* ys, double x[3],
+                                                    double* fvec, double* wa4, double* fjac, int bail_nfev) {
+  const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
+  const int maxfev = 200 * (3 + 1);
+  const double epsmch = SC_DBL_EPS, epsfcn = SC_DBL_EPS;
+  const double p1 = 0.1, p5 = 0.5, p25 = 0.25, p75 = 0.75, p0001 = 1e-4;
+  double diag[3] = {0.0, 0.0, 0.0}, qtf[3], wa1[3], wa2[3], wa3[3], sdiag[3];
+  double r[9];
+  int ipvt[3];
+  int info = 0, nfev = 0, iter = 1, ret = 0;
+  double par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0, fnorm = 0.0;
+  bool live = m >= 3;
+  if (live) {
+    lmg_resid<G>(g, m, xs, ys, x, fvec);
+    nfev = 1;
+    fnorm = lmg_enorm<G>(g, fvec, m, 0);
+  }
+#pragma unroll 1
+  while (__any_sync(0xffffffffu, live)) {
+    bool inner = false;
+    double ratio = 0.0;
+    if (live && bail_nfev > 0 && nfev >= bail_nfev) { ret = -1; live = false; }
+    if (live) {
+      {   // fdjac2
+        const double eps = l3_sqrt(epsfcn > epsmch ? epsfcn : epsmch);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double temp = x[j];
+          double h = eps * fabs(temp);
+          if (h == 0.0) h = eps;
+          x[j] = temp + h;
+          lmg_resid<G>(g, m, xs, ys, x, wa4);
+          x[j] = temp;
+#pragma unroll 1
+          for (int i = g.sub; i < m; i += G) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
+        }
+        nfev += 3;
+      }
+      __syncwarp(g.mask);
+      {   // qrfac with column pivoting; wa1 = rdiag, wa2 = acnorm, wa3 = work
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          wa2[j] = lmg_enorm<G>(g, fjac + j * m, m, 0);
+          wa1[j] = wa2[j];
+          wa3[j] = wa1[j];
+          ipvt[j] = j;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          int kmax = j;
+#pragma unroll
+          for (int k = j; k < 3; ++k)
+            if (wa1[k] > l3_get(wa1, kmax)) kmax = k;
+          if (kmax != j) {
+#pragma unroll 1
+            for (int i = g.sub; i < m; i += G) {
+              const double t = fjac[i + j * m];
+              fjac[i + j * m] = fjac[i + kmax * m];
+              fjac[i + kmax * m] = t;
+            }
+            l3_put(wa1, kmax, wa1[j]);
+            l3_put(wa3, kmax, wa3[j]);
+            const int t = ipvt[j];
+            ipvt[j] = i3_get(ipvt, kmax);
+            i3_put(ipvt, kmax, t);
+            __syncwarp(g.mask);
+          }
+          double ajnorm = lmg_enorm<G>(g, fjac + j * m, m, j);
+          if (ajnorm != 0.0) {
+            if (fjac[j + j * m] < 0.0) ajnorm = -ajnorm;
+            __syncwarp(g.mask);
+#pragma unroll 1
+            for (int i = j + g.sub; i < m; i += G) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
+            __syncwarp(g.mask);
+            const double ajj = fjac[j + j * m];
+#pragma unroll
+            for (int k = j + 1; k < 3; ++k) {
+              double part = 0.0;
+#pragma unroll 1
+              for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * fjac[i + k * m];
+              const double temp = l3_div(lmg_sum<G>(g, part), ajj);
+#pragma unroll 1
+              for (int i = j + g.sub; i < m; i += G) fjac[i + k * m] -= temp * fjac[i + j * m];
+              __syncwarp(g.mask);
+              if (wa1[k] != 0.0) {
+                double t = l3_div(fjac[j + k * m], wa1[k]);
+                const double d = 1.0 - t * t;
+                wa1[k] *= l3_sqrt(d > 0.0 ? d : 0.0);
+                t = l3_div(wa1[k], wa3[k]);
+                if (0.05 * (t * t) <= SC_DBL_EPS) {
+                  wa1[k] = lmg_enorm<G>(g, fjac + k * m, m, j + 1);
+                  wa3[k] = wa1[k];
+                }
+              }
+            }
+          }
+          wa1[j] = -ajnorm;
+        }
+      }
+      if (iter == 1) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { diag[j] = wa2[j]; if (wa2[j] == 0.0) diag[j] = 1.0; }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) wa3[j] = diag[j] * x[j];
+        xnorm = l3_enorm3(wa3[0], wa3[1], wa3[2]);
+        delta = factor * xnorm;
+        if (delta == 0.0) delta = factor;
+      }
+#pragma unroll 1
+      for (int i = g.sub; i < m; i += G) wa4[i] = fvec[i];
+      __syncwarp(g.mask);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double ajj = fjac[j + j * m];
+        if (ajj != 0.0) {
+          double part = 0.0;
+#pragma unroll 1
+          for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * wa4[i];
+          const double temp = l3_div(-lmg_sum<G>(g, part), ajj);
+#pragma unroll 1
+          for (int i = j + g.sub; i < m; i += G) wa4[i] += fjac[i + j * m] * temp;
+          __syncwarp(g.mask);
+        }
+        qtf[j] = wa4[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i + j * 3] = (i == j) ? wa1[j] : fjac[i + j * m];
+      __syncwarp(g.mask);
+      gnorm = 0.0;
+      if (fnorm != 0.0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double w2l = l3_get(wa2, ipvt[j]);
+          if (w2l != 0.0) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i <= j; ++i) sum += r[i + j * 3] * l3_div(qtf[i], fnorm);
+            const double gg = fabs(l3_div(sum, w2l));
+            gnorm = gnorm > gg ? gnorm : gg;
+          }
+        }
+      }
+      if (gnorm <= gtol) {
+        info = 4;
+        ret = info;
+        live = false;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) diag[j] = diag[j] > wa2[j] ? diag[j] : wa2[j];
+        inner = true;
+      }
+    }
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, inner)) {
+      if (inner) {
+        l3_lmpar(r, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          wa1[j] = -wa1[j];
+          wa2[j] = x[j] + wa1[j];
+          wa3[j] = diag[j] * wa1[j];
+        }
+        const double pnorm = l3_enorm3(wa3[0], wa3[1], wa3[2]);
+        if (iter == 1) delta = delta < pnorm ? delta : pnorm;
+        lmg_resid<G>(g, m, xs, ys, wa2, wa4);
+        ++nfev;
+        const double fnorm1 = lmg_enorm<G>(g, wa4, m, 0);
+        double actred = -1.0;
+        if (p1 * fnorm1 < fnorm) { const double d = l3_div(fnorm1, fnorm); actred = 1.0 - d * d; }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          wa3[j] = 0.0;
+          const double temp = l3_get(wa1, ipvt[j]);
+#pragma unroll
+          for (int i = 0; i <= j; ++i) wa3[i] += r[i + j * 3] * temp;
+        }
+        const double temp1 = l3_div(l3_enorm3(wa3[0], wa3[1], wa3[2]), fnorm);
+        const double temp2 = l3_div(l3_sqrt(par) * pnorm, fnorm);
+        const double prered = temp1 * temp1 + l3_div(temp2 * temp2, p5);
+        const double dirder = -(temp1 * temp1 + temp2 * temp2);
+        ratio = 0.0;
+        if (prered != 0.0) ratio = l3_div(actred, prered);
+        if (ratio <= p25) {
+          double temp;
+          if (actred >= 0.0) temp = p5;
+          else temp = l3_div(p5 * dirder, dirder + p5 * actred);
+          if (p1 * fnorm1 >= fnorm || temp < p1) temp = p1;
+          const double q = l3_div(pnorm, p1);
+          delta = temp * (delta < q ? delta : q);
+          par = l3_div(par, temp);
+        } else if (par == 0.0 || ratio >= p75) {
+          delta = l3_div(pnorm, p5);
+          par = p5 * par;
+        }
+        if (ratio >= p0001) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
+#pragma unroll 1
+          for (int i = g.sub; i < m; i += G) fvec[i] = wa4[i];
+          xnorm = l3_enorm3(wa2[0], wa2[1], wa2[2]);
+          fnorm = fnorm1;
+          ++iter;
+        }
+        if (fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0) info = 1;
+        if (delta <= xtol * xnorm) info = 2;
+        if (fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0 && info == 2) info = 3;
+        if (info == 0) {
+          if (nfev >= maxfev) info = 5;
+          if (fabs(actred) <= epsmch && prered <= epsmch && p5 * ratio <= 1.0) info = 6;
+          if (delta <= epsmch * xnorm) info = 7;
+          if (gnorm <= epsmch) info = 8;
+        }
+        if (info != 0) {            // this fit is finished
+          ret = info;
+          live = false;
+          inner = false;
+        } else if (!(ratio < p0001)) {
+          inner = false;            // step accepted: next outer iteration
+        }
+      }
+    }
+  }
+  return ret;
 }

@@ -169,6 +169,70 @@ __global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_kern
   }
 }
 
+// Warp-synchronous first pass (option "fit_sync", experimental): the groups of a warp take their next fits together and
+// run them through lmg_lmdif_gauss_sync, whose loops are warp-uniform -- one converged instruction stream per warp
+// instead of one per group.  A warp stays in a round until its slowest fit is done (or bails: bail_nfev).
+template <int G>
+__global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_sync_kernel(const SignalParams p,
+                                                                                      const SignalScratch s, int m_cap,
+                                                                                      int bail_nfev) {
+  extern __shared__ __align__(16) double fit_smem[];
+  const int lane = threadIdx.x & 31;
+  LmGroup g;
+  g.sub = lane & (G - 1);
+  g.mask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << (lane & ~(G - 1));
+  const int group_in_block = threadIdx.x / G;
+  const unsigned total = *s.queue_n;
+  double* xs = fit_smem + (size_t)group_in_block * 7 * m_cap;
+  double* ys = xs + m_cap;
+  double* fvec = ys + m_cap;
+  double* wa4 = fvec + m_cap;
+  double* fjac = wa4 + m_cap;
+  for (;;) {
+    unsigned item = 0;
+    if (g.sub == 0) item = atomicAdd(s.cursor, 1u);
+    item = __shfl_sync(g.mask, item, lane & ~(G - 1));
+    const bool has = item < total;
+    if (!__any_sync(0xffffffffu, has)) return;          // the whole warp leaves together
+    unsigned q = 0;
+    long long win = 0;
+    int k = 0, m = 0;
+    double par[SC_NP] = {0.0, 0.0, 1.0};
+    if (has) {
+      q = s.queue[item];
+      win = q / SIG_MAX_CAND;
+      k = q % SIG_MAX_CAND;
+      const int f = (int)(win % p.win_frames) + p.win_f0;
+      const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
+      const int idx = s.cand[win * SIG_MAX_CAND + k];
+      int w = p.width;                                   // base.py:319-323
+      if (idx - p.width < 0) w = idx;
+      if (idx + w > n) w = n - idx;
+      m = 2 * w;
+      if (m > m_cap) m = m_cap;
+      const double* t = p.tvals + (f + 1 - n) + (idx - w);
+      const double* y = s.filt + win * p.buf_len + (idx - w);
+      double mx = -INFINITY;
+      for (int i = g.sub; i < m; i += G) {               // the previous round ended with the whole warp converged
+        xs[i] = t[i];
+        ys[i] = y[i];
+        mx = fmax(mx, y[i]);
+      }
+      mx = lmg_max<G>(g, mx);
+      __syncwarp(g.mask);
+      par[0] = mx;                                       // peakutils.gaussian_fit initial guess
+      par[1] = xs[0];
+      par[2] = (xs[1] - xs[0]) * 5.0;
+    }
+    const int info = lmg_lmdif_gauss_sync<G>(g, has ? m : 0, xs, ys, par, fvec, wa4, fjac, bail_nfev);
+    __syncwarp();                                        // every group is done with its slices before the next round
+    if (has && g.sub == 0) {
+      if (info == -1) s.long_queue[atomicAdd(s.long_n, 1u)] = q;
+      else s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334, 336
+    }
+  }
+}
+
 // Stage C, one thread per window: BPM = 60 / mean interval of the accepted peaks (base.py:347-352).
 __global__ void signal_bpm_kernel(const SignalParams p, const SignalScratch s) {
   const int clip = blockIdx.y;
@@ -351,8 +415,13 @@ int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t s
   // option "fit_bail_nfev" = N > 0 (any mode): the first pass gives up on a fit after N evaluations and the second pass
   // runs those fits again, one per warp (SOLO), so that the few 800-evaluation fits do not take turns with other groups
   const int bail = h->fit_bail_nfev > 0 ? h->fit_bail_nfev : ((ev_bulk && h->defer_join) ? SIG_BAIL_NFEV : 0);
-  RM_PROF(h, st_fit, "signal_fit_kernel");
-  signal_fit_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, job->fit_smem, st_fit>>>(p, sc, job->m_cap, bail, 0);
+  if (h->fit_sync) {
+    RM_PROF(h, st_fit, "signal_fit_sync_kernel");
+    signal_fit_sync_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, job->fit_smem, st_fit>>>(p, sc, job->m_cap, bail);
+  } else {
+    RM_PROF(h, st_fit, "signal_fit_kernel");
+    signal_fit_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, job->fit_smem, st_fit>>>(p, sc, job->m_cap, bail, 0);
+  }
   RM_LAUNCH_CHECK(h);
   if (ev_bulk) RM_CUDA(h, cudaEventRecord(ev_bulk, st_fit));
   if (h->fit_bail_nfev > 0) {

@@ -27,3 +27,7 @@ def load_roi():
 
 def load_heat():
     return _build("heat_host", "heat_core.h")
+
+
+def load_lm_group():
+    return _build("lm_group_host", "lm_group.cuh")

@@ -197,3 +197,38 @@ def test_div3_build_switch_changes_no_bits(lib, golden, tmp_path):
             out.append((info, nfev.value, p.tobytes()))
         assert out[0] == out[1]
     assert len(cases) > 500
+
+
+def test_group_lm_forms_agree_on_the_host(lib, golden):
+    """lm_group.cuh compiled for the host with one lane per group: the warp-synchronous form (lmg_lmdif_gauss_sync: both
+    data-dependent loops warp-uniform, fits that have left a loop idle) must give the same info and the same parameter
+    bits as the free-running form the kernels use today, with and without an evaluation limit; and both must agree with
+    the scalar port wherever enorm's plain sum applies (they rescale only outside 1e-140..1e140, MINPACK below 3.8e-20)."""
+    from hostsim import load_lm_group
+    grp = load_lm_group()
+    cases = list(_fit_cases()) + list(_golden_fit_windows(golden))
+    rng = np.random.default_rng(7)
+    for m in (3, 4, 5, 6, 8):
+        for _ in range(40):
+            cases.append((1.6 + 0.1 * np.arange(m), rng.uniform(-0.2, 0.2, m)))
+    cases.append((np.array([0.1, 0.2]), np.array([1.0, 2.0])))          # m < 3: both return 0 untouched
+    n_long = n_bailed = 0
+    for xs, ys in cases:
+        p0 = np.array([ys.max(), xs[0], (xs[1] - xs[0]) * 5])
+        for bail in (0, 60):
+            out = []
+            for fn in (grp.host_group_fit, grp.host_group_fit_sync):
+                p = p0.copy()
+                info = fn(len(xs), dptr(xs), dptr(ys), dptr(p), bail)
+                out.append((info, p.tobytes()))
+            assert out[0] == out[1], (xs, ys, bail, out[0][0], out[1][0])
+            n_bailed += out[0][0] == -1
+        if len(xs) >= 3:
+            p = p0.copy()
+            nfev = C.c_int()
+            info = lib.host_gauss_fit(len(xs), dptr(xs), dptr(ys), dptr(p), C.byref(nfev))
+            pg = p0.copy()
+            info_g = grp.host_group_fit(len(xs), dptr(xs), dptr(ys), dptr(pg), 0)
+            assert info_g == info and pg.tobytes() == p.tobytes(), (xs, ys, info, info_g)
+            n_long += nfev.value >= 400
+    assert len(cases) > 700 and n_long >= 1 and n_bailed >= 1

@@ -1,5 +1,6 @@
-"""Developer tool (round-2 experiment): option "fit_bail_nfev" -- the first Gaussian-fit pass gives up on a fit after N
-evaluations, a second pass runs those fits one per warp -- against the default, at the bench shapes.
+"""Developer tool (round-2 experiment): the Gaussian-fit options against the default, at the bench shapes --
+"fit_bail_nfev" (the first pass gives up on a fit after N evaluations, a second pass runs those fits one per warp),
+"fit_blocks_per_sm" (fewer resident fit blocks) and "fit_sync" (warp-synchronous first pass).
     python tools/dev_fit_solo.py [n_clips] [steps]
 Prints the step time per setting and checks that the result records and the per-frame BPM history do not change."""
 import os, sys
@@ -15,9 +16,11 @@ specs = [synth.clip_spec(i, 640, 480, 256) for i in range(n_clips)]
 dq8 = np.stack([synth.displacement_q8(s) for s in specs])
 clips = eng.synth_clips(specs, dq8)
 base = None
-for bail, per_sm in ((0, 0), (0, 1), (40, 0), (60, 0), (100, 0), (200, 0), (100, 1)):
+for bail, per_sm, sync in ((0, 0, 0), (0, 1, 0), (40, 0, 0), (60, 0, 0), (100, 0, 0), (200, 0, 0), (100, 1, 0),
+                           (0, 0, 1), (60, 0, 1), (100, 0, 1), (200, 0, 1), (100, 1, 1)):
     eng.set_option("fit_bail_nfev", bail)
     eng.set_option("fit_blocks_per_sm", per_sm)
+    eng.set_option("fit_sync", sync)
     rec, taps = eng.run_batch(clips, 10.0, keep=True)
     for _ in range(2):
         eng.run_batch(clips, 10.0)
@@ -36,5 +39,5 @@ for bail, per_sm in ((0, 0), (0, 1), (40, 0), (60, 0), (100, 0), (200, 0), (100,
         base = cur
     else:
         same = all(np.array_equal(a, b, equal_nan=True) for a, b in zip(base, cur))
-    print("fit_bail_nfev %3d, fit_blocks_per_sm %d: step %.3f ms   records and BPM history identical to default: %s" % (
-        bail, per_sm, e0.elapsed_time(e1) / steps, same))
+    print("fit_bail_nfev %3d, fit_blocks_per_sm %d, fit_sync %d: step %.3f ms   records and BPM history identical to default: %s" % (
+        bail, per_sm, sync, e0.elapsed_time(e1) / steps, same))
