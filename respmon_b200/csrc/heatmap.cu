@@ -512,8 +512,14 @@ __global__ void __launch_bounds__(256) minmax_seed_kernel(const TileParams p, in
   }
 }
 
+// Developer switch (round-2 experiment): -DHM_MIN_BLOCKS=4 caps the passes at 128 registers for a fourth resident block.
+#ifdef HM_MIN_BLOCKS
+#define HM_LAUNCH_BOUNDS __launch_bounds__(128, HM_MIN_BLOCKS)
+#else
+#define HM_LAUNCH_BOUNDS __launch_bounds__(128)
+#endif
 template <int PASS>
-__global__ void __launch_bounds__(128) upsample_pass_kernel(const TileParams p) {
+__global__ void HM_LAUNCH_BOUNDS upsample_pass_kernel(const TileParams p) {
   __shared__ double red_a[4], red_b[4];
   __shared__ __align__(16) double stage[HM_STAGES * HM_PW * HM_PH];
   const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
