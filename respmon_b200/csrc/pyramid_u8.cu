@@ -32,6 +32,9 @@
 #ifndef PU_MAX_WARPS
 #define PU_MAX_WARPS 16     // warps per CTA; each warp owns PU_STAGES * 2 KB of shared memory
 #endif
+#ifndef PU_BOUND_WARPS
+#define PU_BOUND_WARPS PU_MAX_WARPS   // warps the register budget is computed for (launch bounds only): a larger value
+#endif                                // leaves registers for another kernel's blocks on the SM (overlapped steps)
 #ifndef PU_CTAS_PER_SM
 #define PU_CTAS_PER_SM 1    // resident CTAs per SM the grid is sized for (smaller CTAs leave room for the measure stage of
 #endif                      // the previous batch when steps overlap: rm_join / "defer_join")
@@ -203,7 +206,7 @@ __device__ __forceinline__ void pu_run_frame(const PuParams& p, const uint8_t* _
 }
 
 template <int WT>
-__global__ void __launch_bounds__(PU_MAX_WARPS * 32, PU_CTAS_PER_SM) pyramid_front_u8_kernel(const PuParams p) {
+__global__ void __launch_bounds__(PU_BOUND_WARPS * 32, PU_CTAS_PER_SM) pyramid_front_u8_kernel(const PuParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / p.n_strips, strip = warp - slot * p.n_strips;

@@ -6,7 +6,8 @@
 #     python -m respmon_b200.build --variant alu2 "-DPU_ALU_TAPS=2"
 #     python -m respmon_b200.build --variant div3 "-DLM_DIV3"
 #     python -m respmon_b200.build --variant hm4  "-DHM_MIN_BLOCKS=4"
-#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh r02a w24 alu1 alu2 div3 hm4'
+#     python -m respmon_b200.build --variant b21  "-DPU_BOUND_WARPS=21"
+#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh r02a w24 alu1 alu2 div3 hm4 b21'
 TAG=${1:-r02a}; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT

@@ -12,4 +12,6 @@ for V in base "$@"; do
   timeout 200 python -m pytest tests -m gpu -q -x -k "calibrate or pipeline" 2>&1 | tail -1 | tee -a $OUT/summary.txt
   timeout 100 python tools/bench_stage.py 64 10 0 > $OUT/stage_$V.log 2>&1
   head -8 $OUT/stage_$V.log | tee -a $OUT/summary.txt
+  timeout 100 python tools/bench_stage.py 64 10 1 > $OUT/stage_defer_$V.log 2>&1     # overlapped steps (two engines, deferred join)
+  echo "deferred: $(head -1 $OUT/stage_defer_$V.log)" | tee -a $OUT/summary.txt
 done
