@@ -1,0 +1,145 @@
+"""CPU: the host side of the drop-in (respmon_b200/monitor.py: constructor, capture plumbing, the frame routing of
+run(), the rolling windows, the freq history, error detection) with the device replaced by the CPU oracle.
+
+monitor.py talks to the GPU only through `Engine`; here `Engine` is a stand-in whose `locate`, `measure_flow`,
+`measure_average` and `signal_bpm` are oracle/cpu_path.py (test infrastructure) on host tensors.  The attributes the
+monitor leaves behind must then equal the ones the UNMODIFIED reference left behind on the same clips (tests/golden) --
+the same checks tests/test_gpu_monitor.py applies to the real engine on a B200."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytest.importorskip("cv2")
+
+from conftest import clip_from_fixture  # noqa: E402
+from oracle import cpu_path as P  # noqa: E402
+
+
+class OracleEngine:
+    """The methods of respmon_b200.engine.Engine that monitor.py calls, computed by the oracle."""
+
+    def __init__(self, device=None, **params):
+        self.device = torch.device("cpu")
+        self.device_index = 0
+        self.params = SimpleNamespace(threshold=P.THRESHOLD, measure_buffer_len=P.MEASURE_LEN, **{
+            k: v for k, v in params.items() if k not in ("threshold", "measure_buffer_len")})
+        self.params.threshold = params.get("threshold", P.THRESHOLD)
+        self.calls = []
+
+    def locate(self, clips, fps, first=0, length=None):
+        self.calls.append(("locate", tuple(clips.shape)))
+        rois, status = [], []
+        for clip in clips:
+            vid = clip.numpy()
+            vid = P.u8_to_unit(vid) if vid.dtype == np.uint8 else vid.astype(np.float64)
+            box = P.locate(vid, fps, threshold=self.params.threshold)
+            rois.append(box if box is not None else (0, 0, 0, 0))
+            status.append(0 if box is not None else 1)
+        return torch.tensor(rois, dtype=torch.int32), torch.tensor(status, dtype=torch.int32), None
+
+    def measure_flow(self, clips, roi, first, n, max_roi=None):
+        self.calls.append(("measure_flow", tuple(clips.shape), first, n))
+        x, y, w, h = (int(v) for v in roi[0])
+        tracker = P.FlowTracker()
+        data = np.empty(n)
+        motion = np.full((n, 2), np.nan, dtype=np.float32)
+        for f in range(n):
+            crop = P.u8_to_unit(clips[0, first + f].numpy())[y:y + h, x:x + w]
+            if len(tracker.motion) >= P.MEASURE_LEN:
+                tracker.motion.popleft()                      # the monitor rolls motion_data (base.py:473-475)
+            before = len(tracker.motion)
+            data[f] = tracker.step(crop)
+            if len(tracker.motion) > before:
+                motion[f] = tracker.motion[-1]
+        status = 2 if tracker.pts is None else (3 if np.isnan(data).any() else 0)
+        return dict(data=torch.from_numpy(data)[None], motion=torch.from_numpy(motion)[None],
+                    status=torch.tensor([status], dtype=torch.int32),
+                    npts=torch.tensor([0 if tracker.pts is None else len(tracker.pts)], dtype=torch.int32))
+
+    def measure_average(self, clips, roi, first, n):
+        x, y, w, h = (int(v) for v in roi[0])
+        return torch.tensor([[np.average(P.u8_to_unit(clips[0, first + f].numpy())[y:y + h, x:x + w]) for f in range(n)]],
+                            dtype=torch.float64)
+
+    def signal_bpm(self, d, fps, status=None):
+        data = d[0].numpy()
+        n, L = len(data), P.MEASURE_LEN
+        t = np.zeros(n)
+        for i in range(1, n):
+            t[i] = t[i - 1] + 1.0 / fps                       # base.py:481-484
+        bpm = np.full(n, np.nan)
+        filt, peaks = np.full(L, np.nan), []
+        for f in range(n):
+            lo = max(0, f + 1 - L)
+            if f + 1 - lo > P.MEASURE_INIT_LEN and not np.isnan(data[lo:f + 1]).any():
+                filtered, pk, b = P.measure_window(data[lo:f + 1], t[lo:f + 1], fps)
+                bpm[f] = np.nan if b is None else b
+                if f == n - 1:
+                    filt[:len(filtered)] = filtered
+                    peaks = pk
+        pk_arr = np.full(L, -1, dtype=np.int32)
+        pk_arr[:len(peaks)] = peaks
+        return dict(bpm=torch.from_numpy(bpm)[None], filtered=torch.from_numpy(filt)[None],
+                    peaks=torch.from_numpy(pk_arr)[None], npeaks=torch.tensor([len(peaks)], dtype=torch.int32))
+
+    def bgr_to_gray(self, bgr):
+        import cv2
+        return torch.from_numpy(cv2.cvtColor(bgr.numpy(), cv2.COLOR_BGR2GRAY))
+
+
+@pytest.fixture
+def monitor_cls(monkeypatch):
+    from respmon_b200 import monitor
+    monkeypatch.setattr(monitor, "Engine", OracleEngine)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    return monitor.RespiratoryMonitor
+
+
+def _check(rm, fix):
+    assert (rm.x, rm.y, rm.w, rm.h) == tuple(int(v) for v in fix["roi"])
+    data = np.array(rm.data)
+    assert data.shape == fix["data"].shape
+    assert np.sqrt(np.mean((data - fix["data"]) ** 2)) <= 1e-4
+    np.testing.assert_allclose(np.array(rm.t), fix["t"], rtol=0, atol=1e-12)
+    assert len(rm.freq) == len(fix["freq"])
+    assert np.max(np.abs(np.array(rm.freq) - fix["freq"])) <= 0.5
+    assert [int(v) for v in rm.peak_indices] == [int(v) for v in fix["peaks"]]
+    np.testing.assert_allclose(np.asarray(rm.filtered_data), fix["filtered"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(np.asarray(rm.peak_times), np.take(fix["t"], fix["peaks"]), rtol=0, atol=1e-12)
+    motion = np.array(rm.motion_data, dtype=np.float32)
+    assert motion.shape == fix["motion"].shape
+    assert np.max(np.abs(motion - fix["motion"])) <= 1e-3
+    assert rm.state == "measure"
+
+
+@pytest.mark.parametrize("name", ["qvga_s1", "odd_s3", "qvga_long_s4"])
+def test_monitor_routing_and_windows_match_the_reference(monitor_cls, golden, name):
+    fix = golden(name)
+    spec, clip = clip_from_fixture(fix)
+    rm = monitor_cls(clip, visualize=None, save_all_data=False, motion_extraction_method="flow", fps_limit=10)
+    _check(rm, fix)
+    calls = rm.engine.calls
+    assert calls[0] == ("locate", (1, 128) + clip.shape[1:])            # frames 1..128 (base.py:429-434)
+    assert calls[1][0] == "measure_flow" and calls[1][1][1] == len(clip) - 130   # frame 129 is consumed by locate
+
+
+def test_short_stream_never_leaves_calibration(monitor_cls, golden):
+    """Fewer frames than the calibration buffer needs (base.py:429-434): no ROI, no data, still 'calibration'."""
+    fix = golden("qvga_s1")
+    spec, clip = clip_from_fixture(fix)
+    rm = monitor_cls(clip[:100], visualize=None, save_all_data=False, motion_extraction_method="flow")
+    assert rm.state == "calibration" and len(rm.data) == 0 and rm.engine.calls == []
+
+
+def test_average_method_and_skip_calibration(monitor_cls, golden):
+    """motion_extraction_method='average' (base.py:355-358) after skip_calibration (base.py:166-172) equals the oracle's
+    run of the same branch."""
+    fix = golden("qvga_s1")
+    spec, clip = clip_from_fixture(fix)
+    ref = P.run_clip(clip, fps=10.0, method="average")
+    rm = monitor_cls(clip, visualize=None, save_all_data=False, motion_extraction_method="average")
+    assert (rm.x, rm.y, rm.w, rm.h) == tuple(ref["roi"])
+    np.testing.assert_allclose(np.array(rm.data), np.array(ref["window_data"]), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(np.array(rm.freq), np.array(ref["freq_window"]), rtol=0, atol=1e-9)
