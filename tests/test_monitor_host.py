@@ -143,3 +143,27 @@ def test_average_method_and_skip_calibration(monitor_cls, golden):
     assert (rm.x, rm.y, rm.w, rm.h) == tuple(ref["roi"])
     np.testing.assert_allclose(np.array(rm.data), np.array(ref["window_data"]), rtol=0, atol=1e-15)
     np.testing.assert_allclose(np.array(rm.freq), np.array(ref["freq_window"]), rtol=0, atol=1e-9)
+
+
+def test_tracking_lost_goes_through_error_and_recalibrates(monitor_cls):
+    """The texture vanishes for a second in the middle of measuring: extract_motion returns nan (base.py:385-386),
+    detect_errors fires (base.py:543-545), the 'error' state lasts error_reset_delay of stream time, reset() clears the
+    buffers (base.py:515-533) and the monitor calibrates and measures again on what follows (host logic only: the same
+    scenario runs against the real engine in tests/test_gpu_monitor.py)."""
+    from respmon_b200 import synth
+    spec = synth.clip_spec(4, 320, 240, 600)
+    broken = synth.make_clip(spec)
+    broken[200:212] = 128                                    # no corners survive a flat frame
+    rm = monitor_cls(broken, motion_extraction_method="flow", error_reset_delay=1.0)
+    assert rm.error_message == "error detection found poor signal"
+    assert rm.state == "measure" and rm.x is not None
+    kinds = [c[0] for c in rm.engine.calls]
+    assert kinds == ["locate", "measure_flow", "locate", "measure_flow"]
+    # LK takes its gradients from the previous frame, so the step into the first flat frame (200) still succeeds and the
+    # step out of it (frame 201, measure sample 71) loses every point.  The error iteration consumes that frame, the
+    # 'error' state 1 s = 10 frames plus the iteration that resets, calibration 128 frames plus the locate frame:
+    # measuring resumes at frame 201 + 1 + 11 + 128 + 1 = 342
+    assert rm.engine.calls[3][1][1] == 600 - 342
+    assert len(rm.data) == min(128, 600 - 342)
+    assert not np.isnan(np.array(rm.data)).any()
+    assert len(rm.freq) > 0 and abs(rm.freq[-1] - spec.truth_bpm) <= 3.0
