@@ -363,6 +363,9 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
   int per_sm = 0;
   RM_CUDA(h, cudaFuncSetAttribute(signal_fit_kernel<SIG_FIT_G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)job->fit_smem));
+  if (h->fit_sync)      // the experimental first pass uses the same slices
+    RM_CUDA(h, cudaFuncSetAttribute(signal_fit_sync_kernel<SIG_FIT_G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)job->fit_smem));
   RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, signal_fit_kernel<SIG_FIT_G>, SIG_FIT_THREADS,
                                                            job->fit_smem));
   job->grid_cap = h->sm_count * (per_sm > 0 ? per_sm : 1);   // persistent grid: what can be resident
