@@ -178,18 +178,7 @@ static inline RecordGeom make_record(const LevelGeom& g, int skip) {
 }
 
 // ---- device helpers ------------------------------------------------------------------------------------------------
-// OpenCV BORDER_REFLECT_101 for an index at most one reflection away.
-__host__ __device__ __forceinline__ int reflect101(int i, int n) {
-  if (n == 1) return 0;
-  if (i < 0) i = -i;
-  if (i >= n) i = 2 * (n - 1) - i;
-  return i;
-}
-
-// The 5-tap [1 4 6 4 1] combination, one rounding per fused step: (a+e) + 4(b+d) + 6c.
-__device__ __forceinline__ double tap5(double a, double b, double c, double d, double e) {
-  return fma(6.0, c, fma(4.0, b + d, a + e));
-}
+#include "pyr_core.h"   // reflect101, tap5, up_taps / up_combine: shared with the host build of the tests
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 

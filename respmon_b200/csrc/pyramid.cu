@@ -37,30 +37,6 @@ __global__ void pyr_down_f64_kernel(const double* __restrict__ src, double* __re
   }
 }
 
-// One axis of cv2.pyrUp at output index o over a source of length n:
-// even: s[i-1] + 6 s[i] + s[i+1]; odd: 4 (s[i] + s[i+1]); s[-1] := s[1] (reflect-101), s[n] := s[n-1] (replicate).
-struct UpTaps {
-  int i0, i1, i2;
-  double w0, w1, w2;
-};
-__device__ __forceinline__ UpTaps up_taps(int o, int n) {
-  UpTaps t;
-  int i = o >> 1;
-  int nx = min(i + 1, n - 1);
-  if (o & 1) {
-    t.i0 = i; t.i1 = nx; t.i2 = nx;
-    t.w0 = 4.0; t.w1 = 4.0; t.w2 = 0.0;
-  } else {
-    t.i0 = reflect101(i - 1, n); t.i1 = i; t.i2 = nx;
-    t.w0 = 1.0; t.w1 = 6.0; t.w2 = 1.0;
-  }
-  return t;
-}
-__device__ __forceinline__ double up_combine(const UpTaps& t, double a, double b, double c) {
-  // even: (a + c) + 6 b ; odd: 4 (a + b)
-  return (t.w2 == 0.0) ? 4.0 * (a + b) : fma(6.0, b, a + c);
-}
-
 __global__ void pyr_up_f64_kernel(const double* __restrict__ src, double* __restrict__ dst,
                                   const double* __restrict__ other, int mode, long long n_img, int sw, int sh, int dw,
                                   int dh) {

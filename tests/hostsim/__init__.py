@@ -31,3 +31,7 @@ def load_heat():
 
 def load_lm_group():
     return _build("lm_group_host", "lm_group.cuh")
+
+
+def load_pyr():
+    return _build("pyr_host", "pyr_core.h")
