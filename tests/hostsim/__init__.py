@@ -6,11 +6,11 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _build(name, header):
+def _build(name, *headers):
     so = os.path.join(_HERE, "_%s.so" % name)
     src = os.path.join(_HERE, "%s.cpp" % name)
-    hdr = os.path.join(_HERE, "..", "..", "respmon_b200", "csrc", header)
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    deps = [src] + [os.path.join(_HERE, "..", "..", "respmon_b200", "csrc", h) for h in headers]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, src])
     return C.CDLL(so)
 
@@ -30,7 +30,7 @@ def load_heat():
 
 
 def load_lm_group():
-    return _build("lm_group_host", "lm_group.cuh")
+    return _build("lm_group_host", "lm_group.cuh", "signal_core.h")
 
 
 def load_pyr():
