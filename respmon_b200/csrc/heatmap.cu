@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(256) minmax_seed_kernel(const TileParams p, in
   }
 }
 
-// Developer switch (round-2 experiment): -DHM_MIN_BLOCKS=4 caps the passes at 128 registers for a fourth resident block.
+// Developer switch (untimed experiment): -DHM_MIN_BLOCKS=4 caps the passes at 128 registers for a fourth resident block.
 #ifdef HM_MIN_BLOCKS
 #define HM_LAUNCH_BOUNDS __launch_bounds__(128, HM_MIN_BLOCKS)
 #else

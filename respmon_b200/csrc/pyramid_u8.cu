@@ -23,7 +23,7 @@
 
 #define PU_STAGES 4
 #define PU_ROWS 8
-// Developer switch (round-2 experiment, default off): the x1 taps of the 5-tap rows as a mask on the ALU pipe instead of a
+// Developer switch (untimed experiment, default off): the x1 taps of the 5-tap rows as a mask on the ALU pipe instead of a
 // dot product with the coefficient vector (…, 0, 1) on the multiplier pipe.  Bit 0: level-1 rows (dp2a), bit 1: level-0
 // rows (dp4a).  Integer arithmetic either way, identical results.
 #ifndef PU_ALU_TAPS

@@ -426,7 +426,7 @@ L3_INL void l3_put(double v[3], int i, double x) {
 L3_NOINL double l3_div(double a, double b) { return a / b; }
 L3_NOINL double l3_sqrt(double a) { return sqrt(a); }
 #ifdef LM_DIV3
-// Developer switch (round-2 experiment, off by default until it has been timed): three independent quotients in one
+// Developer switch (experiment, off by default until it has been timed): three independent quotients in one
 // call -- the same three IEEE divisions, but their instruction chains interleave, so the call costs about one
 // division's latency instead of three (a fit is a latency chain of exactly these calls).  Same bits either way.
 struct L3Triple { double a, b, c; };

@@ -1,4 +1,4 @@
-"""Developer tool (round-2 experiment): Engine.run_batch(cal_parts=k) -- the calibration of k groups of clips on side
+"""Developer tool (untimed experiment): Engine.run_batch(cal_parts=k) -- the calibration of k groups of clips on side
 streams next to each other -- against the default, at the bench shapes: step time and identical records.
     python tools/dev_cal_split.py [n_clips] [steps]"""
 import os, sys

@@ -1,4 +1,4 @@
-"""Developer tool (round-2 experiment): the Gaussian-fit options against the default, at the bench shapes --
+"""Developer tool (untimed experiment): the Gaussian-fit options against the default, at the bench shapes --
 "fit_bail_nfev" (the first pass gives up on a fit after N evaluations, a second pass runs those fits one per warp),
 "fit_blocks_per_sm" (fewer resident fit blocks) and "fit_sync" (warp-synchronous first pass).
     python tools/dev_fit_solo.py [n_clips] [steps]

@@ -1,4 +1,4 @@
-"""Developer tool (round-2 experiment): option "temporal_sparse" (band-pass through the kept bins only) against the
+"""Developer tool (untimed experiment): option "temporal_sparse" (band-pass through the kept bins only) against the
 default FFT kernel: per-kernel time at the bench shape, output difference, bit-identity with the any-T direct kernel, and
 whether a whole batch still yields the same records.
     python tools/dev_temporal_sparse.py"""
