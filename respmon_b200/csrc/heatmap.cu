@@ -274,6 +274,29 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
   };
 #pragma unroll
   for (int t = 0; t < HM_STAGES - 1; ++t) issue(t);
+#ifdef HM_ONE_BARRIER
+  // Developer switch (untimed experiment): one barrier per evaluated frame in the lazy path.  The level-2 patch of frame
+  // t + 1 is expanded (into the other of two patch buffers) in the iteration that evaluates frame t, so the barrier at
+  // the top of an iteration publishes both the expanded patch of frame t and the landed level-3 patch of frame t + 1.
+  static_assert(HM_STAGES >= 3, "the one-barrier pipeline keeps one level-3 patch more in flight");
+  auto expand_patch = [&](int tt) {
+    const double* s3 = stage3 + (tt % HM_STAGES) * HM_P3;
+    double* dst2 = stage + (tt & 1) * HM_PW * HM_PH;
+#pragma unroll
+    for (int c = 0; c < HM_COPIES; ++c) {
+      const int e = tid + c * 128;
+      if (e < n_patch) {
+        const int r = e / pwid, cc = e - r * pwid;
+        dst2[r * HM_PW + cc] = a2_value(s3, pw3, x3lo, y3lo, p.w3, p.h3, xlo + cc, ylo + r);
+      }
+    }
+  };
+  if (lazy && n_list > 0) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(HM_STAGES - 2) : "memory");   // frame 0 has landed
+    __syncthreads();
+    expand_patch(0);
+  }
+#endif
 
   {
     // pass 1 walks the frame list; pass 2 walks every frame in order and consumes the list as it goes (k = position of
@@ -306,6 +329,15 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
         }
       }
       const int t = k++;               // position in the staging ring
+#ifdef HM_ONE_BARRIER
+      if (lazy) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(HM_STAGES - 3) : "memory");   // frame t + 1 has landed
+        __syncthreads();               // patch t (expanded last iteration) is complete; everyone is done with frame t - 1
+        issue(t + HM_STAGES - 1);      // refills the level-3 slot of frame t - 1
+        if (t + 1 < n_list) expand_patch(t + 1);
+      } else
+#endif
+      {
       asm volatile("cp.async.wait_group %0;\n" ::"n"(HM_STAGES - 2) : "memory");
       __syncthreads();                 // frame t has landed for everyone; everyone is done with frame t-1's stage
       issue(t + HM_STAGES - 1);        // refills the stage frame t-1 used
@@ -321,8 +353,13 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
         }
         __syncthreads();               // the patch is complete (the barrier above keeps the previous frame's readers out)
       }
+      }
       if (!active) continue;
+#ifdef HM_ONE_BARRIER
+      const double* l2 = lazy ? stage + (t & 1) * HM_PW * HM_PH : stage + (t % HM_STAGES) * HM_PW * HM_PH;
+#else
       const double* l2 = lazy ? stage : stage + (t % HM_STAGES) * HM_PW * HM_PH;
+#endif
       double v[4][4], o[4][4];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
