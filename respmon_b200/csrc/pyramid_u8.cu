@@ -220,7 +220,14 @@ __global__ void __launch_bounds__(PU_BOUND_WARPS * 32, PU_CTAS_PER_SM) pyramid_f
   const long long g3_elems = (long long)p.W3 * p.H3;
   for (long long frame = (long long)blockIdx.x * p.frames_per_cta + slot; frame < p.n_frames;
        frame += (long long)gridDim.x * p.frames_per_cta) {
+#ifdef PU_IDX32
+    // Developer switch (untimed experiment): the 64-bit division costs 8 % of the kernel's stall samples (ncu r01m) for one
+    // use per frame; frame counts and segment lengths fit 32 bits (checked by pu_launch)
+    const unsigned fr = (unsigned)frame, sl = (unsigned)p.seg_len;
+    const long long sframe = (long long)(fr / sl) * p.seg_stride + p.seg_first + (long long)(fr % sl);
+#else
     const long long sframe = (frame / p.seg_len) * p.seg_stride + p.seg_first + frame % p.seg_len;
+#endif
     const uint8_t* fsrc = p.frames + sframe * p.frame_elems;
     uint32_t* g3 = p.g3 + frame * g3_elems;
     // The strips of a frame share their halo columns.  Left alone, the warps of a slot drift apart over the frames (edge
@@ -251,6 +258,10 @@ int32_t pu_launch(rm_handle* h, const uint8_t* frames, uint32_t* g3, long long n
   p.n_strips = (p.W3 + cap - 1) / cap;
   p.cols_per_strip = (p.W3 + p.n_strips - 1) / p.n_strips;
   if (p.n_strips > 16) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: frame wider than 3584 pixels", __func__);
+#ifdef PU_IDX32
+  if (n_frames >= (1ll << 31) || seg_len >= (1ll << 31) || seg_len < 1)
+    return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: more than 2^31 frames", __func__);
+#endif
   p.frames_per_cta = PU_MAX_WARPS / p.n_strips;
   const int warps = p.frames_per_cta * p.n_strips;
   const int smem = warps * PU_STAGES * PU_STAGE_BYTES;
