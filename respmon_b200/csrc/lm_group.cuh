@@ -72,11 +72,28 @@ template <int G>
 __device__ __noinline__ void lmg_resid(const LmGroup& g, int m, const double* xs, const double* ys, const double* p,
                                           double* f) {
   const double denom = 2.0 * (p[2] * p[2]) + SC_DBL_EPS;
+#ifdef LM_ROWS2
+  // Developer switch (untimed experiment): two rows per trip -- the same division and exp per row, but the two latency
+  // chains overlap (division + exp of the model are 11 % of the fit kernel's stall samples, ncu r01m)
+  int i = g.sub;
+#pragma unroll 1
+  for (; i + G < m; i += 2 * G) {
+    const double d0 = xs[i] - p[1], d1 = xs[i + G] - p[1];
+    const double e0 = exp(-(d0 * d0) / denom), e1 = exp(-(d1 * d1) / denom);
+    f[i] = p[0] * e0 - ys[i];
+    f[i + G] = p[0] * e1 - ys[i + G];
+  }
+  if (i < m) {
+    const double d = xs[i] - p[1];
+    f[i] = p[0] * exp(-(d * d) / denom) - ys[i];
+  }
+#else
 #pragma unroll 1
   for (int i = g.sub; i < m; i += G) {
     const double d = xs[i] - p[1];
     f[i] = p[0] * exp(-(d * d) / denom) - ys[i];
   }
+#endif
 }
 
 // xs, ys, fvec, wa4 (m each) and fjac (3m, column-major) are the group's shared-memory slices; xs/ys filled by the
@@ -142,8 +159,21 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
         x[j] = temp + h;
         lmg_resid<G>(g, m, xs, ys, x, wa4);
         x[j] = temp;
+#ifdef LM_ROWS2
+        {
+          int i = g.sub;
+#pragma unroll 1
+          for (; i + G < m; i += 2 * G) {
+            const double q0 = (wa4[i] - fvec[i]) / h, q1 = (wa4[i + G] - fvec[i + G]) / h;
+            fjac[i + j * m] = q0;
+            fjac[i + G + j * m] = q1;
+          }
+          if (i < m) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
+        }
+#else
 #pragma unroll 1
         for (int i = g.sub; i < m; i += G) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
+#endif
       }
       nfev += 3;
     }
@@ -181,8 +211,22 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
         if (ajnorm != 0.0) {
           if (fjac[j + j * m] < 0.0) ajnorm = -ajnorm;
           __syncwarp(g.mask);                                   // everyone has read the diagonal element
+#ifdef LM_ROWS2
+          {
+            int i = j + g.sub;
+#pragma unroll 1
+            for (; i + G < m; i += 2 * G) {
+              const double q0 = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
+              const double q1 = fjac[i + G + j * m] / ajnorm + 0.0;   // i + G > j; the + 0.0 keeps -0.0 -> +0.0
+              fjac[i + j * m] = q0;
+              fjac[i + G + j * m] = q1;
+            }
+            if (i < m) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
+          }
+#else
 #pragma unroll 1
           for (int i = j + g.sub; i < m; i += G) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
+#endif
           __syncwarp(g.mask);
           const double ajj = fjac[j + j * m];
 #pragma unroll

@@ -200,16 +200,19 @@ def test_div3_build_switch_changes_no_bits(lib, golden, tmp_path):
     # the same switch in the group-cooperative routine of the kernels (gnorm, the ratio test, fdjac's step size)
     from hostsim import load_lm_group
     grp = load_lm_group()
-    so2 = str(tmp_path / "_lm_group_host_div3.so")
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-DLM_DIV3", "-shared", "-fPIC", "-o", so2,
-                           os.path.join(here, "hostsim", "lm_group_host.cpp")])
-    alt2 = C.CDLL(so2)
+    # ... and together with -DLM_ROWS2 (two rows of the model / Jacobian per trip)
+    alts = []
+    for tag, flags in (("div3", ["-DLM_DIV3"]), ("rows2", ["-DLM_ROWS2"]), ("both", ["-DLM_DIV3", "-DLM_ROWS2"])):
+        so2 = str(tmp_path / ("_lm_group_host_%s.so" % tag))
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", *flags, "-shared", "-fPIC", "-o", so2,
+                               os.path.join(here, "hostsim", "lm_group_host.cpp")])
+        alts.append(C.CDLL(so2))
     for xs, ys in cases:
         out = []
-        for fn in (grp.host_group_fit, alt2.host_group_fit):
+        for fn in [grp.host_group_fit] + [a.host_group_fit for a in alts]:
             p = np.array([ys.max(), xs[0], (xs[1] - xs[0]) * 5])
             out.append((fn(len(xs), dptr(xs), dptr(ys), dptr(p), 0), p.tobytes()))
-        assert out[0] == out[1]
+        assert all(o == out[0] for o in out)
 
 
 def test_group_lm_forms_agree_on_the_host(lib, golden):
