@@ -317,6 +317,25 @@ __global__ void __launch_bounds__(256) pyramid_tail_kernel(const TailParams p) {
       const int sw = p.w[p.first - 1], sh = p.h[p.first - 1], dw = p.w[p.first], dh = p.h[p.first];
       uint32_t* s = reinterpret_cast<uint32_t*>(g + acc);     // staged as integers: half the shared memory of float64
       const uint32_t* src = p.g3_in + f * (long long)(sw * sh);
+#ifdef PT_VEC_STAGE
+      // Developer switch (untimed experiment): 38 % of this kernel's stall samples sit on the staging loop (ncu r01k) --
+      // 16-byte loads, all of a thread's loads in flight before the first store
+      if (((sw * sh) & 3) == 0 && (acc & 1) == 0) {      // 16-byte aligned on both sides
+        const uint4* src4 = reinterpret_cast<const uint4*>(src);
+        uint4* s4 = reinterpret_cast<uint4*>(s);
+        const int n4 = (sw * sh) >> 2;
+#pragma unroll 1
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * blockDim.x) {
+          uint4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (i0 + u * (int)blockDim.x < n4) v[u] = src4[i0 + u * blockDim.x];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (i0 + u * (int)blockDim.x < n4) s4[i0 + u * blockDim.x] = v[u];
+        }
+      } else
+#endif
       for (int i = threadIdx.x; i < sw * sh; i += blockDim.x) s[i] = src[i];
       __syncthreads();
       for (int i = threadIdx.x; i < dw * dh; i += blockDim.x) {
