@@ -12,7 +12,8 @@
 #     python -m respmon_b200.build --variant ptv  "-DPT_VEC_STAGE"
 #     python -m respmon_b200.build --variant hm1b "-DHM_ONE_BARRIER"
 #     python -m respmon_b200.build --variant hm1b4 "-DHM_ONE_BARRIER -DHM_MIN_BLOCKS=4"
-#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh r02a w24 alu1 alu2 div3 lmilp hm4 b21 i32 ptv hm1b hm1b4'
+#     python -m respmon_b200.build --variant hmall "-DHM_ONE_BARRIER -DHM_MIN_BLOCKS=4 -DHM_PAR_LIST"
+#   gpurun --timeout 900 -- 'bash tools/round2_first_call.sh r02a w24 alu1 alu2 div3 lmilp hm4 b21 i32 ptv hm1b hm1b4 hmall'
 TAG=${1:-r02a}; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
