@@ -171,3 +171,25 @@ def test_locate_writes_the_reference_calibration_png(golden, name, tmp_path, mon
         for label, (r, c) in panels.items():
             a, b = png[r * H:(r + 1) * H, c * W:(c + 1) * W], gold[r * H:(r + 1) * H, c * W:(c + 1) * W]
             assert np.array_equal(a, b), "%s panel of calibration%d.png: %d bytes differ" % (label, i, int((a != b).sum()))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("RESPMON_EXTRA_GPU_TESTS") != "1",
+                    reason="added after the round's last GPU run; enable with RESPMON_EXTRA_GPU_TESTS=1 once it has passed on a B200")
+@pytest.mark.parametrize("name,method,fps_limit", [("mode_average_qvga_s1", "average", 10),
+                                                   ("mode_average_long_s4", "average", 10),
+                                                   ("mode_flow_fps5_s1", "flow", 5)])
+def test_monitor_other_branches_match_reference(golden, name, method, fps_limit):
+    """'average' extraction (base.py:355-358) and fps_limit below the capture rate (base.py:303-310) against the
+    unmodified reference's attributes (tools/make_golden_modes.py); the CPU twin of this test, with the engine replaced by
+    the oracle, is tests/test_monitor_host.py::test_other_branches_match_the_reference."""
+    from respmon_b200.monitor import RespiratoryMonitor
+    fix = golden(name)
+    spec, clip = clip_from_fixture(fix)
+    rm = RespiratoryMonitor(clip, visualize=None, save_all_data=False, motion_extraction_method=method, fps_limit=fps_limit)
+    assert float(rm.fps) == float(fix["fps"])
+    assert (rm.x, rm.y, rm.w, rm.h) == tuple(int(v) for v in fix["roi"])
+    data = np.array(rm.data)
+    assert data.shape == fix["data"].shape and np.sqrt(np.mean((data - fix["data"]) ** 2)) <= 1e-4
+    assert len(rm.freq) == len(fix["freq"]) and np.max(np.abs(np.array(rm.freq) - fix["freq"])) <= 0.5
+    assert [int(v) for v in rm.peak_indices] == [int(v) for v in fix["peaks"]]
+    assert rm.state == str(fix["state"])

@@ -167,3 +167,23 @@ def test_tracking_lost_goes_through_error_and_recalibrates(monitor_cls):
     assert len(rm.data) == min(128, 600 - 342)
     assert not np.isnan(np.array(rm.data)).any()
     assert len(rm.freq) > 0 and abs(rm.freq[-1] - spec.truth_bpm) <= 3.0
+
+
+@pytest.mark.parametrize("name,method,fps_limit", [("mode_average_qvga_s1", "average", 10),
+                                                   ("mode_average_long_s4", "average", 10),
+                                                   ("mode_flow_fps5_s1", "flow", 5)])
+def test_other_branches_match_the_reference(monitor_cls, golden, name, method, fps_limit):
+    """The 'average' extraction (the reference's constructor default) and fps_limit below the capture rate: the monitor's
+    attributes against the unmodified reference's (tools/make_golden_modes.py)."""
+    fix = golden(name)
+    spec, clip = clip_from_fixture(fix)
+    rm = monitor_cls(clip, visualize=None, save_all_data=False, motion_extraction_method=method, fps_limit=fps_limit)
+    assert float(rm.fps) == float(fix["fps"])
+    assert (rm.x, rm.y, rm.w, rm.h) == tuple(int(v) for v in fix["roi"])
+    data = np.array(rm.data)
+    assert data.shape == fix["data"].shape and np.sqrt(np.mean((data - fix["data"]) ** 2)) <= 1e-6
+    np.testing.assert_allclose(np.array(rm.t), fix["t"], rtol=0, atol=1e-12)
+    assert len(rm.freq) == len(fix["freq"]) and np.max(np.abs(np.array(rm.freq) - fix["freq"])) <= 1e-6
+    assert [int(v) for v in rm.peak_indices] == [int(v) for v in fix["peaks"]]
+    np.testing.assert_allclose(np.asarray(rm.filtered_data), fix["filtered"], rtol=0, atol=1e-6)
+    assert rm.state == str(fix["state"])

@@ -59,3 +59,24 @@ def test_oracle_equals_live_reference():
     assert np.array_equal(np.array(res["window_data"]), np.array(rm.data))
     assert np.array_equal(np.array(res["freq_window"]), np.array(rm.freq))
     assert list(res["peaks"]) == [int(p) for p in rm.peak_indices]
+
+
+MODES = [("mode_average_qvga_s1", "average", 10), ("mode_average_long_s4", "average", 10), ("mode_flow_fps5_s1", "flow", 5)]
+
+
+@pytest.mark.parametrize("name,method,fps_limit", MODES)
+def test_other_branches_match_reference_golden(golden, name, method, fps_limit):
+    """motion_extraction_method='average' (base.py:355-358) and a frame-rate limit below the capture rate
+    (base.py:303-310) against what the unmodified reference left behind (tools/make_golden_modes.py)."""
+    fix = golden(name)
+    _, clip = clip_from_fixture(fix)
+    res = P.run_clip(clip, fps=10.0, method=method, fps_limit=fps_limit)
+    assert tuple(res["roi"]) == tuple(int(v) for v in fix["roi"])
+    data = np.array(res["window_data"])
+    assert data.shape == fix["data"].shape
+    assert np.sqrt(np.mean((data - fix["data"]) ** 2)) <= 1e-6
+    assert np.abs(np.array(res["t"]) - fix["t"]).max() <= 1e-12
+    assert len(res["freq_window"]) == len(fix["freq"])
+    assert np.abs(np.array(res["freq_window"]) - fix["freq"]).max() <= 1e-6
+    assert list(res["peaks"]) == [int(p) for p in fix["peaks"]]
+    assert np.abs(res["filtered"] - fix["filtered"]).max() <= 1e-6
