@@ -187,3 +187,15 @@ def test_other_branches_match_the_reference(monitor_cls, golden, name, method, f
     assert [int(v) for v in rm.peak_indices] == [int(v) for v in fix["peaks"]]
     np.testing.assert_allclose(np.asarray(rm.filtered_data), fix["filtered"], rtol=0, atol=1e-6)
     assert rm.state == str(fix["state"])
+
+
+def test_static_scene_keeps_recalibrating(monitor_cls):
+    """Nothing moves: locate() finds no contour (base.py:569-570), the buffer is refilled and calibration retried
+    (base.py:451-454).  The unmodified reference ends a 300-frame static clip in 'calibration' with no ROI, no data and
+    41 frames in the buffer (1 dropped + 2 x (128 + the locate frame) + 41); so must the drop-in."""
+    from respmon_b200 import synth
+    frame = synth.make_clip(synth.clip_spec(1, 320, 240, 2))[:1]
+    rm = monitor_cls(np.repeat(frame, 300, axis=0), visualize=None, save_all_data=False, motion_extraction_method="flow")
+    assert rm.state == "calibration" and rm.x is None and len(rm.data) == 0
+    assert [c[0] for c in rm.engine.calls] == ["locate", "locate"]
+    assert rm.calibration_buffer_idx == 41
