@@ -62,3 +62,48 @@ def test_pyramid_functions_equal_the_reference(w, h, levels):
     assert np.array_equal(out_a, np.asarray(out_b))
     assert np.array_equal(vp_a[0], np.asarray(vp_b[0]))      # both also leave the result in pyramid[0] (pyramid.py:65)
     assert np.abs(out_a - video).max() <= 1e-12              # collapse o laplacian = identity
+
+
+class Cv2SciPyEngine(Cv2Engine):
+    """... plus the temporal filter (SciPy's fftpack, as the reference) and the clip of transforms.py:184-192."""
+
+    def __init__(self, freq_min, freq_max, amplification):
+        from types import SimpleNamespace
+        self.params = SimpleNamespace(freq_min=freq_min, freq_max=freq_max, amplification=float(amplification))
+        self.device_index = 0
+
+    def temporal_bandpass(self, lap, fps, out=None):
+        from oracle import cpu_path as P
+        x = lap[0].numpy()
+        return torch.from_numpy(P.temporal_filter(x, fps, self.params.freq_min, self.params.freq_max,
+                                                  self.params.amplification))[None]
+
+    def volume_clip_mean(self, raw, threshold=None, want_clipped=True, want_avg=True):
+        r = raw.numpy()
+        lo, hi = r.min(), r.max()
+        top = hi - (hi - lo) * threshold
+        clipped = r.copy()
+        clipped[r >= top] = lo
+        return torch.from_numpy(clipped), None, torch.tensor([lo, hi])
+
+
+@pytest.mark.parametrize("w,h,levels,skip", [(160, 120, 7, 3), (250, 187, 9, 4)])
+def test_eulerian_magnification_glue_equals_the_reference(w, h, levels, skip):
+    """transforms.py:144-198: which levels are filtered, the zero levels, the collapse and the clip, through
+    respmon_b200/transforms.py with library arithmetic on both sides."""
+    from respmon_b200 import synth, transforms as mine
+    ref = shim.load_reference().transforms
+    clip = synth.make_clip(synth.clip_spec(2, w, h, 64))
+    vid = clip.astype(np.float64) * (1.0 / 255)
+    eng = Cv2SciPyEngine(0.1, 1.0, 500)
+    got, got_raw = mine.eulerian_magnification_bandpass(vid, 10.0, 0.1, 1.0, 500, pyramid_levels=levels,
+                                                        skip_levels_at_top=skip, threshold=0.7, engine=eng)
+    exp, exp_raw = ref.eulerian_magnification_bandpass(vid, 10.0, 0.1, 1.0, 500, pyramid_levels=levels,
+                                                       skip_levels_at_top=skip, threshold=0.7)
+    assert got.shape == exp.shape == vid.shape
+    assert np.array_equal(got_raw, exp_raw)
+    assert np.array_equal(got, exp)
+    x = np.random.default_rng(0).standard_normal((64, 5, 7))
+    assert np.array_equal(mine.temporal_bandpass_filter_fft(x, 10.0, freq_min=0.1, freq_max=1.0, amplification_factor=500,
+                                                            engine=eng),
+                          ref.temporal_bandpass_filter_fft(x, 10.0, freq_min=0.1, freq_max=1.0, amplification_factor=500))
