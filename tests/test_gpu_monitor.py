@@ -177,7 +177,9 @@ def test_locate_writes_the_reference_calibration_png(golden, name, tmp_path, mon
                     reason="added after the round's last GPU run; enable with RESPMON_EXTRA_GPU_TESTS=1 once it has passed on a B200")
 @pytest.mark.parametrize("name,method,fps_limit", [("mode_average_qvga_s1", "average", 10),
                                                    ("mode_average_long_s4", "average", 10),
-                                                   ("mode_flow_fps5_s1", "flow", 5)])
+                                                   ("mode_flow_fps5_s1", "flow", 5),
+                                                   ("mode_flow_720p_s5", "flow", 10),
+                                                   ("mode_flow_1080p_s6", "flow", 10)])
 def test_monitor_other_branches_match_reference(golden, name, method, fps_limit):
     """'average' extraction (base.py:355-358) and fps_limit below the capture rate (base.py:303-310) against the
     unmodified reference's attributes (tools/make_golden_modes.py); the CPU twin of this test, with the engine replaced by

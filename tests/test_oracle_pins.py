@@ -61,7 +61,8 @@ def test_oracle_equals_live_reference():
     assert list(res["peaks"]) == [int(p) for p in rm.peak_indices]
 
 
-MODES = [("mode_average_qvga_s1", "average", 10), ("mode_average_long_s4", "average", 10), ("mode_flow_fps5_s1", "flow", 5)]
+MODES = [("mode_average_qvga_s1", "average", 10), ("mode_average_long_s4", "average", 10), ("mode_flow_fps5_s1", "flow", 5),
+         ("mode_flow_720p_s5", "flow", 10), ("mode_flow_1080p_s6", "flow", 10)]
 
 
 @pytest.mark.parametrize("name,method,fps_limit", MODES)

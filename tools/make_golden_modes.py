@@ -20,6 +20,8 @@ CASES = [  # (name, W, H, T, seed, method, fps_limit)
     ("mode_average_qvga_s1", 320, 240, 256, 1, "average", 10),
     ("mode_average_long_s4", 320, 240, 420, 4, "average", 10),
     ("mode_flow_fps5_s1", 320, 240, 256, 1, "flow", 5),
+    ("mode_flow_720p_s5", 1280, 720, 256, 5, "flow", 10),          # BASELINE config 4's resolution
+    ("mode_flow_1080p_s6", 1920, 1080, 256, 6, "flow", 10),        # the largest class of BASELINE config 5
 ]
 
 
@@ -27,7 +29,10 @@ def main():
     import cv2
     import scipy
     out_dir = os.path.join(ROOT, "tests", "golden")
+    only = set(sys.argv[1:])
     for name, W, H, T, seed, method, fps_limit in CASES:
+        if only and name not in only:
+            continue
         spec = synth.clip_spec(seed, W, H, T)
         clip = synth.make_clip(spec)
         rm = shim.run_reference_monitor(clip, fps=10, method=method, fps_limit=fps_limit)
