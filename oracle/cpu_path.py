@@ -255,7 +255,7 @@ def measure_window(data, t, fps, freq_max=FREQ_MAX):
 
 
 # ----------------------------------------------------------------------------- whole clip
-def run_clip(frames_u8, fps=10.0, method="flow", fps_limit=10):
+def run_clip(frames_u8, fps=10.0, method="flow", fps_limit=10, max_area=np.inf):
     """The frame routing of run() (base.py:409-513) on an in-memory uint8 clip.
 
     frame 0 -> 'initialize' (dropped); frames 1..128 -> calibration buffer; frame 129 triggers locate and is
@@ -279,6 +279,7 @@ def run_clip(frames_u8, fps=10.0, method="flow", fps_limit=10):
             if roi is None:
                 buf = []
                 continue
+            roi = shrink_box(*roi, max_area)                                 # base.py:456-458
             res["roi"] = roi
             state = "measure"
         else:

@@ -117,17 +117,25 @@ def load_reference():
     return _loaded
 
 
-def run_reference_monitor(frames_u8, fps=10, method="flow", fps_limit=10):
-    """Construct the reference's RespiratoryMonitor on an in-memory clip; its ctor runs to end-of-stream (base.py:164)."""
+def run_reference_monitor(frames_u8, fps=10, method="flow", fps_limit=10, max_area=None):
+    """Construct the reference's RespiratoryMonitor on an in-memory clip; its ctor runs to end-of-stream (base.py:164).
+
+    max_area: the hyper-parameter `maximum_bounding_box_area` (base.py:80) is hard-coded to np.inf inside the
+    constructor that also runs the program, so a finite value can only be injected where it is used: the `maximum_area`
+    argument of the call at base.py:457-458 is replaced; tools.reduce_bounding_box itself (tools.py:48-57) runs unmodified."""
     ref = load_reference()
     cv2 = ref.cv2
     saved = cv2.VideoCapture
+    saved_reduce = ref.base.reduce_bounding_box
     cv2.VideoCapture = lambda target: FakeCapture(frames_u8, fps)
+    if max_area is not None:
+        ref.base.reduce_bounding_box = lambda x, y, w, h, _inf: ref.tools.reduce_bounding_box(x, y, w, h, max_area)
     try:
         rm = ref.base.RespiratoryMonitor("synthetic", visualize=None, save_all_data=False,
                                          motion_extraction_method=method, fps_limit=fps_limit)
     finally:
         cv2.VideoCapture = saved
+        ref.base.reduce_bounding_box = saved_reduce
     return rm
 
 

@@ -63,13 +63,18 @@ class Benchmarker:
 
 
 def reduce_bounding_box(x, y, w, h, maximum_area):
-    """tools.reduce_bounding_box (tools.py:48-57): shrink the box about its centre until its area is maximum_area."""
-    area = w * h
-    if area <= maximum_area:
+    """tools.reduce_bounding_box (tools.py:48-57): shrink the box about its centre until its area is maximum_area.
+    Width and height stay unrounded while the corner is computed; all four values are rounded half-to-even at the end
+    (np.round), exactly as the reference does."""
+    start_area = w * h
+    if start_area <= maximum_area:
         return x, y, w, h
-    ratio = math.sqrt(float(maximum_area) / float(area))
-    new_w, new_h = int(np.floor(w * ratio)), int(np.floor(h * ratio))
-    return int(x + (w - new_w) / 2), int(y + (h - new_h) / 2), new_w, new_h
+    shrink = np.sqrt(float(maximum_area) / float(start_area))
+    new_w = w * shrink
+    new_h = h * shrink
+    new_x = x + ((w - new_w) / 2.)
+    new_y = y + ((h - new_h) / 2.)
+    return int(np.round(new_x)), int(np.round(new_y)), int(np.round(new_w)), int(np.round(new_h))
 
 
 class _ArrayCapture:
@@ -212,7 +217,9 @@ class RespiratoryMonitor:
         self.status = None                              # rm_clip_status of the last calibrate/measure cycle
         self.calibration_start_time = np.nan
 
-        self.engine = Engine(device, **self._engine_params())   # raises without the CUDA library / a device
+        self._device_arg = device
+        self._engine_key = self._engine_params()
+        self.engine = Engine(device, **self._engine_key)        # raises without the CUDA library / a device
         self._frames = None                             # (T,H,W) uint8 on the device once the stream is drained
         self._pos = 0
         if autorun:
@@ -228,6 +235,18 @@ class RespiratoryMonitor:
                     lk_eps=self.lk_params["criteria"][2], gaussian_cutoff=self.gaussian_cutoff,
                     filter_order=self.filter_order, measure_buffer_len=self.measure_buffer_length,
                     measure_init_len=self.measure_initialization_length)
+
+    def _sync_engine(self):
+        """The reference reads its hyper-parameter attributes (base.py:80-106) at use time; the kernels read rm_params,
+        fixed at rm_create.  If an attribute was changed since the handle was made (autorun=False, then e.g.
+        `rm.threshold = .1`), make a new handle from the current values before the next device call."""
+        key = self._engine_params()
+        if key != self._engine_key:
+            old = self.engine
+            self.engine = Engine(self._device_arg if self._device_arg is not None else old.device_index, **key)
+            self._engine_key = key
+            old.close()
+        return self.engine
 
     @staticmethod
     def _open_capture(target, source_fps):
@@ -334,6 +353,13 @@ class RespiratoryMonitor:
         hyper = dict(freq_min=freq_min, freq_max=freq_max, amplification=amplification, pyramid_levels=pyramid_levels,
                      skip_levels_at_top=skip_levels_at_top, temporal_threshold=temporal_threshold,
                      threshold=int(threshold))
+        if engine is not None:
+            # a handle carries its hyper-parameters (rm_params): refuse explicit arguments that disagree with it rather
+            # than silently calibrating with the handle's values
+            for k, v in hyper.items():
+                have = getattr(engine.params, k, v)
+                if (abs(float(have) - float(v)) > 1e-12 * max(1.0, abs(float(v)))) if isinstance(v, float) else have != v:
+                    raise ValueError("locate(%s=%r) disagrees with the engine's %r" % (k, v, have))
         eng = engine or Engine(None, **hyper)
         vid = calibration_video_data
         vid = torch.from_numpy(np.ascontiguousarray(vid)) if isinstance(vid, np.ndarray) else vid
@@ -372,6 +398,7 @@ class RespiratoryMonitor:
         self.calibration_buffer_idx = self.calibration_buffer_target_length
         self.detect_fps()
         self.peak_minimum_sample_distance = int(np.floor(self.fps / self.freq_max))
+        self._sync_engine()
         self.benchmarker.tick_start('Calibration Measurement')
         location = self.locate(frames, self.fps, save_calibration_image=self.save_calibration_image,
                                freq_min=self.freq_min, freq_max=self.freq_max,
@@ -398,7 +425,7 @@ class RespiratoryMonitor:
         return [float(v) for v in out["data"]]
 
     def _measure_block(self, frames):
-        eng = self.engine
+        eng = self._sync_engine()
         n = frames.shape[0]
         roi = torch.tensor([[self.x, self.y, self.w, self.h]], dtype=torch.int32, device=eng.device)
         clips = frames[None].contiguous() if not frames.is_contiguous() else frames[None]
@@ -425,7 +452,7 @@ class RespiratoryMonitor:
         return idx, [float("nan")] * len(idx)
 
     def _signal(self, data):
-        eng = self.engine
+        eng = self._sync_engine()
         d = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float64)[None]).to(eng.device)
         s = eng.signal_bpm(d, float(self.fps))
         n = data.shape[0]
@@ -473,7 +500,7 @@ class RespiratoryMonitor:
 
     def _run_measure(self):
         """Every remaining frame through the 'measure' branch (base.py:464-495), in one device pass."""
-        eng = self.engine
+        eng = self._sync_engine()
         frames = self._frames[self._pos:]
         n = frames.shape[0]
         self.benchmarker.tick_start('Measurement Loop')

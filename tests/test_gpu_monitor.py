@@ -173,21 +173,27 @@ def test_locate_writes_the_reference_calibration_png(golden, name, tmp_path, mon
             assert np.array_equal(a, b), "%s panel of calibration%d.png: %d bytes differ" % (label, i, int((a != b).sum()))
 
 
-@pytest.mark.skipif(__import__("os").environ.get("RESPMON_EXTRA_GPU_TESTS") != "1",
-                    reason="added after the round's last GPU run; enable with RESPMON_EXTRA_GPU_TESTS=1 once it has passed on a B200")
 @pytest.mark.parametrize("name,method,fps_limit", [("mode_average_qvga_s1", "average", 10),
                                                    ("mode_average_long_s4", "average", 10),
                                                    ("mode_flow_fps5_s1", "flow", 5),
                                                    ("mode_flow_720p_s5", "flow", 10),
-                                                   ("mode_flow_1080p_s6", "flow", 10)])
+                                                   ("mode_flow_1080p_s6", "flow", 10),
+                                                   ("mode_flow_maxarea600_s1", "flow", 10),
+                                                   ("mode_flow_maxarea777_s0", "flow", 10),
+                                                   ("mode_average_maxarea250_s3", "average", 10)])
 def test_monitor_other_branches_match_reference(golden, name, method, fps_limit):
-    """'average' extraction (base.py:355-358) and fps_limit below the capture rate (base.py:303-310) against the
-    unmodified reference's attributes (tools/make_golden_modes.py); the CPU twin of this test, with the engine replaced by
-    the oracle, is tests/test_monitor_host.py::test_other_branches_match_the_reference."""
+    """'average' extraction (base.py:355-358), fps_limit below the capture rate (base.py:303-310), 720p / 1080p clips and
+    a finite maximum_bounding_box_area (base.py:456-458 -> tools.py:48-57) against the unmodified reference's attributes
+    (tools/make_golden_modes.py); the CPU twin of this test, with the engine replaced by the oracle, is
+    tests/test_monitor_host.py::test_other_branches_match_the_reference."""
     from respmon_b200.monitor import RespiratoryMonitor
     fix = golden(name)
     spec, clip = clip_from_fixture(fix)
-    rm = RespiratoryMonitor(clip, visualize=None, save_all_data=False, motion_extraction_method=method, fps_limit=fps_limit)
+    rm = RespiratoryMonitor(clip, visualize=None, save_all_data=False, motion_extraction_method=method,
+                            fps_limit=fps_limit, autorun=False)
+    if "max_area" in fix:
+        rm.maximum_bounding_box_area = float(fix["max_area"])
+    rm.run()
     assert float(rm.fps) == float(fix["fps"])
     assert (rm.x, rm.y, rm.w, rm.h) == tuple(int(v) for v in fix["roi"])
     data = np.array(rm.data)

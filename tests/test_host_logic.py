@@ -43,12 +43,38 @@ def test_product_package_never_imports_the_oracle():
     assert out.returncode == 0, out.stdout + out.stderr
 
 
-def test_reduce_bounding_box_matches_reference_rule():
-    """tools.py:48-57."""
+def _random_boxes(n=2000, seed=7):
+    rng = np.random.default_rng(seed)
+    for _ in range(n):
+        x, y = int(rng.integers(0, 1900)), int(rng.integers(0, 1060))
+        w, h = int(rng.integers(1, 400)), int(rng.integers(1, 300))
+        yield x, y, w, h, float(rng.choice([50, 300, 1000, 2000, 2500.5, 4096, 10000, 1e9, np.inf]))
+
+
+def test_reduce_bounding_box_equals_the_oracle_on_random_boxes():
+    """tools.py:48-57 -- the product's host function against the oracle's restatement (the reference keeps new_w/new_h
+    unrounded while centring and np.round()s all four values)."""
+    from oracle.cpu_path import shrink_box
     from respmon_b200.monitor import reduce_bounding_box
     assert reduce_bounding_box(10, 20, 30, 40, np.inf) == (10, 20, 30, 40)
-    x, y, w, h = reduce_bounding_box(10, 20, 30, 40, 300)
-    assert w * h <= 300 and (w, h) == (15, 20) and (x, y) == (17, 30)
+    assert reduce_bounding_box(10, 20, 30, 40, 300) == (18, 30, 15, 20)            # value of the reference's function
+    assert reduce_bounding_box(10, 20, 100, 50, 2000) == (28, 29, 63, 32)
+    for x, y, w, h, area in _random_boxes():
+        assert reduce_bounding_box(x, y, w, h, area) == shrink_box(x, y, w, h, area), (x, y, w, h, area)
+
+
+def test_reduce_bounding_box_equals_the_reference_function():
+    """Same boxes through the UNMODIFIED reference's tools.reduce_bounding_box (container only)."""
+    from oracle import shim
+    if not shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from oracle.cpu_path import shrink_box
+    from respmon_b200.monitor import reduce_bounding_box
+    ref = shim.load_reference().tools.reduce_bounding_box
+    for x, y, w, h, area in _random_boxes():
+        want = tuple(int(v) for v in ref(x, y, w, h, area))
+        assert reduce_bounding_box(x, y, w, h, area) == want, (x, y, w, h, area)
+        assert shrink_box(x, y, w, h, area) == want
 
 
 @pytest.mark.parametrize("n,world", [(64, 8), (10, 4), (3, 8), (0, 2), (2048, 8)])

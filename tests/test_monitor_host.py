@@ -84,6 +84,9 @@ class OracleEngine:
         return dict(bpm=torch.from_numpy(bpm)[None], filtered=torch.from_numpy(filt)[None],
                     peaks=torch.from_numpy(pk_arr)[None], npeaks=torch.tensor([len(peaks)], dtype=torch.int32))
 
+    def close(self):
+        pass
+
     def bgr_to_gray(self, bgr):
         import cv2
         return torch.from_numpy(cv2.cvtColor(bgr.numpy(), cv2.COLOR_BGR2GRAY))
@@ -171,13 +174,21 @@ def test_tracking_lost_goes_through_error_and_recalibrates(monitor_cls):
 
 @pytest.mark.parametrize("name,method,fps_limit", [("mode_average_qvga_s1", "average", 10),
                                                    ("mode_average_long_s4", "average", 10),
-                                                   ("mode_flow_fps5_s1", "flow", 5)])
+                                                   ("mode_flow_fps5_s1", "flow", 5),
+                                                   ("mode_flow_maxarea600_s1", "flow", 10),
+                                                   ("mode_flow_maxarea777_s0", "flow", 10),
+                                                   ("mode_average_maxarea250_s3", "average", 10)])
 def test_other_branches_match_the_reference(monitor_cls, golden, name, method, fps_limit):
-    """The 'average' extraction (the reference's constructor default) and fps_limit below the capture rate: the monitor's
-    attributes against the unmodified reference's (tools/make_golden_modes.py)."""
+    """The 'average' extraction (the reference's constructor default), fps_limit below the capture rate and a finite
+    maximum_bounding_box_area (base.py:456-458 -> tools.py:48-57): the monitor's attributes against the unmodified
+    reference's (tools/make_golden_modes.py)."""
     fix = golden(name)
     spec, clip = clip_from_fixture(fix)
-    rm = monitor_cls(clip, visualize=None, save_all_data=False, motion_extraction_method=method, fps_limit=fps_limit)
+    rm = monitor_cls(clip, visualize=None, save_all_data=False, motion_extraction_method=method, fps_limit=fps_limit,
+                     autorun=False)
+    if "max_area" in fix:
+        rm.maximum_bounding_box_area = float(fix["max_area"])
+    rm.run()
     assert float(rm.fps) == float(fix["fps"])
     assert (rm.x, rm.y, rm.w, rm.h) == tuple(int(v) for v in fix["roi"])
     data = np.array(rm.data)
@@ -199,3 +210,19 @@ def test_static_scene_keeps_recalibrating(monitor_cls):
     assert rm.state == "calibration" and rm.x is None and len(rm.data) == 0
     assert [c[0] for c in rm.engine.calls] == ["locate", "locate"]
     assert rm.calibration_buffer_idx == 41
+
+
+def test_hyper_parameters_are_read_at_use_time(monitor_cls, golden):
+    """base.py reads self.threshold / freq_max / ... when it uses them (base.py:444-448, :342); the drop-in's handle is
+    rebuilt from the attributes when they changed after construction (autorun=False), and locate() refuses explicit
+    arguments that disagree with a handle it is given."""
+    fix = golden("qvga_s1")
+    spec, clip = clip_from_fixture(fix)
+    rm = monitor_cls(clip, visualize=None, save_all_data=False, motion_extraction_method="flow", autorun=False)
+    first = rm.engine
+    assert first.params.threshold == 20
+    rm.threshold = 0.2
+    rm.run()
+    assert rm.engine is not first and rm.engine.params.threshold == 51
+    with pytest.raises(ValueError, match="disagrees"):
+        monitor_cls.locate(clip[1:129], 10, threshold=20, engine=rm.engine)

@@ -62,7 +62,9 @@ def test_oracle_equals_live_reference():
 
 
 MODES = [("mode_average_qvga_s1", "average", 10), ("mode_average_long_s4", "average", 10), ("mode_flow_fps5_s1", "flow", 5),
-         ("mode_flow_720p_s5", "flow", 10), ("mode_flow_1080p_s6", "flow", 10)]
+         ("mode_flow_720p_s5", "flow", 10), ("mode_flow_1080p_s6", "flow", 10),
+         ("mode_flow_maxarea600_s1", "flow", 10), ("mode_flow_maxarea777_s0", "flow", 10),
+         ("mode_average_maxarea250_s3", "average", 10)]
 
 
 @pytest.mark.parametrize("name,method,fps_limit", MODES)
@@ -71,7 +73,8 @@ def test_other_branches_match_reference_golden(golden, name, method, fps_limit):
     (base.py:303-310) against what the unmodified reference left behind (tools/make_golden_modes.py)."""
     fix = golden(name)
     _, clip = clip_from_fixture(fix)
-    res = P.run_clip(clip, fps=10.0, method=method, fps_limit=fps_limit)
+    max_area = float(fix["max_area"]) if "max_area" in fix else np.inf     # finite: base.py:456-458 -> tools.py:48-57
+    res = P.run_clip(clip, fps=10.0, method=method, fps_limit=fps_limit, max_area=max_area)
     assert tuple(res["roi"]) == tuple(int(v) for v in fix["roi"])
     data = np.array(res["window_data"])
     assert data.shape == fix["data"].shape

@@ -17,9 +17,9 @@
 TAG=${1:-r02a}; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-timeout 300 python -m pytest tests -m gpu -q -x > $OUT/gpu_tests.log 2>&1; tail -2 $OUT/gpu_tests.log
-# tests written after the last GPU run of round 1 (skipped by default until they have passed once)
-RESPMON_EXTRA_GPU_TESTS=1 timeout 200 python -m pytest tests -m gpu -q -k other_branches > $OUT/gpu_tests_extra.log 2>&1; tail -3 $OUT/gpu_tests_extra.log
+timeout 400 python -m pytest tests -m gpu -q > $OUT/gpu_tests.log 2>&1; tail -15 $OUT/gpu_tests.log
+# batch-width sweep (BASELINE config 3 asks for 512 clips per step)
+for NC in 128 256 512; do timeout 200 python tools/bench_stage.py $NC 4 0 > $OUT/width_$NC.log 2>&1; head -12 $OUT/width_$NC.log; done
 timeout 200 python tools/dev_temporal_sparse.py > $OUT/temporal_sparse.log 2>&1; cat $OUT/temporal_sparse.log
 timeout 200 python tools/dev_fit_solo.py 64 10 > $OUT/fit_solo.log 2>&1; cat $OUT/fit_solo.log
 timeout 200 python tools/dev_cal_split.py 64 10 > $OUT/cal_split.log 2>&1; cat $OUT/cal_split.log
