@@ -118,6 +118,7 @@ extern "C" int32_t rm_create(const rm_params* params, int32_t device, rm_handle*
     return RM_ERR_CUDA;
   }
   h->measure_chunks = 4;
+  h->pyramid_mode = 2;
   bool ok = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
@@ -180,6 +181,7 @@ extern "C" int32_t rm_set_option(rm_handle* h, const char* name, int64_t value) 
   if (!h || !name) return RM_ERR_INVALID;
   if (strcmp(name, "force_global_lk") == 0) { h->force_global_lk = value != 0; return RM_OK; }
   if (strcmp(name, "force_generic_front") == 0) { h->force_generic_front = value != 0; return RM_OK; }
+  if (strcmp(name, "pyramid_mode") == 0) { h->pyramid_mode = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return RM_OK; }
   if (strcmp(name, "no_minmax_seed") == 0) { h->no_minmax_seed = value != 0; return RM_OK; }
   if (strcmp(name, "defer_join") == 0) { h->defer_join = value != 0; return RM_OK; }
   if (strcmp(name, "measure_tail_frames") == 0) { h->measure_tail_frames = value < 0 ? 0 : (int)value; return RM_OK; }

@@ -52,6 +52,8 @@ struct rm_handle {
   int lk_state_cap;
   void* sig_job;            // host-side SignalJob of the measure pipeline (signal.cu)
   int no_minmax_seed;       // tests: pass 1 of the heat map without the seed kernel (no pruning at the start)
+  int pyramid_mode;         // option "pyramid_mode": 2 = fused tail + TMA rows (default), 1 = fused tail + cp.async rows,
+                            // 0 = level 3 through HBM + pyramid_tail_kernel; the launch falls back when a mode does not fit
   int force_global_lk;
   int force_generic_front;  // tests: float64 pyramid front even for uint8 frames the integer front supports  // tests: take the global-memory LK path even when the ROI fits shared memory
   int prof_on;

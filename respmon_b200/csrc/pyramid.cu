@@ -530,9 +530,10 @@ static int32_t pyramid_build_impl(rm_handle* h, const void* frames, int32_t dtyp
 
   const bool integer_front = dtype == RM_U8 && !h->force_generic_front && pu_supported(frames, W, H, s);
   if (integer_front) {
-    int32_t rc = pu_launch(h, (const uint8_t*)frames, reinterpret_cast<uint32_t*>(g_skip), n_frames, seg_len, seg_stride,
-                           seg_first, W, H, st);
-    if (rc != RM_OK) return rc;
+    const int mode = pu_best_mode(h, frames, W, H, L, s);
+    int32_t rc = pu_launch(h, mode, (const uint8_t*)frames, reinterpret_cast<uint32_t*>(g_skip), lap_out, n_frames, seg_len,
+                           seg_stride, seg_first, W, H, st);
+    if (rc != RM_OK || mode != 0) return rc;       // fused: the record is written, there is no tail launch
   } else {
     const int elem = dtype == RM_U8 ? 1 : (dtype == RM_F32 ? 4 : 8);
     FrontParams fp;
