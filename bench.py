@@ -10,14 +10,14 @@ runs the reference's whole per-clip path on it with the reference's frame routin
 locate() (pyramid + temporal band-pass + collapse + ROI), frames 130..255 -> extract_motion('flow') + measure().
 A step is one pass over the batch; frames counted = every input frame of every clip (n_clips * 256).
 
-  value     clips resident in HBM before the timed region; CUDA events on the launching stream, max over ranks.  Every
-            step is joined before the next starts (each kernel runs alone; --defer-join overlaps consecutive steps).
+  value     clips resident in HBM before the timed region; CUDA events on the launching stream, max over ranks.
   e2e       the same through BatchMonitor.submit()/collect() from pinned HOST memory: the H2D copies (calibration window
             + ROI crops of the measure frames), the ROI round trip and the D2H read of every step's result records are
             inside the timed region; consecutive steps overlap (upload of step k+1 under the measure tail of step k).
-  roofline  the HBM-bound streaming kernel of the path (pyramid front kernel), timed per launch by CUDA events that the
-            library records on its stream (rm_profile_*), against MEASURED_PEAKS.json; traffic from the committed ncu
-            capture of the same launch shape (profiles/roofline_traffic.json).
+  roofline  the HBM-bound stage of the path: the pyramid stage, frame in -> Laplacian record out (one fused kernel), timed
+            per launch by CUDA events that the library records on its stream (rm_profile_*), over SURVEY 8(d)'s
+            algorithmic bytes (W*H*1 + 8 * record length per frame), against MEASURED_PEAKS.json; traffic from the
+            committed ncu capture of the same launch shape (profiles/roofline_traffic.json).
   extras    calibration-only (BASELINE config 2) and measure-only (config 3's loop) rates, outside the timed region.
   cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/cpu_path.py, cv2/scipy/numpy -- the
             reference tree itself does not exist on the GPU box) on whole clips, one worker process per host core.
@@ -209,36 +209,37 @@ def run_gpu_arm(args) -> dict | None:
     clips = eng.synth_clips(specs, dq8)
     torch.cuda.synchronize()
 
-    # Default: one handle, every step joined before the next starts, so that each kernel -- the HBM-bound front kernel
-    # above all -- runs alone and its CUDA-event duration is its own.  --defer-join alternates two handles and joins
-    # (and, at N > 1, all-gathers) step k after step k+1 has been enqueued: the next batch's calibration then runs
-    # underneath the previous batch's longest Gaussian fits (+9 % frames/s, but kernels time each other's contention).
-    from respmon_b200.engine import Engine
-    engines = [eng, Engine(local_rank)] if args.defer_join else [eng]
-    nE = len(engines)
-    for e in engines:
-        e.defer_join(bool(args.defer_join))
+    # One handle, steps back to back on the current stream.  The path's only collective -- one all-gather of the 32-byte
+    # result records per step -- runs on a side stream behind an event, double-buffered, so that the next step's
+    # calibration does not wait for NCCL's launch latency; the timed region ends when the last gather has finished.
+    engines = [eng]
+    nbuf = 2
     gathered = [torch.empty((world * n_clips, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=eng.device)
-                for _ in engines]
-    records = [torch.empty((n_clips, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=eng.device) for _ in engines]
-
-    def finish(k):
-        if args.defer_join:
-            engines[k % nE].join()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered[k % nE], records[k % nE])   # the path's only collective: 32 B per clip
-            return gathered[k % nE]
-        return records[k % nE]
+                for _ in range(nbuf)]
+    records = [torch.empty((n_clips, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=eng.device) for _ in range(nbuf)]
+    side = torch.cuda.Stream(device=eng.device) if world > 1 else None
+    rec_done = [torch.cuda.Event() for _ in range(nbuf)]
+    gat_done = [torch.cuda.Event() for _ in range(nbuf)]
 
     def run_steps(n):
-        last = None
+        cur = torch.cuda.current_stream(eng.device)
         for k in range(n):
-            engines[k % nE].run_batch(clips, FPS, out=records[k % nE])
-            if not args.defer_join:
-                last = finish(k)
-            elif k > 0:
-                last = finish(k - 1)
-        return finish(n - 1) if (n > 0 and args.defer_join) else last
+            b = k % nbuf
+            if world > 1 and k >= nbuf:
+                cur.wait_event(gat_done[b])                    # the gather of step k - nbuf has read records[b]
+            eng.run_batch(clips, FPS, out=records[b])
+            if world > 1:
+                rec_done[b].record(cur)
+                side.wait_event(rec_done[b])
+                with torch.cuda.stream(side):
+                    dist.all_gather_into_tensor(gathered[b], records[b])   # the path's only collective: 32 B per clip
+                    gat_done[b].record(side)
+        if n == 0:
+            return None
+        if world > 1:
+            cur.wait_stream(side)
+            return gathered[(n - 1) % nbuf]
+        return records[(n - 1) % nbuf]
 
     def barrier():
         if world > 1:
@@ -266,8 +267,6 @@ def run_gpu_arm(args) -> dict | None:
             a_[0] += v_[0]
             a_[1] += v_[1]
         e.profile(False)
-        if args.defer_join:
-            e.defer_join(False)
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=eng.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -356,26 +355,30 @@ def run_gpu_arm(args) -> dict | None:
     total_kernel_ms = sum(v[0] for v in prof.values()) or 1.0
     kernels = sorted(({"name": k, "ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
                        "share": v[0] / total_kernel_ms} for k, v in prof.items()), key=lambda d: -d["ms_per_step"])
-    front = prof.get("pyramid_front_u8_kernel")
+    # everything between the frame read and the Laplacian record: the fused kernel, or (fallback) front + tail kernels
+    stage_kernels = [k for k in ("pyramid_u8_fused_kernel", "pyramid_front_u8_kernel", "pyramid_tail_kernel") if k in prof]
     roofline = None
-    if front:
+    if stage_kernels:
         frames_per_launch = n_clips * 128                     # calibration frames of the batch, one launch per step
-        bytes_per_frame = W * H * 1 + (W // 8) * (H // 8) * 4  # frame read once (u8) + Gaussian level 3 written (u32)
-        dur_s = front[0] / front[1] / 1e3
+        rec_len = eng.record_len(W, H)
+        bytes_per_frame = W * H * 1 + rec_len * 8             # frame read once (u8) + Laplacian levels 4..7 (f64)
+        launches_per_kernel = prof[stage_kernels[0]][1]
+        dur_s = sum(prof[k][0] for k in stage_kernels) / launches_per_kernel / 1e3
         achieved = frames_per_launch * bytes_per_frame / dur_s / 1e9
         traffic, traffic_src = None, None
         try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                tj = json.load(f)["pyramid_front_u8_kernel"]
+                tj = json.load(f)["+".join(stage_kernels)]
             traffic = tj["dram_bytes_per_frame"] * frames_per_launch
             traffic_src = tj["source"]
         except Exception:
             pass
-        roofline = {"kernel": "pyramid_front_u8_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+        roofline = {"kernel": "+".join(stage_kernels), "bound": "hbm", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": peak_src,
+                    "peak_source": peak_src, "stage": "pyramid: frame in -> Laplacian record (levels 4..7) out",
+                    "bytes_per_frame": bytes_per_frame,
                     "bytes_per_launch": frames_per_launch * bytes_per_frame, "launch_ms": dur_s * 1e3,
-                    "share_of_step": front[0] / total_kernel_ms}
+                    "share_of_step": sum(prof[k][0] for k in stage_kernels) / total_kernel_ms}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -410,7 +413,6 @@ def main():
     ap.add_argument("--chunk", type=int, default=32, help="clips per H2D chunk of the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--defer-join", action="store_true", help="overlap consecutive steps (see run_gpu_arm)")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -238,25 +238,14 @@ int32_t rm_pack_results_stream(rm_handle* h, const double* bpm, const int32_t* r
                                const int32_t* npeaks, int32_t n_clips, int32_t cap, int32_t n_valid, rm_result* out,
                                void* stream);
 
-/* Deferred join.  With option "defer_join" = 1, rm_measure_signal returns without making `stream` wait for its signal
- * stage and the rm_pack_results that follows runs behind that stage on a stream owned by the handle, so work enqueued on
- * `stream` afterwards (the next batch's calibration) overlaps the longest Gaussian fits of this batch.  The outputs of
- * both calls are complete only after rm_join(h, stream) -- which makes `stream` wait for them -- or after the next
- * rm_measure_signal / rm_measure_flow / rm_signal_bpm on the handle, which join first.  Keep the output buffers alive
- * until then. */
-int32_t rm_join(rm_handle* h, void* stream);
-
-/* Switches (results never depend on them; they select between bit-identical code paths or schedules).
- *   "defer_join" (0/1)           see rm_join.
+/* Switches (results never depend on them beyond float64 rounding; they select between equivalent code paths or schedules).
  *   "measure_chunks" (1..16)     frame chunks of rm_measure_signal (default 4).
- *   "measure_tail_frames" (>=0)  rm_measure_signal: give the last n frames a chunk of their own (default 0 = off).
  *   "temporal_sparse" (0/1)      rm_temporal_bandpass evaluates only the bins the mask keeps (2 K T multiply-adds per column
- *                                instead of two FFTs; same sums as the any-T kernel; default 0 = off; experimental).
- *   "fit_sync" (0/1)             the groups of a warp run their Gaussian fits in lockstep (warp-uniform LM loops) instead
- *                                of free-running; same results (default 0 = off; experimental).
- *   "fit_blocks_per_sm" (>=0)    > 0: cap on the resident Gaussian-fit blocks per SM (default 0 = what fits; experimental).
- *   "fit_bail_nfev" (0..800)     > 0: the first Gaussian-fit pass gives up on a fit after that many evaluations and a
- *                                second pass runs those fits again, one per warp (default 0 = off; experimental).
+ *                                instead of two FFTs; same sums as the any-T kernel) where that is cheaper (default 1).
+ *   "pyramid_mode" (0/1)         1 (default): uint8 frames whose rows are 16-byte multiples take the one-pass fused pyramid
+ *                                kernel (TMA rows, levels 0..4 as integers, the rest in shared memory); 0: always level 3
+ *                                through HBM + the tail kernel.  Bit-identical records.
+ *   "pyramid_cfg" (0..2)         fused kernel: (ring stages, warps per CTA) = (4, 18) / (3, 21) / (2, 24).
  *   "force_global_lk" (0/1)      track from global memory even when the ROI fits shared memory (the path used for ROIs
  *                                too large to stage).
  *   "force_generic_front" (0/1)  uint8 frames take the float pyramid front kernel instead of the integer one.

@@ -257,11 +257,63 @@ def _descale(v, n):
     return (v + (1 << (n - 1))) >> n
 
 
+def _reduce4(q):
+    """v_reduce_sum(v_float32x4) of OpenCV's SSE2 universal intrinsics: (q0 + q2) + (q1 + q3)."""
+    return np.float32(np.float32(q[0] + q[2]) + np.float32(q[1] + q[3]))
+
+
+def cv_window_sum(prod):
+    """sum of an (win, win) array of exact integer products the way cv::LKTrackerInvoker accumulates the spatial-gradient
+    matrix (modules/video/src/lkpyramid.cpp, opencv 4.x, SSE2 baseline): per window row the first 8*(win//8) columns go
+    through a 4-lane float32 accumulator (lane j takes columns j, j+4 of every group of 8, rows in order), the remaining
+    columns through one scalar float32 accumulator (row-major); total = scalar + ((q0 + q2) + (q1 + q3)).
+    Pinned against cv2.calcOpticalFlowPyrLK bit for bit (tests/test_oracle_np_kernels.py)."""
+    f32 = np.float32
+    win = prod.shape[1]
+    nsimd = (win // 8) * 8
+    p = prod.astype(np.float32)          # |Ix*Iy| <= 4080^2 < 2^24: exact
+    q = np.zeros(4, dtype=np.float32)
+    sc = f32(0)
+    for y in range(prod.shape[0]):
+        for g in range(0, nsimd, 4):
+            q = q + p[y, g:g + 4]
+        for x in range(nsimd, win):
+            sc = f32(sc + p[y, x])
+    return f32(sc + _reduce4(q)) if nsimd else sc
+
+
+def cv_mismatch_sums(diff, ix, iy):
+    """(b1, b2) = sums of diff*Ix, diff*Iy over the window in cv::LKTrackerInvoker's order: in the SIMD part v_dotprod
+    adds the integer products of columns (j, j+4) of a group of 8 exactly, the pair sum is converted to float32 and
+    accumulated per lane (lanes 0, 1 of the first accumulator pair take j = 0, 1; of the second j = 2, 3); the scalar part
+    converts every product to float32 and accumulates row-major; b = scalar + (lane sums combined pairwise)."""
+    f32 = np.float32
+    win = diff.shape[1]
+    nsimd = (win // 8) * 8
+    px, py = diff * ix, diff * iy                         # exact int64
+    qx, qy = np.zeros(4, dtype=np.float32), np.zeros(4, dtype=np.float32)
+    s1, s2 = f32(0), f32(0)
+    for y in range(diff.shape[0]):
+        for g in range(0, nsimd, 8):
+            qx = qx + (px[y, g:g + 4] + px[y, g + 4:g + 8]).astype(np.float32)
+            qy = qy + (py[y, g:g + 4] + py[y, g + 4:g + 8]).astype(np.float32)
+        for x in range(nsimd, win):
+            s1 = f32(s1 + f32(px[y, x]))
+            s2 = f32(s2 + f32(py[y, x]))
+    if nsimd:
+        # qb0 = (x0, y0, x1, y1), qb1 = (x2, y2, x3, y3); qb0 + qb1 -> (x0 + x2, ., x1 + x3, .), then the two halves
+        s1 = f32(s1 + f32(f32(qx[0] + qx[2]) + f32(qx[1] + qx[3])))
+        s2 = f32(s2 + f32(f32(qy[0] + qy[2]) + f32(qy[1] + qy[3])))
+    return s1, s2
+
+
 def lk_track(prev_u8, next_u8, pts, win=15, max_level=2, max_iter=10, eps=0.03, min_eig_thr=1e-4):
     """cv2.calcOpticalFlowPyrLK(prev, next, pts, None, winSize=(15,15), maxLevel=2,
     criteria=(EPS|COUNT, 10, 0.03)) (base.py:371-372).  pts (N,2) float32 -> (next (N,2) f32, status (N,) u8).
 
-    Exact-integer window sums (the float accumulation order inside OpenCV is SIMD-width dependent)."""
+    The window sums are accumulated in float32 in OpenCV's own order (cv_window_sum / cv_mismatch_sums below): the
+    result is bit-identical to cv2's, which an exact-integer sum is not (the rounding of the partial sums occasionally
+    flips an iteration's exit test, and carried points then drift apart by ~1e-3 px over a clip)."""
     f32 = np.float32
     pts = np.asarray(pts, dtype=np.float32).reshape(-1, 2)
     n = len(pts)
@@ -302,9 +354,9 @@ def lk_track(prev_u8, next_u8, pts, win=15, max_level=2, max_iter=10, eps=0.03, 
             Iw = interp(I, y0, x0, 9, wts)
             Ix = interp(Dx, y0, x0, 14, wts)
             Iy = interp(Dy, y0, x0, 14, wts)
-            A11 = f32(int((Ix * Ix).sum())) * flt_scale
-            A12 = f32(int((Ix * Iy).sum())) * flt_scale
-            A22 = f32(int((Iy * Iy).sum())) * flt_scale
+            A11 = cv_window_sum(Ix * Ix) * flt_scale
+            A12 = cv_window_sum(Ix * Iy) * flt_scale
+            A22 = cv_window_sum(Iy * Iy) * flt_scale
             D = A11 * A22 - A12 * A12
             min_eig = (A22 + A11 - np.sqrt((A11 - A22) * (A11 - A22) + f32(4) * A12 * A12)) / f32(2 * win * win)
             if min_eig < min_eig_thr or D < np.finfo(np.float32).eps:
@@ -322,8 +374,8 @@ def lk_track(prev_u8, next_u8, pts, win=15, max_level=2, max_iter=10, eps=0.03, 
                     break
                 wj = _bilinear_weights(np_[0] - f32(jx), np_[1] - f32(jy))
                 diff = interp(J, jy + win, jx + win, 9, wj) - Iw
-                b1 = f32(int((diff * Ix).sum())) * flt_scale
-                b2 = f32(int((diff * Iy).sum())) * flt_scale
+                b1, b2 = cv_mismatch_sums(diff, Ix, Iy)
+                b1, b2 = b1 * flt_scale, b2 * flt_scale
                 delta = np.array([(A12 * b2 - A22 * b1) * D, (A12 * b1 - A11 * b2) * D], dtype=np.float32)
                 np_ = np_ + delta
                 nxt[k] = np_ + half

@@ -85,7 +85,6 @@ SIGNATURES = {
     "rm_measure_signal_stream": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _i32, _i32, _i32, _f64, _P, _P, _P,
                                         _P, _P, _P, _P, _P, _P, _sz, _S]),
     "rm_crop_to_ring": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _P, _i32, _i32, _i32, _i32, _S]),
-    "rm_join": (_i32, [_H, _S]),
     "rm_pack_results": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _P, _S]),
     "rm_pack_results_stream": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _i32, _P, _S]),
     "rm_launch_count": (_i64, [_H]),

@@ -118,18 +118,15 @@ extern "C" int32_t rm_create(const rm_params* params, int32_t device, rm_handle*
     return RM_ERR_CUDA;
   }
   h->measure_chunks = 4;
-  h->pyramid_mode = 2;
+  h->pyramid_mode = 1;
+  h->temporal_sparse = 1;
   bool ok = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaStreamCreateWithFlags(&h->tail_stream, cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && cudaEventCreateWithFlags(&h->ev_packed, cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaEventCreateWithFlags(&h->ev_tail_fork, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < RM_MAX_CHUNKS; ++i) {
     ok = cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_filt[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&h->ev_bulk[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->fit_stream[i], cudaStreamNonBlocking) == cudaSuccess;
   }
   if (!ok) {
@@ -156,14 +153,10 @@ extern "C" int32_t rm_destroy(rm_handle* h) {
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->tail_stream) cudaStreamDestroy(h->tail_stream);
-    if (h->ev_packed) cudaEventDestroy(h->ev_packed);
-    if (h->ev_tail_fork) cudaEventDestroy(h->ev_tail_fork);
     for (int i = 0; i < RM_MAX_CHUNKS; ++i) {
       if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
       if (h->ev_filt[i]) cudaEventDestroy(h->ev_filt[i]);
       if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
-      if (h->ev_bulk[i]) cudaEventDestroy(h->ev_bulk[i]);
       if (h->fit_stream[i]) cudaStreamDestroy(h->fit_stream[i]);
     }
     for (int i = 0; i < h->prof_cap; ++i) {
@@ -181,37 +174,16 @@ extern "C" int32_t rm_set_option(rm_handle* h, const char* name, int64_t value) 
   if (!h || !name) return RM_ERR_INVALID;
   if (strcmp(name, "force_global_lk") == 0) { h->force_global_lk = value != 0; return RM_OK; }
   if (strcmp(name, "force_generic_front") == 0) { h->force_generic_front = value != 0; return RM_OK; }
-  if (strcmp(name, "pyramid_mode") == 0) { h->pyramid_mode = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return RM_OK; }
+  if (strcmp(name, "pyramid_mode") == 0) { h->pyramid_mode = value != 0; return RM_OK; }
+  if (strcmp(name, "pyramid_cfg") == 0) { h->pyramid_cfg = value < 0 || value > 2 ? 0 : (int)value; return RM_OK; }
   if (strcmp(name, "no_minmax_seed") == 0) { h->no_minmax_seed = value != 0; return RM_OK; }
-  if (strcmp(name, "defer_join") == 0) { h->defer_join = value != 0; return RM_OK; }
-  if (strcmp(name, "measure_tail_frames") == 0) { h->measure_tail_frames = value < 0 ? 0 : (int)value; return RM_OK; }
   if (strcmp(name, "temporal_sparse") == 0) { h->temporal_sparse = value != 0; return RM_OK; }
-  if (strcmp(name, "fit_sync") == 0) { h->fit_sync = value != 0; return RM_OK; }
-  if (strcmp(name, "fit_blocks_per_sm") == 0) { h->fit_blocks_per_sm = value < 0 ? 0 : (int)value; return RM_OK; }
-  if (strcmp(name, "fit_bail_nfev") == 0) {
-    if (value < 0 || value > 800) return rm_fail(h, RM_ERR_INVALID, "%s: fit_bail_nfev must be 0..800", __func__);
-    h->fit_bail_nfev = (int)value;
-    return RM_OK;
-  }
   if (strcmp(name, "measure_chunks") == 0) {
     if (value < 1 || value > RM_MAX_CHUNKS) return rm_fail(h, RM_ERR_INVALID, "%s: measure_chunks must be 1..16", __func__);
     h->measure_chunks = (int)value;
     return RM_OK;
   }
   return rm_fail(h, RM_ERR_INVALID, "%s: unknown option", __func__);
-}
-
-int32_t rmi_join(rm_handle* h, cudaStream_t st) {
-  if (h->pending_pack) RM_CUDA(h, cudaStreamWaitEvent(st, h->ev_packed, 0));
-  for (int c = 0; c < h->pending_chunks; ++c) RM_CUDA(h, cudaStreamWaitEvent(st, h->ev_done[c], 0));
-  h->pending_pack = 0;
-  h->pending_chunks = 0;
-  return RM_OK;
-}
-extern "C" int32_t rm_join(rm_handle* h, void* stream) {
-  if (!h) return RM_ERR_INVALID;
-  DeviceGuard dg(h->device);
-  return rmi_join(h, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------- profiling

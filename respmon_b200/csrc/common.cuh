@@ -30,30 +30,17 @@ struct rm_handle {
   cudaStream_t aux_stream;                   // PCA + filtfilt/peaks of the chunks, in frame order
   cudaStream_t fit_stream[RM_MAX_CHUNKS];    // one per chunk: the Gaussian-fit gates of different chunks overlap
   cudaEvent_t ev_fork, ev_join, ev_chunk[RM_MAX_CHUNKS], ev_filt[RM_MAX_CHUNKS], ev_done[RM_MAX_CHUNKS];
-  cudaEvent_t ev_bulk[RM_MAX_CHUNKS];        // first fit pass of the chunk finished (deferred pipeline)
   int measure_chunks;       // option "measure_chunks"
-  int measure_tail_frames;  // option "measure_tail_frames": frames of the last chunk (0: like the others)
-  // Deferred join (option "defer_join"): rm_measure_signal returns without making the caller's stream wait for the
-  // signal stage; rm_pack_results then runs on tail_stream behind it, and the caller's stream catches up in rm_join or
-  // at the next call that reuses the handle's scratch.  Lets the next batch's calibration run under this batch's
-  // longest Gaussian fits.
-  int defer_join;
-  int temporal_sparse;      // option "temporal_sparse": band-pass through the kept bins only (temporal.cu; experimental)
-  int fit_sync;             // option "fit_sync": warp-synchronous first fit pass (signal.cu; experimental)
-  int fit_blocks_per_sm;    // option "fit_blocks_per_sm": > 0 caps the resident fit blocks per SM (fewer divergent streams per SMSP)
-  int fit_bail_nfev;        // option "fit_bail_nfev": > 0 -> bail + solo long pass in every mode (signal.cu)
-  int pending_chunks;       // > 0: ev_done[0..pending_chunks) of the last rm_measure_signal have not been waited for
-  int pending_pack;         // 1: ev_packed (tail_stream) has not been waited for
-  cudaStream_t tail_stream;
-  cudaEvent_t ev_packed, ev_tail_fork;
+  int temporal_sparse;      // option "temporal_sparse": 1 (default) = band-pass through the kept bins where that is cheaper
   float* d_lk_pts;          // (cap_clips, 128, 2) points carried from one LK chunk to the next
   int* d_lk_idx;            // (cap_clips, 128) original corner index of every carried point
   int* d_lk_n;              // (cap_clips, 16) points each block of a clip still tracks
   int lk_state_cap;
   void* sig_job;            // host-side SignalJob of the measure pipeline (signal.cu)
   int no_minmax_seed;       // tests: pass 1 of the heat map without the seed kernel (no pruning at the start)
-  int pyramid_mode;         // option "pyramid_mode": 2 = fused tail + TMA rows (default), 1 = fused tail + cp.async rows,
-                            // 0 = level 3 through HBM + pyramid_tail_kernel; the launch falls back when a mode does not fit
+  int pyramid_mode;         // option "pyramid_mode": 1 = fused TMA kernel where the frames allow it (default), 0 = always the
+                            // fallback (level 3 through HBM + pyramid_tail_kernel) -- tests compare the two bit for bit
+  int pyramid_cfg;          // option "pyramid_cfg": fused kernel's (ring stages, warps per CTA): 0 = (4, 18), 1 = (3, 21), 2 = (2, 24)
   int force_global_lk;
   int force_generic_front;  // tests: float64 pyramid front even for uint8 frames the integer front supports  // tests: take the global-memory LK path even when the ROI fits shared memory
   int prof_on;
@@ -188,6 +175,5 @@ static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / 
 int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int32_t n_frames, double fps, double* bpm_out,
                          double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, const int32_t* status,
                          int n_chunks, cudaStream_t st, int win_f0, int win_frames);
-int32_t rmi_join(rm_handle* h, cudaStream_t st);   // make st wait for whatever a deferred rm_measure_signal left running
 int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t st, cudaStream_t st_fit,
-                         cudaEvent_t ev_filtered, cudaEvent_t ev_bulk);
+                         cudaEvent_t ev_filtered);

@@ -202,9 +202,8 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
       // minimum to every pixel whatever the values are: it is neither staged nor evaluated, its additions still happen,
       // in frame order.  That is the fate of everything that does not move: top sits 30 % above the most negative value.
       const double2* b = p.bounds + ((long long)clip * gridDim.x + tile) * p.T;
-#ifdef HM_PAR_LIST
-      // Developer switch (untimed experiment): the ordered list by ballot + prefix counts instead of one thread walking
-      // the flags (that walk and the wait for it are 12 % of the passes' stall samples in ncu r01n).  Same list.
+      // the ordered list by ballot + prefix counts instead of one thread walking the flags (that walk and the wait for it
+      // were 12 % of the passes' stall samples, ncu r01n; pass 2 0.374 -> 0.326 ms, r02a).  Same list.
       __shared__ int s_cnt[4];
       int n = 0;
       for (int t0 = 0; t0 < p.T; t0 += 128) {                 // blockDim.x == 128: warp w holds frames t0 + 32 w ..
@@ -225,23 +224,6 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
         __syncthreads();
       }
       n_list = n;
-#else
-      unsigned char* flag = reinterpret_cast<unsigned char*>(frame_list + p.T);
-      for (int t = tid; t < p.T; t += blockDim.x) {
-        const double2 lh = b[t];
-        const double mrg = 1e-12 * fmax(fabs(lh.x), fabs(lh.y));
-        flag[t] = !(lh.x - mrg >= top);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int n = 0;
-        for (int t = 0; t < p.T; ++t)
-          if (flag[t]) frame_list[n++] = t;
-        frame_list[p.T + (p.T + 3) / 4] = n;   // past the flags
-      }
-      __syncthreads();
-      n_list = frame_list[p.T + (p.T + 3) / 4];
-#endif
     }
   }
   const long long n2 = (long long)p.w[2] * p.h[2];
@@ -299,29 +281,6 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
   };
 #pragma unroll
   for (int t = 0; t < HM_STAGES - 1; ++t) issue(t);
-#ifdef HM_ONE_BARRIER
-  // Developer switch (untimed experiment): one barrier per evaluated frame in the lazy path.  The level-2 patch of frame
-  // t + 1 is expanded (into the other of two patch buffers) in the iteration that evaluates frame t, so the barrier at
-  // the top of an iteration publishes both the expanded patch of frame t and the landed level-3 patch of frame t + 1.
-  static_assert(HM_STAGES >= 3, "the one-barrier pipeline keeps one level-3 patch more in flight");
-  auto expand_patch = [&](int tt) {
-    const double* s3 = stage3 + (tt % HM_STAGES) * HM_P3;
-    double* dst2 = stage + (tt & 1) * HM_PW * HM_PH;
-#pragma unroll
-    for (int c = 0; c < HM_COPIES; ++c) {
-      const int e = tid + c * 128;
-      if (e < n_patch) {
-        const int r = e / pwid, cc = e - r * pwid;
-        dst2[r * HM_PW + cc] = a2_value(s3, pw3, x3lo, y3lo, p.w3, p.h3, xlo + cc, ylo + r);
-      }
-    }
-  };
-  if (lazy && n_list > 0) {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(HM_STAGES - 2) : "memory");   // frame 0 has landed
-    __syncthreads();
-    expand_patch(0);
-  }
-#endif
 
   {
     // pass 1 walks the frame list; pass 2 walks every frame in order and consumes the list as it goes (k = position of
@@ -354,14 +313,6 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
         }
       }
       const int t = k++;               // position in the staging ring
-#ifdef HM_ONE_BARRIER
-      if (lazy) {
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(HM_STAGES - 3) : "memory");   // frame t + 1 has landed
-        __syncthreads();               // patch t (expanded last iteration) is complete; everyone is done with frame t - 1
-        issue(t + HM_STAGES - 1);      // refills the level-3 slot of frame t - 1
-        if (t + 1 < n_list) expand_patch(t + 1);
-      } else
-#endif
       {
       asm volatile("cp.async.wait_group %0;\n" ::"n"(HM_STAGES - 2) : "memory");
       __syncthreads();                 // frame t has landed for everyone; everyone is done with frame t-1's stage
@@ -380,11 +331,7 @@ __device__ __forceinline__ void upsample_pass_body(const TileParams& p, double* 
       }
       }
       if (!active) continue;
-#ifdef HM_ONE_BARRIER
-      const double* l2 = lazy ? stage + (t & 1) * HM_PW * HM_PH : stage + (t % HM_STAGES) * HM_PW * HM_PH;
-#else
       const double* l2 = lazy ? stage : stage + (t % HM_STAGES) * HM_PW * HM_PH;
-#endif
       double v[4][4], o[4][4];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -574,12 +521,8 @@ __global__ void __launch_bounds__(256) minmax_seed_kernel(const TileParams p, in
   }
 }
 
-// Developer switch (untimed experiment): -DHM_MIN_BLOCKS=4 caps the passes at 128 registers for a fourth resident block.
-#ifdef HM_MIN_BLOCKS
-#define HM_LAUNCH_BOUNDS __launch_bounds__(128, HM_MIN_BLOCKS)
-#else
-#define HM_LAUNCH_BOUNDS __launch_bounds__(128)
-#endif
+// 128 registers (no spills) for a fourth resident block: pass 2 0.410 -> 0.363 ms per 64-clip step (r02a)
+#define HM_LAUNCH_BOUNDS __launch_bounds__(128, 4)
 template <int PASS>
 __global__ void HM_LAUNCH_BOUNDS upsample_pass_kernel(const TileParams p) {
   __shared__ double red_a[4], red_b[4];

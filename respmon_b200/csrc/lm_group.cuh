@@ -72,40 +72,15 @@ template <int G>
 __device__ __noinline__ void lmg_resid(const LmGroup& g, int m, const double* xs, const double* ys, const double* p,
                                           double* f) {
   const double denom = 2.0 * (p[2] * p[2]) + SC_DBL_EPS;
-#ifdef LM_ROWS2
-  // Developer switch (untimed experiment): two rows per trip -- the same division and exp per row, but the two latency
-  // chains overlap (division + exp of the model are 11 % of the fit kernel's stall samples, ncu r01m)
-  int i = g.sub;
-#pragma unroll 1
-  for (; i + G < m; i += 2 * G) {
-    const double d0 = xs[i] - p[1], d1 = xs[i + G] - p[1];
-    const double e0 = exp(-(d0 * d0) / denom), e1 = exp(-(d1 * d1) / denom);
-    f[i] = p[0] * e0 - ys[i];
-    f[i + G] = p[0] * e1 - ys[i + G];
-  }
-  if (i < m) {
-    const double d = xs[i] - p[1];
-    f[i] = p[0] * exp(-(d * d) / denom) - ys[i];
-  }
-#else
 #pragma unroll 1
   for (int i = g.sub; i < m; i += G) {
     const double d = xs[i] - p[1];
     f[i] = p[0] * exp(-(d * d) / denom) - ys[i];
   }
-#endif
 }
 
 // xs, ys, fvec, wa4 (m each) and fjac (3m, column-major) are the group's shared-memory slices; xs/ys filled by the
 // caller (and visible: the caller syncs the group).  x[3] in/out (uniform over the group).  Returns MINPACK info.
-#ifdef LM_TIMING
-__device__ unsigned long long lm_timing[8];
-#define LMT(k) do { if (g.sub == 0) { long long n_ = clock64(); atomicAdd(&lm_timing[k], (unsigned long long)(n_ - tk_)); tk_ = n_; } } while (0)
-#define LMC(k) do { if (g.sub == 0) atomicAdd(&lm_timing[k], 1ull); } while (0)
-#else
-#define LMT(k) do { } while (0)
-#define LMC(k) do { } while (0)
-#endif
 __device__ __forceinline__ int i3_get(const int v[3], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }
 __device__ __forceinline__ void i3_put(int v[3], int i, int x) {
   if (i == 0) v[0] = x;
@@ -116,11 +91,9 @@ __device__ __forceinline__ void i3_put(int v[3], int i, int x) {
 // The 3-parameter state (x, diag, qtf, R, the work vectors, the permutation) is indexed by compile-time constants only
 // -- loops over the parameters are unrolled, run-time indices go through selects (l3_get / l3_put, signal_core.h) -- so
 // it stays in registers; the routine is inlined into the kernel for the same reason.  The O(m) loops are not unrolled.
-// bail_nfev > 0: give up (return -1) once that many function evaluations have been spent at the top of an outer
-// iteration -- the caller re-queues the fit for the long-fit pass, which runs it again from the start without a limit.
 template <int G>
 __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const double* xs, const double* ys, double x[3],
-                                               double* fvec, double* wa4, double* fjac, int bail_nfev) {
+                                               double* fvec, double* wa4, double* fjac) {
   const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
   const int maxfev = 200 * (3 + 1);
   const double epsmch = SC_DBL_EPS, epsfcn = SC_DBL_EPS;
@@ -134,23 +107,11 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
   lmg_resid<G>(g, m, xs, ys, x, fvec);
   nfev = 1;
   double fnorm = lmg_enorm<G>(g, fvec, m, 0);
-#ifdef LM_TIMING
-  long long tk_ = clock64();
-#endif
-#ifdef LM_DIV3
   const double eps_fd = l3_sqrt(epsfcn > epsmch ? epsfcn : epsmch);   // loop invariant (MINPACK recomputes it per call)
-#endif
 #pragma unroll 1
   for (;;) {
-    if (bail_nfev > 0 && nfev >= bail_nfev) return -1;
-    LMT(5);
-    LMC(7);
     {   // fdjac2: forward differences (each lane differences the rows it evaluated)
-#ifdef LM_DIV3
       const double eps = eps_fd;
-#else
-      const double eps = l3_sqrt(epsfcn > epsmch ? epsfcn : epsmch);
-#endif
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const double temp = x[j];
@@ -159,26 +120,12 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
         x[j] = temp + h;
         lmg_resid<G>(g, m, xs, ys, x, wa4);
         x[j] = temp;
-#ifdef LM_ROWS2
-        {
-          int i = g.sub;
-#pragma unroll 1
-          for (; i + G < m; i += 2 * G) {
-            const double q0 = (wa4[i] - fvec[i]) / h, q1 = (wa4[i + G] - fvec[i + G]) / h;
-            fjac[i + j * m] = q0;
-            fjac[i + G + j * m] = q1;
-          }
-          if (i < m) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
-        }
-#else
 #pragma unroll 1
         for (int i = g.sub; i < m; i += G) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
-#endif
       }
       nfev += 3;
     }
     __syncwarp(g.mask);
-    LMT(0);
     {   // qrfac with column pivoting; wa1 = rdiag, wa2 = acnorm, wa3 = work
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -211,22 +158,8 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
         if (ajnorm != 0.0) {
           if (fjac[j + j * m] < 0.0) ajnorm = -ajnorm;
           __syncwarp(g.mask);                                   // everyone has read the diagonal element
-#ifdef LM_ROWS2
-          {
-            int i = j + g.sub;
-#pragma unroll 1
-            for (; i + G < m; i += 2 * G) {
-              const double q0 = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
-              const double q1 = fjac[i + G + j * m] / ajnorm + 0.0;   // i + G > j; the + 0.0 keeps -0.0 -> +0.0
-              fjac[i + j * m] = q0;
-              fjac[i + G + j * m] = q1;
-            }
-            if (i < m) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
-          }
-#else
 #pragma unroll 1
           for (int i = j + g.sub; i < m; i += G) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
-#endif
           __syncwarp(g.mask);
           const double ajj = fjac[j + j * m];
 #pragma unroll
@@ -253,7 +186,6 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
         wa1[j] = -ajnorm;
       }
     }
-    LMT(1);
     if (iter == 1) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) { diag[j] = wa2[j]; if (wa2[j] == 0.0) diag[j] = 1.0; }
@@ -288,7 +220,6 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
     __syncwarp(g.mask);                                          // R and qtf are read before fjac / wa4 change again
     gnorm = 0.0;
     if (fnorm != 0.0) {
-#ifdef LM_DIV3
       // the same quotients qtf[i] / fnorm and sum_j / wa2[l], three per call (a skipped column's quotient is not used)
       const L3Triple qf = l3_div3(qtf[0], fnorm, qtf[1], fnorm, qtf[2], fnorm);
       const double qn[3] = {qf.a, qf.b, qf.c};
@@ -309,30 +240,14 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
           gnorm = gnorm > gg ? gnorm : gg;
         }
       }
-#else
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const double w2l = l3_get(wa2, ipvt[j]);
-        if (w2l != 0.0) {
-          double sum = 0.0;
-#pragma unroll
-          for (int i = 0; i <= j; ++i) sum += r[i + j * 3] * l3_div(qtf[i], fnorm);
-          const double gg = fabs(l3_div(sum, w2l));
-          gnorm = gnorm > gg ? gnorm : gg;
-        }
-      }
-#endif
     }
     if (gnorm <= gtol) { info = 4; break; }
 #pragma unroll
     for (int j = 0; j < 3; ++j) diag[j] = diag[j] > wa2[j] ? diag[j] : wa2[j];
     double ratio = 0.0;
-    LMT(2);
 #pragma unroll 1
     do {
       l3_lmpar(r, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
-      LMT(3);
-      LMC(6);
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         wa1[j] = -wa1[j];
@@ -345,9 +260,6 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
       ++nfev;
       const double fnorm1 = lmg_enorm<G>(g, wa4, m, 0);
       double actred = -1.0;
-#ifndef LM_DIV3
-      if (p1 * fnorm1 < fnorm) { const double d = l3_div(fnorm1, fnorm); actred = 1.0 - d * d; }
-#endif
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         wa3[j] = 0.0;
@@ -355,15 +267,10 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
 #pragma unroll
         for (int i = 0; i <= j; ++i) wa3[i] += r[i + j * 3] * temp;
       }
-#ifdef LM_DIV3
       const L3Triple qr = l3_div3(fnorm1, fnorm, l3_enorm3(wa3[0], wa3[1], wa3[2]), fnorm, l3_sqrt(par) * pnorm, fnorm);
       if (p1 * fnorm1 < fnorm) actred = 1.0 - qr.a * qr.a;
       const double temp1 = qr.b;
       const double temp2 = qr.c;
-#else
-      const double temp1 = l3_div(l3_enorm3(wa3[0], wa3[1], wa3[2]), fnorm);
-      const double temp2 = l3_div(l3_sqrt(par) * pnorm, fnorm);
-#endif
       const double prered = temp1 * temp1 + l3_div(temp2 * temp2, p5);
       const double dirder = -(temp1 * temp1 + temp2 * temp2);
       ratio = 0.0;
@@ -397,246 +304,9 @@ __device__ __forceinline__ int lmg_lmdif_gauss(const LmGroup g, int m, const dou
       if (fabs(actred) <= epsmch && prered <= epsmch && p5 * ratio <= 1.0) info = 6;
       if (delta <= epsmch * xnorm) info = 7;
       if (gnorm <= epsmch) info = 8;
-      LMT(4);
       if (info != 0) break;
     } while (ratio < p0001);
     if (info != 0) break;
   }
   return info;
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Warp-synchronous form (option "fit_sync", experimental).  lmg_lmdif_gauss lets the groups of a warp run free: each is at
-// its own point of MINPACK's control flow, the warp issues their instruction streams one after the other, and an SMSP
-// ends up interleaving a dozen 4-lane streams.  Here every lane of the warp calls the routine together (groups without
-// a fit pass m = 0) and the two data-dependent loops -- outer iterations, trust-region retries -- are warp-uniform:
-// a group that has left a loop idles until the last group of the warp leaves it, so the groups re-converge at the top of
-// every iteration and one instruction stream serves all of them.  Shorter data-dependent branches (pivot swaps, lmpar's
-// own iterations) re-converge at their ends as usual.  Same arithmetic, same order, same results as lmg_lmdif_gauss.
-template <int G>
-__device__ __forceinline__ int lmg_lmdif_gauss_sync(const LmGroup g, int m, const double* xs, const double* ys, double x[3],
-                                                    double* fvec, double* wa4, double* fjac, int bail_nfev) {
-  const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
-  const int maxfev = 200 * (3 + 1);
-  const double epsmch = SC_DBL_EPS, epsfcn = SC_DBL_EPS;
-  const double p1 = 0.1, p5 = 0.5, p25 = 0.25, p75 = 0.75, p0001 = 1e-4;
-  double diag[3] = {0.0, 0.0, 0.0}, qtf[3], wa1[3], wa2[3], wa3[3], sdiag[3];
-  double r[9];
-  int ipvt[3];
-  int info = 0, nfev = 0, iter = 1, ret = 0;
-  double par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0, fnorm = 0.0;
-  bool live = m >= 3;
-  if (live) {
-    lmg_resid<G>(g, m, xs, ys, x, fvec);
-    nfev = 1;
-    fnorm = lmg_enorm<G>(g, fvec, m, 0);
-  }
-#pragma unroll 1
-  while (__any_sync(0xffffffffu, live)) {
-    bool inner = false;
-    double ratio = 0.0;
-    if (live && bail_nfev > 0 && nfev >= bail_nfev) { ret = -1; live = false; }
-    if (live) {
-      {   // fdjac2
-        const double eps = l3_sqrt(epsfcn > epsmch ? epsfcn : epsmch);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const double temp = x[j];
-          double h = eps * fabs(temp);
-          if (h == 0.0) h = eps;
-          x[j] = temp + h;
-          lmg_resid<G>(g, m, xs, ys, x, wa4);
-          x[j] = temp;
-#pragma unroll 1
-          for (int i = g.sub; i < m; i += G) fjac[i + j * m] = (wa4[i] - fvec[i]) / h;
-        }
-        nfev += 3;
-      }
-      __syncwarp(g.mask);
-      {   // qrfac with column pivoting; wa1 = rdiag, wa2 = acnorm, wa3 = work
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          wa2[j] = lmg_enorm<G>(g, fjac + j * m, m, 0);
-          wa1[j] = wa2[j];
-          wa3[j] = wa1[j];
-          ipvt[j] = j;
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          int kmax = j;
-#pragma unroll
-          for (int k = j; k < 3; ++k)
-            if (wa1[k] > l3_get(wa1, kmax)) kmax = k;
-          if (kmax != j) {
-#pragma unroll 1
-            for (int i = g.sub; i < m; i += G) {
-              const double t = fjac[i + j * m];
-              fjac[i + j * m] = fjac[i + kmax * m];
-              fjac[i + kmax * m] = t;
-            }
-            l3_put(wa1, kmax, wa1[j]);
-            l3_put(wa3, kmax, wa3[j]);
-            const int t = ipvt[j];
-            ipvt[j] = i3_get(ipvt, kmax);
-            i3_put(ipvt, kmax, t);
-            __syncwarp(g.mask);
-          }
-          double ajnorm = lmg_enorm<G>(g, fjac + j * m, m, j);
-          if (ajnorm != 0.0) {
-            if (fjac[j + j * m] < 0.0) ajnorm = -ajnorm;
-            __syncwarp(g.mask);
-#pragma unroll 1
-            for (int i = j + g.sub; i < m; i += G) fjac[i + j * m] = fjac[i + j * m] / ajnorm + (i == j ? 1.0 : 0.0);
-            __syncwarp(g.mask);
-            const double ajj = fjac[j + j * m];
-#pragma unroll
-            for (int k = j + 1; k < 3; ++k) {
-              double part = 0.0;
-#pragma unroll 1
-              for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * fjac[i + k * m];
-              const double temp = l3_div(lmg_sum<G>(g, part), ajj);
-#pragma unroll 1
-              for (int i = j + g.sub; i < m; i += G) fjac[i + k * m] -= temp * fjac[i + j * m];
-              __syncwarp(g.mask);
-              if (wa1[k] != 0.0) {
-                double t = l3_div(fjac[j + k * m], wa1[k]);
-                const double d = 1.0 - t * t;
-                wa1[k] *= l3_sqrt(d > 0.0 ? d : 0.0);
-                t = l3_div(wa1[k], wa3[k]);
-                if (0.05 * (t * t) <= SC_DBL_EPS) {
-                  wa1[k] = lmg_enorm<G>(g, fjac + k * m, m, j + 1);
-                  wa3[k] = wa1[k];
-                }
-              }
-            }
-          }
-          wa1[j] = -ajnorm;
-        }
-      }
-      if (iter == 1) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) { diag[j] = wa2[j]; if (wa2[j] == 0.0) diag[j] = 1.0; }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) wa3[j] = diag[j] * x[j];
-        xnorm = l3_enorm3(wa3[0], wa3[1], wa3[2]);
-        delta = factor * xnorm;
-        if (delta == 0.0) delta = factor;
-      }
-#pragma unroll 1
-      for (int i = g.sub; i < m; i += G) wa4[i] = fvec[i];
-      __syncwarp(g.mask);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const double ajj = fjac[j + j * m];
-        if (ajj != 0.0) {
-          double part = 0.0;
-#pragma unroll 1
-          for (int i = j + g.sub; i < m; i += G) part += fjac[i + j * m] * wa4[i];
-          const double temp = l3_div(-lmg_sum<G>(g, part), ajj);
-#pragma unroll 1
-          for (int i = j + g.sub; i < m; i += G) wa4[i] += fjac[i + j * m] * temp;
-          __syncwarp(g.mask);
-        }
-        qtf[j] = wa4[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) r[i + j * 3] = (i == j) ? wa1[j] : fjac[i + j * m];
-      __syncwarp(g.mask);
-      gnorm = 0.0;
-      if (fnorm != 0.0) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const double w2l = l3_get(wa2, ipvt[j]);
-          if (w2l != 0.0) {
-            double sum = 0.0;
-#pragma unroll
-            for (int i = 0; i <= j; ++i) sum += r[i + j * 3] * l3_div(qtf[i], fnorm);
-            const double gg = fabs(l3_div(sum, w2l));
-            gnorm = gnorm > gg ? gnorm : gg;
-          }
-        }
-      }
-      if (gnorm <= gtol) {
-        info = 4;
-        ret = info;
-        live = false;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) diag[j] = diag[j] > wa2[j] ? diag[j] : wa2[j];
-        inner = true;
-      }
-    }
-#pragma unroll 1
-    while (__any_sync(0xffffffffu, inner)) {
-      if (inner) {
-        l3_lmpar(r, ipvt, diag, qtf, delta, &par, wa1, sdiag, wa2, wa3);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          wa1[j] = -wa1[j];
-          wa2[j] = x[j] + wa1[j];
-          wa3[j] = diag[j] * wa1[j];
-        }
-        const double pnorm = l3_enorm3(wa3[0], wa3[1], wa3[2]);
-        if (iter == 1) delta = delta < pnorm ? delta : pnorm;
-        lmg_resid<G>(g, m, xs, ys, wa2, wa4);
-        ++nfev;
-        const double fnorm1 = lmg_enorm<G>(g, wa4, m, 0);
-        double actred = -1.0;
-        if (p1 * fnorm1 < fnorm) { const double d = l3_div(fnorm1, fnorm); actred = 1.0 - d * d; }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          wa3[j] = 0.0;
-          const double temp = l3_get(wa1, ipvt[j]);
-#pragma unroll
-          for (int i = 0; i <= j; ++i) wa3[i] += r[i + j * 3] * temp;
-        }
-        const double temp1 = l3_div(l3_enorm3(wa3[0], wa3[1], wa3[2]), fnorm);
-        const double temp2 = l3_div(l3_sqrt(par) * pnorm, fnorm);
-        const double prered = temp1 * temp1 + l3_div(temp2 * temp2, p5);
-        const double dirder = -(temp1 * temp1 + temp2 * temp2);
-        ratio = 0.0;
-        if (prered != 0.0) ratio = l3_div(actred, prered);
-        if (ratio <= p25) {
-          double temp;
-          if (actred >= 0.0) temp = p5;
-          else temp = l3_div(p5 * dirder, dirder + p5 * actred);
-          if (p1 * fnorm1 >= fnorm || temp < p1) temp = p1;
-          const double q = l3_div(pnorm, p1);
-          delta = temp * (delta < q ? delta : q);
-          par = l3_div(par, temp);
-        } else if (par == 0.0 || ratio >= p75) {
-          delta = l3_div(pnorm, p5);
-          par = p5 * par;
-        }
-        if (ratio >= p0001) {
-#pragma unroll
-          for (int j = 0; j < 3; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
-#pragma unroll 1
-          for (int i = g.sub; i < m; i += G) fvec[i] = wa4[i];
-          xnorm = l3_enorm3(wa2[0], wa2[1], wa2[2]);
-          fnorm = fnorm1;
-          ++iter;
-        }
-        if (fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0) info = 1;
-        if (delta <= xtol * xnorm) info = 2;
-        if (fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0 && info == 2) info = 3;
-        if (info == 0) {
-          if (nfev >= maxfev) info = 5;
-          if (fabs(actred) <= epsmch && prered <= epsmch && p5 * ratio <= 1.0) info = 6;
-          if (delta <= epsmch * xnorm) info = 7;
-          if (gnorm <= epsmch) info = 8;
-        }
-        if (info != 0) {            // this fit is finished
-          ret = info;
-          live = false;
-          inner = false;
-        } else if (!(ratio < p0001)) {
-          inner = false;            // step accepted: next outer iteration
-        }
-      }
-    }
-  }
-  return ret;
 }

@@ -316,6 +316,90 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 }
 __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
 
+// ---- window sums in cv::LKTrackerInvoker's float32 order ------------------------------------------------------------
+// OpenCV accumulates the 2x2 gradient matrix and the mismatch vector in float32 (modules/video/src/lkpyramid.cpp, SSE2
+// universal intrinsics; restated and pinned bit for bit against cv2 in oracle/np_kernels.py cv_window_sum /
+// cv_mismatch_sums): per window row the first nsimd = 8*(win/8) columns go through a 4-lane accumulator (lane j takes
+// columns j and j+4 of a group of 8, rows in order), the other columns through one scalar accumulator (row-major);
+// total = scalar + ((q0 + q2) + (q1 + q3)).  The rounding of those partial sums decides, now and then, whether an
+// iteration's exit test fires, and a carried point then differs by ~0.01 px for the rest of the clip -- so the order
+// is part of "results identical to the reference".
+// Window layout over the warp: lane 2y holds columns 0..7 of window row y, lane 2y+1 columns 8..15 (zero past the
+// window; adding 0.0f changes nothing).  When the sum of |terms| over the window is below 2^24 every partial sum is an
+// exactly representable integer and the float32 result IS the exact integer total: the callers test that first
+// (lk_sums_exact) and only walk the rows in order when a partial sum can actually round.
+__device__ __forceinline__ bool lk_sums_exact(unsigned lane_abs) {
+  return __reduce_add_sync(0xffffffffu, min(lane_abs, 1u << 24)) < (1u << 24);
+}
+struct LkAcc {     // one sum's accumulators
+  float q0, q1, q2, q3, sc;
+  __device__ __forceinline__ void clear() { q0 = q1 = q2 = q3 = sc = 0.f; }
+  // eight consecutive columns of one row, either as a SIMD group or as scalar columns
+  __device__ __forceinline__ void simd(const float v[8]) {
+    q0 = (q0 + v[0]) + v[4]; q1 = (q1 + v[1]) + v[5]; q2 = (q2 + v[2]) + v[6]; q3 = (q3 + v[3]) + v[7];
+  }
+  __device__ __forceinline__ void scalar(const float v[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sc += v[k];
+  }
+  __device__ __forceinline__ float total(bool any_simd) const { return any_simd ? sc + ((q0 + q2) + (q1 + q3)) : sc; }
+};
+// sums of Ix*Ix, Ix*Iy, Iy*Iy (products < 2^24: exact in float32) in OpenCV's order; every lane gets the result
+__device__ __noinline__ void lk_cv_gradient_sums(const int Ixv[8], const int Iyv[8], int win, float& A11, float& A12,
+                                                 float& A22) {
+  const int nsimd = (win >> 3) << 3;
+  LkAcc a11, a12, a22;
+  a11.clear(); a12.clear(); a22.clear();
+  for (int y = 0; y < win; ++y) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float xx[8], xy[8], yy[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int ix = __shfl_sync(0xffffffffu, Ixv[k], 2 * y + half), iy = __shfl_sync(0xffffffffu, Iyv[k], 2 * y + half);
+        xx[k] = (float)(ix * ix); xy[k] = (float)(ix * iy); yy[k] = (float)(iy * iy);
+      }
+      if (nsimd >= 8 * (half + 1)) { a11.simd(xx); a12.simd(xy); a22.simd(yy); }
+      else { a11.scalar(xx); a12.scalar(xy); a22.scalar(yy); }
+    }
+  }
+  A11 = a11.total(nsimd > 0); A12 = a12.total(nsimd > 0); A22 = a22.total(nsimd > 0);
+}
+// sums of diff*Ix, diff*Iy in OpenCV's order: in a SIMD group the products of columns (j, j+4) are added as integers
+// (v_dotprod) before the conversion to float32; scalar columns convert every product.  dx[k] = diff_k * Ix_k etc.
+__device__ __noinline__ void lk_cv_mismatch_sums(const int dx[8], const int dy[8], int win, float& b1, float& b2) {
+  const int nsimd = (win >> 3) << 3;
+  LkAcc ax, ay;
+  ax.clear(); ay.clear();
+  for (int y = 0; y < win; ++y) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      int vx[8], vy[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        vx[k] = __shfl_sync(0xffffffffu, dx[k], 2 * y + half);
+        vy[k] = __shfl_sync(0xffffffffu, dy[k], 2 * y + half);
+      }
+      if (nsimd >= 8 * (half + 1)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float px = (float)(vx[j] + vx[j + 4]), py = (float)(vy[j] + vy[j + 4]);
+          if (j == 0) { ax.q0 += px; ay.q0 += py; }
+          if (j == 1) { ax.q1 += px; ay.q1 += py; }
+          if (j == 2) { ax.q2 += px; ay.q2 += py; }
+          if (j == 3) { ax.q3 += px; ay.q3 += py; }
+        }
+      } else {
+        float fx[8], fy[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { fx[k] = (float)vx[k]; fy[k] = (float)vy[k]; }
+        ax.scalar(fx); ay.scalar(fy);
+      }
+    }
+  }
+  b1 = ax.total(nsimd > 0); b2 = ay.total(nsimd > 0);
+}
+
 // One warp tracks one point through all pyramid levels (cv::LKTrackerInvoker).  patch / deriv are per-warp shared
 // scratch: (win+3)^2 ints and (win+1)^2 short2.  Returns status (1 = tracked).
 template <typename Img>
@@ -324,7 +408,6 @@ __device__ int lk_track_point(const MeasureParams& p, const Img* prev, const Img
                               short2* deriv, int lane) {
   const int win = p.win;
   const int pw = win + 3, dwid = win + 1;
-  const int npx = win * win;
   const float half = (float)(win - 1) * 0.5f;
   const float FLT_SCALE = 1.0f / (float)(1 << 20);
   float nx = 0.f, ny = 0.f;
@@ -374,10 +457,9 @@ __device__ int lk_track_point(const MeasureParams& p, const Img* prev, const Img
     long long sA11 = 0, sA12 = 0, sA22 = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int q = lane + 32 * k;
+      const int wy = lane >> 1, wx = (lane & 1) * 8 + k;   // lane 2y: columns 0..7 of window row y, lane 2y+1: 8..15
       Iw[k] = 0; Ixv[k] = 0; Iyv[k] = 0;
-      if (q < npx) {
-        const int wy = q / win, wx = q - wy * win;
+      if (wy < win && wx < win) {
         const short* pr = patch + (wy + 1) * pw + wx + 1;
         Iw[k] = descale(pr[0] * iw00 + pr[1] * iw01 + pr[pw] * iw10 + pr[pw + 1] * iw11, 9);
         const short2 d00 = deriv[wy * dwid + wx], d01 = deriv[wy * dwid + wx + 1];
@@ -389,8 +471,13 @@ __device__ int lk_track_point(const MeasureParams& p, const Img* prev, const Img
         sA22 += (long long)Iyv[k] * Iyv[k];
       }
     }
-    sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
-    const float A11 = (float)sA11 * FLT_SCALE, A12 = (float)sA12 * FLT_SCALE, A22 = (float)sA22 * FLT_SCALE;
+    float A11, A12, A22;
+    if (lk_sums_exact((unsigned)(sA11 + sA22))) {      // no partial sum can round: the exact totals are OpenCV's floats
+      A11 = (float)warp_sum_ll(sA11); A12 = (float)warp_sum_ll(sA12); A22 = (float)warp_sum_ll(sA22);
+    } else {
+      lk_cv_gradient_sums(Ixv, Iyv, win, A11, A12, A22);
+    }
+    A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
     float D = A11 * A22 - A12 * A12;
     const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
     if (minEig < p.min_eig || D < 1.1920929e-07f) {
@@ -412,20 +499,25 @@ __device__ int lk_track_point(const MeasureParams& p, const Img* prev, const Img
       iw10 = __float2int_rn((1.f - a) * b * 16384.f);
       iw11 = 16384 - iw00 - iw01 - iw10;
       long long sb1 = 0, sb2 = 0;
+      int dxv[8], dyv[8];
+      unsigned babs = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int q = lane + 32 * k;
-        if (q < npx) {
-          const int wy = q / win, wx = q - wy * win;
+        const int wy = lane >> 1, wx = (lane & 1) * 8 + k;
+        dxv[k] = 0; dyv[k] = 0;
+        if (wy < win && wx < win) {
           const int j00 = lk_px(J, lut, jy + wy, jx + wx), j01 = lk_px(J, lut, jy + wy, jx + wx + 1);
           const int j10 = lk_px(J, lut, jy + wy + 1, jx + wx), j11 = lk_px(J, lut, jy + wy + 1, jx + wx + 1);
           const int diff = descale(j00 * iw00 + j01 * iw01 + j10 * iw10 + j11 * iw11, 9) - Iw[k];
-          sb1 += (long long)diff * Ixv[k];
-          sb2 += (long long)diff * Iyv[k];
+          dxv[k] = diff * Ixv[k]; dyv[k] = diff * Iyv[k];
+          sb1 += dxv[k]; sb2 += dyv[k];
+          babs += (unsigned)abs(dxv[k]) + (unsigned)abs(dyv[k]);
         }
       }
-      sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
-      const float b1 = (float)sb1 * FLT_SCALE, b2 = (float)sb2 * FLT_SCALE;
+      float b1, b2;
+      if (lk_sums_exact(babs)) { b1 = (float)warp_sum_ll(sb1); b2 = (float)warp_sum_ll(sb2); }
+      else lk_cv_mismatch_sums(dxv, dyv, win, b1, b2);
+      b1 *= FLT_SCALE; b2 *= FLT_SCALE;
       const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
       qx += dx; qy += dy;
       nx = qx + half; ny = qy + half;
@@ -656,8 +748,13 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
         for (int r = 0; r < 4; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
       }
     }
-    const float A11 = (float)warp_sum_split(sA11) * FLT_SCALE, A12 = (float)warp_sum_split(sA12) * FLT_SCALE,
-                A22 = (float)warp_sum_split(sA22) * FLT_SCALE;
+    float A11, A12, A22;
+    if (lk_sums_exact((unsigned)(sA11 + sA22))) {      // no partial sum can round: the exact totals are OpenCV's floats
+      A11 = (float)warp_sum_split(sA11); A12 = (float)warp_sum_split(sA12); A22 = (float)warp_sum_split(sA22);
+    } else {
+      lk_cv_gradient_sums(Ixv, Iyv, win, A11, A12, A22);
+    }
+    A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
     float D = A11 * A22 - A12 * A12;
     const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
     if (minEig < p.min_eig || D < 1.1920929e-07f) {
@@ -683,17 +780,24 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
       const unsigned char* r0 = lks_smem + J.org + jy * J.pitch + jx + jrow;
       const unsigned char* r1 = r0 + J.pitch;
       int sb1 = 0, sb2 = 0;
+      int dxv[8], dyv[8];
+      unsigned babs = 0;
       int t0 = r0[0], t1 = r1[0];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int u0 = r0[k + 1], u1 = r1[k + 1];
         // pixels past the end of the window carry Ix = Iy = 0: whatever they read contributes nothing
         const int diff = descale(t0 * iw00 + u0 * iw01 + t1 * iw10 + u1 * iw11, 9) - Iw[k];
-        sb1 += diff * Ixv[k];       // |diff| <= 8160, |Ix| <= 4080: eight products stay below 2^30
-        sb2 += diff * Iyv[k];
+        dxv[k] = diff * Ixv[k];     // |diff| <= 8160, |Ix| <= 4080: eight products stay below 2^30
+        dyv[k] = diff * Iyv[k];
+        sb1 += dxv[k]; sb2 += dyv[k];
+        babs += (unsigned)abs(dxv[k]) + (unsigned)abs(dyv[k]);
         t0 = u0; t1 = u1;
       }
-      const float b1 = (float)warp_sum_split(sb1) * FLT_SCALE, b2 = (float)warp_sum_split(sb2) * FLT_SCALE;
+      float b1, b2;
+      if (lk_sums_exact(babs)) { b1 = (float)warp_sum_split(sb1); b2 = (float)warp_sum_split(sb2); }
+      else lk_cv_mismatch_sums(dxv, dyv, win, b1, b2);
+      b1 *= FLT_SCALE; b2 *= FLT_SCALE;
       const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
       qx += dx; qy += dy;
       nx = qx + half; ny = qy + half;
@@ -709,14 +813,6 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
   return status;
 }
 
-#ifdef LK_TIMING
-__device__ long long lk_timing[64 * 8 * 8];
-extern "C" int32_t rm_debug_lk_timing(long long* host_out, int32_t reset) {
-  if (host_out) cudaMemcpyFromSymbol(host_out, lk_timing, sizeof(long long) * 64 * 8 * 8);
-  if (reset) { static long long z[64 * 8 * 8]; cudaMemcpyToSymbol(lk_timing, z, sizeof(z)); }
-  return 0;
-}
-#endif
 __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const MeasureParams p, const float* pts0,
                                                                        int max_total) {
   const int clip = blockIdx.x;
@@ -802,16 +898,8 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
   auto magic_of = [](int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1u) / (unsigned)d); };
   auto refl1 = [](int v, int n) { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); };   // one reflection (n > |overhang|)
   const int nthr = LKS_WARPS * 32;
-#ifdef LK_TIMING
-  long long tb_[6] = {0, 0, 0, 0, 0, 0}, tkb_ = 0;
-#define LKTB(k) do { if (tid == 0) { long long n_ = clock64(); tb_[k] += n_ - tkb_; tkb_ = n_; } } while (0)
-#else
 #define LKTB(k) do { } while (0)
-#endif
   auto build = [&](int raw_slot, int pyr_slot) {
-#ifdef LK_TIMING
-    if (tid == 0) tkb_ = clock64();
-#endif
     const int src = raw_base + raw_slot * L.raw_bytes + xoff;
     const int base = pyr_slot * L.pyr_bytes;
     const bool words = (L.pad & 3) == 0;           // interior columns start on a word boundary
@@ -955,13 +1043,7 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
 
   // the frame before the chunk is the tracker's "previous image": frame 0 for the first chunk
   const int f_first = resume ? p.f0 : 1;
-#ifdef LK_TIMING
-  long long tk0 = 0, acc_wait = 0, acc_build = 0, acc_track = 0, acc_book = 0;
-#define LKT(acc) do { if (tid == 0) { long long n_ = clock64(); acc += n_ - tk0; tk0 = n_; } } while (0)
-  if (tid == 0) tk0 = clock64();
-#else
 #define LKT(acc) do { } while (0)
-#endif
   stage_raw(f_first - 1, (f_first - 1) & 1);
   cp_async_wait<0>();
   __syncthreads();
@@ -1019,18 +1101,6 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
     }
   }
   __syncthreads();
-#ifdef LK_TIMING
-  LKT(acc_book);
-  if (tid == 0) {
-    long long* row = lk_timing + (clip * 8 + (blk & 7)) * 8;
-    row[0] += acc_wait; row[1] += acc_build; row[2] += acc_track; row[3] += acc_book;
-    row[4] += p.f1 - f_first; row[5] = s_n; row[6] = rw; row[7] = rh;
-    if (clip == 22 && blk == 0) {
-      long long* r2 = lk_timing + (63 * 8 + 7) * 8;   // spare row: build sub-phases of one big block
-      for (int q = 0; q < 5; ++q) r2[q] += tb_[q];
-    }
-  }
-#endif
   if (p.st_n) {   // hand the tracker state to the next chunk
     for (int i = tid; i < s_n; i += blockDim.x) {
       const long long slot = (long long)clip * LK_MAX_PTS + blk * p.ppb + i;
@@ -1297,7 +1367,6 @@ static int32_t measure_flow_impl(rm_handle* h, const uint8_t* frames, int32_t n_
   if (rc != RM_OK || n_clips == 0) return rc;
   DeviceGuard dg(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = rmi_join(h, st)) != RM_OK) return rc;
   if ((rc = measure_gftt(h, &job, st)) != RM_OK) return rc;
   if ((rc = measure_lk(h, &job, 0, n_frames, false, st)) != RM_OK) return rc;
   return measure_pca(h, &job, 0, n_frames, st);
@@ -1322,7 +1391,6 @@ extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_
   if (rc != RM_OK || n_clips == 0) return rc;
   DeviceGuard dg(h->device);
   cudaStream_t sa = (cudaStream_t)stream, sb = h->aux_stream;
-  if ((rc = rmi_join(h, sa)) != RM_OK) return rc;   // a deferred predecessor still owns the scratch and the events
   int n_chunks = job.smem_path ? h->measure_chunks : 1;
   if (n_chunks > n_frames) n_chunks = n_frames;
   if (n_chunks > RM_MAX_CHUNKS) n_chunks = RM_MAX_CHUNKS;
@@ -1352,13 +1420,9 @@ extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_
     int first = h->p.measure_init_len + 8;
     if (first > n_frames / n_chunks) first = n_frames / n_chunks;
     if (first < 1) first = 1;
-    // a short LAST chunk too (option "measure_tail_frames"): its fits are all that is left when the tracker ends
-    int tail = h->measure_tail_frames;
-    if (n_chunks < 3 || tail < 1 || tail > (n_frames - first) / 2) tail = 0;
-    const int mid_chunks = n_chunks - 1 - (tail ? 1 : 0), mid_frames = n_frames - first - tail;
+    const int mid_chunks = n_chunks - 1, mid_frames = n_frames - first;
     bounds[1] = first;
     for (int c = 2; c <= 1 + mid_chunks; ++c) bounds[c] = first + (int)((long long)mid_frames * (c - 1) / mid_chunks);
-    if (tail) bounds[n_chunks] = n_frames;
   }
   for (int c = 0; c < n_chunks; ++c) {
     const int f0 = bounds[c], f1 = bounds[c + 1];
@@ -1366,14 +1430,10 @@ extern "C" int32_t rm_measure_signal(rm_handle* h, const uint8_t* frames, int32_
     RM_CUDA(h, cudaEventRecord(h->ev_chunk[c], sa));
     RM_CUDA(h, cudaStreamWaitEvent(sb, h->ev_chunk[c], 0));
     if ((rc = measure_pca(h, &job, f0, f1, sb)) != RM_OK) return rc;
-    if ((rc = rmi_signal_range(h, f0, f1, c, sb, h->fit_stream[c], h->ev_filt[c], h->ev_bulk[c])) != RM_OK) return rc;
+    if ((rc = rmi_signal_range(h, f0, f1, c, sb, h->fit_stream[c], h->ev_filt[c])) != RM_OK) return rc;
     RM_CUDA(h, cudaEventRecord(h->ev_done[c], h->fit_stream[c]));
   }
-  h->pending_chunks = n_chunks;
-  if (!h->defer_join) return rmi_join(h, sa);
-  // deferred: the caller's stream waits for the first fit pass only; the long fits, the BPM fold and rm_pack_results
-  // finish behind it (rm_join)
-  for (int c = 0; c < n_chunks; ++c) RM_CUDA(h, cudaStreamWaitEvent(sa, h->ev_bulk[c], 0));
+  for (int c = 0; c < n_chunks; ++c) RM_CUDA(h, cudaStreamWaitEvent(sa, h->ev_done[c], 0));   // join
   return RM_OK;
 }
 
@@ -1400,7 +1460,6 @@ extern "C" int32_t rm_measure_signal_stream(rm_handle* h, const uint8_t* frames,
   if (!job.smem_path) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: ROI too large for the shared-memory tracker", __func__);
   DeviceGuard dg(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = rmi_join(h, st)) != RM_OK) return rc;
   if (h->lk_state_cap < n_clips) {
     if (f_begin != 0) return rm_fail(h, RM_ERR_INVALID, "%s: no tracker state for this cohort (start with f_begin = 0)", __func__);
     if (h->d_lk_pts) cudaFree(h->d_lk_pts);
@@ -1420,7 +1479,7 @@ extern "C" int32_t rm_measure_signal_stream(rm_handle* h, const uint8_t* frames,
   if (f_begin == 0 && (rc = measure_gftt(h, &job, st)) != RM_OK) return rc;
   if ((rc = measure_lk(h, &job, f_begin, f_end, true, st)) != RM_OK) return rc;
   if ((rc = measure_pca(h, &job, f_begin, f_end, st)) != RM_OK) return rc;
-  return rmi_signal_range(h, f_begin, f_end, 0, st, st, nullptr, nullptr);
+  return rmi_signal_range(h, f_begin, f_end, 0, st, st, nullptr);
 }
 
 // Copies the ROI crop of k new frames of every camera into its crop ring: frames (n_clips, k, H, W), roi (n_clips, 4) in

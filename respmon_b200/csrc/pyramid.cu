@@ -317,9 +317,8 @@ __global__ void __launch_bounds__(256) pyramid_tail_kernel(const TailParams p) {
       const int sw = p.w[p.first - 1], sh = p.h[p.first - 1], dw = p.w[p.first], dh = p.h[p.first];
       uint32_t* s = reinterpret_cast<uint32_t*>(g + acc);     // staged as integers: half the shared memory of float64
       const uint32_t* src = p.g3_in + f * (long long)(sw * sh);
-#ifdef PT_VEC_STAGE
-      // Developer switch (untimed experiment): 38 % of this kernel's stall samples sit on the staging loop (ncu r01k) --
-      // 16-byte loads, all of a thread's loads in flight before the first store
+      // 16-byte loads, all of a thread's loads in flight before the first store (the staging loop held 38 % of this
+      // kernel's stall samples, ncu r01k: 0.300 -> 0.232 ms per 8192 VGA frames, r02a)
       if (((sw * sh) & 3) == 0 && (acc & 1) == 0) {      // 16-byte aligned on both sides
         const uint4* src4 = reinterpret_cast<const uint4*>(src);
         uint4* s4 = reinterpret_cast<uint4*>(s);
@@ -335,7 +334,6 @@ __global__ void __launch_bounds__(256) pyramid_tail_kernel(const TailParams p) {
             if (i0 + u * (int)blockDim.x < n4) s4[i0 + u * blockDim.x] = v[u];
         }
       } else
-#endif
       for (int i = threadIdx.x; i < sw * sh; i += blockDim.x) s[i] = src[i];
       __syncthreads();
       for (int i = threadIdx.x; i < dw * dh; i += blockDim.x) {
@@ -530,10 +528,11 @@ static int32_t pyramid_build_impl(rm_handle* h, const void* frames, int32_t dtyp
 
   const bool integer_front = dtype == RM_U8 && !h->force_generic_front && pu_supported(frames, W, H, s);
   if (integer_front) {
-    const int mode = pu_best_mode(h, frames, W, H, L, s);
-    int32_t rc = pu_launch(h, mode, (const uint8_t*)frames, reinterpret_cast<uint32_t*>(g_skip), lap_out, n_frames, seg_len,
-                           seg_stride, seg_first, W, H, st);
-    if (rc != RM_OK || mode != 0) return rc;       // fused: the record is written, there is no tail launch
+    if (pu_best_mode(h, frames, W, H))              // one kernel: the record is written, there is no tail launch
+      return pu_launch_fused(h, (const uint8_t*)frames, lap_out, n_frames, seg_len, seg_stride, seg_first, W, H, st);
+    int32_t rc = pu_launch_front(h, (const uint8_t*)frames, reinterpret_cast<uint32_t*>(g_skip), n_frames, seg_len,
+                                 seg_stride, seg_first, W, H, st);
+    if (rc != RM_OK) return rc;
   } else {
     const int elem = dtype == RM_U8 ? 1 : (dtype == RM_F32 ? 4 : 8);
     FrontParams fp;

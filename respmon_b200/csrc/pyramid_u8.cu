@@ -1,51 +1,40 @@
-// Integer front of the Gaussian pyramid for uint8 frames: levels 0 -> 1 -> 2 -> 3 in one pass over the frame.
+// The pyramid stage for uint8 frames: frame in -> packed Laplacian record (levels 4..7) out, one kernel, one pass.
 //
-// Reference: the first three cv2.pyrDown calls of create_gaussian_image_pyramid (pyramid.py:9-17) on frames that are
-// gray/255 (transforms.py:20-23).  A uint8 frame makes every Gaussian level an exact integer over a power of two:
-//   level 1 <= 255*2^8 (u16), level 2 <= 255*2^16, level 3 <= 255*2^24 (u32),
-// so the levels are carried as integers -- no rounding at all until the single scale by 2^-32/255 at level 4 -- and
-// the 5-tap rows become dp4a / dp2a dot products.
+// Reference: create_laplacian_image_pyramid (pyramid.py:9-28) on frames that are gray/255 (transforms.py:20-23), of which
+// transforms.py:156-170 only ever reads the Laplacian levels skip..levels-2.  A uint8 frame makes every Gaussian level
+// an exact integer over a power of two:
+//   level 1 <= 255*2^8 (u16), level 2 <= 255*2^16, level 3 <= 255*2^24 (u32), level 4 <= 255*2^32 (u64),
+// so levels 0..4 are carried as integers -- no rounding at all until the single scale by 2^-32/255 at level 4 -- and
+// the 5-tap rows of the first levels are dp4a / dp2a dot products.
 //
-// Work decomposition: one WARP streams one vertical strip of one frame top to bottom, 8 pixels per lane per row
-// (a 256-pixel-wide strip), with no block-level synchronisation at all.
-//   * rows are copied 8 at a time into a warp-private shared-memory ring with cp.async (4 stages, 3 in flight), every
-//     lane copies and later reads back only its own 8 bytes;
-//   * neighbouring pixels come from the neighbouring lanes by shuffle; two lanes on each interior side of a strip are
+// Work decomposition: one WARP streams one vertical strip of one frame top to bottom, 8 pixels per lane per row (a
+// 256-pixel window); the warps of a frame form a *slot*, a CTA holds several slots.
+//   * rows arrive 8 at a time in a warp-private shared-memory ring.  pyramid_u8_fused_kernel: one TMA box per stage
+//     (cp.async.bulk.tensor.3d: 256 bytes x 8 rows of one frame, zero-filled outside the frame) issued by lane 0 and
+//     an mbarrier per stage; every lane reads back only its own 8 bytes per row.  pyramid_front_u8_kernel (fallback,
+//     rows that are not 16-byte multiples): eight 8-byte cp.async per lane per stage;
+//   * neighbouring pixels come from the neighbouring lanes by shuffle; lanes on the interior sides of a strip are
 //     halo (recomputed by the neighbouring strip), image borders are reflect-101 by byte permutes in the edge lanes;
-//   * the vertical 5-tap windows of the three levels are rolling registers; a block of 8 input rows yields 4 level-1
-//     rows, 2 level-2 rows and 1 level-3 row, which the payload lanes store (4 B each, coalesced);
+//   * the vertical 5-tap windows of levels 1..3 are rolling registers: a block of 8 input rows yields 4 level-1 rows,
+//     2 level-2 rows and 1 level-3 row per lane;
+//   * fused kernel: the level-3 row is filtered horizontally across the lanes (64-bit integers) and every second
+//     block the even-column lanes emit a level-4 value (exact integer * 2^-32/255, the reference's float64 value to
+//     within its own rounding) into the slot's level-4 image in shared memory.  When the strips of a frame are
+//     through, the slot's warps build levels 5..8 (pyramid.py:13-15) and the Laplacians 4..7 (pyramid.py:24-26) in
+//     float64 with the arithmetic of pyramid_tail_kernel operation by operation, and write the record;
 //   * the top border is handled by streaming 16 mirrored rows first (reflect-101 about index 0 commutes with the
-//     symmetric kernel and the 2:1 decimation); the bottom border (even sizes do not commute) by an explicit flush.
-// Fused tail (modes 1 and 2): the level-3 rows go to a per-slot image in shared memory instead of HBM; when the strips of
-// a frame are through, the same warps build levels 4..8 and the Laplacians 4..7 (float64, the arithmetic of
-// pyramid_tail_kernel operation by operation) in the slot's idle ring and write the packed record.  HBM traffic per
-// frame is then SURVEY 8(d)'s figure: W*H bytes read once + the record (1600 doubles at VGA) written once.
-// Mode 2 stages the rows with TMA: one cp.async.bulk.tensor.3d (256 bytes x 8 rows, one frame) per stage issued by
-// lane 0 and an mbarrier per stage, instead of eight 8-byte cp.async per lane; out-of-frame columns are zero-filled
-// by the tensor map.  Mode 0 (level 3 to HBM, pyramid_tail_kernel in pyramid.cu finishes) remains for frames whose
-// level images do not fit the shared memory of a slot.
+//     symmetric kernel and the 2:1 decimation); the bottom border (even sizes do not commute) by an explicit flush;
+//     level 4 reflects its own top and bottom rows explicitly.
+// HBM traffic per frame (fused): W*H bytes read once (+ halo columns, L2 hits) and the record written once -- the
+// algorithmic bytes of SURVEY 8(d).  The fallback writes level 3 (W*H/16 bytes) and pyramid_tail_kernel finishes.
 #include <cuda.h>
 #include "common.cuh"
 #include "pyramid_u8.cuh"
 
-#define PU_STAGES 4
 #define PU_ROWS 8
-// Developer switch (untimed experiment, default off): the x1 taps of the 5-tap rows as a mask on the ALU pipe instead of a
-// dot product with the coefficient vector (…, 0, 1) on the multiplier pipe.  Bit 0: level-1 rows (dp2a), bit 1: level-0
-// rows (dp4a).  Integer arithmetic either way, identical results.
-#ifndef PU_ALU_TAPS
-#define PU_ALU_TAPS 0
-#endif
-#ifndef PU_MAX_WARPS
-#define PU_MAX_WARPS 16     // warps per CTA; each warp owns PU_STAGES * 2 KB of shared memory
-#endif
-#ifndef PU_BOUND_WARPS
-#define PU_BOUND_WARPS PU_MAX_WARPS   // warps the register budget is computed for (launch bounds only): a larger value
-#endif                                // leaves registers for another kernel's blocks on the SM (overlapped steps)
-#ifndef PU_CTAS_PER_SM
-#define PU_CTAS_PER_SM 1    // resident CTAs per SM the grid is sized for (smaller CTAs leave room for the measure stage of
-#endif                      // the previous batch when steps overlap: rm_join / "defer_join")
 #define PU_STAGE_BYTES (PU_ROWS * 256)
+#define PU_FRONT_STAGES 4      // fallback kernel: cp.async ring depth
+#define PU_FRONT_WARPS 24      // fallback kernel: warps per CTA (85 registers; 0.626 -> 0.569 ms per 8192 VGA frames, r02a)
 
 __device__ __forceinline__ void pu_cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -56,7 +45,6 @@ template <int N>
 __device__ __forceinline__ void pu_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
-
 __device__ __forceinline__ void pu_mbar_init(unsigned bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
 }
@@ -86,6 +74,10 @@ __device__ __forceinline__ void pu_tma_load(unsigned dst, const CUtensorMap* map
 __device__ __forceinline__ unsigned v5(unsigned a, unsigned b, unsigned c, unsigned d, unsigned e) {
   return ((b + d + c) << 2) + (a + e + (c + c));   // adds and one shift-add: keeps the multiplier pipe for the dot products
 }
+__device__ __forceinline__ unsigned long long v5q(unsigned long long a, unsigned long long b, unsigned long long c,
+                                                  unsigned long long d, unsigned long long e) {
+  return ((b + d + c) << 2) + (a + e + (c + c));
+}
 
 struct PuState {
   unsigned a[4], b[4];     // level 0->1: horizontally filtered rows r-4..r-1, packed column pairs (k0,k1) and (k2,k3)
@@ -100,13 +92,8 @@ __device__ __forceinline__ void pu_h1(unsigned P, unsigned Q, int lane, int last
   unsigned Pr = __shfl_down_sync(0xffffffffu, P, 1);
   if (LEFT && lane == 0) Ql = __byte_perm(P, Q, 0x3254);   // columns -2, -1 are columns 2, 1
   if (RIGHT && lane == last_lane) Pr = Q;                  // column W1 is column W1-2
-#if PU_ALU_TAPS & 1
-  g0 = __dp2a_lo(Ql, 0x0401u, __dp2a_lo(P, 0x0406u, Q & 0xffffu));
-  g1 = __dp2a_lo(P, 0x0401u, __dp2a_lo(Q, 0x0406u, Pr & 0xffffu));
-#else
   g0 = __dp2a_lo(Ql, 0x0401u, __dp2a_lo(P, 0x0406u, __dp2a_lo(Q, 0x0001u, 0u)));
   g1 = __dp2a_lo(P, 0x0401u, __dp2a_lo(Q, 0x0406u, __dp2a_lo(Pr, 0x0001u, 0u)));
-#endif
 }
 // horizontal 5-tap at level 2 -> the lane's level-3 column.  q0, q1 = level-2 columns (2L, 2L+1).
 template <bool LEFT, bool RIGHT>
@@ -130,15 +117,9 @@ __device__ __forceinline__ void pu_block(PuState& s, const uint2 w[PU_ROWS], int
     if (LEFT && lane == 0) wl = __byte_perm(w0, w1, 0x1234);          // pixels -2, -1 are pixels 2, 1
     if (RIGHT && lane == last_lane) wr = __byte_perm(w1, 0u, 0x0002); // pixel W is pixel W-2
     const unsigned k0 = __dp4a(wl, 0x04010000u, __dp4a(w0, 0x00010406u, 0u));
-#if PU_ALU_TAPS & 2
-    const unsigned k1 = __dp4a(w0, 0x04060401u, w1 & 0xffu);
-    const unsigned k2 = __dp4a(w0, 0x04010000u, __dp4a(w1, 0x00010406u, 0u));
-    const unsigned k3 = __dp4a(w1, 0x04060401u, wr & 0xffu);
-#else
     const unsigned k1 = __dp4a(w0, 0x04060401u, __dp4a(w1, 0x00000001u, 0u));
     const unsigned k2 = __dp4a(w0, 0x04010000u, __dp4a(w1, 0x00010406u, 0u));
     const unsigned k3 = __dp4a(w1, 0x04060401u, __dp4a(wr, 0x00000001u, 0u));
-#endif
     ha[i] = k0 + (k1 << 16);
     hb[i] = k2 + (k3 << 16);
   }
@@ -185,36 +166,28 @@ __device__ __forceinline__ unsigned pu_flush(const PuState& s, int lane, int las
   return v5(s.c[0], s.c[1], s.c[2], m, s.c[2]);
 }
 
-// MODE 0: level-3 rows to HBM (g3);  MODE 1: to the slot's shared image (l3), rows staged by cp.async;  MODE 2: same, rows
-// staged by TMA.  `phase` (MODE 2) holds the parity the warp waits for next on each of its PU_STAGES mbarriers.
-template <int WT, bool LEFT, bool RIGHT, int MODE>
-__device__ __forceinline__ void pu_run_frame(const PuParams& p, const CUtensorMap* tmap, const uint8_t* __restrict__ fsrc,
-                                             int sframe, uint32_t* __restrict__ g3, unsigned char* ring, unsigned mbar,
-                                             unsigned& phase, int lane, int col, int store_lo, int store_hi,
-                                             int last_lane) {
+__device__ __forceinline__ void pu_clear(PuState& s) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { s.a[i] = 0; s.b[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { s.g0[i] = 0; s.g1[i] = 0; s.c[i] = 0; }
+}
+
+// ==================================================================================================== fallback front
+// Level 3 (exact integers) to HBM; pyramid_tail_kernel (pyramid.cu) finishes.  Rows by cp.async, any W % 8 == 0.
+template <int WT, bool LEFT, bool RIGHT>
+__device__ __forceinline__ void pu_front_frame(const PuParams& p, const uint8_t* __restrict__ fsrc, uint32_t* __restrict__ g3,
+                                               unsigned char* ring, int lane, int col, int store_lo, int store_hi) {
   const int W = WT ? WT : p.W;        // a compile-time width turns the row offsets of the copies into immediates
+  const int last_lane = store_hi;
   const bool in_img = col >= 0 && col < p.W3 && lane <= store_hi + PU_HALO_LANES;
   const uint8_t* lsrc = fsrc + (in_img ? 8 * col : 0);
   const int src_bytes = in_img ? 8 : 0;
   const int nblk = p.H >> 3;
   unsigned char* my = ring + lane * 8;
-  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
-  const int x0 = 8 * (col - lane);    // first column of the warp's 256-byte window (>= 0; the right end may hang over)
   auto issue = [&](int b) {
-    if (MODE == 2) {
-      if (b < nblk) {
-        __syncwarp();                                              // every lane is done with the stage's previous rows
-        if (lane == 0) {
-          const int stage = (b + 2) & (PU_STAGES - 1);
-          pu_mbar_expect_tx(mbar + 8 * stage, PU_STAGE_BYTES);
-          // rows above the frame are the mirrored rows 16..9 / 8..1: fetched in frame order, read back bottom-up
-          pu_tma_load(ring_s + stage * PU_STAGE_BYTES, tmap, x0, b >= 0 ? 8 * b : -8 * b - 7, sframe, mbar + 8 * stage);
-        }
-      }
-      return;
-    }
     if (b < nblk) {
-      unsigned char* dst = my + ((b + 2) & (PU_STAGES - 1)) * PU_STAGE_BYTES;
+      unsigned char* dst = my + ((b + 2) & (PU_FRONT_STAGES - 1)) * PU_STAGE_BYTES;
       if (b >= 0) {
         const uint8_t* blk = lsrc + (long long)(8 * b) * W;
 #pragma unroll
@@ -228,56 +201,86 @@ __device__ __forceinline__ void pu_run_frame(const PuParams& p, const CUtensorMa
     pu_commit();
   };
   PuState s;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { s.a[i] = 0; s.b[i] = 0; }
-#pragma unroll
-  for (int i = 0; i < 3; ++i) { s.g0[i] = 0; s.g1[i] = 0; s.c[i] = 0; }
+  pu_clear(s);
   issue(-2);
   issue(-1);
   issue(0);
   const bool storing = lane >= store_lo && lane <= store_hi;
   uint32_t* out = g3 + col;
-  auto step = [&](int b, bool mirrored) {
+#pragma unroll 2
+  for (int b = -2; b < nblk; ++b) {
     issue(b + 3);
-    const int stage = (b + 2) & (PU_STAGES - 1);
-    if (MODE == 2) {
-      pu_mbar_wait(mbar + 8 * stage, (phase >> stage) & 1u);
-      phase ^= 1u << stage;
-    } else {
-      pu_wait<3>();                                            // block b has landed (3 younger groups may be in flight)
-    }
-    const unsigned char* src = my + stage * PU_STAGE_BYTES;
+    pu_wait<3>();                                              // block b has landed (3 younger groups may be in flight)
+    const unsigned char* src = my + ((b + 2) & (PU_FRONT_STAGES - 1)) * PU_STAGE_BYTES;
     uint2 w[PU_ROWS];
 #pragma unroll
-    for (int i = 0; i < PU_ROWS; ++i)
-      w[i] = *reinterpret_cast<const uint2*>(src + ((MODE == 2 && mirrored) ? PU_ROWS - 1 - i : i) * 256);
+    for (int i = 0; i < PU_ROWS; ++i) w[i] = *reinterpret_cast<const uint2*>(src + i * 256);
     unsigned o;
     pu_block<LEFT, RIGHT>(s, w, lane, last_lane, o);
     if (b >= 1 && storing) out[(long long)(b - 1) * p.W3] = o;
-  };
-  step(-2, true);
-  step(-1, true);
-#pragma unroll 2
-  for (int b = 0; b < nblk; ++b) step(b, false);
+  }
   const unsigned o = pu_flush<LEFT, RIGHT>(s, lane, last_lane);
   if (storing) out[(long long)(nblk - 1) * p.W3] = o;
-  if (MODE != 2) pu_wait<0>();
+  pu_wait<0>();
 }
 
-// ---------------------------------------------------------------------------------------------------- fused tail
-__device__ __forceinline__ void pu_slot_sync(int slot, int nt) {
+// frame f of the batch is source frame (f / seg_len) * seg_stride + seg_first + f % seg_len; 32-bit division (the 64-bit
+// one cost 8 % of the front kernel's stall samples for one use per frame, ncu r01m; the launch checks the ranges)
+__device__ __forceinline__ long long pu_source_frame(long long frame, long long seg_len, long long seg_stride,
+                                                     long long seg_first) {
+  const unsigned fr = (unsigned)frame, sl = (unsigned)seg_len;
+  return (long long)(fr / sl) * seg_stride + seg_first + (long long)(fr % sl);
+}
+
+template <int WT>
+__global__ void __launch_bounds__(PU_FRONT_WARPS * 32, 1) pyramid_front_u8_kernel(const PuParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = warp / p.n_strips, strip = warp - slot * p.n_strips;
+  unsigned char* ring = smem + (size_t)warp * PU_FRONT_STAGES * PU_STAGE_BYTES;
+  const bool left = strip == 0, right = strip == p.n_strips - 1;
+  const int c0 = strip * p.cols_per_strip;
+  const int c1 = min(p.W3, c0 + p.cols_per_strip);
+  const int lane_off = left ? 0 : PU_HALO_LANES;
+  const int col = c0 - lane_off + lane;
+  const int store_lo = lane_off, store_hi = lane_off + (c1 - c0) - 1;
+  const long long g3_elems = (long long)p.W3 * p.H3;
+  for (long long frame = (long long)blockIdx.x * p.frames_per_cta + slot; frame < p.n_frames;
+       frame += (long long)gridDim.x * p.frames_per_cta) {
+    const long long sframe = pu_source_frame(frame, p.seg_len, p.seg_stride, p.seg_first);
+    const uint8_t* fsrc = p.frames + sframe * p.frame_elems;
+    uint32_t* g3 = p.g3 + frame * g3_elems;
+    // The strips of a frame share their halo columns.  Left alone, the warps of a slot drift apart over the frames (edge
+    // strips are cheaper) until a halo sector read by one warp has left L2 before its neighbour asks for it -- 23 % extra
+    // DRAM reads at 8192 frames per launch (ncu, profiles/r01g).  A named barrier per slot re-aligns them every frame.
+    if (p.n_strips > 1) asm volatile("bar.sync %0, %1;\n" ::"r"(slot + 1), "r"(p.n_strips * 32) : "memory");
+    if (left && right) pu_front_frame<WT, true, true>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
+    else if (left) pu_front_frame<WT, true, false>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
+    else if (right) pu_front_frame<WT, false, true>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
+    else pu_front_frame<WT, false, false>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
+  }
+}
+
+// ==================================================================================================== fused kernel
+// Level-4 columns are the unit of a strip: strip s produces columns [k0, k1); lane L holds level-3 column base + L
+// (base even, so the 256-byte window starts on a 16-byte boundary).  Level 3 is valid in lanes 2..30 of an interior
+// window (lanes 0.. of the left strip, ..last_lane of the right one), a level-4 column with centre lane c needs lanes
+// c-2..c+2: an interior strip yields 13 columns, the edge strips 15 / 14.
+__device__ __forceinline__ void pf_slot_sync(int slot, int nt) {
   if (nt == 32) __syncwarp();
   else asm volatile("bar.sync %0, %1;\n" ::"r"(slot + 1), "r"(nt) : "memory");
 }
-__device__ __forceinline__ double* pu_level(const PuParams& p, int l, unsigned char* ring_slot, unsigned char* extra_slot) {
-  const int o = p.lvl_off[l];
-  return reinterpret_cast<double*>(o >= 0 ? ring_slot + o : extra_slot + (-o - 1));
+__device__ __forceinline__ double* pf_level(const PfParams& p, unsigned char* lvl_slot, int l) {
+  return reinterpret_cast<double*>(lvl_slot + p.lvl_off[l]);
 }
+// i / w for i < 2^16, 2 <= w < 2^16 with m = ceil(2^32 / w); m = 0 stands for w = 1
+__device__ __forceinline__ int pf_div(int i, unsigned m) { return m ? (int)__umulhi((unsigned)i, m) : i; }
+
 // G_{l+1} = pyrDown(G_l) on float64 (pyramid.py:13-15), the arithmetic of pyramid_tail_kernel
-__device__ __forceinline__ void pu_down(const double* __restrict__ s, double* __restrict__ d, int sw, int sh, int dw, int dh,
-                                        int t, int nt) {
+__device__ __forceinline__ void pf_down(const double* __restrict__ s, double* __restrict__ d, int sw, int sh, int dw, int dh,
+                                        unsigned mdw, int t, int nt) {
   for (int i = t; i < dw * dh; i += nt) {
-    const int x = i % dw, y = i / dw;
+    const int y = pf_div(i, mdw), x = i - y * dw;
     const int x0 = reflect101(2 * x - 2, sw), x1 = reflect101(2 * x - 1, sw), x3 = reflect101(2 * x + 1, sw),
               x4 = reflect101(2 * x + 2, sw);
     double r[5];
@@ -289,181 +292,249 @@ __device__ __forceinline__ void pu_down(const double* __restrict__ s, double* __
     d[i] = tap5(r[0], r[1], r[2], r[3], r[4]) * (1.0 / 256.0);
   }
 }
-// L_l = G_l - pyrUp(G_{l+1})   (pyramid.py:24-26)
-__device__ __forceinline__ void pu_lap(const double* __restrict__ cur, const double* __restrict__ s, double* __restrict__ out,
-                                       int sw, int sh, int dw, int dh, int t, int nt) {
-  for (int i = t; i < dw * dh; i += nt) {
-    const int x = i % dw, y = i / dw;
-    const UpTaps tx = up_taps(x, sw), ty = up_taps(y, sh);
-    const double* r0 = s + ty.i0 * sw;
-    const double* r1 = s + ty.i1 * sw;
-    const double* r2 = s + ty.i2 * sw;
-    const double h0 = up_combine(tx, r0[tx.i0], r0[tx.i1], r0[tx.i2]);
-    const double h1 = up_combine(tx, r1[tx.i0], r1[tx.i1], r1[tx.i2]);
-    const double h2 = up_combine(tx, r2[tx.i0], r2[tx.i1], r2[tx.i2]);
-    out[i] = cur[i] - up_combine(ty, h0, h1, h2) * (1.0 / 64.0);
-  }
-}
-// Levels first..top and the Laplacian record of one frame, by the nt threads of the frame's slot (t = 0..nt-1).
-// l3: the frame's level-3 image (exact integers) in shared memory; the slot's ring is idle and holds the levels.
-__device__ __noinline__ void pu_tail(const PuParams& p, const uint32_t* __restrict__ l3, unsigned char* ring_slot,
-                                     unsigned char* extra_slot, double* __restrict__ rec, int slot, int t, int nt) {
-  const int f = p.first, top = p.top;
-  {   // integer level first-1 -> level first: the 5x5 sums stay exact in float64 (< 2^53), one scale at the end
-    const int sw = p.W3, sh = p.H3, dw = p.w[f], dh = p.h[f];
-    double* g = pu_level(p, f, ring_slot, extra_slot);
-    for (int i = t; i < dw * dh; i += nt) {
-      const int x = i % dw, y = i / dw;
-      const int x0 = reflect101(2 * x - 2, sw), x1 = reflect101(2 * x - 1, sw), x3 = reflect101(2 * x + 1, sw),
-                x4 = reflect101(2 * x + 2, sw);
-      double r[5];
+// L_l = G_l - pyrUp(G_{l+1}) (pyramid.py:24-26), one thread per source pixel = 2x2 outputs from its 3x3 neighbourhood;
+// per output the operations of up_taps / up_combine (pyr_core.h) in their order:
+//   even index 2i: s[refl(i-1)] + s[min(i+1,n-1)], then fma(6, s[i], .);   odd index 2i+1: 4 * (s[i] + s[min(i+1,n-1)])
+__device__ __forceinline__ void pf_lap(const double* __restrict__ cur, const double* __restrict__ s, double* __restrict__ out,
+                                       int sw, int sh, int dw, int dh, unsigned msw, int t, int nt) {
+  for (int i = t; i < sw * sh; i += nt) {
+    const int bj = pf_div(i, msw), bi = i - bj * sw;
+    const int cm = reflect101(bi - 1, sw), cp = bi + 1 < sw - 1 ? bi + 1 : sw - 1;
+    const int rm = reflect101(bj - 1, sh), rp = bj + 1 < sh - 1 ? bj + 1 : sh - 1;
+    double he[3], ho[3];
+    const int rows[3] = {rm, bj, rp};
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const uint32_t* row = l3 + reflect101(2 * y + k - 2, sh) * sw;
-        r[k] = tap5((double)row[x0], (double)row[x1], (double)row[2 * x], (double)row[x3], (double)row[x4]);
-      }
-      g[i] = tap5(r[0], r[1], r[2], r[3], r[4]) * p.g_scale;
+    for (int k = 0; k < 3; ++k) {
+      const double* row = s + rows[k] * sw;
+      const double a = row[cm], b = row[bi], c = row[cp];
+      he[k] = fma(6.0, b, a + c);
+      ho[k] = 4.0 * (b + c);
+    }
+    const int x = 2 * bi, y = 2 * bj;
+    const bool x1 = x + 1 < dw, y1 = y + 1 < dh;
+    const double* c0 = cur + y * dw + x;
+    double* o0 = out + y * dw + x;
+    o0[0] = c0[0] - fma(6.0, he[1], he[0] + he[2]) * (1.0 / 64.0);
+    if (x1) o0[1] = c0[1] - fma(6.0, ho[1], ho[0] + ho[2]) * (1.0 / 64.0);
+    if (y1) {
+      o0[dw] = c0[dw] - (4.0 * (he[1] + he[2])) * (1.0 / 64.0);
+      if (x1) o0[dw + 1] = c0[dw + 1] - (4.0 * (ho[1] + ho[2])) * (1.0 / 64.0);
     }
   }
-  pu_slot_sync(slot, nt);
-  if (f + 1 <= top)
-    pu_down(pu_level(p, f, ring_slot, extra_slot), pu_level(p, f + 1, ring_slot, extra_slot), p.w[f], p.h[f], p.w[f + 1],
-            p.h[f + 1], t, nt);
-  pu_slot_sync(slot, nt);
+}
+
+// Levels first+1..top and the Laplacian record of one frame from the slot's level-`first` image, by the nt threads of
+// the slot (t = 0..nt-1).
+__device__ __noinline__ void pf_tail(const PfParams& p, unsigned char* lvl_slot, double* __restrict__ rec, int slot, int t,
+                                     int nt) {
+  const int f = p.first, top = p.top;
+  pf_down(pf_level(p, lvl_slot, f), pf_level(p, lvl_slot, f + 1), p.w[f], p.h[f], p.w[f + 1], p.h[f + 1], p.magic[f + 1], t, nt);
+  pf_slot_sync(slot, nt);
   // the small levels are a chain of tiny images: one warp walks it while the others write the largest Laplacian
   if (t < 32) {
     for (int l = f + 1; l < top; ++l) {
-      pu_down(pu_level(p, l, ring_slot, extra_slot), pu_level(p, l + 1, ring_slot, extra_slot), p.w[l], p.h[l], p.w[l + 1],
-              p.h[l + 1], t, 32);
+      pf_down(pf_level(p, lvl_slot, l), pf_level(p, lvl_slot, l + 1), p.w[l], p.h[l], p.w[l + 1], p.h[l + 1], p.magic[l + 1], t, 32);
       __syncwarp();
     }
   }
   if (nt == 32 || t >= 32) {
     const int t2 = nt == 32 ? t : t - 32, nt2 = nt == 32 ? 32 : nt - 32;
-    pu_lap(pu_level(p, f, ring_slot, extra_slot), pu_level(p, f + 1, ring_slot, extra_slot), rec + p.rec_off[f], p.w[f + 1],
-           p.h[f + 1], p.w[f], p.h[f], t2, nt2);
+    pf_lap(pf_level(p, lvl_slot, f), pf_level(p, lvl_slot, f + 1), rec + p.rec_off[f], p.w[f + 1], p.h[f + 1], p.w[f], p.h[f],
+           p.magic[f + 1], t2, nt2);
   }
-  pu_slot_sync(slot, nt);
+  pf_slot_sync(slot, nt);
   for (int l = f + 1; l < top; ++l)
-    pu_lap(pu_level(p, l, ring_slot, extra_slot), pu_level(p, l + 1, ring_slot, extra_slot), rec + p.rec_off[l], p.w[l + 1],
-           p.h[l + 1], p.w[l], p.h[l], t, nt);
+    pf_lap(pf_level(p, lvl_slot, l), pf_level(p, lvl_slot, l + 1), rec + p.rec_off[l], p.w[l + 1], p.h[l + 1], p.w[l], p.h[l],
+           p.magic[l + 1], t, nt);
 }
 
-template <int WT, int MODE>
-__global__ void __launch_bounds__(PU_BOUND_WARPS * 32, PU_CTAS_PER_SM)
-    pyramid_front_u8_kernel(const __grid_constant__ PuParams p, const __grid_constant__ CUtensorMap tmap) {
+struct PfLane {       // what a lane does with its level-3 / level-4 column
+  int s_m2, s_m1, s_p1, s_p2;   // source lanes of the level-3 columns col-2, col-1, col+1, col+2 (reflect-101 at the image border)
+  int k;                        // level-4 column the lane emits, -1: none
+};
+
+// S-stage TMA ring: `stage` is the ring slot of the next block to consume, `phase` the parity awaited per slot.
+template <int S, bool LEFT, bool RIGHT>
+__device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMap* tmap, int sframe, int next_sframe,
+                                             unsigned ring_s, const unsigned char* my, unsigned mbar, unsigned& phase,
+                                             int& stage, double* __restrict__ g4, const PfLane& ln, int lane, int x0,
+                                             int last_lane) {
+  const int nblk = p.H >> 3;
+  // block b (-2 .. nblk-1) of this frame, then blocks -2 .. of the next one: the ring never drains between frames
+  auto issue = [&](int b, int st) {
+    int z = sframe;
+    if (b >= nblk) { b -= nblk + 2; z = next_sframe; }
+    if (z < 0) return;
+    __syncwarp();                                              // every lane is done with the stage's previous rows
+    if (lane == 0) {
+      pu_mbar_expect_tx(mbar + 8 * st, PU_STAGE_BYTES);
+      // rows above the frame are the mirrored rows 16..9 / 8..1: fetched in frame order, read back bottom-up
+      pu_tma_load(ring_s + st * PU_STAGE_BYTES, tmap, x0, b >= 0 ? 8 * b : -8 * b - 7, z, mbar + 8 * st);
+    }
+  };
+  PuState s;
+  pu_clear(s);
+  unsigned long long hz0 = 0, hz1 = 0, hz2 = 0, hz3 = 0;       // horizontally filtered level-3 rows r-4 .. r-1
+  const int W4 = p.w[p.first];
+  // one level-3 row (r = 0 .. H3-1) of the lane's column: filter across the lanes, every second row emit level 4
+  auto level3_row = [&](unsigned o, int r) {
+    const unsigned a = __shfl_sync(0xffffffffu, o, ln.s_m2), b = __shfl_sync(0xffffffffu, o, ln.s_m1);
+    const unsigned d = __shfl_sync(0xffffffffu, o, ln.s_p1), e = __shfl_sync(0xffffffffu, o, ln.s_p2);
+    const unsigned long long hz = (unsigned long long)a + e + 4ull * ((unsigned long long)b + d) + 6ull * o;
+    if (!(r & 1) && r >= 2) {
+      const unsigned long long v = r == 2 ? v5q(hz, hz3, hz2, hz3, hz) : v5q(hz0, hz1, hz2, hz3, hz);
+      if (ln.k >= 0) g4[((r - 2) >> 1) * W4 + ln.k] = (double)v * p.g_scale;
+    }
+    hz0 = hz1; hz1 = hz2; hz2 = hz3; hz3 = hz;
+  };
+  auto step = [&](int b, bool mirrored) {
+    // the stage consumed S-1 steps ago (block b-1) is free again: fetch block b+S-1 into it
+    issue(b + S - 1, stage == 0 ? S - 1 : stage - 1);
+    pu_mbar_wait(mbar + 8 * stage, (phase >> stage) & 1u);
+    phase ^= 1u << stage;
+    const unsigned char* src = my + stage * PU_STAGE_BYTES;
+    stage = stage + 1 == S ? 0 : stage + 1;
+    uint2 w[PU_ROWS];
+#pragma unroll
+    for (int i = 0; i < PU_ROWS; ++i) w[i] = *reinterpret_cast<const uint2*>(src + (mirrored ? PU_ROWS - 1 - i : i) * 256);
+    unsigned o;
+    pu_block<LEFT, RIGHT>(s, w, lane, last_lane, o);
+    if (b >= 1) level3_row(o, b - 1);
+  };
+  step(-2, true);
+  step(-1, true);
+#pragma unroll 2
+  for (int b = 0; b < nblk; ++b) step(b, false);
+  const int H3 = nblk;
+  level3_row(pu_flush<LEFT, RIGHT>(s, lane, last_lane), H3 - 1);
+  // bottom border of level 4: hz3 = row H3-1, hz2 = H3-2, ...
+  const unsigned long long v = (H3 & 1) ? v5q(hz1, hz2, hz3, hz2, hz1) : v5q(hz0, hz1, hz2, hz3, hz2);
+  if (ln.k >= 0) g4[((H3 - 1) >> 1) * W4 + ln.k] = (double)v * p.g_scale;
+}
+
+// MAXW warps per CTA; registers are allocated to warps four at a time: 65536 / (32 * MAXW rounded up to 4), rounded down
+// to the allocation unit of 8 per thread -- 96 for 18 warps, 80 for 21 and 24
+template <int S, int MAXW>
+__global__ void __maxnreg__((65536 / (32 * ((MAXW + 3) & ~3))) & ~7)
+    pyramid_u8_fused_kernel(const __grid_constant__ PfParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / p.n_strips, strip = warp - slot * p.n_strips;
-  unsigned char* ring = smem + (size_t)warp * PU_STAGES * PU_STAGE_BYTES;
   const bool left = strip == 0, right = strip == p.n_strips - 1;
-  const int c0 = strip * p.cols_per_strip;
-  const int c1 = min(p.W3, c0 + p.cols_per_strip);
-  const int lane_off = left ? 0 : PU_HALO_LANES;
-  const int col = c0 - lane_off + lane;
-  const int store_lo = lane_off, store_hi = lane_off + (c1 - c0) - 1;
-  const long long g3_elems = (long long)p.W3 * p.H3;
-  const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem + p.mbar_base) + warp * PU_STAGES * 8;
+  const int base = p.strip_base[strip];
+  const int col = base + lane;
+  const int last_lane = p.W3 - 1 - base;                        // lane of the last level-3 column (right strip)
+  PfLane ln;
+  ln.s_m2 = (reflect101(col - 2, p.W3) - base) & 31; ln.s_m1 = (reflect101(col - 1, p.W3) - base) & 31;
+  ln.s_p1 = (reflect101(col + 1, p.W3) - base) & 31; ln.s_p2 = (reflect101(col + 2, p.W3) - base) & 31;
+  ln.k = (!(col & 1) && (col >> 1) >= p.strip_k0[strip] && (col >> 1) < p.strip_k1[strip]) ? (col >> 1) : -1;
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(smem) + warp * S * PU_STAGE_BYTES;
+  const unsigned char* my = smem + (size_t)warp * S * PU_STAGE_BYTES + lane * 8;
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem + p.mbar_base) + warp * S * 8;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) pu_mbar_init(mbar + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+  unsigned char* lvl_slot = smem + p.lvl_base + (size_t)slot * p.lvl_stride;
+  double* g4 = pf_level(p, lvl_slot, p.first);
+  const int nt = p.n_strips * 32, t = strip * 32 + lane;
+  const long long stride = (long long)gridDim.x * p.frames_per_cta;
+  long long frame = (long long)blockIdx.x * p.frames_per_cta + slot;
   unsigned phase = 0;
-  if (MODE == 2) {
+  int stage = 0;
+  if (frame < p.n_frames) {   // the first S-1 blocks of the slot's first frame
+    const int z = (int)pu_source_frame(frame, p.seg_len, p.seg_stride, p.seg_first);
     if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < PU_STAGES; ++i) pu_mbar_init(mbar + 8 * i, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      for (int i = 0; i < S - 1; ++i) {
+        const int b = i - 2;
+        pu_mbar_expect_tx(mbar + 8 * i, PU_STAGE_BYTES);
+        pu_tma_load(ring_s + i * PU_STAGE_BYTES, &tmap, 8 * base, b >= 0 ? 8 * b : -8 * b - 7, z, mbar + 8 * i);
+      }
     }
-    __syncthreads();
   }
-  uint32_t* l3 = reinterpret_cast<uint32_t*>(smem + p.l3_base + (size_t)slot * p.l3_stride);
-  unsigned char* ring_slot = smem + (size_t)slot * p.n_strips * PU_STAGES * PU_STAGE_BYTES;
-  unsigned char* extra_slot = smem + p.extra_base + (size_t)slot * p.extra_stride;
-  for (long long frame = (long long)blockIdx.x * p.frames_per_cta + slot; frame < p.n_frames;
-       frame += (long long)gridDim.x * p.frames_per_cta) {
-#ifdef PU_IDX32
-    // Developer switch (untimed experiment): the 64-bit division costs 8 % of the kernel's stall samples (ncu r01m) for one
-    // use per frame; frame counts and segment lengths fit 32 bits (checked by pu_launch)
-    const unsigned fr = (unsigned)frame, sl = (unsigned)p.seg_len;
-    const long long sframe = (long long)(fr / sl) * p.seg_stride + p.seg_first + (long long)(fr % sl);
-#else
-    const long long sframe = (frame / p.seg_len) * p.seg_stride + p.seg_first + frame % p.seg_len;
-#endif
-    const uint8_t* fsrc = p.frames + sframe * p.frame_elems;
-    uint32_t* g3 = MODE == 0 ? p.g3 + frame * g3_elems : l3;
-    // The strips of a frame share their halo columns.  Left alone, the warps of a slot drift apart over the frames (edge
-    // strips are cheaper) until a halo sector read by one warp has left L2 before its neighbour asks for it -- 23 % extra
-    // DRAM reads at 8192 frames per launch (ncu, profiles/r01g).  A named barrier per slot re-aligns them every frame
-    // (fused tail: it also keeps the next frame's rows out of the ring until every warp has left the tail).
-    if (p.n_strips > 1) asm volatile("bar.sync %0, %1;\n" ::"r"(slot + 1), "r"(p.n_strips * 32) : "memory");
-    else if (MODE != 0) __syncwarp();
-    if (left && right) pu_run_frame<WT, true, true, MODE>(p, &tmap, fsrc, (int)sframe, g3, ring, mbar, phase, lane, col, store_lo, store_hi, store_hi);
-    else if (left) pu_run_frame<WT, true, false, MODE>(p, &tmap, fsrc, (int)sframe, g3, ring, mbar, phase, lane, col, store_lo, store_hi, store_hi);
-    else if (right) pu_run_frame<WT, false, true, MODE>(p, &tmap, fsrc, (int)sframe, g3, ring, mbar, phase, lane, col, store_lo, store_hi, store_hi);
-    else pu_run_frame<WT, false, false, MODE>(p, &tmap, fsrc, (int)sframe, g3, ring, mbar, phase, lane, col, store_lo, store_hi, store_hi);
-    if (MODE != 0) {
-      const int nt = p.n_strips * 32;
-      pu_slot_sync(slot, nt);                                  // the level-3 image is complete, the ring is idle
-      pu_tail(p, l3, ring_slot, extra_slot, p.lap_out + frame * p.record_len, slot, strip * 32 + lane, nt);
-      // the levels were written to the ring through the generic proxy; the next frame's rows arrive through the async one
-      if (MODE == 2) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    }
+  for (; frame < p.n_frames; frame += stride) {
+    const int sframe = (int)pu_source_frame(frame, p.seg_len, p.seg_stride, p.seg_first);
+    const int next_sframe = frame + stride < p.n_frames ? (int)pu_source_frame(frame + stride, p.seg_len, p.seg_stride, p.seg_first) : -1;
+    if (left && right) pf_run_frame<S, true, true>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, last_lane);
+    else if (left) pf_run_frame<S, true, false>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, last_lane);
+    else if (right) pf_run_frame<S, false, true>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, last_lane);
+    else pf_run_frame<S, false, false>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, last_lane);
+    // The barrier that completes the level-4 image also re-aligns the strips of the frame (they share halo columns:
+    // left alone they drift apart until a halo sector has left L2 before the neighbour asks for it, profiles/r01g).
+    pf_slot_sync(slot, nt);
+    pf_tail(p, lvl_slot, p.lap_out + frame * p.record_len, slot, t, nt);
+    pf_slot_sync(slot, nt);                                    // the level images are free for the next frame
   }
 }
 
-// The integer path needs: uint8 frames, four front levels, W and H multiples of 8 (all three decimated sizes even),
+// ==================================================================================================== host side
+// The integer paths need: uint8 frames, four front levels, W and H multiples of 8 (all three decimated sizes even),
 // at least 17 rows (the mirrored lead-in) and 8-byte aligned rows.
 bool pu_supported(const void* frames, int W, int H, int skip) {
   return skip == 4 && W % 8 == 0 && H % 8 == 0 && H >= 24 && W >= 16 && ((uintptr_t)frames % 8) == 0;
 }
 
-struct PuPlan {
-  PuParams p;
-  int warps, smem;
+struct PfPlan {
+  PfParams p;
+  int warps, smem, stages, maxw;
 };
-// geometry and shared-memory layout of a launch; false if the fused layout does not fit the SM
-static bool pu_plan(rm_handle* h, int mode, int W, int H, PuPlan& pl) {
-  PuParams& p = pl.p;
+// Strip geometry, shared-memory layout and kernel configuration of a fused launch; false if it does not fit.
+static bool pf_plan(rm_handle* h, int W, int H, PfPlan& pl) {
+  PfParams& p = pl.p;
   memset(&p, 0, sizeof(p));
-  p.frame_elems = (long long)W * H;
-  p.W = W; p.H = H; p.W3 = W / 8; p.H3 = H / 8;
-  const int cap = 32 - 2 * PU_HALO_LANES;                       // payload lanes of an interior strip
-  p.n_strips = (p.W3 + cap - 1) / cap;
-  p.cols_per_strip = (p.W3 + p.n_strips - 1) / p.n_strips;
-  if (p.n_strips > 16) return false;
   const int L = h->p.pyramid_levels, s = h->p.skip_levels_at_top;
+  if (W % 16 || L > RM_MAX_LEVELS || s != 4 || L - 1 <= s) return false;
   LevelGeom g = make_geom(W, H, L);
   RecordGeom rec = make_record(g, s);
+  p.W = W; p.H = H; p.W3 = W / 8; p.H3 = H / 8;
   p.first = s; p.top = L - 1; p.record_len = rec.len;
   p.g_scale = 1.0 / 255;
   for (int l = 0; l < s; ++l) p.g_scale *= 1.0 / 256.0;
-  for (int l = 0; l < L; ++l) { p.w[l] = g.w[l]; p.h[l] = g.h[l]; p.rec_off[l] = rec.off[l]; }
-  const int ring_slot = p.n_strips * PU_STAGES * PU_STAGE_BYTES;
-  int extra = 0, ring_used = 0;
-  if (mode != 0) {
-    for (int l = s; l < L; ++l) {                               // the levels live in the slot's idle ring where they fit
-      const int bytes = g.w[l] * g.h[l] * 8;
-      if (ring_used + bytes <= ring_slot) { p.lvl_off[l] = ring_used; ring_used += bytes; }
-      else { p.lvl_off[l] = -(extra + 1); extra += bytes; }
-    }
+  int lvl_bytes = 0;
+  for (int l = 0; l < L; ++l) {
+    p.w[l] = g.w[l]; p.h[l] = g.h[l]; p.rec_off[l] = rec.off[l];
+    p.magic[l] = g.w[l] > 1 ? (unsigned)((0x100000000ull + g.w[l] - 1) / g.w[l]) : 0u;
+    if (l >= s) { p.lvl_off[l] = lvl_bytes; lvl_bytes += g.w[l] * g.h[l] * 8; }
+    if (l >= s && (long long)g.w[l] * g.h[l] >= 65536) return false;      // pf_div
   }
-  const int l3_bytes = mode != 0 ? ((p.W3 * p.H3 * 4 + 15) & ~15) : 0;
-  extra = (extra + 15) & ~15;
-  int fpc = PU_MAX_WARPS / p.n_strips;
-  if (fpc < 1) return false;
-  if (mode != 0) {
-    const int per_slot = ring_slot + l3_bytes + extra + (mode == 2 ? p.n_strips * PU_STAGES * 8 : 0);
-    const int fit = (h->smem_optin - 128) / per_slot;
-    if (fit < 1) return false;
+  lvl_bytes = (lvl_bytes + 15) & ~15;
+  // strips in level-4 columns
+  const int K = g.w[s];
+  int n = 0, k0 = 0;
+  while (k0 < K) {
+    if (n == 16) return false;
+    const int base = n == 0 ? 0 : 2 * k0 - 4;
+    int k1;
+    if (base + 31 >= p.W3 - 1) k1 = K;                          // the window reaches the right border: the rest
+    else k1 = (base + 28) / 2 + 1;                              // centre lane <= 28
+    if (k1 > K) k1 = K;
+    p.strip_base[n] = base; p.strip_k0[n] = k0; p.strip_k1[n] = k1;
+    k0 = k1; ++n;
+  }
+  p.n_strips = n;
+  // ring depth / warps per CTA: as many frame slots as shared memory, the register file and 15 named barriers allow
+  const int cfg[3][2] = {{4, 18}, {3, 21}, {2, 24}};            // (stages, max warps) in order of preference
+  int pick = h->pyramid_cfg >= 0 && h->pyramid_cfg < 3 ? h->pyramid_cfg : 0;
+  for (int tries = 0; tries < 3; ++tries, pick = (pick + 1) % 3) {
+    const int S = cfg[pick][0], maxw = cfg[pick][1];
+    const int per_slot = n * S * PU_STAGE_BYTES + lvl_bytes + n * S * 8;
+    int fpc = maxw / n;
+    const int fit = (h->smem_optin - 256) / per_slot;
     if (fpc > fit) fpc = fit;
-    if (fpc > 15) fpc = 15;                                     // named barriers 1..15
+    if (fpc > 15) fpc = 15;
+    if (fpc < 1) continue;
+    p.frames_per_cta = fpc;
+    pl.warps = fpc * n; pl.stages = S; pl.maxw = maxw;
+    p.lvl_base = pl.warps * S * PU_STAGE_BYTES; p.lvl_stride = lvl_bytes;
+    p.mbar_base = p.lvl_base + fpc * lvl_bytes;
+    pl.smem = p.mbar_base + pl.warps * S * 8;
+    return true;
   }
-  p.frames_per_cta = fpc;
-  pl.warps = fpc * p.n_strips;
-  p.ring_bytes = pl.warps * PU_STAGES * PU_STAGE_BYTES;
-  p.l3_base = p.ring_bytes; p.l3_stride = l3_bytes;
-  p.extra_base = p.l3_base + fpc * l3_bytes; p.extra_stride = extra;
-  p.mbar_base = p.extra_base + fpc * extra;
-  pl.smem = p.mbar_base + (mode == 2 ? pl.warps * PU_STAGES * 8 : 0);
-  return pl.smem <= h->smem_optin;
+  return false;
 }
 
 typedef CUresult (*pu_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -483,65 +554,79 @@ static pu_encode_fn pu_encoder() {
   return fn;
 }
 
-// The best mode this build supports for these frames: 2 (TMA) needs 16-byte aligned rows and frames, 1 needs the fused
-// layout to fit, 0 otherwise.  Option "pyramid_mode" (0/1/2) caps it (A/B timing, tests of every path).
-int pu_best_mode(rm_handle* h, const void* frames, int W, int H, int n_levels, int skip) {
-  (void)n_levels; (void)skip;
-  PuPlan pl;
-  int mode = h->pyramid_mode;
-  if (mode == 2 && !(W % 16 == 0 && ((uintptr_t)frames % 16) == 0 && pu_encoder() && pu_plan(h, 2, W, H, pl))) mode = 1;
-  if (mode == 1 && !pu_plan(h, 1, W, H, pl)) mode = 0;
-  return mode;
+// 1: the fused TMA kernel can take these frames (rows and frames 16-byte multiples, the level images fit a slot);
+// 0: fallback (level 3 through HBM + pyramid_tail_kernel).  Option "pyramid_mode" = 0 forces the fallback.
+int pu_best_mode(rm_handle* h, const void* frames, int W, int H) {
+  PfPlan pl;
+  if (h->pyramid_mode == 0 || ((uintptr_t)frames % 16) || !pu_encoder() || !pf_plan(h, W, H, pl)) return 0;
+  return 1;
 }
 
-template <int MODE>
-static int32_t pu_launch_mode(rm_handle* h, const PuPlan& pl, const CUtensorMap& map, long long ctas, cudaStream_t st) {
-  const int W = pl.p.W;
-  void (*kern)(const PuParams, const CUtensorMap) =
-      W == 640 ? pyramid_front_u8_kernel<640, MODE>
-      : W == 1280 ? pyramid_front_u8_kernel<1280, MODE>
-      : W == 1920 ? pyramid_front_u8_kernel<1920, MODE>
-      : W == 320 ? pyramid_front_u8_kernel<320, MODE> : pyramid_front_u8_kernel<0, MODE>;
-  RM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
-  RM_PROF(h, st, MODE == 0 ? "pyramid_front_u8_kernel" : (MODE == 1 ? "pyramid_u8_fused_kernel" : "pyramid_u8_fused_tma_kernel"));
-  kern<<<(unsigned)ctas, pl.warps * 32, pl.smem, st>>>(pl.p, map);
+template <int S, int MAXW>
+static int32_t pf_launch_cfg(rm_handle* h, const PfPlan& pl, const CUtensorMap& map, long long ctas, cudaStream_t st) {
+  RM_CUDA(h, cudaFuncSetAttribute(pyramid_u8_fused_kernel<S, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+  RM_PROF(h, st, "pyramid_u8_fused_kernel");
+  pyramid_u8_fused_kernel<S, MAXW><<<(unsigned)ctas, pl.warps * 32, pl.smem, st>>>(pl.p, map);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
 }
 
-int32_t pu_launch(rm_handle* h, int mode, const uint8_t* frames, uint32_t* g3, double* lap_out, long long n_frames,
-                  long long seg_len, long long seg_stride, long long seg_first, int W, int H, cudaStream_t st) {
-  PuPlan pl;
-  if (!pu_plan(h, mode, W, H, pl))
-    return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: frame too wide / level images too large for mode %lld", __func__, mode);
-  PuParams& p = pl.p;
-  p.frames = frames; p.g3 = g3; p.lap_out = lap_out; p.n_frames = n_frames;
+int32_t pu_launch_fused(rm_handle* h, const uint8_t* frames, double* lap_out, long long n_frames, long long seg_len,
+                        long long seg_stride, long long seg_first, int W, int H, cudaStream_t st) {
+  PfPlan pl;
+  if (!pf_plan(h, W, H, pl)) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: frames do not fit the fused pyramid kernel", __func__);
+  PfParams& p = pl.p;
+  p.lap_out = lap_out; p.n_frames = n_frames;
   p.seg_len = seg_len; p.seg_stride = seg_stride; p.seg_first = seg_first;
-#ifdef PU_IDX32
+  // every source frame the launch can touch, as one (W, H, frames) uint8 tensor; box = 256 columns x PU_ROWS rows
+  const long long last = n_frames - 1;
+  const long long n_src = (last / seg_len) * seg_stride + seg_first + last % seg_len + 1;
+  if (n_frames >= (1ll << 31) || seg_len >= (1ll << 31) || seg_len < 1 || n_src >= (1ll << 31))
+    return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: more than 2^31 frames", __func__);
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_src};
+  const cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
+  const cuuint32_t box[3] = {256, PU_ROWS, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  pu_encode_fn enc = pu_encoder();
+  if (!enc) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled not available", __func__);
+  const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return rm_fail(h, RM_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%lld)", __func__, (long long)r);
+  long long ctas = (n_frames + p.frames_per_cta - 1) / p.frames_per_cta;
+  if (ctas > h->sm_count) ctas = h->sm_count;
+  if (pl.stages == 4) return pf_launch_cfg<4, 18>(h, pl, map, ctas, st);
+  if (pl.stages == 3) return pf_launch_cfg<3, 21>(h, pl, map, ctas, st);
+  return pf_launch_cfg<2, 24>(h, pl, map, ctas, st);
+}
+
+int32_t pu_launch_front(rm_handle* h, const uint8_t* frames, uint32_t* g3, long long n_frames, long long seg_len,
+                        long long seg_stride, long long seg_first, int W, int H, cudaStream_t st) {
+  PuParams p;
+  memset(&p, 0, sizeof(p));
+  p.frames = frames; p.g3 = g3; p.n_frames = n_frames; p.frame_elems = (long long)W * H;
+  p.seg_len = seg_len; p.seg_stride = seg_stride; p.seg_first = seg_first;
+  p.W = W; p.H = H; p.W3 = W / 8; p.H3 = H / 8;
+  const int cap = 32 - 2 * PU_HALO_LANES;                       // payload lanes of an interior strip
+  p.n_strips = (p.W3 + cap - 1) / cap;
+  p.cols_per_strip = (p.W3 + p.n_strips - 1) / p.n_strips;
+  if (p.n_strips > 16) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: frame wider than 3584 pixels", __func__);
   if (n_frames >= (1ll << 31) || seg_len >= (1ll << 31) || seg_len < 1)
     return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: more than 2^31 frames", __func__);
-#endif
-  CUtensorMap map;
-  memset(&map, 0, sizeof(map));
-  if (mode == 2) {
-    // every source frame the launch can touch, as one (W, H, frames) uint8 tensor; box = 256 columns x PU_ROWS rows
-    const long long last = n_frames - 1;
-    const long long n_src = (last / seg_len) * seg_stride + seg_first + last % seg_len + 1;
-    if (n_src >= (1ll << 31)) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: more than 2^31 source frames", __func__);
-    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_src};
-    const cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
-    const cuuint32_t box[3] = {256, PU_ROWS, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    pu_encode_fn enc = pu_encoder();
-    if (!enc) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled not available", __func__);
-    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return rm_fail(h, RM_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%lld)", __func__, (long long)r);
-  }
+  p.frames_per_cta = PU_FRONT_WARPS / p.n_strips;
+  if (p.frames_per_cta > 15) p.frames_per_cta = 15;             // named barriers 1..15
+  const int warps = p.frames_per_cta * p.n_strips;
+  const int smem = warps * PU_FRONT_STAGES * PU_STAGE_BYTES;
+  void (*kern)(const PuParams) = W == 640 ? pyramid_front_u8_kernel<640>
+                                 : W == 1280 ? pyramid_front_u8_kernel<1280>
+                                 : W == 1920 ? pyramid_front_u8_kernel<1920>
+                                 : W == 320 ? pyramid_front_u8_kernel<320> : pyramid_front_u8_kernel<0>;
+  RM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   long long ctas = (n_frames + p.frames_per_cta - 1) / p.frames_per_cta;
-  if (ctas > (long long)h->sm_count * PU_CTAS_PER_SM) ctas = (long long)h->sm_count * PU_CTAS_PER_SM;
-  if (mode == 0) return pu_launch_mode<0>(h, pl, map, ctas, st);
-  if (mode == 1) return pu_launch_mode<1>(h, pl, map, ctas, st);
-  return pu_launch_mode<2>(h, pl, map, ctas, st);
+  if (ctas > h->sm_count) ctas = h->sm_count;
+  RM_PROF(h, st, "pyramid_front_u8_kernel");
+  kern<<<(unsigned)ctas, warps * 32, smem, st>>>(p);
+  RM_LAUNCH_CHECK(h);
+  return RM_OK;
 }

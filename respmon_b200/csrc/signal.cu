@@ -50,9 +50,6 @@ struct SignalScratch {
   unsigned* queue;         // fit work items: window * SIG_MAX_CAND + k
   unsigned* queue_n;
   unsigned* cursor;        // next queue item to fit
-  unsigned* long_queue;    // fits that exceeded the evaluation budget of the first pass (same item encoding)
-  unsigned* long_n;
-  unsigned* long_cursor;
 };
 
 __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalParams p, const SignalScratch s) {
@@ -106,28 +103,18 @@ __global__ void __launch_bounds__(64) signal_filter_peaks_kernel(const SignalPar
 #ifndef SIG_FIT_MINB
 #define SIG_FIT_MINB 1
 #endif
-#ifndef SIG_LONG_G
-#define SIG_LONG_G 8          // lanes per fit in the solo long pass (option "fit_bail_nfev")
-#endif
-// bail_nfev > 0 (first pass of the deferred pipeline): a fit that has not converged after that many evaluations is
-// pushed to the long queue instead of being finished; long_pass = 1 drains that queue without a limit.  A handful of
-// fits per batch run ten times longer than the rest (MINPACK gives up on them after 800 evaluations): taking them out
-// of the first pass bounds the latency of everything that waits for the bulk.
-// SOLO (long pass only, option "fit_bail_nfev"): one fit per warp.  Groups that share a warp diverge from each other, so a
-// warp's groups take turns; a fit that runs alone in its warp iterates at its own latency.
-template <int G, bool SOLO = false>
+template <int G>
 __global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_kernel(const SignalParams p, const SignalScratch s,
-                                                                      int m_cap, int bail_nfev, int long_pass) {
+                                                                                    int m_cap) {
   extern __shared__ __align__(16) double fit_smem[];
   const int lane = threadIdx.x & 31;
-  if (SOLO && lane >= G) return;
   LmGroup g;
   g.sub = lane & (G - 1);
   g.mask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << (lane & ~(G - 1));
-  const int group_in_block = SOLO ? (int)(threadIdx.x >> 5) : (int)(threadIdx.x / G);
-  const unsigned total = long_pass ? *s.long_n : *s.queue_n;
-  const unsigned* queue = long_pass ? s.long_queue : s.queue;
-  unsigned* cursor = long_pass ? s.long_cursor : s.cursor;
+  const int group_in_block = (int)(threadIdx.x / G);
+  const unsigned total = *s.queue_n;
+  const unsigned* queue = s.queue;
+  unsigned* cursor = s.cursor;
   double* xs = fit_smem + (size_t)group_in_block * 7 * m_cap;
   double* ys = xs + m_cap;
   double* fvec = ys + m_cap;
@@ -161,75 +148,8 @@ __global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_kern
     mx = lmg_max<G>(g, mx);
     __syncwarp(g.mask);
     double par[SC_NP] = {mx, xs[0], (xs[1] - xs[0]) * 5.0};   // peakutils.gaussian_fit initial guess
-    const int info = lmg_lmdif_gauss<G>(g, m, xs, ys, par, fvec, wa4, fjac, long_pass ? 0 : bail_nfev);
-    if (g.sub == 0) {
-      if (info == -1) s.long_queue[atomicAdd(s.long_n, 1u)] = q;
-      else s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334, 336
-    }
-  }
-}
-
-// Warp-synchronous first pass (option "fit_sync", experimental): the groups of a warp take their next fits together and
-// run them through lmg_lmdif_gauss_sync, whose loops are warp-uniform -- one converged instruction stream per warp
-// instead of one per group.  A warp stays in a round until its slowest fit is done (or bails: bail_nfev).
-template <int G>
-__global__ void __launch_bounds__(SIG_FIT_THREADS, SIG_FIT_MINB) signal_fit_sync_kernel(const SignalParams p,
-                                                                                      const SignalScratch s, int m_cap,
-                                                                                      int bail_nfev) {
-  extern __shared__ __align__(16) double fit_smem[];
-  const int lane = threadIdx.x & 31;
-  LmGroup g;
-  g.sub = lane & (G - 1);
-  g.mask = (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << (lane & ~(G - 1));
-  const int group_in_block = threadIdx.x / G;
-  const unsigned total = *s.queue_n;
-  double* xs = fit_smem + (size_t)group_in_block * 7 * m_cap;
-  double* ys = xs + m_cap;
-  double* fvec = ys + m_cap;
-  double* wa4 = fvec + m_cap;
-  double* fjac = wa4 + m_cap;
-  for (;;) {
-    unsigned item = 0;
-    if (g.sub == 0) item = atomicAdd(s.cursor, 1u);
-    item = __shfl_sync(g.mask, item, lane & ~(G - 1));
-    const bool has = item < total;
-    if (!__any_sync(0xffffffffu, has)) return;          // the whole warp leaves together
-    unsigned q = 0;
-    long long win = 0;
-    int k = 0, m = 0;
-    double par[SC_NP] = {0.0, 0.0, 1.0};
-    if (has) {
-      q = s.queue[item];
-      win = q / SIG_MAX_CAND;
-      k = q % SIG_MAX_CAND;
-      const int f = (int)(win % p.win_frames) + p.win_f0;
-      const int n = f + 1 < p.buf_len ? f + 1 : p.buf_len;
-      const int idx = s.cand[win * SIG_MAX_CAND + k];
-      int w = p.width;                                   // base.py:319-323
-      if (idx - p.width < 0) w = idx;
-      if (idx + w > n) w = n - idx;
-      m = 2 * w;
-      if (m > m_cap) m = m_cap;
-      const double* t = p.tvals + (f + 1 - n) + (idx - w);
-      const double* y = s.filt + win * p.buf_len + (idx - w);
-      double mx = -INFINITY;
-      for (int i = g.sub; i < m; i += G) {               // the previous round ended with the whole warp converged
-        xs[i] = t[i];
-        ys[i] = y[i];
-        mx = fmax(mx, y[i]);
-      }
-      mx = lmg_max<G>(g, mx);
-      __syncwarp(g.mask);
-      par[0] = mx;                                       // peakutils.gaussian_fit initial guess
-      par[1] = xs[0];
-      par[2] = (xs[1] - xs[0]) * 5.0;
-    }
-    const int info = lmg_lmdif_gauss_sync<G>(g, has ? m : 0, xs, ys, par, fvec, wa4, fjac, bail_nfev);
-    __syncwarp();                                        // every group is done with its slices before the next round
-    if (has && g.sub == 0) {
-      if (info == -1) s.long_queue[atomicAdd(s.long_n, 1u)] = q;
-      else s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334, 336
-    }
+    const int info = lmg_lmdif_gauss<G>(g, m, xs, ys, par, fvec, wa4, fjac);
+    if (g.sub == 0) s.acc[win * SIG_MAX_CAND + k] = (info >= 1 && info <= 4 && par[2] < p.cutoff) ? 1 : 0;   // base.py:334, 336
   }
 }
 
@@ -333,7 +253,7 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
   p.tvals = h->d_tvals;
   // scratch owned by the handle, grown on demand
   const size_t n_win = (size_t)n_clips * win_frames;
-  const size_t need = n_win * p.buf_len * 8 + n_win * SIG_MAX_CAND * 2 + n_win * 4 + 2 * n_win * SIG_MAX_CAND * 4 + 1024;
+  const size_t need = n_win * p.buf_len * 8 + n_win * SIG_MAX_CAND * 2 + n_win * 4 + n_win * SIG_MAX_CAND * 4 + 1024;
   if (h->sig_scratch_bytes < need) {
     if (h->d_sig_scratch) cudaFree(h->d_sig_scratch);
     h->d_sig_scratch = nullptr;
@@ -345,14 +265,11 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
   unsigned char* base = reinterpret_cast<unsigned char*>(h->d_sig_scratch);
   sc.filt = reinterpret_cast<double*>(base);                base += n_win * p.buf_len * 8;
   sc.queue = reinterpret_cast<unsigned*>(base);             base += n_win * SIG_MAX_CAND * 4;
-  sc.long_queue = reinterpret_cast<unsigned*>(base);        base += n_win * SIG_MAX_CAND * 4;
   sc.ncand = reinterpret_cast<int*>(base);                  base += n_win * 4;
   sc.queue_n = reinterpret_cast<unsigned*>(base);           base += 256;   // 4 counters per chunk (RM_MAX_CHUNKS <= 16)
   sc.cand = base;                                           base += n_win * SIG_MAX_CAND;
   sc.acc = base;
   sc.cursor = sc.queue_n + 1;
-  sc.long_n = sc.queue_n + 2;
-  sc.long_cursor = sc.queue_n + 3;
   // every window holds at most (buf_len / width + 1) candidates that survive min_dist = width
   job->m_cap = 2 * p.width < SC_MAX_FIT ? 2 * p.width : SC_MAX_FIT;
   if (job->m_cap < 4) job->m_cap = 4;
@@ -363,13 +280,9 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
   int per_sm = 0;
   RM_CUDA(h, cudaFuncSetAttribute(signal_fit_kernel<SIG_FIT_G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)job->fit_smem));
-  if (h->fit_sync)      // the experimental first pass uses the same slices
-    RM_CUDA(h, cudaFuncSetAttribute(signal_fit_sync_kernel<SIG_FIT_G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)job->fit_smem));
   RM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, signal_fit_kernel<SIG_FIT_G>, SIG_FIT_THREADS,
                                                            job->fit_smem));
   job->grid_cap = h->sm_count * (per_sm > 0 ? per_sm : 1);   // persistent grid: what can be resident
-  if (h->fit_blocks_per_sm > 0 && h->fit_blocks_per_sm < per_sm) job->grid_cap = h->sm_count * h->fit_blocks_per_sm;
   RM_CUDA(h, cudaMemsetAsync(sc.queue_n, 0, 256, st));
   RM_PROF(h, st, "tvals_kernel");
   tvals_kernel<<<1, 32, 0, st>>>(p.tvals, n_frames, p.dt);
@@ -378,17 +291,8 @@ int32_t rmi_signal_setup(rm_handle* h, const double* data, int32_t n_clips, int3
 }
 
 // measure() for the windows ending at frames [f0, f1) (chunk index `chunk` selects the fit queue) on stream st.
-#ifdef LM_TIMING
-extern "C" int32_t rm_debug_lm_timing(unsigned long long* host_out8, int32_t reset) {
-  if (host_out8) cudaMemcpyFromSymbol(host_out8, lm_timing, sizeof(unsigned long long) * 8);
-  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(lm_timing, z, sizeof(z)); }
-  return 0;
-}
-#endif
-#define SIG_BAIL_NFEV 200     // evaluations a fit may spend in the first pass (99.97 % of fits need fewer)
-#define SIG_LONG_BLOCKS 16
 int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t st, cudaStream_t st_fit,
-                         cudaEvent_t ev_filtered, cudaEvent_t ev_bulk) {
+                         cudaEvent_t ev_filtered) {
   SignalJob* job = reinterpret_cast<SignalJob*>(h->sig_job);
   if (!job || chunk < 0 || chunk >= RM_MAX_CHUNKS) return rm_fail(h, RM_ERR_INVALID, "%s: no signal job", __func__);
   if (job->p.n_clips == 0 || f1 <= f0) return RM_OK;
@@ -396,11 +300,8 @@ int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t s
   SignalScratch sc = job->sc;
   p.f0 = f0; p.f1 = f1;
   sc.queue = job->sc.queue + (size_t)p.n_clips * (f0 - p.win_f0) * SIG_MAX_CAND;   // a slice no other chunk's windows reach
-  sc.long_queue = job->sc.long_queue + (size_t)p.n_clips * (f0 - p.win_f0) * SIG_MAX_CAND;
   sc.queue_n = job->sc.queue_n + 4 * chunk;
   sc.cursor = sc.queue_n + 1;
-  sc.long_n = sc.queue_n + 2;
-  sc.long_cursor = sc.queue_n + 3;
   dim3 grid(div_up(f1 - f0, 64), p.n_clips);
   RM_PROF(h, st, "signal_filter_peaks_kernel");
   signal_filter_peaks_kernel<<<grid, 64, 0, st>>>(p, sc);
@@ -412,36 +313,9 @@ int32_t rmi_signal_range(rm_handle* h, int f0, int f1, int chunk, cudaStream_t s
   const int groups = SIG_FIT_THREADS / SIG_FIT_G;
   long long grid_fit = div_up((long long)(job->max_items_per_frame * (size_t)(f1 - f0)), groups);
   if (grid_fit > job->grid_cap) grid_fit = job->grid_cap;
-  // deferred pipeline: the first pass hands fits that are still running after SIG_BAIL_NFEV evaluations to a second,
-  // narrow pass (64-thread blocks: they fit beside the next batch's calibration kernels on an SM); ev_bulk marks the
-  // end of the first pass, which is all the caller's stream has to wait for
-  // option "fit_bail_nfev" = N > 0 (any mode): the first pass gives up on a fit after N evaluations and the second pass
-  // runs those fits again, one per warp (SOLO), so that the few 800-evaluation fits do not take turns with other groups
-  const int bail = h->fit_bail_nfev > 0 ? h->fit_bail_nfev : ((ev_bulk && h->defer_join) ? SIG_BAIL_NFEV : 0);
-  if (h->fit_sync) {
-    RM_PROF(h, st_fit, "signal_fit_sync_kernel");
-    signal_fit_sync_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, job->fit_smem, st_fit>>>(p, sc, job->m_cap, bail);
-  } else {
-    RM_PROF(h, st_fit, "signal_fit_kernel");
-    signal_fit_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, job->fit_smem, st_fit>>>(p, sc, job->m_cap, bail, 0);
-  }
+  RM_PROF(h, st_fit, "signal_fit_kernel");
+  signal_fit_kernel<SIG_FIT_G><<<(int)grid_fit, SIG_FIT_THREADS, job->fit_smem, st_fit>>>(p, sc, job->m_cap);
   RM_LAUNCH_CHECK(h);
-  if (ev_bulk) RM_CUDA(h, cudaEventRecord(ev_bulk, st_fit));
-  if (h->fit_bail_nfev > 0) {
-    const int long_threads = 64, long_warps = long_threads / 32;
-    RM_PROF(h, st_fit, "signal_fit_solo_kernel");
-    // one fit per warp: size the grid for many bailed fits (a small N sends a good part of the queue here); blocks
-    // that find the queue empty leave at once
-    signal_fit_kernel<SIG_LONG_G, true><<<h->sm_count * 4, long_threads, (size_t)long_warps * 7 * job->m_cap * sizeof(double),
-                                          st_fit>>>(p, sc, job->m_cap, 0, 1);
-    RM_LAUNCH_CHECK(h);
-  } else if (bail) {
-    const int long_threads = 64, long_groups = long_threads / SIG_FIT_G;
-    RM_PROF(h, st_fit, "signal_fit_long_kernel");
-    signal_fit_kernel<SIG_FIT_G><<<SIG_LONG_BLOCKS, long_threads, (size_t)long_groups * 7 * job->m_cap * sizeof(double),
-                                   st_fit>>>(p, sc, job->m_cap, 0, 1);
-    RM_LAUNCH_CHECK(h);
-  }
   RM_PROF(h, st_fit, "signal_bpm_kernel");
   signal_bpm_kernel<<<grid, 64, 0, st_fit>>>(p, sc);
   RM_LAUNCH_CHECK(h);
@@ -452,16 +326,11 @@ extern "C" int32_t rm_signal_bpm(rm_handle* h, const double* data, int32_t n_cli
                                  double* bpm_out, double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out,
                                  const int32_t* status, void* stream) {
   if (!h) return RM_ERR_INVALID;
-  int32_t rc;
-  {
-    DeviceGuard dg0(h->device);
-    if ((rc = rmi_join(h, (cudaStream_t)stream)) != RM_OK) return rc;
-  }
-  rc = rmi_signal_setup(h, data, n_clips, n_frames, fps, bpm_out, filtered_out, peaks_out, npeaks_out, status, 1,
+  int32_t rc = rmi_signal_setup(h, data, n_clips, n_frames, fps, bpm_out, filtered_out, peaks_out, npeaks_out, status, 1,
                         (cudaStream_t)stream, 0, 0);
   if (rc != RM_OK || n_clips == 0) return rc;
   DeviceGuard dg(h->device);
-  return rmi_signal_range(h, 0, n_frames, 0, (cudaStream_t)stream, (cudaStream_t)stream, nullptr, nullptr);
+  return rmi_signal_range(h, 0, n_frames, 0, (cudaStream_t)stream, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_t* roi, const int32_t* status,
@@ -470,22 +339,9 @@ extern "C" int32_t rm_pack_results(rm_handle* h, const double* bpm, const int32_
   if (n_clips == 0) return RM_OK;
   DeviceGuard dg(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (h->defer_join && h->pending_chunks > 0) {
-    // the signal stage of a deferred rm_measure_signal is still running: pack behind it on the tail stream and let the
-    // caller's stream go on; `out` is complete once rm_join (or the next call that joins) has been waited for
-    RM_CUDA(h, cudaEventRecord(h->ev_tail_fork, st));
-    RM_CUDA(h, cudaStreamWaitEvent(h->tail_stream, h->ev_tail_fork, 0));
-    for (int c = 0; c < h->pending_chunks; ++c) RM_CUDA(h, cudaStreamWaitEvent(h->tail_stream, h->ev_done[c], 0));
-    st = h->tail_stream;
-  }
   RM_PROF(h, st, "pack_results_kernel");
   pack_results_kernel<<<div_up(n_clips, 128), 128, 0, st>>>(bpm, roi, status, npeaks, n_clips, n_frames, n_frames, out);
   RM_LAUNCH_CHECK(h);
-  if (st == h->tail_stream) {
-    RM_CUDA(h, cudaEventRecord(h->ev_packed, st));
-    h->pending_pack = 1;
-    h->pending_chunks = 0;     // ev_packed is behind every ev_done
-  }
   return RM_OK;
 }
 

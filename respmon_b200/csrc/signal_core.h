@@ -425,10 +425,9 @@ L3_INL void l3_put(double v[3], int i, double x) {
 // results are the same bits.
 L3_NOINL double l3_div(double a, double b) { return a / b; }
 L3_NOINL double l3_sqrt(double a) { return sqrt(a); }
-#ifdef LM_DIV3
-// Developer switch (experiment, off by default until it has been timed): three independent quotients in one
-// call -- the same three IEEE divisions, but their instruction chains interleave, so the call costs about one
-// division's latency instead of three (a fit is a latency chain of exactly these calls).  Same bits either way.
+// Three independent quotients in one call -- the same three IEEE divisions, but their instruction chains interleave,
+// so the call costs about one division's latency instead of three (a fit is a latency chain of exactly these calls;
+// fit kernels 9.31 -> 9.11 ms summed per 64-clip step, r02a).  Same bits either way.
 struct L3Triple { double a, b, c; };
 L3_NOINL L3Triple l3_div3(double a0, double b0, double a1, double b1, double a2, double b2) {
   L3Triple q;
@@ -437,7 +436,6 @@ L3_NOINL L3Triple l3_div3(double a0, double b0, double a1, double b1, double a2,
   q.c = a2 / b2;
   return q;
 }
-#endif
 
 // one term of MINPACK enorm's three-range accumulation
 L3_INL void l3_enorm_acc(double xabs, double agiant, double& s1, double& s2, double& s3, double& x1max, double& x3max) {
@@ -585,17 +583,12 @@ L3_INL void l3_lmpar(double r[9], const int ipvt[3], const double diag[3], const
   if (fp <= p1 * delta) { *par = 0.0; return; }
   double parl = 0.0;
   if (nsing >= 3) {
-#ifdef LM_DIV3
     {
       const L3Triple q = l3_div3(l3_get(wa2, ipvt[0]), dxnorm, l3_get(wa2, ipvt[1]), dxnorm, l3_get(wa2, ipvt[2]), dxnorm);
       wa1[0] = l3_get(diag, ipvt[0]) * q.a;
       wa1[1] = l3_get(diag, ipvt[1]) * q.b;
       wa1[2] = l3_get(diag, ipvt[2]) * q.c;
     }
-#else
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { const int l = ipvt[j]; wa1[j] = l3_get(diag, l) * l3_div(l3_get(wa2, l), dxnorm); }
-#endif
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       double sum = 0.0;
@@ -606,7 +599,6 @@ L3_INL void l3_lmpar(double r[9], const int ipvt[3], const double diag[3], const
     const double temp = l3_enorm3(wa1[0], wa1[1], wa1[2]);
     parl = l3_div(l3_div(l3_div(fp, delta), temp), temp);
   }
-#ifdef LM_DIV3
   {
     double sum[3];
 #pragma unroll
@@ -620,15 +612,6 @@ L3_INL void l3_lmpar(double r[9], const int ipvt[3], const double diag[3], const
     wa1[1] = q.b;
     wa1[2] = q.c;
   }
-#else
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    double sum = 0.0;
-#pragma unroll
-    for (int i = 0; i <= j; ++i) sum += r[i + j * 3] * qtb[i];
-    wa1[j] = l3_div(sum, l3_get(diag, ipvt[j]));
-  }
-#endif
   const double gnorm = l3_enorm3(wa1[0], wa1[1], wa1[2]);
   double paru = l3_div(gnorm, delta);
   if (paru == 0.0) paru = l3_div(dwarf, delta < p1 ? delta : p1);
@@ -649,17 +632,12 @@ L3_INL void l3_lmpar(double r[9], const int ipvt[3], const double diag[3], const
     temp = fp;
     fp = dxnorm - delta;
     if (fabs(fp) <= p1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
-#ifdef LM_DIV3
     {
       const L3Triple q = l3_div3(l3_get(wa2, ipvt[0]), dxnorm, l3_get(wa2, ipvt[1]), dxnorm, l3_get(wa2, ipvt[2]), dxnorm);
       wa1[0] = l3_get(diag, ipvt[0]) * q.a;
       wa1[1] = l3_get(diag, ipvt[1]) * q.b;
       wa1[2] = l3_get(diag, ipvt[2]) * q.c;
     }
-#else
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { const int l = ipvt[j]; wa1[j] = l3_get(diag, l) * l3_div(l3_get(wa2, l), dxnorm); }
-#endif
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       wa1[j] = l3_div(wa1[j], sdiag[j]);

@@ -48,21 +48,6 @@ class Engine:
         self._ws = {}
         self._ws_tag = ""       # workspace namespace (locate(parts > 1) runs parts side by side, each with its own scratch)
         self._side = []         # side streams of locate(parts > 1)
-        self._held = None       # tensors a deferred step may still be writing (see defer_join)
-
-    def defer_join(self, on: bool = True):
-        """Let run_batch return while the signal stage of the batch is still running on the handle's own streams
-        (rm_join in include/respmon_b200.h): the records are complete after join().  The engine keeps the step's
-        tensors alive until then."""
-        self.set_option("defer_join", 1 if on else 0)
-        self._defer = bool(on)
-        if not on:
-            self.join()
-
-    def join(self):
-        """Make the current stream wait for everything a deferred run_batch left running."""
-        self._call("rm_join", self._stream())
-        self._held = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -343,9 +328,6 @@ class Engine:
             m = dict(data=data)
             sig = self.signal_bpm(data, fps, status=status)
         rec = self.pack_results(sig["bpm"], roi, status, sig["npeaks"], out=out)
-        if getattr(self, "_defer", False):
-            # the previous step's tensors are safe to release now: this step's rm_measure_signal joined them on the stream
-            self._held = (roi, status, heat, m, sig, rec)
         if keep:
             return rec, dict(roi=roi, status=status, heat=heat, **m, **sig)
         return rec

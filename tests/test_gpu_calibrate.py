@@ -92,14 +92,14 @@ def test_integer_front_is_bit_identical_to_float64_front(eng, w, h):
 
 
 @pytest.mark.parametrize("w,h,n_clips,T", [(640, 480, 23, 5), (320, 240, 40, 4), (1280, 720, 7, 4), (1920, 1080, 3, 4),
-                                           (328, 200, 5, 4), (64, 24, 9, 4), (16, 24, 33, 4), (232, 136, 6, 4),
-                                           (2048, 64, 3, 4)])
-def test_pyramid_modes_are_bit_identical(eng, w, h, n_clips, T):
-    """The three forms of the uint8 pyramid stage -- level 3 through HBM + pyramid_tail_kernel (mode 0), tail fused into
-    the front kernel with cp.async rows (mode 1) and with TMA rows (mode 2, cp.async.bulk.tensor + mbarrier) -- write
-    the same packed Laplacian records bit for bit, over more frames than one wave of CTAs holds, for windows of clips
-    (first frame 1) and for sizes where a mode is not available (328: rows not 16-byte multiples -> no TMA) and falls
-    back.  The float64 front is the fourth witness."""
+                                           (328, 200, 5, 4), (64, 24, 9, 4), (16, 24, 33, 4), (240, 136, 6, 4),
+                                           (2048, 64, 3, 4), (464, 72, 5, 3), (32, 200, 7, 3)])
+def test_pyramid_kernels_are_bit_identical(eng, w, h, n_clips, T):
+    """The forms of the uint8 pyramid stage -- the fused TMA kernel (frame -> record in one pass: cp.async.bulk.tensor rows,
+    integer levels 0..4, the rest in shared memory) in its three ring / occupancy configurations, and the fallback (level
+    3 through HBM + pyramid_tail_kernel) -- write the same packed Laplacian records bit for bit, over more frames than
+    one wave of CTAs holds, for windows of clips (first frame 1), odd level sizes (H/8 = 17, 9, 25) and sizes the fused
+    kernel cannot take (328: rows are not 16-byte multiples) where it falls back.  The float64 front is the last witness."""
     rng = np.random.default_rng(w * 7 + h)
     clips = rng.integers(0, 256, (n_clips, T, h, w)).astype(np.uint8)
     clips[0, 1] = 255
@@ -107,19 +107,24 @@ def test_pyramid_modes_are_bit_identical(eng, w, h, n_clips, T):
     d = dev(clips)
     out = {}
     try:
-        for mode in (0, 1, 2):
-            eng.set_option("pyramid_mode", mode)
-            out[mode] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
+        eng.set_option("pyramid_mode", 0)
+        out["split"] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
+        eng.set_option("pyramid_mode", 1)
+        for cfg in (0, 1, 2):
+            eng.set_option("pyramid_cfg", cfg)
+            out["fused%d" % cfg] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
         eng.set_option("force_generic_front", 1)
         out["f64"] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
     finally:
-        eng.set_option("pyramid_mode", 2)
+        eng.set_option("pyramid_mode", 1)
+        eng.set_option("pyramid_cfg", 0)
         eng.set_option("force_generic_front", 0)
-    for k in (1, 2, "f64"):
-        assert np.array_equal(out[0], out[k]), "mode %s differs from mode 0 in %d values" % (k, int((out[0] != out[k]).sum()))
+    for k in out:
+        assert np.array_equal(out["split"], out[k]), "%s differs from the split path in %d values" % (
+            k, int((out["split"] != out[k]).sum()))
     lap = P.laplacian_levels(P.u8_to_unit(clips[-1, 2]), 9)
     for (l, lw, lh, off) in eng.record_levels(w, h):
-        assert np.abs(out[2][-1, 1, off:off + lw * lh].reshape(lh, lw) - lap[l]).max() <= 2e-14
+        assert np.abs(out["fused0"][-1, 1, off:off + lw * lh].reshape(lh, lw) - lap[l]).max() <= 2e-14
 
 
 def test_pyramid_build_golden_taps(eng, golden):

@@ -104,11 +104,14 @@ def test_pyr_down_u8_and_scharr(w, h):
     assert np.array_equal(dy, cv2.Scharr(img, cv2.CV_16S, 0, 1))
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(12))
 def test_lk_matches_cv2(seed):
+    """calcOpticalFlowPyrLK restated: status identical and the tracked points BIT-identical to cv2's, on smooth and on
+    sharp textures (large gradient sums round in float32: the accumulation order of cv_window_sum / cv_mismatch_sums is
+    what makes the difference between 'close' and 'equal')."""
     rng = np.random.default_rng(100 + seed)
-    h, w = [(30, 47), (64, 64), (40, 90), (120, 100), (33, 33), (200, 150), (31, 80), (70, 70)][seed]
-    base = cv2.GaussianBlur(rng.integers(0, 256, (h + 8, w + 8)).astype(np.uint8), (0, 0), 2.0)
+    h, w = [(30, 47), (64, 64), (40, 90), (120, 100), (33, 33), (200, 150), (31, 80), (70, 70)][seed % 8]
+    base = cv2.GaussianBlur(rng.integers(0, 256, (h + 8, w + 8)).astype(np.uint8), (0, 0), 2.0 if seed < 8 else 0.6)
     base = cv2.normalize(base, None, 0, 255, cv2.NORM_MINMAX)
     sx, sy = rng.uniform(-2, 2, 2)
     M = np.float32([[1, 0, 4 + sx], [0, 1, 4 + sy]])
@@ -119,8 +122,8 @@ def test_lk_matches_cv2(seed):
     out, status = K.lk_track(prev, nxt, pts)
     assert np.array_equal(status, st.ravel())
     ok = status == 1
-    assert np.abs(out[ok] - p1.reshape(-1, 2)[ok]).max() < 2e-3
-    assert np.sqrt(np.mean((out[ok] - p1.reshape(-1, 2)[ok]) ** 2)) < 2e-4
+    assert ok.sum() >= 5
+    assert np.array_equal(out[ok], p1.reshape(-1, 2)[ok]), np.abs(out[ok] - p1.reshape(-1, 2)[ok]).max()
 
 
 def test_lk_on_golden_chain(golden):
@@ -137,7 +140,7 @@ def test_lk_on_golden_chain(golden):
         pts = fix["lk_prev"][off:off + n[i]]
         out, status = K.lk_track(prev, cur, pts)
         assert np.array_equal(status, fix["lk_status"][off:off + n[i]])
-        assert np.abs(out - fix["lk_next"][off:off + n[i]])[status == 1].max() < 1e-3
+        assert np.array_equal(out[status == 1], fix["lk_next"][off:off + n[i]][status == 1])     # bit for bit
         off += n[i]
 
 

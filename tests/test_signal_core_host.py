@@ -174,52 +174,12 @@ def test_register_layout_lm_is_bit_identical_to_the_scalar_port(lib, golden):
     assert len(cases) > 1500 and n_long >= 1
 
 
-def test_div3_build_switch_changes_no_bits(lib, golden, tmp_path):
-    """-DLM_DIV3 (developer switch: three independent divisions of the trust-region code per call) must be a pure
-    scheduling change: same info, nfev and parameter bits as the default build on every fit window."""
-    import subprocess
-    here = os.path.dirname(os.path.abspath(__file__))
-    so = str(tmp_path / "_signal_host_div3.so")
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-DLM_DIV3", "-shared", "-fPIC", "-o", so,
-                           os.path.join(here, "hostsim", "signal_host.cpp")])
-    alt = C.CDLL(so)
-    cases = list(_fit_cases()) + list(_golden_fit_windows(golden))
-    rng = np.random.default_rng(5)
-    for m in (3, 4, 6):
-        for _ in range(40):
-            cases.append((1.6 + 0.1 * np.arange(m), rng.uniform(-0.2, 0.2, m)))
-    for xs, ys in cases:
-        out = []
-        for fn in (lib.host_gauss_fit_l3, alt.host_gauss_fit_l3):
-            p = np.array([ys.max(), xs[0], (xs[1] - xs[0]) * 5])
-            nfev = C.c_int()
-            info = fn(len(xs), dptr(xs), dptr(ys), dptr(p), C.byref(nfev))
-            out.append((info, nfev.value, p.tobytes()))
-        assert out[0] == out[1]
-    assert len(cases) > 500
-    # the same switch in the group-cooperative routine of the kernels (gnorm, the ratio test, fdjac's step size)
-    from hostsim import load_lm_group
-    grp = load_lm_group()
-    # ... and together with -DLM_ROWS2 (two rows of the model / Jacobian per trip)
-    alts = []
-    for tag, flags in (("div3", ["-DLM_DIV3"]), ("rows2", ["-DLM_ROWS2"]), ("both", ["-DLM_DIV3", "-DLM_ROWS2"])):
-        so2 = str(tmp_path / ("_lm_group_host_%s.so" % tag))
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", *flags, "-shared", "-fPIC", "-o", so2,
-                               os.path.join(here, "hostsim", "lm_group_host.cpp")])
-        alts.append(C.CDLL(so2))
-    for xs, ys in cases:
-        out = []
-        for fn in [grp.host_group_fit] + [a.host_group_fit for a in alts]:
-            p = np.array([ys.max(), xs[0], (xs[1] - xs[0]) * 5])
-            out.append((fn(len(xs), dptr(xs), dptr(ys), dptr(p), 0), p.tobytes()))
-        assert all(o == out[0] for o in out)
-
-
-def test_group_lm_forms_agree_on_the_host(lib, golden):
-    """lm_group.cuh compiled for the host with one lane per group: the warp-synchronous form (lmg_lmdif_gauss_sync: both
-    data-dependent loops warp-uniform, fits that have left a loop idle) must give the same info and the same parameter
-    bits as the free-running form the kernels use today, with and without an evaluation limit; and both must agree with
-    the scalar port wherever enorm's plain sum applies (they rescale only outside 1e-140..1e140, MINPACK below 3.8e-20)."""
+def test_group_lm_equals_the_scalar_port_on_the_host(lib, golden):
+    """lm_group.cuh (the group-cooperative fit the kernels run, with the interleaved three-division calls) compiled for the
+    host with one lane per group must give the same info and the same parameter bits as the scalar port of MINPACK
+    wherever enorm's plain sum applies (they rescale only outside 1e-140..1e140, MINPACK below 3.8e-20) -- on synthetic
+    windows, the degenerate tiny windows of the first frames and every fit window of the golden clips, incl. the ones
+    MINPACK gives up on after 800 evaluations."""
     from hostsim import load_lm_group
     grp = load_lm_group()
     cases = list(_fit_cases()) + list(_golden_fit_windows(golden))
@@ -227,24 +187,17 @@ def test_group_lm_forms_agree_on_the_host(lib, golden):
     for m in (3, 4, 5, 6, 8):
         for _ in range(40):
             cases.append((1.6 + 0.1 * np.arange(m), rng.uniform(-0.2, 0.2, m)))
-    cases.append((np.array([0.1, 0.2]), np.array([1.0, 2.0])))          # m < 3: both return 0 untouched
-    n_long = n_bailed = 0
+    n_long = 0
     for xs, ys in cases:
         p0 = np.array([ys.max(), xs[0], (xs[1] - xs[0]) * 5])
-        for bail in (0, 60):
-            out = []
-            for fn in (grp.host_group_fit, grp.host_group_fit_sync):
-                p = p0.copy()
-                info = fn(len(xs), dptr(xs), dptr(ys), dptr(p), bail)
-                out.append((info, p.tobytes()))
-            assert out[0] == out[1], (xs, ys, bail, out[0][0], out[1][0])
-            n_bailed += out[0][0] == -1
-        if len(xs) >= 3:
-            p = p0.copy()
-            nfev = C.c_int()
-            info = lib.host_gauss_fit(len(xs), dptr(xs), dptr(ys), dptr(p), C.byref(nfev))
-            pg = p0.copy()
-            info_g = grp.host_group_fit(len(xs), dptr(xs), dptr(ys), dptr(pg), 0)
-            assert info_g == info and pg.tobytes() == p.tobytes(), (xs, ys, info, info_g)
-            n_long += nfev.value >= 400
-    assert len(cases) > 700 and n_long >= 1 and n_bailed >= 1
+        p = p0.copy()
+        nfev = C.c_int()
+        info = lib.host_gauss_fit(len(xs), dptr(xs), dptr(ys), dptr(p), C.byref(nfev))
+        pg = p0.copy()
+        info_g = grp.host_group_fit(len(xs), dptr(xs), dptr(ys), dptr(pg))
+        assert info_g == info and pg.tobytes() == p.tobytes(), (xs, ys, info, info_g)
+        n_long += nfev.value >= 400
+    p = np.array([2.0, 0.1, 0.5])
+    assert grp.host_group_fit(2, dptr(np.array([0.1, 0.2])), dptr(np.array([1.0, 2.0])), dptr(p)) == 0   # m < 3: untouched
+    assert p.tolist() == [2.0, 0.1, 0.5]
+    assert len(cases) > 700 and n_long >= 1

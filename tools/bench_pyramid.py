@@ -1,6 +1,7 @@
 """Developer tool: the uint8 pyramid stage (frames in -> packed Laplacian records out) per mode at the bench shape.
     python tools/bench_pyramid.py [W H n_clips]
-mode 0 = level 3 through HBM + pyramid_tail_kernel, 1 = fused tail (cp.async rows), 2 = fused tail (TMA rows).
+"split" = level 3 through HBM + pyramid_tail_kernel (the fallback), "fused c" = the one-pass TMA kernel in ring /
+occupancy configuration c (0: 4 stages x 18 warps, 1: 3 x 21, 2: 2 x 24).
 Prints the stage time from CUDA events, the SURVEY 8(d) algorithmic bytes (W*H*1 + record*8 per frame) over it, and
 whether the records equal mode 0's bit for bit."""
 import json, os, sys
@@ -24,8 +25,9 @@ try:
 except Exception:
     pass
 base = None
-for mode in (0, 1, 2):
-    eng.set_option("pyramid_mode", mode)
+for mode in [int(m) for m in os.environ.get('RM_MODES', '-1,0,1,2').split(',')]:
+    eng.set_option("pyramid_mode", 0 if mode < 0 else 1)
+    eng.set_option("pyramid_cfg", max(mode, 0))
     out = eng.pyramid_build_clips(clips, first, length)
     for _ in range(3):
         eng.pyramid_build_clips(clips, first, length)
@@ -42,5 +44,5 @@ for mode in (0, 1, 2):
     nbytes = n_clips * length * (W * H + rec_len * 8)
     same = "-" if base is None else bool(torch.equal(out, base))
     base = out.clone() if base is None else base
-    print("%dx%d x%d clips, mode %d: stage %.3f ms (min %.3f)  %.0f GB/s = %.3f of %.1f   identical to mode 0: %s" % (
-        W, H, n_clips, mode, ms, min(ts), nbytes / ms / 1e6, nbytes / ms / 1e6 / peak, peak, same))
+    print("%dx%d x%d clips, %s: stage %.3f ms (min %.3f)  %.0f GB/s = %.3f of %.1f   identical to split: %s" % (
+        W, H, n_clips, "split" if mode < 0 else "fused %d" % mode, ms, min(ts), nbytes / ms / 1e6, nbytes / ms / 1e6 / peak, peak, same))

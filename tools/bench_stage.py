@@ -1,5 +1,5 @@
 """Developer tool: per-kernel device times of run_batch steps at the bench shapes (not the contract; see bench.py).
-    python tools/bench_stage.py [n_clips] [steps] [defer 0/1]"""
+    python tools/bench_stage.py [n_clips] [steps] [cal_parts]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -8,15 +8,14 @@ from respmon_b200.engine import Engine, results_to_numpy
 
 n_clips = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-defer = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-engs = [Engine(0), Engine(0)] if defer else [Engine(0)]
+parts = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+engs = [Engine(0)]
 for e in engs:
     if os.environ.get("RM_CHUNKS"):
         e.set_option("measure_chunks", int(os.environ["RM_CHUNKS"]))
-    if os.environ.get("RM_TAIL"):
-        e.set_option("measure_tail_frames", int(os.environ["RM_TAIL"]))
-    if defer:
-        e.defer_join(True)
+    for opt in ("pyramid_mode", "pyramid_cfg", "temporal_sparse"):
+        if os.environ.get("RM_" + opt.upper()):
+            e.set_option(opt, int(os.environ["RM_" + opt.upper()]))
 eng = engs[0]
 specs = [synth.clip_spec(i, 640, 480, 256) for i in range(n_clips)]
 dq8 = np.stack([synth.displacement_q8(s) for s in specs])
@@ -25,11 +24,7 @@ recs = [torch.empty((n_clips, 32), dtype=torch.uint8, device="cuda") for _ in en
 
 def run(n):
     for k in range(n):
-        engs[k % len(engs)].run_batch(clips, 10.0, out=recs[k % len(engs)])
-        if defer and k > 0:
-            engs[(k - 1) % 2].join()
-    if defer:
-        engs[(n - 1) % 2].join()
+        engs[k % len(engs)].run_batch(clips, 10.0, out=recs[k % len(engs)], cal_parts=parts)
     return recs[(n - 1) % len(engs)]
 
 run(3)
