@@ -329,6 +329,9 @@ __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1)
 // exactly representable integer and the float32 result IS the exact integer total: the callers test that first
 // (lk_sums_exact) and only walk the rows in order when a partial sum can actually round.
 __device__ __forceinline__ bool lk_sums_exact(unsigned lane_abs) {
+#ifdef LK_FORCE_EXACT   // timing experiment only: always the exact-total tier (results differ from OpenCV's)
+  return true;
+#endif
   return __reduce_add_sync(0xffffffffu, min(lane_abs, 1u << 24)) < (1u << 24);
 }
 struct LkAcc {     // one sum's accumulators
@@ -344,9 +347,44 @@ struct LkAcc {     // one sum's accumulators
   }
   __device__ __forceinline__ float total(bool any_simd) const { return any_simd ? sc + ((q0 + q2) + (q1 + q3)) : sc; }
 };
+// Second tier (the window total can round but no single accumulator can): the five accumulators of a sum -- q0..q3 and the
+// scalar one -- as exact integers, each below 2^24, combined in float32 the way OpenCV combines them.  On the bench clips the
+// total of Ix^2 + Iy^2 passes 2^24 in 44 % of the windows, an accumulator only in 10 % (oracle statistics).
+// Returns false when an accumulator can round: the caller then walks the rows in order (lk_cv_gradient_sums).
+__device__ __forceinline__ bool lk_gradient_sums_by_chain(const int Ixv[8], const int Iyv[8], int win, int lane, float& A11,
+                                                          float& A12, float& A22) {
+  const int nsimd = (win >> 3) << 3;
+  const bool simd_lane = (lane & 1) ? nsimd == 16 : nsimd >= 8;     // this lane's 8 columns are a SIMD group
+  unsigned q11[4] = {0, 0, 0, 0}, q22[4] = {0, 0, 0, 0}, s11 = 0, s22 = 0;
+  int q12[4] = {0, 0, 0, 0}, s12 = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int xx = Ixv[k] * Ixv[k], xy = Ixv[k] * Iyv[k], yy = Iyv[k] * Iyv[k];
+    q11[k & 3] += xx; q12[k & 3] += xy; q22[k & 3] += yy;
+    s11 += xx; s12 += xy; s22 += yy;
+  }
+  const unsigned cap = 1u << 24;
+  bool ok = true;
+  float f11[5], f12[5], f22[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const unsigned v11 = j < 4 ? (simd_lane ? q11[j & 3] : 0u) : (simd_lane ? 0u : s11);
+    const unsigned v22 = j < 4 ? (simd_lane ? q22[j & 3] : 0u) : (simd_lane ? 0u : s22);
+    const int v12 = j < 4 ? (simd_lane ? q12[j & 3] : 0) : (simd_lane ? 0 : s12);
+    const unsigned t11 = __reduce_add_sync(0xffffffffu, min(v11, cap)), t22 = __reduce_add_sync(0xffffffffu, min(v22, cap));
+    ok = ok && t11 < cap && t22 < cap;               // then |sum of Ix Iy| <= (t11 + t22) / 2 < 2^24 as well
+    f11[j] = (float)t11; f22[j] = (float)t22;
+    f12[j] = (float)__reduce_add_sync(0xffffffffu, ok ? v12 : 0);
+  }
+  if (!ok) return false;
+  A11 = nsimd ? f11[4] + ((f11[0] + f11[2]) + (f11[1] + f11[3])) : f11[4];
+  A12 = nsimd ? f12[4] + ((f12[0] + f12[2]) + (f12[1] + f12[3])) : f12[4];
+  A22 = nsimd ? f22[4] + ((f22[0] + f22[2]) + (f22[1] + f22[3])) : f22[4];
+  return true;
+}
 // sums of Ix*Ix, Ix*Iy, Iy*Iy (products < 2^24: exact in float32) in OpenCV's order; every lane gets the result
-__device__ __noinline__ void lk_cv_gradient_sums(const int Ixv[8], const int Iyv[8], int win, float& A11, float& A12,
-                                                 float& A22) {
+__device__ __noinline__ void lk_cv_gradient_sums_impl(const int* Ixv, const int* Iyv, int win, float* out) {
+  float A11, A12, A22;
   const int nsimd = (win >> 3) << 3;
   LkAcc a11, a12, a22;
   a11.clear(); a12.clear(); a22.clear();
@@ -364,10 +402,22 @@ __device__ __noinline__ void lk_cv_gradient_sums(const int Ixv[8], const int Iyv
     }
   }
   A11 = a11.total(nsimd > 0); A12 = a12.total(nsimd > 0); A22 = a22.total(nsimd > 0);
+  out[0] = A11; out[1] = A12; out[2] = A22;
+}
+// the rarely taken call works on copies in local memory: the callers' arrays stay in registers
+__device__ __forceinline__ void lk_cv_gradient_sums(const int Ixv[8], const int Iyv[8], int win, float& A11, float& A12,
+                                                    float& A22) {
+  int tx[8], ty[8];
+  float out[3];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { tx[k] = Ixv[k]; ty[k] = Iyv[k]; }
+  lk_cv_gradient_sums_impl(tx, ty, win, out);
+  A11 = out[0]; A12 = out[1]; A22 = out[2];
 }
 // sums of diff*Ix, diff*Iy in OpenCV's order: in a SIMD group the products of columns (j, j+4) are added as integers
 // (v_dotprod) before the conversion to float32; scalar columns convert every product.  dx[k] = diff_k * Ix_k etc.
-__device__ __noinline__ void lk_cv_mismatch_sums(const int dx[8], const int dy[8], int win, float& b1, float& b2) {
+__device__ __noinline__ void lk_cv_mismatch_sums_impl(const int* dx, const int* dy, int win, float* out) {
+  float b1, b2;
   const int nsimd = (win >> 3) << 3;
   LkAcc ax, ay;
   ax.clear(); ay.clear();
@@ -398,6 +448,15 @@ __device__ __noinline__ void lk_cv_mismatch_sums(const int dx[8], const int dy[8
     }
   }
   b1 = ax.total(nsimd > 0); b2 = ay.total(nsimd > 0);
+  out[0] = b1; out[1] = b2;
+}
+__device__ __forceinline__ void lk_cv_mismatch_sums(const int dx[8], const int dy[8], int win, float& b1, float& b2) {
+  int tx[8], ty[8];
+  float out[2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { tx[k] = dx[k]; ty[k] = dy[k]; }
+  lk_cv_mismatch_sums_impl(tx, ty, win, out);
+  b1 = out[0]; b2 = out[1];
 }
 
 // One warp tracks one point through all pyramid levels (cv::LKTrackerInvoker).  patch / deriv are per-warp shared
@@ -474,7 +533,7 @@ __device__ int lk_track_point(const MeasureParams& p, const Img* prev, const Img
     float A11, A12, A22;
     if (lk_sums_exact((unsigned)(sA11 + sA22))) {      // no partial sum can round: the exact totals are OpenCV's floats
       A11 = (float)warp_sum_ll(sA11); A12 = (float)warp_sum_ll(sA12); A22 = (float)warp_sum_ll(sA22);
-    } else {
+    } else if (!lk_gradient_sums_by_chain(Ixv, Iyv, win, lane, A11, A12, A22)) {
       lk_cv_gradient_sums(Ixv, Iyv, win, A11, A12, A22);
     }
     A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
@@ -751,7 +810,7 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
     float A11, A12, A22;
     if (lk_sums_exact((unsigned)(sA11 + sA22))) {      // no partial sum can round: the exact totals are OpenCV's floats
       A11 = (float)warp_sum_split(sA11); A12 = (float)warp_sum_split(sA12); A22 = (float)warp_sum_split(sA22);
-    } else {
+    } else if (!lk_gradient_sums_by_chain(Ixv, Iyv, win, lane, A11, A12, A22)) {
       lk_cv_gradient_sums(Ixv, Iyv, win, A11, A12, A22);
     }
     A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;

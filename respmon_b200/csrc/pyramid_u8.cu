@@ -87,34 +87,34 @@ struct PuState {
 
 // horizontal 5-tap at level 1 -> the lane's two level-2 columns.  P = level-1 columns (4L, 4L+1), Q = (4L+2, 4L+3).
 template <bool LEFT, bool RIGHT>
-__device__ __forceinline__ void pu_h1(unsigned P, unsigned Q, int lane, int last_lane, unsigned& g0, unsigned& g1) {
+__device__ __forceinline__ void pu_h1(unsigned P, unsigned Q, int lane, int first_lane, int last_lane, unsigned& g0, unsigned& g1) {
   unsigned Ql = __shfl_up_sync(0xffffffffu, Q, 1);
   unsigned Pr = __shfl_down_sync(0xffffffffu, P, 1);
-  if (LEFT && lane == 0) Ql = __byte_perm(P, Q, 0x3254);   // columns -2, -1 are columns 2, 1
+  if (LEFT && lane == first_lane) Ql = __byte_perm(P, Q, 0x3254);   // columns -2, -1 are columns 2, 1
   if (RIGHT && lane == last_lane) Pr = Q;                  // column W1 is column W1-2
   g0 = __dp2a_lo(Ql, 0x0401u, __dp2a_lo(P, 0x0406u, __dp2a_lo(Q, 0x0001u, 0u)));
   g1 = __dp2a_lo(P, 0x0401u, __dp2a_lo(Q, 0x0406u, __dp2a_lo(Pr, 0x0001u, 0u)));
 }
 // horizontal 5-tap at level 2 -> the lane's level-3 column.  q0, q1 = level-2 columns (2L, 2L+1).
 template <bool LEFT, bool RIGHT>
-__device__ __forceinline__ unsigned pu_h2(unsigned q0, unsigned q1, int lane, int last_lane) {
+__device__ __forceinline__ unsigned pu_h2(unsigned q0, unsigned q1, int lane, int first_lane, int last_lane) {
   unsigned ql0 = __shfl_up_sync(0xffffffffu, q0, 1);
   unsigned ql1 = __shfl_up_sync(0xffffffffu, q1, 1);
   unsigned qr0 = __shfl_down_sync(0xffffffffu, q0, 1);
-  if (LEFT && lane == 0) { ql0 = qr0; ql1 = q1; }
+  if (LEFT && lane == first_lane) { ql0 = qr0; ql1 = q1; }
   if (RIGHT && lane == last_lane) qr0 = q0;
   return v5(ql0, ql1, q0, q1, qr0);
 }
 
 template <bool LEFT, bool RIGHT>
-__device__ __forceinline__ void pu_block(PuState& s, const uint2 w[PU_ROWS], int lane, int last_lane, unsigned& out3) {
+__device__ __forceinline__ void pu_block(PuState& s, const uint2 w[PU_ROWS], int lane, int first_lane, int last_lane, unsigned& out3) {
   unsigned ha[PU_ROWS], hb[PU_ROWS];
 #pragma unroll
   for (int i = 0; i < PU_ROWS; ++i) {
     const unsigned w0 = w[i].x, w1 = w[i].y;
     unsigned wl = __shfl_up_sync(0xffffffffu, w1, 1);
     unsigned wr = __shfl_down_sync(0xffffffffu, w0, 1);
-    if (LEFT && lane == 0) wl = __byte_perm(w0, w1, 0x1234);          // pixels -2, -1 are pixels 2, 1
+    if (LEFT && lane == first_lane) wl = __byte_perm(w0, w1, 0x1234);          // pixels -2, -1 are pixels 2, 1
     if (RIGHT && lane == last_lane) wr = __byte_perm(w1, 0u, 0x0002); // pixel W is pixel W-2
     const unsigned k0 = __dp4a(wl, 0x04010000u, __dp4a(w0, 0x00010406u, 0u));
     const unsigned k1 = __dp4a(w0, 0x04060401u, __dp4a(w1, 0x00000001u, 0u));
@@ -137,7 +137,7 @@ __device__ __forceinline__ void pu_block(PuState& s, const uint2 w[PU_ROWS], int
   for (int i = 0; i < 4; ++i) { s.a[i] = ha[4 + i]; s.b[i] = hb[4 + i]; }
   unsigned n0[4], n1[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pu_h1<LEFT, RIGHT>(P[i], Q[i], lane, last_lane, n0[i], n1[i]);
+  for (int i = 0; i < 4; ++i) pu_h1<LEFT, RIGHT>(P[i], Q[i], lane, first_lane, last_lane, n0[i], n1[i]);
   // level-2 rows 2b-1, 2b
   unsigned q0[2], q1[2];
   q0[0] = v5(s.g0[0], s.g0[1], s.g0[2], n0[0], n0[1]);
@@ -146,8 +146,8 @@ __device__ __forceinline__ void pu_block(PuState& s, const uint2 w[PU_ROWS], int
   q1[1] = v5(s.g1[2], n1[0], n1[1], n1[2], n1[3]);
 #pragma unroll
   for (int i = 0; i < 3; ++i) { s.g0[i] = n0[1 + i]; s.g1[i] = n1[1 + i]; }
-  const unsigned m0 = pu_h2<LEFT, RIGHT>(q0[0], q1[0], lane, last_lane);
-  const unsigned m1 = pu_h2<LEFT, RIGHT>(q0[1], q1[1], lane, last_lane);
+  const unsigned m0 = pu_h2<LEFT, RIGHT>(q0[0], q1[0], lane, first_lane, last_lane);
+  const unsigned m1 = pu_h2<LEFT, RIGHT>(q0[1], q1[1], lane, first_lane, last_lane);
   // level-3 row b-1
   out3 = v5(s.c[0], s.c[1], s.c[2], m0, m1);
   s.c[0] = s.c[2]; s.c[1] = m0; s.c[2] = m1;
@@ -155,14 +155,14 @@ __device__ __forceinline__ void pu_block(PuState& s, const uint2 w[PU_ROWS], int
 
 // bottom border of even-sized levels: the last output row of each level uses the window (n-4, n-3, n-2, n-1, n-2)
 template <bool LEFT, bool RIGHT>
-__device__ __forceinline__ unsigned pu_flush(const PuState& s, int lane, int last_lane) {
+__device__ __forceinline__ unsigned pu_flush(const PuState& s, int lane, int first_lane, int last_lane) {
   const unsigned P = v5(s.a[0], s.a[1], s.a[2], s.a[3], s.a[2]);
   const unsigned Q = v5(s.b[0], s.b[1], s.b[2], s.b[3], s.b[2]);
   unsigned n0, n1;
-  pu_h1<LEFT, RIGHT>(P, Q, lane, last_lane, n0, n1);
+  pu_h1<LEFT, RIGHT>(P, Q, lane, first_lane, last_lane, n0, n1);
   const unsigned q0 = v5(s.g0[0], s.g0[1], s.g0[2], n0, s.g0[2]);
   const unsigned q1 = v5(s.g1[0], s.g1[1], s.g1[2], n1, s.g1[2]);
-  const unsigned m = pu_h2<LEFT, RIGHT>(q0, q1, lane, last_lane);
+  const unsigned m = pu_h2<LEFT, RIGHT>(q0, q1, lane, first_lane, last_lane);
   return v5(s.c[0], s.c[1], s.c[2], m, s.c[2]);
 }
 
@@ -216,10 +216,10 @@ __device__ __forceinline__ void pu_front_frame(const PuParams& p, const uint8_t*
 #pragma unroll
     for (int i = 0; i < PU_ROWS; ++i) w[i] = *reinterpret_cast<const uint2*>(src + i * 256);
     unsigned o;
-    pu_block<LEFT, RIGHT>(s, w, lane, last_lane, o);
+    pu_block<LEFT, RIGHT>(s, w, lane, 0, last_lane, o);
     if (b >= 1 && storing) out[(long long)(b - 1) * p.W3] = o;
   }
-  const unsigned o = pu_flush<LEFT, RIGHT>(s, lane, last_lane);
+  const unsigned o = pu_flush<LEFT, RIGHT>(s, lane, 0, last_lane);
   if (storing) out[(long long)(nblk - 1) * p.W3] = o;
   pu_wait<0>();
 }
@@ -354,11 +354,17 @@ struct PfLane {       // what a lane does with its level-3 / level-4 column
 };
 
 // S-stage TMA ring: `stage` is the ring slot of the next block to consume, `phase` the parity awaited per slot.
-template <int S, bool LEFT, bool RIGHT>
-__device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMap* tmap, int sframe, int next_sframe,
-                                             unsigned ring_s, const unsigned char* my, unsigned mbar, unsigned& phase,
-                                             int& stage, double* __restrict__ g4, const PfLane& ln, int lane, int x0,
-                                             int last_lane) {
+// Two instantiations: interior strips (no border code at all) and edge strips, whose image-border fix-ups in pu_block
+// are predicated on the lane (first_lane / last_lane = -1 where the strip lacks that border) instead of compiled per
+// kind of edge.  Three or four variants per CTA (left, interior, right, both) times an unrolled loop plus peeled copies
+// for the mirrored blocks did not fit the 32 KB instruction cache level: 1.5 no_instruction stalls per issue, 0.774 ->
+// 0.708 ms per 8192 VGA frames with a single variant (r02g, r02h); the interior variant is what 720p / 1080p frames
+// (4 of 6, 7 of 9 strips) mostly run.
+template <int S, bool EDGE>
+__device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMap* tmap, const CUtensorMap* tmap_row,
+                                             int sframe, int next_sframe, unsigned ring_s, const unsigned char* my,
+                                             unsigned mbar, unsigned& phase, int& stage, double* __restrict__ g4,
+                                             const PfLane& ln, int lane, int x0, int first_lane, int last_lane) {
   const int nblk = p.H >> 3;
   // block b (-2 .. nblk-1) of this frame, then blocks -2 .. of the next one: the ring never drains between frames
   auto issue = [&](int b, int st) {
@@ -368,8 +374,15 @@ __device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMa
     __syncwarp();                                              // every lane is done with the stage's previous rows
     if (lane == 0) {
       pu_mbar_expect_tx(mbar + 8 * st, PU_STAGE_BYTES);
-      // rows above the frame are the mirrored rows 16..9 / 8..1: fetched in frame order, read back bottom-up
-      pu_tma_load(ring_s + st * PU_STAGE_BYTES, tmap, x0, b >= 0 ? 8 * b : -8 * b - 7, z, mbar + 8 * st);
+      if (b >= 0) {
+        pu_tma_load(ring_s + st * PU_STAGE_BYTES, tmap, x0, 8 * b, z, mbar + 8 * st);
+      } else {
+        // the two blocks above the frame are its rows 16..9 / 8..1 mirrored: eight one-row boxes in that order, so that
+        // the consumer reads every block the same way
+#pragma unroll
+        for (int i = 0; i < PU_ROWS; ++i)
+          pu_tma_load(ring_s + st * PU_STAGE_BYTES + i * 256, tmap_row, x0, -(8 * b + i), z, mbar + 8 * st);
+      }
     }
   };
   PuState s;
@@ -387,7 +400,8 @@ __device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMa
     }
     hz0 = hz1; hz1 = hz2; hz2 = hz3; hz3 = hz;
   };
-  auto step = [&](int b, bool mirrored) {
+#pragma unroll 2
+  for (int b = -2; b < nblk; ++b) {
     // the stage consumed S-1 steps ago (block b-1) is free again: fetch block b+S-1 into it
     issue(b + S - 1, stage == 0 ? S - 1 : stage - 1);
     pu_mbar_wait(mbar + 8 * stage, (phase >> stage) & 1u);
@@ -396,17 +410,13 @@ __device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMa
     stage = stage + 1 == S ? 0 : stage + 1;
     uint2 w[PU_ROWS];
 #pragma unroll
-    for (int i = 0; i < PU_ROWS; ++i) w[i] = *reinterpret_cast<const uint2*>(src + (mirrored ? PU_ROWS - 1 - i : i) * 256);
+    for (int i = 0; i < PU_ROWS; ++i) w[i] = *reinterpret_cast<const uint2*>(src + i * 256);
     unsigned o;
-    pu_block<LEFT, RIGHT>(s, w, lane, last_lane, o);
+    pu_block<EDGE, EDGE>(s, w, lane, first_lane, last_lane, o);
     if (b >= 1) level3_row(o, b - 1);
-  };
-  step(-2, true);
-  step(-1, true);
-#pragma unroll 2
-  for (int b = 0; b < nblk; ++b) step(b, false);
+  }
   const int H3 = nblk;
-  level3_row(pu_flush<LEFT, RIGHT>(s, lane, last_lane), H3 - 1);
+  level3_row(pu_flush<EDGE, EDGE>(s, lane, first_lane, last_lane), H3 - 1);
   // bottom border of level 4: hz3 = row H3-1, hz2 = H3-2, ...
   const unsigned long long v = (H3 & 1) ? v5q(hz1, hz2, hz3, hz2, hz1) : v5q(hz0, hz1, hz2, hz3, hz2);
   if (ln.k >= 0) g4[((H3 - 1) >> 1) * W4 + ln.k] = (double)v * p.g_scale;
@@ -416,14 +426,16 @@ __device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMa
 // to the allocation unit of 8 per thread -- 96 for 18 warps, 80 for 21 and 24
 template <int S, int MAXW>
 __global__ void __maxnreg__((65536 / (32 * ((MAXW + 3) & ~3))) & ~7)
-    pyramid_u8_fused_kernel(const __grid_constant__ PfParams p, const __grid_constant__ CUtensorMap tmap) {
+    pyramid_u8_fused_kernel(const __grid_constant__ PfParams p, const __grid_constant__ CUtensorMap tmap,
+                            const __grid_constant__ CUtensorMap tmap_row) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / p.n_strips, strip = warp - slot * p.n_strips;
   const bool left = strip == 0, right = strip == p.n_strips - 1;
   const int base = p.strip_base[strip];
   const int col = base + lane;
-  const int last_lane = p.W3 - 1 - base;                        // lane of the last level-3 column (right strip)
+  const int first_lane = left ? 0 : -1;                         // lanes holding the image's first / last level-3 column
+  const int last_lane = right ? p.W3 - 1 - base : -1;
   PfLane ln;
   ln.s_m2 = (reflect101(col - 2, p.W3) - base) & 31; ln.s_m1 = (reflect101(col - 1, p.W3) - base) & 31;
   ln.s_p1 = (reflect101(col + 1, p.W3) - base) & 31; ln.s_p2 = (reflect101(col + 2, p.W3) - base) & 31;
@@ -445,24 +457,32 @@ __global__ void __maxnreg__((65536 / (32 * ((MAXW + 3) & ~3))) & ~7)
   long long frame = (long long)blockIdx.x * p.frames_per_cta + slot;
   unsigned phase = 0;
   int stage = 0;
-  if (frame < p.n_frames) {   // the first S-1 blocks of the slot's first frame
+  if (frame < p.n_frames) {   // the first S-1 blocks of the slot's first frame (blocks -2, -1: mirrored rows, one box each)
     const int z = (int)pu_source_frame(frame, p.seg_len, p.seg_stride, p.seg_first);
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < S - 1; ++i) {
         const int b = i - 2;
         pu_mbar_expect_tx(mbar + 8 * i, PU_STAGE_BYTES);
-        pu_tma_load(ring_s + i * PU_STAGE_BYTES, &tmap, 8 * base, b >= 0 ? 8 * b : -8 * b - 7, z, mbar + 8 * i);
+        if (b >= 0) {
+          pu_tma_load(ring_s + i * PU_STAGE_BYTES, &tmap, 8 * base, 8 * b, z, mbar + 8 * i);
+        } else {
+#pragma unroll
+          for (int r = 0; r < PU_ROWS; ++r)
+            pu_tma_load(ring_s + i * PU_STAGE_BYTES + r * 256, &tmap_row, 8 * base, -(8 * b + r), z, mbar + 8 * i);
+        }
       }
     }
   }
   for (; frame < p.n_frames; frame += stride) {
     const int sframe = (int)pu_source_frame(frame, p.seg_len, p.seg_stride, p.seg_first);
     const int next_sframe = frame + stride < p.n_frames ? (int)pu_source_frame(frame + stride, p.seg_len, p.seg_stride, p.seg_first) : -1;
-    if (left && right) pf_run_frame<S, true, true>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, last_lane);
-    else if (left) pf_run_frame<S, true, false>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, last_lane);
-    else if (right) pf_run_frame<S, false, true>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, last_lane);
-    else pf_run_frame<S, false, false>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, last_lane);
+    if (left || right)
+      pf_run_frame<S, true>(p, &tmap, &tmap_row, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base,
+                            first_lane, last_lane);
+    else
+      pf_run_frame<S, false>(p, &tmap, &tmap_row, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base,
+                             first_lane, last_lane);
     // The barrier that completes the level-4 image also re-aligns the strips of the frame (they share halo columns:
     // left alone they drift apart until a halo sector has left L2 before the neighbour asks for it, profiles/r01g).
     pf_slot_sync(slot, nt);
@@ -563,10 +583,11 @@ int pu_best_mode(rm_handle* h, const void* frames, int W, int H) {
 }
 
 template <int S, int MAXW>
-static int32_t pf_launch_cfg(rm_handle* h, const PfPlan& pl, const CUtensorMap& map, long long ctas, cudaStream_t st) {
+static int32_t pf_launch_cfg(rm_handle* h, const PfPlan& pl, const CUtensorMap& map, const CUtensorMap& map_row, long long ctas,
+                             cudaStream_t st) {
   RM_CUDA(h, cudaFuncSetAttribute(pyramid_u8_fused_kernel<S, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
   RM_PROF(h, st, "pyramid_u8_fused_kernel");
-  pyramid_u8_fused_kernel<S, MAXW><<<(unsigned)ctas, pl.warps * 32, pl.smem, st>>>(pl.p, map);
+  pyramid_u8_fused_kernel<S, MAXW><<<(unsigned)ctas, pl.warps * 32, pl.smem, st>>>(pl.p, map, map_row);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
 }
@@ -583,22 +604,24 @@ int32_t pu_launch_fused(rm_handle* h, const uint8_t* frames, double* lap_out, lo
   const long long n_src = (last / seg_len) * seg_stride + seg_first + last % seg_len + 1;
   if (n_frames >= (1ll << 31) || seg_len >= (1ll << 31) || seg_len < 1 || n_src >= (1ll << 31))
     return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: more than 2^31 frames", __func__);
-  CUtensorMap map;
+  CUtensorMap map, map_row;
   const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_src};
   const cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
-  const cuuint32_t box[3] = {256, PU_ROWS, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   pu_encode_fn enc = pu_encoder();
   if (!enc) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled not available", __func__);
-  const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return rm_fail(h, RM_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%lld)", __func__, (long long)r);
+  for (int one_row = 0; one_row < 2; ++one_row) {              // 256 x 8 boxes; 256 x 1 for the mirrored rows above a frame
+    const cuuint32_t box[3] = {256, one_row ? 1u : (cuuint32_t)PU_ROWS, 1};
+    const CUresult r = enc(one_row ? &map_row : &map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return rm_fail(h, RM_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%lld)", __func__, (long long)r);
+  }
   long long ctas = (n_frames + p.frames_per_cta - 1) / p.frames_per_cta;
   if (ctas > h->sm_count) ctas = h->sm_count;
-  if (pl.stages == 4) return pf_launch_cfg<4, 18>(h, pl, map, ctas, st);
-  if (pl.stages == 3) return pf_launch_cfg<3, 21>(h, pl, map, ctas, st);
-  return pf_launch_cfg<2, 24>(h, pl, map, ctas, st);
+  if (pl.stages == 4) return pf_launch_cfg<4, 18>(h, pl, map, map_row, ctas, st);
+  if (pl.stages == 3) return pf_launch_cfg<3, 21>(h, pl, map, map_row, ctas, st);
+  return pf_launch_cfg<2, 24>(h, pl, map, map_row, ctas, st);
 }
 
 int32_t pu_launch_front(rm_handle* h, const uint8_t* frames, uint32_t* g3, long long n_frames, long long seg_len,

@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(TB_WARPS * 32) temporal_direct_kernel(const Te
 //   q[a] = sum_t F[a][t] x[t]        F[a][t] = cos or -sin of harmonic k(j_a) at t        (only the kept bins of the rfft)
 //   r[t] = amp/T sum_a G[a][t] q[a]  G[a][t] = cos(2 pi j_a t / T)                         (the real part of the ifft)
 // is 2 K T multiply-adds per column instead of two length-T FFTs, with no bit reversal and no per-stage barriers.  Same
-// sums in the same order as temporal_direct_kernel (bit-identical to it); the FFT kernel differs from both by rounding.
+// sums in the same order as temporal_direct_kernel (up to the DC offset taken off below); the FFT kernel differs from
+// both by rounding.
 // A block owns a tile of TS_COLS columns: the tile is staged in shared memory, a thread accumulates 2 bins x 4 columns in
 // stage 1 and 8 time samples x 4 columns in stage 2; the coefficient tables are built once per (persistent) block.
 #define TS_COLS 32
@@ -218,9 +219,16 @@ __global__ void __launch_bounds__(TS_THREADS) temporal_sparse_kernel(const Spars
     const double* src = p.b.in + clip * T * p.b.P;
     double* dst = p.b.out + clip * T * p.b.P;
     __syncthreads();                               // tables written; the previous tile's X and Q are free
+    // When the mask drops the DC bin the filter does not see a constant offset: take the column's first sample off
+    // before the sums.  A column that does not change in time (every static pixel) then gives exact zeros, as the
+    // FFT's butterflies do -- locate() depends on it: a static scene must have max == min (base.py:563, :569-570),
+    // not the rounding residue of sum_t cos(.) x.
+    const bool drop_dc = p.kept[0] != 0;
+    const int cc = tid & 31;                         // TS_THREADS is a multiple of 32: a thread stages one column
+    const double x_first = (drop_dc && c0 + cc < p.b.P) ? src[c0 + cc] : 0.0;
     for (int i = tid; i < T * TS_COLS; i += TS_THREADS) {
       const int t = i >> 5, c = i & 31;
-      X[i] = (c0 + c < p.b.P) ? src[(long long)t * p.b.P + c0 + c] : 0.0;
+      X[i] = (c0 + c < p.b.P) ? src[(long long)t * p.b.P + c0 + c] - x_first : 0.0;
     }
     __syncthreads();
     {   // stage 1: bins rg and rg + 16
