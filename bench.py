@@ -19,8 +19,10 @@ A step is one pass over the batch; frames counted = every input frame of every c
             algorithmic bytes (W*H*1 + 8 * record length per frame), against MEASURED_PEAKS.json; traffic from the
             committed ncu capture of the same launch shape (profiles/roofline_traffic.json).
   extras    calibration-only (BASELINE config 2) and measure-only (config 3's loop) rates, outside the timed region.
-  cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/cpu_path.py, cv2/scipy/numpy -- the
-            reference tree itself does not exist on the GPU box) on whole clips, one worker process per host core.
+  cpu_baseline / --impl reference: the reference's own CPU path on whole clips, one worker process per host core: the
+            unmodified base.RespiratoryMonitor under oracle/shim.py (its modules are staged into the git-ignored
+            oracle/_ref/ by oracle/stage_ref.py, which travels to the GPU box) -> kind "reference"; without a staged tree
+            the restatement oracle/cpu_path.py -> kind "port".
 """
 from __future__ import annotations
 
@@ -46,17 +48,28 @@ WORKLOAD = "64 clips/GPU x 640x480x256 u8 synthetic, full path (frames 1-128 cal
 
 # --------------------------------------------------------------------------------------------------- CPU arm
 def _cpu_worker(args):
-    """One whole clip through the CPU oracle (TEST INFRASTRUCTURE used here only as the measured CPU baseline)."""
+    """One whole clip through the reference's CPU path, timed.  Preferred: the UNMODIFIED reference itself --
+    base.RespiratoryMonitor constructed on the clip under oracle/shim.py (oracle/_ref/ holds its staged modules on the
+    GPU box, oracle/stage_ref.py) -> kind "reference".  Fallback when no reference tree was staged: the restatement
+    oracle/cpu_path.run_clip -> kind "port".  (TEST INFRASTRUCTURE, used here only as the measured CPU baseline.)"""
     seed, = args
     import cv2
     cv2.setNumThreads(1)
-    from oracle import cpu_path as P
+    from oracle import shim
     from respmon_b200 import synth
     spec = synth.clip_spec(seed, W, H, T)
     clip = synth.make_clip(spec)
+    if shim.available():
+        shim.load_reference()                                   # imports outside the timer
+        t0 = time.perf_counter()
+        rm = shim.run_reference_monitor(clip, fps=int(FPS), method="flow", fps_limit=int(FPS))
+        dt = time.perf_counter() - t0
+        bpm = float(rm.freq[-1]) if len(rm.freq) else None
+        return dt, bpm, (rm.x, rm.y, rm.w, rm.h), spec.truth_bpm, "reference"
+    from oracle import cpu_path as P
     t0 = time.perf_counter()
     res = P.run_clip(clip, fps=FPS)
-    return time.perf_counter() - t0, res["bpm"], res["roi"], spec.truth_bpm
+    return time.perf_counter() - t0, res["bpm"], res["roi"], spec.truth_bpm, "port"
 
 
 def _cpu_workers():
@@ -90,13 +103,16 @@ def run_reference_arm(steps: int, warmup: int, n_gpus: int) -> dict:
                 bpm_err += [abs(o[1] - o[3]) for o in out if o[1] is not None]
     ms = 1e3 * sum(times) / len(times)
     value = workers * T / (ms / 1e3)
-    sample = "%d clips of 640x480x256 per step (one per worker process, cv2 threads = 1 each)" % workers
+    kind = out[0][4]
+    what = ("the unmodified reference (base.RespiratoryMonitor under oracle/shim.py)" if kind == "reference"
+            else "oracle/cpu_path.run_clip (restatement; no staged reference tree)")
+    sample = "%d clips of 640x480x256 per step, one per worker process, cv2 threads = 1 each, through %s" % (workers, what)
     return {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample, "host_cores": os.cpu_count()},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "median_abs_bpm_error_vs_truth": statistics.median(bpm_err) if bpm_err else None,
@@ -342,6 +358,65 @@ def run_gpu_arm(args) -> dict | None:
     same = bool(np.array_equal(out["bpm"][rank * n_clips:(rank + 1) * n_clips] if world > 1 else out["bpm"],
                                recs["bpm"], equal_nan=True))
 
+    # ---- what the box allows: the same bytes from the same pinned buffer in the same chunks, copies only (no kernels).
+    # e2e is bound by this (2.5 GB of calibration windows per 64-clip step against a few milliseconds of kernels), so
+    # e2e.value / e2e.h2d_ceiling says how much of the host -> device path the pipeline keeps busy at this N.
+    cal_dst = [torch.empty((min(args.chunk, n_clips), 128, H, W), dtype=torch.uint8, device=eng.device) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(eng.device)
+
+    def h2d_only():
+        nbytes = 0
+        with torch.cuda.stream(copy_stream):
+            for i, lo in enumerate(range(0, n_clips, args.chunk)):
+                hi = min(n_clips, lo + args.chunk)
+                for c in range(lo, hi):
+                    cal_dst[i & 1][c - lo].copy_(host[c, 1:129], non_blocking=True)
+                    nbytes += 128 * H * W
+        return nbytes
+
+    h2d_only()
+    barrier()
+    t0 = time.perf_counter()
+    copied = 0
+    for _ in range(e2e_steps):
+        copied += h2d_only()
+    copy_stream.synchronize()
+    barrier()
+    h2d_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([h2d_s], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d_s = float(t.item())
+    h2d_gbs_per_gpu = copied / h2d_s / 1e9
+    h2d_ceiling = frames_per_step * e2e_steps / h2d_s         # frames/s if only the calibration windows crossed PCIe
+    del cal_dst
+
+    # ---- batch width (N = 1): BASELINE config 3 asks for 512 clips per step; the measure stage is latency bound, so wider
+    # steps cost less than proportionally.  The 64-clip figure above stays the headline (round-over-round comparison).
+    width_sweep = None
+    if world == 1 and not args.no_width_sweep:
+        width_sweep = []
+        for nw in (128, 256, 512):
+            if nw * W * H * T > 0.4 * torch.cuda.get_device_properties(eng.device).total_memory:
+                break
+            sp = [synth.clip_spec(100000 + i, W, H, T, fps=FPS) for i in range(nw)]
+            dq = np.stack([synth.displacement_q8(s_) for s_ in sp])
+            big = eng.synth_clips(sp, dq)
+            rec_w = torch.empty((nw, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=eng.device)
+            for _ in range(2):
+                eng.run_batch(big, FPS, out=rec_w)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                eng.run_batch(big, FPS, out=rec_w)
+            b.record()
+            torch.cuda.synchronize()
+            ms_w = a.elapsed_time(b) / 3
+            okw = int((rec_w.cpu().numpy().view(RESULT_DTYPE).reshape(-1)["status"] == 0).sum())
+            width_sweep.append({"clips_per_step": nw, "ms_per_step": ms_w, "frames_per_s": nw * T / ms_w * 1e3, "clips_ok": okw})
+            del big, rec_w
+
     if world > 1:
         dist.destroy_process_group()
     sys.stdout.flush()
@@ -389,12 +464,15 @@ def run_gpu_arm(args) -> dict | None:
                    "parallelism": "clips sharded over %d GPU(s), one all-gather of 32 B result records" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mon.h2d_bytes // e2e_steps,
                 "d2h_bytes_per_step": mon.d2h_bytes // e2e_steps, "steps": e2e_steps, "chunk_clips": args.chunk,
-                "same_results_as_resident_run": same, "numa": numa},
+                "same_results_as_resident_run": same, "numa": numa,
+                "h2d_ceiling": h2d_ceiling, "h2d_only_gbs_per_gpu": h2d_gbs_per_gpu,
+                "fraction_of_h2d_ceiling": e2e_value / h2d_ceiling},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "extras": extras,
+        "width_sweep": width_sweep,
         "kernels": kernels,
         "results": {"clips_ok": int(ok.sum()), "clips": int(n_clips),
                     "median_abs_bpm_error_vs_truth": float(np.median(bpm_err)) if len(bpm_err) else None,
@@ -413,6 +491,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=32, help="clips per H2D chunk of the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-width-sweep", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -245,7 +245,10 @@ int32_t rm_pack_results_stream(rm_handle* h, const double* bpm, const int32_t* r
  *   "pyramid_mode" (0/1)         1 (default): uint8 frames whose rows are 16-byte multiples take the one-pass fused pyramid
  *                                kernel (TMA rows, levels 0..4 as integers, the rest in shared memory); 0: always level 3
  *                                through HBM + the tail kernel.  Bit-identical records.
- *   "pyramid_cfg" (0..2)         fused kernel: (ring stages, warps per CTA) = (4, 18) / (3, 21) / (2, 24).
+ *   "pyramid_cfg" (0..3)         fused kernel: (ring stages, warps per CTA) = by frame width (0, default) / (4, 18) / (3, 21) /
+ *                                (2, 24).
+ *   "pyramid_variants" (0..2)    fused kernel: interior strips run the edge-strip loop too (1), their own loop (2), or by
+ *                                frame width (0, default).
  *   "force_global_lk" (0/1)      track from global memory even when the ROI fits shared memory (the path used for ROIs
  *                                too large to stage).
  *   "force_generic_front" (0/1)  uint8 frames take the float pyramid front kernel instead of the integer one.

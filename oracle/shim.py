@@ -22,6 +22,10 @@ import types
 import numpy as np
 
 REFERENCE_DIR = os.environ.get("RESPMON_REFERENCE_DIR", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_DIR, "base.py")):
+    # the GPU box has no /root/reference: oracle/stage_ref.py copies the unmodified modules to oracle/_ref/ (git-ignored,
+    # shipped with the snapshot) so that bench.py's CPU arm can time the reference itself there
+    REFERENCE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def available() -> bool:

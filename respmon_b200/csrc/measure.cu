@@ -694,8 +694,10 @@ struct LkSmemLayout {
   int pad;
   int pyr_bytes;                                  // one padded pyramid
   int raw_pitch, raw_bytes;                       // crop as copied from the frame (columns aligned down/up to 4)
+  int sums_off;                                   // per-warp scratch of lks_gradient_sums_ordered (LKS_SUMS_BYTES each)
   int total;
 };
+#define LKS_SUMS_BYTES (3 * 16 * 16 * 4)          // three matrices x 16 window rows x 16 columns, float32
 __host__ __device__ inline LkSmemLayout lk_smem_layout(int rw, int rh, int win, int max_level, int warps) {
   LkSmemLayout L;
   L.pad = win + LK_PAD_EXTRA;
@@ -716,8 +718,8 @@ __host__ __device__ inline LkSmemLayout lk_smem_layout(int rw, int rh, int win, 
   L.pyr_bytes = off;
   L.raw_pitch = (rw + 3 + 3) & ~3;
   L.raw_bytes = (L.raw_pitch * rh + 15) & ~15;
-  (void)warps;   // the window setup runs in registers: no per-warp scratch any more
-  L.total = 2 * L.pyr_bytes + 2 * L.raw_bytes;
+  L.sums_off = 2 * L.pyr_bytes + 2 * L.raw_bytes;
+  L.total = L.sums_off + warps * LKS_SUMS_BYTES;
   return L;
 }
 
@@ -734,10 +736,64 @@ struct LkSLevel {   // one padded level in shared memory: `org` is the offset of
   int org, w, h, pitch;
 };
 
+// The gradient sums in OpenCV's order (see lk_cv_gradient_sums) when a partial sum can round -- 44 % of the windows on
+// the bench clips -- without moving every product through a shuffle: the lanes park their float products in the warp's
+// scratch (row y of the window = 16 consecutive floats per matrix), then fifteen lanes walk the fifteen accumulators
+// (q0..q3 of the three matrices in lanes 0..11, the scalar accumulators in lanes 12..14) over the rows in order.
+// About 210 warp instructions per window against 1950 through shuffles (ncu r02j: the shuffle form doubled the kernel).
+__device__ __forceinline__ void lks_gradient_sums_ordered(float* S, const int Ixv[8], const int Iyv[8], int win, int lane,
+                                                          float& A11, float& A12, float& A22) {
+  const int nsimd = (win >> 3) << 3;
+  __syncwarp();
+  {
+    float4* d = reinterpret_cast<float4*>(S + (lane >> 1) * 16 + (lane & 1) * 8);    // lane 2y + half: row y, columns 8 half ..
+    float xx[8], xy[8], yy[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      xx[k] = (float)(Ixv[k] * Ixv[k]); xy[k] = (float)(Ixv[k] * Iyv[k]); yy[k] = (float)(Iyv[k] * Iyv[k]);   // < 2^24: exact
+    }
+    d[0] = make_float4(xx[0], xx[1], xx[2], xx[3]); d[1] = make_float4(xx[4], xx[5], xx[6], xx[7]);
+    d[64] = make_float4(xy[0], xy[1], xy[2], xy[3]); d[65] = make_float4(xy[4], xy[5], xy[6], xy[7]);
+    d[128] = make_float4(yy[0], yy[1], yy[2], yy[3]); d[129] = make_float4(yy[4], yy[5], yy[6], yy[7]);
+  }
+  __syncwarp();
+  float acc = 0.f;
+  if (lane < 12) {                                  // q_j of matrix lane / 4: columns j, j+4 of every SIMD group, rows in order
+    const float* r = S + (lane >> 2) * 256 + (lane & 3);
+    if (nsimd >= 8)
+      for (int y = 0; y < win; ++y, r += 16) {
+        acc = (acc + r[0]) + r[4];
+        if (nsimd == 16) acc = (acc + r[8]) + r[12];
+      }
+  } else if (lane < 15) {                           // the scalar accumulator of matrix lane - 12: the other columns, row-major
+    const float* r = S + (lane - 12) * 256;
+    for (int y = 0; y < win; ++y, r += 16) {
+      if (nsimd == 0) {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) acc += r[x];
+      }
+      if (nsimd < 16) {
+        const float4 a = *reinterpret_cast<const float4*>(r + 8), b = *reinterpret_cast<const float4*>(r + 12);
+        acc += a.x; acc += a.y; acc += a.z; acc += a.w; acc += b.x; acc += b.y; acc += b.z; acc += b.w;
+      }
+    }
+  }
+  __syncwarp();
+  float t[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    const float q0 = __shfl_sync(0xffffffffu, acc, 4 * m), q1 = __shfl_sync(0xffffffffu, acc, 4 * m + 1);
+    const float q2 = __shfl_sync(0xffffffffu, acc, 4 * m + 2), q3 = __shfl_sync(0xffffffffu, acc, 4 * m + 3);
+    const float sc = __shfl_sync(0xffffffffu, acc, 12 + m);
+    t[m] = nsimd ? sc + ((q0 + q2) + (q1 + q3)) : sc;
+  }
+  A11 = t[0]; A12 = t[1]; A22 = t[2];
+}
+
 // One warp tracks one point through the levels (cv::LKTrackerInvoker), images in shared memory.
 // wq[k] = offset (wy * pitch-independent pair) of the lane's k-th window pixel: wy = wq >> 8, wx = wq & 255.
 __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, const LkSLevel* next, int nlev, float px,
-                               float py, float* out_x, float* out_y, const int wq[8],
+                               float py, float* out_x, float* out_y, const int wq[8], float* sums_scratch,
                                int lane) {
   const int win = p.win;
   const float half = (float)(win - 1) * 0.5f;
@@ -811,7 +867,7 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
     if (lk_sums_exact((unsigned)(sA11 + sA22))) {      // no partial sum can round: the exact totals are OpenCV's floats
       A11 = (float)warp_sum_split(sA11); A12 = (float)warp_sum_split(sA12); A22 = (float)warp_sum_split(sA22);
     } else if (!lk_gradient_sums_by_chain(Ixv, Iyv, win, lane, A11, A12, A22)) {
-      lk_cv_gradient_sums(Ixv, Iyv, win, A11, A12, A22);
+      lks_gradient_sums_ordered(sums_scratch, Ixv, Iyv, win, lane, A11, A12, A22);
     }
     A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
     float D = A11 * A22 - A12 * A12;
@@ -957,7 +1013,6 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
   auto magic_of = [](int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1u) / (unsigned)d); };
   auto refl1 = [](int v, int n) { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); };   // one reflection (n > |overhang|)
   const int nthr = LKS_WARPS * 32;
-#define LKTB(k) do { } while (0)
   auto build = [&](int raw_slot, int pyr_slot) {
     const int src = raw_base + raw_slot * L.raw_bytes + xoff;
     const int base = pyr_slot * L.pyr_bytes;
@@ -1016,7 +1071,6 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
       }
     }
     __syncthreads();
-    LKTB(0);
     for (int l = 1; l < L.nlev; ++l) {
       const int spitch = L.pitch[l - 1], dpitch = L.pitch[l];
       const int s0 = base + L.off[l - 1] + L.pad * spitch + L.pad;
@@ -1065,7 +1119,6 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
         }
       }
       __syncthreads();
-      LKTB(l == 1 ? 1 : 3);
       {
         // border pixels only: `pad` full rows above and below, 2 * pad columns beside every image row
         const int pad = L.pad, pwid = dw + 2 * pad;
@@ -1090,7 +1143,6 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
         }
       }
       __syncthreads();
-      LKTB(l == 1 ? 2 : 4);
     }
   };
   auto levels = [&](int pyr_slot, LkSLevel* out) {
@@ -1102,20 +1154,16 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
 
   // the frame before the chunk is the tracker's "previous image": frame 0 for the first chunk
   const int f_first = resume ? p.f0 : 1;
-#define LKT(acc) do { } while (0)
   stage_raw(f_first - 1, (f_first - 1) & 1);
   cp_async_wait<0>();
   __syncthreads();
   build((f_first - 1) & 1, (f_first - 1) & 1);
   if (f_first < p.f1) stage_raw(f_first, f_first & 1);
-  LKT(acc_book);
   for (int f = f_first; f < p.f1; ++f) {
     cp_async_wait<0>();
     __syncthreads();
-    LKT(acc_wait);
     build(f & 1, f & 1);
     if (f + 1 < p.f1) stage_raw(f + 1, (f + 1) & 1);   // lands while this frame is tracked
-    LKT(acc_build);
     LkSLevel prev[LK_MAX_LEVELS], next[LK_MAX_LEVELS];
     levels((f - 1) & 1, prev);
     levels(f & 1, next);
@@ -1123,11 +1171,10 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
     for (int i = warp; i < n; i += LKS_WARPS) {
       float ox, oy;
       const int st = lks_track_point(p, prev, next, L.nlev, s_pts[i][0], s_pts[i][1], &ox, &oy, wq,
-                                     lane);
+                                     reinterpret_cast<float*>(lks_smem + L.sums_off) + warp * (LKS_SUMS_BYTES / 4), lane);
       if (lane == 0) { s_new[i][0] = ox; s_new[i][1] = oy; s_st[i] = st; }
     }
     __syncthreads();
-    LKT(acc_track);
     if (tid == 0) {
       // good_new = p1[st == 1], good_old = pts[st == 1] (base.py:377-382): survivors keep their relative order; their
       // old - new goes out under the point's original index for the ordered float32 mean (base.py:388)
@@ -1145,7 +1192,6 @@ __global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const Mea
       s_n = m;
     }
     __syncthreads();
-    LKT(acc_book);
     if (p.pts_dbg) {   // single-block mode only (bpc == 1): the compacted list is the reference's motion_key_points
       float* dbg = p.pts_dbg + ((long long)clip * p.n_frames + f) * LK_MAX_PTS * 2;
       for (int i = tid; i < LK_MAX_PTS; i += blockDim.x) {

@@ -356,12 +356,12 @@ struct PfLane {       // what a lane does with its level-3 / level-4 column
 // S-stage TMA ring: `stage` is the ring slot of the next block to consume, `phase` the parity awaited per slot.
 // Two instantiations: interior strips (no border code at all) and edge strips, whose image-border fix-ups in pu_block
 // are predicated on the lane (first_lane / last_lane = -1 where the strip lacks that border) instead of compiled per
-// kind of edge.  Three or four variants per CTA (left, interior, right, both) times an unrolled loop plus peeled copies
-// for the mirrored blocks did not fit the 32 KB instruction cache level: 1.5 no_instruction stalls per issue, 0.774 ->
-// 0.708 ms per 8192 VGA frames with a single variant (r02g, r02h); the interior variant is what 720p / 1080p frames
-// (4 of 6, 7 of 9 strips) mostly run.
+// kind of edge.  Three or four variants per CTA (left, interior, right, both) times an unrolled loop plus two peeled
+// copies for the mirrored blocks did not fit the 32 KB instruction cache level: 1.5 no_instruction stalls per issue,
+// 0.774 -> 0.708 ms per 8192 VGA frames with a single variant (r02g, r02h); the interior variant is what 720p / 1080p
+// frames (4 of 6, 7 of 9 strips) mostly run.
 template <int S, bool EDGE>
-__device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMap* tmap, const CUtensorMap* tmap_row,
+__device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMap* tmap,
                                              int sframe, int next_sframe, unsigned ring_s, const unsigned char* my,
                                              unsigned mbar, unsigned& phase, int& stage, double* __restrict__ g4,
                                              const PfLane& ln, int lane, int x0, int first_lane, int last_lane) {
@@ -374,15 +374,8 @@ __device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMa
     __syncwarp();                                              // every lane is done with the stage's previous rows
     if (lane == 0) {
       pu_mbar_expect_tx(mbar + 8 * st, PU_STAGE_BYTES);
-      if (b >= 0) {
-        pu_tma_load(ring_s + st * PU_STAGE_BYTES, tmap, x0, 8 * b, z, mbar + 8 * st);
-      } else {
-        // the two blocks above the frame are its rows 16..9 / 8..1 mirrored: eight one-row boxes in that order, so that
-        // the consumer reads every block the same way
-#pragma unroll
-        for (int i = 0; i < PU_ROWS; ++i)
-          pu_tma_load(ring_s + st * PU_STAGE_BYTES + i * 256, tmap_row, x0, -(8 * b + i), z, mbar + 8 * st);
-      }
+      // rows above the frame are the mirrored rows 16..9 / 8..1: fetched in frame order, read back bottom-up
+      pu_tma_load(ring_s + st * PU_STAGE_BYTES, tmap, x0, b >= 0 ? 8 * b : -8 * b - 7, z, mbar + 8 * st);
     }
   };
   PuState s;
@@ -400,8 +393,7 @@ __device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMa
     }
     hz0 = hz1; hz1 = hz2; hz2 = hz3; hz3 = hz;
   };
-#pragma unroll 2
-  for (int b = -2; b < nblk; ++b) {
+  auto step = [&](int b, bool mirrored) {
     // the stage consumed S-1 steps ago (block b-1) is free again: fetch block b+S-1 into it
     issue(b + S - 1, stage == 0 ? S - 1 : stage - 1);
     pu_mbar_wait(mbar + 8 * stage, (phase >> stage) & 1u);
@@ -410,11 +402,15 @@ __device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMa
     stage = stage + 1 == S ? 0 : stage + 1;
     uint2 w[PU_ROWS];
 #pragma unroll
-    for (int i = 0; i < PU_ROWS; ++i) w[i] = *reinterpret_cast<const uint2*>(src + i * 256);
+    for (int i = 0; i < PU_ROWS; ++i) w[i] = *reinterpret_cast<const uint2*>(src + (mirrored ? PU_ROWS - 1 - i : i) * 256);
     unsigned o;
     pu_block<EDGE, EDGE>(s, w, lane, first_lane, last_lane, o);
     if (b >= 1) level3_row(o, b - 1);
-  }
+  };
+#pragma unroll 1
+  for (int b = -2; b < 0; ++b) step(b, true);                  // one cold copy of the body for the two mirrored blocks
+#pragma unroll 2
+  for (int b = 0; b < nblk; ++b) step(b, false);
   const int H3 = nblk;
   level3_row(pu_flush<EDGE, EDGE>(s, lane, first_lane, last_lane), H3 - 1);
   // bottom border of level 4: hz3 = row H3-1, hz2 = H3-2, ...
@@ -426,8 +422,7 @@ __device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMa
 // to the allocation unit of 8 per thread -- 96 for 18 warps, 80 for 21 and 24
 template <int S, int MAXW>
 __global__ void __maxnreg__((65536 / (32 * ((MAXW + 3) & ~3))) & ~7)
-    pyramid_u8_fused_kernel(const __grid_constant__ PfParams p, const __grid_constant__ CUtensorMap tmap,
-                            const __grid_constant__ CUtensorMap tmap_row) {
+    pyramid_u8_fused_kernel(const __grid_constant__ PfParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / p.n_strips, strip = warp - slot * p.n_strips;
@@ -457,32 +452,26 @@ __global__ void __maxnreg__((65536 / (32 * ((MAXW + 3) & ~3))) & ~7)
   long long frame = (long long)blockIdx.x * p.frames_per_cta + slot;
   unsigned phase = 0;
   int stage = 0;
-  if (frame < p.n_frames) {   // the first S-1 blocks of the slot's first frame (blocks -2, -1: mirrored rows, one box each)
+  if (frame < p.n_frames) {   // the first S-1 blocks of the slot's first frame
     const int z = (int)pu_source_frame(frame, p.seg_len, p.seg_stride, p.seg_first);
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < S - 1; ++i) {
         const int b = i - 2;
         pu_mbar_expect_tx(mbar + 8 * i, PU_STAGE_BYTES);
-        if (b >= 0) {
-          pu_tma_load(ring_s + i * PU_STAGE_BYTES, &tmap, 8 * base, 8 * b, z, mbar + 8 * i);
-        } else {
-#pragma unroll
-          for (int r = 0; r < PU_ROWS; ++r)
-            pu_tma_load(ring_s + i * PU_STAGE_BYTES + r * 256, &tmap_row, 8 * base, -(8 * b + r), z, mbar + 8 * i);
-        }
+        pu_tma_load(ring_s + i * PU_STAGE_BYTES, &tmap, 8 * base, b >= 0 ? 8 * b : -8 * b - 7, z, mbar + 8 * i);
       }
     }
   }
   for (; frame < p.n_frames; frame += stride) {
     const int sframe = (int)pu_source_frame(frame, p.seg_len, p.seg_stride, p.seg_first);
     const int next_sframe = frame + stride < p.n_frames ? (int)pu_source_frame(frame + stride, p.seg_len, p.seg_stride, p.seg_first) : -1;
-    if (left || right)
-      pf_run_frame<S, true>(p, &tmap, &tmap_row, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base,
-                            first_lane, last_lane);
+    if (left || right || p.one_variant)
+      pf_run_frame<S, true>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, first_lane,
+                            last_lane);
     else
-      pf_run_frame<S, false>(p, &tmap, &tmap_row, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base,
-                             first_lane, last_lane);
+      pf_run_frame<S, false>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, first_lane,
+                             last_lane);
     // The barrier that completes the level-4 image also re-aligns the strips of the frame (they share halo columns:
     // left alone they drift apart until a halo sector has left L2 before the neighbour asks for it, profiles/r01g).
     pf_slot_sync(slot, nt);
@@ -536,9 +525,15 @@ static bool pf_plan(rm_handle* h, int W, int H, PfPlan& pl) {
     k0 = k1; ++n;
   }
   p.n_strips = n;
+  // Few strips per frame are mostly edge strips: let the interior ones run the edge code too (one hot loop in the
+  // instruction cache instead of two): 0.734 -> 0.708 ms per 8192 VGA frames; wide frames keep the lean interior loop.
+  p.one_variant = h->pyramid_variants == 1 || (h->pyramid_variants == 0 && n <= 3);
   // ring depth / warps per CTA: as many frame slots as shared memory, the register file and 15 named barriers allow
-  const int cfg[3][2] = {{4, 18}, {3, 21}, {2, 24}};            // (stages, max warps) in order of preference
-  int pick = h->pyramid_cfg >= 0 && h->pyramid_cfg < 3 ? h->pyramid_cfg : 0;
+  const int cfg[3][2] = {{4, 18}, {3, 21}, {2, 24}};            // (stages, max warps)
+  // measured (r02l): frames of up to three strips (VGA: 3 x 8 slots) want the most warps, 2 stages x 24 warps -- 0.667 ms
+  // per 8192 VGA frames against 0.749 with 4 x 18; wider frames, whose level images leave room for few slots anyway,
+  // want the deep ring and the 96 registers: 720p 0.527 against 0.605 ms per 2048 frames, 1080p 0.783 against 0.880
+  int pick = h->pyramid_cfg >= 1 && h->pyramid_cfg <= 3 ? h->pyramid_cfg - 1 : (n <= 3 ? 2 : 0);
   for (int tries = 0; tries < 3; ++tries, pick = (pick + 1) % 3) {
     const int S = cfg[pick][0], maxw = cfg[pick][1];
     const int per_slot = n * S * PU_STAGE_BYTES + lvl_bytes + n * S * 8;
@@ -583,11 +578,10 @@ int pu_best_mode(rm_handle* h, const void* frames, int W, int H) {
 }
 
 template <int S, int MAXW>
-static int32_t pf_launch_cfg(rm_handle* h, const PfPlan& pl, const CUtensorMap& map, const CUtensorMap& map_row, long long ctas,
-                             cudaStream_t st) {
+static int32_t pf_launch_cfg(rm_handle* h, const PfPlan& pl, const CUtensorMap& map, long long ctas, cudaStream_t st) {
   RM_CUDA(h, cudaFuncSetAttribute(pyramid_u8_fused_kernel<S, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
   RM_PROF(h, st, "pyramid_u8_fused_kernel");
-  pyramid_u8_fused_kernel<S, MAXW><<<(unsigned)ctas, pl.warps * 32, pl.smem, st>>>(pl.p, map, map_row);
+  pyramid_u8_fused_kernel<S, MAXW><<<(unsigned)ctas, pl.warps * 32, pl.smem, st>>>(pl.p, map);
   RM_LAUNCH_CHECK(h);
   return RM_OK;
 }
@@ -604,24 +598,22 @@ int32_t pu_launch_fused(rm_handle* h, const uint8_t* frames, double* lap_out, lo
   const long long n_src = (last / seg_len) * seg_stride + seg_first + last % seg_len + 1;
   if (n_frames >= (1ll << 31) || seg_len >= (1ll << 31) || seg_len < 1 || n_src >= (1ll << 31))
     return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: more than 2^31 frames", __func__);
-  CUtensorMap map, map_row;
+  CUtensorMap map;
   const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_src};
   const cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)W * H};
+  const cuuint32_t box[3] = {256, PU_ROWS, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   pu_encode_fn enc = pu_encoder();
   if (!enc) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled not available", __func__);
-  for (int one_row = 0; one_row < 2; ++one_row) {              // 256 x 8 boxes; 256 x 1 for the mirrored rows above a frame
-    const cuuint32_t box[3] = {256, one_row ? 1u : (cuuint32_t)PU_ROWS, 1};
-    const CUresult r = enc(one_row ? &map_row : &map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return rm_fail(h, RM_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%lld)", __func__, (long long)r);
-  }
+  const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return rm_fail(h, RM_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%lld)", __func__, (long long)r);
   long long ctas = (n_frames + p.frames_per_cta - 1) / p.frames_per_cta;
   if (ctas > h->sm_count) ctas = h->sm_count;
-  if (pl.stages == 4) return pf_launch_cfg<4, 18>(h, pl, map, map_row, ctas, st);
-  if (pl.stages == 3) return pf_launch_cfg<3, 21>(h, pl, map, map_row, ctas, st);
-  return pf_launch_cfg<2, 24>(h, pl, map, map_row, ctas, st);
+  if (pl.stages == 4) return pf_launch_cfg<4, 18>(h, pl, map, ctas, st);
+  if (pl.stages == 3) return pf_launch_cfg<3, 21>(h, pl, map, ctas, st);
+  return pf_launch_cfg<2, 24>(h, pl, map, ctas, st);
 }
 
 int32_t pu_launch_front(rm_handle* h, const uint8_t* frames, uint32_t* g3, long long n_frames, long long seg_len,

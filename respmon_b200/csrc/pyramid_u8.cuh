@@ -23,6 +23,7 @@ struct PfParams {          // fused kernel: frames -> packed Laplacian records
   long long n_frames, seg_len, seg_stride, seg_first;
   int W, H, W3, H3;
   int n_strips, frames_per_cta;
+  int one_variant;         // interior strips run the edge instantiation too (see pf_run_frame)
   int strip_base[16];      // level-3 column held by lane 0 of the strip's warp (even)
   int strip_k0[16], strip_k1[16];   // level-`first` columns [k0, k1) the strip emits
   int first, top;          // Gaussian levels first..top are built; Laplacian levels first..top-1 are written

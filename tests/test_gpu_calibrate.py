@@ -110,21 +110,24 @@ def test_pyramid_kernels_are_bit_identical(eng, w, h, n_clips, T):
         eng.set_option("pyramid_mode", 0)
         out["split"] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
         eng.set_option("pyramid_mode", 1)
-        for cfg in (0, 1, 2):
-            eng.set_option("pyramid_cfg", cfg)
-            out["fused%d" % cfg] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
+        for cfg in (0, 1, 2, 3):
+            for variants in (1, 2):
+                eng.set_option("pyramid_cfg", cfg)
+                eng.set_option("pyramid_variants", variants)
+                out["fused%d/%d" % (cfg, variants)] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
         eng.set_option("force_generic_front", 1)
         out["f64"] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
     finally:
         eng.set_option("pyramid_mode", 1)
         eng.set_option("pyramid_cfg", 0)
+        eng.set_option("pyramid_variants", 0)
         eng.set_option("force_generic_front", 0)
     for k in out:
         assert np.array_equal(out["split"], out[k]), "%s differs from the split path in %d values" % (
             k, int((out["split"] != out[k]).sum()))
     lap = P.laplacian_levels(P.u8_to_unit(clips[-1, 2]), 9)
     for (l, lw, lh, off) in eng.record_levels(w, h):
-        assert np.abs(out["fused0"][-1, 1, off:off + lw * lh].reshape(lh, lw) - lap[l]).max() <= 2e-14
+        assert np.abs(out["fused0/1"][-1, 1, off:off + lw * lh].reshape(lh, lw) - lap[l]).max() <= 2e-14
 
 
 def test_pyramid_build_golden_taps(eng, golden):

@@ -1,7 +1,7 @@
 """Developer tool: the uint8 pyramid stage (frames in -> packed Laplacian records out) per mode at the bench shape.
     python tools/bench_pyramid.py [W H n_clips]
 "split" = level 3 through HBM + pyramid_tail_kernel (the fallback), "fused c" = the one-pass TMA kernel in ring /
-occupancy configuration c (0: 4 stages x 18 warps, 1: 3 x 21, 2: 2 x 24).
+occupancy configuration c (0: chosen by frame width, 1: 4 stages x 18 warps, 2: 3 x 21, 3: 2 x 24).
 Prints the stage time from CUDA events, the SURVEY 8(d) algorithmic bytes (W*H*1 + record*8 per frame) over it, and
 whether the records equal mode 0's bit for bit."""
 import json, os, sys
@@ -25,9 +25,10 @@ try:
 except Exception:
     pass
 base = None
-for mode in [int(m) for m in os.environ.get('RM_MODES', '-1,0,1,2').split(',')]:
+for mode in [int(m) for m in os.environ.get('RM_MODES', '-1,0,1,2,3').split(',')]:
     eng.set_option("pyramid_mode", 0 if mode < 0 else 1)
     eng.set_option("pyramid_cfg", max(mode, 0))
+    eng.set_option("pyramid_variants", int(os.environ.get("RM_VARIANTS", "0")))
     out = eng.pyramid_build_clips(clips, first, length)
     for _ in range(3):
         eng.pyramid_build_clips(clips, first, length)
