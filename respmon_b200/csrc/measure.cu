@@ -877,6 +877,9 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
       continue;
     }
     D = 1.f / D;
+    unsigned aI[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) aI[k] = (unsigned)(abs(Ixv[k]) + abs(Iyv[k]));
     float qx = nx - half, qy = ny - half;
     float pdx = 0.f, pdy = 0.f;
     // the lane's window pixels are 8 consecutive columns of one row (wq[0] is the first): 2 x 9 bytes of J per iteration
@@ -895,23 +898,28 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
       const unsigned char* r0 = lks_smem + J.org + jy * J.pitch + jx + jrow;
       const unsigned char* r1 = r0 + J.pitch;
       int sb1 = 0, sb2 = 0;
-      int dxv[8], dyv[8];
-      unsigned babs = 0;
+      int diffv[8];
+      unsigned babs = 0;             // sum of |diff| (|Ix| + |Iy|) >= sum of |diff Ix| + |diff Iy|
       int t0 = r0[0], t1 = r1[0];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int u0 = r0[k + 1], u1 = r1[k + 1];
         // pixels past the end of the window carry Ix = Iy = 0: whatever they read contributes nothing
         const int diff = descale(t0 * iw00 + u0 * iw01 + t1 * iw10 + u1 * iw11, 9) - Iw[k];
-        dxv[k] = diff * Ixv[k];     // |diff| <= 8160, |Ix| <= 4080: eight products stay below 2^30
-        dyv[k] = diff * Iyv[k];
-        sb1 += dxv[k]; sb2 += dyv[k];
-        babs += (unsigned)abs(dxv[k]) + (unsigned)abs(dyv[k]);
+        diffv[k] = diff;
+        sb1 += diff * Ixv[k];       // |diff| <= 8160, |Ix| <= 4080: eight products stay below 2^30
+        sb2 += diff * Iyv[k];
+        babs += (unsigned)abs(diff) * aI[k];
         t0 = u0; t1 = u1;
       }
       float b1, b2;
       if (lk_sums_exact(babs)) { b1 = (float)warp_sum_split(sb1); b2 = (float)warp_sum_split(sb2); }
-      else lk_cv_mismatch_sums(dxv, dyv, win, b1, b2);
+      else {                         // a partial sum can round (never seen on the bench clips): rows in order
+        int dxv[8], dyv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { dxv[k] = diffv[k] * Ixv[k]; dyv[k] = diffv[k] * Iyv[k]; }
+        lk_cv_mismatch_sums(dxv, dyv, win, b1, b2);
+      }
       b1 *= FLT_SCALE; b2 *= FLT_SCALE;
       const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
       qx += dx; qy += dy;
