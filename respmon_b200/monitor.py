@@ -39,27 +39,29 @@ _log = logging.getLogger("respmon_b200")
 
 
 class Benchmarker:
-    """tools.Benchmarker (tools.py:60-82): named wall-clock tick lists with the same report layout."""
+    """tools.Benchmarker (tools.py:60-82): named wall-clock tick lists, same attributes (`starts`, `ticks`), same
+    report layout."""
 
     def __init__(self):
-        self.tags = {}
-        self._open = {}
+        self.starts = dict()
+        self.ticks = dict()
 
     def add_tag(self, tag):
-        self.tags.setdefault(tag, [])
+        self.ticks[tag] = []
 
     def tick_start(self, tag):
-        self._open[tag] = time.time()
+        self.starts[tag] = time.time()
 
     def tick_end(self, tag):
-        self.tags.setdefault(tag, []).append(time.time() - self._open.pop(tag))
+        self.ticks.setdefault(tag, []).append(time.time() - self.starts[tag])
 
     def get_report(self):
-        lines = []
-        for tag, v in self.tags.items():
-            if v:
-                lines.append("{0}: mean={1}, std={2}, n={3}".format(tag, np.mean(v), np.std(v), len(v)))
-        return "\r\n".join(lines)
+        return 'Tag, Average Time (seconds), Iterations\r\n' + \
+               '\r\n'.join(['{0}, {1}, {2}'.format(tag, np.mean(l) if len(l) else float('nan'), len(l))
+                             for tag, l in self.ticks.items()])
+
+    def has_tag(self, tag):
+        return tag in self.ticks
 
 
 def reduce_bounding_box(x, y, w, h, maximum_area):

@@ -61,9 +61,10 @@ def butter_lowpass_filter(data, cutoff, fs, order=5, engine=None):
     return s["filtered"][0, :len(x)].cpu().numpy()
 
 
-def temporal_bandpass_filter_fft(data, fps, freq_min=0.833, freq_max=1, axis=0, amplification_factor=1, verbose=False,
-                                 engine=None):
-    """transforms.py:82-102 along axis 0: packed-real FFT mask filter times the amplification."""
+def temporal_bandpass_filter_fft(data, fps, freq_min=0.833, freq_max=1, axis=0, amplification_factor=50, verbose=False,
+                                 debug='', engine=None):
+    """transforms.py:82-102 along axis 0: packed-real FFT mask filter times the amplification.
+    Same positional order and defaults as the reference (amplification_factor=50, verbose, debug)."""
     if axis != 0:
         raise NotImplementedError("only axis=0 (the reference hard-codes axis 0 for the inverse, App. B.7)")
     eng = engine or default_engine()
@@ -74,14 +75,22 @@ def temporal_bandpass_filter_fft(data, fps, freq_min=0.833, freq_max=1, axis=0, 
     x = np.asarray(data, dtype=np.float64)
     T = x.shape[0]
     d = _dev(x.reshape(1, T, -1), eng)
-    return eng.temporal_bandpass(d, float(fps)).cpu().numpy().reshape(x.shape)
+    result = eng.temporal_bandpass(d, float(fps)).cpu().numpy().reshape(x.shape)
+    if verbose:
+        print('{0}{1},{2}'.format(debug, result.min(), result.max()))          # transforms.py:100-101
+    return result
 
 
 def eulerian_magnification_bandpass(vid_data, fps, freq_min, freq_max, amplification, pyramid_levels=4,
-                                    skip_levels_at_top=2, threshold=0.7, verbose=False, engine=None):
+                                    skip_levels_at_top=2, verbose=False,
+                                    temporal_filter_function=None, threshold=0.7, engine=None):
     """transforms.py:144-198, level by level on the device: Laplacian video pyramid, temporal filter on levels
     skip_levels_at_top .. pyramid_levels-2, collapse of the band-passed pyramid, global min/max clip.
-    Returns (bandpassed_data, raw_bandpassed_data), both (T,H,W) float64."""
+    Returns (bandpassed_data, raw_bandpassed_data), both (T,H,W) float64.  Positional order as in the reference
+    (..., skip_levels_at_top, verbose, temporal_filter_function, threshold); the only temporal filter base.py ever
+    passes is temporal_bandpass_filter_fft, the one the kernels implement."""
+    if temporal_filter_function is not None and temporal_filter_function is not temporal_bandpass_filter_fft:
+        raise NotImplementedError("only temporal_bandpass_filter_fft (transforms.py:82-102) is implemented on the device")
     eng = engine or default_engine()
     if (freq_min, freq_max, float(amplification)) != (eng.params.freq_min, eng.params.freq_max,
                                                       eng.params.amplification):

@@ -142,3 +142,61 @@ def test_gather_records_world_size_2_gloo(counts):
     assert np.array_equal(a, b) and len(a) == n                       # every rank holds every record, in clip order
     assert np.array_equal(a["x"], np.arange(n)) and np.allclose(a["bpm"], np.arange(n) + 0.25)
     assert list(a["status"]) == [0] * counts[0] + [1] * counts[1]
+
+
+def test_api_parity_signatures_match_the_reference():
+    """The API-parity modules take the reference's arguments in the reference's order with the reference's defaults
+    (transforms.py:82-83, :144-146; pyramid.py:9, :20, :31, :51, :60); `engine` is the only extra, keyword, argument.
+    Container only (needs the reference tree)."""
+    import inspect
+    from oracle import shim
+    if not shim.available():
+        pytest.skip("reference tree not present")
+    ref = shim.load_reference()
+    from respmon_b200 import pyramid as my_pyr
+    from respmon_b200 import transforms as my_tr
+    pairs = [(my_tr.temporal_bandpass_filter_fft, ref.transforms.temporal_bandpass_filter_fft),
+             (my_tr.eulerian_magnification_bandpass, ref.transforms.eulerian_magnification_bandpass),
+             (my_tr.butter_lowpass, ref.transforms.butter_lowpass),
+             (my_tr.butter_lowpass_filter, ref.transforms.butter_lowpass_filter),
+             (my_tr.uint8_to_float, ref.transforms.uint8_to_float), (my_tr.float_to_uint8, ref.transforms.float_to_uint8),
+             (my_pyr.create_gaussian_image_pyramid, ref.pyramid.create_gaussian_image_pyramid),
+             (my_pyr.create_laplacian_image_pyramid, ref.pyramid.create_laplacian_image_pyramid),
+             (my_pyr.create_laplacian_video_pyramid, ref.pyramid.create_laplacian_video_pyramid),
+             (my_pyr.collapse_laplacian_pyramid, ref.pyramid.collapse_laplacian_pyramid),
+             (my_pyr.collapse_laplacian_video_pyramid, ref.pyramid.collapse_laplacian_video_pyramid)]
+    for mine, theirs in pairs:
+        a = [(n, p.default) for n, p in inspect.signature(mine).parameters.items() if n != "engine"]
+        b = [(n, p.default) for n, p in inspect.signature(theirs).parameters.items()]
+        assert len(a) == len(b), (mine.__name__, a, b)
+        for (na, da), (nb, db) in zip(a, b):
+            assert na == nb, (mine.__name__, na, nb)
+            if db is not inspect.Parameter.empty and callable(db):   # temporal_filter_function=temporal_bandpass_filter_fft: None stands for it
+                assert da is None
+            else:
+                assert da == db or (da is inspect.Parameter.empty and db is inspect.Parameter.empty), (mine.__name__, na, da, db)
+
+
+def test_benchmarker_matches_the_reference_report():
+    """tools.Benchmarker (tools.py:60-82): attributes, has_tag and the report layout."""
+    import time as _time
+    from respmon_b200.monitor import Benchmarker
+    b = Benchmarker()
+    b.add_tag("Measurement Loop")
+    assert b.has_tag("Measurement Loop") and not b.has_tag("x")
+    b.tick_start("Measurement Loop")
+    _time.sleep(0.001)
+    b.tick_end("Measurement Loop")
+    assert list(b.ticks) == ["Measurement Loop"] and len(b.ticks["Measurement Loop"]) == 1 and "Measurement Loop" in b.starts
+    lines = b.get_report().split("\r\n")
+    assert lines[0] == "Tag, Average Time (seconds), Iterations"
+    assert lines[1].startswith("Measurement Loop, ") and lines[1].endswith(", 1")
+    from oracle import shim
+    if shim.available():
+        rb = shim.load_reference().tools.Benchmarker()
+        rb.add_tag("t")
+        rb.ticks["t"] = [0.5, 1.5]
+        b2 = Benchmarker()
+        b2.add_tag("t")
+        b2.ticks["t"] = [0.5, 1.5]
+        assert b2.get_report() == rb.get_report()
