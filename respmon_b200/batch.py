@@ -127,17 +127,28 @@ class BatchMonitor:
         of the measure frames H2D (second copy stream) -> LK measure + BPM on one of `measure_streams` streams.  The
         measure kernels are latency bound (frames are sequential), so consecutive chunks run them
         concurrently on different streams, each through its own rm_handle (handles own their scratch)."""
-        host = torch.from_numpy(clips) if isinstance(clips, np.ndarray) else clips
-        assert host.dtype == torch.uint8 and host.dim() == 4 and not host.is_cuda and host.is_contiguous()
-        n, T, H, W = host.shape
+        if isinstance(clips, (list, tuple)):
+            # clips held one by one (e.g. the members of one resolution class of a ragged batch): no stacked copy is made,
+            # every clip's calibration window and ROI crops go up from where the clip lies (pinned or pageable)
+            host = [torch.from_numpy(c) if isinstance(c, np.ndarray) else c for c in clips]
+            assert all(c.dtype == torch.uint8 and c.dim() == 3 and not c.is_cuda and c.is_contiguous() and
+                       c.shape == host[0].shape for c in host)
+            n, (T, H, W) = len(host), tuple(host[0].shape)
+            host_np = [c.numpy() for c in host]
+        else:
+            host = torch.from_numpy(clips) if isinstance(clips, np.ndarray) else clips
+            assert host.dtype == torch.uint8 and host.dim() == 4 and not host.is_cuda and host.is_contiguous()
+            n, T, H, W = host.shape
+            host_np = host.numpy()
         measure_first = cal_first + cal_len + 1
         n_meas = T - measure_first
         assert cal_first >= 0 and n_meas >= 1
         if not self.crop_upload:
+            if isinstance(host, list):
+                host = torch.stack(host)
             return dict(done=self._run_full_frames(host, fps, cal_first, cal_len))
         eng = self.engine
         dev = eng.device
-        host_np = host.numpy()
         main = torch.cuda.current_stream(dev)
         copy, copy2 = self._copy_stream, self._crop_stream
         n_ms = len(self._measure_streams)
@@ -156,7 +167,7 @@ class BatchMonitor:
                 if used["cal"][slot]:
                     copy.wait_event(E["cal_freed"][slot])         # locate() of the chunk that last used this buffer is done
                 for c in range(lo, hi):                           # one contiguous block per clip
-                    dst[c - lo].copy_(host[c, cal_first:cal_first + cal_len], non_blocking=True)
+                    dst[c - lo].copy_(host[c][cal_first:cal_first + cal_len], non_blocking=True)
                 E["cal_ready"][slot].record(copy)
             used["cal"][slot] = True
             self.h2d_bytes += dst.numel()
@@ -190,7 +201,7 @@ class BatchMonitor:
             for c in range(m):
                 if ok[c]:
                     x, y, w, h = (int(v) for v in r[c])
-                    sv[c, :, :h, :w] = host_np[lo + c, measure_first:, y:y + h, x:x + w]   # base.py:471
+                    sv[c, :, :h, :w] = host_np[lo + c][measure_first:, y:y + h, x:x + w]   # base.py:471
             crops = self._buffer(("cropdev", ms), (m, n_meas, mh, mw))
             with torch.cuda.stream(copy2):
                 if used["ms"][ms]:
@@ -277,16 +288,17 @@ class BatchMonitor:
 
     def run_mixed(self, clips: list, fps: float, cal_first: int = 1, cal_len: int = 128) -> np.ndarray:
         """Ragged batch (BASELINE config 5): clips is a list of (T,H,W) uint8 arrays of different sizes.  Clips are
-        grouped into resolution classes (one kernel configuration and one set of level sizes per class) and every
-        class goes through `run`; records come back in the order the clips were given."""
+        grouped into resolution classes (one kernel configuration, one set of level sizes and one TMA tensor map per
+        class); the clips of a class are NOT copied together on the host -- each goes up from where it lies -- and all
+        classes are submitted before the first is collected, so the uploads and the latency-bound stages of one class
+        overlap the kernels of another.  Records come back in the order the clips were given."""
         classes = {}
         for i, c in enumerate(clips):
             classes.setdefault(tuple(c.shape), []).append(i)
         out = np.zeros(len(clips), RESULT_DTYPE)
-        for shape, idx in sorted(classes.items()):
-            if isinstance(clips[idx[0]], np.ndarray):
-                stack = np.stack([clips[i] for i in idx])
-            else:
-                stack = torch.stack([clips[i] for i in idx])
-            out[idx] = self.run(stack, fps, cal_first=cal_first, cal_len=cal_len)
+        tickets = []
+        for shape, idx in sorted(classes.items(), key=lambda kv: -int(np.prod(kv[0])) * len(kv[1])):   # heaviest first
+            tickets.append((idx, self.submit([clips[i] for i in idx], fps, cal_first=cal_first, cal_len=cal_len)))
+        for idx, ticket in tickets:
+            out[idx] = self.collect(ticket)
         return out

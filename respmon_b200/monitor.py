@@ -260,8 +260,13 @@ class RespiratoryMonitor:
         import cv2                                      # device / file capture is I/O, not part of the hot path
         return cv2.VideoCapture(target)
 
+    #: frames a capture object may deliver before run() refuses to go on (the whole stream is held on the device: T*H*W
+    #: bytes); finite clips and files stay far below, an endless source (a webcam) would otherwise grow until memory ends
+    max_stream_frames = 1 << 16
+
     def _drain(self):
-        """Read the stream to its end (next_frame, base.py:227-233) into one (T,H,W) uint8 device tensor."""
+        """Read the stream to its end (next_frame, base.py:227-233) into one (T,H,W) uint8 device tensor.  Frames are
+        uploaded in blocks of 64 (one H2D copy and, for BGR sources, one colour conversion per block, not per frame)."""
         if self._frames is not None:
             return
         dev = self.engine.device
@@ -271,21 +276,37 @@ class RespiratoryMonitor:
             self._frames = clip.to(dev).contiguous()
             self.cap.pos = clip.shape[0]
             return
-        frames = []
+        if isinstance(self.capture_target, int):
+            raise RuntimeError("capture_target=%r is a live camera: this class holds the whole stream on the device and "
+                               "returns when it ends; live sources are served frame by frame by "
+                               "respmon_b200.live.LiveFleet" % (self.capture_target,))
+        blocks, pending, total = [], [], 0
+
+        def flush():
+            if not pending:
+                return
+            block = torch.from_numpy(np.ascontiguousarray(np.stack(pending))).to(dev)
+            if block.dim() == 4:                        # BGR -> gray with cv2.cvtColor's fixed-point weights (base.py:230)
+                block = self.engine.bgr_to_gray(block)
+            blocks.append(block)
+            pending.clear()
+
         while self.cap.isOpened():
             self.benchmarker.tick_start('Frame Capture')
             ok, frame = self.cap.read()
             if frame is None or frame is False:
                 break
             self.benchmarker.tick_end('Frame Capture')
-            frame = np.asarray(frame)
-            if frame.ndim == 3:                         # BGR -> gray with cv2.cvtColor's fixed-point weights
-                frame = self.engine.bgr_to_gray(torch.from_numpy(np.ascontiguousarray(frame)).to(dev))
-            else:
-                frame = torch.from_numpy(np.ascontiguousarray(frame)).to(dev)
-            frames.append(frame)
-        self._frames = torch.stack(frames) if frames else torch.empty((0, self.height, self.width), dtype=torch.uint8,
-                                                                      device=dev)
+            pending.append(np.asarray(frame))
+            total += 1
+            if total > self.max_stream_frames:
+                raise RuntimeError("the capture delivered more than max_stream_frames = %d frames: an endless source? "
+                                   "(live sources: respmon_b200.live.LiveFleet)" % self.max_stream_frames)
+            if len(pending) == 64:
+                flush()
+        flush()
+        self._frames = torch.cat(blocks) if blocks else torch.empty((0, self.height, self.width), dtype=torch.uint8,
+                                                                    device=dev)
 
     def next_frame(self):
         """The next gray frame as float64 in [0,1] (base.py:227-233), or False at the end of the stream."""

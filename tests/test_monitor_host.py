@@ -89,7 +89,10 @@ class OracleEngine:
 
     def bgr_to_gray(self, bgr):
         import cv2
-        return torch.from_numpy(cv2.cvtColor(bgr.numpy(), cv2.COLOR_BGR2GRAY))
+        a = bgr.numpy()
+        if a.ndim == 3:
+            return torch.from_numpy(cv2.cvtColor(a, cv2.COLOR_BGR2GRAY))
+        return torch.from_numpy(np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in a]))
 
 
 @pytest.fixture
@@ -226,3 +229,39 @@ def test_hyper_parameters_are_read_at_use_time(monitor_cls, golden):
     assert rm.engine is not first and rm.engine.params.threshold == 51
     with pytest.raises(ValueError, match="disagrees"):
         monitor_cls.locate(clip[1:129], 10, threshold=20, engine=rm.engine)
+
+
+def test_capture_objects_are_read_in_blocks_and_endless_sources_are_refused(monitor_cls, golden):
+    """A capture object delivering BGR frames (what cv2.VideoCapture yields, base.py:227-231) is read to its end in blocks
+    and gives the clip's result; a source that never ends is refused once max_stream_frames is passed, and an integer
+    capture_target (a webcam) is refused outright with a pointer to the live API."""
+    import cv2
+    fix = golden("qvga_s1")
+    spec, clip = clip_from_fixture(fix)
+
+    class Cap:
+        def __init__(self, frames, endless=False):
+            self.frames, self.i, self.endless = frames, 0, endless
+
+        def get(self, prop):
+            return {5: 10.0, 3: float(self.frames.shape[2]), 4: float(self.frames.shape[1])}.get(prop, 0.0)
+
+        def isOpened(self):
+            return True
+
+        def read(self):
+            if self.i >= len(self.frames) and not self.endless:
+                return False, None
+            g = self.frames[self.i % len(self.frames)]
+            self.i += 1
+            return True, cv2.cvtColor(g, cv2.COLOR_GRAY2BGR)
+
+        def release(self):
+            pass
+
+    rm = monitor_cls(Cap(clip), visualize=None, save_all_data=False, motion_extraction_method="flow", fps_limit=10)
+    _check(rm, fix)
+    endless = monitor_cls(Cap(clip[:4], endless=True), visualize=None, motion_extraction_method="flow", autorun=False)
+    endless.max_stream_frames = 300
+    with pytest.raises(RuntimeError, match="endless source"):
+        endless.run()
