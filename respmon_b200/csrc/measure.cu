@@ -329,9 +329,6 @@ __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1)
 // exactly representable integer and the float32 result IS the exact integer total: the callers test that first
 // (lk_sums_exact) and only walk the rows in order when a partial sum can actually round.
 __device__ __forceinline__ bool lk_sums_exact(unsigned lane_abs) {
-#ifdef LK_FORCE_EXACT   // timing experiment only: always the exact-total tier (results differ from OpenCV's)
-  return true;
-#endif
   return __reduce_add_sync(0xffffffffu, min(lane_abs, 1u << 24)) < (1u << 24);
 }
 struct LkAcc {     // one sum's accumulators

@@ -159,9 +159,11 @@ def test_temporal_bandpass_matches_oracle(eng, T, fps):
     assert np.array_equal(xd.cpu().numpy(), got)
 
 
-@pytest.mark.parametrize("name", ["vga_s0", "vga_s2", "qvga_s1", "odd_s3"])
-def test_calibration_heatmap_and_roi_match_golden(eng, golden, name):
+@pytest.mark.parametrize("sparse", [1, 0])
+@pytest.mark.parametrize("name", ["vga_s0", "vga_s2", "qvga_s1", "odd_s3", "qvga_long_s4"])
+def test_calibration_heatmap_and_roi_match_golden(eng, golden, name, sparse):
     fix = golden(name)
+    eng.set_option("temporal_sparse", sparse)
     spec, clip = clip_from_fixture(fix)
     clips = dev(clip[None, 1:129])
     lap = eng.pyramid_build(clips)
@@ -175,10 +177,11 @@ def test_calibration_heatmap_and_roi_match_golden(eng, golden, name):
     minmax = minmax.cpu().numpy()[0]
     assert abs(minmax[0] - fix["raw_min"]) <= 1e-9 and abs(minmax[1] - fix["raw_max"]) <= 1e-9
     assert abs(minmax[2] - fix["avg_min"]) <= 1e-9 and abs(minmax[3] - fix["avg_max"]) <= 1e-9
-    diff = heat.astype(int) - fix["heat_u8"].astype(int)
-    assert np.abs(diff).max() <= 1 and np.count_nonzero(diff) <= 8, (np.abs(diff).max(), np.count_nonzero(diff))
-    assert np.array_equal(heat > P.THRESHOLD, fix["heat_u8"] > P.THRESHOLD)
+    # byte for byte the reference's heat map (base.py:562-564), with either form of the band-pass: measured 0 differing
+    # bytes on every fixture (tools/heat_flips.py, profiles/r02p_heat_flips.txt), so no slack is granted
+    assert np.array_equal(heat, fix["heat_u8"]), "%d heat-map bytes differ" % int((heat != fix["heat_u8"]).sum())
     assert P.select_roi(heat) == tuple(int(v) for v in fix["roi"])
+    eng.set_option("temporal_sparse", 1)
 
 
 def test_calibration_batch_of_clips_matches_oracle(eng):
