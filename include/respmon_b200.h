@@ -35,7 +35,8 @@ typedef enum rm_status {
   RM_ERR_WORKSPACE = -4    /* workspace too small */
 } rm_status;
 
-typedef enum rm_dtype { RM_U8 = 0, RM_F32 = 1, RM_F64 = 2 } rm_dtype;
+typedef enum rm_dtype { RM_U8 = 0, RM_F32 = 1, RM_F64 = 2,
+                        RM_BGR8 = 3 /* 8-bit BGR frames (H, W, 3) as cv2.VideoCapture.read() yields them, base.py:228-230 */ } rm_dtype;
 
 /* per-clip outcome of the batch path; replaces the reference's state flips (base.py:249-253, 451-454, 543-545) */
 typedef enum rm_clip_status {
@@ -109,6 +110,14 @@ int32_t rm_synth_clips(rm_handle* h, const rm_clip_spec* specs, const int32_t* d
 /* ------------------------------------------------------------------ frame ingest */
 /* cv2.cvtColor(frame, COLOR_BGR2GRAY) of next_frame (base.py:230) on interleaved 8-bit BGR pixels. */
 int32_t rm_bgr_to_gray(rm_handle* h, const uint8_t* bgr, uint8_t* gray_out, int64_t n_pixels, void* stream);
+
+/* `cropped_image = current_frame[y:y+h, x:x+w]` (base.py:471) for a run of frames of every clip: frames (n_clips,T,H,W) of
+ * RM_U8, or (n_clips,T,H,W,3) of RM_BGR8 -- then cv2.cvtColor(BGR2GRAY) of next_frame (base.py:230) is applied to the ROI's
+ * pixels only --, roi (n_clips,4) x,y,w,h -> out (n_clips, n_frames, out_h, out_w) uint8, crops top-left aligned.  The
+ * measure entry points take `out` as their frames with ROI origin (0,0). */
+int32_t rm_crop_frames(rm_handle* h, const void* frames, int32_t dtype, int32_t n_clips, int32_t T, int32_t W, int32_t H,
+                       const int32_t* roi, int32_t first_frame, int32_t n_frames, uint8_t* out, int32_t out_w,
+                       int32_t out_h, void* stream);
 
 /* ------------------------------------------------------------------ single-level ops (API parity: pyramid.py) */
 /* uint8_to_float (transforms.py:20-23): u8 -> f64 * (1/255); f32 -> f64 widening. */

@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RESPMON_B200_LIB") or os.path.join(_PKG, "librespmon_b200.so")
 
 RM_OK = 0
-RM_U8, RM_F32, RM_F64 = 0, 1, 2
+RM_U8, RM_F32, RM_F64, RM_BGR8 = 0, 1, 2, 3
 CLIP_OK, CLIP_NO_ROI, CLIP_NO_CORNERS, CLIP_TRACK_LOST, CLIP_NO_PEAKS = range(5)
 CLIP_STATUS_NAMES = ("OK", "NO_ROI", "NO_CORNERS", "TRACK_LOST", "NO_PEAKS")
 
@@ -84,6 +84,7 @@ SIGNATURES = {
                                  _P, _P, _P, _sz, _S]),
     "rm_measure_signal_stream": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _i32, _i32, _i32, _f64, _P, _P, _P,
                                         _P, _P, _P, _P, _P, _P, _sz, _S]),
+    "rm_crop_frames": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _i32, _P, _i32, _i32, _P, _i32, _i32, _S]),
     "rm_crop_to_ring": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _P, _i32, _i32, _i32, _i32, _S]),
     "rm_pack_results": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _P, _S]),
     "rm_pack_results_stream": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _i32, _P, _S]),

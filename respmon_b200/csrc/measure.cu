@@ -681,7 +681,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_track_kernel(const MeasurePa
 // uint8 pyramid levels (cv2.buildOpticalFlowPyramid) are rebuilt in shared memory per frame.  Everything is addressed
 // by offsets into the one dynamic shared array (keeps the accesses LDS/STS), loops are division free, and the window
 // sums are reduced with REDUX (two 32-bit reductions per exact 64-bit sum).
+#ifndef LKS_WARPS
 #define LKS_WARPS 16
+#endif
 extern __shared__ __align__(16) unsigned char lks_smem[];
 
 struct LkSmemLayout {
@@ -933,7 +935,7 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
   return status;
 }
 
-__global__ void __launch_bounds__(LKS_WARPS * 32) lk_track_smem_kernel(const MeasureParams p, const float* pts0,
+__global__ void __launch_bounds__(LKS_WARPS * 32, 512 / (LKS_WARPS * 32)) lk_track_smem_kernel(const MeasureParams p, const float* pts0,
                                                                        int max_total) {
   const int clip = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1607,6 +1609,45 @@ __global__ void crop_to_ring_kernel(const uint8_t* __restrict__ frames, const in
     dst[r * ring_w + c] = src[(long long)r * W + c];
   }
 }
+// ROI crops of a run of frames as one contiguous gray tensor: frames (n_clips, T, H, W[, 3]) of dtype RM_U8 / RM_BGR8,
+// roi (n_clips, 4) -> out (n_clips, n_frames, out_h, out_w) holding frame[y:y+h, x:x+w] (base.py:471) top-left aligned.
+// For BGR frames cv2.cvtColor's fixed point (next_frame, base.py:230) is applied to the ROI's pixels only -- the measure
+// stage never needs the rest of the frame in gray.
+template <bool BGR>
+__global__ void crop_frames_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ roi,
+                                   uint8_t* __restrict__ out, int T, int first, int n_frames, int W, int H, int out_w,
+                                   int out_h) {
+  const int clip = blockIdx.y, j = blockIdx.x;
+  const int x = roi[clip * 4], y = roi[clip * 4 + 1], w = roi[clip * 4 + 2], hh = roi[clip * 4 + 3];
+  if (w < 1 || hh < 1 || x < 0 || y < 0 || x + w > W || y + hh > H || w > out_w || hh > out_h) return;
+  const int PX = BGR ? 3 : 1;
+  const uint8_t* src = frames + (((long long)clip * T + first + j) * W * H + (long long)y * W + x) * PX;
+  uint8_t* dst = out + ((long long)clip * n_frames + j) * out_w * out_h;
+  for (int i = threadIdx.x; i < w * hh; i += blockDim.x) {
+    const int r = i / w, c = i - r * w;
+    const uint8_t* px = src + ((long long)r * W + c) * PX;
+    dst[r * out_w + c] = BGR ? (uint8_t)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + (1u << 14)) >> 15) : px[0];
+  }
+}
+extern "C" int32_t rm_crop_frames(rm_handle* h, const void* frames, int32_t dtype, int32_t n_clips, int32_t T, int32_t W,
+                                  int32_t H, const int32_t* roi, int32_t first_frame, int32_t n_frames, uint8_t* out,
+                                  int32_t out_w, int32_t out_h, void* stream) {
+  RM_CHECK_ARG(h, h && frames && roi && out && n_clips >= 0 && first_frame >= 0 && n_frames >= 1 &&
+                      first_frame + n_frames <= T && out_w >= 1 && out_h >= 1, "bad argument");
+  RM_CHECK_ARG(h, dtype == RM_U8 || dtype == RM_BGR8, "frames must be RM_U8 or RM_BGR8");
+  if (n_clips == 0) return RM_OK;
+  DeviceGuard dg(h->device);
+  RM_PROF(h, (cudaStream_t)stream, "crop_frames_kernel");
+  if (dtype == RM_BGR8)
+    crop_frames_kernel<true><<<dim3(n_frames, n_clips), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)frames, roi, out, T,
+                                                                                        first_frame, n_frames, W, H, out_w, out_h);
+  else
+    crop_frames_kernel<false><<<dim3(n_frames, n_clips), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)frames, roi, out, T,
+                                                                                         first_frame, n_frames, W, H, out_w, out_h);
+  RM_LAUNCH_CHECK(h);
+  return RM_OK;
+}
+
 extern "C" int32_t rm_crop_to_ring(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t k, int32_t W, int32_t H,
                                    const int32_t* roi, uint8_t* ring, int32_t ring_len, int32_t ring_w, int32_t ring_h,
                                    int32_t f_first, void* stream) {

@@ -510,7 +510,7 @@ static int32_t pyramid_build_impl(rm_handle* h, const void* frames, int32_t dtyp
                                   int64_t seg_stride, int64_t seg_first, int32_t W, int32_t H, double* lap_out,
                                   void* workspace, size_t workspace_bytes, void* stream) {
   RM_CHECK_ARG(h, h && frames && lap_out && W >= 1 && H >= 1 && n_frames >= 0, "null pointer or bad size");
-  RM_CHECK_ARG(h, dtype == RM_U8 || dtype == RM_F32 || dtype == RM_F64, "unknown dtype");
+  RM_CHECK_ARG(h, dtype == RM_U8 || dtype == RM_F32 || dtype == RM_F64 || dtype == RM_BGR8, "unknown dtype");
   const int L = h->p.pyramid_levels, s = h->p.skip_levels_at_top;
   if (s < 1 || s > FRONT_MAX_STEPS || L - 1 <= s || L > RM_MAX_LEVELS)
     return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: fused path needs 1 <= skip <= 6 and skip < levels-1", __func__);
@@ -526,12 +526,15 @@ static int32_t pyramid_build_impl(rm_handle* h, const void* frames, int32_t dtyp
   RecordGeom rec = make_record(g, s);
   double* g_skip = reinterpret_cast<double*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
 
-  const bool integer_front = dtype == RM_U8 && !h->force_generic_front && pu_supported(frames, W, H, s);
+  const bool bgr = dtype == RM_BGR8;
+  if (bgr && !pu_supported(frames, W, H, s))
+    return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: BGR frames need W, H multiples of 8 and H >= 24 (else rm_bgr_to_gray first)", __func__);
+  const bool integer_front = bgr || (dtype == RM_U8 && !h->force_generic_front && pu_supported(frames, W, H, s));
   if (integer_front) {
-    if (pu_best_mode(h, frames, W, H))              // one kernel: the record is written, there is no tail launch
+    if (!bgr && pu_best_mode(h, frames, W, H))      // one kernel: the record is written, there is no tail launch
       return pu_launch_fused(h, (const uint8_t*)frames, lap_out, n_frames, seg_len, seg_stride, seg_first, W, H, st);
-    int32_t rc = pu_launch_front(h, (const uint8_t*)frames, reinterpret_cast<uint32_t*>(g_skip), n_frames, seg_len,
-                                 seg_stride, seg_first, W, H, st);
+    int32_t rc = pu_launch_front(h, (const uint8_t*)frames, bgr ? 1 : 0, reinterpret_cast<uint32_t*>(g_skip), n_frames,
+                                 seg_len, seg_stride, seg_first, W, H, st);
     if (rc != RM_OK) return rc;
   } else {
     const int elem = dtype == RM_U8 ? 1 : (dtype == RM_F32 ? 4 : 8);

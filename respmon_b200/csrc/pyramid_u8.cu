@@ -34,6 +34,7 @@
 #define PU_ROWS 8
 #define PU_STAGE_BYTES (PU_ROWS * 256)
 #define PU_FRONT_STAGES 4      // fallback kernel: cp.async ring depth
+#define PU_BGR_STAGES 3        // ... for BGR frames (a stage is three times as large)
 #define PU_FRONT_WARPS 24      // fallback kernel: warps per CTA (85 registers; 0.626 -> 0.569 ms per 8192 VGA frames, r02a)
 
 __device__ __forceinline__ void pu_cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -175,46 +176,67 @@ __device__ __forceinline__ void pu_clear(PuState& s) {
 
 // ==================================================================================================== fallback front
 // Level 3 (exact integers) to HBM; pyramid_tail_kernel (pyramid.cu) finishes.  Rows by cp.async, any W % 8 == 0.
-template <int WT, bool LEFT, bool RIGHT>
+// BGR = true: the frames are 8-bit BGR as cv2.VideoCapture delivers them (next_frame, base.py:227-231) and
+// cv2.cvtColor(frame, COLOR_BGR2GRAY) is folded into the load: a lane copies the 24 bytes of its 8 pixels per row and
+// converts them in registers with OpenCV's 15-bit fixed point, gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15 (the
+// weights split into byte halves so that two dp4a per pixel do the products) -- the frame is read once, 3 bytes per
+// pixel, instead of converted in a pass of its own (3 read + 1 written) and read again.
+__device__ __forceinline__ unsigned pu_gray_of(unsigned px) {      // px = (B, G, R, anything)
+  return (__dp4a(px, 0x00462397u, 16384u) + (__dp4a(px, 0x00264b0eu, 0u) << 8)) >> 15;   // lo (151, 35, 70), hi (14, 75, 38)
+}
+__device__ __forceinline__ uint2 pu_bgr24_to_gray8(uint2 a, uint2 b, uint2 c) {
+  // 24 bytes r0..r5 = 8 pixels of 3 bytes; pixel k starts at byte 3k
+  const unsigned r0 = a.x, r1 = a.y, r2 = b.x, r3 = b.y, r4 = c.x, r5 = c.y;
+  const unsigned g0 = pu_gray_of(r0), g1 = pu_gray_of(__byte_perm(r0, r1, 0x0543)), g2 = pu_gray_of(__byte_perm(r1, r2, 0x0432)),
+                 g3 = pu_gray_of(r2 >> 8);
+  const unsigned g4 = pu_gray_of(r3), g5 = pu_gray_of(__byte_perm(r3, r4, 0x0543)), g6 = pu_gray_of(__byte_perm(r4, r5, 0x0432)),
+                 g7 = pu_gray_of(r5 >> 8);
+  return make_uint2(g0 | (g1 << 8) | (g2 << 16) | (g3 << 24), g4 | (g5 << 8) | (g6 << 16) | (g7 << 24));
+}
+
+template <int WT, bool LEFT, bool RIGHT, bool BGR>
 __device__ __forceinline__ void pu_front_frame(const PuParams& p, const uint8_t* __restrict__ fsrc, uint32_t* __restrict__ g3,
                                                unsigned char* ring, int lane, int col, int store_lo, int store_hi) {
+  constexpr int PX = BGR ? 3 : 1;                       // bytes per pixel in the frame
+  constexpr int STAGES = BGR ? PU_BGR_STAGES : PU_FRONT_STAGES;
+  constexpr int ROWB = 256 * PX, STAGEB = PU_ROWS * ROWB;
   const int W = WT ? WT : p.W;        // a compile-time width turns the row offsets of the copies into immediates
   const int last_lane = store_hi;
   const bool in_img = col >= 0 && col < p.W3 && lane <= store_hi + PU_HALO_LANES;
-  const uint8_t* lsrc = fsrc + (in_img ? 8 * col : 0);
+  const uint8_t* lsrc = fsrc + (in_img ? 8 * PX * col : 0);
   const int src_bytes = in_img ? 8 : 0;
   const int nblk = p.H >> 3;
-  unsigned char* my = ring + lane * 8;
+  unsigned char* my = ring + lane * 8 * PX;
   auto issue = [&](int b) {
     if (b < nblk) {
-      unsigned char* dst = my + ((b + 2) & (PU_FRONT_STAGES - 1)) * PU_STAGE_BYTES;
-      if (b >= 0) {
-        const uint8_t* blk = lsrc + (long long)(8 * b) * W;
+      unsigned char* dst = my + ((b + 2) % STAGES) * STAGEB;
 #pragma unroll
-        for (int i = 0; i < PU_ROWS; ++i) pu_cp_async8(dst + i * 256, blk + i * W, src_bytes);
-      } else {
+      for (int i = 0; i < PU_ROWS; ++i) {
+        // rows above the frame (b < 0) are its mirrored rows
+        const uint8_t* row = lsrc + (long long)(b >= 0 ? 8 * b + i : -(8 * b + i)) * (W * PX);
 #pragma unroll
-        for (int i = 0; i < PU_ROWS; ++i)                      // mirrored rows above the frame
-          pu_cp_async8(dst + i * 256, lsrc + (long long)(-(8 * b + i)) * W, src_bytes);
+        for (int c = 0; c < PX; ++c) pu_cp_async8(dst + i * ROWB + 8 * c, row + 8 * c, src_bytes);
       }
     }
     pu_commit();
   };
   PuState s;
   pu_clear(s);
-  issue(-2);
-  issue(-1);
-  issue(0);
+#pragma unroll
+  for (int b = -2; b < STAGES - 3; ++b) issue(b);             // STAGES - 1 blocks in flight
   const bool storing = lane >= store_lo && lane <= store_hi;
   uint32_t* out = g3 + col;
 #pragma unroll 2
   for (int b = -2; b < nblk; ++b) {
-    issue(b + 3);
-    pu_wait<3>();                                              // block b has landed (3 younger groups may be in flight)
-    const unsigned char* src = my + ((b + 2) & (PU_FRONT_STAGES - 1)) * PU_STAGE_BYTES;
+    issue(b + STAGES - 1);
+    pu_wait<STAGES - 1>();                                     // block b has landed (STAGES - 1 younger groups may be in flight)
+    const unsigned char* src = my + ((b + 2) % STAGES) * STAGEB;
     uint2 w[PU_ROWS];
 #pragma unroll
-    for (int i = 0; i < PU_ROWS; ++i) w[i] = *reinterpret_cast<const uint2*>(src + i * 256);
+    for (int i = 0; i < PU_ROWS; ++i) {
+      const uint2* q = reinterpret_cast<const uint2*>(src + i * ROWB);
+      w[i] = BGR ? pu_bgr24_to_gray8(q[0], q[1], q[2]) : q[0];
+    }
     unsigned o;
     pu_block<LEFT, RIGHT>(s, w, lane, 0, last_lane, o);
     if (b >= 1 && storing) out[(long long)(b - 1) * p.W3] = o;
@@ -232,12 +254,12 @@ __device__ __forceinline__ long long pu_source_frame(long long frame, long long 
   return (long long)(fr / sl) * seg_stride + seg_first + (long long)(fr % sl);
 }
 
-template <int WT>
+template <int WT, bool BGR>
 __global__ void __launch_bounds__(PU_FRONT_WARPS * 32, 1) pyramid_front_u8_kernel(const PuParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = warp / p.n_strips, strip = warp - slot * p.n_strips;
-  unsigned char* ring = smem + (size_t)warp * PU_FRONT_STAGES * PU_STAGE_BYTES;
+  unsigned char* ring = smem + (size_t)warp * (BGR ? PU_BGR_STAGES * 3 : PU_FRONT_STAGES) * PU_STAGE_BYTES;
   const bool left = strip == 0, right = strip == p.n_strips - 1;
   const int c0 = strip * p.cols_per_strip;
   const int c1 = min(p.W3, c0 + p.cols_per_strip);
@@ -254,10 +276,10 @@ __global__ void __launch_bounds__(PU_FRONT_WARPS * 32, 1) pyramid_front_u8_kerne
     // strips are cheaper) until a halo sector read by one warp has left L2 before its neighbour asks for it -- 23 % extra
     // DRAM reads at 8192 frames per launch (ncu, profiles/r01g).  A named barrier per slot re-aligns them every frame.
     if (p.n_strips > 1) asm volatile("bar.sync %0, %1;\n" ::"r"(slot + 1), "r"(p.n_strips * 32) : "memory");
-    if (left && right) pu_front_frame<WT, true, true>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
-    else if (left) pu_front_frame<WT, true, false>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
-    else if (right) pu_front_frame<WT, false, true>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
-    else pu_front_frame<WT, false, false>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
+    if (left && right) pu_front_frame<WT, true, true, BGR>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
+    else if (left) pu_front_frame<WT, true, false, BGR>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
+    else if (right) pu_front_frame<WT, false, true, BGR>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
+    else pu_front_frame<WT, false, false, BGR>(p, fsrc, g3, ring, lane, col, store_lo, store_hi);
   }
 }
 
@@ -616,11 +638,11 @@ int32_t pu_launch_fused(rm_handle* h, const uint8_t* frames, double* lap_out, lo
   return pf_launch_cfg<2, 24>(h, pl, map, ctas, st);
 }
 
-int32_t pu_launch_front(rm_handle* h, const uint8_t* frames, uint32_t* g3, long long n_frames, long long seg_len,
+int32_t pu_launch_front(rm_handle* h, const uint8_t* frames, int bgr, uint32_t* g3, long long n_frames, long long seg_len,
                         long long seg_stride, long long seg_first, int W, int H, cudaStream_t st) {
   PuParams p;
   memset(&p, 0, sizeof(p));
-  p.frames = frames; p.g3 = g3; p.n_frames = n_frames; p.frame_elems = (long long)W * H;
+  p.frames = frames; p.g3 = g3; p.n_frames = n_frames; p.frame_elems = (long long)W * H * (bgr ? 3 : 1);
   p.seg_len = seg_len; p.seg_stride = seg_stride; p.seg_first = seg_first;
   p.W = W; p.H = H; p.W3 = W / 8; p.H3 = H / 8;
   const int cap = 32 - 2 * PU_HALO_LANES;                       // payload lanes of an interior strip
@@ -629,18 +651,26 @@ int32_t pu_launch_front(rm_handle* h, const uint8_t* frames, uint32_t* g3, long 
   if (p.n_strips > 16) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: frame wider than 3584 pixels", __func__);
   if (n_frames >= (1ll << 31) || seg_len >= (1ll << 31) || seg_len < 1)
     return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: more than 2^31 frames", __func__);
-  p.frames_per_cta = PU_FRONT_WARPS / p.n_strips;
+  const int ring_per_warp = (bgr ? PU_BGR_STAGES * 3 : PU_FRONT_STAGES) * PU_STAGE_BYTES;
+  int max_warps = PU_FRONT_WARPS;
+  if (max_warps * ring_per_warp > h->smem_optin) max_warps = h->smem_optin / ring_per_warp;
+  p.frames_per_cta = max_warps / p.n_strips;
   if (p.frames_per_cta > 15) p.frames_per_cta = 15;             // named barriers 1..15
+  if (p.frames_per_cta < 1) return rm_fail(h, RM_ERR_UNSUPPORTED, "%s: frame too wide for the BGR ring", __func__);
   const int warps = p.frames_per_cta * p.n_strips;
-  const int smem = warps * PU_FRONT_STAGES * PU_STAGE_BYTES;
-  void (*kern)(const PuParams) = W == 640 ? pyramid_front_u8_kernel<640>
-                                 : W == 1280 ? pyramid_front_u8_kernel<1280>
-                                 : W == 1920 ? pyramid_front_u8_kernel<1920>
-                                 : W == 320 ? pyramid_front_u8_kernel<320> : pyramid_front_u8_kernel<0>;
+  const int smem = warps * ring_per_warp;
+  void (*kern)(const PuParams);
+  if (bgr)
+    kern = W == 640 ? pyramid_front_u8_kernel<640, true> : W == 1280 ? pyramid_front_u8_kernel<1280, true>
+           : W == 1920 ? pyramid_front_u8_kernel<1920, true> : pyramid_front_u8_kernel<0, true>;
+  else
+    kern = W == 640 ? pyramid_front_u8_kernel<640, false> : W == 1280 ? pyramid_front_u8_kernel<1280, false>
+           : W == 1920 ? pyramid_front_u8_kernel<1920, false>
+           : W == 320 ? pyramid_front_u8_kernel<320, false> : pyramid_front_u8_kernel<0, false>;
   RM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   long long ctas = (n_frames + p.frames_per_cta - 1) / p.frames_per_cta;
   if (ctas > h->sm_count) ctas = h->sm_count;
-  RM_PROF(h, st, "pyramid_front_u8_kernel");
+  RM_PROF(h, st, bgr ? "pyramid_front_bgr_kernel" : "pyramid_front_u8_kernel");
   kern<<<(unsigned)ctas, warps * 32, smem, st>>>(p);
   RM_LAUNCH_CHECK(h);
   return RM_OK;

@@ -40,5 +40,5 @@ bool pu_supported(const void* frames, int W, int H, int skip);
 int pu_best_mode(rm_handle* h, const void* frames, int W, int H);
 int32_t pu_launch_fused(rm_handle* h, const uint8_t* frames, double* lap_out, long long n_frames, long long seg_len,
                         long long seg_stride, long long seg_first, int W, int H, cudaStream_t st);
-int32_t pu_launch_front(rm_handle* h, const uint8_t* frames, uint32_t* g3, long long n_frames, long long seg_len,
+int32_t pu_launch_front(rm_handle* h, const uint8_t* frames, int bgr, uint32_t* g3, long long n_frames, long long seg_len,
                         long long seg_stride, long long seg_first, int W, int H, cudaStream_t st);

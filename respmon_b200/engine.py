@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import RM_F32, RM_F64, RM_U8, RmParams, check
+from ._cabi import RM_BGR8, RM_F32, RM_F64, RM_U8, RmParams, check
 
 _DTYPES = {torch.uint8: RM_U8, torch.float32: RM_F32, torch.float64: RM_F64}
 
@@ -217,21 +217,25 @@ class Engine:
         return heat, minmax
 
     def pyramid_build_clips(self, clips: torch.Tensor, first: int, length: int) -> torch.Tensor:
-        """Packed Laplacian records of frames [first, first+length) of every clip of (n,T,H,W), read in place."""
-        assert clips.is_cuda and clips.is_contiguous() and clips.dtype in _DTYPES and clips.dim() == 4
-        n, T, H, W = clips.shape
+        """Packed Laplacian records of frames [first, first+length) of every clip of (n,T,H,W), read in place.
+        (n,T,H,W,3) uint8 = BGR frames as a capture delivers them: the colour conversion of next_frame (base.py:230) is
+        folded into the pyramid kernel's load (RM_BGR8)."""
+        assert clips.is_cuda and clips.is_contiguous() and clips.dtype in _DTYPES
+        bgr = clips.dim() == 5 and clips.shape[-1] == 3 and clips.dtype == torch.uint8
+        assert clips.dim() == 4 or bgr
+        n, T, H, W = clips.shape[:4]
         rec = self.record_len(W, H)
         out = torch.empty((n, length, rec), dtype=torch.float64, device=self.device)
         need = C.c_size_t()
         self._call("rm_pyramid_workspace_bytes", W, H, n * length, C.byref(need))
         ws = self._workspace("pyr", need.value)
-        self._call("rm_pyramid_build_clips", _ptr(clips), _DTYPES[clips.dtype], n, T, first, length, W, H, _ptr(out),
-                   _ptr(ws), ws.numel(), self._stream())
+        self._call("rm_pyramid_build_clips", _ptr(clips), RM_BGR8 if bgr else _DTYPES[clips.dtype], n, T, first, length,
+                   W, H, _ptr(out), _ptr(ws), ws.numel(), self._stream())
         return out
 
     def calibrate_heatmaps(self, clips: torch.Tensor, fps: float, first: int = 0, length: int | None = None):
         """clips (n_clips, T, H, W) -> heat maps of frames [first, first+length); the calibration kernels back to back."""
-        n, T, H, W = clips.shape
+        n, T, H, W = clips.shape[:4]
         length = T - first if length is None else length
         lap = self.pyramid_build_clips(clips, first, length)
         self.temporal_bandpass(lap, fps, out=lap)
@@ -301,6 +305,25 @@ class Engine:
         finally:
             self._ws_tag = ""
         return tuple(torch.cat([o[k] for o in outs]) for k in range(3))
+
+    def crop_frames(self, clips: torch.Tensor, roi: torch.Tensor, first: int, n_frames: int,
+                    out_size: tuple[int, int] | None = None) -> torch.Tensor:
+        """`frame[y:y+h, x:x+w]` (base.py:471) of frames [first, first+n_frames) of every clip -> (n, n_frames, out_h, out_w)
+        uint8, top-left aligned.  clips (n,T,H,W) gray or (n,T,H,W,3) BGR (converted like next_frame, base.py:230, on the
+        ROI's pixels only); roi (n,4) x,y,w,h.  out_size (w, h) defaults to the largest ROI (one small D2H read)."""
+        assert clips.is_cuda and clips.is_contiguous() and clips.dtype == torch.uint8
+        bgr = clips.dim() == 5 and clips.shape[-1] == 3
+        assert clips.dim() == 4 or bgr
+        n, T, H, W = clips.shape[:4]
+        roi = roi.to(self.device, torch.int32).contiguous()
+        if out_size is None:
+            r = roi.cpu()
+            out_size = (max(1, int(r[:, 2].max())), max(1, int(r[:, 3].max()))) if n else (1, 1)
+        ow, oh = out_size
+        out = torch.zeros((n, n_frames, oh, ow), dtype=torch.uint8, device=self.device)
+        self._call("rm_crop_frames", _ptr(clips), RM_BGR8 if bgr else RM_U8, n, T, W, H, _ptr(roi), first, n_frames, _ptr(out),
+                   ow, oh, self._stream())
+        return out
 
     # ------------------------------------------------------------------ whole clips
     def run_batch(self, clips: torch.Tensor, fps: float, cal_first: int = 1, cal_len: int = 128,

@@ -283,12 +283,11 @@ class RespiratoryMonitor:
         blocks, pending, total = [], [], 0
 
         def flush():
+            # BGR frames stay BGR on the device: the pyramid kernel converts while it loads the calibration frames and the
+            # measure stage converts the ROI's pixels only -- there is no colour-conversion pass over the frames
             if not pending:
                 return
-            block = torch.from_numpy(np.ascontiguousarray(np.stack(pending))).to(dev)
-            if block.dim() == 4:                        # BGR -> gray with cv2.cvtColor's fixed-point weights (base.py:230)
-                block = self.engine.bgr_to_gray(block)
-            blocks.append(block)
+            blocks.append(torch.from_numpy(np.ascontiguousarray(np.stack(pending))).to(dev))
             pending.clear()
 
         while self.cap.isOpened():
@@ -308,13 +307,17 @@ class RespiratoryMonitor:
         self._frames = torch.cat(blocks) if blocks else torch.empty((0, self.height, self.width), dtype=torch.uint8,
                                                                     device=dev)
 
+    def _gray(self, frames):
+        """(k,H,W) gray frames of a (k,H,W[,3]) slice of the stream (cv2.cvtColor's fixed point for BGR, base.py:230)."""
+        return self.engine.bgr_to_gray(frames.contiguous()) if frames.dim() == 4 else frames
+
     def next_frame(self):
         """The next gray frame as float64 in [0,1] (base.py:227-233), or False at the end of the stream."""
         self._drain()
         if self._pos >= self._frames.shape[0]:
             return False
         self._pos += 1
-        return self._frames[self._pos - 1].cpu().numpy() * (1.0 / 255)
+        return self._gray(self._frames[self._pos - 1:self._pos])[0].cpu().numpy() * (1.0 / 255)
 
     # ------------------------------------------------------------------ reference methods
     def skip_calibration(self, x, y, w, h):
@@ -389,6 +392,8 @@ class RespiratoryMonitor:
         vid = vid.to(eng.device)
         if vid.dtype not in (torch.uint8, torch.float32, torch.float64):
             raise TypeError("calibration_video_data must be uint8 / float32 / float64")
+        if vid.dim() == 4 and not (vid.dtype == torch.uint8 and vid.shape[-1] == 3):
+            raise TypeError("4-D calibration_video_data must be (T,H,W,3) uint8 BGR frames")
         roi, status, heat = eng.locate(vid[None].contiguous(), float(fps))
         if verbose:
             print("roi", roi.cpu().numpy()[0], "status", int(status[0]))
@@ -397,7 +402,8 @@ class RespiratoryMonitor:
         box = tuple(int(v) for v in roi[0].cpu())
         if save_calibration_image:
             _log.info("Creating calibration image.")
-            mosaic = calibration_mosaic(eng, vid, float(fps), heat[0], box, int(eng.params.threshold))
+            gray = eng.bgr_to_gray(vid.contiguous()) if vid.dim() == 4 else vid      # the diagnostic panels want gray frames
+            mosaic = calibration_mosaic(eng, gray, float(fps), heat[0], box, int(eng.params.threshold))
             import cv2   # file output and drawing only; the panels themselves are computed on the device
             i = 0
             while os.path.exists("calibration%s.png" % i):       # base.py:593-595
@@ -452,6 +458,11 @@ class RespiratoryMonitor:
         n = frames.shape[0]
         roi = torch.tensor([[self.x, self.y, self.w, self.h]], dtype=torch.int32, device=eng.device)
         clips = frames[None].contiguous() if not frames.is_contiguous() else frames[None]
+        if frames.dim() == 4:
+            # BGR stream: only the ROI's pixels are ever needed in gray (base.py:471 crops before anything else looks at
+            # the frame) -- crop + convert them, then measure on the crops with the ROI at their origin
+            clips = eng.crop_frames(clips, roi, 0, n, out_size=(self.w, self.h))
+            roi = torch.tensor([[0, 0, self.w, self.h]], dtype=torch.int32, device=eng.device)
         out = {}
         if self.motion_extraction_method == "flow":
             m = eng.measure_flow(clips, roi, 0, n, max_roi=(self.w, self.h))

@@ -62,8 +62,38 @@ def test_monitor_accepts_a_capture_object_with_bgr_frames(golden):
         def release(self):
             pass
 
-    rm = RespiratoryMonitor(Cap(), visualize=None, save_all_data=False, motion_extraction_method="flow")
+    rm = RespiratoryMonitor(Cap(), visualize=None, save_all_data=False, motion_extraction_method="flow", autorun=False)
+    rm.engine.profile(True)
+    rm.run()
     _check(rm, fix)
+    # frame ingest is fused: the BGR frames are converted inside the pyramid kernel's load and, for the measure stage, on
+    # the ROI's pixels only -- no colour-conversion pass over the frames
+    launched = set(rm.engine.profile_report())
+    assert "bgr_to_gray_kernel" not in launched
+    assert "pyramid_front_bgr_kernel" in launched and "crop_frames_kernel" in launched
+
+
+def test_bgr_ingest_is_bit_identical_to_convert_then_gray(golden):
+    """Colour frames: the BGR-fused pyramid load (RM_BGR8) and the BGR crop give exactly what cv2.cvtColor followed by the
+    gray paths give -- on random colours, for frame windows of clips, at a one-strip and a three-strip width."""
+    import cv2
+    from respmon_b200.engine import Engine
+    eng = Engine(0)
+    rng = np.random.default_rng(11)
+    for (w, h, n, T) in ((640, 480, 3, 6), (160, 120, 5, 5), (328, 72, 2, 4)):
+        bgr = rng.integers(0, 256, (n, T, h, w, 3)).astype(np.uint8)
+        bgr[0, 1] = 255
+        gray = np.stack([[cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in c] for c in bgr])
+        d_bgr, d_gray = torch.from_numpy(bgr).cuda(), torch.from_numpy(gray).cuda()
+        assert torch.equal(eng.bgr_to_gray(d_bgr), d_gray)
+        a = eng.pyramid_build_clips(d_bgr, 1, T - 1)
+        b = eng.pyramid_build_clips(d_gray, 1, T - 1)
+        assert torch.equal(a, b), (w, h, int((a != b).sum()))
+        roi = torch.tensor([[5, 7, 40, 30]] * n, dtype=torch.int32)
+        ca = eng.crop_frames(d_bgr, roi, 1, T - 1)
+        cb = eng.crop_frames(d_gray, roi, 1, T - 1)
+        assert torch.equal(ca, cb) and np.array_equal(cb.cpu().numpy(), gray[:, 1:, 7:37, 5:45])
+    eng.close()
 
 
 def test_bgr_to_gray_matches_cv2():

@@ -33,6 +33,9 @@ class OracleEngine:
         rois, status = [], []
         for clip in clips:
             vid = clip.numpy()
+            if vid.ndim == 4:                                     # BGR frames: next_frame's cv2.cvtColor (base.py:230)
+                import cv2
+                vid = np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in vid])
             vid = P.u8_to_unit(vid) if vid.dtype == np.uint8 else vid.astype(np.float64)
             box = P.locate(vid, fps, threshold=self.params.threshold)
             rois.append(box if box is not None else (0, 0, 0, 0))
@@ -86,6 +89,14 @@ class OracleEngine:
 
     def close(self):
         pass
+
+    def crop_frames(self, clips, roi, first, n_frames, out_size=None):
+        import cv2
+        x, y, w, h = (int(v) for v in roi[0])
+        a = clips[0, first:first + n_frames].numpy()
+        if a.ndim == 4:
+            a = np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in a])
+        return torch.from_numpy(np.ascontiguousarray(a[None, :, y:y + h, x:x + w]))
 
     def bgr_to_gray(self, bgr):
         import cv2
