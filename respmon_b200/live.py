@@ -203,6 +203,8 @@ class LiveFleet:
     Per camera the frames reach the kernels exactly as RespiratoryMonitor.run() routes them, whatever the block sizes of
     push() (tests/test_gpu_live.py compares the two on a clip whose texture vanishes mid-way)."""
 
+    cohort_cls = None      # the class of the cohorts a fleet creates (LiveCohort; the CPU tests substitute an oracle-backed one)
+
     def __init__(self, width: int, height: int, fps: float = 10.0, device: int | None = None,
                  error_reset_delay: float = 10.0, cap: int = 65536, ring_len: int = 33, cal_len: int = 128, **hyper):
         self.W, self.H, self.fps, self.device = int(width), int(height), float(fps), device
@@ -231,8 +233,9 @@ class LiveFleet:
                 self.cohorts.remove(co)
 
     def _new_cohort(self, ids, start_state):
-        live = LiveCohort(len(ids), self.W, self.H, self.fps, device=self.device, cap=self.cap, ring_len=self.ring_len,
-                          cal_len=self.cal_len, start_state=start_state, **self.hyper)
+        live = (self.cohort_cls or LiveCohort)(len(ids), self.W, self.H, self.fps, device=self.device, cap=self.cap,
+                                               ring_len=self.ring_len, cal_len=self.cal_len, start_state=start_state,
+                                               **self.hyper)
         co = dict(live=live, members=list(ids))
         self.cohorts.append(co)
         for slot, cid in enumerate(ids):
@@ -247,7 +250,10 @@ class LiveFleet:
         ids = list(self.cams) if ids is None else list(ids)
         f = torch.from_numpy(frames) if isinstance(frames, np.ndarray) else frames
         assert f.dim() == 4 and f.shape[0] == len(ids) and tuple(f.shape[2:]) == (self.H, self.W) and f.dtype == torch.uint8
-        dev = torch.device("cuda", torch.cuda.current_device() if self.device is None else int(self.device))
+        if self.cohort_cls is None:
+            dev = torch.device("cuda", torch.cuda.current_device() if self.device is None else int(self.device))
+        else:
+            dev = f.device                                         # substituted cohorts say where their frames live
         f = f.to(dev, non_blocking=True)
         k = f.shape[1]
         row = {cid: i for i, cid in enumerate(ids)}
