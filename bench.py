@@ -553,23 +553,38 @@ def run_config_arm(args) -> dict | None:
     local_rec = torch.zeros((cap, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     gathered = torch.empty((world * cap, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
 
+    ragged_engine = per_class[0]["eng"] if len(per_class) > 1 else None
+    mixed_rec = {}
+
     def step():
         cur = torch.cuda.current_stream(dev)
-        fork = torch.cuda.Event()
-        fork.record(cur)
-        pos = 0
-        for c in per_class:
-            c["stream"].wait_event(fork)
-            with torch.cuda.stream(c["stream"]):
-                lo = 0
-                for ch in c["chunks"]:
-                    c["eng"].run_batch(ch, FPS, out=c["rec"][lo:lo + ch.shape[0]])
-                    lo += ch.shape[0]
-                local_rec[pos:pos + len(c["idx"])].copy_(c["rec"], non_blocking=True)
-            pos += len(c["idx"])
-            done = torch.cuda.Event()
-            done.record(c["stream"])
-            cur.wait_event(done)
+        if ragged_engine is not None and not args.per_class_measure:
+            # mixed resolutions: calibration per class, ONE ragged crop launch (rm_clip_desc) and ONE measure stage over all
+            # classes -- chunk by chunk (a chunk holds its share of every class)
+            pos = 0
+            n_chunks = max(len(c["chunks"]) for c in per_class)
+            for k in range(n_chunks):
+                group = [c["chunks"][k] for c in per_class if k < len(c["chunks"])]
+                rec = ragged_engine.run_mixed(group, FPS)
+                mixed_rec[k] = rec
+                local_rec[pos:pos + rec.shape[0]].copy_(rec, non_blocking=True)
+                pos += rec.shape[0]
+        else:
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            pos = 0
+            for c in per_class:
+                c["stream"].wait_event(fork)
+                with torch.cuda.stream(c["stream"]):
+                    lo = 0
+                    for ch in c["chunks"]:
+                        c["eng"].run_batch(ch, FPS, out=c["rec"][lo:lo + ch.shape[0]])
+                        lo += ch.shape[0]
+                    local_rec[pos:pos + len(c["idx"])].copy_(c["rec"], non_blocking=True)
+                pos += len(c["idx"])
+                done = torch.cuda.Event()
+                done.record(c["stream"])
+                cur.wait_event(done)
         if world > 1:
             dist.all_gather_into_tensor(gathered, local_rec)
             return gathered
@@ -614,12 +629,20 @@ def run_config_arm(args) -> dict | None:
     # records by global clip index
     allrec = out.cpu().numpy().view(RESULT_DTYPE).reshape(world, cap) if world > 1 else out.cpu().numpy().view(RESULT_DTYPE).reshape(1, cap)
     by_clip = {}
+    ragged = len(classes) > 1 and not args.per_class_measure
     for r in range(world):
-        pos = 0
-        for (w, h) in classes:
-            for i in [i for i in owners[r] if shapes[i] == (T, h, w)]:
-                by_clip[i] = allrec[r, pos]
-                pos += 1
+        per = [[i for i in owners[r] if shapes[i] == (T, h, w)] for (w, h) in classes]
+        per = [p_ for p_ in per if p_]
+        order = []
+        if ragged:                                 # chunk-major: chunk k holds clips [k*chunk, (k+1)*chunk) of every class
+            for k in range(max((len(p_) + args.chunk - 1) // args.chunk for p_ in per)):
+                for p_ in per:
+                    order += p_[k * args.chunk:(k + 1) * args.chunk]
+        else:
+            for p_ in per:
+                order += p_
+        for pos, i in enumerate(order):
+            by_clip[i] = allrec[r, pos]
     if world > 1:
         dist.destroy_process_group()
     sys.stdout.flush()
@@ -657,8 +680,10 @@ def run_config_arm(args) -> dict | None:
                    "pixel_rate_Gpx_per_s": pixels_per_step / (ms_per_step / 1e3) / 1e9, "chunk_clips": args.chunk,
                    "input_dtype": "u8", "l2": "clips resident in HBM, %.1f GB per GPU > 126 MB L2 (no flush needed)"
                                                % (sum(ch.numel() for c in per_class for ch in c["chunks"]) / 1e9),
-                   "parallelism": "clips balanced over %d GPU(s) by pixels, one stream + handle per resolution class, one "
-                                  "all-gather of 32 B result records" % world},
+                   "parallelism": ("clips balanced over %d GPU(s) by pixels; " % world) + (
+                       "calibration per resolution class, one ragged crop launch (rm_clip_desc) and ONE measure stage over "
+                       "all classes" if ragged else "one stream + handle per resolution class") +
+                       "; one all-gather of 32 B result records"},
         "gpu_launches": int(launches), "clocks": clocks,
         "parity": {"clips_checked_against_cpu_oracle": len(ref), "roi_identical": roi_equal,
                    "max_abs_bpm_diff": max(bpm_err) if bpm_err else None, "sample": sample},
@@ -677,6 +702,8 @@ def main():
     ap.add_argument("--config", type=int, default=None, choices=[4, 5],
                     help="run BASELINE config 4 or 5 at its stated size instead of the headline workload")
     ap.add_argument("--parity-clips", type=int, default=16, help="--config: clips re-run through the CPU oracle")
+    ap.add_argument("--per-class-measure", action="store_true",
+                    help="--config 5: one measure stage per resolution class on its own stream instead of one over all classes")
     ap.add_argument("--chunk", type=int, default=32, help="clips per H2D chunk of the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -119,6 +119,23 @@ int32_t rm_crop_frames(rm_handle* h, const void* frames, int32_t dtype, int32_t 
                        const int32_t* roi, int32_t first_frame, int32_t n_frames, uint8_t* out, int32_t out_w,
                        int32_t out_h, void* stream);
 
+/* Ragged batches (BASELINE config 5): one descriptor per clip.  `frame_offset` = byte offset of the clip's first
+ * frame from `base` (base may be NULL: then it is the absolute device address), `row_stride` = bytes between rows
+ * (W for packed gray frames, 3 W for packed BGR).  Clips of any mix of resolutions go through ONE launch; the descriptor
+ * table lives in device memory. */
+typedef struct rm_clip_desc {
+  int64_t frame_offset;
+  int32_t W, H, T, row_stride;
+} rm_clip_desc;
+
+/* rm_crop_frames over a ragged batch: out (n_clips, n_frames, out_h, out_w) gets frame[y:y+h, x:x+w] (base.py:471) of
+ * frames [first_frame, first_frame+n_frames) of every clip, whatever its resolution; roi (n_clips,4) in each clip's own
+ * frame coordinates.  With the crops in one tensor the measure stage (rm_measure_signal, ROI origin 0,0) runs once over
+ * all resolution classes. */
+int32_t rm_crop_frames_ragged(rm_handle* h, const void* base, int32_t dtype, const rm_clip_desc* descs, int32_t n_clips,
+                              const int32_t* roi, int32_t first_frame, int32_t n_frames, uint8_t* out, int32_t out_w,
+                              int32_t out_h, void* stream);
+
 /* ------------------------------------------------------------------ single-level ops (API parity: pyramid.py) */
 /* uint8_to_float (transforms.py:20-23): u8 -> f64 * (1/255); f32 -> f64 widening. */
 int32_t rm_to_f64(rm_handle* h, const void* src, int32_t dtype, double* dst, int64_t n, void* stream);

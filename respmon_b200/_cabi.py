@@ -36,6 +36,11 @@ class RmResult(C.Structure):
                 ("status", C.c_int32), ("n_peaks", C.c_int32)]
 
 
+class RmClipDesc(C.Structure):
+    """rm_clip_desc (include/respmon_b200.h): one clip of a ragged batch."""
+    _fields_ = [("frame_offset", C.c_int64), ("W", C.c_int32), ("H", C.c_int32), ("T", C.c_int32), ("row_stride", C.c_int32)]
+
+
 class RmClipSpec(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("n_frames", C.c_int32), ("seed", C.c_int32),
                 ("x0", C.c_int32), ("y0", C.c_int32), ("w0", C.c_int32), ("h0", C.c_int32)]
@@ -85,6 +90,7 @@ SIGNATURES = {
     "rm_measure_signal_stream": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _i32, _i32, _i32, _f64, _P, _P, _P,
                                         _P, _P, _P, _P, _P, _P, _sz, _S]),
     "rm_crop_frames": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _i32, _P, _i32, _i32, _P, _i32, _i32, _S]),
+    "rm_crop_frames_ragged": (_i32, [_H, _P, _i32, _P, _i32, _P, _i32, _i32, _P, _i32, _i32, _S]),
     "rm_crop_to_ring": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _P, _i32, _i32, _i32, _i32, _S]),
     "rm_pack_results": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _P, _S]),
     "rm_pack_results_stream": (_i32, [_H, _P, _P, _P, _P, _i32, _i32, _i32, _P, _S]),

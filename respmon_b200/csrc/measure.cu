@@ -1648,6 +1648,46 @@ extern "C" int32_t rm_crop_frames(rm_handle* h, const void* frames, int32_t dtyp
   return RM_OK;
 }
 
+// The same for a RAGGED batch (BASELINE config 5: clips of different resolutions in one batch): every clip is described by
+// an rm_clip_desc -- where its first frame lies, its frame size, its length, its row pitch -- and one launch crops the ROIs
+// of all clips, whatever their resolution class, into one (n_clips, n_frames, out_h, out_w) tensor.  From there on the
+// measure stage is a single batch: one tracker / PCA / filter / fit pipeline over all classes.
+template <bool BGR>
+__global__ void crop_frames_ragged_kernel(const uint8_t* __restrict__ base, const rm_clip_desc* __restrict__ descs,
+                                          const int32_t* __restrict__ roi, uint8_t* __restrict__ out, int first,
+                                          int n_frames, int out_w, int out_h) {
+  const int clip = blockIdx.y, j = blockIdx.x;
+  const rm_clip_desc d = descs[clip];
+  const int x = roi[clip * 4], y = roi[clip * 4 + 1], w = roi[clip * 4 + 2], hh = roi[clip * 4 + 3];
+  if (w < 1 || hh < 1 || x < 0 || y < 0 || x + w > d.W || y + hh > d.H || w > out_w || hh > out_h || first + j >= d.T) return;
+  const int PX = BGR ? 3 : 1;
+  const uint8_t* src = base + d.frame_offset + ((long long)(first + j) * d.H + y) * d.row_stride + (long long)x * PX;
+  uint8_t* dst = out + ((long long)clip * n_frames + j) * out_w * out_h;
+  for (int i = threadIdx.x; i < w * hh; i += blockDim.x) {
+    const int r = i / w, c = i - r * w;
+    const uint8_t* px = src + (long long)r * d.row_stride + c * PX;
+    dst[r * out_w + c] = BGR ? (uint8_t)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + (1u << 14)) >> 15) : px[0];
+  }
+}
+extern "C" int32_t rm_crop_frames_ragged(rm_handle* h, const void* base, int32_t dtype, const rm_clip_desc* descs,
+                                         int32_t n_clips, const int32_t* roi, int32_t first_frame, int32_t n_frames,
+                                         uint8_t* out, int32_t out_w, int32_t out_h, void* stream) {
+  RM_CHECK_ARG(h, h && descs && roi && out && n_clips >= 0 && first_frame >= 0 && n_frames >= 1 && out_w >= 1 && out_h >= 1,
+               "bad argument");
+  RM_CHECK_ARG(h, dtype == RM_U8 || dtype == RM_BGR8, "frames must be RM_U8 or RM_BGR8");
+  if (n_clips == 0) return RM_OK;
+  DeviceGuard dg(h->device);
+  RM_PROF(h, (cudaStream_t)stream, "crop_frames_ragged_kernel");
+  if (dtype == RM_BGR8)
+    crop_frames_ragged_kernel<true><<<dim3(n_frames, n_clips), 256, 0, (cudaStream_t)stream>>>(
+        (const uint8_t*)base, descs, roi, out, first_frame, n_frames, out_w, out_h);
+  else
+    crop_frames_ragged_kernel<false><<<dim3(n_frames, n_clips), 256, 0, (cudaStream_t)stream>>>(
+        (const uint8_t*)base, descs, roi, out, first_frame, n_frames, out_w, out_h);
+  RM_LAUNCH_CHECK(h);
+  return RM_OK;
+}
+
 extern "C" int32_t rm_crop_to_ring(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t k, int32_t W, int32_t H,
                                    const int32_t* roi, uint8_t* ring, int32_t ring_len, int32_t ring_w, int32_t ring_h,
                                    int32_t f_first, void* stream) {

@@ -355,6 +355,55 @@ class Engine:
             return rec, dict(roi=roi, status=status, heat=heat, **m, **sig)
         return rec
 
+    def run_mixed(self, classes: list, fps: float, cal_first: int = 1, cal_len: int = 128, method: str = "flow",
+                  keep: bool = False):
+        """run_batch for a RAGGED batch resident in HBM (BASELINE config 5): `classes` is a list of (n_c, T, H_c, W_c) uint8
+        tensors, one per resolution class (same T).  Calibration runs per class -- the pyramid kernel's strip plan, level
+        sizes and TMA tensor map are per resolution -- then ONE launch crops the ROIs of all clips of all classes into one
+        tensor through their rm_clip_desc descriptors (rm_crop_frames_ragged) and the measure stage runs ONCE over the
+        whole batch: one tracker / PCA / filter / Gaussian-fit pipeline instead of one latency chain per class.
+        Returns (sum n_c, 32) uint8 records in class order (and the intermediate tensors when keep=True)."""
+        assert classes and all(c.is_cuda and c.dtype == torch.uint8 and c.is_contiguous() and c.dim() == 4 for c in classes)
+        T = classes[0].shape[1]
+        assert all(c.shape[1] == T for c in classes)
+        measure_first = cal_first + cal_len + 1
+        n_meas = T - measure_first
+        assert cal_first >= 0 and n_meas >= 1
+        rois, stats = [], []
+        for c in classes:
+            roi, status, _ = self.locate(c, fps, cal_first, cal_len)
+            rois.append(roi)
+            stats.append(status)
+        roi = torch.cat(rois)
+        status = torch.cat(stats)
+        n = roi.shape[0]
+        r = roi.cpu()                                          # the one read-back: sizes the crop tensor
+        mw, mh = max(1, int(r[:, 2].max())), max(1, int(r[:, 3].max()))
+        descs = (_cabi.RmClipDesc * n)()
+        i = 0
+        for c in classes:
+            nc, _, H, W = c.shape
+            for k in range(nc):
+                descs[i] = _cabi.RmClipDesc(c.data_ptr() + k * T * H * W, W, H, T, W)    # base = NULL: absolute addresses
+                i += 1
+        d_descs = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(self.device)
+        crops = torch.zeros((n, n_meas, mh, mw), dtype=torch.uint8, device=self.device)
+        self._call("rm_crop_frames_ragged", C.c_void_p(0), RM_U8, _ptr(d_descs), n, _ptr(roi), measure_first, n_meas,
+                   _ptr(crops), mw, mh, self._stream())
+        roi0 = roi.clone()
+        roi0[:, :2] = 0                                        # the crop's own origin
+        if method == "flow":
+            m = self.measure_signal(crops, roi0, 0, n_meas, fps, status=status, max_roi=(mw, mh))
+            sig = {k: m[k] for k in ("bpm", "filtered", "peaks", "npeaks")}
+        else:
+            data = self.measure_average(crops, roi0, 0, n_meas)
+            m = dict(data=data)
+            sig = self.signal_bpm(data, fps, status=status)
+        rec = self.pack_results(sig["bpm"], roi, status, sig["npeaks"])
+        if keep:
+            return rec, dict(roi=roi, status=status, data=m["data"], **sig)
+        return rec
+
     # ------------------------------------------------------------------ synthetic data
     def synth_clips(self, specs, dq8: np.ndarray) -> torch.Tensor:
         """Generate clips on the device (bit-identical to synth.make_clip).  specs: list of synth.ClipSpec."""

@@ -89,3 +89,27 @@ def test_config5_1080p_in_a_mixed_batch(eng):
         assert (got["x"][2], got["y"][2], got["w"][2], got["h"][2]) == tuple(want2["roi"])
     alone = mon.run(clips[3][None], 10.0)[0]
     assert got[3] == alone
+
+
+def test_ragged_resident_batch_equals_per_class_batches():
+    """Engine.run_mixed (BASELINE config 5, clips resident in HBM): calibration per resolution class, one ragged crop launch
+    through rm_clip_desc descriptors, ONE measure stage over all classes -- records identical to running every class on
+    its own through run_batch (the measure stage is batch-invariant: every clip is independent)."""
+    import numpy as np
+    import torch
+    from respmon_b200 import synth
+    from respmon_b200.engine import Engine, results_to_numpy
+    eng = Engine(0)
+    classes, want = [], []
+    for ci, (w, h) in enumerate(((320, 240), (640, 480), (1920, 1080))):
+        specs = [synth.clip_spec(100 + 3 * k + ci, w, h, 256) for k in range(3 if w < 1920 else 2)]
+        dq8 = np.stack([synth.displacement_q8(s) for s in specs])
+        clips = eng.synth_clips(specs, dq8)
+        classes.append(clips)
+        want.append(results_to_numpy(eng.run_batch(clips, 10.0)).copy())
+    got = results_to_numpy(eng.run_mixed(classes, 10.0))
+    want = np.concatenate(want)
+    assert (want["status"] == 0).sum() >= 6
+    for f in want.dtype.names:
+        assert np.array_equal(got[f], want[f], equal_nan=True), f
+    eng.close()
