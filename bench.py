@@ -337,8 +337,10 @@ def run_gpu_arm(args) -> dict | None:
     mon.h2d_bytes = mon.d2h_bytes = 0
     t0 = time.perf_counter()
     prev = None
-    for _ in range(e2e_steps):           # submit / collect: the upload of step k+1 overlaps the measure tail of step k;
-        ticket = mon.submit(host, FPS)   # every step's records are read back to the host inside the timed region
+    for k_ in range(e2e_steps):          # submit / collect: the upload of step k+1 overlaps the measure tail of step k;
+        # every step's records are read back to the host inside the timed region; the next batch is announced so that its
+        # first chunk goes up behind this batch's last one
+        ticket = mon.submit(host, FPS, prefetch=host if k_ + 1 < e2e_steps else None)
         if prev is not None:
             out = mon.collect(prev)
             if world > 1:
@@ -491,6 +493,23 @@ CONFIGS = {
 }
 
 
+def record_order(owned, shapes, classes, chunk, ragged):
+    """Global clip indices of one rank in the order its result records are written (--config arms).  Per-class path: class
+    after class.  Ragged path (one measure stage over all classes): chunk k holds clips [k*chunk, (k+1)*chunk) of every
+    class, so the order is chunk-major, classes in their listed order inside a chunk."""
+    per = [[i for i in owned if shapes[i] == (T, h, w)] for (w, h) in classes]
+    per = [p_ for p_ in per if p_]
+    order = []
+    if ragged:
+        for k in range(max((len(p_) + chunk - 1) // chunk for p_ in per) if per else 0):
+            for p_ in per:
+                order += p_[k * chunk:(k + 1) * chunk]
+    else:
+        for p_ in per:
+            order += p_
+    return order
+
+
 def _oracle_clip(args):
     """CPU parity sample for --config: one clip regenerated from its seed and run through the oracle (checker only)."""
     seed, w, h = args
@@ -631,17 +650,7 @@ def run_config_arm(args) -> dict | None:
     by_clip = {}
     ragged = len(classes) > 1 and not args.per_class_measure
     for r in range(world):
-        per = [[i for i in owners[r] if shapes[i] == (T, h, w)] for (w, h) in classes]
-        per = [p_ for p_ in per if p_]
-        order = []
-        if ragged:                                 # chunk-major: chunk k holds clips [k*chunk, (k+1)*chunk) of every class
-            for k in range(max((len(p_) + args.chunk - 1) // args.chunk for p_ in per)):
-                for p_ in per:
-                    order += p_[k * args.chunk:(k + 1) * args.chunk]
-        else:
-            for p_ in per:
-                order += p_
-        for pos, i in enumerate(order):
+        for pos, i in enumerate(record_order(owners[r], shapes, classes, args.chunk, ragged)):
             by_clip[i] = allrec[r, pos]
     if world > 1:
         dist.destroy_process_group()

@@ -200,3 +200,24 @@ def test_benchmarker_matches_the_reference_report():
         b2.add_tag("t")
         b2.ticks["t"] = [0.5, 1.5]
         assert b2.get_report() == rb.get_report()
+
+
+def test_bench_config_record_order_is_a_permutation_of_the_ranks_clips():
+    """bench.py --config 4|5: the order in which a rank writes its records (per class, or chunk-major for the ragged path
+    with one measure stage over all classes) covers each of its clips exactly once."""
+    import bench
+    from respmon_b200.batch import balance_clips
+    classes = bench.CONFIGS[5]["classes"]
+    total = 61
+    shapes = [(bench.T,) + classes[i % 3][::-1] for i in range(total)]
+    owners = balance_clips(shapes, 4)
+    for r in range(4):
+        for ragged in (False, True):
+            for chunk in (4, 64):
+                order = bench.record_order(owners[r], shapes, classes, chunk, ragged)
+                assert sorted(order) == owners[r]
+        # ragged, chunk 4: the first chunk holds the first 4 clips of every class, classes in the listed order
+        order = bench.record_order(owners[r], shapes, classes, 4, True)
+        per = [[i for i in owners[r] if shapes[i][1:] == c[::-1]] for c in classes]
+        head = [i for p_ in per for i in p_[:4]]
+        assert order[:len(head)] == head

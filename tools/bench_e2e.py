@@ -21,11 +21,17 @@ for chunk, streams, mch in [(32, 2, 4), (32, 2, 1), (32, 3, 2), (16, 2, 4), (64,
         e.set_option("measure_chunks", mch)
     out = mon.run(host, 10.0)
     torch.cuda.synchronize()
+    steps = 12
     t0 = time.perf_counter()
-    for _ in range(3):
-        out = mon.run(host, 10.0)
+    prev = None
+    for _ in range(steps):                      # pipelined like bench.py's e2e leg
+        ticket = mon.submit(host, 10.0)
+        if prev is not None:
+            out = mon.collect(prev)
+        prev = ticket
+    out = mon.collect(prev)
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / 3
+    dt = (time.perf_counter() - t0) / steps
     if ref is None: ref = out
     same = all(np.array_equal(out[f], ref[f], equal_nan=True) for f in out.dtype.names)
     print("chunk %2d streams %d measure_chunks %d : %.1f ms/step  %.0f frames/s  same=%s" % (chunk, streams, mch, dt * 1e3, n_clips * 256 / dt, same), flush=True)
