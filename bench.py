@@ -337,10 +337,8 @@ def run_gpu_arm(args) -> dict | None:
     mon.h2d_bytes = mon.d2h_bytes = 0
     t0 = time.perf_counter()
     prev = None
-    for k_ in range(e2e_steps):          # submit / collect: the upload of step k+1 overlaps the measure tail of step k;
-        # every step's records are read back to the host inside the timed region; the next batch is announced so that its
-        # first chunk goes up behind this batch's last one
-        ticket = mon.submit(host, FPS, prefetch=host if k_ + 1 < e2e_steps else None)
+    for _ in range(e2e_steps):           # submit / collect: the upload of step k+1 overlaps the measure tail of step k;
+        ticket = mon.submit(host, FPS)   # every step's records are read back to the host inside the timed region
         if prev is not None:
             out = mon.collect(prev)
             if world > 1:

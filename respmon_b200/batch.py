@@ -79,7 +79,6 @@ class BatchMonitor:
         self._pinned = {}
         self._ev = None
         self._copy_stream = torch.cuda.Stream(self.engine.device)
-        self._prefetched = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -119,11 +118,8 @@ class BatchMonitor:
             self._seq = 0                                                  # chunks submitted so far (slot rotation)
         return self._ev
 
-    def submit(self, clips, fps: float, cal_first: int = 1, cal_len: int = 128, prefetch=None):
-        """Enqueue a batch and return a ticket for collect().  `prefetch`: the batch that will be submitted next (same
-        shape conventions) -- its first chunk's calibration window is queued on the copy stream behind this batch's last
-        one, so the host -> device path does not idle while the host waits for the last chunk's ROI (about 3 ms per
-        64-clip step otherwise).  Returns as soon as the last chunk's measure stage has been
+    def submit(self, clips, fps: float, cal_first: int = 1, cal_len: int = 128):
+        """Enqueue a batch and return a ticket for collect().  Returns as soon as the last chunk's measure stage has been
         enqueued, so the upload of the next submit() overlaps the tail of this one (buffers and streams are handed from
         batch to batch through events; the results of every batch are complete when its collect() returns).
 
@@ -177,19 +173,12 @@ class BatchMonitor:
             self.h2d_bytes += dst.numel()
             return dst
 
-        pre = self._prefetched
-        self._prefetched = None
-        if pre is not None and pre["key"] == (id(clips), cal_first, cal_len, seq0) and chunks:
-            pending = pre["dst"]                                  # queued by the previous submit(prefetch=clips)
-        else:
-            pending = upload_cal(0) if chunks else None
+        pending = upload_cal(0) if chunks else None
         for i, (lo, hi) in enumerate(chunks):
             slot, ms = (seq0 + i) & 1, (seq0 + i) % n_ms
             cal = pending
             if i + 1 < len(chunks):
                 pending = upload_cal(i + 1)                       # overlaps everything below
-            elif prefetch is not None:
-                self._prefetch_first_chunk(prefetch, cal_first, cal_len, seq0 + len(chunks), E, used)
             m = hi - lo
             main.wait_event(E["cal_ready"][slot])
             roi, status, _ = eng.locate(cal, fps, 0, cal_len)
@@ -245,27 +234,6 @@ class BatchMonitor:
             e.record(mstream)
             done.append(e)
         return dict(records=records, done_events=done, keep=keep)
-
-    def _prefetch_first_chunk(self, clips, cal_first, cal_len, seq, E, used):
-        """Queue the calibration window of the first chunk of the NEXT batch (see submit(prefetch=...))."""
-        host = [torch.from_numpy(c) if isinstance(c, np.ndarray) else c for c in clips] if isinstance(clips, (list, tuple)) \
-            else (torch.from_numpy(clips) if isinstance(clips, np.ndarray) else clips)
-        n = len(host)
-        if n == 0:
-            return
-        H, W = (host[0].shape[1:] if isinstance(host, list) else host.shape[2:])
-        hi = min(n, self.chunk_clips)
-        slot = seq & 1
-        dst = self._buffer(("cal", slot), (hi, cal_len, H, W))
-        with torch.cuda.stream(self._copy_stream):
-            if used["cal"][slot]:
-                self._copy_stream.wait_event(E["cal_freed"][slot])
-            for c in range(hi):
-                dst[c].copy_(host[c][cal_first:cal_first + cal_len], non_blocking=True)
-            E["cal_ready"][slot].record(self._copy_stream)
-        used["cal"][slot] = True
-        self.h2d_bytes += dst.numel()
-        self._prefetched = dict(key=(id(clips), cal_first, cal_len, seq), dst=dst, keep=host)
 
     def collect(self, ticket) -> np.ndarray:
         """Wait for a submitted batch and read its records back (the device->host read of the step's result)."""

@@ -97,26 +97,3 @@ def test_submit_collect_overlapped_batches_equal_sequential_runs():
     for g, w in zip(got, want):
         _same(g, w)
 
-
-def test_submit_with_prefetch_of_the_next_batch_equals_plain_submits():
-    """submit(prefetch=next): the first chunk of the next batch goes up behind this batch's last one.  Same records as
-    without the announcement -- also when the announced batch is not the one submitted next (the prefetch is dropped) and
-    when batches differ in size and resolution."""
-    from respmon_b200.batch import BatchMonitor
-    batches = [torch.from_numpy(_clips(range(50, 55), 320, 240)).pin_memory(),
-               torch.from_numpy(_clips(range(55, 58), 320, 240)).pin_memory(),
-               torch.from_numpy(_clips(range(58, 60), 250, 187)).pin_memory()]
-    seq = [0, 0, 1, 2, 0]
-    ref = BatchMonitor(0, chunk_clips=2)
-    want = [ref.run(batches[i], 10.0) for i in seq]
-    mon = BatchMonitor(0, chunk_clips=2)
-    announced = [0, 1, 0, 0, None]            # right, right, WRONG (batch 2 follows, batch 0 was announced), right, none
-    tickets, got = [], []
-    for k, i in enumerate(seq):
-        nxt = None if announced[k] is None else batches[announced[k]]
-        tickets.append(mon.submit(batches[i], 10.0, prefetch=nxt))
-        if len(tickets) >= 2:
-            got.append(mon.collect(tickets[-2]))
-    got.append(mon.collect(tickets[-1]))
-    for g, w in zip(got, want):
-        _same(g, w)
