@@ -130,6 +130,21 @@ def test_pyramid_kernels_are_bit_identical(eng, w, h, n_clips, T):
         assert np.abs(out["fused0/1"][-1, 1, off:off + lw * lh].reshape(lh, lw) - lap[l]).max() <= 2e-14
 
 
+def test_pyramid_kernels_agree_on_random_sizes(eng):
+    """Random frame sizes (W a multiple of 16 up to 2560, H a multiple of 8 from 24): the fused TMA kernel, whatever strip
+    plan and slot count the size gives it (or its fallback where the level images do not fit), equals the split path."""
+    rng = np.random.default_rng(2024)
+    sizes = [(16 * int(rng.integers(1, 161)), 8 * int(rng.integers(3, 60))) for _ in range(14)] + [(2560, 24), (16, 472)]
+    for (w, h) in sizes:
+        n = max(2, min(40, 3_000_000 // (w * h)))
+        frames = dev(rng.integers(0, 256, (n, h, w)).astype(np.uint8))
+        eng.set_option("pyramid_mode", 0)
+        want = eng.pyramid_build(frames)
+        eng.set_option("pyramid_mode", 1)
+        got = eng.pyramid_build(frames)
+        assert torch.equal(want, got), (w, h, int((want != got).sum()))
+
+
 def test_pyramid_build_golden_taps(eng, golden):
     for name in ("vga_s0", "odd_s3"):
         fix = golden(name)
