@@ -246,6 +246,14 @@ int32_t rm_measure_signal_stream(rm_handle* h, const uint8_t* frames, int32_t n_
                                  int32_t* npts_out, int32_t* status_io, double* bpm_out, double* filtered_out,
                                  int32_t* peaks_out, int32_t* npeaks_out, void* workspace, size_t workspace_bytes,
                                  void* stream);
+/* The same for motion_extraction_method = 'average' (base.py:355-358): the mean of the float crop of the new frames
+ * [f_begin, f_end), read from the crop ring (roi = (0, 0, w, h) per camera inside its ring slot), is written to data_out
+ * at the frames' absolute positions and measure() (base.py:340-352) runs on the windows ending at them.  No state is
+ * carried between calls. */
+int32_t rm_measure_average_stream(rm_handle* h, const uint8_t* ring, int32_t n_clips, int32_t ring_len, int32_t W, int32_t H,
+                                  const int32_t* roi, int32_t cap, int32_t f_begin, int32_t f_end, double fps,
+                                  double* data_out, int32_t* status_io, double* bpm_out, double* filtered_out,
+                                  int32_t* peaks_out, int32_t* npeaks_out, void* stream);
 /* crop = frame[y:y+h, x:x+w] (base.py:471) of k new frames per camera into the crop ring: frames (n_clips, k, H, W), roi
  * in frame coordinates, ring (n_clips, ring_len, ring_h, ring_w); block frame j goes to slot (f_first + j) % ring_len. */
 int32_t rm_crop_to_ring(rm_handle* h, const uint8_t* frames, int32_t n_clips, int32_t k, int32_t W, int32_t H,

@@ -89,6 +89,8 @@ SIGNATURES = {
                                  _P, _P, _P, _sz, _S]),
     "rm_measure_signal_stream": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _i32, _i32, _i32, _f64, _P, _P, _P,
                                         _P, _P, _P, _P, _P, _P, _sz, _S]),
+    "rm_measure_average_stream": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _i32, _i32, _i32, _f64, _P, _P, _P, _P, _P, _P,
+                                         _S]),
     "rm_crop_frames": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _i32, _P, _i32, _i32, _P, _i32, _i32, _S]),
     "rm_crop_frames_ragged": (_i32, [_H, _P, _i32, _P, _i32, _P, _i32, _i32, _P, _i32, _i32, _S]),
     "rm_crop_to_ring": (_i32, [_H, _P, _i32, _i32, _i32, _i32, _P, _P, _i32, _i32, _i32, _i32, _S]),

@@ -1602,6 +1602,48 @@ extern "C" int32_t rm_measure_signal_stream(rm_handle* h, const uint8_t* frames,
   return rmi_signal_range(h, f_begin, f_end, 0, st, st, nullptr);
 }
 
+// 'average' extraction for live cohorts: the mean of the float crop (base.py:355-358) of the new frames [f_begin, f_end)
+// read from the crop ring, written at their absolute positions of the (n_clips, cap) history -- the same sums in the same
+// order as measure_average_kernel on the whole clip.
+__global__ void measure_average_ring_kernel(const uint8_t* __restrict__ ring, const int32_t* __restrict__ roi, int ring_len,
+                                            int W, int H, int cap, int f_begin, double* __restrict__ data) {
+  const int clip = blockIdx.y, f = f_begin + blockIdx.x;
+  const int rw = roi[clip * 4 + 2], rh = roi[clip * 4 + 3];
+  __shared__ double red[8];
+  const uint8_t* img = ring + ((long long)clip * ring_len + f % ring_len) * W * H;
+  double acc = 0.0;
+  const double inv = 1.0 / 255;
+  for (int i = threadIdx.x; i < rw * rh; i += blockDim.x) acc += (double)img[(long long)(i / rw) * W + (i % rw)] * inv;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) acc += red[w];
+    data[(long long)clip * cap + f] = acc / (double)(rw * rh);
+  }
+}
+
+// rm_measure_signal_stream for motion_extraction_method = 'average': no tracker, no state between calls.
+extern "C" int32_t rm_measure_average_stream(rm_handle* h, const uint8_t* ring, int32_t n_clips, int32_t ring_len, int32_t W,
+                                             int32_t H, const int32_t* roi, int32_t cap, int32_t f_begin, int32_t f_end,
+                                             double fps, double* data_out, int32_t* status_io, double* bpm_out,
+                                             double* filtered_out, int32_t* peaks_out, int32_t* npeaks_out, void* stream) {
+  RM_CHECK_ARG(h, h && ring && roi && data_out && bpm_out && fps > 0, "null pointer or bad fps");
+  RM_CHECK_ARG(h, f_begin >= 0 && f_end > f_begin && f_end <= cap && f_end - f_begin < ring_len, "bad frame block");
+  if (n_clips == 0) return RM_OK;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t rc;
+  if ((rc = rmi_signal_setup(h, data_out, n_clips, cap, fps, bpm_out, filtered_out, peaks_out, npeaks_out, status_io, 1, st,
+                             f_begin, f_end - f_begin)) != RM_OK)
+    return rc;
+  dim3 grid(f_end - f_begin, n_clips);
+  RM_PROF(h, st, "measure_average_ring_kernel");
+  measure_average_ring_kernel<<<grid, 256, 0, st>>>(ring, roi, ring_len, W, H, cap, f_begin, data_out);
+  RM_LAUNCH_CHECK(h);
+  return rmi_signal_range(h, f_begin, f_end, 0, st, st, nullptr);
+}
+
 // Copies the ROI crop of k new frames of every camera into its crop ring: frames (n_clips, k, H, W), roi (n_clips, 4) in
 // frame coordinates, ring (n_clips, ring_len, ring_h, ring_w); frame j of the block goes to slot (f_first + j) % ring_len.
 __global__ void crop_to_ring_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ roi,

@@ -446,7 +446,9 @@ template <int S, int MAXW>
 __global__ void __maxnreg__((65536 / (32 * ((MAXW + 3) & ~3))) & ~7)
     pyramid_u8_fused_kernel(const __grid_constant__ PfParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: the compiler then knows that everything derived from it (strip, slot, ring and
+  // barrier addresses, frame numbers, TMA coordinates) is warp-uniform and keeps it in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int slot = warp / p.n_strips, strip = warp - slot * p.n_strips;
   const bool left = strip == 0, right = strip == p.n_strips - 1;
   const int base = p.strip_base[strip];

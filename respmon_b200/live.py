@@ -24,8 +24,12 @@ from .engine import Engine, _ptr
 
 class LiveCohort:
     def __init__(self, n_cameras: int, width: int, height: int, fps: float = 10.0, device: int | None = None,
-                 cap: int = 4096, ring_len: int = 33, cal_len: int = 128, start_state: str = "initialize", **hyper):
+                 cap: int = 4096, ring_len: int = 33, cal_len: int = 128, start_state: str = "initialize",
+                 max_area: float = float("inf"), method: str = "flow", **hyper):
         assert start_state in ("initialize", "calibration")
+        assert method in ("flow", "average")
+        self.method = method               # motion_extraction_method (base.py:354-407)
+        self.max_area = max_area           # maximum_bounding_box_area (base.py:80, :456-458 -> tools.py:48-57)
         self.engine = Engine(device, **hyper)
         self.n, self.W, self.H, self.fps = int(n_cameras), int(width), int(height), float(fps)
         self.cap, self.ring_len, self.cal_len = int(cap), int(ring_len), int(cal_len)
@@ -88,6 +92,11 @@ class LiveCohort:
         if not ok.any():                                            # base.py:451-454: refill the buffer and retry
             self._cal_idx = 0
             return
+        if self.max_area != float("inf"):                           # base.py:456-458
+            from .monitor import reduce_bounding_box
+            r = np.array([reduce_bounding_box(*(int(v) for v in row), self.max_area) if ok[i] else tuple(row)
+                          for i, row in enumerate(r)], dtype=np.int32)
+            roi = torch.from_numpy(r).to(eng.device)
         self.roi, self.status = roi, status
         self._roi_host, self._ok_host, self._stages = [tuple(int(v) for v in row) for row in r], ok, None
         self._mw, self._mh = int(max(1, r[ok, 2].max())), int(max(1, r[ok, 3].max()))
@@ -147,6 +156,12 @@ class LiveCohort:
         else:
             eng._call("rm_crop_to_ring", _ptr(block), self.n, k, self.W, self.H, _ptr(self.roi), _ptr(self._ring),
                       self.ring_len, self._mw, self._mh, f0, eng._stream())
+        if self.method == "average":
+            eng._call("rm_measure_average_stream", _ptr(self._ring), self.n, self.ring_len, self._mw, self._mh,
+                      _ptr(self._roi0), self.cap, f0, f0 + k, self.fps, _ptr(self.data), _ptr(self.status), _ptr(self.bpm),
+                      _ptr(self.filtered), _ptr(self.peaks), _ptr(self.npeaks), eng._stream())
+            self.n_measured = f0 + k
+            return
         eng._call("rm_measure_signal_stream", _ptr(self._ring), self.n, self.ring_len, self._mw, self._mh, _ptr(self._roi0),
                   self._mw, self._mh, self.cap, f0, f0 + k, self.fps, _ptr(self.data), _ptr(self.motion), _ptr(self.npts),
                   _ptr(self.status), _ptr(self.bpm), _ptr(self.filtered), _ptr(self.peaks), _ptr(self.npeaks),
@@ -206,8 +221,10 @@ class LiveFleet:
     cohort_cls = None      # the class of the cohorts a fleet creates (LiveCohort; the CPU tests substitute an oracle-backed one)
 
     def __init__(self, width: int, height: int, fps: float = 10.0, device: int | None = None,
-                 error_reset_delay: float = 10.0, cap: int = 65536, ring_len: int = 33, cal_len: int = 128, **hyper):
+                 error_reset_delay: float = 10.0, cap: int = 65536, ring_len: int = 33, cal_len: int = 128,
+                 max_area: float = float("inf"), method: str = "flow", **hyper):
         self.W, self.H, self.fps, self.device = int(width), int(height), float(fps), device
+        self.max_area, self.method = max_area, method
         self.error_reset_delay = float(error_reset_delay)
         self.cap, self.ring_len, self.cal_len, self.hyper = int(cap), int(ring_len), int(cal_len), hyper
         self.cams = {}        # id -> dict(cohort, slot, state, wait, errors, last)
@@ -235,7 +252,7 @@ class LiveFleet:
     def _new_cohort(self, ids, start_state):
         live = (self.cohort_cls or LiveCohort)(len(ids), self.W, self.H, self.fps, device=self.device, cap=self.cap,
                                                ring_len=self.ring_len, cal_len=self.cal_len, start_state=start_state,
-                                               **self.hyper)
+                                               max_area=self.max_area, method=self.method, **self.hyper)
         co = dict(live=live, members=list(ids))
         self.cohorts.append(co)
         for slot, cid in enumerate(ids):
@@ -351,6 +368,18 @@ class LiveFleet:
         if co is None or co["live"].state != "measure":
             return dict(data=np.zeros(0), bpm=np.zeros(0))
         return self._snapshot(co, cam["slot"], co["live"].n_measured)
+
+    def details(self, cam_id) -> dict:
+        """Everything RespiratoryMonitor keeps of the camera's current measure run: data, bpm, motion (per measure frame) and
+        filtered / peaks of the window that ends at the last frame (base.py:340-352); None outside 'measure'."""
+        cam = self.cams[cam_id]
+        co = cam["cohort"]
+        if co is None or co["live"].state != "measure":
+            return None
+        h, slot = co["live"].history(), cam["slot"]
+        npk = int(h["npeaks"][slot])
+        return dict(data=h["data"][slot], bpm=h["bpm"][slot], motion=h["motion"][slot], filtered=h["filtered"][slot],
+                    peaks=[int(v) for v in h["peaks"][slot][:npk]])
 
     def close(self):
         for co in self.cohorts:

@@ -146,7 +146,8 @@ def compose_mosaic(total_avg, avg_raw, avg, box, threshold):
 class RespiratoryMonitor:
     def __init__(self, capture_target=0, save_calibration_image=False, visualize=None, fig_size=None,
                  fps_limit=10, error_reset_delay=10.0, save_all_data=False,
-                 motion_extraction_method='average', *, source_fps=None, device=None, autorun=True):
+                 motion_extraction_method='average', *, source_fps=None, device=None, autorun=True, live=None,
+                 live_block=16):
         # argument contract of base.py:24-34 (AssertionError on violation)
         assert isinstance(fps_limit, (int, float)) and fps_limit > 0, "fps_limit must be a positive int or float"
         assert isinstance(save_calibration_image, bool), "save_calibration_image must be bool"
@@ -219,6 +220,11 @@ class RespiratoryMonitor:
         self.status = None                              # rm_clip_status of the last calibrate/measure cycle
         self.calibration_start_time = np.nan
 
+        # live = True: frames are consumed a few at a time as the capture delivers them, with bounded memory, the way the
+        # reference's run() loop does (base.py:413-505) -- for cameras (capture_target = a device index: the default) and
+        # streams too long to hold; live = False: the stream is read to its end first and processed in one device pass
+        self.live = isinstance(capture_target, int) if live is None else bool(live)
+        self.live_block = int(live_block)
         self._device_arg = device
         self._engine_key = self._engine_params()
         self.engine = Engine(device, **self._engine_key)        # raises without the CUDA library / a device
@@ -276,10 +282,6 @@ class RespiratoryMonitor:
             self._frames = clip.to(dev).contiguous()
             self.cap.pos = clip.shape[0]
             return
-        if isinstance(self.capture_target, int):
-            raise RuntimeError("capture_target=%r is a live camera: this class holds the whole stream on the device and "
-                               "returns when it ends; live sources are served frame by frame by "
-                               "respmon_b200.live.LiveFleet" % (self.capture_target,))
         blocks, pending, total = [], [], 0
 
         def flush():
@@ -300,7 +302,8 @@ class RespiratoryMonitor:
             total += 1
             if total > self.max_stream_frames:
                 raise RuntimeError("the capture delivered more than max_stream_frames = %d frames: an endless source? "
-                                   "(live sources: respmon_b200.live.LiveFleet)" % self.max_stream_frames)
+                                   "(construct the monitor with live=True, or use respmon_b200.live.LiveFleet)"
+                                   % self.max_stream_frames)
             if len(pending) == 64:
                 flush()
         flush()
@@ -510,6 +513,8 @@ class RespiratoryMonitor:
         """run (base.py:409-513) over the whole stream."""
         for tag in ('Measurement Loop', 'Frame Capture', 'Calibration Measurement'):
             self.benchmarker.add_tag(tag)
+        if self.live and not isinstance(self.cap, _ArrayCapture):
+            return self._run_live()
         self._drain()
         T = self._frames.shape[0]
         while self._pos < T:
@@ -585,6 +590,92 @@ class RespiratoryMonitor:
         self._pos += stop
         if stop < n:
             self.trigger_error("error detection found poor signal")
+
+    def _run_live(self):
+        """run() for sources that are consumed as they come (base.py:413-505): frames are read `live_block` at a time and
+        pushed through a one-camera LiveFleet, which walks the same state machine on them -- initialize, calibration
+        (retry without ROI), measure, error -> error_reset_delay of stream time -> reset -> calibration -- in bounded memory
+        (the 128-frame calibration buffer, a ring of ROI crops, the per-frame histories); after every block the monitor's
+        attributes (x, y, w, h, state, data, t, freq, motion_data, filtered_data, peak_indices, peak_times, all_data) are
+        brought up to date exactly as the whole-stream path leaves them."""
+        from .live import LiveFleet
+        dev = self.engine.device
+        t_start = time.time()
+        first = self._read_block(self.calibration_buffer_target_length + 1) if (self.fps == 0 or self.fps is np.nan) else None
+        if first is not None and self.fps is np.nan:                # detect_fps (base.py:303-310): measured over the fill
+            self.fps = self.calibration_buffer_target_length / max(time.time() - t_start, 1e-9)
+        self.detect_fps()
+        self.peak_minimum_sample_distance = int(np.floor(self.fps / self.freq_max))
+        fleet = LiveFleet(self.width, self.height, float(self.fps), device=self.engine.device_index,
+                          error_reset_delay=float(self.error_reset_delay), cal_len=self.calibration_buffer_target_length,
+                          max_area=self.maximum_bounding_box_area, method=self.motion_extraction_method,
+                          **self._engine_params())
+        fleet.add_camera(0)
+        n_prev, errors = 0, 0
+        L, dt = self.measure_buffer_length, 1.0 / float(self.fps)
+        try:
+            while True:
+                block = first if first is not None else self._read_block(self.live_block)
+                first = None
+                if block is None:
+                    break
+                self.benchmarker.tick_start('Measurement Loop')
+                frames = torch.from_numpy(block).to(dev)
+                if frames.dim() == 4:                                # BGR frames: next_frame's cvtColor (base.py:230)
+                    frames = self.engine.bgr_to_gray(frames)
+                st = fleet.push(frames[None])[0]
+                if st["errors"] > errors:                            # detect_errors fired (base.py:489-494): error, later reset
+                    errors = st["errors"]
+                    self.trigger_error("error detection found poor signal")
+                    self.reset()
+                    n_prev = 0
+                self.state = st["state"]
+                if st["state"] == "measure":
+                    if n_prev == 0 and st["roi"] is not None:
+                        self.x, self.y, self.w, self.h = st["roi"]
+                        self.status = st["status"]
+                    det = fleet.details(0)
+                    n_now = len(det["data"])
+                    for f in range(n_prev, n_now):
+                        for b in self.buffers:                       # base.py:473-475
+                            if len(b) >= L:
+                                b.popleft()
+                        v = float(det["data"][f])
+                        self.data.append(v)
+                        tv = 0.0 if len(self.t) == 0 else self.t[-1] + dt   # base.py:481-484
+                        self.t.append(tv)
+                        if self.motion_extraction_method == "flow" and f >= 1 and not math.isnan(det["motion"][f, 0]):
+                            self.motion_data.append([det["motion"][f, 0], det["motion"][f, 1]])
+                        if self.save_all_data:
+                            self.all_data.append((tv, v))
+                        if not math.isnan(det["bpm"][f]):
+                            self.freq.append(float(det["bpm"][f]))
+                    if n_now > self.measure_initialization_length and n_now > n_prev:
+                        Lw = min(n_now, L)
+                        self.filtered_data = det["filtered"][:Lw]
+                        self.peak_indices = det["peaks"]
+                        self.peak_times = np.take(np.asarray(self.t), self.peak_indices)
+                    n_prev = n_now
+                self.benchmarker.tick_end('Measurement Loop')
+                self.update_ui()
+        finally:
+            fleet.close()
+        _log.info("Capture closed.")
+        self.cap.release()
+        if self.save_all_data:
+            np.save(str(self.capture_target if not hasattr(self.capture_target, "shape") else "clip") + '.npy', self.all_data)
+
+    def _read_block(self, k):
+        """Up to k frames from the capture as one array, or None at the end of the stream."""
+        out = []
+        while len(out) < k and self.cap.isOpened():
+            self.benchmarker.tick_start('Frame Capture')
+            ok, frame = self.cap.read()
+            if frame is None or frame is False:
+                break
+            self.benchmarker.tick_end('Frame Capture')
+            out.append(np.asarray(frame))
+        return np.ascontiguousarray(np.stack(out)) if out else None
 
     @property
     def bpm(self):

@@ -231,3 +231,71 @@ def test_monitor_other_branches_match_reference(golden, name, method, fps_limit)
     assert len(rm.freq) == len(fix["freq"]) and np.max(np.abs(np.array(rm.freq) - fix["freq"])) <= 0.5
     assert [int(v) for v in rm.peak_indices] == [int(v) for v in fix["peaks"]]
     assert rm.state == str(fix["state"])
+
+
+class _ArrayCap:
+    """cv2.VideoCapture-like source over a (T, H, W) uint8 array."""
+
+    def __init__(self, clip, fps=10.0):
+        self.clip, self.i, self.fps = clip, 0, fps
+
+    def get(self, prop):
+        return {5: self.fps, 3: float(self.clip.shape[2]), 4: float(self.clip.shape[1])}.get(prop, 0.0)
+
+    def isOpened(self):
+        return True
+
+    def read(self):
+        if self.i >= len(self.clip):
+            return False, None
+        self.i += 1
+        return True, self.clip[self.i - 1]
+
+    def release(self):
+        pass
+
+
+@pytest.mark.parametrize("name,method,block", [("qvga_s1", "flow", 7), ("qvga_long_s4", "flow", 16), ("vga_s2", "flow", 1),
+                                               ("mode_average_qvga_s1", "average", 5),
+                                               ("mode_average_long_s4", "average", 31),
+                                               ("mode_flow_maxarea600_s1", "flow", 16)])
+def test_monitor_live_mode_matches_reference_attributes(golden, name, method, block):
+    """RespiratoryMonitor(live=True) -- what a camera index or an endless stream gets: frames are consumed `live_block` at a
+    time as the capture delivers them, in bounded memory, through a one-camera LiveFleet -- leaves the attributes the
+    unmodified reference leaves on the same clip (CPU twin with the oracle: tests/test_live_host.py)."""
+    from respmon_b200.monitor import RespiratoryMonitor
+    fix = golden(name)
+    spec, clip = clip_from_fixture(fix)
+    rm = RespiratoryMonitor(_ArrayCap(clip), visualize=None, save_all_data=False, motion_extraction_method=method,
+                            fps_limit=10, live=True, live_block=block, autorun=False)
+    if "max_area" in fix:
+        rm.maximum_bounding_box_area = float(fix["max_area"])
+    rm.run()
+    assert (rm.x, rm.y, rm.w, rm.h) == tuple(int(v) for v in fix["roi"])
+    assert rm.state == "measure"
+    data = np.array(rm.data)
+    assert data.shape == fix["data"].shape and np.sqrt(np.mean((data - fix["data"]) ** 2)) <= 1e-4
+    np.testing.assert_allclose(np.array(rm.t), fix["t"], rtol=0, atol=1e-12)
+    assert len(rm.freq) == len(fix["freq"]) and np.max(np.abs(np.array(rm.freq) - fix["freq"])) <= 0.5
+    assert [int(v) for v in rm.peak_indices] == [int(v) for v in fix["peaks"]]
+    np.testing.assert_allclose(np.asarray(rm.filtered_data), fix["filtered"], rtol=0, atol=2e-4)
+    if method == "flow" and "motion" in fix:
+        motion = np.array(rm.motion_data, dtype=np.float32)
+        assert motion.shape == fix["motion"].shape and np.max(np.abs(motion - fix["motion"])) <= 1e-3
+
+
+def test_monitor_live_mode_error_cycle_equals_the_whole_stream_path():
+    """The clip of test_tracking_lost_goes_through_error_and_recalibrates through live mode in odd block sizes: error,
+    error_reset_delay of stream time, reset, calibration, measure again -- the same attributes as the whole-stream path."""
+    from respmon_b200 import synth
+    from respmon_b200.monitor import RespiratoryMonitor
+    clip = synth.make_clip(synth.clip_spec(4, 320, 240, 600))
+    clip[200:212] = 128
+    want = RespiratoryMonitor(clip, motion_extraction_method="flow", error_reset_delay=1.0)
+    got = RespiratoryMonitor(_ArrayCap(clip), motion_extraction_method="flow", error_reset_delay=1.0, live=True, live_block=13)
+    assert got.error_message == want.error_message == "error detection found poor signal"
+    assert got.state == want.state == "measure"
+    assert (got.x, got.y, got.w, got.h) == (want.x, want.y, want.w, want.h)
+    assert len(got.data) == len(want.data) and np.array_equal(np.array(got.data), np.array(want.data))
+    assert len(got.freq) == len(want.freq) and np.allclose(got.freq, want.freq, rtol=0, atol=1e-9)
+    assert [int(v) for v in got.peak_indices] == [int(v) for v in want.peak_indices]

@@ -18,8 +18,10 @@ class OracleCohort:
     """LiveCohort's interface (push / latest / state / n_measured / status / data / bpm / close) computed by the oracle."""
 
     def __init__(self, n, width, height, fps=10.0, device=None, cap=4096, ring_len=33, cal_len=128,
-                 start_state="initialize", **hyper):
-        self.n, self.fps, self.cal_len, self.state = n, float(fps), cal_len, start_state
+                 start_state="initialize", max_area=float("inf"), method="flow", **hyper):
+        self.n, self.fps, self.cal_len, self.state, self.max_area = n, float(fps), cal_len, start_state, max_area
+        self.method = method
+        self._last = [None] * n
         self._cal = [[] for _ in range(n)]
         self.n_measured = 0
         self.roi = self.status = None
@@ -40,7 +42,7 @@ class OracleCohort:
                     if all(b is None for b in boxes):
                         self._cal = [[] for _ in range(self.n)]
                         continue
-                    self.roi = [b if b is not None else (0, 0, 0, 0) for b in boxes]
+                    self.roi = [P.shrink_box(*b, self.max_area) if b is not None else (0, 0, 0, 0) for b in boxes]
                     self.status = torch.tensor([0 if b is not None else 1 for b in boxes], dtype=torch.int32)
                     self._trk = [P.FlowTracker() for _ in range(self.n)]
                     self._t = []
@@ -55,12 +57,14 @@ class OracleCohort:
                     trk = self._trk[c]
                     if len(trk.motion) >= P.MEASURE_LEN:
                         trk.motion.popleft()
-                    v = trk.step(P.u8_to_unit(f[c, j])[y:y + h, x:x + w])
+                    crop = P.u8_to_unit(f[c, j])[y:y + h, x:x + w]
+                    v = trk.step(crop) if self.method == "flow" else float(np.average(crop))      # base.py:355-358
                     self.data[c, q] = v
                     lo = max(0, q + 1 - P.MEASURE_LEN)
                     win = self.data[c, lo:q + 1].numpy()
                     if q + 1 - lo > P.MEASURE_INIT_LEN and not np.isnan(win).any():
-                        _, _, b = P.measure_window(win, np.array(self._t[lo:q + 1]), self.fps)
+                        filt, pk, b = P.measure_window(win, np.array(self._t[lo:q + 1]), self.fps)
+                        self._last[c] = (filt, pk)
                         if b is not None:
                             self.bpm[c, q] = b
                 self.n_measured += 1
@@ -76,6 +80,21 @@ class OracleCohort:
                 if len(v):
                     out["bpm"][c] = v[-1]
         return out
+
+    def history(self):
+        m, Lw = self.n_measured, P.MEASURE_LEN
+        filt = np.full((self.n, Lw), np.nan)
+        peaks = np.full((self.n, Lw), -1, dtype=np.int32)
+        npk = np.zeros(self.n, dtype=np.int32)
+        motion = np.full((self.n, m, 2), np.nan, dtype=np.float32)
+        for c in range(self.n):
+            if self._last[c] is not None:
+                f, pk = self._last[c]
+                filt[c, :len(f)] = f
+                peaks[c, :len(pk)] = pk
+                npk[c] = len(pk)
+        return dict(data=self.data[:, :m].numpy(), bpm=self.bpm[:, :m].numpy(), motion=motion, filtered=filt, peaks=peaks,
+                    npeaks=npk)
 
     def close(self):
         pass
@@ -129,3 +148,46 @@ def test_fleet_routes_frames_like_the_monitor(fleet_cls, blocks):
     fleet.remove_camera("A")
     fleet.remove_camera("C")
     assert len(fleet.cohorts) == 1 and set(fleet.latest()) == {"B"}
+
+
+@pytest.mark.parametrize("name,method", [("qvga_s1", "flow"), ("odd_s3", "flow"), ("mode_average_qvga_s1", "average"),
+                                         ("mode_average_long_s4", "average")])
+def test_monitor_live_mode_leaves_the_reference_attributes(fleet_cls, golden, name, method):
+    """RespiratoryMonitor(live=True): frames consumed `live_block` at a time from a capture object through a one-camera
+    fleet, in bounded memory -- the attributes the reference leaves behind on the same clip (golden) must come out the
+    same as from the whole-stream path (motion_data is not kept by the oracle-backed cohort of this CPU test; the GPU twin
+    in tests/test_gpu_monitor.py checks it)."""
+    from conftest import clip_from_fixture
+    LiveFleet, Monitor = fleet_cls
+    fix = golden(name)
+    spec, clip = clip_from_fixture(fix)
+
+    class Cap:
+        def __init__(self):
+            self.i = 0
+
+        def get(self, prop):
+            return {5: 10.0, 3: float(clip.shape[2]), 4: float(clip.shape[1])}.get(prop, 0.0)
+
+        def isOpened(self):
+            return True
+
+        def read(self):
+            if self.i >= len(clip):
+                return False, None
+            self.i += 1
+            return True, clip[self.i - 1]
+
+        def release(self):
+            pass
+
+    rm = Monitor(Cap(), visualize=None, save_all_data=False, motion_extraction_method=method, fps_limit=10, live=True,
+                 live_block=7)
+    assert (rm.x, rm.y, rm.w, rm.h) == tuple(int(v) for v in fix["roi"])
+    assert rm.state == "measure"
+    data = np.array(rm.data)
+    assert data.shape == fix["data"].shape and np.sqrt(np.mean((data - fix["data"]) ** 2)) <= 1e-6
+    np.testing.assert_allclose(np.array(rm.t), fix["t"], rtol=0, atol=1e-12)
+    assert len(rm.freq) == len(fix["freq"]) and np.max(np.abs(np.array(rm.freq) - fix["freq"])) <= 1e-6
+    assert [int(v) for v in rm.peak_indices] == [int(v) for v in fix["peaks"]]
+    np.testing.assert_allclose(np.asarray(rm.filtered_data), fix["filtered"], rtol=0, atol=1e-6)
