@@ -281,8 +281,9 @@ int32_t rm_pack_results_stream(rm_handle* h, const double* bpm, const int32_t* r
  *                                through HBM + the tail kernel.  Bit-identical records.
  *   "pyramid_cfg" (0..3)         fused kernel: (ring stages, warps per CTA) = by frame width (0, default) / (4, 18) / (3, 21) /
  *                                (2, 24).
- *   "pyramid_variants" (0..2)    fused kernel: interior strips run the edge-strip loop too (1), their own loop (2), or by
- *                                frame width (0, default).
+ *   "pyramid_g4" (0..2)          fused kernel: the level-4 image of a frame lives in shared memory (1), in the frame's
+ *                                record, where its Laplacian replaces it (2), or wherever more frame slots fit an SM (0,
+ *                                default: the record where shared memory would hold a single frame slot, 1080p).
  *   "force_global_lk" (0/1)      track from global memory even when the ROI fits shared memory (the path used for ROIs
  *                                too large to stage).
  *   "force_generic_front" (0/1)  uint8 frames take the float pyramid front kernel instead of the integer one.

@@ -175,7 +175,7 @@ extern "C" int32_t rm_set_option(rm_handle* h, const char* name, int64_t value) 
   if (strcmp(name, "force_global_lk") == 0) { h->force_global_lk = value != 0; return RM_OK; }
   if (strcmp(name, "force_generic_front") == 0) { h->force_generic_front = value != 0; return RM_OK; }
   if (strcmp(name, "pyramid_mode") == 0) { h->pyramid_mode = value != 0; return RM_OK; }
-  if (strcmp(name, "pyramid_variants") == 0) { h->pyramid_variants = value < 0 || value > 2 ? 0 : (int)value; return RM_OK; }
+  if (strcmp(name, "pyramid_g4") == 0) { h->pyramid_g4 = value < 0 || value > 2 ? 0 : (int)value; return RM_OK; }
   if (strcmp(name, "pyramid_cfg") == 0) { h->pyramid_cfg = value < 0 || value > 3 ? 0 : (int)value; return RM_OK; }
   if (strcmp(name, "no_minmax_seed") == 0) { h->no_minmax_seed = value != 0; return RM_OK; }
   if (strcmp(name, "temporal_sparse") == 0) { h->temporal_sparse = value != 0; return RM_OK; }

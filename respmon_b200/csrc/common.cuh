@@ -40,7 +40,8 @@ struct rm_handle {
   int no_minmax_seed;       // tests: pass 1 of the heat map without the seed kernel (no pruning at the start)
   int pyramid_mode;         // option "pyramid_mode": 1 = fused TMA kernel where the frames allow it (default), 0 = always the
                             // fallback (level 3 through HBM + pyramid_tail_kernel) -- tests compare the two bit for bit
-  int pyramid_variants;     // option "pyramid_variants": 0 = auto, 1 = one loop variant for all strips, 2 = interior + edge variants
+  int pyramid_g4;           // option "pyramid_g4": level-4 image of the fused kernel: 0 = where more frame slots fit (default),
+                            // 1 = shared memory, 2 = in the record
   int pyramid_cfg;          // option "pyramid_cfg": fused kernel's (ring stages, warps per CTA): 0 = by frame width (default),
                             // 1 = (4, 18), 2 = (3, 21), 3 = (2, 24)
   int force_global_lk;

@@ -299,7 +299,10 @@ __device__ __forceinline__ double* pf_level(const PfParams& p, unsigned char* lv
 __device__ __forceinline__ int pf_div(int i, unsigned m) { return m ? (int)__umulhi((unsigned)i, m) : i; }
 
 // G_{l+1} = pyrDown(G_l) on float64 (pyramid.py:13-15), the arithmetic of pyramid_tail_kernel
-__device__ __forceinline__ void pf_down(const double* __restrict__ s, double* __restrict__ d, int sw, int sh, int dw, int dh,
+// SRC_SMEM = false: s is global memory this kernel has just written (g4_global) -- not __restrict__, so that the loads
+// cannot become non-coherent ones
+template <bool SRC_SMEM>
+__device__ __forceinline__ void pf_down_t(const double* s, double* __restrict__ d, int sw, int sh, int dw, int dh,
                                         unsigned mdw, int t, int nt) {
   for (int i = t; i < dw * dh; i += nt) {
     const int y = pf_div(i, mdw), x = i - y * dw;
@@ -314,11 +317,17 @@ __device__ __forceinline__ void pf_down(const double* __restrict__ s, double* __
     d[i] = tap5(r[0], r[1], r[2], r[3], r[4]) * (1.0 / 256.0);
   }
 }
+__device__ __forceinline__ void pf_down(const double* __restrict__ s, double* __restrict__ d, int sw, int sh, int dw, int dh,
+                                        unsigned mdw, int t, int nt) {
+  pf_down_t<true>(s, d, sw, sh, dw, dh, mdw, t, nt);
+}
 // L_l = G_l - pyrUp(G_{l+1}) (pyramid.py:24-26), one thread per source pixel = 2x2 outputs from its 3x3 neighbourhood;
 // per output the operations of up_taps / up_combine (pyr_core.h) in their order:
 //   even index 2i: s[refl(i-1)] + s[min(i+1,n-1)], then fma(6, s[i], .);   odd index 2i+1: 4 * (s[i] + s[min(i+1,n-1)])
-__device__ __forceinline__ void pf_lap(const double* __restrict__ cur, const double* __restrict__ s, double* __restrict__ out,
-                                       int sw, int sh, int dw, int dh, unsigned msw, int t, int nt) {
+// IN_PLACE: cur is out (global memory: every thread reads the four values of `cur` it replaces)
+template <bool IN_PLACE>
+__device__ __forceinline__ void pf_lap_t(const double* cur, const double* __restrict__ s, double* out,
+                                         int sw, int sh, int dw, int dh, unsigned msw, int t, int nt) {
   for (int i = t; i < sw * sh; i += nt) {
     const int bj = pf_div(i, msw), bi = i - bj * sw;
     const int cm = reflect101(bi - 1, sw), cp = bi + 1 < sw - 1 ? bi + 1 : sw - 1;
@@ -345,12 +354,20 @@ __device__ __forceinline__ void pf_lap(const double* __restrict__ cur, const dou
   }
 }
 
+__device__ __forceinline__ void pf_lap(const double* __restrict__ cur, const double* __restrict__ s, double* __restrict__ out,
+                                       int sw, int sh, int dw, int dh, unsigned msw, int t, int nt) {
+  pf_lap_t<false>(cur, s, out, sw, sh, dw, dh, msw, t, nt);
+}
 // Levels first+1..top and the Laplacian record of one frame from the slot's level-`first` image, by the nt threads of
 // the slot (t = 0..nt-1).
-__device__ __noinline__ void pf_tail(const PfParams& p, unsigned char* lvl_slot, double* __restrict__ rec, int slot, int t,
-                                     int nt) {
+// The level-`first` image the stream wrote is in the slot's shared memory, or (G4G, PfParams::g4_global) in place in the
+// record, where its Laplacian replaces it.
+template <bool G4G>
+__device__ __noinline__ void pf_tail(const PfParams& p, unsigned char* lvl_slot, double* rec, int slot, int t, int nt) {
   const int f = p.first, top = p.top;
-  pf_down(pf_level(p, lvl_slot, f), pf_level(p, lvl_slot, f + 1), p.w[f], p.h[f], p.w[f + 1], p.h[f + 1], p.magic[f + 1], t, nt);
+  const double* g_first = G4G ? rec + p.rec_off[f] : pf_level(p, lvl_slot, f);
+  if (G4G) pf_down_t<false>(g_first, pf_level(p, lvl_slot, f + 1), p.w[f], p.h[f], p.w[f + 1], p.h[f + 1], p.magic[f + 1], t, nt);
+  else pf_down(g_first, pf_level(p, lvl_slot, f + 1), p.w[f], p.h[f], p.w[f + 1], p.h[f + 1], p.magic[f + 1], t, nt);
   pf_slot_sync(slot, nt);
   // the small levels are a chain of tiny images: one warp walks it while the others write the largest Laplacian
   if (t < 32) {
@@ -361,8 +378,12 @@ __device__ __noinline__ void pf_tail(const PfParams& p, unsigned char* lvl_slot,
   }
   if (nt == 32 || t >= 32) {
     const int t2 = nt == 32 ? t : t - 32, nt2 = nt == 32 ? 32 : nt - 32;
-    pf_lap(pf_level(p, lvl_slot, f), pf_level(p, lvl_slot, f + 1), rec + p.rec_off[f], p.w[f + 1], p.h[f + 1], p.w[f], p.h[f],
-           p.magic[f + 1], t2, nt2);
+    if (G4G)
+      pf_lap_t<true>(g_first, pf_level(p, lvl_slot, f + 1), rec + p.rec_off[f], p.w[f + 1], p.h[f + 1], p.w[f], p.h[f],
+                     p.magic[f + 1], t2, nt2);
+    else
+      pf_lap(g_first, pf_level(p, lvl_slot, f + 1), rec + p.rec_off[f], p.w[f + 1], p.h[f + 1], p.w[f], p.h[f],
+             p.magic[f + 1], t2, nt2);
   }
   pf_slot_sync(slot, nt);
   for (int l = f + 1; l < top; ++l)
@@ -370,74 +391,303 @@ __device__ __noinline__ void pf_tail(const PfParams& p, unsigned char* lvl_slot,
            p.magic[l + 1], t, nt);
 }
 
-struct PfLane {       // what a lane does with its level-3 / level-4 column
-  int s_m2, s_m1, s_p1, s_p2;   // source lanes of the level-3 columns col-2, col-1, col+1, col+2 (reflect-101 at the image border)
+// ---- per-lane constants of a strip's warp
+// Image borders are reflect-101.  In the fused kernel they cost no instructions in the stream: the lane that holds the
+// image's first / last column gets its own *filter weights* (the mirrored taps are folded onto the columns they mirror and
+// the neighbour's contribution is weighted zero) and its own shuffle source lanes, prepared once per kernel.
+struct PfLane {
+  int s_m2, s_m1, s_p1, s_p2;   // level 3: source lanes of columns col-2, col-1, col+1, col+2
   int k;                        // level-4 column the lane emits, -1: none
+  // level 0 (8 pixels per lane, w0 = pixels 0..3, w1 = 4..7, wl / wr = the neighbours' w1 / w0):
+  //   k0 = dp4a(wl, l0_wl) + dp4a(w0, l0_w0)        interior: (.,.,1,4) (6,4,1,.)     first lane: 0, (6,8,2,.)
+  //   k3 = dp4a(w1, l0_w1) + dp4a(wr, l0_wr)        interior: (1,4,6,4) (1,.,.,.)     last lane: (1,4,7,4), 0
+  unsigned l0_wl, l0_w0, l0_w1, l0_wr;
+  // level 1 (P = columns (0,1), Q = (2,3) as 16-bit pairs, Ql / Pr the neighbours' Q / P), byte pairs for dp2a lo | hi:
+  //   g0 = dp2a_lo(Ql, h1_a) + dp2a_hi(P, h1_a) + dp2a_lo(Q, h1_b)
+  //   g1 = dp2a_hi(P, h1_c) + dp2a_hi(Q, h1_b) + dp2a_lo(Pr, h1_c)
+  unsigned h1_a, h1_b, h1_c;
+  int h2_l0, h2_l1, h2_r0;      // level 2: source lanes of columns 2L-2, 2L-1 (q0 / q1 of the left lane) and 2L+2
 };
 
-// S-stage TMA ring: `stage` is the ring slot of the next block to consume, `phase` the parity awaited per slot.
-// Two instantiations: interior strips (no border code at all) and edge strips, whose image-border fix-ups in pu_block
-// are predicated on the lane (first_lane / last_lane = -1 where the strip lacks that border) instead of compiled per
-// kind of edge.  Three or four variants per CTA (left, interior, right, both) times an unrolled loop plus two peeled
-// copies for the mirrored blocks did not fit the 32 KB instruction cache level: 1.5 no_instruction stalls per issue,
-// 0.774 -> 0.708 ms per 8192 VGA frames with a single variant (r02g, r02h); the interior variant is what 720p / 1080p
-// frames (4 of 6, 7 of 9 strips) mostly run.
-template <int S, bool EDGE>
-__device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMap* tmap,
-                                             int sframe, int next_sframe, unsigned ring_s, const unsigned char* my,
-                                             unsigned mbar, unsigned& phase, int& stage, double* __restrict__ g4,
-                                             const PfLane& ln, int lane, int x0, int first_lane, int last_lane) {
-  const int nblk = p.H >> 3;
-  // block b (-2 .. nblk-1) of this frame, then blocks -2 .. of the next one: the ring never drains between frames
-  auto issue = [&](int b, int st) {
-    int z = sframe;
-    if (b >= nblk) { b -= nblk + 2; z = next_sframe; }
-    if (z < 0) return;
-    __syncwarp();                                              // every lane is done with the stage's previous rows
-    if (lane == 0) {
-      pu_mbar_expect_tx(mbar + 8 * st, PU_STAGE_BYTES);
-      // rows above the frame are the mirrored rows 16..9 / 8..1: fetched in frame order, read back bottom-up
-      pu_tma_load(ring_s + st * PU_STAGE_BYTES, tmap, x0, b >= 0 ? 8 * b : -8 * b - 7, z, mbar + 8 * st);
+__device__ __forceinline__ void pf_lane_setup(PfLane& ln, int lane, int col, int base, int W3, int first_lane, int last_lane,
+                                              int k0, int k1) {
+  ln.s_m2 = (reflect101(col - 2, W3) - base) & 31; ln.s_m1 = (reflect101(col - 1, W3) - base) & 31;
+  ln.s_p1 = (reflect101(col + 1, W3) - base) & 31; ln.s_p2 = (reflect101(col + 2, W3) - base) & 31;
+  ln.k = (!(col & 1) && (col >> 1) >= k0 && (col >> 1) < k1) ? (col >> 1) : -1;
+  const bool first = lane == first_lane, last = lane == last_lane;
+  ln.l0_wl = first ? 0u : 0x04010000u;  ln.l0_w0 = first ? 0x00020806u : 0x00010406u;
+  ln.l0_w1 = last ? 0x04070401u : 0x04060401u;  ln.l0_wr = last ? 0u : 0x00000001u;
+  ln.h1_a = first ? 0x08060000u : 0x04060401u;
+  ln.h1_b = (last ? 0x04070000u : 0x04060000u) | (first ? 0x0002u : 0x0001u);
+  ln.h1_c = last ? 0x04010000u : 0x04010001u;
+  ln.h2_l0 = first ? lane + 1 : (lane ? lane - 1 : 0);
+  ln.h2_l1 = first ? lane : (lane ? lane - 1 : 0);
+  ln.h2_r0 = last ? lane : (lane < 31 ? lane + 1 : 31);
+}
+
+// pu_block for the fused kernel: the same sums, image borders by the lane's weights (EDGE) or none at all
+template <bool EDGE>
+__device__ __forceinline__ void pf_block(PuState& s, const uint2 w[PU_ROWS], const PfLane& ln, unsigned& out3) {
+  unsigned ha[PU_ROWS], hb[PU_ROWS];
+#pragma unroll
+  for (int i = 0; i < PU_ROWS; ++i) {
+    const unsigned w0 = w[i].x, w1 = w[i].y;
+    const unsigned wl = __shfl_up_sync(0xffffffffu, w1, 1);
+    const unsigned wr = __shfl_down_sync(0xffffffffu, w0, 1);
+    const unsigned k0 = __dp4a(wl, EDGE ? ln.l0_wl : 0x04010000u, __dp4a(w0, EDGE ? ln.l0_w0 : 0x00010406u, 0u));
+    const unsigned k1 = __dp4a(w0, 0x04060401u, __dp4a(w1, 0x00000001u, 0u));
+    const unsigned k2 = __dp4a(w0, 0x04010000u, __dp4a(w1, 0x00010406u, 0u));
+    const unsigned k3 = __dp4a(w1, EDGE ? ln.l0_w1 : 0x04060401u, __dp4a(wr, EDGE ? ln.l0_wr : 0x00000001u, 0u));
+    ha[i] = k0 + (k1 << 16);       // (a byte permute instead of the shift-add, i.e. ALU instead of FMA pipe: +-1 %, r03c)
+    hb[i] = k2 + (k3 << 16);
+  }
+  unsigned P[4], Q[4];
+  P[0] = v5(s.a[0], s.a[1], s.a[2], s.a[3], ha[0]);
+  P[1] = v5(s.a[2], s.a[3], ha[0], ha[1], ha[2]);
+  P[2] = v5(ha[0], ha[1], ha[2], ha[3], ha[4]);
+  P[3] = v5(ha[2], ha[3], ha[4], ha[5], ha[6]);
+  Q[0] = v5(s.b[0], s.b[1], s.b[2], s.b[3], hb[0]);
+  Q[1] = v5(s.b[2], s.b[3], hb[0], hb[1], hb[2]);
+  Q[2] = v5(hb[0], hb[1], hb[2], hb[3], hb[4]);
+  Q[3] = v5(hb[2], hb[3], hb[4], hb[5], hb[6]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { s.a[i] = ha[4 + i]; s.b[i] = hb[4 + i]; }
+  unsigned n0[4], n1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned Ql = __shfl_up_sync(0xffffffffu, Q[i], 1);
+    const unsigned Pr = __shfl_down_sync(0xffffffffu, P[i], 1);
+    const unsigned a = EDGE ? ln.h1_a : 0x04060401u, b = EDGE ? ln.h1_b : 0x04060001u, c = EDGE ? ln.h1_c : 0x04010001u;
+    n0[i] = __dp2a_lo(Ql, a, __dp2a_hi(P[i], a, __dp2a_lo(Q[i], b, 0u)));
+    n1[i] = __dp2a_hi(P[i], c, __dp2a_hi(Q[i], b, __dp2a_lo(Pr, c, 0u)));
+  }
+  unsigned q0[2], q1[2];
+  q0[0] = v5(s.g0[0], s.g0[1], s.g0[2], n0[0], n0[1]);
+  q0[1] = v5(s.g0[2], n0[0], n0[1], n0[2], n0[3]);
+  q1[0] = v5(s.g1[0], s.g1[1], s.g1[2], n1[0], n1[1]);
+  q1[1] = v5(s.g1[2], n1[0], n1[1], n1[2], n1[3]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { s.g0[i] = n0[1 + i]; s.g1[i] = n1[1 + i]; }
+  unsigned m[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    unsigned ql0, ql1, qr0;
+    if (EDGE) {
+      ql0 = __shfl_sync(0xffffffffu, q0[i], ln.h2_l0); ql1 = __shfl_sync(0xffffffffu, q1[i], ln.h2_l1);
+      qr0 = __shfl_sync(0xffffffffu, q0[i], ln.h2_r0);
+    } else {
+      ql0 = __shfl_up_sync(0xffffffffu, q0[i], 1); ql1 = __shfl_up_sync(0xffffffffu, q1[i], 1);
+      qr0 = __shfl_down_sync(0xffffffffu, q0[i], 1);
     }
-  };
+    m[i] = v5(ql0, ql1, q0[i], q1[i], qr0);
+  }
+  out3 = v5(s.c[0], s.c[1], s.c[2], m[0], m[1]);
+  s.c[0] = s.c[2]; s.c[1] = m[0]; s.c[2] = m[1];
+}
+
+// bottom border of even-sized levels (pu_flush with the lane's weights)
+template <bool EDGE>
+__device__ __forceinline__ unsigned pf_flush(const PuState& s, const PfLane& ln) {
+  const unsigned P = v5(s.a[0], s.a[1], s.a[2], s.a[3], s.a[2]);
+  const unsigned Q = v5(s.b[0], s.b[1], s.b[2], s.b[3], s.b[2]);
+  const unsigned Ql = __shfl_up_sync(0xffffffffu, Q, 1);
+  const unsigned Pr = __shfl_down_sync(0xffffffffu, P, 1);
+  const unsigned a = EDGE ? ln.h1_a : 0x04060401u, b = EDGE ? ln.h1_b : 0x04060001u, c = EDGE ? ln.h1_c : 0x04010001u;
+  const unsigned n0 = __dp2a_lo(Ql, a, __dp2a_hi(P, a, __dp2a_lo(Q, b, 0u)));
+  const unsigned n1 = __dp2a_hi(P, c, __dp2a_hi(Q, b, __dp2a_lo(Pr, c, 0u)));
+  const unsigned q0 = v5(s.g0[0], s.g0[1], s.g0[2], n0, s.g0[2]);
+  const unsigned q1 = v5(s.g1[0], s.g1[1], s.g1[2], n1, s.g1[2]);
+  const unsigned ql0 = __shfl_sync(0xffffffffu, q0, ln.h2_l0), ql1 = __shfl_sync(0xffffffffu, q1, ln.h2_l1);
+  const unsigned qr0 = __shfl_sync(0xffffffffu, q0, ln.h2_r0);
+  const unsigned m = v5(ql0, ql1, q0, q1, qr0);
+  return v5(s.c[0], s.c[1], s.c[2], m, s.c[2]);
+}
+
+// ---- a warp's TMA ring: S stages of 8 rows x 256 bytes, one mbarrier per stage.  Everything here is warp-uniform.
+struct PfRing {
+  unsigned ring_s, mbar;   // shared-space addresses of stage 0 and of its mbarrier
+  unsigned lds;            // shared-space address of the lane's 8 bytes in row 0 of stage 0
+  unsigned soff;           // byte offset of the stage the next block is consumed from (stage * PU_STAGE_BYTES)
+  unsigned par;            // parity awaited on the stages of the current round of the ring
+  int fy, fz;              // next fetch: the box whose first row is fy of source frame fz (-1: nothing left)
+  int x0;                  // first pixel column of the strip's window
+};
+__device__ __forceinline__ bool pf_elect() {
+  unsigned ok;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok));
+  return ok != 0;
+}
+// the box at rows fy.. of frame fz into the stage at byte offset soff; all lanes are done with what the stage held
+__device__ __forceinline__ void pf_issue(const PfRing& r, const CUtensorMap* tmap, unsigned soff) {
+  __syncwarp();
+  if (pf_elect()) {
+    const unsigned bar = r.mbar + (soff >> 8);          // 8 bytes of barrier per 2048 bytes of stage
+    pu_mbar_expect_tx(bar, PU_STAGE_BYTES);
+    pu_tma_load(r.ring_s + soff, tmap, r.x0, r.fy, r.fz, bar);
+  }
+}
+// Fetch order of a frame: the mirrored lead-in rows 9..16 and 1..8 (read back bottom-up: rows 16..9 are rows -16..-9 of the
+// reflect-101 extension, 8..1 rows -8..-1), then rows 0.., 8.., ..., H-8..; then the next frame of the slot.
+__device__ __forceinline__ void pf_fetch_any(PfRing& r, const CUtensorMap* tmap, unsigned soff, int H, int next_sframe) {
+  if (r.fz >= 0) pf_issue(r, tmap, soff);
+  r.fy = r.fy == 9 ? 1 : (r.fy == 1 ? 0 : r.fy + 8);
+  if (r.fy == H) { r.fy = 9; r.fz = next_sframe; }
+}
+__device__ __forceinline__ uint2 pf_lds8(unsigned addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+// level 4 from the level-3 rows of the lane's column.  A level-3 row is filtered across the lanes in 64-bit integers and
+// continues in float64: every value is an integer below 2^41, so all sums are exact (= the 64-bit integer ones) and the
+// only rounding is the final scale by 2^-32 / 255.  Output row R = h[2R-2] + 4 h[2R-1] + 6 h[2R] + 4 h[2R+1] + h[2R+2] is
+// built in accumulators as the rows arrive: `cur` collects output r/2 (r even), `nxt` the one after.
+struct PfL4 {
+  double cur, nxt;
+};
+__device__ __forceinline__ double pf_l3_hfilter(unsigned o, const PfLane& ln) {
+  const unsigned a = __shfl_sync(0xffffffffu, o, ln.s_m2), b = __shfl_sync(0xffffffffu, o, ln.s_m1);
+  const unsigned d = __shfl_sync(0xffffffffu, o, ln.s_p1), e = __shfl_sync(0xffffffffu, o, ln.s_p2);
+  const unsigned long long hq = (unsigned long long)a + e + 4ull * ((unsigned long long)b + d) + 6ull * o;
+  return (double)(long long)hq;
+}
+// rows r >= 3 (no border left): odd rows add 4 h to both outputs; even rows complete output r/2 - 1
+template <bool ODD>
+__device__ __forceinline__ void pf_l4_row(PfL4& a, double h, int r, double* __restrict__ g4k, int W4, double g_scale) {
+  if (ODD) {
+    a.cur = fma(4.0, h, a.cur);
+    a.nxt = fma(4.0, h, a.nxt);
+  } else {
+    if (g4k) g4k[((r - 2) >> 1) * W4] = (a.cur + h) * g_scale;
+    a.cur = fma(6.0, h, a.nxt);
+    a.nxt = h;
+  }
+}
+// any row, including the top border (rows -2, -1 are rows 2, 1)
+__device__ __forceinline__ void pf_l4_row_any(PfL4& a, double h, int r, double* __restrict__ g4k, int W4, double g_scale) {
+  if (r == 0) { a.cur = 6.0 * h; a.nxt = h; }
+  else if (r == 1) { a.cur = fma(8.0, h, a.cur); a.nxt = fma(4.0, h, a.nxt); }
+  else if (r == 2) {
+    if (g4k) g4k[0] = fma(2.0, h, a.cur) * g_scale;
+    a.cur = fma(6.0, h, a.nxt);
+    a.nxt = h;
+  } else if (r & 1) pf_l4_row<true>(a, h, r, g4k, W4, g_scale);
+  else pf_l4_row<false>(a, h, r, g4k, W4, g_scale);
+}
+
+// One frame of one strip: blocks -2 .. nblk-1 of 8 rows.  The steady state (`hot`: blocks 4 .. nblk-S, in pairs) has no
+// special case left in it -- no mirrored rows, no level-4 border, fetches well inside the frame, and with STATIC (two stages, an
+// even number of blocks per frame) the ring stage of every block is a compile-time constant; the few blocks at either end of
+// the frame run one general (`cold`) copy of the body.
+template <int S, bool STATIC>
+__device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMap* tmap, PfRing& rg, int next_sframe,
+                                             double* __restrict__ g4k, const PfLane& ln) {
+  const int nblk = p.H >> 3, H = p.H;
   PuState s;
   pu_clear(s);
-  unsigned long long hz0 = 0, hz1 = 0, hz2 = 0, hz3 = 0;       // horizontally filtered level-3 rows r-4 .. r-1
+  PfL4 l4;
+  l4.cur = 0; l4.nxt = 0;
   const int W4 = p.w[p.first];
-  // one level-3 row (r = 0 .. H3-1) of the lane's column: filter across the lanes, every second row emit level 4
-  auto level3_row = [&](unsigned o, int r) {
-    const unsigned a = __shfl_sync(0xffffffffu, o, ln.s_m2), b = __shfl_sync(0xffffffffu, o, ln.s_m1);
-    const unsigned d = __shfl_sync(0xffffffffu, o, ln.s_p1), e = __shfl_sync(0xffffffffu, o, ln.s_p2);
-    const unsigned long long hz = (unsigned long long)a + e + 4ull * ((unsigned long long)b + d) + 6ull * o;
-    if (!(r & 1) && r >= 2) {
-      const unsigned long long v = r == 2 ? v5q(hz, hz3, hz2, hz3, hz) : v5q(hz0, hz1, hz2, hz3, hz);
-      if (ln.k >= 0) g4[((r - 2) >> 1) * W4 + ln.k] = (double)v * p.g_scale;
-    }
-    hz0 = hz1; hz1 = hz2; hz2 = hz3; hz3 = hz;
-  };
-  auto step = [&](int b, bool mirrored) {
-    // the stage consumed S-1 steps ago (block b-1) is free again: fetch block b+S-1 into it
-    issue(b + S - 1, stage == 0 ? S - 1 : stage - 1);
-    pu_mbar_wait(mbar + 8 * stage, (phase >> stage) & 1u);
-    phase ^= 1u << stage;
-    const unsigned char* src = my + stage * PU_STAGE_BYTES;
-    stage = stage + 1 == S ? 0 : stage + 1;
+  const double g_scale = p.g_scale;
+  auto cold = [&](int b) {
+    const unsigned prev = rg.soff == 0 ? (S - 1) * PU_STAGE_BYTES : rg.soff - PU_STAGE_BYTES;
+    pf_fetch_any(rg, tmap, prev, H, next_sframe);    // the stage consumed by the previous block takes block b+S-1
+    pu_mbar_wait(rg.mbar + (rg.soff >> 8), rg.par);
+    const bool mirrored = b < 0;
+    const unsigned src = rg.lds + rg.soff + (mirrored ? (PU_ROWS - 1) * 256 : 0);
+    const int rstep = mirrored ? -256 : 256;
     uint2 w[PU_ROWS];
 #pragma unroll
-    for (int i = 0; i < PU_ROWS; ++i) w[i] = *reinterpret_cast<const uint2*>(src + (mirrored ? PU_ROWS - 1 - i : i) * 256);
+    for (int i = 0; i < PU_ROWS; ++i) w[i] = pf_lds8(src + i * rstep);
+    rg.soff += PU_STAGE_BYTES;
+    if (rg.soff == S * PU_STAGE_BYTES) { rg.soff = 0; rg.par ^= 1u; }
     unsigned o;
-    pu_block<EDGE, EDGE>(s, w, lane, first_lane, last_lane, o);
-    if (b >= 1) level3_row(o, b - 1);
+    pf_block<true>(s, w, ln, o);
+    if (b >= 1) pf_l4_row_any(l4, pf_l3_hfilter(o, ln), b - 1, g4k, W4, g_scale);
   };
+  // hot pairs start at an even block (row b-1 odd, then row b even); the last one fetches block nblk-2 at most, so that
+  // the step past the frame's last box (next frame, mirrored rows) is the general body's
+  const int hot_end = nblk - S - ((nblk - S) & 1);
+  const int lead_end = nblk < 4 ? nblk : 4;
+  int b = -2;
 #pragma unroll 1
-  for (int b = -2; b < 0; ++b) step(b, true);                  // one cold copy of the body for the two mirrored blocks
-#pragma unroll 2
-  for (int b = 0; b < nblk; ++b) step(b, false);
-  const int H3 = nblk;
-  level3_row(pu_flush<EDGE, EDGE>(s, lane, first_lane, last_lane), H3 - 1);
-  // bottom border of level 4: hz3 = row H3-1, hz2 = H3-2, ...
-  const unsigned long long v = (H3 & 1) ? v5q(hz1, hz2, hz3, hz2, hz1) : v5q(hz0, hz1, hz2, hz3, hz2);
-  if (ln.k >= 0) g4[((H3 - 1) >> 1) * W4 + ln.k] = (double)v * p.g_scale;
+  for (; b < lead_end; ++b) cold(b);
+  if (hot_end > 4) {
+#pragma unroll 1
+    for (; b < hot_end; b += 2) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        // STATIC: block b+j is consumed from stage j and its predecessor's stage, 1 - j, takes block b+j+1
+        const unsigned soff = STATIC ? j * PU_STAGE_BYTES : rg.soff;
+        const unsigned prev = STATIC ? (1 - j) * PU_STAGE_BYTES : (soff == 0 ? (S - 1) * PU_STAGE_BYTES : soff - PU_STAGE_BYTES);
+        pf_issue(rg, tmap, prev);
+        rg.fy += 8;
+        pu_mbar_wait(rg.mbar + (soff >> 8), rg.par);
+        const unsigned src = rg.lds + soff;
+        uint2 w[PU_ROWS];
+#pragma unroll
+        for (int i = 0; i < PU_ROWS; ++i) w[i] = pf_lds8(src + i * 256);
+        if (STATIC) {
+          if (j == 1) rg.par ^= 1u;
+        } else {
+          rg.soff += PU_STAGE_BYTES;
+          if (rg.soff == S * PU_STAGE_BYTES) { rg.soff = 0; rg.par ^= 1u; }
+        }
+        unsigned o;
+        pf_block<true>(s, w, ln, o);
+        const double h = pf_l3_hfilter(o, ln);
+        if (j == 0) pf_l4_row<true>(l4, h, b - 1, g4k, W4, g_scale);
+        else pf_l4_row<false>(l4, h, b, g4k, W4, g_scale);
+      }
+    }
+  }
+#pragma unroll 1
+  for (; b < nblk; ++b) cold(b);
+  // The last level-3 row (r = H3 - 1) comes out of the flush; it also closes level 4, whose last output row needs the rows
+  // below the image: H3 odd (r even):  rows r+1, r+2 are rows r-1, r-2:  out = 6 h + 2 (h[r-2] + 4 h[r-1]) = 6 h + 2 nxt;
+  //                  H3 even (r odd):  row r+1 is row r-1:               out = cur + 4 h + h[r-1]          = cur + 4 h + nxt.
+  const int r = nblk - 1;
+  const double h = pf_l3_hfilter(pf_flush<true>(s, ln), ln);
+  if (g4k) {
+    if (r & 1) g4k[(r >> 1) * W4] = (fma(4.0, h, l4.cur) + l4.nxt) * g_scale;
+    else {
+      g4k[((r - 2) >> 1) * W4] = (r == 2 ? fma(2.0, h, l4.cur) : l4.cur + h) * g_scale;
+      g4k[(r >> 1) * W4] = fma(6.0, h, l4.nxt + l4.nxt) * g_scale;
+    }
+  }
+}
+
+// the frames of one slot's strip warp, one after the other
+template <int S, bool G4G>
+__device__ __forceinline__ void pf_frames(const PfParams& p, const CUtensorMap& tmap, PfRing& rg, const PfLane& ln,
+                                          unsigned char* lvl_slot, int slot, int strip, int lane) {
+  const int nt = p.n_strips * 32, t = strip * 32 + lane;
+  const long long stride = (long long)gridDim.x * p.frames_per_cta;
+  long long frame = (long long)blockIdx.x * p.frames_per_cta + slot;
+  rg.fy = 9;
+  rg.fz = frame < p.n_frames ? (int)pu_source_frame(frame, p.seg_len, p.seg_stride, p.seg_first) : -1;
+  {   // the first S-1 blocks of the slot's first frame
+    const int next0 = frame + stride < p.n_frames ? (int)pu_source_frame(frame + stride, p.seg_len, p.seg_stride, p.seg_first) : -1;
+#pragma unroll
+    for (int i = 0; i < S - 1; ++i) pf_fetch_any(rg, &tmap, i * PU_STAGE_BYTES, p.H, next0);
+  }
+  // two stages and an even number of 8-row blocks per frame (+ the 2 lead-in blocks): every frame starts on stage 0
+  const bool static_ring = S == 2 && !((p.H >> 3) & 1);
+  double* g4_smem = pf_level(p, lvl_slot, p.first);
+  for (; frame < p.n_frames; frame += stride) {
+    const int next_sframe = frame + stride < p.n_frames ? (int)pu_source_frame(frame + stride, p.seg_len, p.seg_stride, p.seg_first) : -1;
+    double* rec = p.lap_out + frame * p.record_len;
+    double* g4 = G4G ? rec + p.rec_off[p.first] : g4_smem;
+    double* g4k = ln.k >= 0 ? g4 + ln.k : nullptr;               // the lane's level-4 column, if it emits one
+    if (S == 2 && static_ring) pf_run_frame<S, S == 2>(p, &tmap, rg, next_sframe, g4k, ln);
+    else pf_run_frame<S, false>(p, &tmap, rg, next_sframe, g4k, ln);
+    // The barrier that completes the level-4 image also re-aligns the strips of the frame (they share halo columns:
+    // left alone they drift apart until a halo sector has left L2 before the neighbour asks for it, profiles/r01g).
+    pf_slot_sync(slot, nt);
+    pf_tail<G4G>(p, lvl_slot, rec, slot, t, nt);
+    pf_slot_sync(slot, nt);                                    // the level images are free for the next frame
+  }
 }
 
 // MAXW warps per CTA; registers are allocated to warps four at a time: 65536 / (32 * MAXW rounded up to 4), rounded down
@@ -447,61 +697,35 @@ __global__ void __maxnreg__((65536 / (32 * ((MAXW + 3) & ~3))) & ~7)
     pyramid_u8_fused_kernel(const __grid_constant__ PfParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   // the warp index through a shuffle: the compiler then knows that everything derived from it (strip, slot, ring and
-  // barrier addresses, frame numbers, TMA coordinates) is warp-uniform and keeps it in uniform registers
+  // barrier addresses, frame numbers, TMA coordinates) is warp-uniform
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int slot = warp / p.n_strips, strip = warp - slot * p.n_strips;
   const bool left = strip == 0, right = strip == p.n_strips - 1;
   const int base = p.strip_base[strip];
-  const int col = base + lane;
-  const int first_lane = left ? 0 : -1;                         // lanes holding the image's first / last level-3 column
-  const int last_lane = right ? p.W3 - 1 - base : -1;
   PfLane ln;
-  ln.s_m2 = (reflect101(col - 2, p.W3) - base) & 31; ln.s_m1 = (reflect101(col - 1, p.W3) - base) & 31;
-  ln.s_p1 = (reflect101(col + 1, p.W3) - base) & 31; ln.s_p2 = (reflect101(col + 2, p.W3) - base) & 31;
-  ln.k = (!(col & 1) && (col >> 1) >= p.strip_k0[strip] && (col >> 1) < p.strip_k1[strip]) ? (col >> 1) : -1;
-  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(smem) + warp * S * PU_STAGE_BYTES;
-  const unsigned char* my = smem + (size_t)warp * S * PU_STAGE_BYTES + lane * 8;
-  const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem + p.mbar_base) + warp * S * 8;
+  // lanes holding the image's first / last level-3 column (-1: the strip lacks that border)
+  pf_lane_setup(ln, lane, base + lane, base, p.W3, left ? 0 : -1, right ? p.W3 - 1 - base : -1, p.strip_k0[strip],
+                p.strip_k1[strip]);
+  const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+  PfRing rg;
+  rg.ring_s = smem_s + warp * S * PU_STAGE_BYTES;
+  rg.lds = rg.ring_s + lane * 8;
+  rg.mbar = smem_s + p.mbar_base + warp * S * 8;
+  rg.soff = 0; rg.par = 0;
+  rg.x0 = 8 * base;
   if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < S; ++i) pu_mbar_init(mbar + 8 * i, 1);
+    for (int i = 0; i < S; ++i) pu_mbar_init(rg.mbar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   }
   __syncthreads();
   unsigned char* lvl_slot = smem + p.lvl_base + (size_t)slot * p.lvl_stride;
-  double* g4 = pf_level(p, lvl_slot, p.first);
-  const int nt = p.n_strips * 32, t = strip * 32 + lane;
-  const long long stride = (long long)gridDim.x * p.frames_per_cta;
-  long long frame = (long long)blockIdx.x * p.frames_per_cta + slot;
-  unsigned phase = 0;
-  int stage = 0;
-  if (frame < p.n_frames) {   // the first S-1 blocks of the slot's first frame
-    const int z = (int)pu_source_frame(frame, p.seg_len, p.seg_stride, p.seg_first);
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < S - 1; ++i) {
-        const int b = i - 2;
-        pu_mbar_expect_tx(mbar + 8 * i, PU_STAGE_BYTES);
-        pu_tma_load(ring_s + i * PU_STAGE_BYTES, &tmap, 8 * base, b >= 0 ? 8 * b : -8 * b - 7, z, mbar + 8 * i);
-      }
-    }
-  }
-  for (; frame < p.n_frames; frame += stride) {
-    const int sframe = (int)pu_source_frame(frame, p.seg_len, p.seg_stride, p.seg_first);
-    const int next_sframe = frame + stride < p.n_frames ? (int)pu_source_frame(frame + stride, p.seg_len, p.seg_stride, p.seg_first) : -1;
-    if (left || right || p.one_variant)
-      pf_run_frame<S, true>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, first_lane,
-                            last_lane);
-    else
-      pf_run_frame<S, false>(p, &tmap, sframe, next_sframe, ring_s, my, mbar, phase, stage, g4, ln, lane, 8 * base, first_lane,
-                             last_lane);
-    // The barrier that completes the level-4 image also re-aligns the strips of the frame (they share halo columns:
-    // left alone they drift apart until a halo sector has left L2 before the neighbour asks for it, profiles/r01g).
-    pf_slot_sync(slot, nt);
-    pf_tail(p, lvl_slot, p.lap_out + frame * p.record_len, slot, t, nt);
-    pf_slot_sync(slot, nt);                                    // the level images are free for the next frame
-  }
+  // Level 4 of a frame goes to the slot's shared memory, or -- wide frames, whose level-4 image (65 KB at 1080p) would leave
+  // room for one frame slot per SM -- straight into the frame's record, where the tail turns it into its Laplacian in
+  // place.  Two instantiations, so that every access keeps its address space (a launch runs one of them).
+  if (p.g4_global) pf_frames<S, true>(p, tmap, rg, ln, lvl_slot, slot, strip, lane);
+  else pf_frames<S, false>(p, tmap, rg, ln, lvl_slot, slot, strip, lane);
 }
 
 // ==================================================================================================== host side
@@ -527,14 +751,20 @@ static bool pf_plan(rm_handle* h, int W, int H, PfPlan& pl) {
   p.first = s; p.top = L - 1; p.record_len = rec.len;
   p.g_scale = 1.0 / 255;
   for (int l = 0; l < s; ++l) p.g_scale *= 1.0 / 256.0;
-  int lvl_bytes = 0;
   for (int l = 0; l < L; ++l) {
     p.w[l] = g.w[l]; p.h[l] = g.h[l]; p.rec_off[l] = rec.off[l];
     p.magic[l] = g.w[l] > 1 ? (unsigned)((0x100000000ull + g.w[l] - 1) / g.w[l]) : 0u;
-    if (l >= s) { p.lvl_off[l] = lvl_bytes; lvl_bytes += g.w[l] * g.h[l] * 8; }
     if (l >= s && (long long)g.w[l] * g.h[l] >= 65536) return false;      // pf_div
   }
-  lvl_bytes = (lvl_bytes + 15) & ~15;
+  // level images of a slot: levels first..top, or first+1..top with level `first` in the record (g4_global)
+  auto layout = [&](bool g4_global) {
+    int bytes = 0;
+    for (int l = s; l < L; ++l) {
+      if (l == s && g4_global) { p.lvl_off[l] = 0; continue; }
+      p.lvl_off[l] = bytes; bytes += g.w[l] * g.h[l] * 8;
+    }
+    return (bytes + 15) & ~15;
+  };
   // strips in level-4 columns
   const int K = g.w[s];
   int n = 0, k0 = 0;
@@ -549,22 +779,27 @@ static bool pf_plan(rm_handle* h, int W, int H, PfPlan& pl) {
     k0 = k1; ++n;
   }
   p.n_strips = n;
-  // Few strips per frame are mostly edge strips: let the interior ones run the edge code too (one hot loop in the
-  // instruction cache instead of two): 0.734 -> 0.708 ms per 8192 VGA frames; wide frames keep the lean interior loop.
-  p.one_variant = h->pyramid_variants == 1 || (h->pyramid_variants == 0 && n <= 3);
   // ring depth / warps per CTA: as many frame slots as shared memory, the register file and 15 named barriers allow
   const int cfg[3][2] = {{4, 18}, {3, 21}, {2, 24}};            // (stages, max warps)
-  // measured (r02l): frames of up to three strips (VGA: 3 x 8 slots) want the most warps, 2 stages x 24 warps -- 0.667 ms
-  // per 8192 VGA frames against 0.749 with 4 x 18; wider frames, whose level images leave room for few slots anyway,
-  // want the deep ring and the 96 registers: 720p 0.527 against 0.605 ms per 2048 frames, 1080p 0.783 against 0.880
-  int pick = h->pyramid_cfg >= 1 && h->pyramid_cfg <= 3 ? h->pyramid_cfg - 1 : (n <= 3 ? 2 : 0);
+  auto slots = [&](int S, int maxw, bool g4_global) {
+    int want = maxw / n;
+    if (want > 15) want = 15;
+    const int per_slot = n * S * PU_STAGE_BYTES + layout(g4_global) + n * S * 8;
+    const int fit = (h->smem_optin - 256) / per_slot;
+    return want < fit ? want : fit;
+  };
+  // measured (profiles/r03_pyramid_configs.txt): frames of up to three strips (VGA: 3 x 8 slots) want the most warps, 2 stages
+  // x 24 warps (0.586 against 0.676 ms per 8192 VGA frames with 4 x 18); wider frames want the deep ring and 96 registers
+  // as long as two frames fit an SM with their level-4 images in shared memory (720p: 0.479 against 0.523 ms per 2048
+  // frames); where only one would (1080p: a 65 KB level-4 image), level 4 goes to the record instead and the shallow ring
+  // leaves the L1 cache it is then read through (0.639 against 0.723 ms per 1024 frames).
+  int pick = h->pyramid_cfg >= 1 && h->pyramid_cfg <= 3 ? h->pyramid_cfg - 1 : (n <= 3 || slots(4, 18, false) < 2 ? 2 : 0);
   for (int tries = 0; tries < 3; ++tries, pick = (pick + 1) % 3) {
     const int S = cfg[pick][0], maxw = cfg[pick][1];
-    const int per_slot = n * S * PU_STAGE_BYTES + lvl_bytes + n * S * 8;
-    int fpc = maxw / n;
-    const int fit = (h->smem_optin - 256) / per_slot;
-    if (fpc > fit) fpc = fit;
-    if (fpc > 15) fpc = 15;
+    const int in_smem = slots(S, maxw, false), in_rec = slots(S, maxw, true);
+    p.g4_global = h->pyramid_g4 == 2 || (h->pyramid_g4 == 0 && in_smem < 2 && in_rec > in_smem);
+    const int fpc = p.g4_global ? in_rec : in_smem;
+    const int lvl_bytes = layout(p.g4_global != 0);
     if (fpc < 1) continue;
     p.frames_per_cta = fpc;
     pl.warps = fpc * n; pl.stages = S; pl.maxw = maxw;

@@ -23,10 +23,10 @@ struct PfParams {          // fused kernel: frames -> packed Laplacian records
   long long n_frames, seg_len, seg_stride, seg_first;
   int W, H, W3, H3;
   int n_strips, frames_per_cta;
-  int one_variant;         // interior strips run the edge instantiation too (see pf_run_frame)
   int strip_base[16];      // level-3 column held by lane 0 of the strip's warp (even)
   int strip_k0[16], strip_k1[16];   // level-`first` columns [k0, k1) the strip emits
   int first, top;          // Gaussian levels first..top are built; Laplacian levels first..top-1 are written
+  int g4_global;           // level `first` is written into the record (and turned into its Laplacian there), not into shared memory
   int w[RM_MAX_LEVELS], h[RM_MAX_LEVELS], rec_off[RM_MAX_LEVELS];
   int lvl_off[RM_MAX_LEVELS];       // byte offset of Gaussian level l inside a slot's level images
   unsigned magic[RM_MAX_LEVELS];    // ceil(2^32 / w[l])

@@ -93,13 +93,17 @@ def test_integer_front_is_bit_identical_to_float64_front(eng, w, h):
 
 @pytest.mark.parametrize("w,h,n_clips,T", [(640, 480, 23, 5), (320, 240, 40, 4), (1280, 720, 7, 4), (1920, 1080, 3, 4),
                                            (328, 200, 5, 4), (64, 24, 9, 4), (16, 24, 33, 4), (240, 136, 6, 4),
-                                           (2048, 64, 3, 4), (464, 72, 5, 3), (32, 200, 7, 3)])
+                                           (2048, 64, 3, 4), (464, 72, 5, 3), (32, 200, 7, 3), (96, 32, 9, 4),
+                                           (160, 40, 9, 4), (80, 48, 9, 4), (176, 56, 5, 4), (48, 80, 900, 4),
+                                           (640, 480, 420, 4), (1280, 720, 150, 3)])
 def test_pyramid_kernels_are_bit_identical(eng, w, h, n_clips, T):
     """The forms of the uint8 pyramid stage -- the fused TMA kernel (frame -> record in one pass: cp.async.bulk.tensor rows,
     integer levels 0..4, the rest in shared memory) in its three ring / occupancy configurations, and the fallback (level
     3 through HBM + pyramid_tail_kernel) -- write the same packed Laplacian records bit for bit, over more frames than
-    one wave of CTAs holds, for windows of clips (first frame 1), odd level sizes (H/8 = 17, 9, 25) and sizes the fused
-    kernel cannot take (328: rows are not 16-byte multiples) where it falls back.  The float64 front is the last witness."""
+    one wave of CTAs holds, for windows of clips (first frame 1), odd level sizes (H/8 = 17, 9, 25), every frame height
+    from 3 to 10 blocks of 8 rows (the steady-state loop of the fused kernel starts at block 4 and ends 1..3 blocks before
+    the frame does; below that only its general body runs) and sizes the fused kernel cannot take (328: rows are not
+    16-byte multiples) where it falls back.  The float64 front is the last witness."""
     rng = np.random.default_rng(w * 7 + h)
     clips = rng.integers(0, 256, (n_clips, T, h, w)).astype(np.uint8)
     clips[0, 1] = 255
@@ -111,23 +115,23 @@ def test_pyramid_kernels_are_bit_identical(eng, w, h, n_clips, T):
         out["split"] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
         eng.set_option("pyramid_mode", 1)
         for cfg in (0, 1, 2, 3):
-            for variants in (1, 2):
+            for g4 in (0, 1, 2):              # level 4 where more frame slots fit / in shared memory / in the record
                 eng.set_option("pyramid_cfg", cfg)
-                eng.set_option("pyramid_variants", variants)
-                out["fused%d/%d" % (cfg, variants)] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
+                eng.set_option("pyramid_g4", g4)
+                out["fused%d/%d" % (cfg, g4)] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
         eng.set_option("force_generic_front", 1)
         out["f64"] = eng.pyramid_build_clips(d, 1, T - 1).cpu().numpy()
     finally:
         eng.set_option("pyramid_mode", 1)
         eng.set_option("pyramid_cfg", 0)
-        eng.set_option("pyramid_variants", 0)
+        eng.set_option("pyramid_g4", 0)
         eng.set_option("force_generic_front", 0)
     for k in out:
         assert np.array_equal(out["split"], out[k]), "%s differs from the split path in %d values" % (
             k, int((out["split"] != out[k]).sum()))
     lap = P.laplacian_levels(P.u8_to_unit(clips[-1, 2]), 9)
     for (l, lw, lh, off) in eng.record_levels(w, h):
-        assert np.abs(out["fused0/1"][-1, 1, off:off + lw * lh].reshape(lh, lw) - lap[l]).max() <= 2e-14
+        assert np.abs(out["fused0/0"][-1, 1, off:off + lw * lh].reshape(lh, lw) - lap[l]).max() <= 2e-14
 
 
 def test_pyramid_kernels_agree_on_random_sizes(eng):

@@ -28,7 +28,7 @@ base = None
 for mode in [int(m) for m in os.environ.get('RM_MODES', '-1,0,1,2,3').split(',')]:
     eng.set_option("pyramid_mode", 0 if mode < 0 else 1)
     eng.set_option("pyramid_cfg", max(mode, 0))
-    eng.set_option("pyramid_variants", int(os.environ.get("RM_VARIANTS", "0")))
+    eng.set_option("pyramid_g4", int(os.environ.get("RM_G4", "0")))
     out = eng.pyramid_build_clips(clips, first, length)
     for _ in range(3):
         eng.pyramid_build_clips(clips, first, length)
