@@ -114,7 +114,10 @@ int32_t rm_bgr_to_gray(rm_handle* h, const uint8_t* bgr, uint8_t* gray_out, int6
 /* `cropped_image = current_frame[y:y+h, x:x+w]` (base.py:471) for a run of frames of every clip: frames (n_clips,T,H,W) of
  * RM_U8, or (n_clips,T,H,W,3) of RM_BGR8 -- then cv2.cvtColor(BGR2GRAY) of next_frame (base.py:230) is applied to the ROI's
  * pixels only --, roi (n_clips,4) x,y,w,h -> out (n_clips, n_frames, out_h, out_w) uint8, crops top-left aligned.  The
- * measure entry points take `out` as their frames with ROI origin (0,0). */
+ * measure entry points take `out` as their frames with ROI origin (0,0).  `frames` (here and in rm_crop_frames_ragged) may
+ * be PINNED HOST memory (cudaHostAlloc / cudaHostRegister: device-addressable under unified addressing): the crop is then
+ * the upload of the measure frames -- only the ROI's rows cross PCIe, as aligned words of one request per row, the ROI
+ * never visits the host and no staging copy is made. */
 int32_t rm_crop_frames(rm_handle* h, const void* frames, int32_t dtype, int32_t n_clips, int32_t T, int32_t W, int32_t H,
                        const int32_t* roi, int32_t first_frame, int32_t n_frames, uint8_t* out, int32_t out_w,
                        int32_t out_h, void* stream);

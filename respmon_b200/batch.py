@@ -62,10 +62,16 @@ class BatchMonitor:
     Only the bytes the path reads cross PCIe: the calibration window of every clip (frames cal_first ..
     cal_first+cal_len-1, base.py:429-434) goes up first; once locate() has produced the ROI, the measure frames go up
     as ROI crops -- the reference itself only ever looks at `frame[y:y+h, x:x+w]` of those frames (base.py:471).
-    Uploads run on a copy stream and overlap the kernels of the previous chunk (two buffers of each kind)."""
+    Uploads run on a copy stream and overlap the kernels of the previous chunk (two buffers of each kind).
+
+    Clips in PINNED host memory take the mapped path (`mapped=True`): the crop kernel reads the ROI's rows of the measure
+    frames straight out of the host buffer (pinned memory is device-addressable), so the ROI never visits the host, no
+    staging copy is made and submit() does not wait for anything -- the host -> device queue never drains between chunks
+    or batches.  The crop tensors are sized by `roi_cap` (w, h), which grows to the largest ROI seen; a batch in which
+    an ROI exceeded it is noticed in collect() and its chunk re-run through the staged path."""
 
     def __init__(self, device: int | None = None, chunk_clips: int = 32, method: str = "flow", crop_upload: bool = True,
-                 measure_streams: int = 2, measure_chunks: int = 4, **hyper):
+                 measure_streams: int = 2, measure_chunks: int = 4, mapped: bool = True, roi_cap: tuple = (64, 64), **hyper):
         self.engine = Engine(device, **hyper)
         self._measure_engines = [Engine(self.engine.device_index, **hyper) for _ in range(max(1, measure_streams))]
         for e in self._measure_engines:
@@ -75,10 +81,14 @@ class BatchMonitor:
         self.chunk_clips = int(chunk_clips)
         self.method = method
         self.crop_upload = bool(crop_upload)
+        self.mapped = bool(mapped)
+        self.roi_cap = (int(roi_cap[0]), int(roi_cap[1]))
+        self.reruns = 0                  # chunks re-run because an ROI exceeded roi_cap
         self._bufs = {}
         self._pinned = {}
         self._ev = None
         self._copy_stream = torch.cuda.Stream(self.engine.device)
+        self._read_stream = torch.cuda.Stream(self.engine.device)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -147,6 +157,8 @@ class BatchMonitor:
             if isinstance(host, list):
                 host = torch.stack(host)
             return dict(done=self._run_full_frames(host, fps, cal_first, cal_len))
+        if self.mapped and (all(c.is_pinned() for c in host) if isinstance(host, list) else host.is_pinned()):
+            return self._submit_mapped(host, n, T, H, W, fps, cal_first, cal_len)
         eng = self.engine
         dev = eng.device
         main = torch.cuda.current_stream(dev)
@@ -239,11 +251,134 @@ class BatchMonitor:
         """Wait for a submitted batch and read its records back (the device->host read of the step's result)."""
         if "done" in ticket:
             return ticket["done"]
+        if "mapped" in ticket:
+            return self._collect_mapped(ticket)
         main = torch.cuda.current_stream(self.engine.device)
         for e in ticket["done_events"]:
             main.wait_event(e)
         out = ticket["records"].cpu().numpy().view(RESULT_DTYPE).reshape(-1)
         self.d2h_bytes += ticket["records"].numel()
+        ticket["keep"] = None
+        return out
+
+    # ------------------------------------------------------------------ mapped path (clips in pinned host memory)
+    def _submit_mapped(self, host, n, T, H, W, fps, cal_first, cal_len):
+        """Per chunk: calibration window H2D (copy stream) -> locate() (caller's stream) -> on one of the measure streams:
+        crop kernel reading the ROI's rows of the measure frames from the mapped host buffer, LK measure + BPM, records.
+        Nothing here waits on the host: buffers pass from chunk to chunk and batch to batch through events."""
+        from . import _cabi
+        from .engine import RM_U8, _ptr
+        import ctypes as C
+        eng = self.engine
+        dev = eng.device
+        main = torch.cuda.current_stream(dev)
+        copy = self._copy_stream
+        n_ms = len(self._measure_streams)
+        measure_first = cal_first + cal_len + 1
+        n_meas = T - measure_first
+        chunks = self._chunk_schedule(n)
+        E = self._slot_events()
+        used = self._used
+        records = torch.empty((n, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        keep = [host]
+        seq0 = self._seq
+        cap_w, cap_h = min(W, self.roi_cap[0]), min(H, self.roi_cap[1])
+        as_list = isinstance(host, list)
+
+        def upload_cal(i):
+            lo, hi = chunks[i]
+            slot = (seq0 + i) & 1
+            dst = self._buffer(("cal", slot), (hi - lo, cal_len, H, W))
+            with torch.cuda.stream(copy):
+                if used["cal"][slot]:
+                    copy.wait_event(E["cal_freed"][slot])         # locate() of the chunk that last used this buffer is done
+                for c in range(lo, hi):                           # one contiguous block per clip
+                    dst[c - lo].copy_(host[c][cal_first:cal_first + cal_len], non_blocking=True)
+                E["cal_ready"][slot].record(copy)
+            used["cal"][slot] = True
+            self.h2d_bytes += dst.numel()
+            return dst
+
+        pending = upload_cal(0) if chunks else None
+        for i, (lo, hi) in enumerate(chunks):
+            slot, ms = (seq0 + i) & 1, (seq0 + i) % n_ms
+            cal = pending
+            if i + 1 < len(chunks):
+                pending = upload_cal(i + 1)
+            m = hi - lo
+            main.wait_event(E["cal_ready"][slot])
+            roi, status, _ = eng.locate(cal, fps, 0, cal_len)
+            E["cal_freed"][slot].record(main)
+            E["roi_done"][slot].record(main)
+            mstream, meng = self._measure_streams[ms], self._measure_engines[ms]
+            with torch.cuda.stream(mstream):
+                mstream.wait_event(E["roi_done"][slot])
+                if as_list:
+                    descs = (_cabi.RmClipDesc * m)()
+                    for k in range(m):
+                        descs[k] = _cabi.RmClipDesc(host[lo + k].data_ptr(), W, H, T, W)   # base = NULL: absolute addresses
+                    d_descs = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(dev, non_blocking=True)
+                    crops = torch.zeros((m, n_meas, cap_h, cap_w), dtype=torch.uint8, device=dev)
+                    meng._call("rm_crop_frames_ragged", C.c_void_p(0), RM_U8, _ptr(d_descs), m, _ptr(roi), measure_first,
+                               n_meas, _ptr(crops), cap_w, cap_h, meng._stream())
+                    keep.append(d_descs)
+                else:
+                    crops = meng.crop_frames(host[lo:hi], roi, measure_first, n_meas, out_size=(cap_w, cap_h))
+                roi0 = roi.clone()
+                roi0[:, :2] = 0                                   # the crop's own origin
+                st = status.clone()
+                if self.method == "flow":
+                    sig = meng.measure_signal(crops, roi0, 0, n_meas, fps, status=st, max_roi=(cap_w, cap_h))
+                    data = sig["data"]
+                else:
+                    data = meng.measure_average(crops, roi0, 0, n_meas)
+                    sig = meng.signal_bpm(data, fps, status=st)
+                meng.pack_results(sig["bpm"], roi, st, sig["npeaks"], out=records[lo:hi])
+            keep.append((roi, status, roi0, st, data, sig, crops))
+        self._seq = seq0 + len(chunks)
+        done = []
+        for mstream in self._measure_streams:
+            e = torch.cuda.Event()
+            e.record(mstream)
+            done.append(e)
+        return dict(records=records, done_events=done, keep=keep, chunks=chunks, cap=(cap_w, cap_h),
+                    mapped=dict(host=host, fps=fps, cal_first=cal_first, cal_len=cal_len, n_meas=n_meas, W=W))
+
+    def _collect_mapped(self, ticket) -> np.ndarray:
+        # read back on a stream of its own: the caller's stream may already hold the next batch's locate() calls, which
+        # wait for uploads that have not happened yet
+        rd = self._read_stream
+        rec = ticket["records"]
+        host_rec = torch.empty(rec.shape, dtype=torch.uint8).pin_memory() if rec.numel() else torch.empty(rec.shape, dtype=torch.uint8)
+        with torch.cuda.stream(rd):
+            for e in ticket["done_events"]:
+                rd.wait_event(e)
+            host_rec.copy_(rec, non_blocking=True)
+        rd.synchronize()
+        out = host_rec.numpy().view(RESULT_DTYPE).reshape(-1).copy()
+        self.d2h_bytes += rec.numel()
+        a = ticket["mapped"]
+        cap_w, cap_h = ticket["cap"]
+        found = out["status"] != 1                                            # every clip but RM_CLIP_NO_ROI has a box
+        # bytes the crop kernel read over PCIe: the ROI's rows of the measure frames as aligned 32-bit words
+        span = ((out["x"] & 3) + out["w"] + 3) // 4 * 4 if a["W"] % 4 == 0 else out["w"]
+        fits = (out["w"] <= cap_w) & (out["h"] <= cap_h)
+        self.h2d_bytes += int((span * out["h"] * a["n_meas"])[found & fits].sum())
+        over = found & ~fits
+        if over.any():
+            # an ROI larger than the crop tensors: remember the size for the batches to come and redo the chunks concerned
+            # through the staged path, which sizes its crops after reading the ROIs
+            self.roi_cap = (max(self.roi_cap[0], (int(out["w"][found].max()) + 15) // 16 * 16),
+                            max(self.roi_cap[1], (int(out["h"][found].max()) + 15) // 16 * 16))
+            host = a["host"]
+            mapped, self.mapped = self.mapped, False
+            try:
+                for lo, hi in ticket["chunks"]:
+                    if over[lo:hi].any():
+                        self.reruns += 1
+                        out[lo:hi] = self.collect(self.submit(host[lo:hi], a["fps"], a["cal_first"], a["cal_len"]))
+            finally:
+                self.mapped = mapped
         ticket["keep"] = None
         return out
 

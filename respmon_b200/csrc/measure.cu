@@ -1663,6 +1663,37 @@ __global__ void crop_to_ring_kernel(const uint8_t* __restrict__ frames, const in
 // roi (n_clips, 4) -> out (n_clips, n_frames, out_h, out_w) holding frame[y:y+h, x:x+w] (base.py:471) top-left aligned.
 // For BGR frames cv2.cvtColor's fixed point (next_frame, base.py:230) is applied to the ROI's pixels only -- the measure
 // stage never needs the rest of the frame in gray.
+// Gray rows are read one row per warp as aligned 32-bit words (one request of up to 128 contiguous bytes per row): the
+// frames may lie in pinned HOST memory mapped into the device's address space -- then the crop is the upload, and only the
+// ROI's rows cross PCIe -- where byte-sized requests would cost a bus transaction each.  `end` = one past the clip's last
+// byte: a row's last word is assembled from bytes if it would reach past it.
+__device__ __forceinline__ void crop_rows_gray(const uint8_t* __restrict__ src, long long row_stride, const uint8_t* end,
+                                               uint8_t* __restrict__ dst, int w, int hh, int out_w) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < hh; r += nwarps) {
+    const uint8_t* row = src + (long long)r * row_stride;
+    const int mis = (int)((uintptr_t)row & 3);
+    const uint8_t* w0 = row - mis;
+    uint8_t* drow = dst + r * out_w;
+    const int nwords = (mis + w + 3) >> 2;
+    for (int k = lane; k < nwords; k += 32) {
+      const uint8_t* wp = w0 + 4 * k;
+      unsigned v;
+      if (wp + 4 <= end) v = *reinterpret_cast<const unsigned*>(wp);
+      else {
+        v = 0;
+        for (int b = 0; b < 4; ++b)
+          if (wp + b < end) v |= (unsigned)wp[b] << (8 * b);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int c = 4 * k - mis + b;
+        if (c >= 0 && c < w) drow[c] = (uint8_t)(v >> (8 * b));
+      }
+    }
+  }
+}
+
 template <bool BGR>
 __global__ void crop_frames_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ roi,
                                    uint8_t* __restrict__ out, int T, int first, int n_frames, int W, int H, int out_w,
@@ -1673,10 +1704,14 @@ __global__ void crop_frames_kernel(const uint8_t* __restrict__ frames, const int
   const int PX = BGR ? 3 : 1;
   const uint8_t* src = frames + (((long long)clip * T + first + j) * W * H + (long long)y * W + x) * PX;
   uint8_t* dst = out + ((long long)clip * n_frames + j) * out_w * out_h;
+  if (!BGR) {
+    crop_rows_gray(src, W, frames + (long long)(clip + 1) * T * W * H, dst, w, hh, out_w);
+    return;
+  }
   for (int i = threadIdx.x; i < w * hh; i += blockDim.x) {
     const int r = i / w, c = i - r * w;
     const uint8_t* px = src + ((long long)r * W + c) * PX;
-    dst[r * out_w + c] = BGR ? (uint8_t)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + (1u << 14)) >> 15) : px[0];
+    dst[r * out_w + c] = (uint8_t)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + (1u << 14)) >> 15);
   }
 }
 extern "C" int32_t rm_crop_frames(rm_handle* h, const void* frames, int32_t dtype, int32_t n_clips, int32_t T, int32_t W,
@@ -1713,10 +1748,14 @@ __global__ void crop_frames_ragged_kernel(const uint8_t* __restrict__ base, cons
   const int PX = BGR ? 3 : 1;
   const uint8_t* src = base + d.frame_offset + ((long long)(first + j) * d.H + y) * d.row_stride + (long long)x * PX;
   uint8_t* dst = out + ((long long)clip * n_frames + j) * out_w * out_h;
+  if (!BGR) {
+    crop_rows_gray(src, d.row_stride, base + d.frame_offset + (long long)d.T * d.H * d.row_stride, dst, w, hh, out_w);
+    return;
+  }
   for (int i = threadIdx.x; i < w * hh; i += blockDim.x) {
     const int r = i / w, c = i - r * w;
     const uint8_t* px = src + (long long)r * d.row_stride + c * PX;
-    dst[r * out_w + c] = BGR ? (uint8_t)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + (1u << 14)) >> 15) : px[0];
+    dst[r * out_w + c] = (uint8_t)((3735u * px[0] + 19235u * px[1] + 9798u * px[2] + (1u << 14)) >> 15);
   }
 }
 extern "C" int32_t rm_crop_frames_ragged(rm_handle* h, const void* base, int32_t dtype, const rm_clip_desc* descs,

@@ -310,8 +310,9 @@ class Engine:
                     out_size: tuple[int, int] | None = None) -> torch.Tensor:
         """`frame[y:y+h, x:x+w]` (base.py:471) of frames [first, first+n_frames) of every clip -> (n, n_frames, out_h, out_w)
         uint8, top-left aligned.  clips (n,T,H,W) gray or (n,T,H,W,3) BGR (converted like next_frame, base.py:230, on the
-        ROI's pixels only); roi (n,4) x,y,w,h.  out_size (w, h) defaults to the largest ROI (one small D2H read)."""
-        assert clips.is_cuda and clips.is_contiguous() and clips.dtype == torch.uint8
+        ROI's pixels only), on the device or in pinned host memory (then only the ROI's rows cross PCIe); roi (n,4) x,y,w,h.
+        out_size (w, h) defaults to the largest ROI (one small D2H read)."""
+        assert (clips.is_cuda or clips.is_pinned()) and clips.is_contiguous() and clips.dtype == torch.uint8
         bgr = clips.dim() == 5 and clips.shape[-1] == 3
         assert clips.dim() == 4 or bgr
         n, T, H, W = clips.shape[:4]

@@ -97,3 +97,24 @@ def test_submit_collect_overlapped_batches_equal_sequential_runs():
     for g, w in zip(got, want):
         _same(g, w)
 
+
+
+def test_mapped_path_grows_its_roi_cap_and_reruns_what_overflowed():
+    """Clips in pinned host memory: the crop kernel reads the ROI rows of the measure frames straight from the host buffer
+    into crop tensors sized by roi_cap.  With a cap smaller than the ROIs the batch is noticed in collect(), its chunks are
+    redone through the staged path and the cap grows: same records, and the next batch needs no second pass.  A list of
+    separately pinned clips takes the descriptor form of the crop kernel."""
+    from respmon_b200.batch import BatchMonitor
+    clips = _clips(range(70, 75), 320, 240)
+    want = BatchMonitor(0, chunk_clips=2, mapped=False).run(clips, 10.0)
+    host = torch.from_numpy(clips).pin_memory()
+    mon = BatchMonitor(0, chunk_clips=2, roi_cap=(8, 8))
+    got = mon.run(host, 10.0)
+    _same(got, want)
+    assert mon.reruns == 3 and mon.roi_cap[0] >= want["w"].max() and mon.roi_cap[1] >= want["h"].max()
+    got = mon.run(host, 10.0)
+    _same(got, want)
+    assert mon.reruns == 3
+    parts = [torch.from_numpy(c).pin_memory() for c in clips]
+    _same(mon.run(parts, 10.0), want)
+    assert mon.reruns == 3
