@@ -282,7 +282,7 @@ int32_t rm_pack_results_stream(rm_handle* h, const double* bpm, const int32_t* r
  *   "pyramid_mode" (0/1)         1 (default): uint8 frames whose rows are 16-byte multiples take the one-pass fused pyramid
  *                                kernel (TMA rows, levels 0..4 as integers, the rest in shared memory); 0: always level 3
  *                                through HBM + the tail kernel.  Bit-identical records.
- *   "pyramid_cfg" (0..3)         fused kernel: (ring stages, warps per CTA) = by frame width (0, default) / (4, 18) / (3, 21) /
+ *   "pyramid_cfg" (0..3)         fused kernel: (ring stages, warps per CTA) = by frame width (0, default) / (4, 18) / (2, 18) /
  *                                (2, 24).
  *   "pyramid_g4" (0..2)          fused kernel: the level-4 image of a frame lives in shared memory (1), in the frame's
  *                                record, where its Laplacian replaces it (2), or wherever more frame slots fit an SM (0,

@@ -780,7 +780,7 @@ static bool pf_plan(rm_handle* h, int W, int H, PfPlan& pl) {
   }
   p.n_strips = n;
   // ring depth / warps per CTA: as many frame slots as shared memory, the register file and 15 named barriers allow
-  const int cfg[3][2] = {{4, 18}, {3, 21}, {2, 24}};            // (stages, max warps)
+  const int cfg[3][2] = {{4, 18}, {2, 18}, {2, 24}};            // (stages, max warps)
   auto slots = [&](int S, int maxw, bool g4_global) {
     int want = maxw / n;
     if (want > 15) want = 15;
@@ -792,8 +792,9 @@ static bool pf_plan(rm_handle* h, int W, int H, PfPlan& pl) {
   // x 24 warps (0.586 against 0.676 ms per 8192 VGA frames with 4 x 18); wider frames want the deep ring and 96 registers
   // as long as two frames fit an SM with their level-4 images in shared memory (720p: 0.479 against 0.523 ms per 2048
   // frames); where only one would (1080p: a 65 KB level-4 image), level 4 goes to the record instead and the shallow ring
-  // leaves the L1 cache it is then read through (0.639 against 0.723 ms per 1024 frames).
-  int pick = h->pyramid_cfg >= 1 && h->pyramid_cfg <= 3 ? h->pyramid_cfg - 1 : (n <= 3 || slots(4, 18, false) < 2 ? 2 : 0);
+  // leaves the L1 cache it is then read through: 2 stages x 18 warps at 96 registers (0.593 ms per 1024 frames against
+  // 0.631 with 2 x 24 at 80 registers and 0.695 with 4 x 18).
+  int pick = h->pyramid_cfg >= 1 && h->pyramid_cfg <= 3 ? h->pyramid_cfg - 1 : (n <= 3 ? 2 : (slots(4, 18, false) < 2 ? 1 : 0));
   for (int tries = 0; tries < 3; ++tries, pick = (pick + 1) % 3) {
     const int S = cfg[pick][0], maxw = cfg[pick][1];
     const int in_smem = slots(S, maxw, false), in_rec = slots(S, maxw, true);
@@ -871,7 +872,7 @@ int32_t pu_launch_fused(rm_handle* h, const uint8_t* frames, double* lap_out, lo
   long long ctas = (n_frames + p.frames_per_cta - 1) / p.frames_per_cta;
   if (ctas > h->sm_count) ctas = h->sm_count;
   if (pl.stages == 4) return pf_launch_cfg<4, 18>(h, pl, map, ctas, st);
-  if (pl.stages == 3) return pf_launch_cfg<3, 21>(h, pl, map, ctas, st);
+  if (pl.maxw == 18) return pf_launch_cfg<2, 18>(h, pl, map, ctas, st);
   return pf_launch_cfg<2, 24>(h, pl, map, ctas, st);
 }
 

@@ -1,7 +1,7 @@
 """Developer tool: the uint8 pyramid stage (frames in -> packed Laplacian records out) per mode at the bench shape.
     python tools/bench_pyramid.py [W H n_clips]
 "split" = level 3 through HBM + pyramid_tail_kernel (the fallback), "fused c" = the one-pass TMA kernel in ring /
-occupancy configuration c (0: chosen by frame width, 1: 4 stages x 18 warps, 2: 3 x 21, 3: 2 x 24).
+occupancy configuration c (0: chosen by frame width, 1: 4 stages x 18 warps, 2: 2 x 18, 3: 2 x 24).
 Prints the stage time from CUDA events, the SURVEY 8(d) algorithmic bytes (W*H*1 + record*8 per frame) over it, and
 whether the records equal mode 0's bit for bit."""
 import json, os, sys
