@@ -400,7 +400,7 @@ struct PfLane {
   int k;                        // level-4 column the lane emits, -1: none
   // level 0 (8 pixels per lane, w0 = pixels 0..3, w1 = 4..7, wl / wr = the neighbours' w1 / w0):
   //   k0 = dp4a(wl, l0_wl) + dp4a(w0, l0_w0)        interior: (.,.,1,4) (6,4,1,.)     first lane: 0, (6,8,2,.)
-  //   k3 = dp4a(w1, l0_w1) + dp4a(wr, l0_wr)        interior: (1,4,6,4) (1,.,.,.)     last lane: (1,4,7,4), 0
+  //   k3 = dp4a(w1, l0_w1) + (wr & l0_wr)           interior: (1,4,6,4), byte mask    last lane: (1,4,7,4), 0
   unsigned l0_wl, l0_w0, l0_w1, l0_wr;
   // level 1 (P = columns (0,1), Q = (2,3) as 16-bit pairs, Ql / Pr the neighbours' Q / P), byte pairs for dp2a lo | hi:
   //   g0 = dp2a_lo(Ql, h1_a) + dp2a_hi(P, h1_a) + dp2a_lo(Q, h1_b)
@@ -416,7 +416,7 @@ __device__ __forceinline__ void pf_lane_setup(PfLane& ln, int lane, int col, int
   ln.k = (!(col & 1) && (col >> 1) >= k0 && (col >> 1) < k1) ? (col >> 1) : -1;
   const bool first = lane == first_lane, last = lane == last_lane;
   ln.l0_wl = first ? 0u : 0x04010000u;  ln.l0_w0 = first ? 0x00020806u : 0x00010406u;
-  ln.l0_w1 = last ? 0x04070401u : 0x04060401u;  ln.l0_wr = last ? 0u : 0x00000001u;
+  ln.l0_w1 = last ? 0x04070401u : 0x04060401u;  ln.l0_wr = last ? 0u : 0xffu;
   ln.h1_a = first ? 0x08060000u : 0x04060401u;
   ln.h1_b = (last ? 0x04070000u : 0x04060000u) | (first ? 0x0002u : 0x0001u);
   ln.h1_c = last ? 0x04010000u : 0x04010001u;
@@ -426,7 +426,7 @@ __device__ __forceinline__ void pf_lane_setup(PfLane& ln, int lane, int col, int
 }
 
 // pu_block for the fused kernel: the same sums, image borders by the lane's weights (EDGE) or none at all
-template <bool EDGE>
+template <bool EDGE, bool MASK_TAP>
 __device__ __forceinline__ void pf_block(PuState& s, const uint2 w[PU_ROWS], const PfLane& ln, unsigned& out3) {
   unsigned ha[PU_ROWS], hb[PU_ROWS];
 #pragma unroll
@@ -434,10 +434,19 @@ __device__ __forceinline__ void pf_block(PuState& s, const uint2 w[PU_ROWS], con
     const unsigned w0 = w[i].x, w1 = w[i].y;
     const unsigned wl = __shfl_up_sync(0xffffffffu, w1, 1);
     const unsigned wr = __shfl_down_sync(0xffffffffu, w0, 1);
+    // MASK_TAP: a single tap of weight 1 is a byte mask (ALU pipe) feeding the accumulator, not a dot product of its own
+    // -- the integer-multiply pipe is the busier one: VGA 0.580 -> 0.559 ms, 1080p 0.590 -> 0.579 (two-stage rings); the
+    // four-stage configuration at 96 registers (720p) is 2 % faster with the dot product (r03r)
     const unsigned k0 = __dp4a(wl, EDGE ? ln.l0_wl : 0x04010000u, __dp4a(w0, EDGE ? ln.l0_w0 : 0x00010406u, 0u));
-    const unsigned k1 = __dp4a(w0, 0x04060401u, __dp4a(w1, 0x00000001u, 0u));
     const unsigned k2 = __dp4a(w0, 0x04010000u, __dp4a(w1, 0x00010406u, 0u));
-    const unsigned k3 = __dp4a(w1, EDGE ? ln.l0_w1 : 0x04060401u, __dp4a(wr, EDGE ? ln.l0_wr : 0x00000001u, 0u));
+    unsigned k1, k3;
+    if (MASK_TAP) {
+      k1 = __dp4a(w0, 0x04060401u, w1 & 0xffu);
+      k3 = __dp4a(w1, EDGE ? ln.l0_w1 : 0x04060401u, wr & (EDGE ? ln.l0_wr : 0xffu));
+    } else {
+      k1 = __dp4a(w0, 0x04060401u, __dp4a(w1, 0x00000001u, 0u));
+      k3 = __dp4a(w1, EDGE ? ln.l0_w1 : 0x04060401u, __dp4a(wr, EDGE ? (ln.l0_wr & 1u) : 1u, 0u));
+    }
     ha[i] = k0 + (k1 << 16);       // (a byte permute instead of the shift-add, i.e. ALU instead of FMA pipe: +-1 %, r03c)
     hb[i] = k2 + (k3 << 16);
   }
@@ -603,7 +612,7 @@ __device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMa
     rg.soff += PU_STAGE_BYTES;
     if (rg.soff == S * PU_STAGE_BYTES) { rg.soff = 0; rg.par ^= 1u; }
     unsigned o;
-    pf_block<true>(s, w, ln, o);
+    pf_block<true, S == 2>(s, w, ln, o);
     if (b >= 1) pf_l4_row_any(l4, pf_l3_hfilter(o, ln), b - 1, g4k, W4, g_scale);
   };
   // hot pairs start at an even block (row b-1 odd, then row b even); the last one fetches block nblk-2 at most, so that
@@ -635,7 +644,7 @@ __device__ __forceinline__ void pf_run_frame(const PfParams& p, const CUtensorMa
           if (rg.soff == S * PU_STAGE_BYTES) { rg.soff = 0; rg.par ^= 1u; }
         }
         unsigned o;
-        pf_block<true>(s, w, ln, o);
+        pf_block<true, S == 2>(s, w, ln, o);
         const double h = pf_l3_hfilter(o, ln);
         if (j == 0) pf_l4_row<true>(l4, h, b - 1, g4k, W4, g_scale);
         else pf_l4_row<false>(l4, h, b, g4k, W4, g_scale);
@@ -789,12 +798,12 @@ static bool pf_plan(rm_handle* h, int W, int H, PfPlan& pl) {
     return want < fit ? want : fit;
   };
   // measured (profiles/r03_pyramid_configs.txt): frames of up to three strips (VGA: 3 x 8 slots) want the most warps, 2 stages
-  // x 24 warps (0.586 against 0.676 ms per 8192 VGA frames with 4 x 18); wider frames want the deep ring and 96 registers
-  // as long as two frames fit an SM with their level-4 images in shared memory (720p: 0.479 against 0.523 ms per 2048
-  // frames); where only one would (1080p: a 65 KB level-4 image), level 4 goes to the record instead and the shallow ring
-  // leaves the L1 cache it is then read through: 2 stages x 18 warps at 96 registers (0.593 ms per 1024 frames against
-  // 0.631 with 2 x 24 at 80 registers and 0.695 with 4 x 18).
-  int pick = h->pyramid_cfg >= 1 && h->pyramid_cfg <= 3 ? h->pyramid_cfg - 1 : (n <= 3 ? 2 : (slots(4, 18, false) < 2 ? 1 : 0));
+  // x 24 warps at 80 registers (0.558 against 0.625 ms per 8192 VGA frames with 2 x 18 at 96 and 0.676 with 4 x 18); wider
+  // frames, whose level images leave room for two or three slots, want the 96 registers, and the shallow ring leaves them
+  // the shared memory for a third slot (720p: 0.465 against 0.485 ms per 2048 frames with 4 x 18) or, with level 4 in the
+  // record, for a second one and the L1 cache the record is then read through (1080p: 0.589 against 0.609 with 2 x 24 and
+  // 0.714 with 4 x 18 per 1024 frames).
+  int pick = h->pyramid_cfg >= 1 && h->pyramid_cfg <= 3 ? h->pyramid_cfg - 1 : (n <= 3 ? 2 : 1);
   for (int tries = 0; tries < 3; ++tries, pick = (pick + 1) % 3) {
     const int S = cfg[pick][0], maxw = cfg[pick][1];
     const int in_smem = slots(S, maxw, false), in_rec = slots(S, maxw, true);
