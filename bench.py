@@ -376,18 +376,21 @@ def run_gpu_arm(args) -> dict | None:
         return nbytes
 
     h2d_only()
-    barrier()
-    t0 = time.perf_counter()
-    copied = 0
-    for _ in range(e2e_steps):
-        copied += h2d_only()
-    copy_stream.synchronize()
-    barrier()
-    h2d_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([h2d_s], dtype=torch.float64, device=eng.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        h2d_s = float(t.item())
+    h2d_s = None
+    for _ in range(2):                        # a ceiling is the best the box has shown: the faster of two passes
+        barrier()
+        t0 = time.perf_counter()
+        copied = 0
+        for _ in range(e2e_steps):
+            copied += h2d_only()
+        copy_stream.synchronize()
+        barrier()
+        dt_ = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_], dtype=torch.float64, device=eng.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_ = float(t.item())
+        h2d_s = dt_ if h2d_s is None else min(h2d_s, dt_)
     h2d_gbs_per_gpu = copied / h2d_s / 1e9
     h2d_ceiling = frames_per_step * e2e_steps / h2d_s         # frames/s if only the calibration windows crossed PCIe
     del cal_dst
