@@ -613,33 +613,55 @@ def run_config_arm(args) -> dict | None:
     local_rec = torch.zeros((cap, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     gathered = torch.empty((world * cap, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
 
-    ragged_engine = per_class[0]["eng"] if len(per_class) > 1 else None
+    # Consecutive chunks alternate over --streams streams, each with its own handle: chunk k+1 calibrates while chunk k
+    # tracks and fits (the measure stage is a latency chain that leaves most SMs idle; bench.py's `overlapped_steps`).
+    n_str = max(1, args.streams)
+    ragged = len(per_class) > 1 and not args.per_class_measure
+    if ragged:
+        lanes = [dict(eng=per_class[0]["eng"] if j == 0 else Engine(local_rank), stream=torch.cuda.Stream(dev))
+                 for j in range(n_str)]
+    else:
+        for c in per_class:
+            c["lanes"] = [dict(eng=c["eng"] if j == 0 else Engine(local_rank), stream=c["stream"] if j == 0 else torch.cuda.Stream(dev))
+                          for j in range(n_str)]
+    all_engines = [l_["eng"] for l_ in lanes] if ragged else [l_["eng"] for c in per_class for l_ in c["lanes"]]
     mixed_rec = {}
 
     def step():
         cur = torch.cuda.current_stream(dev)
-        if ragged_engine is not None and not args.per_class_measure:
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        if ragged:
             # mixed resolutions: calibration per class, ONE ragged crop launch (rm_clip_desc) and ONE measure stage over all
             # classes -- chunk by chunk (a chunk holds its share of every class)
             pos = 0
             n_chunks = max(len(c["chunks"]) for c in per_class)
+            for l_ in lanes:
+                l_["stream"].wait_event(fork)
             for k in range(n_chunks):
                 group = [c["chunks"][k] for c in per_class if k < len(c["chunks"])]
-                rec = ragged_engine.run_mixed(group, FPS)
-                mixed_rec[k] = rec
-                local_rec[pos:pos + rec.shape[0]].copy_(rec, non_blocking=True)
+                l_ = lanes[k % n_str]
+                with torch.cuda.stream(l_["stream"]):
+                    rec = l_["eng"].run_mixed(group, FPS)
+                    mixed_rec[k] = rec
+                    local_rec[pos:pos + rec.shape[0]].copy_(rec, non_blocking=True)
                 pos += rec.shape[0]
+            for l_ in lanes:
+                cur.wait_stream(l_["stream"])
         else:
-            fork = torch.cuda.Event()
-            fork.record(cur)
             pos = 0
             for c in per_class:
-                c["stream"].wait_event(fork)
+                for l_ in c["lanes"]:
+                    l_["stream"].wait_event(fork)
+                lo = 0
+                for k, ch in enumerate(c["chunks"]):
+                    l_ = c["lanes"][k % n_str]
+                    with torch.cuda.stream(l_["stream"]):
+                        l_["eng"].run_batch(ch, FPS, out=c["rec"][lo:lo + ch.shape[0]])
+                    lo += ch.shape[0]
+                for l_ in c["lanes"][1:]:
+                    c["stream"].wait_stream(l_["stream"])
                 with torch.cuda.stream(c["stream"]):
-                    lo = 0
-                    for ch in c["chunks"]:
-                        c["eng"].run_batch(ch, FPS, out=c["rec"][lo:lo + ch.shape[0]])
-                        lo += ch.shape[0]
                     local_rec[pos:pos + len(c["idx"])].copy_(c["rec"], non_blocking=True)
                 pos += len(c["idx"])
                 done = torch.cuda.Event()
@@ -659,7 +681,7 @@ def run_config_arm(args) -> dict | None:
         step()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    launches0 = sum(c["eng"].launch_count for c in per_class)
+    launches0 = sum(e_.launch_count for e_ in all_engines)
     for c in per_class:
         c["eng"].profile(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -670,7 +692,7 @@ def run_config_arm(args) -> dict | None:
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
-    launches = sum(c["eng"].launch_count for c in per_class) - launches0
+    launches = sum(e_.launch_count for e_ in all_engines) - launches0
     prof = {}
     for c in per_class:
         for k_, v_ in c["eng"].profile_report().items():
@@ -728,6 +750,7 @@ def run_config_arm(args) -> dict | None:
         "config": {"workload": cfg["name"], "total_clips": total, "clips_per_gpu": [len(o) for o in owners],
                    "frames_per_step": frames_per_step, "pixels_per_step": pixels_per_step,
                    "pixel_rate_Gpx_per_s": pixels_per_step / (ms_per_step / 1e3) / 1e9, "chunk_clips": args.chunk,
+                   "streams": n_str,
                    "input_dtype": "u8", "l2": "clips resident in HBM, %.1f GB per GPU > 126 MB L2 (no flush needed)"
                                                % (sum(ch.numel() for c in per_class for ch in c["chunks"]) / 1e9),
                    "parallelism": ("clips balanced over %d GPU(s) by pixels; " % world) + (
@@ -755,6 +778,7 @@ def main():
     ap.add_argument("--per-class-measure", action="store_true",
                     help="--config 5: one measure stage per resolution class on its own stream instead of one over all classes")
     ap.add_argument("--chunk", type=int, default=32, help="clips per H2D chunk of the end-to-end leg")
+    ap.add_argument("--streams", type=int, default=2, help="--config: streams (with a handle each) the chunks alternate over")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-width-sweep", action="store_true")
