@@ -401,38 +401,29 @@ def run_gpu_arm(args) -> dict | None:
     # exclusive steps (round-over-round comparison; the roofline kernel is timed with the GPU to itself).
     overlapped = None
     if world == 1 and not args.no_width_sweep:
-        from respmon_b200.engine import Engine
+        from respmon_b200.engine import EngineRing
         overlapped = []
         for n_streams in (2, 3):
-            engs = [eng] + [Engine(local_rank) for _ in range(n_streams - 1)]
-            streams = [torch.cuda.Stream(eng.device) for _ in range(n_streams)]
+            ring = EngineRing(local_rank, n_streams)
             recs_o = [torch.empty((n_clips, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=eng.device)
                       for _ in range(n_streams)]
-
-            def run_overlapped(n):
-                for k in range(n):
-                    with torch.cuda.stream(streams[k % n_streams]):
-                        engs[k % n_streams].run_batch(clips, FPS, out=recs_o[k % n_streams])
-
-            run_overlapped(2 * n_streams)
+            for k in range(2 * n_streams):
+                ring.run_batch(clips, FPS, out=recs_o[k % n_streams])
+            ring.join()
             torch.cuda.synchronize()
-            cur = torch.cuda.current_stream(eng.device)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for s_ in streams:
-                s_.wait_stream(cur)
             n_o = max(args.steps, 4 * n_streams)
-            run_overlapped(n_o)
-            for s_ in streams:
-                cur.wait_stream(s_)
+            a.record()
+            for k in range(n_o):
+                ring.run_batch(clips, FPS, out=recs_o[k % n_streams])
+            ring.join()
             b.record()
             torch.cuda.synchronize()
             ms_o = a.elapsed_time(b) / n_o
             same_o = all(bool(np.array_equal(r_.cpu().numpy(), rec.cpu().numpy())) for r_ in recs_o)    # byte for byte
             overlapped.append({"streams": n_streams, "steps": n_o, "ms_per_step": ms_o, "frames_per_s": n_clips * T / ms_o * 1e3,
-                               "same_records_as_exclusive_steps": same_o})
-            for e_ in engs[1:]:
-                e_.close()
+                               "same_records_as_exclusive_steps": same_o, "api": "respmon_b200.engine.EngineRing"})
+            ring.close()
 
     # ---- batch width (N = 1): BASELINE config 3 asks for 512 clips per step; the measure stage is latency bound, so wider
     # steps cost less than proportionally.  The 64-clip figure above stays the headline (round-over-round comparison).

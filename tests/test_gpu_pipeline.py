@@ -156,3 +156,24 @@ def test_measure_pipeline_with_a_roi_too_large_for_shared_memory(eng):
     else:
         assert abs(got - bpm) <= 0.5
         assert int(out["npeaks"][0]) == len(peaks)
+
+
+def test_engine_ring_overlapped_batches_equal_sequential_batches():
+    """EngineRing: consecutive batches alternate over two handles on two streams (one calibrates while the other tracks and
+    fits); every batch's records equal those of a plain Engine.run_batch, whatever the batch sizes in flight."""
+    from respmon_b200 import synth
+    from respmon_b200.engine import Engine, EngineRing
+    eng = Engine(0)
+    batches = []
+    for b, n in enumerate((3, 5, 2, 4, 3)):
+        specs = [synth.clip_spec(100 * b + i, 320, 240, 256) for i in range(n)]
+        batches.append(eng.synth_clips(specs, np.stack([synth.displacement_q8(s) for s in specs])))
+    want = [eng.run_batch(c, 10.0).cpu().numpy() for c in batches]
+    ring = EngineRing(0, 2)
+    got = [ring.run_batch(c, 10.0) for c in batches]
+    ring.join()
+    for g, w in zip(got, want):
+        assert np.array_equal(g.cpu().numpy(), w)
+    assert ring.launch_count > 0
+    ring.close()
+    eng.close()
