@@ -128,6 +128,21 @@ class BatchMonitor:
             self._seq = 0                                                  # chunks submitted so far (slot rotation)
         return self._ev
 
+    def _upload_cal(self, host, chunk, slot, cal_first, cal_len, H, W):
+        """Calibration windows of the clips [lo, hi) -> device buffer `slot` (of two), on the copy stream."""
+        lo, hi = chunk
+        E, used, copy = self._slot_events(), self._used, self._copy_stream
+        dst = self._buffer(("cal", slot), (hi - lo, cal_len, H, W))
+        with torch.cuda.stream(copy):
+            if used["cal"][slot]:
+                copy.wait_event(E["cal_freed"][slot])             # locate() of the chunk that last used this buffer is done
+            for c in range(lo, hi):                               # one contiguous block per clip
+                dst[c - lo].copy_(host[c][cal_first:cal_first + cal_len], non_blocking=True)
+            E["cal_ready"][slot].record(copy)
+        used["cal"][slot] = True
+        self.h2d_bytes += dst.numel()
+        return dst
+
     def submit(self, clips, fps: float, cal_first: int = 1, cal_len: int = 128):
         """Enqueue a batch and return a ticket for collect().  Returns as soon as the last chunk's measure stage has been
         enqueued, so the upload of the next submit() overlaps the tail of this one (buffers and streams are handed from
@@ -172,18 +187,7 @@ class BatchMonitor:
         seq0 = self._seq
 
         def upload_cal(i):
-            lo, hi = chunks[i]
-            slot = (seq0 + i) & 1
-            dst = self._buffer(("cal", slot), (hi - lo, cal_len, H, W))
-            with torch.cuda.stream(copy):
-                if used["cal"][slot]:
-                    copy.wait_event(E["cal_freed"][slot])         # locate() of the chunk that last used this buffer is done
-                for c in range(lo, hi):                           # one contiguous block per clip
-                    dst[c - lo].copy_(host[c][cal_first:cal_first + cal_len], non_blocking=True)
-                E["cal_ready"][slot].record(copy)
-            used["cal"][slot] = True
-            self.h2d_bytes += dst.numel()
-            return dst
+            return self._upload_cal(host, chunks[i], (seq0 + i) & 1, cal_first, cal_len, H, W)
 
         pending = upload_cal(0) if chunks else None
         for i, (lo, hi) in enumerate(chunks):
@@ -272,7 +276,6 @@ class BatchMonitor:
         eng = self.engine
         dev = eng.device
         main = torch.cuda.current_stream(dev)
-        copy = self._copy_stream
         n_ms = len(self._measure_streams)
         measure_first = cal_first + cal_len + 1
         n_meas = T - measure_first
@@ -286,18 +289,7 @@ class BatchMonitor:
         as_list = isinstance(host, list)
 
         def upload_cal(i):
-            lo, hi = chunks[i]
-            slot = (seq0 + i) & 1
-            dst = self._buffer(("cal", slot), (hi - lo, cal_len, H, W))
-            with torch.cuda.stream(copy):
-                if used["cal"][slot]:
-                    copy.wait_event(E["cal_freed"][slot])         # locate() of the chunk that last used this buffer is done
-                for c in range(lo, hi):                           # one contiguous block per clip
-                    dst[c - lo].copy_(host[c][cal_first:cal_first + cal_len], non_blocking=True)
-                E["cal_ready"][slot].record(copy)
-            used["cal"][slot] = True
-            self.h2d_bytes += dst.numel()
-            return dst
+            return self._upload_cal(host, chunks[i], (seq0 + i) & 1, cal_first, cal_len, H, W)
 
         pending = upload_cal(0) if chunks else None
         for i, (lo, hi) in enumerate(chunks):
