@@ -281,7 +281,6 @@ class BatchMonitor:
         n_meas = T - measure_first
         chunks = self._chunk_schedule(n)
         E = self._slot_events()
-        used = self._used
         records = torch.empty((n, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
         keep = [host]
         seq0 = self._seq
