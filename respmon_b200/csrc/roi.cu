@@ -55,8 +55,20 @@ __global__ void roi_init_kernel(const RoiParams p) {
   const long long hw = (long long)p.W * p.H;
   const uint8_t* heat = p.heat + blockIdx.y * hw;
   int32_t* L = p.labels + blockIdx.y * hw;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x)
-    L[i] = heat[i] > p.threshold ? (int)i : -1;
+  if ((hw & 3) == 0 && (((uintptr_t)p.heat | (uintptr_t)p.labels) & 15) == 0) {
+    // four pixels per thread: one 4-byte load, one 16-byte store
+    const uchar4* h4 = reinterpret_cast<const uchar4*>(heat);
+    int4* L4 = reinterpret_cast<int4*>(L);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < hw / 4; q += (long long)gridDim.x * blockDim.x) {
+      const uchar4 v = h4[q];
+      const int i = (int)(4 * q);
+      L4[q] = make_int4(v.x > p.threshold ? i : -1, v.y > p.threshold ? i + 1 : -1, v.z > p.threshold ? i + 2 : -1,
+                        v.w > p.threshold ? i + 3 : -1);
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x)
+      L[i] = heat[i] > p.threshold ? (int)i : -1;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) { p.best[blockIdx.y] = 0ull; p.list_n[blockIdx.y] = 0; }
 }
 
