@@ -64,9 +64,11 @@ __global__ void __launch_bounds__(256) up_level_kernel(const double* __restrict_
                                                        long long n_img, int sw, int sh, int dw, int dh) {
   const long long per_img = (long long)sw * sh;
   const long long total = n_img * per_img;
+  const bool small = total < (1ll << 31);      // 32-bit index arithmetic (a 64-bit division costs about a hundred instructions)
+#pragma unroll 1
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const long long img = idx / per_img;
+    const long long img = small ? (long long)((unsigned)idx / (unsigned)per_img) : idx / per_img;
     const int r = (int)(idx - img * per_img);
     const int y = r / sw, x = r - y * sw;
     const double* s = src + img * per_img;
@@ -562,6 +564,9 @@ __global__ void __launch_bounds__(256) heat_normalise_kernel(const double* __res
   if (VEC) {
     const double2* a2 = reinterpret_cast<const double2*>(a);
     uchar4* o4 = reinterpret_cast<uchar4*>(o);
+    // (not unrolled: a thread has one trip, and the trip count an unrolled grid-stride loop needs is a 64-bit division
+    // -- 370 of the 500 instructions a thread executed, ncu r04b)
+#pragma unroll 1
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < hw / 4; q += stride) {
       const double2 lo = a2[2 * q], hi = a2[2 * q + 1];
       o4[q] = make_uchar4(heat_u8(lo.x, mn, range), heat_u8(lo.y, mn, range), heat_u8(hi.x, mn, range),
