@@ -495,7 +495,8 @@ def run_gpu_arm(args) -> dict | None:
         "config": {"workload": WORKLOAD, "clips_per_gpu": n_clips, "frames_per_step": frames_per_step,
                    "input_dtype": "u8", "l2": "inputs %.1f GB per GPU per step > 126 MB L2 (no flush needed)"
                                                % (clips.numel() / 1e9),
-                   "parallelism": "clips sharded over %d GPU(s), one all-gather of 32 B result records" % world},
+                   "parallelism": "clips sharded over %d GPU(s), one all-gather of 32 B result records" % world,
+                   "steps_in_flight": 1},     # exclusive steps on one stream; `overlapped_steps` has two and three in flight
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mon.h2d_bytes // e2e_steps,
                 "d2h_bytes_per_step": mon.d2h_bytes // e2e_steps, "steps": e2e_steps, "chunk_clips": args.chunk,
                 "same_results_as_resident_run": same, "numa": numa,
