@@ -86,7 +86,16 @@ def _cpu_workers():
     return max(1, min(n, 64))
 
 
-def run_reference_arm(steps: int, warmup: int, n_gpus: int) -> dict:
+def workload_config(n_clips: int, world: int) -> dict:
+    """The `config` of both arms: it names the workload (the reference arm times a bounded sample of it, described in its
+    `cpu_baseline.sample`)."""
+    return {"workload": WORKLOAD, "clips_per_gpu": n_clips, "frames_per_step": world * n_clips * T, "input_dtype": "u8",
+            "l2": "inputs %.1f GB per GPU per step > 126 MB L2 (no flush needed)" % (n_clips * T * H * W / 1e9),
+            "parallelism": "clips sharded over %d GPU(s), one all-gather of 32 B result records" % world,
+            "steps_in_flight": 1}     # exclusive steps on one stream; the GPU arm's `overlapped_steps` has two and three in flight
+
+
+def run_reference_arm(steps: int, warmup: int, n_gpus: int, n_clips: int = 64) -> dict:
     """Each step: one clip per worker process, all host cores busy; value = frames of the sample / slowest worker."""
     import multiprocessing as mp
     workers = _cpu_workers()
@@ -111,8 +120,9 @@ def run_reference_arm(steps: int, warmup: int, n_gpus: int) -> dict:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample, "host_cores": os.cpu_count()},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample},
+        "config": workload_config(n_clips, n_gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample,
+                         "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "median_abs_bpm_error_vs_truth": statistics.median(bpm_err) if bpm_err else None,
@@ -492,11 +502,7 @@ def run_gpu_arm(args) -> dict | None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_gpu": n_clips, "frames_per_step": frames_per_step,
-                   "input_dtype": "u8", "l2": "inputs %.1f GB per GPU per step > 126 MB L2 (no flush needed)"
-                                               % (clips.numel() / 1e9),
-                   "parallelism": "clips sharded over %d GPU(s), one all-gather of 32 B result records" % world,
-                   "steps_in_flight": 1},     # exclusive steps on one stream; `overlapped_steps` has two and three in flight
+        "config": workload_config(n_clips, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": mon.h2d_bytes // e2e_steps,
                 "d2h_bytes_per_step": mon.d2h_bytes // e2e_steps, "steps": e2e_steps, "chunk_clips": args.chunk,
                 "same_results_as_resident_run": same, "numa": numa,
@@ -778,7 +784,7 @@ def main():
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        print(json.dumps(run_reference_arm(max(1, args.steps), max(0, args.warmup), args.gpus)), flush=True)
+        print(json.dumps(run_reference_arm(max(1, args.steps), max(0, args.warmup), args.gpus, args.clips or 64)), flush=True)
         return
     args.clips_given = args.clips is not None
     if args.clips is None:
